@@ -1,0 +1,282 @@
+"""Oracle pinned by invariants — the reference ships no golden vectors for this path,
+MuJoCo/pinocchio are not installable, so these are the checks that stand in for them ("parity unpinned")."""
+import numpy as np
+import pytest
+
+from d3il_b200.scene import mjcf
+from d3il_b200.scene.blob import links_from_scene
+from oracle.oracle import OracleEnv, collide
+
+G_CYL, G_BOX = 5, 6
+
+
+def make(scene):
+    blob, sc = scene
+    return OracleEnv(blob, sc.header), sc
+
+
+def set_q(env, sc, qarm, qvel_arm=None, objs=None):
+    s = env.get_state()
+    nq, nv = sc.header["nq"], sc.header["nv"]
+    s[:7] = qarm
+    s[nq:nq + nv] = 0
+    if qvel_arm is not None:
+        s[nq:nq + 7] = qvel_arm
+    if objs is not None:
+        s[9:nq] = np.asarray(objs).reshape(-1)
+    env.set_state(s)
+
+
+def test_fk_known_answers(pushing_scene):
+    """B.9(1): URDF-chain FK KATs from SURVEY §8c."""
+    env, sc = make(pushing_scene)
+    q0 = np.array([0, 0.1745, 0, -0.8727, 0, 1.2217, 0.7854])
+    p, quat, J = env.ik_fk(q0)
+    assert np.allclose(p, [0.550900, 0, 0.699822], atol=2e-5)
+    assert np.allclose(np.abs(quat), [0, 0.996195, 0, 0.087156], atol=2e-5)
+    p, _, _ = env.ik_fk(np.zeros(7))
+    assert np.allclose(p, [0.088, 0, 0.821], atol=1e-9)
+    # Jacobian = finite difference of FK
+    rng = np.random.default_rng(0)
+    q = rng.uniform(-1, 1, 7)
+    p0, _, J = env.ik_fk(q)
+    for i in range(7):
+        dq = np.zeros(7); dq[i] = 1e-6
+        p1, _, _ = env.ik_fk(q + dq)
+        assert np.allclose((p1 - p0) / 1e-6, J[:3, i], atol=1e-5)
+
+
+def test_mjcf_chain_matches_urdf_chain(pushing_scene, pushing_contexts):
+    """B.9(1): physics-side tcp (MJCF chain) == controller-side grasptarget (URDF chain) up to XML rounding."""
+    env, sc = make(pushing_scene)
+    env.reset(pushing_contexts[0])
+    rng = np.random.default_rng(1)
+    for _ in range(5):
+        q = rng.uniform(-1.5, 1.5, 7); q[3] = -abs(q[3]) - 0.2
+        set_q(env, sc, q); env.forward()
+        p, _, _ = env.ik_fk(q)
+        assert np.allclose(env.robot_state(), p, atol=2e-6)
+
+
+def test_mass_matrix_matches_numpy_crba(pushing_scene, pushing_contexts):
+    """B.9(2): oracle CRBA vs the independent numpy composite-inertia build; symmetric positive definite."""
+    env, sc = make(pushing_scene)
+    links = links_from_scene(sc)
+    rng = np.random.default_rng(2)
+    env.reset(pushing_contexts[3])
+    for _ in range(3):
+        q = rng.uniform(-1.5, 1.5, 7); q[3] = -abs(q[3]) - 0.2
+        objs = pushing_contexts[rng.integers(60)].copy()
+        objs[:, 2] = 0.011
+        set_q(env, sc, q, objs=objs); env.forward()
+        nv = sc.header["nv"]
+        M = env.probe("M").reshape(nv, nv)
+        s = env.get_state()
+        qpl = list(s[:9]) + [s[9 + 7 * k: 16 + 7 * k] for k in range(sc.header["nobj"])]
+        Mref, _ = mjcf.mass_matrix(links, qpl)
+        assert np.allclose(M, Mref, atol=1e-10)
+        assert np.allclose(M, M.T) and np.linalg.eigvalsh(M).min() > 0
+
+
+def test_bias_is_lagrangian(pushing_scene, pushing_contexts):
+    """B.9(2): RNE bias == Christoffel terms of M(q) + potential gradient (finite differences on the numpy model)."""
+    env, sc = make(pushing_scene)
+    links = links_from_scene(sc)[:9]
+    rng = np.random.default_rng(3)
+    env.reset(pushing_contexts[0])
+    q = np.concatenate([rng.uniform(-1, 1, 7), [0.01, 0.02]]); q[3] = -1.5
+    qd = np.concatenate([rng.uniform(-1, 1, 7), [0.05, -0.03]])
+    s = env.get_state(); nq, nv = sc.header["nq"], sc.header["nv"]
+    s[:9] = q; s[nq:nq + nv] = 0; s[nq:nq + 9] = qd
+    env.set_state(s); env.forward()
+    bias = env.probe("bias")[:9]
+
+    def Mof(qq):
+        return mjcf.mass_matrix(links, list(qq))[0]
+
+    def V(qq):
+        P, R = mjcf.link_fk(links, list(qq))
+        return sum(L.mass * 9.81 * (P[i] + R[i] @ L.ipos)[2] for i, L in enumerate(links))
+
+    h = 1e-6
+    dM = np.zeros((9, 9, 9)); g = np.zeros(9)
+    for k in range(9):
+        e = np.zeros(9); e[k] = h
+        dM[:, :, k] = (Mof(q + e) - Mof(q - e)) / (2 * h)
+        g[k] = (V(q + e) - V(q - e)) / (2 * h)
+    c = np.einsum("ijk,j,k->i", dM, qd, qd) - 0.5 * np.einsum("jki,j,k->i", dM, qd, qd)
+    assert np.allclose(bias, c + g, atol=2e-6)
+
+
+def test_free_fall(pushing_scene, pushing_contexts):
+    """B.9(3): a box above the table falls with -g (semi-implicit Euler: z_n = z0 - g h^2 n(n+1)/2)."""
+    env, sc = make(pushing_scene)
+    ctx = pushing_contexts[0].copy(); ctx[:, 2] = 0.5
+    env.reset(ctx)
+    z0 = env.get_state()[9 + 2]
+    env.substep(100)
+    z = env.get_state()[9 + 2]
+    n = 100
+    # reset already took one tick (v = -g h), so ticks 2..n+1 contribute -g h^2 k each
+    assert abs((z - z0) + 9.81 * 1e-6 * ((n + 1) * (n + 2) / 2 - 1)) < 1e-12
+
+
+def test_box_rest_force_balance(pushing_scene, pushing_contexts):
+    """B.9(4,5): at rest the table carries m*g, friction stays inside the (regularised) cone, no drift."""
+    env, sc = make(pushing_scene)
+    env.reset(pushing_contexts[5])
+    env.substep(600)
+    s0 = env.get_state()
+    env.substep(200)
+    s1 = env.get_state()
+    nq, nv = sc.header["nq"], sc.header["nv"]
+    assert np.abs(s1[9:nq] - s0[9:nq]).max() < 1e-7          # boxes do not creep
+    assert np.abs(s1[nq + 9:nq + nv]).max() < 1e-5
+    f = env.probe("efc_force"); con = env.probe("contacts").reshape(-1, 12)
+    J = env.probe("efc_J").reshape(-1, nv)
+    qc = J.T @ f
+    # vertical constraint force on each box == weight (0.05 kg)
+    assert abs(qc[9 + 2] - 0.05 * 9.81) < 1e-6 and abs(qc[15 + 2] - 0.05 * 9.81) < 1e-6
+    for c in con:
+        e0 = int(c[11])
+        if e0 < 0:
+            continue
+        fn, ft = f[e0], np.hypot(f[e0 + 1], f[e0 + 2])
+        assert fn >= -1e-12 and ft <= 1.0 * fn + 1e-9        # friction coefficient 1 (max of the pair)
+    assert 0.0109 < s1[9 + 2] < 0.011                          # rests ~16 um inside the table top (soft contact)
+
+
+def test_gravity_compensated_arm_holds(avoiding_scene):
+    """B.9(3): with the joint-PD + stale-bias gravity compensation the arm stays at init_qpos."""
+    env, sc = make(avoiding_scene)
+    env.reset()
+    q0 = env.get_state()[:7].copy()
+    env.substep(300)
+    assert np.abs(env.get_state()[:7] - q0).max() < 2e-5
+
+
+def test_solver_optimality_and_cone(pushing_scene, pushing_contexts):
+    """B.9(6): Newton result satisfies the KKT stationarity of the primal problem; forces lie in the dual cone."""
+    env, sc = make(pushing_scene)
+    env.reset(pushing_contexts[7])                  # deep initial penetration: 16 contacts, 48 rows
+    nv = sc.header["nv"]
+    M = env.probe("M").reshape(nv, nv); J = env.probe("efc_J").reshape(-1, nv)
+    f = env.probe("efc_force"); qacc = env.probe("qacc"); qs = env.probe("qacc_smooth")
+    assert J.shape[0] == 48
+    grad = M @ (qacc - qs) - J.T @ f
+    assert np.abs(grad).max() < 1e-7
+    con = env.probe("contacts").reshape(-1, 12)
+    for c in con:
+        e0 = int(c[11]); mu = c[10]
+        assert f[e0] >= 0
+        # regularised cone: |f_t| <= mu_reg * f_n * (f0/mu) ... in scaled variables  f_t/f0 <= f_n/mu
+        assert np.hypot(f[e0 + 1], f[e0 + 2]) / 1.0 <= f[e0] / mu + 1e-9
+
+
+def test_determinism_and_state_roundtrip(pushing_scene, pushing_contexts):
+    """B.9(8): set_state(get_state()) is idempotent and reset reproduces bit-identical trajectories."""
+    env, sc = make(pushing_scene)
+    traj = []
+    for rep in range(2):
+        env.reset(pushing_contexts[11])
+        des = env.robot_state().copy()
+        out = []
+        for k in range(10):
+            des[1] += 0.005
+            o, r, d, info = env.step(np.concatenate([des, [0, 1, 0, 0]]))
+            if k == 4:
+                env.set_state(env.get_state())
+            out.append(env.get_state())
+        traj.append(np.array(out))
+    assert np.array_equal(traj[0], traj[1])
+
+
+def _numpy_ik_tick(sc, q, des_pos, des_quat):
+    """numpy restatement of IKControllers.py:197-276 (np.linalg.svd / solve exactly as the reference calls them)."""
+    from d3il_b200.scene import blob as B
+    from d3il_b200.scene.compile import ik_fk, quat_error
+    C = sc.ctrl
+    chain = [(C[12 * i: 12 * i + 3], C[12 * i + 3: 12 * i + 12].reshape(3, 3)) for i in range(7)]
+    ee = (C[B.C_IK_EE: B.C_IK_EE + 3], C[B.C_IK_EE + 3: B.C_IK_EE + 12].reshape(3, 3))
+    q = q.copy(); dq = np.array(des_quat, float)
+    for _ in range(3):
+        p, cq, J = ik_fk(chain, ee, q)
+        if np.linalg.norm(cq - dq) > np.linalg.norm(cq + dq):
+            dq = -dq
+        acc = np.hstack((C[B.C_PGAIN_POS:B.C_PGAIN_POS + 3] * np.clip(des_pos - p, -0.01, 0.01),
+                         C[B.C_PGAIN_QUAT:B.C_PGAIN_QUAT + 3] * np.clip(quat_error(cq, dq), -0.1, 0.1)))
+        A = J @ J.T + C[B.C_JREG] * np.eye(6)
+        u, sv, v = np.linalg.svd(A, full_matrices=False)
+        A = u @ np.diag(np.clip(sv, C[B.C_SVD_MIN], C[B.C_SVD_MAX])) @ v
+        qd_null = C[B.C_PGAIN_NULL:B.C_PGAIN_NULL + 7] * np.clip(C[B.C_REST:B.C_REST + 7] - q, -0.2, 0.2)
+        qd = J.T @ np.linalg.solve(A, acc - J @ qd_null) + qd_null
+        if np.linalg.norm(qd) > 3:
+            qd = qd * 3 / np.linalg.norm(qd)
+        q = np.clip(q + C[B.C_LRATE] * qd, C[B.C_JMIN:B.C_JMIN + 7], C[B.C_JMAX:B.C_JMAX + 7])
+    return q
+
+
+def test_ik_tick_matches_numpy_restatement(avoiding_scene):
+    """a5: the oracle's Jacobi-eigen IK iteration == numpy svd/solve restatement of IKControllers.py:197-276."""
+    env, sc = make(avoiding_scene)
+    env.reset()
+    rng = np.random.default_rng(5)
+    nq, nv = 9, 9
+    o = nq + 2 * nv
+    for trial in range(4):
+        tcp = env.robot_state().copy()
+        des = tcp + rng.uniform(-0.02, 0.02, 3)
+        s = env.get_state()
+        s[o + 23: o + 26] = des; s[o + 26: o + 30] = [0, 1, 0, 0]
+        s[o + 44 + 1] = 1                 # ctrl_mode = Cartesian
+        env.set_state(s)
+        valid = s[o + 44] != 0
+        q_start = s[o + 16: o + 23].copy() if valid else s[:7].copy()
+        env.substep(1)
+        ikq = env.get_state()[o + 16: o + 23]
+        ref = _numpy_ik_tick(sc, q_start, des, [0, 1, 0, 0])
+        assert np.allclose(ikq, ref, atol=1e-12), np.abs(ikq - ref).max()
+        env.substep(20)
+
+
+# ------------------------------------------------------------------ narrow phase known answers
+def test_box_box_flat_rest_gives_four_corners():
+    q = [1, 0, 0, 0]
+    c = collide(G_BOX, [0.4, 0, -0.02], q, [0.49, 0.98, 0.001], G_BOX, [0.5, 0.1, 0.0109], [np.cos(0.3), 0, 0, np.sin(0.3)], [0.03, 0.03, 0.03])
+    assert c.shape == (4, 7)
+    assert np.allclose(c[:, 3:6], [0, 0, 1])
+    assert np.allclose(c[:, 6], -0.0001, atol=1e-12)
+    assert np.allclose(np.sort(np.hypot(c[:, 0] - 0.5, c[:, 1] - 0.1)), 0.03 * np.sqrt(2))
+
+
+def test_box_box_separated_and_edge():
+    q = [1, 0, 0, 0]
+    assert collide(G_BOX, [0, 0, 0], q, [0.03] * 3, G_BOX, [0.07, 0, 0], q, [0.03] * 3).shape[0] == 0
+    # edge-edge: B rotated 45deg about x and 45deg about y-ish, touching A's top edge
+    qa = mjcf.mat2quat(mjcf.rpy2mat([0.0, 0.0, np.pi / 4]))
+    qb = mjcf.mat2quat(mjcf.rpy2mat([np.pi / 4, 0.0, 0.0]))
+    c = collide(G_BOX, [0, 0, 0], qa, [0.03] * 3, G_BOX, [0.0, 0.0, 0.03 + 0.03 * np.sqrt(2) - 0.001], qb, [0.03] * 3)
+    assert c.shape[0] >= 1 and np.all(c[:, 6] < 0) and np.all(c[:, 5] > 0.9)
+
+
+def test_cyl_box_side_face_and_corner():
+    q = [1, 0, 0, 0]
+    # vertical rod flush against the +x face of a box: normal -x (cyl -> box), depth 2 mm, point at mid overlap height
+    c = collide(G_CYL, [0.038, 0.0, 0.15], q, [0.01, 0.15], G_BOX, [0, 0, 0.011], q, [0.03] * 3)
+    assert c.shape == (1, 7)
+    assert np.allclose(c[0, 3:6], [-1, 0, 0]) and abs(c[0, 6] + 0.002) < 1e-12
+    assert abs(c[0, 2] - 0.5 * (0.0 + 0.041)) < 1e-9 and abs(c[0, 0] - 0.029) < 1e-12
+    # rod near the vertical edge (corner in top view): normal along the diagonal
+    d = 0.03 + (0.01 - 0.001) / np.sqrt(2)
+    c = collide(G_CYL, [d, d, 0.15], q, [0.01, 0.15], G_BOX, [0, 0, 0.011], q, [0.03] * 3)
+    assert c.shape == (1, 7)
+    assert np.allclose(c[0, 3:6], [-np.sqrt(0.5), -np.sqrt(0.5), 0], atol=1e-9) and abs(c[0, 6] + 0.001) < 1e-9
+    # separated
+    assert collide(G_CYL, [0.041, 0.0, 0.15], q, [0.01, 0.15], G_BOX, [0, 0, 0.011], q, [0.03] * 3).shape[0] == 0
+
+
+def test_cyl_cyl_parallel():
+    q = [1, 0, 0, 0]
+    c = collide(G_CYL, [0.5, -0.136, 0.152], q, [0.01, 0.15], G_CYL, [0.5, -0.1, 0.0], q, [0.03, 0.07])
+    assert c.shape == (1, 7) and abs(c[0, 6] + 0.004) < 1e-12 and np.allclose(c[0, 3:6], [0, 1, 0])
+    assert collide(G_CYL, [0.5, -0.1401, 0.152], q, [0.01, 0.15], G_CYL, [0.5, -0.1, 0.0], q, [0.03, 0.07]).shape[0] == 0
