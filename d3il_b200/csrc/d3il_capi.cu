@@ -1,0 +1,388 @@
+// d3il_capi.cu — CUDA kernels (sm_100a) + the C ABI of include/d3il.h.
+//
+// Data layout in HBM (DESIGN.md "memory"):
+//   state  : [n_envs][row] fp32, env-major rows padded to 32 floats (128 B) — one warp owns one env and streams its
+//            row in/out with fully coalesced 128 B transactions; between the two touches the state lives in shared memory
+//            for all 35 physics ticks of the env step.
+//   ik_*   : IK-controller state, field-major SoA [field][n_envs] (the IK kernel is one THREAD per env).
+//   traj   : [n_ticks][21][n_envs] fp32 joint set-points (q_hi, q_lo, qd) written by the IK kernel (coalesced along
+//            envs), read by the physics kernel.
+// Kernels: k_ik (thread per env: the 3 x n_ticks damped-least-squares iterations of the open-loop IK reference, fp64),
+//          k_env (warp per env: Gym pre-step sampling, n_ticks physics ticks, post-step info), k_reset (warp per env).
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#include <new>
+#include <vector>
+
+#include "../../include/d3il.h"
+#include "d3il_model.h"
+
+#define G_LANES 32
+#define ENVS_PER_CTA 8
+#define CTA_THREADS (G_LANES * ENVS_PER_CTA)
+
+static thread_local std::string g_err;
+extern "C" const char* d3il_last_error(void) { return g_err.c_str(); }
+#define CK(call)                                                                                       \
+  do {                                                                                                 \
+    cudaError_t e_ = (call);                                                                           \
+    if (e_ != cudaSuccess) { g_err = std::string(#call) + ": " + cudaGetErrorString(e_); return -2; } \
+  } while (0)
+
+struct DevIk {            // SoA views, [field][n]
+  double* q;              // [7][n]
+  float* des;             // [7][n]  des_pos(3), des_quat(4)
+  float* jt;              // [21][n] last set-point: q_hi(7), q_lo(7), qd(7)
+  int* valid;             // [n]
+};
+struct DevCtx {
+  const Model* model;     // global copy, staged into shared memory per CTA
+  Lay lay;
+  float* state;           // [n][row]
+  int row, n, ws_stride;
+  DevIk ik;
+  float* traj;            // [ticks][21][n]
+  float tol; int max_iter;
+};
+
+struct d3il_env {
+  Model m; Lay L;
+  DevCtx d;
+  int device, n, max_ticks;
+  long long launches;
+  size_t smem_bytes;
+  // pinned + device staging for the *_host calls
+  float *h_in, *h_out, *d_in, *d_out; uint8_t *h_mask, *d_mask; size_t in_floats, out_floats;
+  cudaStream_t own_stream;
+};
+
+// ------------------------------------------------------------------------------------------------ kernels
+__device__ __forceinline__ void stage_model(Model* sm, const Model* gm) {
+  const int* src = (const int*)gm; int* dst = (int*)sm;
+  for (int i = threadIdx.x; i < (int)(sizeof(Model) / 4); i += blockDim.x) dst[i] = src[i];
+  __syncthreads();
+}
+
+// IK reference generator: one thread per env (a5/a6).  mode: 1 = take the set-point from `action` (env step),
+// 0 = keep the stored set-point (d3il_substep).  In joint-PD mode (after reset) the held set-point is replicated.
+__global__ void __launch_bounds__(128) k_ik(DevCtx c, const float* __restrict__ action, int n_ticks, int use_action) {
+  __shared__ tab_t sctrl[D3_CTRL_W];
+  for (int i = threadIdx.x; i < D3_CTRL_W; i += blockDim.x) sctrl[i] = c.model->ctrl[i];
+  __syncthreads();
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= c.n) return;
+  const int n = c.n;
+  const float* row = c.state + (size_t)e * c.row;
+  IkState s;
+  for (int k = 0; k < 7; k++) { s.q[k] = c.ik.q[k * n + e]; s.jt_q[k] = c.ik.jt[k * n + e]; s.jt_qlo[k] = c.ik.jt[(7 + k) * n + e]; s.jt_qd[k] = c.ik.jt[(14 + k) * n + e]; }
+  s.valid = c.ik.valid[e];
+  int cart = use_action ? 1 : (row[c.lay.misc + ST_CTRL_MODE] != 0.f);
+  if (use_action) {
+    const float* a = action + (size_t)e * 7;
+    float nq = rsqrtf(a[3] * a[3] + a[4] * a[4] + a[5] * a[5] + a[6] * a[6]);
+    s.des_pos[0] = a[0]; s.des_pos[1] = a[1]; s.des_pos[2] = a[2];
+    for (int k = 0; k < 4; k++) s.des_quat[k] = a[3 + k] * nq;
+    for (int k = 0; k < 7; k++) c.ik.des[k * n + e] = k < 3 ? s.des_pos[k] : s.des_quat[k - 3];
+  } else {
+    for (int k = 0; k < 3; k++) s.des_pos[k] = c.ik.des[k * n + e];
+    for (int k = 0; k < 4; k++) s.des_quat[k] = c.ik.des[(3 + k) * n + e];
+  }
+  if (cart && !s.valid) {                      // IKControllers.py:168-169: old_q NaN -> measured joints
+    for (int k = 0; k < 7; k++) s.q[k] = (double)row[c.lay.qpos + k] + (double)row[c.lay.qlo + k];
+    s.valid = 1;
+  }
+  for (int t = 0; t < n_ticks; t++) {
+    if (cart) ik_tick(sctrl, s);
+    float* tr = c.traj + (size_t)t * 21 * n + e;
+    for (int k = 0; k < 7; k++) { tr[k * n] = s.jt_q[k]; tr[(7 + k) * n] = s.jt_qlo[k]; tr[(14 + k) * n] = s.jt_qd[k]; }
+  }
+  for (int k = 0; k < 7; k++) { c.ik.q[k * n + e] = s.q[k]; c.ik.jt[k * n + e] = s.jt_q[k]; c.ik.jt[(7 + k) * n + e] = s.jt_qlo[k]; c.ik.jt[(14 + k) * n + e] = s.jt_qd[k]; }
+  c.ik.valid[e] = s.valid;
+}
+
+// Env step: one warp per env.  gym = 1: GymEnvWrapper.step semantics around the ticks; gym = 0: bare ticks (substep).
+__global__ void __launch_bounds__(CTA_THREADS, 1)
+k_env(DevCtx c, int n_ticks, int gym, float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ done, float* __restrict__ info) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Model* sm = (Model*)smem_raw;
+  stage_model(sm, c.model);
+  const Model& m = *sm;
+  const Lay& L = c.lay;
+  const int warp = threadIdx.x / G_LANES;
+  Cx cx; cx.lane = threadIdx.x % G_LANES; cx.mask = 0xffffffffu;
+  const int e = blockIdx.x * ENVS_PER_CTA + warp;
+  if (e >= c.n) return;
+  float* w = (float*)(smem_raw + ((sizeof(Model) + 127) & ~(size_t)127)) + (size_t)warp * c.ws_stride;
+  float* row = c.state + (size_t)e * c.row;
+  for (int i = cx.lane; i < L.n_state; i += G_LANES) w[i] = row[i];
+  __syncwarp();
+  if (gym) env_prestep<G_LANES>(cx, m, L, w, obs + (size_t)e * m.obs_dim, reward + e, done + e);
+  for (int t = 0; t < n_ticks; t++) {
+    const float* tr = c.traj + (size_t)t * 21 * c.n + e;
+    for (int k = cx.lane; k < 21; k += G_LANES) w[L.jt + k] = tr[(size_t)k * c.n];
+    __syncwarp();
+    physics_tick<G_LANES>(cx, m, L, w, w + L.jt, w + L.jt + 7, w + L.jt + 14, c.tol, c.max_iter);
+  }
+  if (gym) env_poststep<G_LANES>(cx, m, L, w, info + (size_t)e * m.info_dim);
+  for (int i = cx.lane; i < L.n_state; i += G_LANES) row[i] = w[i];
+}
+
+__global__ void __launch_bounds__(CTA_THREADS, 1)
+k_reset(DevCtx c, const float* __restrict__ ctx, const uint8_t* __restrict__ mask, float* __restrict__ obs) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Model* sm = (Model*)smem_raw;
+  stage_model(sm, c.model);
+  const Model& m = *sm;
+  const Lay& L = c.lay;
+  const int warp = threadIdx.x / G_LANES;
+  Cx cx; cx.lane = threadIdx.x % G_LANES; cx.mask = 0xffffffffu;
+  const int e = blockIdx.x * ENVS_PER_CTA + warp;
+  if (e >= c.n) return;
+  if (mask && !mask[e]) return;
+  float* w = (float*)(smem_raw + ((sizeof(Model) + 127) & ~(size_t)127)) + (size_t)warp * c.ws_stride;
+  env_reset<G_LANES>(cx, m, L, w, (ctx && m.ctx_dim > 0) ? ctx + (size_t)e * m.ctx_dim : nullptr, c.tol, c.max_iter);
+  float* row = c.state + (size_t)e * c.row;
+  for (int i = cx.lane; i < L.n_state; i += G_LANES) row[i] = w[i];
+  const int n = c.n;
+  for (int k = cx.lane; k < 7; k += G_LANES) {
+    c.ik.q[k * n + e] = 0; c.ik.des[k * n + e] = 0;
+    c.ik.jt[k * n + e] = (float)m.ctrl[D3C_INIT_QPOS + k]; c.ik.jt[(7 + k) * n + e] = 0; c.ik.jt[(14 + k) * n + e] = 0;
+  }
+  if (cx.lane == 0) {
+    c.ik.valid[e] = 0;
+    if (obs) task_obs(m, L, w, obs + (size_t)e * m.obs_dim);
+  }
+}
+
+__global__ void k_robot_state(DevCtx c, float* __restrict__ tcp) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= c.n) return;
+  const float* row = c.state + (size_t)e * c.row;
+  for (int k = 0; k < 3; k++) tcp[(size_t)e * 3 + k] = row[c.lay.tcp + k];
+}
+
+// ------------------------------------------------------------------------------------------------ C ABI
+extern "C" int d3il_create(d3il_env** out, const void* blob, size_t nbytes, int n_envs, int device) {
+  if (!out || !blob || n_envs <= 0) { g_err = "d3il_create: bad arguments"; return -1; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { g_err = "d3il_create: no usable CUDA device (this library has no CPU path)"; return -3; }
+  d3il_env* h = new (std::nothrow) d3il_env();
+  if (!h) { g_err = "out of memory"; return -1; }
+  memset(&h->d, 0, sizeof(h->d));
+  std::string err;
+  if (!d3il_build_model(blob, nbytes, h->m, h->L, err)) { g_err = "d3il_create: " + err; delete h; return -1; }
+  if (h->m.act_dim != 7) { g_err = "d3il_create: only Cartesian (7-D) action scenes are supported"; delete h; return -1; }
+  h->device = device; h->n = n_envs; h->launches = 0; h->max_ticks = h->m.n_substeps > 64 ? h->m.n_substeps : 64;
+  CK(cudaSetDevice(device));
+  DevCtx& d = h->d;
+  d.lay = h->L; d.n = n_envs; d.row = (h->L.n_state + 31) & ~31; d.ws_stride = (h->L.total + 31) & ~31;
+  d.tol = 1e-6f; d.max_iter = 12;
+  Model* dm = nullptr;
+  CK(cudaMalloc(&dm, sizeof(Model)));
+  CK(cudaMemcpy(dm, &h->m, sizeof(Model), cudaMemcpyHostToDevice));
+  d.model = dm;
+  CK(cudaMalloc(&d.state, (size_t)n_envs * d.row * sizeof(float)));
+  CK(cudaMemset(d.state, 0, (size_t)n_envs * d.row * sizeof(float)));
+  CK(cudaMalloc(&d.ik.q, (size_t)7 * n_envs * sizeof(double)));
+  CK(cudaMalloc(&d.ik.des, (size_t)7 * n_envs * sizeof(float)));
+  CK(cudaMalloc(&d.ik.jt, (size_t)21 * n_envs * sizeof(float)));
+  CK(cudaMalloc(&d.ik.valid, (size_t)n_envs * sizeof(int)));
+  CK(cudaMemset(d.ik.q, 0, (size_t)7 * n_envs * sizeof(double)));
+  CK(cudaMemset(d.ik.des, 0, (size_t)7 * n_envs * sizeof(float)));
+  CK(cudaMemset(d.ik.jt, 0, (size_t)21 * n_envs * sizeof(float)));
+  CK(cudaMemset(d.ik.valid, 0, (size_t)n_envs * sizeof(int)));
+  CK(cudaMalloc(&d.traj, (size_t)h->max_ticks * 21 * n_envs * sizeof(float)));
+  h->smem_bytes = ((sizeof(Model) + 127) & ~(size_t)127) + (size_t)ENVS_PER_CTA * d.ws_stride * sizeof(float);
+  if (h->smem_bytes > 227 * 1024) { g_err = "d3il_create: scene workspace does not fit in shared memory"; delete h; return -1; }
+  CK(cudaFuncSetAttribute(k_env, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  CK(cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  // staging for the host-buffer entry points
+  const Model& m = h->m;
+  h->in_floats = (size_t)n_envs * (m.act_dim > m.ctx_dim ? m.act_dim : m.ctx_dim);
+  h->out_floats = (size_t)n_envs * (m.obs_dim + 1 + m.info_dim + 3) + (n_envs + 3) / 4 + 8;
+  CK(cudaMallocHost(&h->h_in, h->in_floats * sizeof(float)));
+  CK(cudaMallocHost(&h->h_out, h->out_floats * sizeof(float)));
+  CK(cudaMallocHost(&h->h_mask, n_envs));
+  CK(cudaMalloc(&h->d_in, h->in_floats * sizeof(float)));
+  CK(cudaMalloc(&h->d_out, h->out_floats * sizeof(float)));
+  CK(cudaMalloc(&h->d_mask, n_envs));
+  CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  *out = h;
+  return 0;
+}
+
+extern "C" void d3il_destroy(d3il_env* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaFree((void*)h->d.model); cudaFree(h->d.state); cudaFree(h->d.ik.q); cudaFree(h->d.ik.des); cudaFree(h->d.ik.jt); cudaFree(h->d.ik.valid);
+  cudaFree(h->d.traj); cudaFreeHost(h->h_in); cudaFreeHost(h->h_out); cudaFreeHost(h->h_mask); cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_mask);
+  cudaStreamDestroy(h->own_stream);
+  delete h;
+}
+
+extern "C" int d3il_dims(const d3il_env* h, int32_t out[D3IL_NDIMS]) {
+  if (!h || !out) { g_err = "d3il_dims: bad arguments"; return -1; }
+  out[D3IL_DIM_OBS] = h->m.obs_dim; out[D3IL_DIM_ACT] = h->m.act_dim; out[D3IL_DIM_CTX] = h->m.ctx_dim; out[D3IL_DIM_INFO] = h->m.info_dim;
+  out[D3IL_DIM_STATE] = d3il_state_dim(h->m); out[D3IL_DIM_NENVS] = h->n; out[D3IL_DIM_SUBSTEPS] = h->m.n_substeps; out[D3IL_DIM_MAXSTEPS] = h->m.max_steps;
+  return 0;
+}
+
+extern "C" int d3il_set_solver(d3il_env* h, double tol, int max_iter) {
+  if (!h || tol <= 0 || max_iter < 1) { g_err = "d3il_set_solver: bad arguments"; return -1; }
+  h->d.tol = (float)tol; h->d.max_iter = max_iter;
+  return 0;
+}
+extern "C" long long d3il_kernel_launches(const d3il_env* h) { return h ? h->launches : 0; }
+
+static inline int env_grid(const d3il_env* h) { return (h->n + ENVS_PER_CTA - 1) / ENVS_PER_CTA; }
+
+extern "C" int d3il_reset(d3il_env* h, const float* ctx, const uint8_t* mask, float* obs, void* stream) {
+  if (!h) { g_err = "d3il_reset: null handle"; return -1; }
+  if (h->m.ctx_dim > 0 && !ctx) { g_err = "d3il_reset: this scene needs a context per env"; return -1; }
+  CK(cudaSetDevice(h->device));
+  k_reset<<<env_grid(h), CTA_THREADS, h->smem_bytes, (cudaStream_t)stream>>>(h->d, ctx, mask, obs);
+  h->launches += 1;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int d3il_step(d3il_env* h, const float* action, float* obs, float* reward, uint8_t* done, float* info, void* stream) {
+  if (!h || !action || !obs || !reward || !done || !info) { g_err = "d3il_step: null argument"; return -1; }
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  k_ik<<<(h->n + 127) / 128, 128, 0, s>>>(h->d, action, h->m.n_substeps, 1);
+  k_env<<<env_grid(h), CTA_THREADS, h->smem_bytes, s>>>(h->d, h->m.n_substeps, 1, obs, reward, done, info);
+  h->launches += 2;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int d3il_substep(d3il_env* h, int n, void* stream) {
+  if (!h || n < 0) { g_err = "d3il_substep: bad arguments"; return -1; }
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  while (n > 0) {
+    int k = n < h->max_ticks ? n : h->max_ticks;
+    k_ik<<<(h->n + 127) / 128, 128, 0, s>>>(h->d, nullptr, k, 0);
+    k_env<<<env_grid(h), CTA_THREADS, h->smem_bytes, s>>>(h->d, k, 0, nullptr, nullptr, nullptr, nullptr);
+    h->launches += 2;
+    n -= k;
+  }
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+extern "C" int d3il_robot_state(d3il_env* h, float* tcp, void* stream) {
+  if (!h || !tcp) { g_err = "d3il_robot_state: null argument"; return -1; }
+  CK(cudaSetDevice(h->device));
+  k_robot_state<<<(h->n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->d, tcp);
+  h->launches += 1;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// ---- host-buffer variants (end-to-end path: pinned staging, H2D, kernels, D2H, sync)
+extern "C" int d3il_reset_host(d3il_env* h, const float* ctx, const uint8_t* mask, float* obs) {
+  if (!h) { g_err = "d3il_reset_host: null handle"; return -1; }
+  const Model& m = h->m; const size_t n = h->n;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = h->own_stream;
+  if (m.ctx_dim > 0) {
+    if (!ctx) { g_err = "d3il_reset_host: this scene needs a context per env"; return -1; }
+    memcpy(h->h_in, ctx, n * m.ctx_dim * sizeof(float));
+    CK(cudaMemcpyAsync(h->d_in, h->h_in, n * m.ctx_dim * sizeof(float), cudaMemcpyHostToDevice, s));
+  }
+  if (mask) { memcpy(h->h_mask, mask, n); CK(cudaMemcpyAsync(h->d_mask, h->h_mask, n, cudaMemcpyHostToDevice, s)); }
+  int rc = d3il_reset(h, m.ctx_dim > 0 ? h->d_in : nullptr, mask ? h->d_mask : nullptr, obs ? h->d_out : nullptr, s);
+  if (rc) return rc;
+  if (obs) {
+    // rows of envs that were not reset keep their previous device-side content; only masked rows are meaningful
+    CK(cudaMemcpyAsync(h->h_out, h->d_out, n * m.obs_dim * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    for (size_t e = 0; e < n; e++) if (!mask || mask[e]) memcpy(obs + e * m.obs_dim, h->h_out + e * m.obs_dim, m.obs_dim * sizeof(float));
+  } else CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+extern "C" int d3il_step_host(d3il_env* h, const float* action, float* obs, float* reward, uint8_t* done, float* info) {
+  if (!h || !action || !obs || !reward || !done || !info) { g_err = "d3il_step_host: null argument"; return -1; }
+  const Model& m = h->m; const size_t n = h->n;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = h->own_stream;
+  memcpy(h->h_in, action, n * m.act_dim * sizeof(float));
+  CK(cudaMemcpyAsync(h->d_in, h->h_in, n * m.act_dim * sizeof(float), cudaMemcpyHostToDevice, s));
+  float* d_obs = h->d_out; float* d_rew = d_obs + n * m.obs_dim; float* d_info = d_rew + n; uint8_t* d_done = (uint8_t*)(d_info + n * m.info_dim);
+  int rc = d3il_step(h, h->d_in, d_obs, d_rew, d_done, d_info, s);
+  if (rc) return rc;
+  size_t bytes = (n * (m.obs_dim + 1 + m.info_dim)) * sizeof(float) + n;
+  CK(cudaMemcpyAsync(h->h_out, h->d_out, bytes, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  memcpy(obs, h->h_out, n * m.obs_dim * sizeof(float));
+  memcpy(reward, h->h_out + n * m.obs_dim, n * sizeof(float));
+  memcpy(info, h->h_out + n * (m.obs_dim + 1), n * m.info_dim * sizeof(float));
+  memcpy(done, (uint8_t*)(h->h_out + n * (m.obs_dim + 1 + m.info_dim)), n);
+  return 0;
+}
+
+extern "C" int d3il_robot_state_host(d3il_env* h, float* tcp) {
+  if (!h || !tcp) { g_err = "d3il_robot_state_host: null argument"; return -1; }
+  CK(cudaSetDevice(h->device));
+  int rc = d3il_robot_state(h, h->d_out, h->own_stream);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h->h_out, h->d_out, (size_t)h->n * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->own_stream));
+  CK(cudaStreamSynchronize(h->own_stream));
+  memcpy(tcp, h->h_out, (size_t)h->n * 3 * sizeof(float));
+  return 0;
+}
+
+// ---- flat fp64 state of one env (parity tests)
+static int fetch_env(d3il_env* h, int e, std::vector<float>& row, IkState& ik) {
+  const int n = h->n;
+  row.resize(h->d.row);
+  CK(cudaMemcpy(row.data(), h->d.state + (size_t)e * h->d.row, h->d.row * sizeof(float), cudaMemcpyDeviceToHost));
+  float des[7], jt[21];
+  for (int k = 0; k < 7; k++) {
+    CK(cudaMemcpy(&ik.q[k], h->d.ik.q + (size_t)k * n + e, sizeof(double), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&des[k], h->d.ik.des + (size_t)k * n + e, sizeof(float), cudaMemcpyDeviceToHost));
+  }
+  for (int k = 0; k < 21; k++) CK(cudaMemcpy(&jt[k], h->d.ik.jt + (size_t)k * n + e, sizeof(float), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(&ik.valid, h->d.ik.valid + e, sizeof(int), cudaMemcpyDeviceToHost));
+  for (int k = 0; k < 3; k++) ik.des_pos[k] = des[k];
+  for (int k = 0; k < 4; k++) ik.des_quat[k] = des[3 + k];
+  for (int k = 0; k < 7; k++) { ik.jt_q[k] = jt[k]; ik.jt_qlo[k] = jt[7 + k]; ik.jt_qd[k] = jt[14 + k]; }
+  return 0;
+}
+
+extern "C" int d3il_get_state(d3il_env* h, double* out, int e) {
+  if (!h || !out || e < 0 || e >= h->n) { g_err = "d3il_get_state: bad arguments"; return -1; }
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  std::vector<float> row; IkState ik;
+  int rc = fetch_env(h, e, row, ik);
+  if (rc) return rc;
+  d3il_pack_state(h->m, h->L, row.data(), ik, out);
+  return 0;
+}
+
+extern "C" int d3il_set_state(d3il_env* h, const double* in, int e) {
+  if (!h || !in || e < 0 || e >= h->n) { g_err = "d3il_set_state: bad arguments"; return -1; }
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  const int n = h->n;
+  std::vector<float> row(h->d.row, 0.f); IkState ik;
+  d3il_unpack_state(h->m, h->L, row.data(), ik, in);
+  CK(cudaMemcpy(h->d.state + (size_t)e * h->d.row, row.data(), h->d.row * sizeof(float), cudaMemcpyHostToDevice));
+  float des[7], jt[21];
+  for (int k = 0; k < 3; k++) des[k] = ik.des_pos[k];
+  for (int k = 0; k < 4; k++) des[3 + k] = ik.des_quat[k];
+  for (int k = 0; k < 7; k++) { jt[k] = ik.jt_q[k]; jt[7 + k] = ik.jt_qlo[k]; jt[14 + k] = ik.jt_qd[k]; }
+  for (int k = 0; k < 7; k++) {
+    CK(cudaMemcpy(h->d.ik.q + (size_t)k * n + e, &ik.q[k], sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->d.ik.des + (size_t)k * n + e, &des[k], sizeof(float), cudaMemcpyHostToDevice));
+  }
+  for (int k = 0; k < 21; k++) CK(cudaMemcpy(h->d.ik.jt + (size_t)k * n + e, &jt[k], sizeof(float), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(h->d.ik.valid + e, &ik.valid, sizeof(int), cudaMemcpyHostToDevice));
+  return 0;
+}

@@ -1,0 +1,1106 @@
+// d3il_core.cuh — lane-cooperative fp32 core of the batched env step (one G-lane group per env).
+//
+// The hot path of SURVEY.md §8(a) rows a3/a4/a7/a8/a9 (Scene.next_step -> MjRobot.prepare_step -> mj_step ->
+// receiveState; reference environments/d3il/d3il_sim/core/Scene.py:121-138, sims/mj_beta/MjRobot.py:125-184,
+// mujoco.mj_step [EXT]) re-designed for a warp: every phase is a strided loop over links / dofs / pairs / contacts /
+// constraint rows with the group's lanes, operands staged in shared memory, group barriers between phases and
+// shuffle reductions for the scalar solver quantities.  No tensor cores: there is no dense contraction here.
+//
+// The file compiles two ways:
+//   * nvcc (device): G = 32 (or 16/8) lanes per env, GSYNC = __syncwarp, reductions = __shfl_xor_sync.
+//   * -DD3IL_EMU (host, tests only): G = 1, one "lane" walks every strided loop sequentially.  This is how the
+//     kernel logic is checked against the fp64 oracle in the CPU container.  To keep both builds equivalent the code
+//     never branches on a particular lane id: cross-lane data always goes through workspace memory + GSYNC, or
+//     through the all-reduce helpers below.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#ifndef D3IL_REAL
+#define D3IL_REAL float
+#endif
+typedef D3IL_REAL real;
+#ifdef D3IL_TAB64
+typedef double tab_t;   // test-only: exact tables for logic checks against the fp64 oracle
+#else
+typedef float tab_t;    // model tables are fp32 in shared memory
+#endif
+
+#ifdef D3IL_EMU
+#define DEVFN static inline
+#define D3_RESTRICT
+struct Cx { int lane; unsigned mask; };
+template <int G> DEVFN void gsync(const Cx&) {}
+template <int G> DEVFN real gsum(const Cx&, real x) { return x; }
+template <int G> DEVFN real gmaxr(const Cx&, real x) { return x; }
+template <int G> DEVFN int gsumi(const Cx&, int x) { return x; }
+template <int G> DEVFN int gori(const Cx&, int x) { return x; }
+#else
+#define DEVFN __device__ __forceinline__
+#define D3_RESTRICT __restrict__
+struct Cx { int lane; unsigned mask; };
+template <int G> DEVFN void gsync(const Cx& cx) { __syncwarp(cx.mask); }
+template <int G> DEVFN real gsum(const Cx& cx, real x) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) x += __shfl_xor_sync(cx.mask, x, o, G);
+  return x;
+}
+template <int G> DEVFN real gmaxr(const Cx& cx, real x) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) x = fmaxf(x, __shfl_xor_sync(cx.mask, x, o, G));
+  return x;
+}
+template <int G> DEVFN int gsumi(const Cx& cx, int x) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) x += __shfl_xor_sync(cx.mask, x, o, G);
+  return x;
+}
+template <int G> DEVFN int gori(const Cx& cx, int x) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) x |= __shfl_xor_sync(cx.mask, x, o, G);
+  return x;
+}
+#endif
+
+#define LANES(i, n) for (int i = cx.lane; i < (n); i += G)
+
+// ------------------------------------------------------------------------------------------------ model tables
+// Float copy of the D3SC scene blob (d3il_b200/scene/blob.py) + derived index tables, staged into shared memory
+// once per CTA.  All arrays are sized for the largest scene we compile (Sorting-6: 15 links, nv 45).
+#define D3_MAXLINK 16
+#define D3_MAXV 48
+#define D3_MAXQ 56
+#define D3_MAXGEOM 24
+#define D3_MAXPAIR 48
+#define D3_NARM 7
+#define D3_NROB 9
+#define D3_LINK_W 32
+#define D3_GEOM_W 24
+#define D3_PAIR_W 24
+#define D3_CTRL_W 192
+
+enum { D3C_IK_ORIGIN = 0, D3C_IK_EE = 84, D3C_PGAIN_POS = 96, D3C_PGAIN_QUAT = 99, D3C_PGAIN_NULL = 102, D3C_REST = 109,
+       D3C_JMIN = 116, D3C_JMAX = 123, D3C_PD_P = 130, D3C_PD_D = 137, D3C_JREG = 144, D3C_SVD_MIN = 145, D3C_SVD_MAX = 146,
+       D3C_NUM_ITER = 147, D3C_LRATE = 148, D3C_DT = 149, D3C_INIT_QPOS = 150, D3C_TCP_POS = 157, D3C_TCP_QUAT = 160,
+       D3C_GRAVITY = 164, D3C_IMPRATIO = 167, D3C_TOL = 168, D3C_JNT_SOLREF = 169, D3C_JNT_SOLIMP = 171, D3C_MEANINERTIA = 179 };
+enum { D3G_CYLINDER = 5, D3G_BOX = 6 };
+enum { D3T_AVOIDING = 0, D3T_PUSHING = 1 };
+
+struct Model {
+  int task_id, nlink, nobj, nq, nv, ngeom, npair, n_substeps, max_steps, obs_dim, act_dim, ctx_dim, info_dim, ctrl_kind, ntaskp;
+  int maxcon, maxrow, nmpair;            // workspace caps and number of structurally non-zero (a>=b) entries of M
+  int ws_floats;                          // per-env workspace size
+  int pad_[1];
+  // per link
+  int l_parent[D3_MAXLINK], l_jtype[D3_MAXLINK], l_qadr[D3_MAXLINK], l_dadr[D3_MAXLINK], l_ndof[D3_MAXLINK], l_limited[D3_MAXLINK];
+  unsigned l_anc[D3_MAXLINK];             // bit j set: link j is an ancestor-or-self
+  unsigned l_desc[D3_MAXLINK];            // bit j set: link j is a descendant-or-self
+  int l_ref[D3_MAXLINK];                  // link whose origin is the spatial reference point of this link's kinematic tree
+  int d_link[D3_MAXV];
+  unsigned char mp_a[D3_MAXV * 8], mp_b[D3_MAXV * 8];   // (a,b) list of related dof pairs, a >= b
+  tab_t link[D3_MAXLINK * D3_LINK_W];
+  tab_t geom[D3_MAXGEOM * D3_GEOM_W];
+  tab_t geomR[D3_MAXGEOM * 9];
+  tab_t pair[D3_MAXPAIR * D3_PAIR_W];
+  tab_t ctrl[D3_CTRL_W];
+  tab_t taskp[32];
+};
+
+// ------------------------------------------------------------------------------------------------ per-env workspace
+// Offsets (in reals) into the env's slice of shared memory.  Persistent state first (mirrors the HBM row), then
+// scratch.  Everything is a function of the Model's sizes, computed once on the host (d3il_layout).
+struct Lay {
+  // persistent state (HBM <-> shared at kernel entry/exit)
+  int qpos, qlo, qvel, warm, bias_prev, tcp, misc; // qlo: low words of the 9 robot joint angles (two-float qpos);
+                                                    // tcp: pos3+quat4 ; misc: 16 scalars (see ST_*)
+  int n_state;
+  // scratch
+  int xpos, xmat, S, I10, Ic, vel, cj, frc, F, M, Lm, H, bias, qfrc_smooth, qacc_smooth, qacc, qfrc_c, grad, pvec, Ma, tmpv;
+  int act, jt, con, ncon_pair, J, aref, D, jar, frcE, Jp, hd, hb, etype, econ, total;
+};
+enum { ST_GRIP_SET = 0, ST_GRASP, ST_CTRL_MODE, ST_STEP, ST_TERM, ST_STATUS, ST_OBST, ST_TASK0, ST_TASK1, ST_TASK2, ST_TASK3, ST_NMISC = 16 };
+#define D3_CON_W 20    // per contact: pos3, frame9, dist, incl, mu, dim, g1, g2, pair, row0
+
+static inline void d3il_layout(const Model& m, Lay& L) {
+  int o = 0;
+  auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
+  L.qpos = take(m.nq); L.qlo = take(D3_NROB); L.qvel = take(m.nv); L.warm = take(m.nv); L.bias_prev = take(D3_NROB); L.tcp = take(7); L.misc = take(ST_NMISC);
+  L.n_state = o;
+  L.xpos = take(3 * m.nlink); L.xmat = take(9 * m.nlink); L.S = take(6 * m.nv); L.I10 = take(10 * m.nlink); L.Ic = take(10 * m.nlink);
+  L.vel = take(6 * m.nlink); L.cj = take(6 * m.nlink); L.frc = take(6 * m.nlink); L.F = take(6 * m.nv);
+  L.M = take(m.nv * m.nv); L.Lm = take(m.nv * m.nv); L.H = take(m.nv * m.nv);
+  L.bias = take(m.nv); L.qfrc_smooth = take(m.nv); L.qacc_smooth = take(m.nv); L.qacc = take(m.nv); L.qfrc_c = take(m.nv);
+  L.grad = take(m.nv); L.pvec = take(m.nv); L.Ma = take(m.nv); L.tmpv = take(m.nv);
+  L.act = take(D3_NROB); L.jt = take(3 * D3_NARM); L.con = take(D3_CON_W * m.maxcon); L.ncon_pair = take(m.npair + 4);
+  L.J = take(m.maxrow * m.nv); L.aref = take(m.maxrow); L.D = take(m.maxrow); L.jar = take(m.maxrow); L.frcE = take(m.maxrow);
+  L.Jp = take(m.maxrow); L.hd = take(m.maxrow); L.hb = take(9 * m.maxcon); L.etype = take(m.maxrow); L.econ = take(m.maxrow);
+  L.total = o;
+}
+
+// ------------------------------------------------------------------------------------------------ small math
+DEVFN real dot3(const real* a, const real* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+DEVFN void cross3(real* o, const real* a, const real* b) {
+  real x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+DEVFN real norm3(const real* a) { return sqrt(dot3(a, a)); }
+DEVFN void mat_vec3(real* o, const real* R, const real* v) {
+  real x = R[0] * v[0] + R[1] * v[1] + R[2] * v[2], y = R[3] * v[0] + R[4] * v[1] + R[5] * v[2], z = R[6] * v[0] + R[7] * v[1] + R[8] * v[2];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+DEVFN void matT_vec3(real* o, const real* R, const real* v) {
+  real x = R[0] * v[0] + R[3] * v[1] + R[6] * v[2], y = R[1] * v[0] + R[4] * v[1] + R[7] * v[2], z = R[2] * v[0] + R[5] * v[1] + R[8] * v[2];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+DEVFN void mat_mul3(real* o, const real* A, const real* B) {
+  real t[9];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) t[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+#pragma unroll
+  for (int i = 0; i < 9; i++) o[i] = t[i];
+}
+DEVFN void quat2mat(real* R, const real* q) {
+  real n = 1 / sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  real w = q[0] * n, x = q[1] * n, y = q[2] * n, z = q[3] * n;
+  R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - w * z); R[2] = 2 * (x * z + w * y);
+  R[3] = 2 * (x * y + w * z); R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - w * x);
+  R[6] = 2 * (x * z - w * y); R[7] = 2 * (y * z + w * x); R[8] = 1 - 2 * (x * x + y * y);
+}
+DEVFN void mat2quat(real* q, const real* R) {
+  real t = R[0] + R[4] + R[8];
+  if (t > 0) { real s = sqrt(t + 1) * 2; q[0] = (real)0.25 * s; q[1] = (R[7] - R[5]) / s; q[2] = (R[2] - R[6]) / s; q[3] = (R[3] - R[1]) / s; }
+  else if (R[0] > R[4] && R[0] > R[8]) { real s = sqrt(1 + R[0] - R[4] - R[8]) * 2; q[0] = (R[7] - R[5]) / s; q[1] = (real)0.25 * s; q[2] = (R[1] + R[3]) / s; q[3] = (R[2] + R[6]) / s; }
+  else if (R[4] > R[8]) { real s = sqrt(1 + R[4] - R[0] - R[8]) * 2; q[0] = (R[2] - R[6]) / s; q[1] = (R[1] + R[3]) / s; q[2] = (real)0.25 * s; q[3] = (R[5] + R[7]) / s; }
+  else { real s = sqrt(1 + R[8] - R[0] - R[4]) * 2; q[0] = (R[3] - R[1]) / s; q[1] = (R[2] + R[6]) / s; q[2] = (R[5] + R[7]) / s; q[3] = (real)0.25 * s; }
+  real n = 1 / sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  q[0] *= n; q[1] *= n; q[2] *= n; q[3] *= n;
+}
+DEVFN real clampr(real x, real lo, real hi) { return x < lo ? lo : (x > hi ? hi : x); }
+DEVFN real absr(real x) { return x < 0 ? -x : x; }
+DEVFN real maxr(real a, real b) { return a > b ? a : b; }
+DEVFN real minr(real a, real b) { return a < b ? a : b; }
+
+// ------------------------------------------------------------------------------------------------ kinematics
+// Each lane composes the transforms from the root down to "its" link (the arm is a chain of depth <= 9, free bodies
+// depth 1), so no inter-lane communication is needed; world pose, joint motion subspace S (world axes, linear part at
+// the world origin) and the 10-parameter spatial inertia about the world origin land in the workspace.
+template <int G>
+DEVFN void kinematics(const Cx& cx, const Model& m, const Lay& L, real* w) {
+  LANES(i, m.nlink) {
+    real p[3] = {0, 0, 0}, R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    if (m.l_jtype[i] == 2) {
+      real* q = w + L.qpos + m.l_qadr[i];
+      real n = 1 / sqrt(q[3] * q[3] + q[4] * q[4] + q[5] * q[5] + q[6] * q[6]);
+      q[3] *= n; q[4] *= n; q[5] *= n; q[6] *= n;                     // mj_kinematics normalises the quaternion in qpos
+      p[0] = q[0]; p[1] = q[1]; p[2] = q[2];
+      quat2mat(R, q + 3);
+    } else {
+      // walk root -> i through the ancestor mask (links are topologically ordered)
+      unsigned anc = m.l_anc[i];
+      for (int j = 0; j <= i; j++) {
+        if (!((anc >> j) & 1u)) continue;
+        const tab_t* Lk = m.link + D3_LINK_W * j;
+        real off[3], lp[3] = {(real)Lk[2], (real)Lk[3], (real)Lk[4]}, lq[4] = {(real)Lk[5], (real)Lk[6], (real)Lk[7], (real)Lk[8]};
+        mat_vec3(off, R, lp);
+        p[0] += off[0]; p[1] += off[1]; p[2] += off[2];
+        real Rq[9]; quat2mat(Rq, lq); mat_mul3(R, R, Rq);
+        real q = w[L.qpos + m.l_qadr[j]];
+        real ax[3] = {(real)Lk[9], (real)Lk[10], (real)Lk[11]};
+        if (m.l_jtype[j] == 0) {
+          real s = sin((real)0.5 * q), c = cos((real)0.5 * q), hq[4] = {c, s * ax[0], s * ax[1], s * ax[2]}, Rj[9];
+          quat2mat(Rj, hq); mat_mul3(R, R, Rj);
+        } else {
+          real a[3]; mat_vec3(a, R, ax);
+          p[0] += a[0] * q; p[1] += a[1] * q; p[2] += a[2] * q;
+        }
+      }
+    }
+    for (int k = 0; k < 3; k++) w[L.xpos + 3 * i + k] = p[k];
+    for (int k = 0; k < 9; k++) w[L.xmat + 9 * i + k] = R[k];
+  }
+  gsync<G>(cx);
+  // Spatial quantities are taken about a per-tree reference point (the origin of link l_ref: the wrist for the arm, the
+  // body itself for free objects) instead of the world origin: in fp32 the parallel-axis terms m|c|^2 would otherwise
+  // swamp the small distal inertias (MuJoCo uses the subtree CoM for the same reason).
+  LANES(i, m.nlink) {
+    const real* R = w + L.xmat + 9 * i;
+    const real* pr = w + L.xpos + 3 * m.l_ref[i];
+    real p[3] = {w[L.xpos + 3 * i] - pr[0], w[L.xpos + 3 * i + 1] - pr[1], w[L.xpos + 3 * i + 2] - pr[2]};
+    const tab_t* Lk = m.link + D3_LINK_W * i;
+    if (m.l_jtype[i] == 2) {
+      for (int k = 0; k < 3; k++) {
+        real* Sl = w + L.S + 6 * (m.l_dadr[i] + k); real* Sa = w + L.S + 6 * (m.l_dadr[i] + 3 + k);
+        for (int c = 0; c < 6; c++) Sl[c] = 0;
+        Sl[3 + k] = 1;
+        real a[3] = {R[k], R[3 + k], R[6 + k]};
+        Sa[0] = a[0]; Sa[1] = a[1]; Sa[2] = a[2]; cross3(Sa + 3, p, a);
+      }
+    } else {
+      real ax[3] = {(real)Lk[9], (real)Lk[10], (real)Lk[11]}, a[3];
+      mat_vec3(a, R, ax);
+      real* S = w + L.S + 6 * m.l_dadr[i];
+      if (m.l_jtype[i] == 0) { S[0] = a[0]; S[1] = a[1]; S[2] = a[2]; cross3(S + 3, p, a); }
+      else { S[0] = S[1] = S[2] = 0; S[3] = a[0]; S[4] = a[1]; S[5] = a[2]; }
+    }
+    // spatial inertia about the reference point: m, h = m c, IO = R I R^T + m (|c|^2 1 - c c^T)
+    real mass = Lk[12], ip[3] = {(real)Lk[13], (real)Lk[14], (real)Lk[15]}, c[3];
+    mat_vec3(c, R, ip); c[0] += p[0]; c[1] += p[1]; c[2] += p[2];
+    real Ib[9] = {(real)Lk[16], (real)Lk[19], (real)Lk[20], (real)Lk[19], (real)Lk[17], (real)Lk[21], (real)Lk[20], (real)Lk[21], (real)Lk[18]};
+    real RI[9], Rt[9] = {R[0], R[3], R[6], R[1], R[4], R[7], R[2], R[5], R[8]}, Iw[9];
+    mat_mul3(RI, R, Ib); mat_mul3(Iw, RI, Rt);
+    real cc = dot3(c, c);
+    real* I10 = w + L.I10 + 10 * i;
+    I10[0] = mass; I10[1] = mass * c[0]; I10[2] = mass * c[1]; I10[3] = mass * c[2];
+    I10[4] = Iw[0] + mass * (cc - c[0] * c[0]); I10[5] = Iw[4] + mass * (cc - c[1] * c[1]); I10[6] = Iw[8] + mass * (cc - c[2] * c[2]);
+    I10[7] = Iw[1] - mass * c[0] * c[1]; I10[8] = Iw[2] - mass * c[0] * c[2]; I10[9] = Iw[5] - mass * c[1] * c[2];
+  }
+  gsync<G>(cx);
+}
+
+// [n; f] = I10 * [w; v]
+DEVFN void inertia_apply(const real* I, const real* sv, real* o) {
+  const real* h = I + 1;
+  real hv[3], hw[3];
+  cross3(hv, h, sv + 3); cross3(hw, h, sv);
+  o[0] = I[4] * sv[0] + I[7] * sv[1] + I[8] * sv[2] + hv[0];
+  o[1] = I[7] * sv[0] + I[5] * sv[1] + I[9] * sv[2] + hv[1];
+  o[2] = I[8] * sv[0] + I[9] * sv[1] + I[6] * sv[2] + hv[2];
+  o[3] = I[0] * sv[3] - hw[0]; o[4] = I[0] * sv[4] - hw[1]; o[5] = I[0] * sv[5] - hw[2];
+}
+
+// Composite inertias, mass matrix (CRBA) and bias forces (RNE with qacc = 0) — SURVEY App. B.3.
+template <int G>
+DEVFN void dynamics(const Cx& cx, const Model& m, const Lay& L, real* w) {
+  const int nl = m.nlink, nv = m.nv;
+  // (1) composite inertia = sum over descendants ; link velocity = sum over ancestor dofs
+  LANES(i, nl) {
+    real acc[10];
+    for (int k = 0; k < 10; k++) acc[k] = 0;
+    unsigned desc = m.l_desc[i];
+    for (int j = i; j < nl; j++) if ((desc >> j) & 1u) for (int k = 0; k < 10; k++) acc[k] += w[L.I10 + 10 * j + k];
+    for (int k = 0; k < 10; k++) w[L.Ic + 10 * i + k] = acc[k];
+    real v[6] = {0, 0, 0, 0, 0, 0};
+    unsigned anc = m.l_anc[i];
+    for (int j = 0; j <= i; j++) if ((anc >> j) & 1u)
+      for (int d = m.l_dadr[j]; d < m.l_dadr[j] + m.l_ndof[j]; d++) { real qd = w[L.qvel + d]; for (int k = 0; k < 6; k++) v[k] += w[L.S + 6 * d + k] * qd; }
+    for (int k = 0; k < 6; k++) w[L.vel + 6 * i + k] = v[k];
+    // joint bias acceleration cJ = d/dt(S) qd
+    real vj[6] = {0, 0, 0, 0, 0, 0}, cj[6] = {0, 0, 0, 0, 0, 0};
+    for (int d = m.l_dadr[i]; d < m.l_dadr[i] + m.l_ndof[i]; d++) { real qd = w[L.qvel + d]; for (int k = 0; k < 6; k++) vj[k] += w[L.S + 6 * d + k] * qd; }
+    if (m.l_jtype[i] == 2) {
+      cross3(cj + 3, w + L.qvel + m.l_dadr[i], vj);                     // v_p x omega
+    } else {
+      real t1[3], t2[3];
+      cross3(cj, v, vj); cross3(t1, v, vj + 3); cross3(t2, v + 3, vj);
+      cj[3] = t1[0] + t2[0]; cj[4] = t1[1] + t2[1]; cj[5] = t1[2] + t2[2];
+    }
+    for (int k = 0; k < 6; k++) w[L.cj + 6 * i + k] = cj[k];
+  }
+  gsync<G>(cx);
+  // (2) F_d = Ic[link(d)] S_d ; link force f_i = I_i a_i + v_i x* (I_i v_i)
+  LANES(d, nv) { inertia_apply(w + L.Ic + 10 * m.d_link[d], w + L.S + 6 * d, w + L.F + 6 * d); }
+  LANES(i, nl) {
+    real a[6] = {0, 0, 0, -(real)m.ctrl[D3C_GRAVITY], -(real)m.ctrl[D3C_GRAVITY + 1], -(real)m.ctrl[D3C_GRAVITY + 2]};
+    unsigned anc = m.l_anc[i];
+    for (int j = 0; j <= i; j++) if ((anc >> j) & 1u) for (int k = 0; k < 6; k++) a[k] += w[L.cj + 6 * j + k];
+    real Ia[6], Iv[6], t1[3], t2[3], t3[3];
+    const real* v = w + L.vel + 6 * i;
+    inertia_apply(w + L.I10 + 10 * i, a, Ia); inertia_apply(w + L.I10 + 10 * i, v, Iv);
+    cross3(t1, v, Iv); cross3(t2, v + 3, Iv + 3); cross3(t3, v, Iv + 3);
+    real* f = w + L.frc + 6 * i;
+    for (int k = 0; k < 3; k++) { f[k] = Ia[k] + t1[k] + t2[k]; f[3 + k] = Ia[3 + k] + t3[k]; }
+  }
+  gsync<G>(cx);
+  // (3) M[a][b] = S_b . F_a over the related pair list ; bias_d = S_d . sum_{desc} f
+  LANES(e, m.nmpair) {
+    int a = m.mp_a[e], b = m.mp_b[e];
+    real s = 0;
+    for (int k = 0; k < 6; k++) s += w[L.S + 6 * b + k] * w[L.F + 6 * a + k];
+    w[L.M + a * nv + b] = s; w[L.M + b * nv + a] = s;
+  }
+  LANES(d, nv) {
+    int li = m.d_link[d];
+    unsigned desc = m.l_desc[li];
+    real f[6] = {0, 0, 0, 0, 0, 0};
+    for (int j = li; j < nl; j++) if ((desc >> j) & 1u) for (int k = 0; k < 6; k++) f[k] += w[L.frc + 6 * j + k];
+    real s = 0;
+    for (int k = 0; k < 6; k++) s += w[L.S + 6 * d + k] * f[k];
+    w[L.bias + d] = s;
+  }
+  gsync<G>(cx);
+}
+
+// ------------------------------------------------------------------------------------------------ narrow phase
+// Same deterministic rules as the oracle (DESIGN.md "collision"): box-box SAT + face clipping / edge-edge,
+// cylinder-box candidate-axis SAT + feature contact point, cylinder-cylinder via axis segments.
+struct RawCon { real pos[3], n[3], dist; };
+
+DEVFN int clip_poly(real (*P)[3], int n, real hu, real hv) {
+  real Q[12][3];
+  for (int plane = 0; plane < 4; plane++) {
+    int ax = plane >> 1; real sg = (plane & 1) ? (real)-1 : (real)1, h = ax ? hv : hu;
+    int mcount = 0;
+    for (int i = 0; i < n; i++) {
+      const real* a = P[i]; const real* b = P[(i + 1) % n];
+      real da = h - sg * a[ax], db = h - sg * b[ax];
+      if (da >= 0) { Q[mcount][0] = a[0]; Q[mcount][1] = a[1]; Q[mcount][2] = a[2]; mcount++; }
+      if ((da >= 0) != (db >= 0)) { real t = da / (da - db); for (int k = 0; k < 3; k++) Q[mcount][k] = a[k] + t * (b[k] - a[k]); mcount++; }
+    }
+    n = mcount;
+    for (int i = 0; i < n; i++) { P[i][0] = Q[i][0]; P[i][1] = Q[i][1]; P[i][2] = Q[i][2]; }
+    if (n == 0) return 0;
+  }
+  return n;
+}
+
+DEVFN int collide_box_box(const real* pA, const real* RA, const real* hA, const real* pB, const real* RB, const real* hB, real margin, RawCon* out) {
+  real Rr[9], AbsR[9], t[3], d[3] = {pB[0] - pA[0], pB[1] - pA[1], pB[2] - pA[2]};
+  matT_vec3(t, RA, d);
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+    real s = RA[i] * RB[j] + RA[3 + i] * RB[3 + j] + RA[6 + i] * RB[6 + j];
+    Rr[3 * i + j] = s; AbsR[3 * i + j] = absr(s);
+  }
+  real best = (real)-1e30; int code = -1; real bsign = 1;
+  for (int i = 0; i < 3; i++) {
+    real sep = absr(t[i]) - (hA[i] + hB[0] * AbsR[3 * i] + hB[1] * AbsR[3 * i + 1] + hB[2] * AbsR[3 * i + 2]);
+    if (sep > margin) return 0;
+    if (sep > best) { best = sep; code = i; bsign = t[i] >= 0 ? (real)1 : (real)-1; }
+  }
+  for (int j = 0; j < 3; j++) {
+    real tb = t[0] * Rr[j] + t[1] * Rr[3 + j] + t[2] * Rr[6 + j];
+    real sep = absr(tb) - (hB[j] + hA[0] * AbsR[j] + hA[1] * AbsR[3 + j] + hA[2] * AbsR[6 + j]);
+    if (sep > margin) return 0;
+    if (sep > best + (real)1e-6) { best = sep; code = 3 + j; bsign = tb >= 0 ? (real)1 : (real)-1; }
+  }
+  real ebest = (real)-1e30; int ecode = -1; real en[3] = {0, 0, 0};
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
+    real ai[3] = {RA[i], RA[3 + i], RA[6 + i]}, bj[3] = {RB[j], RB[3 + j], RB[6 + j]}, ax[3];
+    cross3(ax, ai, bj);
+    real l = norm3(ax);
+    if (l < (real)1e-6) continue;
+    ax[0] /= l; ax[1] /= l; ax[2] /= l;
+    real dist = dot3(ax, d), ra = 0, rb = 0;
+    for (int k = 0; k < 3; k++) {
+      real ak[3] = {RA[k], RA[3 + k], RA[6 + k]}, bk[3] = {RB[k], RB[3 + k], RB[6 + k]};
+      ra += hA[k] * absr(dot3(ax, ak)); rb += hB[k] * absr(dot3(ax, bk));
+    }
+    real sep = absr(dist) - (ra + rb);
+    if (sep > margin) return 0;
+    if (sep > ebest) { ebest = sep; ecode = 3 * i + j; real sg = dist >= 0 ? (real)1 : (real)-1; en[0] = sg * ax[0]; en[1] = sg * ax[1]; en[2] = sg * ax[2]; }
+  }
+  if (ecode >= 0 && ebest * (real)1.05 > best + (real)1e-9 && ebest > best) {
+    int i = ecode / 3, j = ecode % 3;
+    real ca[3] = {pA[0], pA[1], pA[2]}, cb[3] = {pB[0], pB[1], pB[2]};
+    for (int k = 0; k < 3; k++) {
+      if (k != i) { real ak[3] = {RA[k], RA[3 + k], RA[6 + k]}; real s = dot3(en, ak) >= 0 ? (real)1 : (real)-1; for (int c = 0; c < 3; c++) ca[c] += s * hA[k] * ak[c]; }
+      if (k != j) { real bk[3] = {RB[k], RB[3 + k], RB[6 + k]}; real s = dot3(en, bk) >= 0 ? (real)-1 : (real)1; for (int c = 0; c < 3; c++) cb[c] += s * hB[k] * bk[c]; }
+    }
+    real ua[3] = {RA[i], RA[3 + i], RA[6 + i]}, ub[3] = {RB[j], RB[3 + j], RB[6 + j]}, ww[3] = {ca[0] - cb[0], ca[1] - cb[1], ca[2] - cb[2]};
+    real b = dot3(ua, ub), dd = dot3(ua, ww), ee = dot3(ub, ww), den = 1 - b * b;
+    real sa = den > (real)1e-12 ? (b * ee - dd) / den : 0, sb = den > (real)1e-12 ? (ee - b * dd) / den : 0;
+    sa = clampr(sa, -hA[i], hA[i]); sb = clampr(sb, -hB[j], hB[j]);
+    for (int k = 0; k < 3; k++) { out[0].pos[k] = (real)0.5 * (ca[k] + sa * ua[k] + cb[k] + sb * ub[k]); out[0].n[k] = en[k]; }
+    out[0].dist = ebest;
+    return 1;
+  }
+  int refIsA = code < 3, ax = refIsA ? code : code - 3;
+  const real *pR_ = refIsA ? pA : pB, *RR = refIsA ? RA : RB, *hR = refIsA ? hA : hB;
+  const real *pI = refIsA ? pB : pA, *RI = refIsA ? RB : RA, *hI = refIsA ? hB : hA;
+  real nref[3], sgn = refIsA ? bsign : -bsign;
+  for (int k = 0; k < 3; k++) nref[k] = sgn * RR[3 * k + ax];
+  int jx = 0; real jb = -1;
+  for (int j = 0; j < 3; j++) { real c[3] = {RI[j], RI[3 + j], RI[6 + j]}; real v = absr(dot3(nref, c)); if (v > jb) { jb = v; jx = j; } }
+  real cI[3] = {RI[jx], RI[3 + jx], RI[6 + jx]};
+  real isg = dot3(nref, cI) > 0 ? (real)-1 : (real)1;
+  int k1 = (jx + 1) % 3, k2 = (jx + 2) % 3;
+  if (k1 > k2) { int tmp = k1; k1 = k2; k2 = tmp; }
+  int u = (ax + 1) % 3, v = (ax + 2) % 3;
+  if (u > v) { int tmp = u; u = v; v = tmp; }
+  real P[12][3];
+  for (int c = 0; c < 4; c++) {
+    real s1 = (c == 1 || c == 2) ? (real)1 : (real)-1, s2 = (c >= 2) ? (real)1 : (real)-1;
+    real ww[3], wl[3];
+    for (int k = 0; k < 3; k++) ww[k] = pI[k] + isg * hI[jx] * RI[3 * k + jx] + s1 * hI[k1] * RI[3 * k + k1] + s2 * hI[k2] * RI[3 * k + k2] - pR_[k];
+    matT_vec3(wl, RR, ww);
+    P[c][0] = wl[u]; P[c][1] = wl[v]; P[c][2] = sgn * wl[ax] - hR[ax];
+  }
+  int n = clip_poly(P, 4, hR[u], hR[v]);
+  int cnt = 0;
+  for (int c = 0; c < n && cnt < 8; c++) {
+    real dist = P[c][2];
+    if (dist >= margin) continue;
+    real wl[3]; wl[u] = P[c][0]; wl[v] = P[c][1]; wl[ax] = sgn * (hR[ax] + (real)0.5 * dist);
+    real ww[3]; mat_vec3(ww, RR, wl);
+    for (int k = 0; k < 3; k++) { out[cnt].pos[k] = pR_[k] + ww[k]; out[cnt].n[k] = refIsA ? nref[k] : -nref[k]; }
+    out[cnt].dist = dist; cnt++;
+  }
+  return cnt;
+}
+
+DEVFN int zonotope_closest(const real d[2], const real g[3][2], real q[2], real nin[2]) {
+  int inside = 1; real bestpen = (real)1e30;
+  for (int k = 0; k < 3; k++) {
+    real l = sqrt(g[k][0] * g[k][0] + g[k][1] * g[k][1]);
+    if (l < (real)1e-12) continue;
+    real nk[2] = {-g[k][1] / l, g[k][0] / l};
+    real ww = 0;
+    for (int j = 0; j < 3; j++) if (j != k) ww += absr(nk[0] * g[j][0] + nk[1] * g[j][1]);
+    real s = d[0] * nk[0] + d[1] * nk[1];
+    real sep = absr(s) - ww;
+    if (sep > 0) inside = 0;
+    if (-sep < bestpen) { bestpen = -sep; real sg = s >= 0 ? (real)1 : (real)-1; nin[0] = sg * nk[0]; nin[1] = sg * nk[1]; }
+  }
+  if (inside) return 0;
+  real bd = (real)1e30;
+  for (int k = 0; k < 3; k++) {
+    real l2 = g[k][0] * g[k][0] + g[k][1] * g[k][1];
+    real nk[2] = {-g[k][1], g[k][0]};
+    for (int sgi = 0; sgi < 2; sgi++) {
+      real sg = sgi ? (real)-1 : (real)1, p0[2] = {d[0], d[1]};
+      for (int j = 0; j < 3; j++) if (j != k) { real c = nk[0] * g[j][0] + nk[1] * g[j][1]; real s = (c >= 0 ? (real)1 : (real)-1) * sg; p0[0] += s * g[j][0]; p0[1] += s * g[j][1]; }
+      real lam = l2 > (real)1e-24 ? clampr(-(p0[0] * g[k][0] + p0[1] * g[k][1]) / l2, -1, 1) : 0;
+      real c[2] = {p0[0] + lam * g[k][0], p0[1] + lam * g[k][1]};
+      real dd = c[0] * c[0] + c[1] * c[1];
+      if (dd < bd) { bd = dd; q[0] = c[0]; q[1] = c[1]; }
+    }
+  }
+  return 1;
+}
+
+DEVFN int collide_cyl_box(const real* c, const real* Rc, const real* sz, const real* b, const real* Rb, const real* e3, real margin, RawCon* out) {
+  real r = sz[0], h = sz[1];
+  real a[3] = {Rc[2], Rc[5], Rc[8]}, B[3][3], d[3];
+  for (int k = 0; k < 3; k++) { B[k][0] = Rb[k]; B[k][1] = Rb[3 + k]; B[k][2] = Rb[6 + k]; d[k] = b[k] - c[k]; }
+  real best = (real)1e30, n[3] = {0, 0, 0};
+  real cand[5][3]; int nc = 0;
+  for (int k = 0; k < 3; k++) { real s = dot3(B[k], d) >= 0 ? (real)1 : (real)-1; cand[nc][0] = s * B[k][0]; cand[nc][1] = s * B[k][1]; cand[nc][2] = s * B[k][2]; nc++; }
+  { real s = dot3(a, d) >= 0 ? (real)1 : (real)-1; cand[nc][0] = s * a[0]; cand[nc][1] = s * a[1]; cand[nc][2] = s * a[2]; nc++; }
+  {
+    real u[3] = {Rc[0], Rc[3], Rc[6]}, ww[3] = {Rc[1], Rc[4], Rc[7]};
+    real d2[2] = {dot3(d, u), dot3(d, ww)}, g[3][2], q[2] = {0, 0}, nin[2] = {0, 0};
+    for (int k = 0; k < 3; k++) { g[k][0] = e3[k] * dot3(B[k], u); g[k][1] = e3[k] * dot3(B[k], ww); }
+    if (zonotope_closest(d2, g, q, nin)) {
+      real l = sqrt(q[0] * q[0] + q[1] * q[1]);
+      if (l > (real)1e-12) { for (int k = 0; k < 3; k++) cand[nc][k] = (q[0] * u[k] + q[1] * ww[k]) / l; nc++; }
+    } else {
+      for (int k = 0; k < 3; k++) cand[nc][k] = nin[0] * u[k] + nin[1] * ww[k];
+      nc++;
+    }
+  }
+  for (int ci = 0; ci < nc; ci++) {
+    const real* nx = cand[ci];
+    real na = dot3(nx, a), perp = 1 - na * na;
+    real hc = h * absr(na) + r * sqrt(perp > 0 ? perp : 0);
+    real hb = e3[0] * absr(dot3(nx, B[0])) + e3[1] * absr(dot3(nx, B[1])) + e3[2] * absr(dot3(nx, B[2]));
+    real ov = hc + hb - dot3(nx, d);
+    if (ov < -margin) return 0;
+    if (ov < best - (real)1e-9) { best = ov; n[0] = nx[0]; n[1] = nx[1]; n[2] = nx[2]; }
+  }
+  const real EPS = (real)1e-4;
+  real na = dot3(n, a), pc[3];
+  int zero[3], nz = 0; real mm[3];
+  for (int k = 0; k < 3; k++) { mm[k] = -dot3(n, B[k]); zero[k] = absr(mm[k]) < EPS; nz += zero[k]; }
+  if (absr(na) > 1 - (real)1e-8) {
+    real s = na >= 0 ? (real)1 : (real)-1; for (int k = 0; k < 3; k++) pc[k] = c[k] + s * h * a[k];
+  } else if (absr(na) >= EPS) {
+    real s = na >= 0 ? (real)1 : (real)-1, pr[3];
+    for (int k = 0; k < 3; k++) pr[k] = n[k] - na * a[k];
+    real l = norm3(pr);
+    for (int k = 0; k < 3; k++) pc[k] = c[k] + s * h * a[k] + r * pr[k] / l;
+  } else {
+    real t0 = -h, t1 = h, base[3];
+    for (int k = 0; k < 3; k++) base[k] = c[k] + r * n[k] - b[k];
+    if (nz >= 1) {
+      for (int k = 0; k < 3; k++) if (zero[k]) {
+        real x0 = dot3(base, B[k]), dx = dot3(a, B[k]);
+        if (absr(dx) < (real)1e-12) continue;
+        real ta = (-e3[k] - x0) / dx, tb = (e3[k] - x0) / dx;
+        if (ta > tb) { real tmp = ta; ta = tb; tb = tmp; }
+        if (ta > t0) t0 = ta;
+        if (tb < t1) t1 = tb;
+      }
+      if (t0 > t1) { real mid = (real)0.5 * (t0 + t1); t0 = t1 = clampr(mid, -h, h); }
+    }
+    real ts;
+    if (nz == 2) ts = (real)0.5 * (t0 + t1);
+    else {
+      real v[3] = {0, 0, 0};
+      for (int k = 0; k < 3; k++) if (!zero[k]) { real s = mm[k] >= 0 ? (real)1 : (real)-1; for (int cc = 0; cc < 3; cc++) v[cc] += s * e3[k] * B[k][cc]; }
+      if (nz == 1) {
+        int ke = zero[0] ? 0 : (zero[1] ? 1 : 2);
+        real bb = dot3(a, B[ke]), w0[3] = {base[0] - v[0], base[1] - v[1], base[2] - v[2]};
+        real dd = dot3(a, w0), ee = dot3(B[ke], w0), den = 1 - bb * bb;
+        ts = den > (real)1e-12 ? (bb * ee - dd) / den : (real)0.5 * (t0 + t1);
+      } else {
+        real w0[3] = {v[0] - base[0], v[1] - base[1], v[2] - base[2]};
+        ts = dot3(w0, a);
+      }
+      ts = clampr(ts, t0, t1);
+    }
+    for (int k = 0; k < 3; k++) pc[k] = c[k] + r * n[k] + ts * a[k];
+  }
+  for (int k = 0; k < 3; k++) { out->pos[k] = pc[k] - (real)0.5 * best * n[k]; out->n[k] = n[k]; }
+  out->dist = -best;
+  return out->dist < margin;
+}
+
+DEVFN int collide_cyl_cyl(const real* c1, const real* R1, const real* s1, const real* c2, const real* R2, const real* s2, real margin, RawCon* out) {
+  real a1[3] = {R1[2], R1[5], R1[8]}, a2[3] = {R2[2], R2[5], R2[8]}, ww[3] = {c1[0] - c2[0], c1[1] - c2[1], c1[2] - c2[2]};
+  real b = dot3(a1, a2), d = dot3(a1, ww), e = dot3(a2, ww), den = 1 - b * b, t1, t2;
+  if (den > (real)1e-8) {
+    t1 = clampr((b * e - d) / den, -s1[1], s1[1]);
+    t2 = clampr(e + b * t1, -s2[1], s2[1]);
+    t1 = clampr(-d + b * t2, -s1[1], s1[1]);
+  } else {
+    real l2 = (-s2[1] - e) / b, h2 = (s2[1] - e) / b;
+    if (l2 > h2) { real tmp = l2; l2 = h2; h2 = tmp; }
+    real lo = maxr(-s1[1], l2), hi = minr(s1[1], h2);
+    t1 = lo > hi ? clampr((real)0.5 * (lo + hi), -s1[1], s1[1]) : (real)0.5 * (lo + hi);
+    t2 = clampr(e + b * t1, -s2[1], s2[1]);
+  }
+  real p1[3], dv[3];
+  for (int k = 0; k < 3; k++) { p1[k] = c1[k] + t1 * a1[k]; dv[k] = c2[k] + t2 * a2[k] - p1[k]; }
+  real l = norm3(dv), dist = l - s1[0] - s2[0];
+  if (dist >= margin || l < (real)1e-12) return 0;
+  for (int k = 0; k < 3; k++) { out->n[k] = dv[k] / l; out->pos[k] = p1[k] + out->n[k] * (s1[0] + (real)0.5 * dist); }
+  out->dist = dist;
+  return 1;
+}
+
+DEVFN void make_frame(real* f) {
+  real y[3] = {0, 0, 0};
+  if (f[1] < (real)0.5 && f[1] > (real)-0.5) y[1] = 1; else y[2] = 1;
+  real t = dot3(f, y);
+  y[0] -= t * f[0]; y[1] -= t * f[1]; y[2] -= t * f[2];
+  real l = 1 / norm3(y);
+  f[3] = y[0] * l; f[4] = y[1] * l; f[5] = y[2] * l;
+  cross3(f + 6, f, f + 3);
+}
+
+DEVFN void geom_pose(const Model& m, const Lay& L, const real* w, int g, real* p, real* R) {
+  const tab_t* gm = m.geom + D3_GEOM_W * g;
+  int li = (int)gm[1];
+  real gp[3] = {(real)gm[2], (real)gm[3], (real)gm[4]}, gR[9];
+  for (int k = 0; k < 9; k++) gR[k] = m.geomR[9 * g + k];
+  if (li < 0) { p[0] = gp[0]; p[1] = gp[1]; p[2] = gp[2]; for (int k = 0; k < 9; k++) R[k] = gR[k]; return; }
+  real o[3]; mat_vec3(o, w + L.xmat + 9 * li, gp);
+  for (int k = 0; k < 3; k++) p[k] = w[L.xpos + 3 * li + k] + o[k];
+  mat_mul3(R, w + L.xmat + 9 * li, gR);
+}
+
+// One lane per candidate pair; contact slots are assigned in pair order through a count table so the contact list is
+// deterministic.  Returns (all lanes) the number of contacts; sets the obstacle flag in misc.
+template <int G>
+DEVFN int collision(const Cx& cx, const Model& m, const Lay& L, real* w) {
+  RawCon rc[8];
+  int myn = 0, mypair = -1;
+  // NOTE: npair <= G is required for the single-pass scheme below (checked on the host); pairs beyond G use more passes.
+  int ntot = 0, obst = 0;
+  for (int base = 0; base < m.npair; base += G) {
+    int ip = base + cx.lane;
+    myn = 0; mypair = -1;
+    if (ip < m.npair) {
+      const tab_t* pr = m.pair + D3_PAIR_W * ip;
+      int g1 = (int)pr[0], g2 = (int)pr[1];
+      const tab_t *ga = m.geom + D3_GEOM_W * g1, *gb = m.geom + D3_GEOM_W * g2;
+      real p1[3], R1[9], p2[3], R2[9];
+      geom_pose(m, L, w, g1, p1, R1); geom_pose(m, L, w, g2, p2, R2);
+      real dc[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]}, margin = pr[15];
+      if (norm3(dc) <= (real)ga[12] + (real)gb[12] + margin) {
+        real s1[3] = {(real)ga[9], (real)ga[10], (real)ga[11]}, s2[3] = {(real)gb[9], (real)gb[10], (real)gb[11]};
+        int t1 = (int)ga[0], t2 = (int)gb[0];
+        if (t1 == D3G_BOX && t2 == D3G_BOX) myn = collide_box_box(p1, R1, s1, p2, R2, s2, margin, rc);
+        else if (t1 == D3G_CYLINDER && t2 == D3G_BOX) myn = collide_cyl_box(p1, R1, s1, p2, R2, s2, margin, rc);
+        else if (t1 == D3G_CYLINDER && t2 == D3G_CYLINDER) myn = collide_cyl_cyl(p1, R1, s1, p2, R2, s2, margin, rc);
+      }
+      mypair = ip;
+      w[L.ncon_pair + ip - base] = (real)myn;
+    }
+    gsync<G>(cx);
+    int cnt_here = m.npair - base < G ? m.npair - base : G;
+    if (mypair >= 0) {
+      int off = ntot;
+      for (int j = 0; j < ip - base; j++) off += (int)w[L.ncon_pair + j];
+      const tab_t* pr = m.pair + D3_PAIR_W * ip;
+      for (int i = 0; i < myn; i++) {
+        if (off + i >= m.maxcon) break;
+        real* c = w + L.con + D3_CON_W * (off + i);
+        c[0] = rc[i].pos[0]; c[1] = rc[i].pos[1]; c[2] = rc[i].pos[2];
+        c[3] = rc[i].n[0]; c[4] = rc[i].n[1]; c[5] = rc[i].n[2];
+        make_frame(c + 3);
+        c[12] = rc[i].dist; c[13] = (real)pr[15] - (real)pr[16]; c[14] = 0; c[15] = pr[2];
+        c[16] = pr[0]; c[17] = pr[1]; c[18] = (real)ip; c[19] = -1;
+      }
+      if (myn > 0 && (((int)pr[17]) & 1)) obst = 1;
+    }
+    for (int j = 0; j < cnt_here; j++) ntot += (int)w[L.ncon_pair + j];
+    gsync<G>(cx);
+  }
+  obst = gori<G>(cx, obst);
+  LANES(z, 1) {
+    w[L.misc + ST_OBST] = (real)obst;
+    if (ntot > m.maxcon) w[L.misc + ST_STATUS] = (real)(((int)w[L.misc + ST_STATUS]) | 2);
+  }
+  if (ntot > m.maxcon) ntot = m.maxcon;
+  return ntot;
+}
+
+// ------------------------------------------------------------------------------------------------ constraints
+DEVFN real impedance(const real* solimp, real pos, real margin) {
+  real dmin = solimp[0], dmax = solimp[1], width = solimp[2], mid = solimp[3], power = solimp[4];
+  if (width < (real)1e-15 || dmin == dmax) return (real)0.5 * (dmin + dmax);
+  real x = absr(pos - margin) / width;
+  if (x >= 1) return dmax;
+  if (x <= 0) return dmin;
+  real y;
+  if (power == 1) y = x;
+  else if (power == 2) y = x <= mid ? x * x / mid : 1 - (1 - x) * (1 - x) / (1 - mid);
+  else if (x <= mid) y = pow(x, power) / pow(mid, power - 1);
+  else y = 1 - pow(1 - x, power) / pow(1 - mid, power - 1);
+  return dmin + y * (dmax - dmin);
+}
+
+// Rows: joint limits first, then dim rows per active contact (elliptic).  Returns nefc (all lanes).
+template <int G>
+DEVFN int make_constraints(const Cx& cx, const Model& m, const Lay& L, real* w, int ncon) {
+  const int nv = m.nv;
+  // --- joint limit rows: deterministic order (link, side); every lane scans (cheap: <= 18 candidates)
+  int ne = 0;
+  for (int i = 0; i < m.nlink; i++) {
+    if (!m.l_limited[i] || m.l_jtype[i] == 2) continue;
+    const tab_t* Lk = m.link + D3_LINK_W * i;
+    real q = w[L.qpos + m.l_qadr[i]];
+    for (int side = 0; side < 2; side++) {
+      real dist = side == 0 ? q - (real)Lk[23] : (real)Lk[24] - q;
+      if (dist >= 0) continue;
+      if (ne < m.maxrow) {
+        LANES(d, nv) w[L.J + ne * nv + d] = 0;
+        LANES(z, 1) {
+          real solref[2] = {(real)m.ctrl[D3C_JNT_SOLREF], (real)m.ctrl[D3C_JNT_SOLREF + 1]}, solimp[5];
+          for (int k = 0; k < 5; k++) solimp[k] = m.ctrl[D3C_JNT_SOLIMP + k];
+          real imp = impedance(solimp, dist, 0);
+          real kk = 1 / (solimp[1] * solimp[1] * solref[0] * solref[0] * solref[1] * solref[1]), bb = 2 / (solimp[1] * solref[0]);
+          real sg = side == 0 ? (real)1 : (real)-1;
+          real Rv = maxr((real)1e-15, (1 - imp) / imp * (real)Lk[27]);
+          w[L.D + ne] = 1 / Rv;
+          w[L.aref + ne] = -bb * sg * w[L.qvel + m.l_dadr[i]] - kk * imp * dist;
+          w[L.etype + ne] = 0; w[L.econ + ne] = -1;
+        }
+        gsync<G>(cx);
+        LANES(z, 1) w[L.J + ne * nv + m.l_dadr[i]] = side == 0 ? (real)1 : (real)-1;
+        ne++;
+      } else { LANES(z, 1) w[L.misc + ST_STATUS] = (real)(((int)w[L.misc + ST_STATUS]) | 2); }
+    }
+  }
+  // --- contact rows: row0 by prefix over contact dims (every lane computes the same prefix)
+  int row = ne;
+  for (int c = 0; c < ncon; c++) {
+    real* cc = w + L.con + D3_CON_W * c;
+    int dim = (int)cc[15];
+    int active = cc[12] < cc[13];
+    if (active && row + dim <= m.maxrow) { LANES(z, 1) cc[19] = (real)row; row += dim; }
+    else { LANES(z, 1) { cc[19] = -1; if (active) w[L.misc + ST_STATUS] = (real)(((int)w[L.misc + ST_STATUS]) | 2); } }
+  }
+  gsync<G>(cx);
+  const real impratio = m.ctrl[D3C_IMPRATIO];
+  // Jacobian rows: one (contact, dof) item per lane step
+  LANES(item, ncon * nv) {
+    int c = item / nv, d = item - c * nv;
+    const real* cc = w + L.con + D3_CON_W * c;
+    int row0 = (int)cc[19];
+    if (row0 < 0) continue;
+    int dim = (int)cc[15];
+    int l1 = (int)m.geom[D3_GEOM_W * (int)cc[16] + 1], l2 = (int)m.geom[D3_GEOM_W * (int)cc[17] + 1];
+    int dl = m.d_link[d];
+    int in1 = l1 >= 0 && ((m.l_anc[l1] >> dl) & 1u), in2 = l2 >= 0 && ((m.l_anc[l2] >> dl) & 1u);
+    real jd[3] = {0, 0, 0}, jr[3] = {0, 0, 0};
+    if (in1 != in2) {
+      const real* S = w + L.S + 6 * d;
+      const real* pr = w + L.xpos + 3 * m.l_ref[dl];
+      real rr[3] = {cc[0] - pr[0], cc[1] - pr[1], cc[2] - pr[2]}, wxr[3];
+      cross3(wxr, S, rr);
+      real sg = in2 ? (real)1 : (real)-1;
+      jd[0] = sg * (S[3] + wxr[0]); jd[1] = sg * (S[4] + wxr[1]); jd[2] = sg * (S[5] + wxr[2]);
+      jr[0] = sg * S[0]; jr[1] = sg * S[1]; jr[2] = sg * S[2];
+    }
+    for (int r = 0; r < dim; r++) {
+      const real* ax = cc + 3 + 3 * (r < 3 ? r : 0);
+      w[L.J + (row0 + r) * nv + d] = r < 3 ? dot3(ax, jd) : dot3(ax, jr);
+    }
+  }
+  gsync<G>(cx);
+  // per-contact reference acceleration / regularisation
+  LANES(c, ncon) {
+    real* cc = w + L.con + D3_CON_W * c;
+    int row0 = (int)cc[19];
+    if (row0 < 0) continue;
+    int dim = (int)cc[15];
+    const tab_t* pr = m.pair + D3_PAIR_W * (int)cc[18];
+    real solref[2] = {(real)pr[8], (real)pr[9]}, solimp[5] = {(real)pr[10], (real)pr[11], (real)pr[12], (real)pr[13], (real)pr[14]};
+    real fr[5] = {(real)pr[3], (real)pr[4], (real)pr[5], (real)pr[6], (real)pr[7]};
+    real imp = impedance(solimp, cc[12], cc[13]);
+    real kk = 1 / (solimp[1] * solimp[1] * solref[0] * solref[0] * solref[1] * solref[1]), bb = 2 / (solimp[1] * solref[0]);
+    real tran = (real)m.geom[D3_GEOM_W * (int)cc[16] + 13] + (real)m.geom[D3_GEOM_W * (int)cc[17] + 13];
+    real R0 = maxr((real)1e-15, (1 - imp) / imp * tran), R1 = R0 / impratio;
+    cc[14] = fr[0] * sqrt(R1 / R0);
+    for (int r = 0; r < dim; r++) {
+      real Rv = r == 0 ? R0 : (r == 1 ? R1 : R1 * fr[0] * fr[0] / (fr[r - 1] * fr[r - 1]));
+      real vel = 0;
+      for (int d = 0; d < nv; d++) vel += w[L.J + (row0 + r) * nv + d] * w[L.qvel + d];
+      w[L.D + row0 + r] = 1 / Rv;
+      w[L.aref + row0 + r] = -bb * vel - (r == 0 ? kk * imp * (cc[12] - cc[13]) : 0);
+      w[L.etype + row0 + r] = r == 0 ? 1 : 2; w[L.econ + row0 + r] = (real)c;
+    }
+  }
+  gsync<G>(cx);
+  return row;
+}
+
+// Evaluate the constraint cost at jar (workspace array `jar_off`): forces -> frc_off, optional Hessian pieces
+// (hd per row, 3x3/4x4 cone block per contact in hb; hb[...][0] < -0.5e30 marks "no cone block").
+// Returns the group-wide cost.  One lane per limit row / per contact.
+template <int G, bool HESS>
+DEVFN real constraint_eval(const Cx& cx, const Model& m, const Lay& L, real* w, int ne, int ncon, int jar_off, int frc_off, int hd_off, int hb_off) {
+  real cost = 0;
+  LANES(i, ne) {
+    if (w[L.etype + i] != 0) continue;
+    real j = w[jar_off + i], Dv = w[L.D + i];
+    if (j < 0) { cost += (real)0.5 * Dv * j * j; w[frc_off + i] = -Dv * j; if (HESS) w[hd_off + i] = Dv; }
+    else { w[frc_off + i] = 0; if (HESS) w[hd_off + i] = 0; }
+  }
+  LANES(c, ncon) {
+    const real* cc = w + L.con + D3_CON_W * c;
+    int i = (int)cc[19];
+    if (i < 0) continue;
+    int dim = (int)cc[15];
+    const tab_t* pr = m.pair + D3_PAIR_W * (int)cc[18];
+    real mu = cc[14], U[4], fr[3] = {(real)pr[3], (real)pr[4], (real)pr[5]}, T = 0;
+    U[0] = w[jar_off + i] * mu;
+    for (int j = 1; j < dim; j++) { U[j] = w[jar_off + i + j] * fr[j - 1]; T += U[j] * U[j]; }
+    T = sqrt(T);
+    real N = U[0];
+    if (HESS) w[hb_off + 9 * c] = (real)-1e30;
+    if (N >= mu * T || (T <= 0 && N >= 0)) {
+      for (int j = 0; j < dim; j++) { w[frc_off + i + j] = 0; if (HESS) w[hd_off + i + j] = 0; }
+    } else if (mu * N + T <= 0 || (T <= 0 && N < 0)) {
+      for (int j = 0; j < dim; j++) { real Dv = w[L.D + i + j], jj = w[jar_off + i + j]; cost += (real)0.5 * Dv * jj * jj; w[frc_off + i + j] = -Dv * jj; if (HESS) w[hd_off + i + j] = Dv; }
+    } else {
+      real Dm = w[L.D + i] / maxr((real)1e-15, mu * mu * (1 + mu * mu)), NmT = N - mu * T;
+      cost += (real)0.5 * Dm * NmT * NmT;
+      real f0 = -Dm * NmT * mu;
+      w[frc_off + i] = f0;
+      for (int j = 1; j < dim; j++) w[frc_off + i + j] = -f0 / T * U[j] * fr[j - 1];
+      if (HESS) {
+        // condim 3 only stores a 3x3 block (condim 4 contacts are not generated by the rod tasks)
+        real g[3]; g[0] = mu; g[1] = -mu * fr[0] * U[1] / T; g[2] = -mu * fr[1] * U[2] / T;
+        for (int a = 0; a < 3; a++) for (int b2 = 0; b2 < 3; b2++) {
+          real v = g[a] * g[b2];
+          if (a > 0 && b2 > 0) v -= mu * NmT / T * fr[a - 1] * fr[b2 - 1] * ((a == b2 ? (real)1 : (real)0) - U[a] * U[b2] / (T * T));
+          w[hb_off + 9 * c + 3 * a + b2] = Dm * v;
+        }
+      }
+    }
+  }
+  return gsum<G>(cx, cost);
+}
+
+// Dense in-place Cholesky of the n x n matrix at `A` (lower), lane-parallel right-looking.  The strict lower triangle
+// receives L; the diagonal keeps the pivots d_k = L_kk^2 (so no lane ever rewrites an entry the others still read).
+// Returns 0 ok / 1 not positive definite.
+template <int G>
+DEVFN int chol_factor(const Cx& cx, real* A, int n) {
+  int bad = 0;
+  for (int k = 0; k < n; k++) {
+    real dkk = A[k * n + k];
+    if (!(dkk > 0)) { bad = 1; dkk = 1; }
+    real inv = 1 / sqrt(dkk);
+    int rem = n - k - 1;
+    LANES(i, rem) { A[(k + 1 + i) * n + k] *= inv; }
+    gsync<G>(cx);
+    LANES(e, rem * (rem + 1) / 2) {
+      // unrank e -> (i >= j) in the trailing block
+      int i = (int)((sqrt((real)(8 * e + 1)) - 1) * (real)0.5);
+      while (i * (i + 1) / 2 > e) i--;
+      while ((i + 1) * (i + 2) / 2 <= e) i++;
+      int j = e - i * (i + 1) / 2;
+      A[(k + 1 + i) * n + (k + 1 + j)] -= A[(k + 1 + i) * n + k] * A[(k + 1 + j) * n + k];
+    }
+    gsync<G>(cx);
+  }
+  return bad;
+}
+// Solve L L^T x = b in place.  Element x[i] is owned by lane i % G in both sweeps (each lane only ever reads entries
+// it wrote itself), so the only cross-lane traffic is the shuffle reduction of the dot products.
+template <int G>
+DEVFN void chol_solve(const Cx& cx, const real* A, int n, real* x) {
+  for (int i = 0; i < n; i++) {
+    real s = 0;
+    LANES(k, i) s += A[i * n + k] * x[k];
+    s = gsum<G>(cx, s);
+    if ((i % G) == cx.lane) x[i] = (x[i] - s) / sqrt(A[i * n + i]);
+  }
+  for (int i = n - 1; i >= 0; i--) {
+    real s = 0;
+    LANES(k, n) if (k > i) s += A[k * n + i] * x[k];
+    s = gsum<G>(cx, s);
+    if ((i % G) == cx.lane) x[i] = (x[i] - s) / sqrt(A[i * n + i]);
+  }
+  gsync<G>(cx);
+}
+
+// Newton solver on the primal problem: result in qacc / frcE / qfrc_c.  Returns iterations.
+template <int G>
+DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w, int ne, int ncon, real tol, int max_iter) {
+  const int nv = m.nv;
+  if (ne == 0) {
+    LANES(d, nv) { w[L.qacc + d] = w[L.qacc_smooth + d]; w[L.qfrc_c + d] = 0; }
+    gsync<G>(cx);
+    return 0;
+  }
+  const real scale = 1 / ((real)m.ctrl[D3C_MEANINERTIA] * (real)(nv > 1 ? nv : 1));
+  // ---- warm start: cheaper of qacc_warmstart and qacc_smooth
+  real cw, cs;
+  {
+    LANES(i, ne) { real s = -w[L.aref + i]; for (int d = 0; d < nv; d++) s += w[L.J + i * nv + d] * w[L.warm + d]; w[L.jar + i] = s; }
+    gsync<G>(cx);
+    cw = constraint_eval<G, false>(cx, m, L, w, ne, ncon, L.jar, L.frcE, 0, 0);
+    real part = 0;
+    LANES(d, nv) { real s = 0; for (int k = 0; k < nv; k++) s += w[L.M + d * nv + k] * (w[L.warm + k] - w[L.qacc_smooth + k]); part += (real)0.5 * (w[L.warm + d] - w[L.qacc_smooth + d]) * s; }
+    cw += gsum<G>(cx, part);
+    gsync<G>(cx);
+    LANES(i, ne) { real s = -w[L.aref + i]; for (int d = 0; d < nv; d++) s += w[L.J + i * nv + d] * w[L.qacc_smooth + d]; w[L.jar + i] = s; }
+    gsync<G>(cx);
+    cs = constraint_eval<G, false>(cx, m, L, w, ne, ncon, L.jar, L.frcE, 0, 0);
+    gsync<G>(cx);
+    LANES(d, nv) w[L.qacc + d] = cw < cs ? w[L.warm + d] : w[L.qacc_smooth + d];
+    gsync<G>(cx);
+  }
+  real cost = 0, oldcost = 0;
+  int iter = 0;
+  for (; iter < max_iter; iter++) {
+    LANES(i, ne) { real s = -w[L.aref + i]; for (int d = 0; d < nv; d++) s += w[L.J + i * nv + d] * w[L.qacc + d]; w[L.jar + i] = s; }
+    gsync<G>(cx);
+    oldcost = cost;
+    cost = constraint_eval<G, true>(cx, m, L, w, ne, ncon, L.jar, L.frcE, L.hd, L.hb);
+    real part = 0;
+    LANES(d, nv) {
+      real s = 0;
+      for (int k = 0; k < nv; k++) s += w[L.M + d * nv + k] * (w[L.qacc + k] - w[L.qacc_smooth + k]);
+      w[L.Ma + d] = s; part += (real)0.5 * (w[L.qacc + d] - w[L.qacc_smooth + d]) * s;
+    }
+    cost += gsum<G>(cx, part);
+    gsync<G>(cx);
+    real g2 = 0;
+    LANES(d, nv) { real s = w[L.Ma + d]; for (int i = 0; i < ne; i++) s -= w[L.J + i * nv + d] * w[L.frcE + i]; w[L.grad + d] = s; g2 += s * s; }
+    real gn = sqrt(gsum<G>(cx, g2));
+    gsync<G>(cx);
+#ifdef D3IL_DEBUG_SOLVER
+    printf("  newton it %d cost %.12g gn %.6g\n", iter, (double)cost, (double)gn);
+#endif
+    if (scale * gn < tol) break;
+    if (iter > 0 && scale * (oldcost - cost) < tol * (real)1e-3) break;
+    // ---- H = M + J^T Hc J  (dense lower, lane per entry)
+    LANES(e, nv * (nv + 1) / 2) {
+      int i = (int)((sqrt((real)(8 * e + 1)) - 1) * (real)0.5);
+      while (i * (i + 1) / 2 > e) i--;
+      while ((i + 1) * (i + 2) / 2 <= e) i++;
+      int j = e - i * (i + 1) / 2;
+      real s = w[L.M + i * nv + j];
+      for (int r = 0; r < ne; r++) {
+        real ji = w[L.J + r * nv + i];
+        if (ji == 0) continue;
+        int et = (int)w[L.etype + r];
+        int c = (int)w[L.econ + r];
+        if (et != 0 && w[L.hb + 9 * c] > (real)-0.5e30) {
+          int r0 = (int)w[L.con + D3_CON_W * c + 19], a = r - r0;
+          real t = 0;
+          for (int b2 = 0; b2 < 3; b2++) t += w[L.hb + 9 * c + 3 * a + b2] * w[L.J + (r0 + b2) * nv + j];
+          s += ji * t;
+        } else s += ji * w[L.hd + r] * w[L.J + r * nv + j];
+      }
+      w[L.H + i * nv + j] = s;
+    }
+    gsync<G>(cx);
+    if (chol_factor<G>(cx, w + L.H, nv)) { LANES(z, 1) w[L.misc + ST_STATUS] = (real)(((int)w[L.misc + ST_STATUS]) | 4); break; }
+    LANES(d, nv) w[L.pvec + d] = -w[L.grad + d];
+    gsync<G>(cx);
+    chol_solve<G>(cx, w + L.H, nv, w + L.pvec);
+    // ---- exact line search (safeguarded 1-D Newton), quantities reduced across lanes
+    LANES(i, ne) { real s = 0; for (int d = 0; d < nv; d++) s += w[L.J + i * nv + d] * w[L.pvec + d]; w[L.Jp + i] = s; }
+    real a1 = 0, a2 = 0, a3 = 0;
+    LANES(d, nv) {
+      real s = 0;
+      for (int k = 0; k < nv; k++) s += w[L.M + d * nv + k] * w[L.pvec + k];
+      a1 += w[L.pvec + d] * s; a2 += w[L.pvec + d] * w[L.Ma + d]; a3 += w[L.grad + d] * w[L.pvec + d];
+    }
+    real pMp = gsum<G>(cx, a1), pMa = gsum<G>(cx, a2), d0 = gsum<G>(cx, a3);
+    gsync<G>(cx);
+    real lo = 0, hi = -1, alpha = 1, dlo = d0, dhi = 0;
+    // tmpv doubles as jar(alpha) (sized nv; we need ne) -> reuse hd as scratch is unsafe, so evaluate in place on frcE/H rows:
+    // jar(alpha) is written over L.hd (not needed any more this iteration), forces to L.frcE after the loop.
+    for (int ls = 0; ls < 20; ls++) {
+      LANES(i, ne) w[L.hd + i] = w[L.jar + i] + alpha * w[L.Jp + i];
+      gsync<G>(cx);
+      // first and second directional derivatives from forces / cone blocks at jar(alpha)
+      real d1p = 0, d2p = 0;
+      LANES(i, ne) {
+        if (w[L.etype + i] != 0) continue;
+        real j = w[L.hd + i];
+        if (j < 0) { d1p += w[L.D + i] * j * w[L.Jp + i]; d2p += w[L.D + i] * w[L.Jp + i] * w[L.Jp + i]; }
+      }
+      LANES(c, ncon) {
+        const real* cc = w + L.con + D3_CON_W * c;
+        int i = (int)cc[19];
+        if (i < 0) continue;
+        int dim = (int)cc[15];
+        const tab_t* pr = m.pair + D3_PAIR_W * (int)cc[18];
+        real mu = cc[14], U[4], V[4], fr[3] = {(real)pr[3], (real)pr[4], (real)pr[5]}, T = 0;
+        U[0] = w[L.hd + i] * mu; V[0] = w[L.Jp + i] * mu;
+        for (int j = 1; j < dim; j++) { U[j] = w[L.hd + i + j] * fr[j - 1]; V[j] = w[L.Jp + i + j] * fr[j - 1]; T += U[j] * U[j]; }
+        T = sqrt(T);
+        real N = U[0];
+        if (N >= mu * T || (T <= 0 && N >= 0)) {
+        } else if (mu * N + T <= 0 || (T <= 0 && N < 0)) {
+          for (int j = 0; j < dim; j++) { real Dv = w[L.D + i + j]; d1p += Dv * w[L.hd + i + j] * w[L.Jp + i + j]; d2p += Dv * w[L.Jp + i + j] * w[L.Jp + i + j]; }
+        } else {
+          // s = 0.5 Dm (N - mu T)^2 along the line: dN = V0, dT = (U_t . V_t)/T, d2T = (|V_t|^2 - dT^2)/T
+          real Dm = w[L.D + i] / maxr((real)1e-15, mu * mu * (1 + mu * mu)), NmT = N - mu * T;
+          real UV = 0, VV = 0;
+          for (int j = 1; j < dim; j++) { UV += U[j] * V[j]; VV += V[j] * V[j]; }
+          real dT = UV / T, d2T = (VV - dT * dT) / T, dn = V[0] - mu * dT;
+          d1p += Dm * NmT * dn;
+          d2p += Dm * (dn * dn - NmT * mu * d2T);
+        }
+      }
+      real d1 = gsum<G>(cx, d1p) + pMa + alpha * pMp, d2 = gsum<G>(cx, d2p) + pMp;
+      gsync<G>(cx);
+#ifdef D3IL_DEBUG_SOLVER
+      printf("      ls %d alpha %.9g d1 %.6g d2 %.6g lo %.6g hi %.6g\n", ls, (double)alpha, (double)d1, (double)d2, (double)lo, (double)hi);
+#endif
+      if (absr(d1) <= (real)1e-3 * absr(d0)) break;
+      if (d1 < 0) { lo = alpha; dlo = d1; } else { hi = alpha; dhi = d1; }
+      real next = alpha - d1 / d2;
+      if (hi < 0) { if (!(next > lo)) next = 2 * alpha; }
+      else {
+        // bracketed: Newton step unless it hugs an end point (it can cycle across a kink of phi'), then false position
+        real wd = hi - lo;
+        if (!(next > lo + (real)0.05 * wd && next < hi - (real)0.05 * wd)) {
+          real sec = lo + wd * (-dlo) / (dhi - dlo);
+          next = clampr(sec, lo + (real)0.05 * wd, hi - (real)0.05 * wd);
+        }
+        if (wd < (real)1e-6 * (1 + hi)) { alpha = next; break; }
+      }
+      alpha = next;
+    }
+#ifdef D3IL_DEBUG_SOLVER
+    printf("    ls alpha %.9g lo %.6g hi %.6g d0 %.6g\n", (double)alpha, (double)lo, (double)hi, (double)d0);
+    for (int t = 0; t <= 4; t++) {
+      real al = alpha * t / 4;
+      for (int i = 0; i < ne; i++) w[L.hd + i] = w[L.jar + i] + al * w[L.Jp + i];
+      real cc_ = constraint_eval<G, false>(cx, m, L, w, ne, ncon, L.hd, L.tmpv + 0 * 0 + 0, 0, 0);
+      printf("      phi(%.4g) = %.10g (constraint %.10g)\n", (double)al, (double)(cc_ + al * pMa + 0.5 * al * al * pMp), (double)cc_);
+    }
+#endif
+    LANES(d, nv) w[L.qacc + d] += alpha * w[L.pvec + d];
+    gsync<G>(cx);
+  }
+  if (iter >= max_iter) {
+    // final force evaluation at the last iterate
+    LANES(i, ne) { real s = -w[L.aref + i]; for (int d = 0; d < nv; d++) s += w[L.J + i * nv + d] * w[L.qacc + d]; w[L.jar + i] = s; }
+    gsync<G>(cx);
+    constraint_eval<G, false>(cx, m, L, w, ne, ncon, L.jar, L.frcE, 0, 0);
+    gsync<G>(cx);
+  }
+  LANES(d, nv) { real s = 0; for (int i = 0; i < ne; i++) s += w[L.J + i * nv + d] * w[L.frcE + i]; w[L.qfrc_c + d] = s; }
+  gsync<G>(cx);
+  return iter;
+}
+
+// ------------------------------------------------------------------------------------------------ one physics tick
+// jt_q / jt_qd: joint set-point for this tick (from the IK kernel in Cartesian mode, or the held pose after reset).
+template <int G>
+DEVFN void physics_tick(const Cx& cx, const Model& m, const Lay& L, real* w, const real* jt_q, const real* jt_qlo, const real* jt_qd, real tol, int max_iter) {
+  const int nv = m.nv;
+  const real h = m.ctrl[D3C_DT];
+  // --- MjRobot.prepare_step: joint PD + stale-bias gravity compensation, finger law (Robots.py:441-476), actuator clamp
+  LANES(k, D3_NARM) {
+    // joint angles and their set-points are two-float numbers: the difference of the high words is exact (Sterbenz)
+    real perr = (jt_q[k] - w[L.qpos + k]) + (jt_qlo[k] - w[L.qlo + k]);
+    real tau = (real)m.ctrl[D3C_PD_P + k] * perr + (real)m.ctrl[D3C_PD_D + k] * (jt_qd[k] - w[L.qvel + k]) + w[L.bias_prev + k];
+    real fr = m.link[D3_LINK_W * k + 26];
+    w[L.act + k] = clampr(tau, -fr, fr);
+  }
+  LANES(k, 2) {
+    real w0 = w[L.qpos + 7], w1 = w[L.qpos + 8], mean = (real)0.5 * (w0 + w1), wk = k ? w1 : w0, vk = w[L.qvel + 7 + k];
+    real set = w[L.misc + ST_GRIP_SET], f = 500 * (mean - wk), g;
+    if (mean - set > (real)0.005) g = w[L.misc + ST_GRASP] != 0 ? (real)-20 : 10 * ((real)-0.2 - vk);
+    else g = clampr(500 * (set - wk) - 10 * vk, -5, 5);
+    real fr = m.link[D3_LINK_W * (7 + k) + 26];
+    w[L.act + 7 + k] = clampr(f + g, -fr, fr);
+  }
+  // --- mj_step: position-dependent stage
+  kinematics<G>(cx, m, L, w);
+  // stale-by-one-tick tcp pose: body 'tcp' hangs off link 7 (index 6)
+  LANES(z, 1) {
+    real o[3], tp[3] = {(real)m.ctrl[D3C_TCP_POS], (real)m.ctrl[D3C_TCP_POS + 1], (real)m.ctrl[D3C_TCP_POS + 2]};
+    real tq[4] = {(real)m.ctrl[D3C_TCP_QUAT], (real)m.ctrl[D3C_TCP_QUAT + 1], (real)m.ctrl[D3C_TCP_QUAT + 2], (real)m.ctrl[D3C_TCP_QUAT + 3]}, Rt[9], R[9];
+    mat_vec3(o, w + L.xmat + 54, tp);
+    for (int k = 0; k < 3; k++) w[L.tcp + k] = w[L.xpos + 18 + k] + o[k];
+    quat2mat(Rt, tq); mat_mul3(R, w + L.xmat + 54, Rt); mat2quat(w + L.tcp + 3, R);
+  }
+  LANES(e, nv * nv) w[L.M + e] = 0;
+  gsync<G>(cx);
+  dynamics<G>(cx, m, L, w);
+  int ncon = collision<G>(cx, m, L, w);
+  int ne = make_constraints<G>(cx, m, L, w, ncon);
+  // --- smooth dynamics
+  LANES(d, nv) {
+    int li = m.d_link[d];
+    real passive = m.l_jtype[li] == 2 ? (real)0 : -(real)m.link[D3_LINK_W * li + 25] * w[L.qvel + d];
+    real act = d < D3_NROB ? w[L.act + d] : (real)0;
+    real f = passive - w[L.bias + d] + act;
+    w[L.qfrc_smooth + d] = f; w[L.qacc_smooth + d] = f;
+  }
+  LANES(e, nv * nv) w[L.Lm + e] = w[L.M + e];
+  gsync<G>(cx);
+  if (chol_factor<G>(cx, w + L.Lm, nv)) { LANES(z, 1) w[L.misc + ST_STATUS] = (real)(((int)w[L.misc + ST_STATUS]) | 1); }
+  chol_solve<G>(cx, w + L.Lm, nv, w + L.qacc_smooth);
+  solve_constraints<G>(cx, m, L, w, ne, ncon, tol, max_iter);
+  LANES(d, nv) w[L.warm + d] = w[L.qacc + d];
+  LANES(k, D3_NROB) w[L.bias_prev + k] = w[L.bias + k];
+  // --- mj_Euler with implicit joint damping: (M + h B) qacc* = qfrc_smooth + qfrc_constraint
+  LANES(e, nv * nv) w[L.Lm + e] = w[L.M + e];
+  gsync<G>(cx);
+  LANES(d, nv) {
+    int li = m.d_link[d];
+    if (m.l_jtype[li] != 2) w[L.Lm + d * nv + d] += h * (real)m.link[D3_LINK_W * li + 25];
+    w[L.tmpv + d] = w[L.qfrc_smooth + d] + w[L.qfrc_c + d];
+  }
+  gsync<G>(cx);
+  chol_factor<G>(cx, w + L.Lm, nv);
+  chol_solve<G>(cx, w + L.Lm, nv, w + L.tmpv);
+  LANES(d, nv) w[L.qvel + d] += h * w[L.tmpv + d];
+  gsync<G>(cx);
+  LANES(i, m.nlink) {
+    if (m.l_jtype[i] != 2) {
+      // compensated (Kahan) integration of the robot joint angles; links 0..8 are the robot, qadr == link index
+      real hi = w[L.qpos + m.l_qadr[i]], t = h * w[L.qvel + m.l_dadr[i]] + w[L.qlo + i], sres = hi + t;
+      w[L.qlo + i] = t - (sres - hi); w[L.qpos + m.l_qadr[i]] = sres;
+      continue;
+    }
+    real* q = w + L.qpos + m.l_qadr[i]; const real* v = w + L.qvel + m.l_dadr[i];
+    q[0] += h * v[0]; q[1] += h * v[1]; q[2] += h * v[2];
+    real wn = norm3(v + 3), ang = wn * h;
+    if (ang > 0) {
+      real s = sin((real)0.5 * ang) / wn, c = cos((real)0.5 * ang);
+      real a0 = q[3], a1 = q[4], a2 = q[5], a3 = q[6], b1 = s * v[3], b2 = s * v[4], b3 = s * v[5];
+      real r0 = a0 * c - a1 * b1 - a2 * b2 - a3 * b3, r1 = a0 * b1 + a1 * c + a2 * b3 - a3 * b2;
+      real r2 = a0 * b2 - a1 * b3 + a2 * c + a3 * b1, r3 = a0 * b3 + a1 * b2 - a2 * b1 + a3 * c;
+      real n = 1 / sqrt(r0 * r0 + r1 * r1 + r2 * r2 + r3 * r3);
+      q[3] = r0 * n; q[4] = r1 * n; q[5] = r2 * n; q[6] = r3 * n;
+    }
+  }
+  gsync<G>(cx);
+}

@@ -1,0 +1,286 @@
+// d3il_env.cuh — env-level logic on top of d3il_core.cuh: the Cartesian-impedance IK reference generator (one thread
+// per env), Gym reset/step bookkeeping, observations, termination and mode logic for the compiled tasks.
+//
+// Reference restated (all under environments/d3il/): controllers/IKControllers.py:163-323 (a5),
+// core/Model.py:37-66 (a6), gyms/gym_env_wrapper.py:45-137 (a2), envs/gym_pushing_env/.../pushing.py:255-488,
+// envs/gym_avoiding_env/.../avoiding.py:117-262 (a10-a12).  Dual-compilable like the core (see header there).
+#pragma once
+#include "d3il_core.cuh"
+
+// ------------------------------------------------------------------------------------------------ IK reference (a5/a6)
+// Per-env controller state.  The joint reference `q` is integrated in double (increments of 1e-3 * qd are below
+// fp32 resolution at |q| ~ 2.5 rad — SURVEY §7 hard part 2); everything else is fp32.
+struct IkState {
+  double q[D3_NARM];
+  real des_pos[3], des_quat[4];
+  real jt_q[D3_NARM], jt_qlo[D3_NARM], jt_qd[D3_NARM];    // last joint set-point handed to the PD loop (q as two floats)
+  int valid;
+};
+
+// The whole IK reference runs in fp64 (B200 has a 1:2 fp64 pipe; this is ~0.6 MFLOP per env step on a path that is
+// otherwise fp32): with fp32 forward kinematics the 1e-7 m position noise is amplified by gain/dt into ~1e-3 N m of PD
+// torque noise, which is what dominated the kernel-vs-oracle velocity error.
+typedef double ikr;
+DEVFN void ik_cross3(ikr* o, const ikr* a, const ikr* b) {
+  ikr x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+DEVFN void ik_mat_vec3(ikr* o, const ikr* R, const ikr* v) {
+  ikr x = R[0] * v[0] + R[1] * v[1] + R[2] * v[2], y = R[3] * v[0] + R[4] * v[1] + R[5] * v[2], z = R[6] * v[0] + R[7] * v[1] + R[8] * v[2];
+  o[0] = x; o[1] = y; o[2] = z;
+}
+DEVFN void ik_mat_mul3(ikr* o, const ikr* A, const ikr* B) {
+  ikr t[9];
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) t[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+  for (int i = 0; i < 9; i++) o[i] = t[i];
+}
+DEVFN void ik_mat2quat(ikr* q, const ikr* R) {
+  ikr t = R[0] + R[4] + R[8];
+  if (t > 0) { ikr s = sqrt(t + 1) * 2; q[0] = 0.25 * s; q[1] = (R[7] - R[5]) / s; q[2] = (R[2] - R[6]) / s; q[3] = (R[3] - R[1]) / s; }
+  else if (R[0] > R[4] && R[0] > R[8]) { ikr s = sqrt(1 + R[0] - R[4] - R[8]) * 2; q[0] = (R[7] - R[5]) / s; q[1] = 0.25 * s; q[2] = (R[1] + R[3]) / s; q[3] = (R[2] + R[6]) / s; }
+  else if (R[4] > R[8]) { ikr s = sqrt(1 + R[4] - R[0] - R[8]) * 2; q[0] = (R[2] - R[6]) / s; q[1] = (R[1] + R[3]) / s; q[2] = 0.25 * s; q[3] = (R[5] + R[7]) / s; }
+  else { ikr s = sqrt(1 + R[8] - R[0] - R[4]) * 2; q[0] = (R[3] - R[1]) / s; q[1] = (R[2] + R[6]) / s; q[2] = (R[5] + R[7]) / s; q[3] = 0.25 * s; }
+  ikr n = 1 / sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  q[0] *= n; q[1] *= n; q[2] *= n; q[3] *= n;
+}
+DEVFN ikr ik_clamp(ikr x, ikr lo, ikr hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
+DEVFN void ik_fk(const tab_t* C, const ikr* q, ikr* pos, ikr* quat, ikr* J) {
+  ikr p[3] = {0, 0, 0}, R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, org[7][3], axs[7][3];
+  for (int i = 0; i < 7; i++) {
+    const tab_t* o = C + D3C_IK_ORIGIN + 12 * i;
+    ikr ov[3] = {(ikr)o[0], (ikr)o[1], (ikr)o[2]}, oR[9], t[3];
+    for (int k = 0; k < 9; k++) oR[k] = o[3 + k];
+    ik_mat_vec3(t, R, ov); p[0] += t[0]; p[1] += t[1]; p[2] += t[2];
+    ik_mat_mul3(R, R, oR);
+    ikr c = cos(q[i]), s = sin(q[i]), Rz[9] = {c, -s, 0, s, c, 0, 0, 0, 1};
+    ik_mat_mul3(R, R, Rz);
+    org[i][0] = p[0]; org[i][1] = p[1]; org[i][2] = p[2];
+    axs[i][0] = R[2]; axs[i][1] = R[5]; axs[i][2] = R[8];
+  }
+  const tab_t* o = C + D3C_IK_EE;
+  ikr ov[3] = {(ikr)o[0], (ikr)o[1], (ikr)o[2]}, oR[9], t[3], Re[9];
+  for (int k = 0; k < 9; k++) oR[k] = o[3 + k];
+  ik_mat_vec3(t, R, ov);
+  pos[0] = p[0] + t[0]; pos[1] = p[1] + t[1]; pos[2] = p[2] + t[2];
+  ik_mat_mul3(Re, R, oR); ik_mat2quat(quat, Re);
+  for (int i = 0; i < 7; i++) {
+    ikr r[3] = {pos[0] - org[i][0], pos[1] - org[i][1], pos[2] - org[i][2]}, l[3];
+    ik_cross3(l, axs[i], r);
+    for (int k = 0; k < 3; k++) { J[k * 7 + i] = l[k]; J[(3 + k) * 7 + i] = axs[i][k]; }
+  }
+}
+
+// cyclic Jacobi eigen-decomposition of a symmetric 6x6 (np.linalg.svd of the SPD matrix J J^T + reg I)
+DEVFN void jacobi6(ikr* A, ikr* wv, ikr* V) {
+  for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) V[i * 6 + j] = (i == j) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 30; sweep++) {
+    ikr off = 0, diag = 0;
+    for (int i = 0; i < 6; i++) { diag += A[i * 6 + i] * A[i * 6 + i]; for (int j = i + 1; j < 6; j++) off += A[i * 6 + j] * A[i * 6 + j]; }
+    if (off <= 1e-28 * diag) break;
+    for (int p = 0; p < 5; p++) for (int q = p + 1; q < 6; q++) {
+      ikr apq = A[p * 6 + q];
+      if (apq == 0) continue;
+      ikr theta = (A[q * 6 + q] - A[p * 6 + p]) / (2 * apq);
+      ikr t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1));
+      ikr c = 1 / sqrt(t * t + 1), s = t * c;
+      for (int k = 0; k < 6; k++) { ikr akp = A[k * 6 + p], akq = A[k * 6 + q]; A[k * 6 + p] = c * akp - s * akq; A[k * 6 + q] = s * akp + c * akq; }
+      for (int k = 0; k < 6; k++) { ikr apk = A[p * 6 + k], aqk = A[q * 6 + k]; A[p * 6 + k] = c * apk - s * aqk; A[q * 6 + k] = s * apk + c * aqk; }
+      for (int k = 0; k < 6; k++) { ikr vkp = V[k * 6 + p], vkq = V[k * 6 + q]; V[k * 6 + p] = c * vkp - s * vkq; V[k * 6 + q] = s * vkp + c * vkq; }
+    }
+  }
+  for (int i = 0; i < 6; i++) wv[i] = A[i * 6 + i];
+}
+
+// One getControl() call of CartPosQuatImpedenceController: num_iter damped-least-squares iterations on the open-loop
+// joint reference; outputs the joint PD set-point (q_des as two floats, qd_des) for this physics tick.
+DEVFN void ik_tick(const tab_t* C, IkState& s) {
+  ikr q[7], des_quat[4] = {(ikr)s.des_quat[0], (ikr)s.des_quat[1], (ikr)s.des_quat[2], (ikr)s.des_quat[3]};
+  for (int k = 0; k < 7; k++) q[k] = s.q[k];
+  const int niter = (int)C[D3C_NUM_ITER];
+  for (int it = 0; it < niter; it++) {
+    ikr pos[3], cq[4], J[42];
+    ik_fk(C, q, pos, cq, J);
+    ikr dm = 0, dp = 0;
+    for (int k = 0; k < 4; k++) { dm += (cq[k] - des_quat[k]) * (cq[k] - des_quat[k]); dp += (cq[k] + des_quat[k]) * (cq[k] + des_quat[k]); }
+    if (dm > dp) for (int k = 0; k < 4; k++) des_quat[k] = -des_quat[k];
+    ikr qe[3], acc[6];
+    qe[0] = cq[0] * des_quat[1] - des_quat[0] * cq[1] - cq[3] * des_quat[2] + cq[2] * des_quat[3];
+    qe[1] = cq[0] * des_quat[2] - des_quat[0] * cq[2] + cq[3] * des_quat[1] - cq[1] * des_quat[3];
+    qe[2] = cq[0] * des_quat[3] - des_quat[0] * cq[3] - cq[2] * des_quat[1] + cq[1] * des_quat[2];
+    for (int k = 0; k < 3; k++) {
+      acc[k] = (ikr)C[D3C_PGAIN_POS + k] * ik_clamp((ikr)s.des_pos[k] - pos[k], -0.01, 0.01);
+      acc[3 + k] = (ikr)C[D3C_PGAIN_QUAT + k] * ik_clamp(qe[k], -0.1, 0.1);
+    }
+    ikr A[36], wv[6], V[36];
+    for (int r = 0; r < 6; r++) for (int c = r; c < 6; c++) {
+      ikr sum = 0;
+      for (int k = 0; k < 7; k++) sum += J[r * 7 + k] * J[c * 7 + k];
+      if (r == c) sum += (ikr)C[D3C_JREG];
+      A[r * 6 + c] = sum; A[c * 6 + r] = sum;
+    }
+    jacobi6(A, wv, V);
+    ikr qd_null[7], rhs[6], y[6], x[6];
+    for (int k = 0; k < 7; k++) qd_null[k] = (ikr)C[D3C_PGAIN_NULL + k] * ik_clamp((ikr)C[D3C_REST + k] - q[k], -0.2, 0.2);
+    for (int r = 0; r < 6; r++) { ikr sum = acc[r]; for (int k = 0; k < 7; k++) sum -= J[r * 7 + k] * qd_null[k]; rhs[r] = sum; }
+    for (int c = 0; c < 6; c++) { ikr sum = 0; for (int r = 0; r < 6; r++) sum += V[r * 6 + c] * rhs[r]; y[c] = sum / ik_clamp(fabs(wv[c]), (ikr)C[D3C_SVD_MIN], (ikr)C[D3C_SVD_MAX]); }
+    for (int r = 0; r < 6; r++) { ikr sum = 0; for (int c = 0; c < 6; c++) sum += V[r * 6 + c] * y[c]; x[r] = sum; }
+    ikr qd[7], nrm = 0;
+    for (int k = 0; k < 7; k++) { ikr sum = qd_null[k]; for (int r = 0; r < 6; r++) sum += J[r * 7 + k] * x[r]; qd[k] = sum; nrm += sum * sum; }
+    nrm = sqrt(nrm);
+    if (nrm > 3) for (int k = 0; k < 7; k++) qd[k] *= 3 / nrm;
+    for (int k = 0; k < 7; k++) q[k] = ik_clamp(q[k] + (ikr)C[D3C_LRATE] * qd[k], (ikr)C[D3C_JMIN + k], (ikr)C[D3C_JMAX + k]);
+  }
+  for (int k = 0; k < 7; k++) {
+    s.jt_q[k] = (real)q[k];
+    s.jt_qlo[k] = (real)(q[k] - (double)s.jt_q[k]);
+    s.jt_qd[k] = (real)((q[k] - s.q[k]) / (ikr)C[D3C_DT]);
+    s.q[k] = q[k];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ task logic
+DEVFN real dist3(const real* a, const real* b) { real d[3] = {a[0] - b[0], a[1] - b[1], a[2] - b[2]}; return norm3(d); }
+
+// tan(quat2euler(q)[-1]) — utils/geometric_transformation.py:92-153
+DEVFN real tan_yaw(const real* q) {
+  real R[9]; quat2mat(R, q);
+  real cy = sqrt(R[8] * R[8] + R[5] * R[5]);
+  real yaw = cy > (real)8.881784197001252e-16 ? -atan2(R[1], R[0]) : -atan2(-R[3], R[4]);
+  return tan(yaw);
+}
+
+DEVFN void task_obs(const Model& m, const Lay& L, const real* w, float* obs) {
+  if (m.task_id == D3T_PUSHING) {
+    const real *b1 = w + L.qpos + 9, *b2 = w + L.qpos + 16;
+    obs[0] = (float)w[L.tcp]; obs[1] = (float)w[L.tcp + 1];
+    obs[2] = (float)b1[0]; obs[3] = (float)b1[1]; obs[4] = (float)tan_yaw(b1 + 3);
+    obs[5] = (float)b2[0]; obs[6] = (float)b2[1]; obs[7] = (float)tan_yaw(b2 + 3);
+  } else {
+    obs[0] = (float)w[L.tcp]; obs[1] = (float)w[L.tcp + 1];
+  }
+}
+
+DEVFN void pushing_dists(const Model& m, const Lay& L, const real* w, real* d4) {
+  const real *b1 = w + L.qpos + 9, *b2 = w + L.qpos + 16;
+  real g1[3] = {(real)m.taskp[0], (real)m.taskp[1], (real)m.taskp[2]}, g2[3] = {(real)m.taskp[3], (real)m.taskp[4], (real)m.taskp[5]};
+  d4[0] = dist3(b1, g1); d4[1] = dist3(b1, g2); d4[2] = dist3(b2, g1); d4[3] = dist3(b2, g2);
+}
+
+// _check_early_termination (sets `terminated`); serial helper, call from a single lane
+DEVFN int task_early_term(const Model& m, const Lay& L, real* w) {
+  if (m.task_id == D3T_PUSHING) {
+    real d[4], md = m.taskp[6];
+    pushing_dists(m, L, w, d);
+    if ((d[0] <= md && d[3] <= md) || (d[1] <= md && d[2] <= md)) { w[L.misc + ST_TERM] = 1; return 1; }
+    return 0;
+  }
+  int success = w[L.tcp + 1] > (real)m.taskp[3];
+  if (success || w[L.misc + ST_OBST] != 0) { if (success) w[L.misc + ST_TASK1] = 1; w[L.misc + ST_TERM] = 1; return 1; }
+  return 0;
+}
+
+DEVFN real task_reward(const Model& m, const Lay& L, const real* w) {
+  if (m.task_id == D3T_PUSHING) {
+    const real* b1 = w + L.qpos + 9;
+    real g1[3] = {(real)m.taskp[0], (real)m.taskp[1], (real)m.taskp[2]};
+    real dx = w[L.tcp] - b1[0], dy = w[L.tcp + 1] - b1[1];
+    return -(sqrt(dx * dx + dy * dy) + dist3(b1, g1));
+  }
+  return 0;
+}
+
+// info after the substeps: pushing [success, mode, mean_distance, status]; avoiding [success, 9 mode bits, status]
+DEVFN void task_post(const Model& m, const Lay& L, real* w, float* info) {
+  for (int k = 0; k < m.info_dim; k++) info[k] = 0;
+  if (m.task_id == D3T_PUSHING) {
+    int success = task_early_term(m, L, w);
+    real d[4], md = m.taskp[6];
+    pushing_dists(m, L, w, d);
+    int fv = (int)w[L.misc + ST_TASK0], visit = -1, mode = -1;
+    if (d[0] <= md && fv != 0) visit = 0; else if (d[1] <= md && fv != 1) visit = 1; else if (d[2] <= md && fv != 2) visit = 2; else if (d[3] <= md && fv != 3) visit = 3;
+    if (fv == -1) w[L.misc + ST_TASK0] = (real)visit;
+    else {
+      if (fv == 0 && visit == 3) mode = 0; else if (fv == 3 && visit == 0) mode = 1; else if (fv == 1 && visit == 2) mode = 2; else if (fv == 2 && visit == 1) mode = 3;
+    }
+    info[0] = (float)success; info[1] = (float)mode; info[2] = (float)((real)0.5 * (minr(d[0], d[1]) + minr(d[2], d[3]))); info[3] = (float)w[L.misc + ST_STATUS];
+  } else {
+    real x = w[L.tcp], y = w[L.tcp + 1];
+    const tab_t* T = m.taskp;
+    int passed = (int)w[L.misc + ST_TASK2], code = (int)w[L.misc + ST_TASK3];
+    if (y - (real)0.03 <= (real)T[0] && (real)T[0] <= y + (real)0.03 && !(passed & 1)) { if (x < (real)T[4]) code |= 1; else if (x > (real)T[4]) code |= 2; passed |= 1; }
+    if (y - (real)0.03 <= (real)T[1] && (real)T[1] <= y + (real)0.03 && !(passed & 2)) {
+      if (x < (real)T[5]) code |= 4; else if ((real)T[5] < x && x < (real)T[6]) code |= 8; else if (x > (real)T[6]) code |= 16;
+      passed |= 2;
+    }
+    if (y >= (real)T[2] && !(passed & 4)) {
+      if (x < (real)T[7]) code |= 32;
+      if ((real)T[7] < x && x < (real)T[8]) code |= 64; else if ((real)T[8] < x && x < (real)T[9]) code |= 128; else if (x > (real)T[7]) code |= 256;
+      passed |= 4;
+    }
+    w[L.misc + ST_TASK2] = (real)passed; w[L.misc + ST_TASK3] = (real)code;
+    info[0] = (float)w[L.misc + ST_TASK1];
+    for (int k = 0; k < 9; k++) info[1 + k] = (float)((code >> k) & 1);
+    info[10] = (float)w[L.misc + ST_STATUS];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ Gym reset / step
+// reset (a12): state <- (init_qpos, 0), forward pass for tcp + qfrc_bias, object poses <- context, ONE tick under joint PD.
+template <int G>
+DEVFN void env_reset(const Cx& cx, const Model& m, const Lay& L, real* w, const float* ctx /*[nobj*7] or null*/, real tol, int max_iter) {
+  LANES(d, m.nq) w[L.qpos + d] = d < D3_NARM ? (real)m.ctrl[D3C_INIT_QPOS + d] : (real)0;
+  LANES(d, m.nv) { w[L.qvel + d] = 0; w[L.warm + d] = 0; }
+  LANES(d, D3_NROB) w[L.qlo + d] = 0;
+  LANES(k, ST_NMISC) w[L.misc + k] = 0;
+  gsync<G>(cx);
+  LANES(i, m.nlink - D3_NROB) {
+    const tab_t* Lk = m.link + D3_LINK_W * (D3_NROB + i);
+    real* q = w + L.qpos + m.l_qadr[D3_NROB + i];
+    for (int k = 0; k < 7; k++) q[k] = Lk[2 + k];
+  }
+  LANES(z, 1) { w[L.misc + ST_GRIP_SET] = (real)0.001; w[L.misc + ST_TASK0] = -1; }
+  gsync<G>(cx);
+  kinematics<G>(cx, m, L, w);
+  LANES(z, 1) {
+    real o[3], tp[3] = {(real)m.ctrl[D3C_TCP_POS], (real)m.ctrl[D3C_TCP_POS + 1], (real)m.ctrl[D3C_TCP_POS + 2]};
+    real tq[4] = {(real)m.ctrl[D3C_TCP_QUAT], (real)m.ctrl[D3C_TCP_QUAT + 1], (real)m.ctrl[D3C_TCP_QUAT + 2], (real)m.ctrl[D3C_TCP_QUAT + 3]}, Rt[9], R[9];
+    mat_vec3(o, w + L.xmat + 54, tp);
+    for (int k = 0; k < 3; k++) w[L.tcp + k] = w[L.xpos + 18 + k] + o[k];
+    quat2mat(Rt, tq); mat_mul3(R, w + L.xmat + 54, Rt); mat2quat(w + L.tcp + 3, R);
+  }
+  LANES(e, m.nv * m.nv) w[L.M + e] = 0;
+  gsync<G>(cx);
+  dynamics<G>(cx, m, L, w);
+  LANES(k, D3_NROB) w[L.bias_prev + k] = w[L.bias + k];
+  gsync<G>(cx);
+  if (ctx) {
+    LANES(d, 7 * m.nobj) w[L.qpos + D3_NROB + d] = ctx[d];
+    gsync<G>(cx);
+  }
+  real jq[D3_NARM], jql[D3_NARM], jqd[D3_NARM];
+  for (int k = 0; k < D3_NARM; k++) { jq[k] = m.ctrl[D3C_INIT_QPOS + k]; jql[k] = 0; jqd[k] = 0; }
+  physics_tick<G>(cx, m, L, w, jq, jql, jqd, tol, max_iter);
+}
+
+// pre-substep half of GymEnvWrapper.step (gym_env_wrapper.py:67-90): open fingers, Cartesian mode, sample obs /
+// reward / done BEFORE the substeps.
+template <int G>
+DEVFN void env_prestep(const Cx& cx, const Model& m, const Lay& L, real* w, float* obs, float* reward, unsigned char* done) {
+  LANES(z, 1) {
+    w[L.misc + ST_GRIP_SET] = (real)0.04; w[L.misc + ST_GRASP] = 0; w[L.misc + ST_CTRL_MODE] = 1;
+    task_obs(m, L, w, obs);
+    *reward = (float)task_reward(m, L, w);
+    int early = task_early_term(m, L, w);
+    *done = (w[L.misc + ST_TERM] != 0 || early || (int)w[L.misc + ST_STEP] >= m.max_steps - 1) ? 1 : 0;
+  }
+  gsync<G>(cx);
+}
+template <int G>
+DEVFN void env_poststep(const Cx& cx, const Model& m, const Lay& L, real* w, float* info) {
+  LANES(z, 1) {
+    w[L.misc + ST_STEP] += 1;
+    task_post(m, L, w, info);
+  }
+  gsync<G>(cx);
+}

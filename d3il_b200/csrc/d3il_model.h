@@ -1,0 +1,109 @@
+// d3il_model.h — host-side: D3SC scene blob -> `Model` (fp32 tables + index tables) and flat-state (de)serialisation.
+// Shared by the CUDA library (d3il_capi.cu) and the CPU emulation harness used in tests.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+
+#include <string>
+
+#include "d3il_env.cuh"
+
+#define D3SC_MAGIC 0x43533344
+#define D3SC_HDR_INTS 32
+
+static inline bool d3il_build_model(const void* blob, size_t nbytes, Model& m, Lay& L, std::string& err) {
+  const int32_t* h = (const int32_t*)blob;
+  if (nbytes < 4 * D3SC_HDR_INTS || h[0] != D3SC_MAGIC || h[1] != 1) { err = "not a D3SC v1 scene blob"; return false; }
+  memset(&m, 0, sizeof(m));
+  m.task_id = h[2]; m.nlink = h[3]; m.nobj = h[4]; m.nq = h[5]; m.nv = h[6]; m.ngeom = h[7]; m.npair = h[8]; m.n_substeps = h[9];
+  m.max_steps = h[10]; m.obs_dim = h[11]; m.act_dim = h[12]; m.ctx_dim = h[13]; m.info_dim = h[14]; m.ctrl_kind = h[15]; m.ntaskp = h[16];
+  if (m.nlink > D3_MAXLINK || m.nq > D3_MAXQ || m.nv > D3_MAXV || m.ngeom > D3_MAXGEOM || m.npair > D3_MAXPAIR || m.ntaskp > 32) { err = "scene exceeds compiled table sizes"; return false; }
+  if (m.task_id != D3T_AVOIDING && m.task_id != D3T_PUSHING) { err = "task not supported by this build of the CUDA path"; return false; }
+  size_t need = 4 * D3SC_HDR_INTS + 8 * ((size_t)m.nlink * D3_LINK_W + (size_t)m.ngeom * D3_GEOM_W + (size_t)m.npair * D3_PAIR_W + D3_CTRL_W + m.ntaskp);
+  if (need != nbytes) { err = "scene blob size mismatch"; return false; }
+  const double* p = (const double*)((const char*)blob + 4 * D3SC_HDR_INTS);
+  for (int i = 0; i < m.nlink; i++, p += D3_LINK_W) {
+    for (int k = 0; k < D3_LINK_W; k++) m.link[D3_LINK_W * i + k] = (tab_t)p[k];
+    m.l_parent[i] = (int)p[0]; m.l_jtype[i] = (int)p[1]; m.l_limited[i] = (int)p[22]; m.l_qadr[i] = (int)p[29]; m.l_dadr[i] = (int)p[30];
+    m.l_ndof[i] = m.l_jtype[i] == 2 ? 6 : 1;
+    m.l_anc[i] = (1u << i) | (m.l_parent[i] >= 0 ? m.l_anc[m.l_parent[i]] : 0u);
+    for (int k = 0; k < m.l_ndof[i]; k++) m.d_link[m.l_dadr[i] + k] = i;
+  }
+  for (int i = 0; i < m.nlink; i++) for (int j = 0; j < m.nlink; j++) if ((m.l_anc[j] >> i) & 1u) m.l_desc[i] |= 1u << j;
+  for (int i = 0; i < m.nlink; i++) {
+    int root = i; while (m.l_parent[root] >= 0) root = m.l_parent[root];
+    m.l_ref[i] = (root == 0 && m.nlink > 6) ? 6 : root;     // arm tree: wrist (link 7 origin); free bodies: themselves
+  }
+  for (int i = 0; i < m.ngeom; i++, p += D3_GEOM_W) {
+    for (int k = 0; k < D3_GEOM_W; k++) m.geom[D3_GEOM_W * i + k] = (tab_t)p[k];
+    double q[4] = {p[5], p[6], p[7], p[8]};
+    double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    double w = q[0] / n, x = q[1] / n, y = q[2] / n, z = q[3] / n;
+    double R[9] = {1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y), 2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x),
+                   2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)};
+    for (int k = 0; k < 9; k++) m.geomR[9 * i + k] = (tab_t)R[k];
+  }
+  int conmax = 0;
+  for (int i = 0; i < m.npair; i++, p += D3_PAIR_W) {
+    for (int k = 0; k < D3_PAIR_W; k++) m.pair[D3_PAIR_W * i + k] = (tab_t)p[k];
+    int t1 = (int)m.geom[D3_GEOM_W * (int)p[0]], t2 = (int)m.geom[D3_GEOM_W * (int)p[1]];
+    conmax += (t1 == D3G_BOX && t2 == D3G_BOX) ? 8 : 1;
+    if ((int)p[2] != 3) { err = "only condim 3 contacts are supported by this build of the CUDA path"; return false; }
+  }
+  for (int k = 0; k < D3_CTRL_W; k++) m.ctrl[k] = (tab_t)p[k];
+  p += D3_CTRL_W;
+  for (int k = 0; k < m.ntaskp; k++) m.taskp[k] = (tab_t)p[k];
+  // structurally non-zero entries of M: dof a >= b with link(b) an ancestor-or-self of link(a)
+  m.nmpair = 0;
+  for (int a = 0; a < m.nv; a++) for (int b = 0; b <= a; b++)
+    if ((m.l_anc[m.d_link[a]] >> m.d_link[b]) & 1u) {
+      if (m.nmpair >= D3_MAXV * 8) { err = "mass-matrix pair table overflow"; return false; }
+      m.mp_a[m.nmpair] = (unsigned char)a; m.mp_b[m.nmpair] = (unsigned char)b; m.nmpair++;
+    }
+  m.maxcon = conmax < 24 ? ((conmax + 3) & ~3) : 24;
+  m.maxrow = 3 * m.maxcon + 6;
+  if (m.maxrow > 64) m.maxrow = 64;
+  d3il_layout(m, L);
+  m.ws_floats = L.total;
+  return true;
+}
+
+// ---- flat fp64 state, identical layout to oracle/d3il_oracle.c::d3o_get_state (nq + 2 nv + 60)
+static inline int d3il_state_dim(const Model& m) { return m.nq + 2 * m.nv + 60; }
+
+template <class T>
+static inline void d3il_pack_state(const Model& m, const Lay& L, const T* w /*workspace/state row*/, const IkState& ik, double* out) {
+  double* p = out;
+  for (int k = 0; k < m.nq; k++) *p++ = (double)w[L.qpos + k] + (k < D3_NROB ? (double)w[L.qlo + k] : 0.0);
+  for (int k = 0; k < m.nv; k++) *p++ = w[L.qvel + k];
+  for (int k = 0; k < m.nv; k++) *p++ = w[L.warm + k];
+  for (int k = 0; k < 9; k++) *p++ = w[L.bias_prev + k];
+  for (int k = 0; k < 7; k++) *p++ = w[L.tcp + k];
+  for (int k = 0; k < 7; k++) *p++ = ik.q[k];
+  for (int k = 0; k < 3; k++) *p++ = ik.des_pos[k];
+  for (int k = 0; k < 4; k++) *p++ = ik.des_quat[k];
+  for (int k = 0; k < 7; k++) *p++ = (double)ik.jt_q[k] + (double)ik.jt_qlo[k];
+  for (int k = 0; k < 7; k++) *p++ = ik.jt_qd[k];
+  *p++ = ik.valid; *p++ = w[L.misc + ST_CTRL_MODE]; *p++ = w[L.misc + ST_GRIP_SET]; *p++ = w[L.misc + ST_GRASP]; *p++ = w[L.misc + ST_STEP];
+  *p++ = w[L.misc + ST_TERM]; *p++ = w[L.misc + ST_STATUS]; *p++ = w[L.misc + ST_OBST];
+  for (int k = 0; k < 4; k++) *p++ = w[L.misc + ST_TASK0 + k];
+  for (int k = 0; k < 4; k++) *p++ = 0;
+}
+template <class T>
+static inline void d3il_unpack_state(const Model& m, const Lay& L, T* w, IkState& ik, const double* in) {
+  const double* p = in;
+  for (int k = 0; k < m.nq; k++) { w[L.qpos + k] = (T)*p; if (k < D3_NROB) w[L.qlo + k] = (T)(*p - (double)w[L.qpos + k]); p++; }
+  for (int k = 0; k < m.nv; k++) w[L.qvel + k] = (T)*p++;
+  for (int k = 0; k < m.nv; k++) w[L.warm + k] = (T)*p++;
+  for (int k = 0; k < 9; k++) w[L.bias_prev + k] = (T)*p++;
+  for (int k = 0; k < 7; k++) w[L.tcp + k] = (T)*p++;
+  for (int k = 0; k < 7; k++) ik.q[k] = *p++;
+  for (int k = 0; k < 3; k++) ik.des_pos[k] = (real)*p++;
+  for (int k = 0; k < 4; k++) ik.des_quat[k] = (real)*p++;
+  for (int k = 0; k < 7; k++) { ik.jt_q[k] = (real)*p; ik.jt_qlo[k] = (real)(*p - (double)ik.jt_q[k]); p++; }
+  for (int k = 0; k < 7; k++) ik.jt_qd[k] = (real)*p++;
+  ik.valid = (int)*p++;
+  w[L.misc + ST_CTRL_MODE] = (T)*p++; w[L.misc + ST_GRIP_SET] = (T)*p++; w[L.misc + ST_GRASP] = (T)*p++; w[L.misc + ST_STEP] = (T)*p++;
+  w[L.misc + ST_TERM] = (T)*p++; w[L.misc + ST_STATUS] = (T)*p++; w[L.misc + ST_OBST] = (T)*p++;
+  for (int k = 0; k < 4; k++) w[L.misc + ST_TASK0 + k] = (T)*p++;
+}

@@ -833,8 +833,9 @@ static void solve_constraints(Env* e) {
     for (int i = 0; i < ne; i++) { double s = 0; for (int d = 0; d < nv; d++) s += e->J[i * nv + d] * p[d]; Jp[i] = s; }
     double pMp = 0, pMa = 0;
     for (int d = 0; d < nv; d++) { double s = 0; for (int k = 0; k < nv; k++) s += e->M[d * nv + k] * p[k]; pMp += p[d] * s; pMa += p[d] * Ma[d]; }
-    double lo = 0, hi = -1, alpha = 1, d0 = 0;
+    double lo = 0, hi = -1, alpha = 1, d0 = 0, dlo, dhi = 0;
     for (int d = 0; d < nv; d++) d0 += grad[d] * p[d];                 /* phi'(0) < 0 */
+    dlo = d0;
     static double jal[MAXEFC], hd2[MAXEFC], hb2[MAXCON][36]; static int mid2[MAXCON];
     for (int ls = 0; ls < 50; ls++) {
       for (int i = 0; i < ne; i++) jal[i] = jar[i] + alpha * Jp[i];
@@ -849,11 +850,18 @@ static void solve_constraints(Env* e) {
         } else d2 += hd2[i] * Jp[i] * Jp[i];
       }
       if (fabs(d1) <= 1e-10 * fabs(d0) + 1e-300) break;
-      if (d1 < 0) lo = alpha; else hi = alpha;
+      if (d1 < 0) { lo = alpha; dlo = d1; } else { hi = alpha; dhi = d1; }
       double next = alpha - d1 / d2;
       if (hi < 0) { if (!(next > lo)) next = 2 * alpha + 1e-12; }
-      else if (!(next > lo && next < hi)) next = 0.5 * (lo + hi);
-      if (hi >= 0 && hi - lo < 1e-15 * (1 + hi)) { alpha = next; break; }
+      else {
+        /* bracketed: Newton step unless it hugs an end point (it can cycle across a kink of phi'), then false position */
+        double wd = hi - lo;
+        if (!(next > lo + 0.05 * wd && next < hi - 0.05 * wd)) {
+          double sec = lo + wd * (-dlo) / (dhi - dlo);
+          next = clampd(sec, lo + 0.05 * wd, hi - 0.05 * wd);
+        }
+        if (wd < 1e-15 * (1 + hi)) { alpha = next; break; }
+      }
       alpha = next;
     }
     for (int d = 0; d < nv; d++) a[d] += alpha * p[d];

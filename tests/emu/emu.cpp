@@ -1,0 +1,79 @@
+// emu.cpp — TEST-ONLY host build of the CUDA kernel core (d3il_b200/csrc/d3il_core.cuh, d3il_env.cuh) with G = 1.
+// Lets the kernel logic be checked against the fp64 oracle in the CPU container; not part of the product path
+// (the product library d3il_b200/csrc/libd3il.so has no CPU execution path at all).
+#define D3IL_EMU 1
+#include <stdlib.h>
+
+#include <vector>
+
+#include "../../d3il_b200/csrc/d3il_model.h"
+
+struct Emu {
+  Model m; Lay L; IkState ik;
+  std::vector<real> w;
+  real tol; int max_iter;
+};
+static const Cx CX = {0, 0};
+
+extern "C" {
+Emu* emu_create(const void* blob, size_t n) {
+  Emu* e = new Emu();
+  std::string err;
+  if (!d3il_build_model(blob, n, e->m, e->L, err)) { fprintf(stderr, "emu_create: %s\n", err.c_str()); delete e; return nullptr; }
+  e->w.assign(e->L.total, 0);
+  memset(&e->ik, 0, sizeof(e->ik));
+  e->tol = sizeof(real) == 4 ? (real)1e-6 : (real)1e-10;
+  e->max_iter = sizeof(real) == 4 ? 12 : 100;
+  return e;
+}
+void emu_destroy(Emu* e) { delete e; }
+void emu_set_solver(Emu* e, double tol, int max_iter) { e->tol = (real)tol; e->max_iter = max_iter; }
+int emu_ws_floats(Emu* e) { return e->L.total; }
+int emu_n_state(Emu* e) { return e->L.n_state; }
+int emu_state_dim(Emu* e) { return d3il_state_dim(e->m); }
+
+static void tick(Emu* e) {
+  real* w = e->w.data();
+  if (w[e->L.misc + ST_CTRL_MODE] != 0) {
+    if (!e->ik.valid) { for (int k = 0; k < 7; k++) e->ik.q[k] = (double)w[e->L.qpos + k] + (double)w[e->L.qlo + k]; e->ik.valid = 1; }
+    ik_tick(e->m.ctrl, e->ik);
+  }
+  physics_tick<1>(CX, e->m, e->L, w, e->ik.jt_q, e->ik.jt_qlo, e->ik.jt_qd, e->tol, e->max_iter);
+}
+void emu_reset(Emu* e, const double* ctx) {
+  std::vector<float> c(e->m.ctx_dim > 0 ? e->m.ctx_dim : 1);
+  if (ctx) for (int k = 0; k < e->m.ctx_dim; k++) c[k] = (float)ctx[k];
+  memset(&e->ik, 0, sizeof(e->ik));
+  for (int k = 0; k < 7; k++) { e->ik.jt_q[k] = e->m.ctrl[D3C_INIT_QPOS + k]; e->ik.jt_qlo[k] = 0; e->ik.jt_qd[k] = 0; }
+  env_reset<1>(CX, e->m, e->L, e->w.data(), ctx ? c.data() : nullptr, e->tol, e->max_iter);
+}
+void emu_step(Emu* e, const double* action, float* obs, double* reward, int* done, double* info) {
+  real* w = e->w.data();
+  double n = sqrt(action[3] * action[3] + action[4] * action[4] + action[5] * action[5] + action[6] * action[6]);
+  for (int k = 0; k < 3; k++) e->ik.des_pos[k] = (real)action[k];
+  for (int k = 0; k < 4; k++) e->ik.des_quat[k] = (real)(action[3 + k] / n);
+  float r; unsigned char d; float inf[16];
+  env_prestep<1>(CX, e->m, e->L, w, obs, &r, &d);
+  for (int i = 0; i < e->m.n_substeps; i++) tick(e);
+  env_poststep<1>(CX, e->m, e->L, w, inf);
+  *reward = r; *done = d;
+  for (int k = 0; k < e->m.info_dim; k++) info[k] = inf[k];
+}
+void emu_substep(Emu* e, int n) { for (int i = 0; i < n; i++) tick(e); }
+void emu_robot_state(Emu* e, double* tcp) { for (int k = 0; k < 3; k++) tcp[k] = e->w[e->L.tcp + k]; }
+void emu_get_obs(Emu* e, float* obs) { task_obs(e->m, e->L, e->w.data(), obs); }
+int emu_probe(Emu* e, const char* what, double* out, int cap) {
+  const Lay& L = e->L; const Model& m = e->m; int off = -1, n = 0;
+  std::string s(what);
+  if (s == "M") { off = L.M; n = m.nv * m.nv; } else if (s == "bias") { off = L.bias; n = m.nv; } else if (s == "qacc") { off = L.qacc; n = m.nv; }
+  else if (s == "qacc_smooth") { off = L.qacc_smooth; n = m.nv; } else if (s == "efc_J") { off = L.J; n = m.maxrow * m.nv; }
+  else if (s == "efc_aref") { off = L.aref; n = m.maxrow; } else if (s == "efc_D") { off = L.D; n = m.maxrow; } else if (s == "efc_force") { off = L.frcE; n = m.maxrow; }
+  else if (s == "contacts") { off = L.con; n = D3_CON_W * m.maxcon; } else if (s == "qfrc_c") { off = L.qfrc_c; n = m.nv; } else if (s == "act") { off = L.act; n = 9; }
+  else if (s == "qfrc_smooth") { off = L.qfrc_smooth; n = m.nv; }
+  if (off < 0 || n > cap) return -1;
+  for (int k = 0; k < n; k++) out[k] = e->w[off + k];
+  return n;
+}
+void emu_get_state(Emu* e, double* out) { d3il_pack_state(e->m, e->L, e->w.data(), e->ik, out); }
+void emu_set_state(Emu* e, const double* in) { d3il_unpack_state(e->m, e->L, e->w.data(), e->ik, in); }
+}

@@ -1,0 +1,216 @@
+"""GPU parity tests (run on the B200 box): CUDA path through the C ABI vs the fp64 oracle on identical inputs.
+
+Protocol of SURVEY.md §8c (the true reference cannot run anywhere in this project, so the oracle is the checker):
+  (i)   teacher-forced single physics tick, all state components;
+  (ii)  one env step (35 ticks) closed loop;
+  (iii) contact-free full episodes (Avoiding) closed loop;
+  (iv)  contact-rich long horizons: task-metric agreement, not trajectories (chaotic).
+Tolerances (fp32 kernels vs fp64 oracle) are written next to each assert.
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from d3il_b200.scene.blob import load_scene          # noqa: E402
+from oracle.oracle import OracleEnv                   # noqa: E402
+from tests.util import oracle_rollout_states, random_walk_actions, scripted_push_actions, with_setpoint  # noqa: E402
+
+
+def _benv(task, n):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from d3il_b200.batched_env import BatchedEnv
+    return BatchedEnv(task, n, 0)
+
+
+def test_reset_matches_oracle(pushing_contexts):
+    """a12: reset = state install + one tick under joint PD, for all 60 shipped evaluation contexts."""
+    blob, sc = load_scene("pushing")
+    env = _benv("pushing", 60)
+    ctx = torch.tensor(pushing_contexts, dtype=torch.float32, device="cuda")
+    obs = env.reset(ctx).cpu().numpy()
+    o = OracleEnv(blob, sc.header)
+    nq, nv = sc.header["nq"], sc.header["nv"]
+    for i in range(60):
+        oo = o.reset(pushing_contexts[i])
+        s_ref, s = o.get_state(), env.get_state(i)
+        # the contexts are float32 on the device; positions agree to fp32 resolution
+        assert np.allclose(s[:nq], s_ref[:nq], rtol=1e-4, atol=2e-6), np.abs(s[:nq] - s_ref[:nq]).max()
+        # one tick of the 11 mm-deep spawn transient: velocities up to ~0.5 m/s, accelerations ~500 m/s^2
+        assert np.allclose(s[nq:nq + nv], s_ref[nq:nq + nv], rtol=1e-3, atol=1e-4), np.abs(s[nq:nq + nv] - s_ref[nq:nq + nv]).max()
+        assert np.allclose(obs[i], oo, rtol=1e-4, atol=1e-5)
+    env.close()
+
+
+def test_single_tick_teacher_forced(pushing_contexts):
+    """(i): from ~100 oracle states along a contact-rich scripted push, one tick on the GPU vs one tick of the oracle."""
+    blob, sc = load_scene("pushing")
+    nq, nv = sc.header["nq"], sc.header["nv"]
+    ctx = pushing_contexts[0]
+    o = OracleEnv(blob, sc.header)
+    o.reset(ctx)
+    acts = scripted_push_actions(ctx, o.robot_state())
+    _, states, _ = oracle_rollout_states("pushing", ctx, acts)
+    starts = []
+    o2 = OracleEnv(blob, sc.header)
+    for k in range(0, len(acts), 2):                       # 55 env steps x ticks {0, 17}: 110 teacher-forced states
+        o2.set_state(with_setpoint(states[k], sc, acts[k]))
+        for t in range(18):
+            if t in (0, 17):
+                starts.append(o2.get_state())
+            o2.substep(1)
+    env = _benv("pushing", len(starts))
+    env.reset(torch.tensor(np.repeat(ctx[None], len(starts), 0), dtype=torch.float32, device="cuda"))
+    for i, s in enumerate(starts):
+        env.set_state(i, s)
+    env.substep(1)
+    worst_q = worst_v = 0.0
+    for i, s in enumerate(starts):
+        o2.set_state(s)
+        o2.substep(1)
+        ref, got = o2.get_state(), env.get_state(i)
+        dq = np.abs(got[:nq] - ref[:nq]) / (1e-4 * np.abs(ref[:nq]) + 1e-6)
+        # velocity after one tick: v + h*a.  fp32 resolves a to ~1e-4 of the largest acceleration in the system
+        # (stiff contacts: up to 1e3 rad/s^2 during impacts), so the bound scales with h*|a|_inf as well as |v|.
+        acc = np.abs(ref[nq:nq + nv] - s[nq:nq + nv]).max()
+        dv = np.abs(got[nq:nq + nv] - ref[nq:nq + nv]) / (1e-4 * np.abs(ref[nq:nq + nv]) + 2e-4 * acc + 5e-6)
+        worst_q, worst_v = max(worst_q, dq.max()), max(worst_v, dv.max())
+    assert worst_q <= 1.0, worst_q          # qpos: rel 1e-4 + abs 1e-6
+    assert worst_v <= 1.0, worst_v
+    env.close()
+
+
+def test_env_step_closed_loop(pushing_contexts):
+    """(ii): a full env step (35 ticks incl. IK reference, PD, contacts) from oracle states, GPU vs oracle."""
+    blob, sc = load_scene("pushing")
+    nq, nv = sc.header["nq"], sc.header["nv"]
+    ctx = pushing_contexts[3]
+    o = OracleEnv(blob, sc.header)
+    o.reset(ctx)
+    acts = random_walk_actions(o.robot_state(), 64, seed=1)
+    _, states, outs = oracle_rollout_states("pushing", ctx, acts)
+    n = len(acts)
+    env = _benv("pushing", n)
+    env.reset(torch.tensor(np.repeat(ctx[None], n, 0), dtype=torch.float32, device="cuda"))
+    for i in range(n):
+        env.set_state(i, states[i])
+    obs, rew, done, info = env.step(torch.tensor(acts, dtype=torch.float32, device="cuda"))
+    obs, rew, done, info = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy(), info.cpu().numpy()
+    o2 = OracleEnv(blob, sc.header)
+    for i in range(n):
+        o2.set_state(states[i])
+        oo, rr, dd, ii = o2.step(acts[i])
+        ref, got = o2.get_state(), env.get_state(i)
+        assert np.allclose(got[:nq], ref[:nq], rtol=1e-4, atol=5e-6), (i, np.abs(got[:nq] - ref[:nq]).max())
+        assert np.allclose(got[nq:nq + nv], ref[nq:nq + nv], rtol=1e-3, atol=2e-4), (i, np.abs(got[nq:nq + nv] - ref[nq:nq + nv]).max())
+        assert np.allclose(obs[i], oo, rtol=1e-4, atol=1e-5) and abs(rew[i] - rr) < 1e-5 and bool(done[i]) == dd
+        assert np.allclose(info[i, :3], ii[:3], rtol=1e-4, atol=1e-5) and info[i, 3] == 0
+    env.close()
+
+
+def test_avoiding_episode_closed_loop():
+    """(iii): contact-free closed-loop episodes on Avoiding (robot only): tcp path within 1e-4 rel of the oracle over
+    the whole 250-step episode (8750 physics ticks), several action streams at once."""
+    blob, sc = load_scene("avoiding")
+    n = 8
+    env = _benv("avoiding", n)
+    env.reset()
+    tcp0 = env.robot_state().cpu().numpy()[0].astype(np.float64)
+    # streams that stay in the free corridor x in [0.3, 0.4] (left of every obstacle), moving +y to the finish line
+    streams = []
+    for i in range(n):
+        rng = np.random.default_rng(i)
+        des = tcp0.copy()
+        acts = []
+        for k in range(250):
+            tgt_x = 0.33 + 0.005 * i
+            des[0] += np.clip(tgt_x - des[0], -0.004, 0.004) + rng.uniform(-0.001, 0.001)
+            des[1] += 0.004 + rng.uniform(-0.002, 0.002)
+            acts.append(np.concatenate([des, [0, 1, 0, 0]]))
+        streams.append(np.array(acts))
+    streams = np.array(streams)
+    oracles = [OracleEnv(blob, sc.header) for _ in range(n)]
+    for oe in oracles:
+        oe.reset()
+    finished = np.zeros(n, bool)
+    for k in range(250):
+        obs, rew, done, info = env.step(torch.tensor(streams[:, k], dtype=torch.float32, device="cuda"))
+        obs, done, info = obs.cpu().numpy(), done.cpu().numpy(), info.cpu().numpy()
+        for i, oe in enumerate(oracles):
+            if finished[i]:
+                continue
+            oo, rr, dd, ii = oe.step(streams[i, k])
+            assert np.allclose(obs[i], oo, rtol=1e-4, atol=2e-5), (k, i, obs[i], oo)
+            assert bool(done[i]) == dd and np.array_equal(info[i, :10], ii[:10]), (k, i, info[i], ii)
+            finished[i] = dd
+    assert finished.all()          # every stream crosses the finish line (success) before the step cap
+    env.close()
+
+
+def test_determinism_and_batch_consistency(pushing_contexts):
+    """Bit-exact reproducibility (B.9(8)): same inputs -> same bits, across runs and across env slots of one batch."""
+    n = 64
+    ctx = np.repeat(pushing_contexts[7][None], n, 0)
+    acts = scripted_push_actions(pushing_contexts[7], [0.5249, -0.2797, 0.1224], n_steps=90)
+    finals = []
+    for rep in range(2):
+        env = _benv("pushing", n)
+        env.reset(torch.tensor(ctx, dtype=torch.float32, device="cuda"))
+        for a in acts:
+            env.step(torch.tensor(np.repeat(a[None], n, 0), dtype=torch.float32, device="cuda"))
+        finals.append(np.array([env.get_state(i) for i in range(n)]))
+        env.close()
+    assert np.array_equal(finals[0], finals[1])
+    assert all(np.array_equal(finals[0][0], finals[0][i]) for i in range(n))
+    # the push actually moved box 1
+    assert abs(finals[0][0][9 + 1] - pushing_contexts[7][0, 1]) > 0.05
+
+
+def test_host_api_equals_device_api(pushing_contexts):
+    n = 60
+    env_d, env_h = _benv("pushing", n), _benv("pushing", n)
+    obs_d = env_d.reset(torch.tensor(pushing_contexts, dtype=torch.float32, device="cuda")).cpu().numpy()
+    obs_h = env_h.reset_host(pushing_contexts.astype(np.float32))
+    assert np.array_equal(obs_d, obs_h)
+    tcp = env_h.robot_state_host()
+    assert np.array_equal(tcp, env_d.robot_state().cpu().numpy())
+    rng = np.random.default_rng(0)
+    des = np.concatenate([tcp, np.tile([0, 1, 0, 0], (n, 1))], 1).astype(np.float32)
+    for k in range(5):
+        des[:, :2] += rng.uniform(-0.01, 0.01, (n, 2)).astype(np.float32)
+        od, rd, dd, idd = (t.cpu().numpy() for t in env_d.step(torch.tensor(des, device="cuda")))
+        oh, rh, dh, ih = env_h.step_host(des)
+        assert np.array_equal(od, oh) and np.array_equal(rd, rh) and np.array_equal(dd, dh) and np.array_equal(idd, ih)
+    env_d.close(); env_h.close()
+
+
+def test_full_size_properties(pushing_contexts):
+    """BASELINE config 2 size (4096 envs): size-independent properties — finite states, no solver/overflow faults, boxes
+    stay on the table, envs that share a context and an action stream stay bit-identical, masked reset only touches the
+    masked envs."""
+    n = 4096
+    env = _benv("pushing", n)
+    ctx = pushing_contexts[np.arange(n) % 60]
+    env.reset(torch.tensor(ctx, dtype=torch.float32, device="cuda"))
+    tcp = env.robot_state().clone()
+    des = torch.cat([tcp, torch.tensor([0, 1, 0, 0], device="cuda").repeat(n, 1)], 1)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    lo, hi = torch.tensor([0.3, -0.45], device="cuda"), torch.tensor([0.8, 0.45], device="cuda")
+    for k in range(40):
+        d = (torch.rand(60, 2, generator=g, device="cuda") * 0.02 - 0.01).repeat((n + 59) // 60, 1)[:n]   # stream = f(context id)
+        des[:, :2] = torch.minimum(torch.maximum(des[:, :2] + d, lo), hi)
+        obs, rew, done, info = env.step(des)
+    assert torch.isfinite(obs).all() and torch.isfinite(info).all()
+    assert (info[:, 3] == 0).all()
+    s0, s60, s120 = env.get_state(5), env.get_state(65), env.get_state(4085)
+    assert np.array_equal(s0, s60) and np.array_equal(s0, s120)
+    assert 0.0105 < s0[9 + 2] < 0.0115 and 0.0105 < s0[16 + 2] < 0.0115
+    # masked reset
+    before = env.get_state(1)
+    mask = torch.zeros(n, dtype=torch.uint8, device="cuda"); mask[0] = 1
+    env.reset(torch.tensor(ctx, dtype=torch.float32, device="cuda"), mask)
+    assert np.array_equal(env.get_state(1), before)
+    assert env.get_state(0)[23 + 42 + 44 + 4] == 0            # step counter of the reset env
+    env.close()

@@ -1,0 +1,58 @@
+"""Shared helpers for the parity tests: scripted action streams and oracle roll-outs."""
+import numpy as np
+
+from d3il_b200.scene.blob import load_scene
+from oracle.oracle import OracleEnv
+
+
+def scripted_push_actions(ctx, tcp0, n_steps=110, speed=0.006, approach_steps=60):
+    """Drive the rod behind box 1 (-y side), then push it towards +y: exercises rod-box and box-table contacts."""
+    des = np.array(tcp0, dtype=np.float64).copy()
+    box = ctx[0, :2]
+    behind = np.array([box[0], box[1] - 0.08])
+    out = []
+    for k in range(n_steps):
+        goal = behind if k < approach_steps else np.array([box[0], 0.3])
+        d = goal - des[:2]
+        n = np.linalg.norm(d)
+        if n > speed:
+            d = d / n * speed
+        des[:2] += d
+        out.append(np.concatenate([des, [0, 1, 0, 0]]))
+    return np.array(out)
+
+
+def random_walk_actions(tcp0, n_steps, seed, lo=(0.3, -0.45), hi=(0.8, 0.45), step=0.01):
+    """BASELINE.md §3 synthetic stream: dxy ~ U(-0.01, 0.01)^2 accumulated on the desired xy, clipped to the workspace."""
+    rng = np.random.default_rng(seed)
+    des = np.array(tcp0, dtype=np.float64).copy()
+    out = []
+    for _ in range(n_steps):
+        des[:2] = np.clip(des[:2] + rng.uniform(-step, step, 2), lo, hi)
+        out.append(np.concatenate([des, [0, 1, 0, 0]]))
+    return np.array(out)
+
+
+def oracle_rollout_states(task, ctx, actions, every=1):
+    """Roll the oracle and return the flat state BEFORE each env step plus the step outputs."""
+    blob, sc = load_scene(task)
+    env = OracleEnv(blob, sc.header)
+    env.reset(ctx)
+    states, outs = [], []
+    for k, a in enumerate(actions):
+        if k % every == 0:
+            states.append(env.get_state())
+        outs.append(env.step(a))
+    return env, np.array(states), outs
+
+
+def with_setpoint(state, sc, action, grip=0.04):
+    """Flat state with the Cartesian set-point installed (what GymEnvWrapper.step does before its substeps)."""
+    s = state.copy()
+    o = sc.header["nq"] + 2 * sc.header["nv"]
+    s[o + 23:o + 26] = action[:3]
+    s[o + 26:o + 30] = action[3:] / np.linalg.norm(action[3:])
+    s[o + 44 + 1] = 1      # ctrl_mode
+    s[o + 44 + 2] = grip   # gripper set-point
+    s[o + 44 + 3] = 0      # grasp flag
+    return s
