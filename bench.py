@@ -1,0 +1,314 @@
+#!/usr/bin/env python
+"""bench.py — env steps/sec of the batched rollout hot path (BASELINE.json metric).
+
+Our arm (default): Pushing, 4096 envs per GPU, synthetic random-walk action stream, contexts
+``pushing/test_contexts.pkl[i % 60]``, 400-step episodes with auto-reset.  One "step" = one env step of every env in
+the batch (= 35 physics ticks each, incl. the IK controller, observation, termination/mode bookkeeping and the masked
+reset of finished envs).  ``value`` is measured with everything resident in HBM, ``e2e`` through the host-buffer C ABI
+(numpy in / numpy out, H2D + D2H inside the timed region).
+
+``--impl reference`` times the CPU implementation of the same path — the fp64 oracle port (``oracle/``; the real
+reference needs mujoco/pinocchio, which cannot be installed here) — one env per worker process on all host cores, the
+reference's own sharding scheme (``simulation/pushing_sim.py:114-135``).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "env_steps_per_sec"
+UNIT = "env-steps/s"
+TASK = "pushing"
+N_ENVS = 4096            # per GPU (BASELINE.json configs[1])
+WORKSPACE_LO, WORKSPACE_HI = (0.3, -0.45), (0.8, 0.45)
+
+
+def load_contexts():
+    return np.load(os.path.join(ROOT, "d3il_b200", "data", "pushing_test_contexts.npy"))
+
+
+# ------------------------------------------------------------------------------------------------ CPU (oracle) arm
+def _cpu_worker(args):
+    """One env on one core: `n_steps` env steps of the Pushing workload; returns (env steps done, seconds)."""
+    wid, n_steps, seed = args
+    try:
+        os.sched_setaffinity(0, {wid % os.cpu_count()})
+    except Exception:
+        pass
+    from d3il_b200.scene.blob import load_scene
+    from oracle.oracle import OracleEnv          # bench.py's cpu_baseline / reference leg: allowed user of oracle/
+
+    blob, sc = load_scene(TASK)
+    ctxs = load_contexts()
+    env = OracleEnv(blob, sc.header)
+    rng = np.random.default_rng(seed)
+    env.reset(ctxs[wid % 60])
+    des = env.robot_state().copy()
+    t0 = time.perf_counter()
+    for k in range(n_steps):
+        des[:2] = np.clip(des[:2] + rng.uniform(-0.01, 0.01, 2), WORKSPACE_LO, WORKSPACE_HI)
+        _, _, done, _ = env.step(np.concatenate([des, [0.0, 1.0, 0.0, 0.0]]))
+        if done:
+            env.reset(ctxs[(wid + k) % 60])
+            des = env.robot_state().copy()
+    return n_steps, time.perf_counter() - t0
+
+
+def cpu_sample(n_workers: int, steps_per_worker: int, pool=None):
+    """Bounded sample of the workload on `n_workers` cores; returns (env-steps/s aggregate, wall seconds)."""
+    jobs = [(w, steps_per_worker, 1000 + w) for w in range(n_workers)]
+    t0 = time.perf_counter()
+    if n_workers == 1:
+        res = [_cpu_worker(jobs[0])]
+    else:
+        res = pool.map(_cpu_worker, jobs)
+    wall = time.perf_counter() - t0
+    return sum(r[0] for r in res) / wall, wall
+
+
+def run_reference(args):
+    """--impl reference: the oracle port on all host cores (kind "port"); each step is a bounded sample."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle.oracle as oo
+    oo.build()
+    cores = os.cpu_count() or 1
+    steps_per_worker = 256
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        for _ in range(args.warmup):
+            cpu_sample(cores, 32, pool)
+        t0 = time.perf_counter()
+        tot = 0
+        for _ in range(args.steps):
+            v, wall = cpu_sample(cores, steps_per_worker, pool)
+            tot += steps_per_worker * cores
+        dt = time.perf_counter() - t0
+    value = tot / dt
+    sample = f"{cores} worker processes x {steps_per_worker} env steps of the Pushing workload per step (one fp64 oracle env per core)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "pushing-4096env-randomwalk (bounded CPU sample: one env per host core)", "task": TASK, "n_substeps": 35},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+class ClockSampler:
+    FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.strip().split(", ") for r in open(self.f.name) if r.strip()]
+        os.unlink(self.f.name)
+        sm, reasons = [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                out["sm_max_mhz"] = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+        out["reasons"] = sorted(reasons)
+        out["samples"] = len(sm)
+        return out
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    from d3il_b200.batched_env import BatchedEnv
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    n = args.envs
+    K, W = args.steps, max(args.warmup, 3)
+
+    ctxs = load_contexts()
+    ctx_ids = (np.arange(n) + rank * n) % 60
+    ctx_t = torch.tensor(ctxs[ctx_ids], dtype=torch.float32, device=dev)
+    env = BatchedEnv(TASK, n, local)
+    env.reset(ctx_t)
+    quat = torch.tensor([0.0, 1.0, 0.0, 0.0], device=dev).repeat(n, 1)
+    tcp0 = env.robot_state().clone()
+    des = torch.cat([tcp0, quat], 1).contiguous()
+    lo = torch.tensor(WORKSPACE_LO, device=dev)
+    hi = torch.tensor(WORKSPACE_HI, device=dev)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    # synthetic action stream, resident in HBM before the timed region: deltas ~ U(-0.01, 0.01)^2 per env per step
+    pool_len = 64
+    deltas = (torch.rand(pool_len, n, 2, generator=gen, device=dev) * 0.02 - 0.01)
+    returns = torch.zeros(n, 3, device=dev)          # per-env episode result rows (success, mode, mean_distance)
+
+    def one_step(k):
+        des[:, :2] = torch.minimum(torch.maximum(des[:, :2] + deltas[k % pool_len], lo), hi)
+        obs, rew, done, info = env.step(des)
+        # episode bookkeeping + auto-reset of finished envs (masked reset kernel; desired pose snaps back to the start pose)
+        returns.copy_(torch.where(done.bool().unsqueeze(1), info[:, :3], returns))
+        env.reset(ctx_t, done)
+        des[:, :3] = torch.where(done.bool().unsqueeze(1), tcp0, des[:, :3])
+
+    for k in range(W):
+        one_step(k)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches0 = env.kernel_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for k in range(K):
+        one_step(W + k)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    launches = env.kernel_launches - launches0
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        dist.barrier()
+        # the path's only exchange: gather the per-env episode result rows at rollout end (replaces the shared-memory
+        # result tensors of simulation/pushing_sim.py:97-99)
+        gathered = [torch.zeros_like(returns) for _ in range(world)] if rank == 0 else None
+        dist.gather(returns, gathered, dst=0)
+    clocks = sampler.stop() if sampler else None
+    value = world * n * K / (ms * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-kernel device time (CUDA events on the launching stream, inside the library) for the roofline object
+    env.set_profiling(True)
+    for k in range(8):
+        one_step(k)
+    ik_ms, env_ms, nprof = env.get_profile()
+    env.set_profiling(False)
+    k_env_ms = env_ms / max(nprof, 1)
+    k_ik_ms = ik_ms / max(nprof, 1)
+    n_state = env.scene.header["nq"] + env.scene.header["nv"] * 2 + 9 + 9 + 7 + 16      # persistent fp32 words per env
+    alg_bytes_env = 2 * 4 * n_state + 4 * env.act_dim + 4 * env.obs_dim + 4 + 1 + 4 * env.info_dim
+    alg_bytes_launch = alg_bytes_env * n
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = alg_bytes_launch / (k_env_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                "kernel": "k_env", "kernel_ms": k_env_ms, "ik_kernel_ms": k_ik_ms, "alg_bytes_per_env_step": alg_bytes_env,
+                "note": "fused 35-tick kernel is ALU/latency-bound, not HBM-bound (SURVEY §8d); see DESIGN.md for the fp32 issue-rate view"}
+
+    # ---- e2e: same workload through the host-buffer C ABI (numpy in/out, H2D + D2H every step)
+    e2e_steps = max(8, min(K, 64))
+    env.reset(ctx_t)
+    tcp_h = env.robot_state_host()
+    des_h = np.concatenate([tcp_h, np.tile(np.array([0, 1, 0, 0], np.float32), (n, 1))], 1).astype(np.float32)
+    deltas_h = deltas[:, :, :].cpu().numpy()
+    ctx_h = ctxs[ctx_ids].astype(np.float32)
+    lo_h, hi_h = np.array(WORKSPACE_LO, np.float32), np.array(WORKSPACE_HI, np.float32)
+    h2d = d2h = 0
+    for k in range(3):
+        env.step_host(des_h)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        des_h[:, :2] = np.clip(des_h[:, :2] + deltas_h[k % pool_len], lo_h, hi_h)
+        obs_h, rew_h, done_h, info_h = env.step_host(des_h)
+        h2d += des_h.nbytes
+        d2h += obs_h.nbytes + rew_h.nbytes + done_h.nbytes + info_h.nbytes
+        if done_h.any():
+            env.reset_host(ctx_h, done_h)
+            h2d += ctx_h.nbytes + done_h.nbytes
+            des_h[done_h.astype(bool), :3] = tcp_h[done_h.astype(bool)]
+    dt = time.perf_counter() - t0
+    e2e = {"value": n * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d // e2e_steps, "d2h_bytes_per_step": d2h // e2e_steps,
+           "steps": e2e_steps, "n_gpus": 1}
+
+    # ---- CPU baseline beside it: the oracle port on this box's host cores, bounded sample
+    import oracle.oracle as oo
+    oo.build()
+    cores = os.cpu_count() or 1
+    spw = 192
+    with mp.get_context("fork").Pool(cores) as pool:
+        cpu_sample(cores, 16, pool)
+        cpu_val, cpu_wall = cpu_sample(cores, spw, pool)
+    one_val, one_wall = cpu_sample(1, 1500)
+    cpu_baseline = {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
+                    "sample": f"{cores} processes x {spw} env steps (one fp64 oracle env per core, {cpu_wall:.1f} s); single core: {one_val:.0f} env-steps/s over 1500 steps",
+                    "single_core_value": one_val}
+
+    print(json.dumps({
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"pushing-{n}env-per-gpu-randomwalk", "task": TASK, "envs_per_gpu": n, "n_substeps": 35, "episode_len": 400,
+                   "auto_reset": True, "l2_note": "state+trajectory working set per step is rewritten every step (no cross-step reuse of inputs); timing is launch-to-launch on one stream"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "target": {"env_steps_per_sec": 1.0e6, "met": bool(value >= 1.0e6)},
+    }))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=N_ENVS, help="envs per GPU")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -130,6 +130,16 @@ class BatchedEnv:
     def set_solver(self, tolerance: float, max_iterations: int):
         _lib.check(self._L.d3il_set_solver(self._h, float(tolerance), int(max_iterations)), "d3il_set_solver")
 
+    def set_profiling(self, on: bool):
+        _lib.check(self._L.d3il_set_profiling(self._h, int(on)), "d3il_set_profiling")
+
+    def get_profile(self):
+        """(ms spent in the IK kernel, ms spent in the env-step kernel, number of profiled env steps)."""
+        ms = (C.c_double * 2)()
+        n = C.c_longlong()
+        _lib.check(self._L.d3il_get_profile(self._h, ms, C.byref(n)), "d3il_get_profile")
+        return ms[0], ms[1], n.value
+
     @property
     def kernel_launches(self) -> int:
         return int(self._L.d3il_kernel_launches(self._h))

@@ -55,6 +55,7 @@ struct d3il_env {
   // pinned + device staging for the *_host calls
   float *h_in, *h_out, *d_in, *d_out; uint8_t *h_mask, *d_mask; size_t in_floats, out_floats;
   cudaStream_t own_stream;
+  int profiling; cudaEvent_t ev[3]; double prof_ms[2]; long long prof_n;
 };
 
 // ------------------------------------------------------------------------------------------------ kernels
@@ -208,6 +209,8 @@ extern "C" int d3il_create(d3il_env** out, const void* blob, size_t nbytes, int 
   CK(cudaMalloc(&h->d_out, h->out_floats * sizeof(float)));
   CK(cudaMalloc(&h->d_mask, n_envs));
   CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  h->profiling = 0; h->prof_ms[0] = h->prof_ms[1] = 0; h->prof_n = 0;
+  for (int i = 0; i < 3; i++) CK(cudaEventCreate(&h->ev[i]));
   *out = h;
   return 0;
 }
@@ -234,6 +237,16 @@ extern "C" int d3il_set_solver(d3il_env* h, double tol, int max_iter) {
   return 0;
 }
 extern "C" long long d3il_kernel_launches(const d3il_env* h) { return h ? h->launches : 0; }
+extern "C" int d3il_set_profiling(d3il_env* h, int on) {
+  if (!h) { g_err = "d3il_set_profiling: null handle"; return -1; }
+  h->profiling = on; h->prof_ms[0] = h->prof_ms[1] = 0; h->prof_n = 0;
+  return 0;
+}
+extern "C" int d3il_get_profile(const d3il_env* h, double out_ms[2], long long* n_steps) {
+  if (!h || !out_ms || !n_steps) { g_err = "d3il_get_profile: bad arguments"; return -1; }
+  out_ms[0] = h->prof_ms[0]; out_ms[1] = h->prof_ms[1]; *n_steps = h->prof_n;
+  return 0;
+}
 
 static inline int env_grid(const d3il_env* h) { return (h->n + ENVS_PER_CTA - 1) / ENVS_PER_CTA; }
 
@@ -251,10 +264,21 @@ extern "C" int d3il_step(d3il_env* h, const float* action, float* obs, float* re
   if (!h || !action || !obs || !reward || !done || !info) { g_err = "d3il_step: null argument"; return -1; }
   CK(cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;
+  if (h->profiling) CK(cudaEventRecord(h->ev[0], s));
   k_ik<<<(h->n + 127) / 128, 128, 0, s>>>(h->d, action, h->m.n_substeps, 1);
+  if (h->profiling) CK(cudaEventRecord(h->ev[1], s));
   k_env<<<env_grid(h), CTA_THREADS, h->smem_bytes, s>>>(h->d, h->m.n_substeps, 1, obs, reward, done, info);
   h->launches += 2;
   CK(cudaGetLastError());
+  if (h->profiling) {
+    // per-kernel device time on the launching stream (bench.py roofline); synchronises, so only for profiling passes
+    CK(cudaEventRecord(h->ev[2], s));
+    CK(cudaEventSynchronize(h->ev[2]));
+    float a = 0, b = 0;
+    CK(cudaEventElapsedTime(&a, h->ev[0], h->ev[1]));
+    CK(cudaEventElapsedTime(&b, h->ev[1], h->ev[2]));
+    h->prof_ms[0] += a; h->prof_ms[1] += b; h->prof_n += 1;
+  }
   return 0;
 }
 

@@ -19,7 +19,7 @@ DIM_NAMES = ("obs", "act", "ctx", "info", "state", "n_envs", "n_substeps", "max_
 EXPORTS = (
     "d3il_create", "d3il_destroy", "d3il_last_error", "d3il_dims", "d3il_reset", "d3il_step", "d3il_robot_state",
     "d3il_reset_host", "d3il_step_host", "d3il_robot_state_host", "d3il_substep", "d3il_get_state", "d3il_set_state",
-    "d3il_set_solver", "d3il_kernel_launches",
+    "d3il_set_solver", "d3il_kernel_launches", "d3il_set_profiling", "d3il_get_profile",
 )
 
 
@@ -56,6 +56,8 @@ def lib():
         L.d3il_set_solver.argtypes = [vp, C.c_double, C.c_int]
         L.d3il_kernel_launches.argtypes = [vp]
         L.d3il_kernel_launches.restype = C.c_longlong
+        L.d3il_set_profiling.argtypes = [vp, C.c_int]
+        L.d3il_get_profile.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
         _LIB = L
     return _LIB
 

@@ -68,6 +68,10 @@ int d3il_set_state(d3il_env* env, const double* in_host, int env_index);
 /* Solver controls (Newton tolerance on the scaled gradient, iteration cap) and launch accounting for bench.py. */
 int d3il_set_solver(d3il_env* env, double tolerance, int max_iterations);
 long long d3il_kernel_launches(const d3il_env* env);
+/* Profiling passes: when on, d3il_step brackets its two kernels (IK reference, env step) with CUDA events on the
+ * launching stream and accumulates their device times (ms); d3il_step then synchronises, so keep it off when timing. */
+int d3il_set_profiling(d3il_env* env, int on);
+int d3il_get_profile(const d3il_env* env, double out_ms[2], long long* n_steps);
 
 #ifdef __cplusplus
 }

@@ -118,7 +118,8 @@ def test_avoiding_episode_closed_loop():
     env = _benv("avoiding", n)
     env.reset()
     tcp0 = env.robot_state().cpu().numpy()[0].astype(np.float64)
-    # streams that stay in the free corridor x in [0.3, 0.4] (left of every obstacle), moving +y to the finish line
+    # streams 0..5 stay in the free corridor x < 0.315 (left of every obstacle) and cross the finish line;
+    # streams 6, 7 run into obstacle l3_top (x 0.35, y 0.26) and must terminate by failure in the same env step
     streams = []
     for i in range(n):
         rng = np.random.default_rng(i)
@@ -134,7 +135,7 @@ def test_avoiding_episode_closed_loop():
     oracles = [OracleEnv(blob, sc.header) for _ in range(n)]
     for oe in oracles:
         oe.reset()
-    finished = np.zeros(n, bool)
+    finished, touched, outcome = np.zeros(n, bool), np.zeros(n, bool), np.zeros(n)
     for k in range(250):
         obs, rew, done, info = env.step(torch.tensor(streams[:, k], dtype=torch.float32, device="cuda"))
         obs, done, info = obs.cpu().numpy(), done.cpu().numpy(), info.cpu().numpy()
@@ -142,10 +143,16 @@ def test_avoiding_episode_closed_loop():
             if finished[i]:
                 continue
             oo, rr, dd, ii = oe.step(streams[i, k])
-            assert np.allclose(obs[i], oo, rtol=1e-4, atol=2e-5), (k, i, obs[i], oo)
+            if i < 6 or not touched[i]:
+                assert np.allclose(obs[i], oo, rtol=1e-4, atol=2e-5), (k, i, obs[i], oo)
+            else:                      # after the 30 N impact with the obstacle only the outcome is compared
+                assert np.allclose(obs[i], oo, atol=1e-3), (k, i, obs[i], oo)
+            touched[i] |= oe.get_state()[27 + 44 + 7] != 0
             assert bool(done[i]) == dd and np.array_equal(info[i, :10], ii[:10]), (k, i, info[i], ii)
             finished[i] = dd
-    assert finished.all()          # every stream crosses the finish line (success) before the step cap
+            outcome[i] = ii[0]
+    assert finished.all()          # every stream ends before the step cap
+    assert list(outcome) == [1, 1, 1, 1, 1, 1, 0, 0]      # six successes, two obstacle hits
     env.close()
 
 
