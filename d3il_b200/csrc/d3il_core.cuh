@@ -64,6 +64,20 @@ template <int G> DEVFN int gori(const Cx& cx, int x) {
 
 #define LANES(i, n) for (int i = cx.lane; i < (n); i += G)
 
+// Register-distributed vectors: element i lives in slot i / G of lane i % G.
+#define D3_SLOTS(G) ((D3_MAXV + (G) - 1) / (G))
+template <int G>
+DEVFN real elem_bcast(const Cx& cx, const real* xr, int c) {
+#ifdef D3IL_EMU
+  return xr[c];
+#else
+  real v = 0;
+#pragma unroll
+  for (int sl = 0; sl < D3_SLOTS(G); sl++) { real t = __shfl_sync(cx.mask, xr[sl], c % G, G); if (sl == c / G) v = t; }
+  return v;
+#endif
+}
+
 // ------------------------------------------------------------------------------------------------ model tables
 // Float copy of the D3SC scene blob (d3il_b200/scene/blob.py) + derived index tables, staged into shared memory
 // once per CTA.  All arrays are sized for the largest scene we compile (Sorting-6: 15 links, nv 45).
@@ -97,6 +111,10 @@ struct Model {
   unsigned l_desc[D3_MAXLINK];            // bit j set: link j is a descendant-or-self
   int l_ref[D3_MAXLINK];                  // link whose origin is the spatial reference point of this link's kinematic tree
   int d_link[D3_MAXV];
+  int d_bs[D3_MAXV], d_be[D3_MAXV];       // [start, end) of the dof's kinematic-tree block (M is block diagonal over these)
+  int maxblk;                             // largest block
+  int ndamp, damp_first, damp_end;        // trailing damped dofs of the arm block (implicit-damping refactor)
+  unsigned char tri_i[136], tri_j[136];   // row-major lower-triangle unranking table for n <= 16
   unsigned char mp_a[D3_MAXV * 8], mp_b[D3_MAXV * 8];   // (a,b) list of related dof pairs, a >= b
   tab_t link[D3_MAXLINK * D3_LINK_W];
   tab_t geom[D3_MAXGEOM * D3_GEOM_W];
@@ -115,11 +133,11 @@ struct Lay {
                                                     // tcp: pos3+quat4 ; misc: 16 scalars (see ST_*)
   int n_state;
   // scratch
-  int xpos, xmat, S, I10, Ic, vel, cj, frc, F, M, Lm, H, bias, qfrc_smooth, qacc_smooth, qacc, qfrc_c, grad, pvec, Ma, tmpv;
+  int xpos, xmat, S, I10, Ic, vel, cj, frc, F, M, mdinv, mpiv, H, hdinv, hpiv, bias, qfrc_smooth, qacc_smooth, qacc, qfrc_c, grad, pvec, Ma, tmpv;
   int act, jt, con, ncon_pair, J, aref, D, jar, frcE, Jp, hd, hb, etype, econ, total;
 };
 enum { ST_GRIP_SET = 0, ST_GRASP, ST_CTRL_MODE, ST_STEP, ST_TERM, ST_STATUS, ST_OBST, ST_TASK0, ST_TASK1, ST_TASK2, ST_TASK3, ST_NMISC = 16 };
-#define D3_CON_W 20    // per contact: pos3, frame9, dist, incl, mu, dim, g1, g2, pair, row0
+#define D3_CON_W 24    // per contact: pos3, frame9, dist, incl, mu, dim, g1, g2, pair, row0, dof ranges a0,a1,b0,b1
 
 static inline void d3il_layout(const Model& m, Lay& L) {
   int o = 0;
@@ -128,7 +146,7 @@ static inline void d3il_layout(const Model& m, Lay& L) {
   L.n_state = o;
   L.xpos = take(3 * m.nlink); L.xmat = take(9 * m.nlink); L.S = take(6 * m.nv); L.I10 = take(10 * m.nlink); L.Ic = take(10 * m.nlink);
   L.vel = take(6 * m.nlink); L.cj = take(6 * m.nlink); L.frc = take(6 * m.nlink); L.F = take(6 * m.nv);
-  L.M = take(m.nv * m.nv); L.Lm = take(m.nv * m.nv); L.H = take(m.nv * m.nv);
+  L.M = take(m.nv * m.nv); L.mdinv = take(m.nv); L.mpiv = take(m.nv); L.H = take(m.nv * m.nv); L.hdinv = take(m.nv); L.hpiv = take(m.nv);
   L.bias = take(m.nv); L.qfrc_smooth = take(m.nv); L.qacc_smooth = take(m.nv); L.qacc = take(m.nv); L.qfrc_c = take(m.nv);
   L.grad = take(m.nv); L.pvec = take(m.nv); L.Ma = take(m.nv); L.tmpv = take(m.nv);
   L.act = take(D3_NROB); L.jt = take(3 * D3_NARM); L.con = take(D3_CON_W * m.maxcon); L.ncon_pair = take(m.npair + 4);
@@ -318,7 +336,7 @@ DEVFN void dynamics(const Cx& cx, const Model& m, const Lay& L, real* w) {
     int a = m.mp_a[e], b = m.mp_b[e];
     real s = 0;
     for (int k = 0; k < 6; k++) s += w[L.S + 6 * b + k] * w[L.F + 6 * a + k];
-    w[L.M + a * nv + b] = s; w[L.M + b * nv + a] = s;
+    w[L.M + b * nv + a] = s;                                          // upper triangle + diagonal hold M (b <= a)
   }
   LANES(d, nv) {
     int li = m.d_link[d];
@@ -662,11 +680,27 @@ DEVFN real impedance(const real* solimp, real pos, real margin) {
   return dmin + y * (dmax - dmin);
 }
 
-// Rows: joint limits first, then dim rows per active contact (elliptic).  Returns nefc (all lanes).
+// dof range touched by a geom's link: robot links reach dofs [0, own dof]; free bodies their 6 dofs; static: empty
+DEVFN void link_range(const Model& m, int li, int* lo, int* hi) {
+  if (li < 0) { *lo = 0; *hi = 0; return; }
+  if (m.l_jtype[li] == 2) { *lo = m.l_dadr[li]; *hi = m.l_dadr[li] + 6; return; }
+  *lo = m.d_bs[m.l_dadr[li]]; *hi = m.l_dadr[li] + 1;
+}
+
+// J row . v restricted to the contact's dof ranges
+DEVFN real jrow_dot(const real* Jrow, const real* v, int a0, int a1, int b0, int b1) {
+  real s = 0;
+  for (int d = a0; d < a1; d++) s += Jrow[d] * v[d];
+  for (int d = b0; d < b1; d++) s += Jrow[d] * v[d];
+  return s;
+}
+
+// Rows: joint limits first (one dof each), then dim rows per active contact (elliptic).  Returns nefc (all lanes);
+// *coupled is set when some contact joins two different kinematic-tree blocks (then H is not block diagonal).
 template <int G>
-DEVFN int make_constraints(const Cx& cx, const Model& m, const Lay& L, real* w, int ncon) {
+DEVFN int make_constraints(const Cx& cx, const Model& m, const Lay& L, real* w, int ncon, int* nlimit, int* coupled) {
   const int nv = m.nv;
-  // --- joint limit rows: deterministic order (link, side); every lane scans (cheap: <= 18 candidates)
+  // --- joint limit rows: deterministic order (link, side); every lane scans the same state
   int ne = 0;
   for (int i = 0; i < m.nlink; i++) {
     if (!m.l_limited[i] || m.l_jtype[i] == 2) continue;
@@ -676,7 +710,6 @@ DEVFN int make_constraints(const Cx& cx, const Model& m, const Lay& L, real* w, 
       real dist = side == 0 ? q - (real)Lk[23] : (real)Lk[24] - q;
       if (dist >= 0) continue;
       if (ne < m.maxrow) {
-        LANES(d, nv) w[L.J + ne * nv + d] = 0;
         LANES(z, 1) {
           real solref[2] = {(real)m.ctrl[D3C_JNT_SOLREF], (real)m.ctrl[D3C_JNT_SOLREF + 1]}, solimp[5];
           for (int k = 0; k < 5; k++) solimp[k] = m.ctrl[D3C_JNT_SOLIMP + k];
@@ -686,31 +719,41 @@ DEVFN int make_constraints(const Cx& cx, const Model& m, const Lay& L, real* w, 
           real Rv = maxr((real)1e-15, (1 - imp) / imp * (real)Lk[27]);
           w[L.D + ne] = 1 / Rv;
           w[L.aref + ne] = -bb * sg * w[L.qvel + m.l_dadr[i]] - kk * imp * dist;
-          w[L.etype + ne] = 0; w[L.econ + ne] = -1;
+          w[L.etype + ne] = 0;
+          w[L.econ + ne] = (real)(side == 0 ? m.l_dadr[i] + 1 : -(m.l_dadr[i] + 1));     // limit rows: signed dof id (+lower / -upper)
         }
-        gsync<G>(cx);
-        LANES(z, 1) w[L.J + ne * nv + m.l_dadr[i]] = side == 0 ? (real)1 : (real)-1;
         ne++;
       } else { LANES(z, 1) w[L.misc + ST_STATUS] = (real)(((int)w[L.misc + ST_STATUS]) | 2); }
     }
   }
-  // --- contact rows: row0 by prefix over contact dims (every lane computes the same prefix)
-  int row = ne;
+  *nlimit = ne;
+  // --- contact rows: row0 by prefix over contact dims (every lane computes the same prefix), dof ranges per contact
+  int row = ne, cpl = 0;
   for (int c = 0; c < ncon; c++) {
     real* cc = w + L.con + D3_CON_W * c;
     int dim = (int)cc[15];
     int active = cc[12] < cc[13];
-    if (active && row + dim <= m.maxrow) { LANES(z, 1) cc[19] = (real)row; row += dim; }
+    int l1 = (int)m.geom[D3_GEOM_W * (int)cc[16] + 1], l2 = (int)m.geom[D3_GEOM_W * (int)cc[17] + 1];
+    int a0, a1, b0, b1;
+    link_range(m, l1, &a0, &a1); link_range(m, l2, &b0, &b1);
+    if (a1 > a0 && b1 > b0) {
+      if (b0 < a0) { int t0 = a0, t1 = a1; a0 = b0; a1 = b1; b0 = t0; b1 = t1; }
+      if (b0 < a1) { a1 = a1 > b1 ? a1 : b1; b0 = b1 = 0; }                  // same tree: merge into one range
+      else if (active) cpl = 1;                                               // two different blocks
+    } else if (a1 == a0) { a0 = b0; a1 = b1; b0 = b1 = 0; }
+    if (active && row + dim <= m.maxrow) { LANES(z, 1) { cc[19] = (real)row; cc[20] = (real)a0; cc[21] = (real)a1; cc[22] = (real)b0; cc[23] = (real)b1; } row += dim; }
     else { LANES(z, 1) { cc[19] = -1; if (active) w[L.misc + ST_STATUS] = (real)(((int)w[L.misc + ST_STATUS]) | 2); } }
   }
+  *coupled = cpl;
   gsync<G>(cx);
   const real impratio = m.ctrl[D3C_IMPRATIO];
-  // Jacobian rows: one (contact, dof) item per lane step
+  // Jacobian rows: one (contact, dof) item per lane step; entries outside the contact's dof ranges are never read
   LANES(item, ncon * nv) {
     int c = item / nv, d = item - c * nv;
     const real* cc = w + L.con + D3_CON_W * c;
     int row0 = (int)cc[19];
     if (row0 < 0) continue;
+    if (!((d >= (int)cc[20] && d < (int)cc[21]) || (d >= (int)cc[22] && d < (int)cc[23]))) continue;
     int dim = (int)cc[15];
     int l1 = (int)m.geom[D3_GEOM_W * (int)cc[16] + 1], l2 = (int)m.geom[D3_GEOM_W * (int)cc[17] + 1];
     int dl = m.d_link[d];
@@ -747,8 +790,7 @@ DEVFN int make_constraints(const Cx& cx, const Model& m, const Lay& L, real* w, 
     cc[14] = fr[0] * sqrt(R1 / R0);
     for (int r = 0; r < dim; r++) {
       real Rv = r == 0 ? R0 : (r == 1 ? R1 : R1 * fr[0] * fr[0] / (fr[r - 1] * fr[r - 1]));
-      real vel = 0;
-      for (int d = 0; d < nv; d++) vel += w[L.J + (row0 + r) * nv + d] * w[L.qvel + d];
+      real vel = jrow_dot(w + L.J + (row0 + r) * nv, w + L.qvel, (int)cc[20], (int)cc[21], (int)cc[22], (int)cc[23]);
       w[L.D + row0 + r] = 1 / Rv;
       w[L.aref + row0 + r] = -bb * vel - (r == 0 ? kk * imp * (cc[12] - cc[13]) : 0);
       w[L.etype + row0 + r] = r == 0 ? 1 : 2; w[L.econ + row0 + r] = (real)c;
@@ -758,101 +800,161 @@ DEVFN int make_constraints(const Cx& cx, const Model& m, const Lay& L, real* w, 
   return row;
 }
 
-// Evaluate the constraint cost at jar (workspace array `jar_off`): forces -> frc_off, optional Hessian pieces
-// (hd per row, 3x3/4x4 cone block per contact in hb; hb[...][0] < -0.5e30 marks "no cone block").
-// Returns the group-wide cost.  One lane per limit row / per contact.
-template <int G, bool HESS>
-DEVFN real constraint_eval(const Cx& cx, const Model& m, const Lay& L, real* w, int ne, int ncon, int jar_off, int frc_off, int hd_off, int hb_off) {
-  real cost = 0;
-  LANES(i, ne) {
-    if (w[L.etype + i] != 0) continue;
-    real j = w[jar_off + i], Dv = w[L.D + i];
-    if (j < 0) { cost += (real)0.5 * Dv * j * j; w[frc_off + i] = -Dv * j; if (HESS) w[hd_off + i] = Dv; }
-    else { w[frc_off + i] = 0; if (HESS) w[hd_off + i] = 0; }
+// jar = J v - aref for every row (v: workspace offset of a dof vector).  One lane per limit row / per contact.
+template <int G>
+DEVFN void eval_jar(const Cx& cx, const Model& m, const Lay& L, real* w, int nlimit, int ncon, int v_off, int out_off, bool sub_aref) {
+  const int nv = m.nv;
+  LANES(i, nlimit) {
+    int sd = (int)w[L.econ + i];
+    real s = sd > 0 ? w[v_off + sd - 1] : -w[v_off - sd - 1];
+    w[out_off + i] = sub_aref ? s - w[L.aref + i] : s;
   }
   LANES(c, ncon) {
     const real* cc = w + L.con + D3_CON_W * c;
     int i = (int)cc[19];
     if (i < 0) continue;
     int dim = (int)cc[15];
-    const tab_t* pr = m.pair + D3_PAIR_W * (int)cc[18];
-    real mu = cc[14], U[4], fr[3] = {(real)pr[3], (real)pr[4], (real)pr[5]}, T = 0;
-    U[0] = w[jar_off + i] * mu;
-    for (int j = 1; j < dim; j++) { U[j] = w[jar_off + i + j] * fr[j - 1]; T += U[j] * U[j]; }
-    T = sqrt(T);
-    real N = U[0];
-    if (HESS) w[hb_off + 9 * c] = (real)-1e30;
-    if (N >= mu * T || (T <= 0 && N >= 0)) {
-      for (int j = 0; j < dim; j++) { w[frc_off + i + j] = 0; if (HESS) w[hd_off + i + j] = 0; }
-    } else if (mu * N + T <= 0 || (T <= 0 && N < 0)) {
-      for (int j = 0; j < dim; j++) { real Dv = w[L.D + i + j], jj = w[jar_off + i + j]; cost += (real)0.5 * Dv * jj * jj; w[frc_off + i + j] = -Dv * jj; if (HESS) w[hd_off + i + j] = Dv; }
-    } else {
-      real Dm = w[L.D + i] / maxr((real)1e-15, mu * mu * (1 + mu * mu)), NmT = N - mu * T;
-      cost += (real)0.5 * Dm * NmT * NmT;
-      real f0 = -Dm * NmT * mu;
-      w[frc_off + i] = f0;
-      for (int j = 1; j < dim; j++) w[frc_off + i + j] = -f0 / T * U[j] * fr[j - 1];
-      if (HESS) {
-        // condim 3 only stores a 3x3 block (condim 4 contacts are not generated by the rod tasks)
-        real g[3]; g[0] = mu; g[1] = -mu * fr[0] * U[1] / T; g[2] = -mu * fr[1] * U[2] / T;
-        for (int a = 0; a < 3; a++) for (int b2 = 0; b2 < 3; b2++) {
-          real v = g[a] * g[b2];
-          if (a > 0 && b2 > 0) v -= mu * NmT / T * fr[a - 1] * fr[b2 - 1] * ((a == b2 ? (real)1 : (real)0) - U[a] * U[b2] / (T * T));
-          w[hb_off + 9 * c + 3 * a + b2] = Dm * v;
-        }
-      }
+    for (int r = 0; r < dim; r++) {
+      real s = jrow_dot(w + L.J + (i + r) * nv, w + v_off, (int)cc[20], (int)cc[21], (int)cc[22], (int)cc[23]);
+      w[out_off + i + r] = sub_aref ? s - w[L.aref + i + r] : s;
     }
-  }
-  return gsum<G>(cx, cost);
-}
-
-// Dense in-place Cholesky of the n x n matrix at `A` (lower), lane-parallel right-looking.  The strict lower triangle
-// receives L; the diagonal keeps the pivots d_k = L_kk^2 (so no lane ever rewrites an entry the others still read).
-// Returns 0 ok / 1 not positive definite.
-template <int G>
-DEVFN int chol_factor(const Cx& cx, real* A, int n) {
-  int bad = 0;
-  for (int k = 0; k < n; k++) {
-    real dkk = A[k * n + k];
-    if (!(dkk > 0)) { bad = 1; dkk = 1; }
-    real inv = 1 / sqrt(dkk);
-    int rem = n - k - 1;
-    LANES(i, rem) { A[(k + 1 + i) * n + k] *= inv; }
-    gsync<G>(cx);
-    LANES(e, rem * (rem + 1) / 2) {
-      // unrank e -> (i >= j) in the trailing block
-      int i = (int)((sqrt((real)(8 * e + 1)) - 1) * (real)0.5);
-      while (i * (i + 1) / 2 > e) i--;
-      while ((i + 1) * (i + 2) / 2 <= e) i++;
-      int j = e - i * (i + 1) / 2;
-      A[(k + 1 + i) * n + (k + 1 + j)] -= A[(k + 1 + i) * n + k] * A[(k + 1 + j) * n + k];
-    }
-    gsync<G>(cx);
-  }
-  return bad;
-}
-// Solve L L^T x = b in place.  Element x[i] is owned by lane i % G in both sweeps (each lane only ever reads entries
-// it wrote itself), so the only cross-lane traffic is the shuffle reduction of the dot products.
-template <int G>
-DEVFN void chol_solve(const Cx& cx, const real* A, int n, real* x) {
-  for (int i = 0; i < n; i++) {
-    real s = 0;
-    LANES(k, i) s += A[i * n + k] * x[k];
-    s = gsum<G>(cx, s);
-    if ((i % G) == cx.lane) x[i] = (x[i] - s) / sqrt(A[i * n + i]);
-  }
-  for (int i = n - 1; i >= 0; i--) {
-    real s = 0;
-    LANES(k, n) if (k > i) s += A[k * n + i] * x[k];
-    s = gsum<G>(cx, s);
-    if ((i % G) == cx.lane) x[i] = (x[i] - s) / sqrt(A[i * n + i]);
   }
   gsync<G>(cx);
 }
 
+// Constraint cost at jar (workspace offset jar_off): forces -> frc_off; HESS: per-limit-row curvature in hd and a 3x3
+// block per contact in hb (zero / diagonal / full for the top / bottom / middle zone of the elliptic cone).
+// Returns the group-wide cost.  One lane per limit row / per contact.
+template <int G, bool HESS>
+DEVFN real constraint_eval(const Cx& cx, const Model& m, const Lay& L, real* w, int nlimit, int ncon, int jar_off, int frc_off) {
+  real cost = 0;
+  LANES(i, nlimit) {
+    real j = w[jar_off + i], Dv = w[L.D + i];
+    if (j < 0) { cost += (real)0.5 * Dv * j * j; w[frc_off + i] = -Dv * j; if (HESS) w[L.hd + i] = Dv; }
+    else { w[frc_off + i] = 0; if (HESS) w[L.hd + i] = 0; }
+  }
+  LANES(c, ncon) {
+    const real* cc = w + L.con + D3_CON_W * c;
+    int i = (int)cc[19];
+    if (i < 0) continue;
+    const tab_t* pr = m.pair + D3_PAIR_W * (int)cc[18];
+    real mu = cc[14], U[3], fr[2] = {(real)pr[3], (real)pr[4]};
+    U[0] = w[jar_off + i] * mu; U[1] = w[jar_off + i + 1] * fr[0]; U[2] = w[jar_off + i + 2] * fr[1];
+    real T = sqrt(U[1] * U[1] + U[2] * U[2]), N = U[0];
+    real H9[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (N >= mu * T || (T <= 0 && N >= 0)) {
+      w[frc_off + i] = 0; w[frc_off + i + 1] = 0; w[frc_off + i + 2] = 0;
+    } else if (mu * N + T <= 0 || (T <= 0 && N < 0)) {
+      for (int j = 0; j < 3; j++) { real Dv = w[L.D + i + j], jj = w[jar_off + i + j]; cost += (real)0.5 * Dv * jj * jj; w[frc_off + i + j] = -Dv * jj; H9[4 * j] = Dv; }
+    } else {
+      real Dm = w[L.D + i] / maxr((real)1e-15, mu * mu * (1 + mu * mu)), NmT = N - mu * T;
+      cost += (real)0.5 * Dm * NmT * NmT;
+      real f0 = -Dm * NmT * mu;
+      w[frc_off + i] = f0; w[frc_off + i + 1] = -f0 / T * U[1] * fr[0]; w[frc_off + i + 2] = -f0 / T * U[2] * fr[1];
+      if (HESS) {
+        real g[3]; g[0] = mu; g[1] = -mu * fr[0] * U[1] / T; g[2] = -mu * fr[1] * U[2] / T;
+        for (int a = 0; a < 3; a++) for (int b2 = 0; b2 < 3; b2++) {
+          real v = g[a] * g[b2];
+          if (a > 0 && b2 > 0) v -= mu * NmT / T * fr[a - 1] * fr[b2 - 1] * ((a == b2 ? (real)1 : (real)0) - U[a] * U[b2] / (T * T));
+          H9[3 * a + b2] = Dm * v;
+        }
+      }
+    }
+    if (HESS) for (int k = 0; k < 9; k++) w[L.hb + 9 * c + k] = H9[k];
+  }
+  return gsum<G>(cx, cost);
+}
+
+// Cholesky of a symmetric matrix that is block diagonal over the partition cells [ps(i), pe(i)) (all cells advance in
+// lock-step, one column per step).  The strict lower triangle of A (leading dimension n) holds the input and receives
+// L; the running pivots live in piv[] (initialised by the caller with the diagonal), dinv[] receives 1 / L_kk.
+// Row i is owned by lane i % G.  Returns 1 if a pivot was not positive.
+template <int G>
+DEVFN int chol_factor_part(const Cx& cx, real* A, int n, const int* ps, const int* pe, bool whole, int maxsz, real* piv, real* dinv) {
+  int bad = 0;
+  for (int k = 0; k < maxsz; k++) {
+    LANES(i, n) {
+      int c = (whole ? 0 : ps[i]) + k, e = whole ? n : pe[i];
+      if (c >= e || i < c) continue;
+      real p = piv[c];
+      if (!(p > 0)) { bad = 1; p = 1; }
+      real inv = 1 / sqrt(p);
+      if (i == c) dinv[c] = inv; else A[i * n + c] *= inv;
+    }
+    gsync<G>(cx);
+    LANES(i, n) {
+      int c = (whole ? 0 : ps[i]) + k, e = whole ? n : pe[i];
+      if (c >= e || i <= c) continue;
+      real lic = A[i * n + c];
+      for (int j = c + 1; j < i; j++) A[i * n + j] -= lic * A[j * n + c];
+      piv[i] -= lic * lic;
+    }
+    gsync<G>(cx);
+  }
+  return gori<G>(cx, bad);
+}
+
+// Solve L L^T x = b in place for the same partitioned factor.  x is pulled into registers (element i in lane i % G),
+// finished elements are broadcast with shuffles; no shared-memory traffic for x and no barriers inside the sweeps.
+template <int G>
+DEVFN void chol_solve_part(const Cx& cx, const real* A, int n, const int* ps, const int* pe, bool whole, int maxsz, const real* dinv, real* x) {
+  real xr[D3_SLOTS(G)];
+#pragma unroll
+  for (int sl = 0; sl < D3_SLOTS(G); sl++) { int i = sl * G + cx.lane; xr[sl] = i < n ? x[i] : (real)0; }
+  for (int k = 0; k < maxsz; k++) {
+    real xcs[D3_SLOTS(G)];          // read phase first: every slot sees the pre-step values of x
+#pragma unroll
+    for (int sl = 0; sl < D3_SLOTS(G); sl++) {
+      int i = sl * G + cx.lane;
+      int ii = i < n ? i : n - 1;
+      int c = (whole ? 0 : ps[ii]) + k, e = whole ? n : pe[ii];
+      int cc = c < e ? c : e - 1;
+      xcs[sl] = elem_bcast<G>(cx, xr, cc) * dinv[cc];
+    }
+#pragma unroll
+    for (int sl = 0; sl < D3_SLOTS(G); sl++) {
+      int i = sl * G + cx.lane;
+      int ii = i < n ? i : n - 1;
+      int c = (whole ? 0 : ps[ii]) + k, e = whole ? n : pe[ii];
+      if (i < n && c < e) { if (i == c) xr[sl] = xcs[sl]; else if (i > c) xr[sl] -= A[i * n + c] * xcs[sl]; }
+    }
+  }
+  for (int k = maxsz - 1; k >= 0; k--) {
+    real xcs[D3_SLOTS(G)];
+#pragma unroll
+    for (int sl = 0; sl < D3_SLOTS(G); sl++) {
+      int i = sl * G + cx.lane;
+      int ii = i < n ? i : n - 1;
+      int s0 = whole ? 0 : ps[ii], c = s0 + k, e = whole ? n : pe[ii];
+      int cc = c < e ? c : e - 1;
+      xcs[sl] = elem_bcast<G>(cx, xr, cc) * dinv[cc];
+    }
+#pragma unroll
+    for (int sl = 0; sl < D3_SLOTS(G); sl++) {
+      int i = sl * G + cx.lane;
+      int ii = i < n ? i : n - 1;
+      int s0 = whole ? 0 : ps[ii], c = s0 + k, e = whole ? n : pe[ii];
+      if (i < n && c < e) { if (i == c) xr[sl] = xcs[sl]; else if (i < c && i >= s0) xr[sl] -= A[c * n + i] * xcs[sl]; }
+    }
+  }
+#pragma unroll
+  for (int sl = 0; sl < D3_SLOTS(G); sl++) { int i = sl * G + cx.lane; if (i < n) x[i] = xr[sl]; }
+  gsync<G>(cx);
+}
+
+// y_d = sum_k M[d][k] v[k] within the dof's block (M stored in the upper triangle + diagonal of the M buffer)
+DEVFN real mrow_dot(const Model& m, const real* M, int nv, int d, const real* v, const real* vsub) {
+  real s = 0;
+  for (int k = m.d_bs[d]; k < m.d_be[d]; k++) {
+    real mk = k >= d ? M[d * nv + k] : M[k * nv + d];
+    s += mk * (vsub ? v[k] - vsub[k] : v[k]);
+  }
+  return s;
+}
+
 // Newton solver on the primal problem: result in qacc / frcE / qfrc_c.  Returns iterations.
 template <int G>
-DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w, int ne, int ncon, real tol, int max_iter) {
+DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w, int ne, int nlimit, int ncon, int coupled, real tol, int max_iter) {
   const int nv = m.nv;
   if (ne == 0) {
     LANES(d, nv) { w[L.qacc + d] = w[L.qacc_smooth + d]; w[L.qfrc_c + d] = 0; }
@@ -860,19 +962,17 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
     return 0;
   }
   const real scale = 1 / ((real)m.ctrl[D3C_MEANINERTIA] * (real)(nv > 1 ? nv : 1));
+  const real* M = w + L.M;
   // ---- warm start: cheaper of qacc_warmstart and qacc_smooth
-  real cw, cs;
   {
-    LANES(i, ne) { real s = -w[L.aref + i]; for (int d = 0; d < nv; d++) s += w[L.J + i * nv + d] * w[L.warm + d]; w[L.jar + i] = s; }
-    gsync<G>(cx);
-    cw = constraint_eval<G, false>(cx, m, L, w, ne, ncon, L.jar, L.frcE, 0, 0);
+    eval_jar<G>(cx, m, L, w, nlimit, ncon, L.warm, L.jar, true);
+    real cw = constraint_eval<G, false>(cx, m, L, w, nlimit, ncon, L.jar, L.frcE);
     real part = 0;
-    LANES(d, nv) { real s = 0; for (int k = 0; k < nv; k++) s += w[L.M + d * nv + k] * (w[L.warm + k] - w[L.qacc_smooth + k]); part += (real)0.5 * (w[L.warm + d] - w[L.qacc_smooth + d]) * s; }
+    LANES(d, nv) part += (real)0.5 * (w[L.warm + d] - w[L.qacc_smooth + d]) * mrow_dot(m, M, nv, d, w + L.warm, w + L.qacc_smooth);
     cw += gsum<G>(cx, part);
     gsync<G>(cx);
-    LANES(i, ne) { real s = -w[L.aref + i]; for (int d = 0; d < nv; d++) s += w[L.J + i * nv + d] * w[L.qacc_smooth + d]; w[L.jar + i] = s; }
-    gsync<G>(cx);
-    cs = constraint_eval<G, false>(cx, m, L, w, ne, ncon, L.jar, L.frcE, 0, 0);
+    eval_jar<G>(cx, m, L, w, nlimit, ncon, L.qacc_smooth, L.jar, true);
+    real cs = constraint_eval<G, false>(cx, m, L, w, nlimit, ncon, L.jar, L.frcE);
     gsync<G>(cx);
     LANES(d, nv) w[L.qacc + d] = cw < cs ? w[L.warm + d] : w[L.qacc_smooth + d];
     gsync<G>(cx);
@@ -880,20 +980,30 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
   real cost = 0, oldcost = 0;
   int iter = 0;
   for (; iter < max_iter; iter++) {
-    LANES(i, ne) { real s = -w[L.aref + i]; for (int d = 0; d < nv; d++) s += w[L.J + i * nv + d] * w[L.qacc + d]; w[L.jar + i] = s; }
-    gsync<G>(cx);
+    eval_jar<G>(cx, m, L, w, nlimit, ncon, L.qacc, L.jar, true);
     oldcost = cost;
-    cost = constraint_eval<G, true>(cx, m, L, w, ne, ncon, L.jar, L.frcE, L.hd, L.hb);
+    cost = constraint_eval<G, true>(cx, m, L, w, nlimit, ncon, L.jar, L.frcE);
     real part = 0;
     LANES(d, nv) {
-      real s = 0;
-      for (int k = 0; k < nv; k++) s += w[L.M + d * nv + k] * (w[L.qacc + k] - w[L.qacc_smooth + k]);
+      real s = mrow_dot(m, M, nv, d, w + L.qacc, w + L.qacc_smooth);
       w[L.Ma + d] = s; part += (real)0.5 * (w[L.qacc + d] - w[L.qacc_smooth + d]) * s;
     }
     cost += gsum<G>(cx, part);
     gsync<G>(cx);
+    // grad = M (a - a_s) - J^T f : lane per dof, contacts filtered by their dof ranges
     real g2 = 0;
-    LANES(d, nv) { real s = w[L.Ma + d]; for (int i = 0; i < ne; i++) s -= w[L.J + i * nv + d] * w[L.frcE + i]; w[L.grad + d] = s; g2 += s * s; }
+    LANES(d, nv) {
+      real s = w[L.Ma + d];
+      for (int i = 0; i < nlimit; i++) { int sd = (int)w[L.econ + i]; if (sd == d + 1) s -= w[L.frcE + i]; else if (sd == -(d + 1)) s += w[L.frcE + i]; }
+      for (int c = 0; c < ncon; c++) {
+        const real* cc = w + L.con + D3_CON_W * c;
+        int i = (int)cc[19];
+        if (i < 0) continue;
+        if ((d >= (int)cc[20] && d < (int)cc[21]) || (d >= (int)cc[22] && d < (int)cc[23]))
+          s -= w[L.J + i * nv + d] * w[L.frcE + i] + w[L.J + (i + 1) * nv + d] * w[L.frcE + i + 1] + w[L.J + (i + 2) * nv + d] * w[L.frcE + i + 2];
+      }
+      w[L.grad + d] = s; g2 += s * s;
+    }
     real gn = sqrt(gsum<G>(cx, g2));
     gsync<G>(cx);
 #ifdef D3IL_DEBUG_SOLVER
@@ -901,84 +1011,76 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
 #endif
     if (scale * gn < tol) break;
     if (iter > 0 && scale * (oldcost - cost) < tol * (real)1e-3) break;
-    // ---- H = M + J^T Hc J  (dense lower, lane per entry)
-    LANES(e, nv * (nv + 1) / 2) {
-      int i = (int)((sqrt((real)(8 * e + 1)) - 1) * (real)0.5);
-      while (i * (i + 1) / 2 > e) i--;
-      while ((i + 1) * (i + 2) / 2 <= e) i++;
-      int j = e - i * (i + 1) / 2;
-      real s = w[L.M + i * nv + j];
-      for (int r = 0; r < ne; r++) {
-        real ji = w[L.J + r * nv + i];
-        if (ji == 0) continue;
-        int et = (int)w[L.etype + r];
-        int c = (int)w[L.econ + r];
-        if (et != 0 && w[L.hb + 9 * c] > (real)-0.5e30) {
-          int r0 = (int)w[L.con + D3_CON_W * c + 19], a = r - r0;
-          real t = 0;
-          for (int b2 = 0; b2 < 3; b2++) t += w[L.hb + 9 * c + 3 * a + b2] * w[L.J + (r0 + b2) * nv + j];
-          s += ji * t;
-        } else s += ji * w[L.hd + r] * w[L.J + r * nv + j];
+    // ---- H = M + J^T Hc J (lower triangle).  Block diagonal unless a contact couples two trees.
+    LANES(e, nv * nv) w[L.H + e] = 0;
+    gsync<G>(cx);
+    LANES(e, m.nmpair) { int a = m.mp_a[e], b = m.mp_b[e]; w[L.H + a * nv + b] = M[b * nv + a]; }
+    gsync<G>(cx);
+    LANES(i, nlimit) { int sd = (int)w[L.econ + i]; int d = (sd > 0 ? sd : -sd) - 1; w[L.H + d * nv + d] += w[L.hd + i]; }
+    gsync<G>(cx);
+    for (int c = 0; c < ncon; c++) {
+      const real* cc = w + L.con + D3_CON_W * c;
+      int r0 = (int)cc[19];
+      if (r0 < 0) continue;
+      int a0 = (int)cc[20], a1 = (int)cc[21], b0 = (int)cc[22], b1 = (int)cc[23], na = a1 - a0, nn = na + b1 - b0;
+      const real* Hb = w + L.hb + 9 * c;
+      const real *J0 = w + L.J + r0 * nv, *J1 = J0 + nv, *J2 = J1 + nv;
+      LANES(e, nn * (nn + 1) / 2) {
+        int li = m.tri_i[e], lj = m.tri_j[e];
+        int gi = li < na ? a0 + li : b0 + li - na, gj = lj < na ? a0 + lj : b0 + lj - na;
+        real i0 = J0[gi], i1 = J1[gi], i2 = J2[gi];
+        real t0 = i0 * Hb[0] + i1 * Hb[3] + i2 * Hb[6], t1 = i0 * Hb[1] + i1 * Hb[4] + i2 * Hb[7], t2 = i0 * Hb[2] + i1 * Hb[5] + i2 * Hb[8];
+        w[L.H + gi * nv + gj] += t0 * J0[gj] + t1 * J1[gj] + t2 * J2[gj];
       }
-      w[L.H + i * nv + j] = s;
-    }
-    gsync<G>(cx);
-    if (chol_factor<G>(cx, w + L.H, nv)) { LANES(z, 1) w[L.misc + ST_STATUS] = (real)(((int)w[L.misc + ST_STATUS]) | 4); break; }
-    LANES(d, nv) w[L.pvec + d] = -w[L.grad + d];
-    gsync<G>(cx);
-    chol_solve<G>(cx, w + L.H, nv, w + L.pvec);
-    // ---- exact line search (safeguarded 1-D Newton), quantities reduced across lanes
-    LANES(i, ne) { real s = 0; for (int d = 0; d < nv; d++) s += w[L.J + i * nv + d] * w[L.pvec + d]; w[L.Jp + i] = s; }
-    real a1 = 0, a2 = 0, a3 = 0;
-    LANES(d, nv) {
-      real s = 0;
-      for (int k = 0; k < nv; k++) s += w[L.M + d * nv + k] * w[L.pvec + k];
-      a1 += w[L.pvec + d] * s; a2 += w[L.pvec + d] * w[L.Ma + d]; a3 += w[L.grad + d] * w[L.pvec + d];
-    }
-    real pMp = gsum<G>(cx, a1), pMa = gsum<G>(cx, a2), d0 = gsum<G>(cx, a3);
-    gsync<G>(cx);
-    real lo = 0, hi = -1, alpha = 1, dlo = d0, dhi = 0;
-    // tmpv doubles as jar(alpha) (sized nv; we need ne) -> reuse hd as scratch is unsafe, so evaluate in place on frcE/H rows:
-    // jar(alpha) is written over L.hd (not needed any more this iteration), forces to L.frcE after the loop.
-    for (int ls = 0; ls < 20; ls++) {
-      LANES(i, ne) w[L.hd + i] = w[L.jar + i] + alpha * w[L.Jp + i];
       gsync<G>(cx);
-      // first and second directional derivatives from forces / cone blocks at jar(alpha)
+    }
+    LANES(d, nv) { w[L.hpiv + d] = w[L.H + d * nv + d]; w[L.pvec + d] = -w[L.grad + d]; }
+    gsync<G>(cx);
+    int maxsz = coupled ? nv : m.maxblk;
+    if (chol_factor_part<G>(cx, w + L.H, nv, m.d_bs, m.d_be, coupled != 0, maxsz, w + L.hpiv, w + L.hdinv)) {
+      LANES(z, 1) w[L.misc + ST_STATUS] = (real)(((int)w[L.misc + ST_STATUS]) | 4);
+      break;
+    }
+    chol_solve_part<G>(cx, w + L.H, nv, m.d_bs, m.d_be, coupled != 0, maxsz, w + L.hdinv, w + L.pvec);
+    // ---- exact line search (safeguarded 1-D Newton / false position), quantities reduced across lanes
+    eval_jar<G>(cx, m, L, w, nlimit, ncon, L.pvec, L.Jp, false);
+    real a1s = 0, a2s = 0, a3s = 0;
+    LANES(d, nv) {
+      real s = mrow_dot(m, M, nv, d, w + L.pvec, nullptr);
+      a1s += w[L.pvec + d] * s; a2s += w[L.pvec + d] * w[L.Ma + d]; a3s += w[L.grad + d] * w[L.pvec + d];
+    }
+    real pMp = gsum<G>(cx, a1s), pMa = gsum<G>(cx, a2s), d0 = gsum<G>(cx, a3s);
+    real lo = 0, hi = -1, alpha = 1, dlo = d0, dhi = 0;
+    for (int ls = 0; ls < 20; ls++) {
+      // first and second directional derivatives at jar + alpha Jp (nothing is written: no barrier needed)
       real d1p = 0, d2p = 0;
-      LANES(i, ne) {
-        if (w[L.etype + i] != 0) continue;
-        real j = w[L.hd + i];
+      LANES(i, nlimit) {
+        real j = w[L.jar + i] + alpha * w[L.Jp + i];
         if (j < 0) { d1p += w[L.D + i] * j * w[L.Jp + i]; d2p += w[L.D + i] * w[L.Jp + i] * w[L.Jp + i]; }
       }
       LANES(c, ncon) {
         const real* cc = w + L.con + D3_CON_W * c;
         int i = (int)cc[19];
         if (i < 0) continue;
-        int dim = (int)cc[15];
         const tab_t* pr = m.pair + D3_PAIR_W * (int)cc[18];
-        real mu = cc[14], U[4], V[4], fr[3] = {(real)pr[3], (real)pr[4], (real)pr[5]}, T = 0;
-        U[0] = w[L.hd + i] * mu; V[0] = w[L.Jp + i] * mu;
-        for (int j = 1; j < dim; j++) { U[j] = w[L.hd + i + j] * fr[j - 1]; V[j] = w[L.Jp + i + j] * fr[j - 1]; T += U[j] * U[j]; }
-        T = sqrt(T);
-        real N = U[0];
+        real mu = cc[14], U[3], V[3], jl[3], fr[2] = {(real)pr[3], (real)pr[4]};
+        for (int j = 0; j < 3; j++) jl[j] = w[L.jar + i + j] + alpha * w[L.Jp + i + j];
+        U[0] = jl[0] * mu; V[0] = w[L.Jp + i] * mu;
+        U[1] = jl[1] * fr[0]; V[1] = w[L.Jp + i + 1] * fr[0]; U[2] = jl[2] * fr[1]; V[2] = w[L.Jp + i + 2] * fr[1];
+        real T = sqrt(U[1] * U[1] + U[2] * U[2]), N = U[0];
         if (N >= mu * T || (T <= 0 && N >= 0)) {
         } else if (mu * N + T <= 0 || (T <= 0 && N < 0)) {
-          for (int j = 0; j < dim; j++) { real Dv = w[L.D + i + j]; d1p += Dv * w[L.hd + i + j] * w[L.Jp + i + j]; d2p += Dv * w[L.Jp + i + j] * w[L.Jp + i + j]; }
+          for (int j = 0; j < 3; j++) { real Dv = w[L.D + i + j], jp = w[L.Jp + i + j]; d1p += Dv * jl[j] * jp; d2p += Dv * jp * jp; }
         } else {
           // s = 0.5 Dm (N - mu T)^2 along the line: dN = V0, dT = (U_t . V_t)/T, d2T = (|V_t|^2 - dT^2)/T
           real Dm = w[L.D + i] / maxr((real)1e-15, mu * mu * (1 + mu * mu)), NmT = N - mu * T;
-          real UV = 0, VV = 0;
-          for (int j = 1; j < dim; j++) { UV += U[j] * V[j]; VV += V[j] * V[j]; }
+          real UV = U[1] * V[1] + U[2] * V[2], VV = V[1] * V[1] + V[2] * V[2];
           real dT = UV / T, d2T = (VV - dT * dT) / T, dn = V[0] - mu * dT;
           d1p += Dm * NmT * dn;
           d2p += Dm * (dn * dn - NmT * mu * d2T);
         }
       }
       real d1 = gsum<G>(cx, d1p) + pMa + alpha * pMp, d2 = gsum<G>(cx, d2p) + pMp;
-      gsync<G>(cx);
-#ifdef D3IL_DEBUG_SOLVER
-      printf("      ls %d alpha %.9g d1 %.6g d2 %.6g lo %.6g hi %.6g\n", ls, (double)alpha, (double)d1, (double)d2, (double)lo, (double)hi);
-#endif
       if (absr(d1) <= (real)1e-3 * absr(d0)) break;
       if (d1 < 0) { lo = alpha; dlo = d1; } else { hi = alpha; dhi = d1; }
       real next = alpha - d1 / d2;
@@ -994,32 +1096,34 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
       }
       alpha = next;
     }
-#ifdef D3IL_DEBUG_SOLVER
-    printf("    ls alpha %.9g lo %.6g hi %.6g d0 %.6g\n", (double)alpha, (double)lo, (double)hi, (double)d0);
-    for (int t = 0; t <= 4; t++) {
-      real al = alpha * t / 4;
-      for (int i = 0; i < ne; i++) w[L.hd + i] = w[L.jar + i] + al * w[L.Jp + i];
-      real cc_ = constraint_eval<G, false>(cx, m, L, w, ne, ncon, L.hd, L.tmpv + 0 * 0 + 0, 0, 0);
-      printf("      phi(%.4g) = %.10g (constraint %.10g)\n", (double)al, (double)(cc_ + al * pMa + 0.5 * al * al * pMp), (double)cc_);
-    }
-#endif
     LANES(d, nv) w[L.qacc + d] += alpha * w[L.pvec + d];
     gsync<G>(cx);
   }
   if (iter >= max_iter) {
     // final force evaluation at the last iterate
-    LANES(i, ne) { real s = -w[L.aref + i]; for (int d = 0; d < nv; d++) s += w[L.J + i * nv + d] * w[L.qacc + d]; w[L.jar + i] = s; }
-    gsync<G>(cx);
-    constraint_eval<G, false>(cx, m, L, w, ne, ncon, L.jar, L.frcE, 0, 0);
+    eval_jar<G>(cx, m, L, w, nlimit, ncon, L.qacc, L.jar, true);
+    constraint_eval<G, false>(cx, m, L, w, nlimit, ncon, L.jar, L.frcE);
     gsync<G>(cx);
   }
-  LANES(d, nv) { real s = 0; for (int i = 0; i < ne; i++) s += w[L.J + i * nv + d] * w[L.frcE + i]; w[L.qfrc_c + d] = s; }
+  // qfrc_constraint = J^T f
+  LANES(d, nv) {
+    real s = 0;
+    for (int i = 0; i < nlimit; i++) { int sd = (int)w[L.econ + i]; if (sd == d + 1) s += w[L.frcE + i]; else if (sd == -(d + 1)) s -= w[L.frcE + i]; }
+    for (int c = 0; c < ncon; c++) {
+      const real* cc = w + L.con + D3_CON_W * c;
+      int i = (int)cc[19];
+      if (i < 0) continue;
+      if ((d >= (int)cc[20] && d < (int)cc[21]) || (d >= (int)cc[22] && d < (int)cc[23]))
+        s += w[L.J + i * nv + d] * w[L.frcE + i] + w[L.J + (i + 1) * nv + d] * w[L.frcE + i + 1] + w[L.J + (i + 2) * nv + d] * w[L.frcE + i + 2];
+    }
+    w[L.qfrc_c + d] = s;
+  }
   gsync<G>(cx);
   return iter;
 }
 
 // ------------------------------------------------------------------------------------------------ one physics tick
-// jt_q / jt_qd: joint set-point for this tick (from the IK kernel in Cartesian mode, or the held pose after reset).
+// jt_q / jt_qlo / jt_qd: joint set-point for this tick (from the IK reference in Cartesian mode, or the held pose).
 template <int G>
 DEVFN void physics_tick(const Cx& cx, const Model& m, const Lay& L, real* w, const real* jt_q, const real* jt_qlo, const real* jt_qd, real tol, int max_iter) {
   const int nv = m.nv;
@@ -1050,37 +1154,53 @@ DEVFN void physics_tick(const Cx& cx, const Model& m, const Lay& L, real* w, con
     for (int k = 0; k < 3; k++) w[L.tcp + k] = w[L.xpos + 18 + k] + o[k];
     quat2mat(Rt, tq); mat_mul3(R, w + L.xmat + 54, Rt); mat2quat(w + L.tcp + 3, R);
   }
-  LANES(e, nv * nv) w[L.M + e] = 0;
+  LANES(e, nv * nv) w[L.M + e] = 0;     // unrelated dof pairs inside a block (the two fingers) must read as zero
   gsync<G>(cx);
   dynamics<G>(cx, m, L, w);
   int ncon = collision<G>(cx, m, L, w);
-  int ne = make_constraints<G>(cx, m, L, w, ncon);
-  // --- smooth dynamics
+  int nlimit = 0, coupled = 0;
+  int ne = make_constraints<G>(cx, m, L, w, ncon, &nlimit, &coupled);
+  // --- smooth dynamics: qacc_smooth = M^-1 (passive - bias + actuation); M is block diagonal over the trees
   LANES(d, nv) {
     int li = m.d_link[d];
     real passive = m.l_jtype[li] == 2 ? (real)0 : -(real)m.link[D3_LINK_W * li + 25] * w[L.qvel + d];
     real act = d < D3_NROB ? w[L.act + d] : (real)0;
     real f = passive - w[L.bias + d] + act;
     w[L.qfrc_smooth + d] = f; w[L.qacc_smooth + d] = f;
+    w[L.mpiv + d] = w[L.M + d * nv + d];
   }
-  LANES(e, nv * nv) w[L.Lm + e] = w[L.M + e];
+  LANES(e, m.nmpair) { int a = m.mp_a[e], b = m.mp_b[e]; if (a != b) w[L.M + a * nv + b] = w[L.M + b * nv + a]; }   // lower <- upper
   gsync<G>(cx);
-  if (chol_factor<G>(cx, w + L.Lm, nv)) { LANES(z, 1) w[L.misc + ST_STATUS] = (real)(((int)w[L.misc + ST_STATUS]) | 1); }
-  chol_solve<G>(cx, w + L.Lm, nv, w + L.qacc_smooth);
-  solve_constraints<G>(cx, m, L, w, ne, ncon, tol, max_iter);
-  LANES(d, nv) w[L.warm + d] = w[L.qacc + d];
+  if (chol_factor_part<G>(cx, w + L.M, nv, m.d_bs, m.d_be, false, m.maxblk, w + L.mpiv, w + L.mdinv)) { LANES(z, 1) w[L.misc + ST_STATUS] = (real)(((int)w[L.misc + ST_STATUS]) | 1); }
+  chol_solve_part<G>(cx, w + L.M, nv, m.d_bs, m.d_be, false, m.maxblk, w + L.mdinv, w + L.qacc_smooth);
+  solve_constraints<G>(cx, m, L, w, ne, nlimit, ncon, coupled, tol, max_iter);
+  LANES(d, nv) { w[L.warm + d] = w[L.qacc + d]; w[L.tmpv + d] = w[L.qfrc_smooth + d] + w[L.qfrc_c + d]; }
   LANES(k, D3_NROB) w[L.bias_prev + k] = w[L.bias + k];
-  // --- mj_Euler with implicit joint damping: (M + h B) qacc* = qfrc_smooth + qfrc_constraint
-  LANES(e, nv * nv) w[L.Lm + e] = w[L.M + e];
-  gsync<G>(cx);
-  LANES(d, nv) {
-    int li = m.d_link[d];
-    if (m.l_jtype[li] != 2) w[L.Lm + d * nv + d] += h * (real)m.link[D3_LINK_W * li + 25];
-    w[L.tmpv + d] = w[L.qfrc_smooth + d] + w[L.qfrc_c + d];
+  // --- mj_Euler with implicit joint damping: (M + h B) qacc* = qfrc_smooth + qfrc_constraint.  Only the trailing
+  //     `ndamp` dofs of the arm block are damped (the fingers), so the factor of M + hB differs from the factor of M
+  //     in its last ndamp rows only: rebuild that corner (serial, ndamp = 2) instead of refactorising.
+  LANES(z, 1) {
+    const int f0 = m.damp_first, f1 = m.damp_end;
+    real T[16];
+    for (int a = f0; a < f1; a++) for (int b = f0; b <= a; b++) {
+      real s = 0;
+      for (int k = f0; k <= b; k++) {
+        real la = k == a ? 1 / w[L.mdinv + a] : w[L.M + a * nv + k], lb = k == b ? 1 / w[L.mdinv + b] : w[L.M + b * nv + k];
+        s += la * lb;
+      }
+      if (a == b) s += h * (real)m.link[D3_LINK_W * m.d_link[a] + 25];
+      T[(a - f0) * 4 + (b - f0)] = s;
+    }
+    for (int a = f0; a < f1; a++) {
+      for (int b = f0; b <= a; b++) {
+        real s = T[(a - f0) * 4 + (b - f0)];
+        for (int k = f0; k < b; k++) s -= w[L.M + a * nv + k] * w[L.M + b * nv + k];
+        if (a == b) w[L.mdinv + a] = 1 / sqrt(s); else w[L.M + a * nv + b] = s * w[L.mdinv + b];
+      }
+    }
   }
   gsync<G>(cx);
-  chol_factor<G>(cx, w + L.Lm, nv);
-  chol_solve<G>(cx, w + L.Lm, nv, w + L.tmpv);
+  chol_solve_part<G>(cx, w + L.M, nv, m.d_bs, m.d_be, false, m.maxblk, w + L.mdinv, w + L.tmpv);
   LANES(d, nv) w[L.qvel + d] += h * w[L.tmpv + d];
   gsync<G>(cx);
   LANES(i, m.nlink) {

@@ -60,6 +60,22 @@ static inline bool d3il_build_model(const void* blob, size_t nbytes, Model& m, L
       if (m.nmpair >= D3_MAXV * 8) { err = "mass-matrix pair table overflow"; return false; }
       m.mp_a[m.nmpair] = (unsigned char)a; m.mp_b[m.nmpair] = (unsigned char)b; m.nmpair++;
     }
+  // kinematic-tree blocks of the (block-diagonal) mass matrix, implicit-damping corner, triangle unranking table
+  m.maxblk = 0;
+  for (int d = 0; d < m.nv; d++) {
+    int root = m.d_link[d]; while (m.l_parent[root] >= 0) root = m.l_parent[root];
+    int lo = m.nv, hi = 0;
+    for (int e = 0; e < m.nv; e++) { int r = m.d_link[e]; while (m.l_parent[r] >= 0) r = m.l_parent[r]; if (r == root) { if (e < lo) lo = e; if (e + 1 > hi) hi = e + 1; } }
+    m.d_bs[d] = lo; m.d_be[d] = hi;
+    if (hi - lo > m.maxblk) m.maxblk = hi - lo;
+  }
+  m.ndamp = 0; m.damp_first = m.damp_end = 0;
+  for (int d = 0; d < m.nv; d++) if (m.l_jtype[m.d_link[d]] != 2 && m.link[D3_LINK_W * m.d_link[d] + 25] > 0) { if (!m.ndamp) m.damp_first = d; m.ndamp++; m.damp_end = d + 1; }
+  if (m.ndamp) {
+    bool ok = m.ndamp <= 4 && m.damp_end - m.damp_first == m.ndamp && m.damp_end == m.d_be[m.damp_first];
+    if (!ok) { err = "damped dofs must be the trailing dofs of their block"; return false; }
+  }
+  { int e = 0; for (int i = 0; i < 16; i++) for (int j = 0; j <= i; j++) { m.tri_i[e] = (unsigned char)i; m.tri_j[e] = (unsigned char)j; e++; } }
   m.maxcon = conmax < 24 ? ((conmax + 3) & ~3) : 24;
   m.maxrow = 3 * m.maxcon + 6;
   if (m.maxrow > 64) m.maxrow = 64;

@@ -1,0 +1,4 @@
+"""Drop-in rollout harnesses with the reference's class names and constructor signatures (``simulation/*_sim.py``)."""
+from .avoiding_sim import Avoiding_Sim  # noqa: F401
+from .base_sim import BaseSim  # noqa: F401
+from .pushing_sim import Pushing_Sim  # noqa: F401

@@ -1,0 +1,78 @@
+"""``BaseSim`` — same constructor and abstract ``test_agent(agent)`` as the reference (``simulation/base_sim.py:8-30``).
+
+What changes underneath: instead of one MuJoCo env per spawned CPU process (``pushing_sim.py:114-135``) every
+(context, rollout) pair is one env instance of a single ``BatchedEnv`` on this rank's GPU; with ``torch.distributed``
+initialised, env instances are sharded by contiguous (context, rollout) ranges across ranks and the per-env result
+rows are gathered once at rollout end (the replacement of the ``share_memory_()`` result tensors).
+"""
+from __future__ import annotations
+
+import abc
+import logging
+import os
+
+import numpy as np
+import torch
+
+log = logging.getLogger(__name__)
+
+
+def _wandb_log(d):
+    try:
+        import wandb
+        if wandb.run is not None:
+            wandb.log(d)
+    except Exception:
+        pass
+
+
+class BaseSim(abc.ABC):
+    def __init__(self, seed: int, device: str, render: bool = True, n_cores: int = 1, if_vision: bool = False):
+        self.seed = seed
+        self.device = device
+        self.render = render
+        self.n_cores = n_cores          # kept for config compatibility; parallelism is the env batch, not CPU cores
+        self.if_vision = if_vision
+        self.working_dir = os.getcwd()
+        self.env_name = "BaseEnvironment"
+        if if_vision:
+            raise NotImplementedError("vision observations need a rasteriser and are outside the batched state-based path")
+
+    @abc.abstractmethod
+    def test_agent(self, agent):
+        pass
+
+    # ---- sharding helpers shared by the task sims
+    @staticmethod
+    def dist_info():
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+        return 0, 1
+
+    @staticmethod
+    def shard_range(n_items: int, rank: int, world: int):
+        """Contiguous item range of this rank (the reference's ``contexts[i*workload:(i+1)*workload]`` split)."""
+        per = (n_items + world - 1) // world
+        lo = min(rank * per, n_items)
+        return lo, min(lo + per, n_items)
+
+    @staticmethod
+    def gather_rows(local_rows: torch.Tensor, n_items: int) -> torch.Tensor:
+        """All-gather per-env result rows ([n_local, k]) into [n_items, k] on every rank (one collective per rollout)."""
+        import torch.distributed as dist
+        rank, world = BaseSim.dist_info()
+        if world == 1:
+            return local_rows
+        per = (n_items + world - 1) // world
+        pad = torch.zeros(per, local_rows.shape[1], dtype=local_rows.dtype, device=local_rows.device)
+        pad[: local_rows.shape[0]] = local_rows
+        out = [torch.zeros_like(pad) for _ in range(world)]
+        dist.all_gather(out, pad)
+        return torch.cat(out, 0)[:n_items]
+
+    def _cuda_index(self) -> int:
+        d = torch.device(self.device) if not isinstance(self.device, torch.device) else self.device
+        if d.type != "cuda":
+            raise RuntimeError("the batched simulation runs on CUDA devices only")
+        return d.index if d.index is not None else torch.cuda.current_device()

@@ -70,6 +70,7 @@ int emu_probe(Emu* e, const char* what, double* out, int cap) {
   else if (s == "efc_aref") { off = L.aref; n = m.maxrow; } else if (s == "efc_D") { off = L.D; n = m.maxrow; } else if (s == "efc_force") { off = L.frcE; n = m.maxrow; }
   else if (s == "contacts") { off = L.con; n = D3_CON_W * m.maxcon; } else if (s == "qfrc_c") { off = L.qfrc_c; n = m.nv; } else if (s == "act") { off = L.act; n = 9; }
   else if (s == "qfrc_smooth") { off = L.qfrc_smooth; n = m.nv; }
+  else if (s == "M") { off = L.M; n = m.nv * m.nv; }
   if (off < 0 || n > cap) return -1;
   for (int k = 0; k < n; k++) out[k] = e->w[off + k];
   return n;

@@ -126,7 +126,7 @@ def test_avoiding_episode_closed_loop():
         des = tcp0.copy()
         acts = []
         for k in range(250):
-            tgt_x = 0.33 + 0.005 * i
+            tgt_x = 0.300 + 0.002 * i if i < 6 else 0.345
             des[0] += np.clip(tgt_x - des[0], -0.004, 0.004) + rng.uniform(-0.001, 0.001)
             des[1] += 0.004 + rng.uniform(-0.002, 0.002)
             acts.append(np.concatenate([des, [0, 1, 0, 0]]))
