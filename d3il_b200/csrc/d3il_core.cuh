@@ -62,6 +62,13 @@ template <int G> DEVFN int gori(const Cx& cx, int x) {
 }
 #endif
 
+// compiled table sizes (largest scene: Sorting-6, 15 links, nv 45)
+#define D3_MAXLINK 16
+#define D3_MAXV 48
+#define D3_MAXQ 56
+#define D3_MAXGEOM 24
+#define D3_MAXPAIR 48
+
 #define LANES(i, n) for (int i = cx.lane; i < (n); i += G)
 
 // Register-distributed vectors: element i lives in slot i / G of lane i % G.
@@ -81,11 +88,6 @@ DEVFN real elem_bcast(const Cx& cx, const real* xr, int c) {
 // ------------------------------------------------------------------------------------------------ model tables
 // Float copy of the D3SC scene blob (d3il_b200/scene/blob.py) + derived index tables, staged into shared memory
 // once per CTA.  All arrays are sized for the largest scene we compile (Sorting-6: 15 links, nv 45).
-#define D3_MAXLINK 16
-#define D3_MAXV 48
-#define D3_MAXQ 56
-#define D3_MAXGEOM 24
-#define D3_MAXPAIR 48
 #define D3_NARM 7
 #define D3_NROB 9
 #define D3_LINK_W 32
