@@ -19,7 +19,9 @@
 #include "d3il_model.h"
 
 #define G_LANES 32
-#define ENVS_PER_CTA 8
+#ifndef ENVS_PER_CTA
+#define ENVS_PER_CTA 7     // 2 CTAs/SM x 7 envs: 4096 envs = 1.98 waves on 148 SMs (13.3 KB of shared memory per env)
+#endif
 #define CTA_THREADS (G_LANES * ENVS_PER_CTA)
 
 static thread_local std::string g_err;
@@ -93,8 +95,9 @@ __global__ void __launch_bounds__(128) k_ik(DevCtx c, const float* __restrict__ 
     for (int k = 0; k < 7; k++) s.q[k] = (double)row[c.lay.qpos + k] + (double)row[c.lay.qlo + k];
     s.valid = 1;
   }
+  double V[36]; int vwarm = 0;              // eigenbasis carried across the IK iterations of this launch
   for (int t = 0; t < n_ticks; t++) {
-    if (cart) ik_tick(sctrl, s);
+    if (cart) ik_tick(sctrl, s, V, &vwarm);
     float* tr = c.traj + (size_t)t * 21 * n + e;
     for (int k = 0; k < 7; k++) { tr[k * n] = s.jt_q[k]; tr[(7 + k) * n] = s.jt_qlo[k]; tr[(14 + k) * n] = s.jt_qd[k]; }
   }
@@ -103,7 +106,7 @@ __global__ void __launch_bounds__(128) k_ik(DevCtx c, const float* __restrict__ 
 }
 
 // Env step: one warp per env.  gym = 1: GymEnvWrapper.step semantics around the ticks; gym = 0: bare ticks (substep).
-__global__ void __launch_bounds__(CTA_THREADS, 1)
+__global__ void __launch_bounds__(CTA_THREADS, 2)
 k_env(DevCtx c, int n_ticks, int gym, float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ done, float* __restrict__ info) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Model* sm = (Model*)smem_raw;
@@ -129,7 +132,7 @@ k_env(DevCtx c, int n_ticks, int gym, float* __restrict__ obs, float* __restrict
   for (int i = cx.lane; i < L.n_state; i += G_LANES) row[i] = w[i];
 }
 
-__global__ void __launch_bounds__(CTA_THREADS, 1)
+__global__ void __launch_bounds__(CTA_THREADS, 2)
 k_reset(DevCtx c, const float* __restrict__ ctx, const uint8_t* __restrict__ mask, float* __restrict__ obs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Model* sm = (Model*)smem_raw;

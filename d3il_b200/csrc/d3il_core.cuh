@@ -141,19 +141,29 @@ struct Lay {
 enum { ST_GRIP_SET = 0, ST_GRASP, ST_CTRL_MODE, ST_STEP, ST_TERM, ST_STATUS, ST_OBST, ST_TASK0, ST_TASK1, ST_TASK2, ST_TASK3, ST_NMISC = 16 };
 #define D3_CON_W 24    // per contact: pos3, frame9, dist, incl, mu, dim, g1, g2, pair, row0, dof ranges a0,a1,b0,b1
 
+#define D3_JW 16       // compact Jacobian row: entries of the contact's two dof ranges (<= 9 + 6), padded to 16
+
 static inline void d3il_layout(const Model& m, Lay& L) {
   int o = 0;
   auto take = [&](int n) { int r = o; o += (n + 3) & ~3; return r; };
   L.qpos = take(m.nq); L.qlo = take(D3_NROB); L.qvel = take(m.nv); L.warm = take(m.nv); L.bias_prev = take(D3_NROB); L.tcp = take(7); L.misc = take(ST_NMISC);
   L.n_state = o;
-  L.xpos = take(3 * m.nlink); L.xmat = take(9 * m.nlink); L.S = take(6 * m.nv); L.I10 = take(10 * m.nlink); L.Ic = take(10 * m.nlink);
-  L.vel = take(6 * m.nlink); L.cj = take(6 * m.nlink); L.frc = take(6 * m.nlink); L.F = take(6 * m.nv);
-  L.M = take(m.nv * m.nv); L.mdinv = take(m.nv); L.mpiv = take(m.nv); L.H = take(m.nv * m.nv); L.hdinv = take(m.nv); L.hpiv = take(m.nv);
+  // live for the whole tick
+  L.M = take(m.nv * m.nv); L.mdinv = take(m.nv); L.mpiv = take(m.nv);
   L.bias = take(m.nv); L.qfrc_smooth = take(m.nv); L.qacc_smooth = take(m.nv); L.qacc = take(m.nv); L.qfrc_c = take(m.nv);
-  L.grad = take(m.nv); L.pvec = take(m.nv); L.Ma = take(m.nv); L.tmpv = take(m.nv);
-  L.act = take(D3_NROB); L.jt = take(3 * D3_NARM); L.con = take(D3_CON_W * m.maxcon); L.ncon_pair = take(m.npair + 4);
-  L.J = take(m.maxrow * m.nv); L.aref = take(m.maxrow); L.D = take(m.maxrow); L.jar = take(m.maxrow); L.frcE = take(m.maxrow);
-  L.Jp = take(m.maxrow); L.hd = take(m.maxrow); L.hb = take(9 * m.maxcon); L.etype = take(m.maxrow); L.econ = take(m.maxrow);
+  L.act = take(D3_NROB); L.jt = take(3 * D3_NARM); L.con = take(D3_CON_W * m.maxcon);
+  L.J = take(m.maxrow * D3_JW); L.aref = take(m.maxrow); L.D = take(m.maxrow); L.hd = take(2 * D3_NROB); L.econ = take(2 * D3_NROB);
+  // region X, two views that are never live together:
+  //   view 1 (kinematics, dynamics, collision, constraint assembly)   view 2 (Newton solver, Euler)
+  const int x0 = o;
+  L.xpos = take(3 * m.nlink); L.xmat = take(9 * m.nlink); L.S = take(6 * m.nv); L.I10 = take(10 * m.nlink); L.Ic = take(10 * m.nlink);
+  L.vel = take(6 * m.nlink); L.cj = take(6 * m.nlink); L.frc = take(6 * m.nlink); L.F = take(6 * m.nv); L.ncon_pair = take(m.npair + 4);
+  const int x1 = o;
+  o = x0;
+  L.H = take(m.nv * m.nv); L.hdinv = take(m.nv); L.hpiv = take(m.nv); L.jar = take(m.maxrow); L.frcE = take(m.maxrow); L.Jp = take(m.maxrow);
+  L.hb = take(9 * m.maxcon); L.grad = take(m.nv); L.pvec = take(m.nv); L.Ma = take(m.nv); L.tmpv = take(m.nv);
+  if (x1 > o) o = x1;
+  L.etype = 0;
   L.total = o;
 }
 
@@ -692,10 +702,13 @@ DEVFN void link_range(const Model& m, int li, int* lo, int* hi) {
 // J row . v restricted to the contact's dof ranges
 DEVFN real jrow_dot(const real* Jrow, const real* v, int a0, int a1, int b0, int b1) {
   real s = 0;
-  for (int d = a0; d < a1; d++) s += Jrow[d] * v[d];
-  for (int d = b0; d < b1; d++) s += Jrow[d] * v[d];
+  for (int d = a0; d < a1; d++) s += Jrow[d - a0] * v[d];
+  const real* Jb = Jrow + (a1 - a0) - b0;
+  for (int d = b0; d < b1; d++) s += Jb[d] * v[d];
   return s;
 }
+// compact-row entry of dof d (must lie in one of the ranges)
+DEVFN real jrow_at(const real* Jrow, int d, int a0, int a1, int b0) { return d < a1 && d >= a0 ? Jrow[d - a0] : Jrow[(a1 - a0) + d - b0]; }
 
 // Rows: joint limits first (one dof each), then dim rows per active contact (elliptic).  Returns nefc (all lanes);
 // *coupled is set when some contact joins two different kinematic-tree blocks (then H is not block diagonal).
@@ -721,7 +734,6 @@ DEVFN int make_constraints(const Cx& cx, const Model& m, const Lay& L, real* w, 
           real Rv = maxr((real)1e-15, (1 - imp) / imp * (real)Lk[27]);
           w[L.D + ne] = 1 / Rv;
           w[L.aref + ne] = -bb * sg * w[L.qvel + m.l_dadr[i]] - kk * imp * dist;
-          w[L.etype + ne] = 0;
           w[L.econ + ne] = (real)(side == 0 ? m.l_dadr[i] + 1 : -(m.l_dadr[i] + 1));     // limit rows: signed dof id (+lower / -upper)
         }
         ne++;
@@ -755,7 +767,9 @@ DEVFN int make_constraints(const Cx& cx, const Model& m, const Lay& L, real* w, 
     const real* cc = w + L.con + D3_CON_W * c;
     int row0 = (int)cc[19];
     if (row0 < 0) continue;
-    if (!((d >= (int)cc[20] && d < (int)cc[21]) || (d >= (int)cc[22] && d < (int)cc[23]))) continue;
+    int a0 = (int)cc[20], a1 = (int)cc[21], b0 = (int)cc[22], b1 = (int)cc[23];
+    if (!((d >= a0 && d < a1) || (d >= b0 && d < b1))) continue;
+    int loc = d < a1 && d >= a0 ? d - a0 : (a1 - a0) + d - b0;
     int dim = (int)cc[15];
     int l1 = (int)m.geom[D3_GEOM_W * (int)cc[16] + 1], l2 = (int)m.geom[D3_GEOM_W * (int)cc[17] + 1];
     int dl = m.d_link[d];
@@ -772,7 +786,7 @@ DEVFN int make_constraints(const Cx& cx, const Model& m, const Lay& L, real* w, 
     }
     for (int r = 0; r < dim; r++) {
       const real* ax = cc + 3 + 3 * (r < 3 ? r : 0);
-      w[L.J + (row0 + r) * nv + d] = r < 3 ? dot3(ax, jd) : dot3(ax, jr);
+      w[L.J + (row0 + r) * D3_JW + loc] = r < 3 ? dot3(ax, jd) : dot3(ax, jr);
     }
   }
   gsync<G>(cx);
@@ -792,10 +806,9 @@ DEVFN int make_constraints(const Cx& cx, const Model& m, const Lay& L, real* w, 
     cc[14] = fr[0] * sqrt(R1 / R0);
     for (int r = 0; r < dim; r++) {
       real Rv = r == 0 ? R0 : (r == 1 ? R1 : R1 * fr[0] * fr[0] / (fr[r - 1] * fr[r - 1]));
-      real vel = jrow_dot(w + L.J + (row0 + r) * nv, w + L.qvel, (int)cc[20], (int)cc[21], (int)cc[22], (int)cc[23]);
+      real vel = jrow_dot(w + L.J + (row0 + r) * D3_JW, w + L.qvel, (int)cc[20], (int)cc[21], (int)cc[22], (int)cc[23]);
       w[L.D + row0 + r] = 1 / Rv;
       w[L.aref + row0 + r] = -bb * vel - (r == 0 ? kk * imp * (cc[12] - cc[13]) : 0);
-      w[L.etype + row0 + r] = r == 0 ? 1 : 2; w[L.econ + row0 + r] = (real)c;
     }
   }
   gsync<G>(cx);
@@ -817,7 +830,7 @@ DEVFN void eval_jar(const Cx& cx, const Model& m, const Lay& L, real* w, int nli
     if (i < 0) continue;
     int dim = (int)cc[15];
     for (int r = 0; r < dim; r++) {
-      real s = jrow_dot(w + L.J + (i + r) * nv, w + v_off, (int)cc[20], (int)cc[21], (int)cc[22], (int)cc[23]);
+      real s = jrow_dot(w + L.J + (i + r) * D3_JW, w + v_off, (int)cc[20], (int)cc[21], (int)cc[22], (int)cc[23]);
       w[out_off + i + r] = sub_aref ? s - w[L.aref + i + r] : s;
     }
   }
@@ -1001,8 +1014,11 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
         const real* cc = w + L.con + D3_CON_W * c;
         int i = (int)cc[19];
         if (i < 0) continue;
-        if ((d >= (int)cc[20] && d < (int)cc[21]) || (d >= (int)cc[22] && d < (int)cc[23]))
-          s -= w[L.J + i * nv + d] * w[L.frcE + i] + w[L.J + (i + 1) * nv + d] * w[L.frcE + i + 1] + w[L.J + (i + 2) * nv + d] * w[L.frcE + i + 2];
+        int a0 = (int)cc[20], a1 = (int)cc[21], b0 = (int)cc[22], b1 = (int)cc[23];
+        if ((d >= a0 && d < a1) || (d >= b0 && d < b1)) {
+          const real* Jr = w + L.J + i * D3_JW + (d < a1 && d >= a0 ? d - a0 : (a1 - a0) + d - b0);
+          s -= Jr[0] * w[L.frcE + i] + Jr[D3_JW] * w[L.frcE + i + 1] + Jr[2 * D3_JW] * w[L.frcE + i + 2];
+        }
       }
       w[L.grad + d] = s; g2 += s * s;
     }
@@ -1026,13 +1042,13 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
       if (r0 < 0) continue;
       int a0 = (int)cc[20], a1 = (int)cc[21], b0 = (int)cc[22], b1 = (int)cc[23], na = a1 - a0, nn = na + b1 - b0;
       const real* Hb = w + L.hb + 9 * c;
-      const real *J0 = w + L.J + r0 * nv, *J1 = J0 + nv, *J2 = J1 + nv;
+      const real *J0 = w + L.J + r0 * D3_JW, *J1 = J0 + D3_JW, *J2 = J1 + D3_JW;
       LANES(e, nn * (nn + 1) / 2) {
         int li = m.tri_i[e], lj = m.tri_j[e];
         int gi = li < na ? a0 + li : b0 + li - na, gj = lj < na ? a0 + lj : b0 + lj - na;
-        real i0 = J0[gi], i1 = J1[gi], i2 = J2[gi];
+        real i0 = J0[li], i1 = J1[li], i2 = J2[li];
         real t0 = i0 * Hb[0] + i1 * Hb[3] + i2 * Hb[6], t1 = i0 * Hb[1] + i1 * Hb[4] + i2 * Hb[7], t2 = i0 * Hb[2] + i1 * Hb[5] + i2 * Hb[8];
-        w[L.H + gi * nv + gj] += t0 * J0[gj] + t1 * J1[gj] + t2 * J2[gj];
+        w[L.H + gi * nv + gj] += t0 * J0[lj] + t1 * J1[lj] + t2 * J2[lj];
       }
       gsync<G>(cx);
     }
@@ -1115,8 +1131,11 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
       const real* cc = w + L.con + D3_CON_W * c;
       int i = (int)cc[19];
       if (i < 0) continue;
-      if ((d >= (int)cc[20] && d < (int)cc[21]) || (d >= (int)cc[22] && d < (int)cc[23]))
-        s += w[L.J + i * nv + d] * w[L.frcE + i] + w[L.J + (i + 1) * nv + d] * w[L.frcE + i + 1] + w[L.J + (i + 2) * nv + d] * w[L.frcE + i + 2];
+      int a0 = (int)cc[20], a1 = (int)cc[21], b0 = (int)cc[22], b1 = (int)cc[23];
+      if ((d >= a0 && d < a1) || (d >= b0 && d < b1)) {
+        const real* Jr = w + L.J + i * D3_JW + (d < a1 && d >= a0 ? d - a0 : (a1 - a0) + d - b0);
+        s += Jr[0] * w[L.frcE + i] + Jr[D3_JW] * w[L.frcE + i + 1] + Jr[2 * D3_JW] * w[L.frcE + i + 2];
+      }
     }
     w[L.qfrc_c + d] = s;
   }

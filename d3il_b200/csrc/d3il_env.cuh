@@ -71,9 +71,17 @@ DEVFN void ik_fk(const tab_t* C, const ikr* q, ikr* pos, ikr* quat, ikr* J) {
   }
 }
 
-// cyclic Jacobi eigen-decomposition of a symmetric 6x6 (np.linalg.svd of the SPD matrix J J^T + reg I)
-DEVFN void jacobi6(ikr* A, ikr* wv, ikr* V) {
-  for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) V[i * 6 + j] = (i == j) ? 1.0 : 0.0;
+// Cyclic Jacobi eigen-decomposition of a symmetric 6x6 (np.linalg.svd of the SPD matrix J J^T + reg I).
+// `V` carries the eigenbasis of the previous call when `warm` is set: A changes by O(1e-3) per IK iteration, so
+// rotating into the old basis first leaves a nearly diagonal matrix and one or two sweeps finish it (instead of ~7).
+DEVFN void jacobi6(ikr* A, ikr* wv, ikr* V, int warm) {
+  if (warm) {
+    ikr T[36];
+    for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) { ikr s = 0; for (int k = 0; k < 6; k++) s += A[i * 6 + k] * V[k * 6 + j]; T[i * 6 + j] = s; }
+    for (int i = 0; i < 6; i++) for (int j = i; j < 6; j++) { ikr s = 0; for (int k = 0; k < 6; k++) s += V[k * 6 + i] * T[k * 6 + j]; A[i * 6 + j] = s; A[j * 6 + i] = s; }
+  } else {
+    for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) V[i * 6 + j] = (i == j) ? 1.0 : 0.0;
+  }
   for (int sweep = 0; sweep < 30; sweep++) {
     ikr off = 0, diag = 0;
     for (int i = 0; i < 6; i++) { diag += A[i * 6 + i] * A[i * 6 + i]; for (int j = i + 1; j < 6; j++) off += A[i * 6 + j] * A[i * 6 + j]; }
@@ -94,7 +102,7 @@ DEVFN void jacobi6(ikr* A, ikr* wv, ikr* V) {
 
 // One getControl() call of CartPosQuatImpedenceController: num_iter damped-least-squares iterations on the open-loop
 // joint reference; outputs the joint PD set-point (q_des as two floats, qd_des) for this physics tick.
-DEVFN void ik_tick(const tab_t* C, IkState& s) {
+DEVFN void ik_tick(const tab_t* C, IkState& s, ikr* V, int* vwarm) {
   ikr q[7], des_quat[4] = {(ikr)s.des_quat[0], (ikr)s.des_quat[1], (ikr)s.des_quat[2], (ikr)s.des_quat[3]};
   for (int k = 0; k < 7; k++) q[k] = s.q[k];
   const int niter = (int)C[D3C_NUM_ITER];
@@ -112,14 +120,15 @@ DEVFN void ik_tick(const tab_t* C, IkState& s) {
       acc[k] = (ikr)C[D3C_PGAIN_POS + k] * ik_clamp((ikr)s.des_pos[k] - pos[k], -0.01, 0.01);
       acc[3 + k] = (ikr)C[D3C_PGAIN_QUAT + k] * ik_clamp(qe[k], -0.1, 0.1);
     }
-    ikr A[36], wv[6], V[36];
+    ikr A[36], wv[6];
     for (int r = 0; r < 6; r++) for (int c = r; c < 6; c++) {
       ikr sum = 0;
       for (int k = 0; k < 7; k++) sum += J[r * 7 + k] * J[c * 7 + k];
       if (r == c) sum += (ikr)C[D3C_JREG];
       A[r * 6 + c] = sum; A[c * 6 + r] = sum;
     }
-    jacobi6(A, wv, V);
+    jacobi6(A, wv, V, *vwarm);
+    *vwarm = 1;
     ikr qd_null[7], rhs[6], y[6], x[6];
     for (int k = 0; k < 7; k++) qd_null[k] = (ikr)C[D3C_PGAIN_NULL + k] * ik_clamp((ikr)C[D3C_REST + k] - q[k], -0.2, 0.2);
     for (int r = 0; r < 6; r++) { ikr sum = acc[r]; for (int k = 0; k < 7; k++) sum -= J[r * 7 + k] * qd_null[k]; rhs[r] = sum; }

@@ -76,9 +76,8 @@ static inline bool d3il_build_model(const void* blob, size_t nbytes, Model& m, L
     if (!ok) { err = "damped dofs must be the trailing dofs of their block"; return false; }
   }
   { int e = 0; for (int i = 0; i < 16; i++) for (int j = 0; j <= i; j++) { m.tri_i[e] = (unsigned char)i; m.tri_j[e] = (unsigned char)j; e++; } }
-  m.maxcon = conmax < 24 ? ((conmax + 3) & ~3) : 24;
-  m.maxrow = 3 * m.maxcon + 6;
-  if (m.maxrow > 64) m.maxrow = 64;
+  m.maxcon = conmax < 20 ? ((conmax + 3) & ~3) : 20;
+  m.maxrow = 3 * m.maxcon + 4;
   d3il_layout(m, L);
   m.ws_floats = L.total;
   return true;

@@ -9,7 +9,7 @@
 #include "../../d3il_b200/csrc/d3il_model.h"
 
 struct Emu {
-  Model m; Lay L; IkState ik;
+  Model m; Lay L; IkState ik; double V[36]; int vwarm;
   std::vector<real> w;
   real tol; int max_iter;
 };
@@ -22,6 +22,7 @@ Emu* emu_create(const void* blob, size_t n) {
   if (!d3il_build_model(blob, n, e->m, e->L, err)) { fprintf(stderr, "emu_create: %s\n", err.c_str()); delete e; return nullptr; }
   e->w.assign(e->L.total, 0);
   memset(&e->ik, 0, sizeof(e->ik));
+  e->vwarm = 0;
   e->tol = sizeof(real) == 4 ? (real)1e-6 : (real)1e-10;
   e->max_iter = sizeof(real) == 4 ? 12 : 100;
   return e;
@@ -36,7 +37,7 @@ static void tick(Emu* e) {
   real* w = e->w.data();
   if (w[e->L.misc + ST_CTRL_MODE] != 0) {
     if (!e->ik.valid) { for (int k = 0; k < 7; k++) e->ik.q[k] = (double)w[e->L.qpos + k] + (double)w[e->L.qlo + k]; e->ik.valid = 1; }
-    ik_tick(e->m.ctrl, e->ik);
+    ik_tick(e->m.ctrl, e->ik, e->V, &e->vwarm);
   }
   physics_tick<1>(CX, e->m, e->L, w, e->ik.jt_q, e->ik.jt_qlo, e->ik.jt_qd, e->tol, e->max_iter);
 }
