@@ -18,7 +18,9 @@
 #include "../../include/d3il.h"
 #include "d3il_model.h"
 
-#define G_LANES 32
+#ifndef G_LANES
+#define G_LANES 32          // lanes cooperating on one env (32 = one warp per env; 16 = two envs per warp)
+#endif
 #ifndef ENVS_PER_CTA
 #define ENVS_PER_CTA 7     // 2 CTAs/SM x 7 envs: 4096 envs = 1.98 waves on 148 SMs (13.3 KB of shared memory per env)
 #endif
@@ -114,18 +116,19 @@ k_env(DevCtx c, int n_ticks, int gym, float* __restrict__ obs, float* __restrict
   const Model& m = *sm;
   const Lay& L = c.lay;
   const int warp = threadIdx.x / G_LANES;
-  Cx cx; cx.lane = threadIdx.x % G_LANES; cx.mask = 0xffffffffu;
+  Cx cx; cx.lane = threadIdx.x % G_LANES;
+  cx.mask = G_LANES == 32 ? 0xffffffffu : (((1u << G_LANES) - 1u) << (((threadIdx.x & 31) / G_LANES) * G_LANES));
   const int e = blockIdx.x * ENVS_PER_CTA + warp;
   if (e >= c.n) return;
   float* w = (float*)(smem_raw + ((sizeof(Model) + 127) & ~(size_t)127)) + (size_t)warp * c.ws_stride;
   float* row = c.state + (size_t)e * c.row;
   for (int i = cx.lane; i < L.n_state; i += G_LANES) w[i] = row[i];
-  __syncwarp();
+  __syncwarp(cx.mask);
   if (gym) env_prestep<G_LANES>(cx, m, L, w, obs + (size_t)e * m.obs_dim, reward + e, done + e);
   for (int t = 0; t < n_ticks; t++) {
     const float* tr = c.traj + (size_t)t * 21 * c.n + e;
     for (int k = cx.lane; k < 21; k += G_LANES) w[L.jt + k] = tr[(size_t)k * c.n];
-    __syncwarp();
+    __syncwarp(cx.mask);
     physics_tick<G_LANES>(cx, m, L, w, w + L.jt, w + L.jt + 7, w + L.jt + 14, c.tol, c.max_iter);
   }
   if (gym) env_poststep<G_LANES>(cx, m, L, w, info + (size_t)e * m.info_dim);
@@ -140,7 +143,8 @@ k_reset(DevCtx c, const float* __restrict__ ctx, const uint8_t* __restrict__ mas
   const Model& m = *sm;
   const Lay& L = c.lay;
   const int warp = threadIdx.x / G_LANES;
-  Cx cx; cx.lane = threadIdx.x % G_LANES; cx.mask = 0xffffffffu;
+  Cx cx; cx.lane = threadIdx.x % G_LANES;
+  cx.mask = G_LANES == 32 ? 0xffffffffu : (((1u << G_LANES) - 1u) << (((threadIdx.x & 31) / G_LANES) * G_LANES));
   const int e = blockIdx.x * ENVS_PER_CTA + warp;
   if (e >= c.n) return;
   if (mask && !mask[e]) return;

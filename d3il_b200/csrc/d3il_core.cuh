@@ -28,6 +28,7 @@ typedef float tab_t;    // model tables are fp32 in shared memory
 
 #ifdef D3IL_EMU
 #define DEVFN static inline
+#define DEVNI static inline
 #define D3_RESTRICT
 struct Cx { int lane; unsigned mask; };
 template <int G> DEVFN void gsync(const Cx&) {}
@@ -37,6 +38,7 @@ template <int G> DEVFN int gsumi(const Cx&, int x) { return x; }
 template <int G> DEVFN int gori(const Cx&, int x) { return x; }
 #else
 #define DEVFN __device__ __forceinline__
+#define DEVNI __device__ __noinline__       // big, multiply-instantiated routines: the kernel is instruction-fetch bound
 #define D3_RESTRICT __restrict__
 struct Cx { int lane; unsigned mask; };
 template <int G> DEVFN void gsync(const Cx& cx) { __syncwarp(cx.mask); }
@@ -207,6 +209,25 @@ DEVFN void mat2quat(real* q, const real* R) {
   real n = 1 / sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
   q[0] *= n; q[1] *= n; q[2] *= n; q[3] *= n;
 }
+// sin/cos for |x| <= ~4 (joint half-angles, per-tick rotation increments): Cody-Waite reduction by pi/2 and
+// minimax polynomials on [-pi/4, pi/4]; ~1 ulp in fp32 and a fraction of the code size of sinf/cosf.
+DEVFN void sincos_small(real x, real* sn, real* cs) {
+#ifdef __CUDA_ARCH__
+  float k = rintf(x * 0.636619772f);
+  float r = fmaf(k, -1.57079601e+00f, x);
+  r = fmaf(k, -3.13916473e-07f, r);
+  r = fmaf(k, -5.39030253e-15f, r);
+  float r2 = r * r;
+  float sp = fmaf(fmaf(fmaf(-1.95152959e-4f, r2, 8.33216087e-3f), r2, -1.66666546e-1f), r2 * r, r);
+  float cp = fmaf(fmaf(fmaf(fmaf(2.44331571e-5f, r2, -1.38873163e-3f), r2, 4.16666457e-2f), r2, -0.5f), r2, 1.0f);
+  int q = (int)k & 3;
+  float s1 = (q & 1) ? cp : sp, c1 = (q & 1) ? sp : cp;
+  *sn = (q & 2) ? -s1 : s1;
+  *cs = ((q + 1) & 2) ? -c1 : c1;
+#else
+  *sn = sin(x); *cs = cos(x);
+#endif
+}
 DEVFN real clampr(real x, real lo, real hi) { return x < lo ? lo : (x > hi ? hi : x); }
 DEVFN real absr(real x) { return x < 0 ? -x : x; }
 DEVFN real maxr(real a, real b) { return a > b ? a : b; }
@@ -217,7 +238,7 @@ DEVFN real minr(real a, real b) { return a < b ? a : b; }
 // depth 1), so no inter-lane communication is needed; world pose, joint motion subspace S (world axes, linear part at
 // the world origin) and the 10-parameter spatial inertia about the world origin land in the workspace.
 template <int G>
-DEVFN void kinematics(const Cx& cx, const Model& m, const Lay& L, real* w) {
+DEVNI void kinematics(const Cx& cx, const Model& m, const Lay& L, real* w) {
   LANES(i, m.nlink) {
     real p[3] = {0, 0, 0}, R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
     if (m.l_jtype[i] == 2) {
@@ -239,7 +260,8 @@ DEVFN void kinematics(const Cx& cx, const Model& m, const Lay& L, real* w) {
         real q = w[L.qpos + m.l_qadr[j]];
         real ax[3] = {(real)Lk[9], (real)Lk[10], (real)Lk[11]};
         if (m.l_jtype[j] == 0) {
-          real s = sin((real)0.5 * q), c = cos((real)0.5 * q), hq[4] = {c, s * ax[0], s * ax[1], s * ax[2]}, Rj[9];
+          real s, c; sincos_small((real)0.5 * q, &s, &c);
+          real hq[4] = {c, s * ax[0], s * ax[1], s * ax[2]}, Rj[9];
           quat2mat(Rj, hq); mat_mul3(R, R, Rj);
         } else {
           real a[3]; mat_vec3(a, R, ax);
@@ -302,7 +324,7 @@ DEVFN void inertia_apply(const real* I, const real* sv, real* o) {
 
 // Composite inertias, mass matrix (CRBA) and bias forces (RNE with qacc = 0) — SURVEY App. B.3.
 template <int G>
-DEVFN void dynamics(const Cx& cx, const Model& m, const Lay& L, real* w) {
+DEVNI void dynamics(const Cx& cx, const Model& m, const Lay& L, real* w) {
   const int nl = m.nlink, nv = m.nv;
   // (1) composite inertia = sum over descendants ; link velocity = sum over ancestor dofs
   LANES(i, nl) {
@@ -385,7 +407,7 @@ DEVFN int clip_poly(real (*P)[3], int n, real hu, real hv) {
   return n;
 }
 
-DEVFN int collide_box_box(const real* pA, const real* RA, const real* hA, const real* pB, const real* RB, const real* hB, real margin, RawCon* out) {
+DEVNI int collide_box_box(const real* pA, const real* RA, const real* hA, const real* pB, const real* RB, const real* hB, real margin, RawCon* out) {
   real Rr[9], AbsR[9], t[3], d[3] = {pB[0] - pA[0], pB[1] - pA[1], pB[2] - pA[2]};
   matT_vec3(t, RA, d);
   for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) {
@@ -499,7 +521,7 @@ DEVFN int zonotope_closest(const real d[2], const real g[3][2], real q[2], real 
   return 1;
 }
 
-DEVFN int collide_cyl_box(const real* c, const real* Rc, const real* sz, const real* b, const real* Rb, const real* e3, real margin, RawCon* out) {
+DEVNI int collide_cyl_box(const real* c, const real* Rc, const real* sz, const real* b, const real* Rb, const real* e3, real margin, RawCon* out) {
   real r = sz[0], h = sz[1];
   real a[3] = {Rc[2], Rc[5], Rc[8]}, B[3][3], d[3];
   for (int k = 0; k < 3; k++) { B[k][0] = Rb[k]; B[k][1] = Rb[3 + k]; B[k][2] = Rb[6 + k]; d[k] = b[k] - c[k]; }
@@ -576,7 +598,7 @@ DEVFN int collide_cyl_box(const real* c, const real* Rc, const real* sz, const r
   return out->dist < margin;
 }
 
-DEVFN int collide_cyl_cyl(const real* c1, const real* R1, const real* s1, const real* c2, const real* R2, const real* s2, real margin, RawCon* out) {
+DEVNI int collide_cyl_cyl(const real* c1, const real* R1, const real* s1, const real* c2, const real* R2, const real* s2, real margin, RawCon* out) {
   real a1[3] = {R1[2], R1[5], R1[8]}, a2[3] = {R2[2], R2[5], R2[8]}, ww[3] = {c1[0] - c2[0], c1[1] - c2[1], c1[2] - c2[2]};
   real b = dot3(a1, a2), d = dot3(a1, ww), e = dot3(a2, ww), den = 1 - b * b, t1, t2;
   if (den > (real)1e-8) {
@@ -687,8 +709,13 @@ DEVFN real impedance(const real* solimp, real pos, real margin) {
   real y;
   if (power == 1) y = x;
   else if (power == 2) y = x <= mid ? x * x / mid : 1 - (1 - x) * (1 - x) / (1 - mid);
+#ifdef __CUDA_ARCH__
+  else if (x <= mid) y = __powf(x, power) / __powf(mid, power - 1);      // not reached by the compiled scenes (power == 2)
+  else y = 1 - __powf(1 - x, power) / __powf(1 - mid, power - 1);
+#else
   else if (x <= mid) y = pow(x, power) / pow(mid, power - 1);
   else y = 1 - pow(1 - x, power) / pow(1 - mid, power - 1);
+#endif
   return dmin + y * (dmax - dmin);
 }
 
@@ -817,7 +844,7 @@ DEVFN int make_constraints(const Cx& cx, const Model& m, const Lay& L, real* w, 
 
 // jar = J v - aref for every row (v: workspace offset of a dof vector).  One lane per limit row / per contact.
 template <int G>
-DEVFN void eval_jar(const Cx& cx, const Model& m, const Lay& L, real* w, int nlimit, int ncon, int v_off, int out_off, bool sub_aref) {
+DEVNI void eval_jar(const Cx& cx, const Model& m, const Lay& L, real* w, int nlimit, int ncon, int v_off, int out_off, bool sub_aref) {
   const int nv = m.nv;
   LANES(i, nlimit) {
     int sd = (int)w[L.econ + i];
@@ -841,7 +868,7 @@ DEVFN void eval_jar(const Cx& cx, const Model& m, const Lay& L, real* w, int nli
 // block per contact in hb (zero / diagonal / full for the top / bottom / middle zone of the elliptic cone).
 // Returns the group-wide cost.  One lane per limit row / per contact.
 template <int G, bool HESS>
-DEVFN real constraint_eval(const Cx& cx, const Model& m, const Lay& L, real* w, int nlimit, int ncon, int jar_off, int frc_off) {
+DEVNI real constraint_eval(const Cx& cx, const Model& m, const Lay& L, real* w, int nlimit, int ncon, int jar_off, int frc_off) {
   real cost = 0;
   LANES(i, nlimit) {
     real j = w[jar_off + i], Dv = w[L.D + i];
@@ -885,7 +912,7 @@ DEVFN real constraint_eval(const Cx& cx, const Model& m, const Lay& L, real* w, 
 // L; the running pivots live in piv[] (initialised by the caller with the diagonal), dinv[] receives 1 / L_kk.
 // Row i is owned by lane i % G.  Returns 1 if a pivot was not positive.
 template <int G>
-DEVFN int chol_factor_part(const Cx& cx, real* A, int n, const int* ps, const int* pe, bool whole, int maxsz, real* piv, real* dinv) {
+DEVNI int chol_factor_part(const Cx& cx, real* A, int n, const int* ps, const int* pe, bool whole, int maxsz, real* piv, real* dinv) {
   int bad = 0;
   for (int k = 0; k < maxsz; k++) {
     LANES(i, n) {
@@ -912,7 +939,7 @@ DEVFN int chol_factor_part(const Cx& cx, real* A, int n, const int* ps, const in
 // Solve L L^T x = b in place for the same partitioned factor.  x is pulled into registers (element i in lane i % G),
 // finished elements are broadcast with shuffles; no shared-memory traffic for x and no barriers inside the sweeps.
 template <int G>
-DEVFN void chol_solve_part(const Cx& cx, const real* A, int n, const int* ps, const int* pe, bool whole, int maxsz, const real* dinv, real* x) {
+DEVNI void chol_solve_part(const Cx& cx, const real* A, int n, const int* ps, const int* pe, bool whole, int maxsz, const real* dinv, real* x) {
   real xr[D3_SLOTS(G)];
 #pragma unroll
   for (int sl = 0; sl < D3_SLOTS(G); sl++) { int i = sl * G + cx.lane; xr[sl] = i < n ? x[i] : (real)0; }
@@ -1235,7 +1262,8 @@ DEVFN void physics_tick(const Cx& cx, const Model& m, const Lay& L, real* w, con
     q[0] += h * v[0]; q[1] += h * v[1]; q[2] += h * v[2];
     real wn = norm3(v + 3), ang = wn * h;
     if (ang > 0) {
-      real s = sin((real)0.5 * ang) / wn, c = cos((real)0.5 * ang);
+      real s, c; sincos_small((real)0.5 * ang, &s, &c);
+      s /= wn;
       real a0 = q[3], a1 = q[4], a2 = q[5], a3 = q[6], b1 = s * v[3], b2 = s * v[4], b3 = s * v[5];
       real r0 = a0 * c - a1 * b1 - a2 * b2 - a3 * b3, r1 = a0 * b1 + a1 * c + a2 * b3 - a3 * b2;
       real r2 = a0 * b2 - a1 * b3 + a2 * c + a3 * b1, r3 = a0 * b3 + a1 * b2 - a2 * b1 + a3 * c;
