@@ -118,8 +118,10 @@ k_env(DevCtx c, int n_ticks, int gym, float* __restrict__ obs, float* __restrict
   const int warp = threadIdx.x / G_LANES;
   Cx cx; cx.lane = threadIdx.x % G_LANES;
   cx.mask = G_LANES == 32 ? 0xffffffffu : (((1u << G_LANES) - 1u) << (((threadIdx.x & 31) / G_LANES) * G_LANES));
-  const int e = blockIdx.x * ENVS_PER_CTA + warp;
-  if (e >= c.n) return;
+  // Groups past the end of the batch shadow the last env (same inputs, same control flow, identical outputs) so that
+  // every thread of the CTA reaches the phase barriers inside physics_tick.
+  const int e_raw = blockIdx.x * ENVS_PER_CTA + warp;
+  const int e = e_raw < c.n ? e_raw : c.n - 1;
   float* w = (float*)(smem_raw + ((sizeof(Model) + 127) & ~(size_t)127)) + (size_t)warp * c.ws_stride;
   float* row = c.state + (size_t)e * c.row;
   for (int i = cx.lane; i < L.n_state; i += G_LANES) w[i] = row[i];
@@ -129,10 +131,10 @@ k_env(DevCtx c, int n_ticks, int gym, float* __restrict__ obs, float* __restrict
     const float* tr = c.traj + (size_t)t * 21 * c.n + e;
     for (int k = cx.lane; k < 21; k += G_LANES) w[L.jt + k] = tr[(size_t)k * c.n];
     __syncwarp(cx.mask);
-    physics_tick<G_LANES>(cx, m, L, w, w + L.jt, w + L.jt + 7, w + L.jt + 14, c.tol, c.max_iter);
+    physics_tick<G_LANES, true>(cx, m, L, w, w + L.jt, w + L.jt + 7, w + L.jt + 14, c.tol, c.max_iter);
   }
   if (gym) env_poststep<G_LANES>(cx, m, L, w, info + (size_t)e * m.info_dim);
-  for (int i = cx.lane; i < L.n_state; i += G_LANES) row[i] = w[i];
+  if (e_raw < c.n) for (int i = cx.lane; i < L.n_state; i += G_LANES) row[i] = w[i];
 }
 
 __global__ void __launch_bounds__(CTA_THREADS, 2)
@@ -417,3 +419,9 @@ extern "C" int d3il_set_state(d3il_env* h, const double* in, int e) {
   CK(cudaMemcpy(h->d.ik.valid + e, &ik.valid, sizeof(int), cudaMemcpyHostToDevice));
   return 0;
 }
+
+#ifdef D3IL_PHASE_TIMING
+extern "C" int d3il_debug_phase_cycles(unsigned long long* out24) {
+  return cudaMemcpyFromSymbol(out24, g_phase_cycles, sizeof(unsigned long long) * 24) == cudaSuccess ? 0 : -2;
+}
+#endif

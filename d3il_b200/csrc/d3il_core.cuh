@@ -73,6 +73,31 @@ template <int G> DEVFN int gori(const Cx& cx, int x) {
 
 #define LANES(i, n) for (int i = cx.lane; i < (n); i += G)
 
+// The env-step kernel is instruction-fetch bound (tens of KB of straight-line code per phase, one env per group):
+// CTA-wide barriers at fixed phase boundaries keep every warp of the CTA inside the same code region, so one
+// instruction fetch serves all of them.  CS = false (reset kernel with masked early exits, host emulation): no barriers.
+template <bool CS> DEVFN void cta_sync() {
+#if defined(__CUDA_ARCH__)
+  if (CS) __syncthreads();
+#endif
+}
+
+#if defined(D3IL_PHASE_TIMING) && !defined(D3IL_EMU)
+// debug build only: per-phase cycle counts of the group that owns env 0 (profiles/phase_timing.py)
+__device__ unsigned long long g_phase_cycles[24];
+#endif
+#if defined(D3IL_PHASE_TIMING) && defined(__CUDA_ARCH__)
+#define PHASE_T0() long long t_ph = clock64()
+__device__ __forceinline__ bool blockIdx_is0() { return blockIdx.x == 0 && threadIdx.x == 0; }
+__device__ __forceinline__ void count_iter() { g_phase_cycles[20] += 1; }
+#define PHASE(k) do { long long t_now = clock64(); if (blockIdx.x == 0 && threadIdx.x == 0) g_phase_cycles[k] += (unsigned long long)(t_now - t_ph); t_ph = t_now; } while (0)
+#else
+#define PHASE_T0() ((void)0)
+#define PHASE(k) ((void)0)
+DEVFN bool blockIdx_is0() { return false; }
+DEVFN void count_iter() {}
+#endif
+
 // Register-distributed vectors: element i lives in slot i / G of lane i % G.
 #define D3_SLOTS(G) ((D3_MAXV + (G) - 1) / (G))
 template <int G>
@@ -1021,7 +1046,9 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
   }
   real cost = 0, oldcost = 0;
   int iter = 0;
+  PHASE_T0();
   for (; iter < max_iter; iter++) {
+    PHASE(15);
     eval_jar<G>(cx, m, L, w, nlimit, ncon, L.qacc, L.jar, true);
     oldcost = cost;
     cost = constraint_eval<G, true>(cx, m, L, w, nlimit, ncon, L.jar, L.frcE);
@@ -1054,6 +1081,8 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
 #ifdef D3IL_DEBUG_SOLVER
     printf("  newton it %d cost %.12g gn %.6g\n", iter, (double)cost, (double)gn);
 #endif
+    PHASE(8);
+    if (blockIdx_is0()) count_iter();
     if (scale * gn < tol) break;
     if (iter > 0 && scale * (oldcost - cost) < tol * (real)1e-3) break;
     // ---- H = M + J^T Hc J (lower triangle).  Block diagonal unless a contact couples two trees.
@@ -1079,6 +1108,7 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
       }
       gsync<G>(cx);
     }
+    PHASE(9);
     LANES(d, nv) { w[L.hpiv + d] = w[L.H + d * nv + d]; w[L.pvec + d] = -w[L.grad + d]; }
     gsync<G>(cx);
     int maxsz = coupled ? nv : m.maxblk;
@@ -1086,7 +1116,9 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
       LANES(z, 1) w[L.misc + ST_STATUS] = (real)(((int)w[L.misc + ST_STATUS]) | 4);
       break;
     }
+    PHASE(10);
     chol_solve_part<G>(cx, w + L.H, nv, m.d_bs, m.d_be, coupled != 0, maxsz, w + L.hdinv, w + L.pvec);
+    PHASE(11);
     // ---- exact line search (safeguarded 1-D Newton / false position), quantities reduced across lanes
     eval_jar<G>(cx, m, L, w, nlimit, ncon, L.pvec, L.Jp, false);
     real a1s = 0, a2s = 0, a3s = 0;
@@ -1143,6 +1175,7 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
     }
     LANES(d, nv) w[L.qacc + d] += alpha * w[L.pvec + d];
     gsync<G>(cx);
+    PHASE(12);
   }
   if (iter >= max_iter) {
     // final force evaluation at the last iterate
@@ -1172,10 +1205,11 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
 
 // ------------------------------------------------------------------------------------------------ one physics tick
 // jt_q / jt_qlo / jt_qd: joint set-point for this tick (from the IK reference in Cartesian mode, or the held pose).
-template <int G>
+template <int G, bool CS>
 DEVFN void physics_tick(const Cx& cx, const Model& m, const Lay& L, real* w, const real* jt_q, const real* jt_qlo, const real* jt_qd, real tol, int max_iter) {
   const int nv = m.nv;
   const real h = m.ctrl[D3C_DT];
+  PHASE_T0();
   // --- MjRobot.prepare_step: joint PD + stale-bias gravity compensation, finger law (Robots.py:441-476), actuator clamp
   LANES(k, D3_NARM) {
     // joint angles and their set-points are two-float numbers: the difference of the high words is exact (Sterbenz)
@@ -1202,12 +1236,20 @@ DEVFN void physics_tick(const Cx& cx, const Model& m, const Lay& L, real* w, con
     for (int k = 0; k < 3; k++) w[L.tcp + k] = w[L.xpos + 18 + k] + o[k];
     quat2mat(Rt, tq); mat_mul3(R, w + L.xmat + 54, Rt); mat2quat(w + L.tcp + 3, R);
   }
+  PHASE(0);
+  cta_sync<CS>();
   LANES(e, nv * nv) w[L.M + e] = 0;     // unrelated dof pairs inside a block (the two fingers) must read as zero
   gsync<G>(cx);
   dynamics<G>(cx, m, L, w);
+  PHASE(1);
+  cta_sync<CS>();
   int ncon = collision<G>(cx, m, L, w);
+  PHASE(2);
+  cta_sync<CS>();
   int nlimit = 0, coupled = 0;
   int ne = make_constraints<G>(cx, m, L, w, ncon, &nlimit, &coupled);
+  PHASE(3);
+  cta_sync<CS>();
   // --- smooth dynamics: qacc_smooth = M^-1 (passive - bias + actuation); M is block diagonal over the trees
   LANES(d, nv) {
     int li = m.d_link[d];
@@ -1221,7 +1263,11 @@ DEVFN void physics_tick(const Cx& cx, const Model& m, const Lay& L, real* w, con
   gsync<G>(cx);
   if (chol_factor_part<G>(cx, w + L.M, nv, m.d_bs, m.d_be, false, m.maxblk, w + L.mpiv, w + L.mdinv)) { LANES(z, 1) w[L.misc + ST_STATUS] = (real)(((int)w[L.misc + ST_STATUS]) | 1); }
   chol_solve_part<G>(cx, w + L.M, nv, m.d_bs, m.d_be, false, m.maxblk, w + L.mdinv, w + L.qacc_smooth);
+  PHASE(4);
+  cta_sync<CS>();
   solve_constraints<G>(cx, m, L, w, ne, nlimit, ncon, coupled, tol, max_iter);
+  PHASE(5);
+  cta_sync<CS>();
   LANES(d, nv) { w[L.warm + d] = w[L.qacc + d]; w[L.tmpv + d] = w[L.qfrc_smooth + d] + w[L.qfrc_c + d]; }
   LANES(k, D3_NROB) w[L.bias_prev + k] = w[L.bias + k];
   // --- mj_Euler with implicit joint damping: (M + h B) qacc* = qfrc_smooth + qfrc_constraint.  Only the trailing
@@ -1272,4 +1318,6 @@ DEVFN void physics_tick(const Cx& cx, const Model& m, const Lay& L, real* w, con
     }
   }
   gsync<G>(cx);
+  PHASE(6);
+  cta_sync<CS>();
 }

@@ -269,7 +269,7 @@ DEVFN void env_reset(const Cx& cx, const Model& m, const Lay& L, real* w, const 
   }
   real jq[D3_NARM], jql[D3_NARM], jqd[D3_NARM];
   for (int k = 0; k < D3_NARM; k++) { jq[k] = m.ctrl[D3C_INIT_QPOS + k]; jql[k] = 0; jqd[k] = 0; }
-  physics_tick<G>(cx, m, L, w, jq, jql, jqd, tol, max_iter);
+  physics_tick<G, false>(cx, m, L, w, jq, jql, jqd, tol, max_iter);
 }
 
 // pre-substep half of GymEnvWrapper.step (gym_env_wrapper.py:67-90): open fingers, Cartesian mode, sample obs /

@@ -39,7 +39,7 @@ static void tick(Emu* e) {
     if (!e->ik.valid) { for (int k = 0; k < 7; k++) e->ik.q[k] = (double)w[e->L.qpos + k] + (double)w[e->L.qlo + k]; e->ik.valid = 1; }
     ik_tick(e->m.ctrl, e->ik, e->V, &e->vwarm);
   }
-  physics_tick<1>(CX, e->m, e->L, w, e->ik.jt_q, e->ik.jt_qlo, e->ik.jt_qd, e->tol, e->max_iter);
+  physics_tick<1, false>(CX, e->m, e->L, w, e->ik.jt_q, e->ik.jt_qlo, e->ik.jt_qd, e->tol, e->max_iter);
 }
 void emu_reset(Emu* e, const double* ctx) {
   std::vector<float> c(e->m.ctx_dim > 0 ? e->m.ctx_dim : 1);
