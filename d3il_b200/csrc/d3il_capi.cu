@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(128) k_ik(DevCtx c, const float* __restrict__ 
 }
 
 // Env step: one warp per env.  gym = 1: GymEnvWrapper.step semantics around the ticks; gym = 0: bare ticks (substep).
-__global__ void __launch_bounds__(CTA_THREADS, 2)
+__global__ void __launch_bounds__(CTA_THREADS, (CTA_THREADS > 256 ? 1 : 2))
 k_env(DevCtx c, int n_ticks, int gym, float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ done, float* __restrict__ info) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Model* sm = (Model*)smem_raw;
@@ -137,7 +137,7 @@ k_env(DevCtx c, int n_ticks, int gym, float* __restrict__ obs, float* __restrict
   if (e_raw < c.n) for (int i = cx.lane; i < L.n_state; i += G_LANES) row[i] = w[i];
 }
 
-__global__ void __launch_bounds__(CTA_THREADS, 2)
+__global__ void __launch_bounds__(CTA_THREADS, (CTA_THREADS > 256 ? 1 : 2))
 k_reset(DevCtx c, const float* __restrict__ ctx, const uint8_t* __restrict__ mask, float* __restrict__ obs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Model* sm = (Model*)smem_raw;

@@ -76,6 +76,13 @@ template <int G> DEVFN int gori(const Cx& cx, int x) {
 // The env-step kernel is instruction-fetch bound (tens of KB of straight-line code per phase, one env per group):
 // CTA-wide barriers at fixed phase boundaries keep every warp of the CTA inside the same code region, so one
 // instruction fetch serves all of them.  CS = false (reset kernel with masked early exits, host emulation): no barriers.
+// CTA-wide "does anybody still need another iteration" vote (plain flag without CTA barriers)
+template <bool CS> DEVFN int cta_any(int pred) {
+#if defined(__CUDA_ARCH__)
+  if (CS) return __syncthreads_or(pred);
+#endif
+  return pred;
+}
 template <bool CS> DEVFN void cta_sync() {
 #if defined(__CUDA_ARCH__)
   if (CS) __syncthreads();
@@ -1020,18 +1027,16 @@ DEVFN real mrow_dot(const Model& m, const real* M, int nv, int d, const real* v,
 }
 
 // Newton solver on the primal problem: result in qacc / frcE / qfrc_c.  Returns iterations.
-template <int G>
+template <int G, bool CS>
 DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w, int ne, int nlimit, int ncon, int coupled, real tol, int max_iter) {
   const int nv = m.nv;
-  if (ne == 0) {
-    LANES(d, nv) { w[L.qacc + d] = w[L.qacc_smooth + d]; w[L.qfrc_c + d] = 0; }
-    gsync<G>(cx);
-    return 0;
-  }
+  // Envs without active rows take qacc = qacc_smooth but keep walking the (CTA-uniform) iteration loop below.
+  int done = ne == 0;
+  if (done) { LANES(d, nv) { w[L.qacc + d] = w[L.qacc_smooth + d]; w[L.qfrc_c + d] = 0; } gsync<G>(cx); }
   const real scale = 1 / ((real)m.ctrl[D3C_MEANINERTIA] * (real)(nv > 1 ? nv : 1));
   const real* M = w + L.M;
   // ---- warm start: cheaper of qacc_warmstart and qacc_smooth
-  {
+  if (!done) {
     eval_jar<G>(cx, m, L, w, nlimit, ncon, L.warm, L.jar, true);
     real cw = constraint_eval<G, false>(cx, m, L, w, nlimit, ncon, L.jar, L.frcE);
     real part = 0;
@@ -1049,6 +1054,7 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
   PHASE_T0();
   for (; iter < max_iter; iter++) {
     PHASE(15);
+    if (!done) {
     eval_jar<G>(cx, m, L, w, nlimit, ncon, L.qacc, L.jar, true);
     oldcost = cost;
     cost = constraint_eval<G, true>(cx, m, L, w, nlimit, ncon, L.jar, L.frcE);
@@ -1083,8 +1089,12 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
 #endif
     PHASE(8);
     if (blockIdx_is0()) count_iter();
-    if (scale * gn < tol) break;
-    if (iter > 0 && scale * (oldcost - cost) < tol * (real)1e-3) break;
+    if (scale * gn < tol) done = 1;
+    if (iter > 0 && scale * (oldcost - cost) < tol * (real)1e-3) done = 1;
+    }
+    // all groups of the CTA iterate together (converged ones idle) so the Newton body stays fetch-shared
+    if (!cta_any<CS>(!done)) break;
+    if (!done) {
     // ---- H = M + J^T Hc J (lower triangle).  Block diagonal unless a contact couples two trees.
     LANES(e, nv * nv) w[L.H + e] = 0;
     gsync<G>(cx);
@@ -1176,15 +1186,16 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
     LANES(d, nv) w[L.qacc + d] += alpha * w[L.pvec + d];
     gsync<G>(cx);
     PHASE(12);
+    }
   }
-  if (iter >= max_iter) {
+  if (ne > 0 && !done) {
     // final force evaluation at the last iterate
     eval_jar<G>(cx, m, L, w, nlimit, ncon, L.qacc, L.jar, true);
     constraint_eval<G, false>(cx, m, L, w, nlimit, ncon, L.jar, L.frcE);
     gsync<G>(cx);
   }
   // qfrc_constraint = J^T f
-  LANES(d, nv) {
+  if (ne > 0) LANES(d, nv) {
     real s = 0;
     for (int i = 0; i < nlimit; i++) { int sd = (int)w[L.econ + i]; if (sd == d + 1) s += w[L.frcE + i]; else if (sd == -(d + 1)) s -= w[L.frcE + i]; }
     for (int c = 0; c < ncon; c++) {
@@ -1265,7 +1276,7 @@ DEVFN void physics_tick(const Cx& cx, const Model& m, const Lay& L, real* w, con
   chol_solve_part<G>(cx, w + L.M, nv, m.d_bs, m.d_be, false, m.maxblk, w + L.mdinv, w + L.qacc_smooth);
   PHASE(4);
   cta_sync<CS>();
-  solve_constraints<G>(cx, m, L, w, ne, nlimit, ncon, coupled, tol, max_iter);
+  solve_constraints<G, CS>(cx, m, L, w, ne, nlimit, ncon, coupled, tol, max_iter);
   PHASE(5);
   cta_sync<CS>();
   LANES(d, nv) { w[L.warm + d] = w[L.qacc + d]; w[L.tmpv + d] = w[L.qfrc_smooth + d] + w[L.qfrc_c + d]; }

@@ -1,6 +1,6 @@
 set -e
 cd d3il_b200/csrc
-for cfg in "32 7" "32 8" "16 16" "8 16"; do
+for cfg in "32 7" "32 14" "32 16" "16 16" "16 14"; do
   set -- $cfg
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -ftz=true -prec-div=false -prec-sqrt=false -Xcompiler -fPIC -DG_LANES=$1 -DENVS_PER_CTA=$2 -shared -o libd3il.so d3il_capi.cu 2>/dev/null
   cd ../..
