@@ -47,14 +47,13 @@ struct DevCtx {
   int row, n, ws_stride;
   DevIk ik;
   float* traj;            // [ticks][21][n]
-  int* ik_flags;          // [n_ik_blocks] ticks published by each IK block (monotonic: launch_id * 64 + tick + 1)
   float tol; int max_iter;
 };
 
 struct d3il_env {
   Model m; Lay L;
   DevCtx d;
-  int device, n, max_ticks, n_ik_blocks, launch_id;
+  int device, n, max_ticks;
   long long launches;
   size_t smem_bytes;
   // pinned + device staging for the *_host calls
@@ -70,15 +69,14 @@ __device__ __forceinline__ void stage_model(Model* sm, const Model* gm) {
   __syncthreads();
 }
 
-// IK reference generator role: one thread per env (a5/a6).  use_action = 1: take the set-point from `action` (env
-// step); 0: keep the stored set-point (d3il_substep).  In joint-PD mode (after reset) the held set-point is replicated.
-// Each tick's set-points go to `traj` and are published to the physics CTAs of the same launch with a release flag.
-__device__ __noinline__ void ik_role(const DevCtx& c, tab_t* sctrl, const float* __restrict__ action, int n_ticks, int use_action, int flag_base) {
+// IK reference generator: one thread per env (a5/a6).  mode: 1 = take the set-point from `action` (env step),
+// 0 = keep the stored set-point (d3il_substep).  In joint-PD mode (after reset) the held set-point is replicated.
+__global__ void __launch_bounds__(128) k_ik(DevCtx c, const float* __restrict__ action, int n_ticks, int use_action) {
+  __shared__ tab_t sctrl[D3_CTRL_W];
   for (int i = threadIdx.x; i < D3_CTRL_W; i += blockDim.x) sctrl[i] = c.model->ctrl[i];
   __syncthreads();
-  const int e_raw = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = e_raw < c.n;
-  const int e = live ? e_raw : c.n - 1;
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= c.n) return;
   const int n = c.n;
   const float* row = c.state + (size_t)e * c.row;
   IkState s;
@@ -90,7 +88,7 @@ __device__ __noinline__ void ik_role(const DevCtx& c, tab_t* sctrl, const float*
     float nq = rsqrtf(a[3] * a[3] + a[4] * a[4] + a[5] * a[5] + a[6] * a[6]);
     s.des_pos[0] = a[0]; s.des_pos[1] = a[1]; s.des_pos[2] = a[2];
     for (int k = 0; k < 4; k++) s.des_quat[k] = a[3 + k] * nq;
-    if (live) for (int k = 0; k < 7; k++) c.ik.des[k * n + e] = k < 3 ? s.des_pos[k] : s.des_quat[k - 3];
+    for (int k = 0; k < 7; k++) c.ik.des[k * n + e] = k < 3 ? s.des_pos[k] : s.des_quat[k - 3];
   } else {
     for (int k = 0; k < 3; k++) s.des_pos[k] = c.ik.des[k * n + e];
     for (int k = 0; k < 4; k++) s.des_quat[k] = c.ik.des[(3 + k) * n + e];
@@ -99,32 +97,20 @@ __device__ __noinline__ void ik_role(const DevCtx& c, tab_t* sctrl, const float*
     for (int k = 0; k < 7; k++) s.q[k] = (double)row[c.lay.qpos + k] + (double)row[c.lay.qlo + k];
     s.valid = 1;
   }
-  double V[36]; int vwarm = 0;                 // eigenbasis carried across the IK iterations of this launch
+  double V[36]; int vwarm = 0;              // eigenbasis carried across the IK iterations of this launch
   for (int t = 0; t < n_ticks; t++) {
     if (cart) ik_tick(sctrl, s, V, &vwarm);
-    if (live) {
-      float* tr = c.traj + (size_t)t * 21 * n + e;
-      for (int k = 0; k < 7; k++) { tr[k * n] = s.jt_q[k]; tr[(7 + k) * n] = s.jt_qlo[k]; tr[(14 + k) * n] = s.jt_qd[k]; }
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) *(volatile int*)(c.ik_flags + blockIdx.x) = flag_base + t + 1;
+    float* tr = c.traj + (size_t)t * 21 * n + e;
+    for (int k = 0; k < 7; k++) { tr[k * n] = s.jt_q[k]; tr[(7 + k) * n] = s.jt_qlo[k]; tr[(14 + k) * n] = s.jt_qd[k]; }
   }
-  if (live) {
-    for (int k = 0; k < 7; k++) { c.ik.q[k * n + e] = s.q[k]; c.ik.jt[k * n + e] = s.jt_q[k]; c.ik.jt[(7 + k) * n + e] = s.jt_qlo[k]; c.ik.jt[(14 + k) * n + e] = s.jt_qd[k]; }
-    c.ik.valid[e] = s.valid;
-  }
+  for (int k = 0; k < 7; k++) { c.ik.q[k * n + e] = s.q[k]; c.ik.jt[k * n + e] = s.jt_q[k]; c.ik.jt[(7 + k) * n + e] = s.jt_qlo[k]; c.ik.jt[(14 + k) * n + e] = s.jt_qd[k]; }
+  c.ik.valid[e] = s.valid;
 }
 
-// Env step, one launch per env step with two CTA roles:
-//   blocks [0, n_ik)    : IK reference (thread per env, fp64) — never wait on anything, dispatched first;
-//   blocks [n_ik, grid) : physics, one G-lane group per env; tick t starts once the IK block(s) owning this CTA's envs
-//                         have published tick t (acquire on the flag), so the IK latency hides behind the physics.
-// gym = 1: GymEnvWrapper.step semantics around the ticks; gym = 0: bare ticks (d3il_substep).
+// Env step: one warp per env.  gym = 1: GymEnvWrapper.step semantics around the ticks; gym = 0: bare ticks (substep).
 __global__ void __launch_bounds__(CTA_THREADS, (CTA_THREADS > 256 ? 1 : 2))
-k_env(DevCtx c, int n_ticks, int gym, int n_ik, int flag_base, const float* __restrict__ action, float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ done, float* __restrict__ info) {
+k_env(DevCtx c, int n_ticks, int gym, float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ done, float* __restrict__ info) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  if ((int)blockIdx.x < n_ik) { ik_role(c, (tab_t*)smem_raw, action, n_ticks, gym, flag_base); return; }
   Model* sm = (Model*)smem_raw;
   stage_model(sm, c.model);
   const Model& m = *sm;
@@ -134,26 +120,16 @@ k_env(DevCtx c, int n_ticks, int gym, int n_ik, int flag_base, const float* __re
   cx.mask = G_LANES == 32 ? 0xffffffffu : (((1u << G_LANES) - 1u) << (((threadIdx.x & 31) / G_LANES) * G_LANES));
   // Groups past the end of the batch shadow the last env (same inputs, same control flow, identical outputs) so that
   // every thread of the CTA reaches the phase barriers inside physics_tick.
-  const int e_raw = ((int)blockIdx.x - n_ik) * ENVS_PER_CTA + warp;
+  const int e_raw = blockIdx.x * ENVS_PER_CTA + warp;
   const int e = e_raw < c.n ? e_raw : c.n - 1;
-  // IK blocks that feed this CTA's envs (envs of a CTA are contiguous; an IK block covers CTA_THREADS envs)
-  const int e_first = ((int)blockIdx.x - n_ik) * ENVS_PER_CTA;
-  const int e_last = min(e_first + ENVS_PER_CTA - 1, c.n - 1);
-  const int ikb0 = e_first / CTA_THREADS, ikb1 = e_last / CTA_THREADS;
   float* w = (float*)(smem_raw + ((sizeof(Model) + 127) & ~(size_t)127)) + (size_t)warp * c.ws_stride;
   float* row = c.state + (size_t)e * c.row;
   for (int i = cx.lane; i < L.n_state; i += G_LANES) w[i] = row[i];
   __syncwarp(cx.mask);
   if (gym) env_prestep<G_LANES>(cx, m, L, w, obs + (size_t)e * m.obs_dim, reward + e, done + e);
   for (int t = 0; t < n_ticks; t++) {
-    if (threadIdx.x == 0) {
-      const int want = flag_base + t + 1;
-      for (int b = ikb0; b <= ikb1; b++) while (*(volatile int*)(c.ik_flags + b) < want) __nanosleep(200);
-      __threadfence();
-    }
-    __syncthreads();
     const float* tr = c.traj + (size_t)t * 21 * c.n + e;
-    for (int k = cx.lane; k < 21; k += G_LANES) w[L.jt + k] = __ldcg(tr + (size_t)k * c.n);
+    for (int k = cx.lane; k < 21; k += G_LANES) w[L.jt + k] = tr[(size_t)k * c.n];
     __syncwarp(cx.mask);
     physics_tick<G_LANES, true>(cx, m, L, w, w + L.jt, w + L.jt + 7, w + L.jt + 14, c.tol, c.max_iter);
   }
@@ -227,9 +203,6 @@ extern "C" int d3il_create(d3il_env** out, const void* blob, size_t nbytes, int 
   CK(cudaMemset(d.ik.jt, 0, (size_t)21 * n_envs * sizeof(float)));
   CK(cudaMemset(d.ik.valid, 0, (size_t)n_envs * sizeof(int)));
   CK(cudaMalloc(&d.traj, (size_t)h->max_ticks * 21 * n_envs * sizeof(float)));
-  h->n_ik_blocks = (n_envs + CTA_THREADS - 1) / CTA_THREADS; h->launch_id = 0;
-  CK(cudaMalloc(&d.ik_flags, (size_t)h->n_ik_blocks * sizeof(int)));
-  CK(cudaMemset(d.ik_flags, 0, (size_t)h->n_ik_blocks * sizeof(int)));
   h->smem_bytes = ((sizeof(Model) + 127) & ~(size_t)127) + (size_t)ENVS_PER_CTA * d.ws_stride * sizeof(float);
   if (h->smem_bytes > 227 * 1024) { g_err = "d3il_create: scene workspace does not fit in shared memory"; delete h; return -1; }
   CK(cudaFuncSetAttribute(k_env, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
@@ -255,7 +228,7 @@ extern "C" void d3il_destroy(d3il_env* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaFree((void*)h->d.model); cudaFree(h->d.state); cudaFree(h->d.ik.q); cudaFree(h->d.ik.des); cudaFree(h->d.ik.jt); cudaFree(h->d.ik.valid);
-  cudaFree(h->d.traj); cudaFree(h->d.ik_flags); cudaFreeHost(h->h_in); cudaFreeHost(h->h_out); cudaFreeHost(h->h_mask); cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_mask);
+  cudaFree(h->d.traj); cudaFreeHost(h->h_in); cudaFreeHost(h->h_out); cudaFreeHost(h->h_mask); cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_mask);
   cudaStreamDestroy(h->own_stream);
   delete h;
 }
@@ -301,10 +274,10 @@ extern "C" int d3il_step(d3il_env* h, const float* action, float* obs, float* re
   CK(cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;
   if (h->profiling) CK(cudaEventRecord(h->ev[0], s));
+  k_ik<<<(h->n + 127) / 128, 128, 0, s>>>(h->d, action, h->m.n_substeps, 1);
   if (h->profiling) CK(cudaEventRecord(h->ev[1], s));
-  h->launch_id = (h->launch_id + 1) & 0xffffff;
-  k_env<<<h->n_ik_blocks + env_grid(h), CTA_THREADS, h->smem_bytes, s>>>(h->d, h->m.n_substeps, 1, h->n_ik_blocks, h->launch_id * 64, action, obs, reward, done, info);
-  h->launches += 1;
+  k_env<<<env_grid(h), CTA_THREADS, h->smem_bytes, s>>>(h->d, h->m.n_substeps, 1, obs, reward, done, info);
+  h->launches += 2;
   CK(cudaGetLastError());
   if (h->profiling) {
     // per-kernel device time on the launching stream (bench.py roofline); synchronises, so only for profiling passes
@@ -324,9 +297,9 @@ extern "C" int d3il_substep(d3il_env* h, int n, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   while (n > 0) {
     int k = n < h->max_ticks ? n : h->max_ticks;
-    h->launch_id = (h->launch_id + 1) & 0xffffff;
-    k_env<<<h->n_ik_blocks + env_grid(h), CTA_THREADS, h->smem_bytes, s>>>(h->d, k, 0, h->n_ik_blocks, h->launch_id * 64, nullptr, nullptr, nullptr, nullptr, nullptr);
-    h->launches += 1;
+    k_ik<<<(h->n + 127) / 128, 128, 0, s>>>(h->d, nullptr, k, 0);
+    k_env<<<env_grid(h), CTA_THREADS, h->smem_bytes, s>>>(h->d, k, 0, nullptr, nullptr, nullptr, nullptr);
+    h->launches += 2;
     n -= k;
   }
   CK(cudaGetLastError());
