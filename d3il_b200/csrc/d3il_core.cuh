@@ -29,6 +29,7 @@ typedef float tab_t;    // model tables are fp32 in shared memory
 #ifdef D3IL_EMU
 #define DEVFN static inline
 #define DEVNI static inline
+#define HDFN static inline
 #define D3_RESTRICT
 struct Cx { int lane; unsigned mask; };
 template <int G> DEVFN void gsync(const Cx&) {}
@@ -38,6 +39,7 @@ template <int G> DEVFN int gsumi(const Cx&, int x) { return x; }
 template <int G> DEVFN int gori(const Cx&, int x) { return x; }
 #else
 #define DEVFN __device__ __forceinline__
+#define HDFN __host__ __device__ __forceinline__
 #define DEVNI __device__ __noinline__       // big, multiply-instantiated routines: the kernel is instruction-fetch bound
 #define D3_RESTRICT __restrict__
 struct Cx { int lane; unsigned mask; };
@@ -150,6 +152,9 @@ struct Model {
   int d_bs[D3_MAXV], d_be[D3_MAXV];       // [start, end) of the dof's kinematic-tree block (M is block diagonal over these)
   int maxblk;                             // largest block
   int ndamp, damp_first, damp_end;        // trailing damped dofs of the arm block (implicit-damping refactor)
+  unsigned char p_rng[D3_MAXPAIR * 4];    // per pair: dof ranges [a0,a1) [b0,b1) touched by its two geoms (static)
+  unsigned char p_cpl[D3_MAXPAIR];        // pair joins two different kinematic-tree blocks
+  unsigned char g_slab[32];               // geom is a static, axis-aligned box (table top, support): eligible for the slab fast path
   unsigned char tri_i[136], tri_j[136];   // row-major lower-triangle unranking table for n <= 16
   unsigned char mp_a[D3_MAXV * 8], mp_b[D3_MAXV * 8];   // (a,b) list of related dof pairs, a >= b
   tab_t link[D3_MAXLINK * D3_LINK_W];
@@ -170,7 +175,7 @@ struct Lay {
   int n_state;
   // scratch
   int xpos, xmat, S, I10, Ic, vel, cj, frc, F, M, mdinv, mpiv, H, hdinv, hpiv, bias, qfrc_smooth, qacc_smooth, qacc, qfrc_c, grad, pvec, Ma, tmpv;
-  int act, jt, con, ncon_pair, J, aref, D, jar, frcE, Jp, hd, hb, etype, econ, total;
+  int act, jt, con, ncon_pair, limflag, cflag, J, aref, D, jar, frcE, Jp, hd, hb, etype, econ, total;
 };
 enum { ST_GRIP_SET = 0, ST_GRASP, ST_CTRL_MODE, ST_STEP, ST_TERM, ST_STATUS, ST_OBST, ST_TASK0, ST_TASK1, ST_TASK2, ST_TASK3, ST_NMISC = 16 };
 #define D3_CON_W 24    // per contact: pos3, frame9, dist, incl, mu, dim, g1, g2, pair, row0, dof ranges a0,a1,b0,b1
@@ -191,7 +196,7 @@ static inline void d3il_layout(const Model& m, Lay& L) {
   //   view 1 (kinematics, dynamics, collision, constraint assembly)   view 2 (Newton solver, Euler)
   const int x0 = o;
   L.xpos = take(3 * m.nlink); L.xmat = take(9 * m.nlink); L.S = take(6 * m.nv); L.I10 = take(10 * m.nlink); L.Ic = take(10 * m.nlink);
-  L.vel = take(6 * m.nlink); L.cj = take(6 * m.nlink); L.frc = take(6 * m.nlink); L.F = take(6 * m.nv); L.ncon_pair = take(m.npair + 4);
+  L.vel = take(6 * m.nlink); L.cj = take(6 * m.nlink); L.frc = take(6 * m.nlink); L.F = take(6 * m.nv); L.ncon_pair = take(m.npair + 4); L.limflag = take(2 * D3_NROB); L.cflag = take(m.maxcon);
   const int x1 = o;
   o = x0;
   L.H = take(m.nv * m.nv); L.hdinv = take(m.nv); L.hpiv = take(m.nv); L.jar = take(m.maxrow); L.frcE = take(m.maxrow); L.Jp = take(m.maxrow);
@@ -437,6 +442,38 @@ DEVFN int clip_poly(real (*P)[3], int n, real hu, real hv) {
     if (n == 0) return 0;
   }
   return n;
+}
+
+// Fast path of collide_box_box for a dynamic box B resting on / sunk into the top face of a big static axis-aligned
+// box A (table plane, support body): when B's bounding circle lies inside A's top rectangle, B's centre is above A's
+// and the overlap along z is shallower than B's bounding radius, the SAT of the general routine always selects A's +z
+// face (every other axis overlaps by at least the bounding radius; ties go to A's faces), nothing is clipped, and the
+// contacts are the vertices of B's most downward face that lie below the top plane.  Same arithmetic, same order.
+// Returns -1 when the preconditions do not hold (caller falls back to the general routine).
+DEVFN int collide_slab_box(const real* pA, const real* hA, const real* pB, const real* RB, const real* hB, real rboundB, real margin, RawCon* out) {
+  real tx = pB[0] - pA[0], ty = pB[1] - pA[1], tz = pB[2] - pA[2];
+  if (!(absr(tx) + rboundB <= hA[0] && absr(ty) + rboundB <= hA[1] && tz > 0)) return -1;
+  real rBz = hB[0] * absr(RB[6]) + hB[1] * absr(RB[7]) + hB[2] * absr(RB[8]);
+  real sepz = tz - (hA[2] + rBz);
+  if (sepz > margin) return 0;
+  if (!(sepz > (real)-0.5 * rboundB)) return -1;
+  int jx = 0; real jb = -1;
+  for (int j = 0; j < 3; j++) { real v = absr(RB[6 + j]); if (v > jb) { jb = v; jx = j; } }
+  real isg = RB[6 + jx] > 0 ? (real)-1 : (real)1;
+  int k1 = (jx + 1) % 3, k2 = (jx + 2) % 3;
+  if (k1 > k2) { int tmp = k1; k1 = k2; k2 = tmp; }
+  int cnt = 0;
+  for (int c = 0; c < 4; c++) {
+    real s1 = (c == 1 || c == 2) ? (real)1 : (real)-1, s2 = (c >= 2) ? (real)1 : (real)-1;
+    real ww[3];
+    for (int k = 0; k < 3; k++) ww[k] = pB[k] + isg * hB[jx] * RB[3 * k + jx] + s1 * hB[k1] * RB[3 * k + k1] + s2 * hB[k2] * RB[3 * k + k2] - pA[k];
+    real dist = ww[2] - hA[2];
+    if (dist >= margin) continue;
+    out[cnt].pos[0] = pA[0] + ww[0]; out[cnt].pos[1] = pA[1] + ww[1]; out[cnt].pos[2] = pA[2] + (hA[2] + (real)0.5 * dist);
+    out[cnt].n[0] = 0; out[cnt].n[1] = 0; out[cnt].n[2] = 1;
+    out[cnt].dist = dist; cnt++;
+  }
+  return cnt;
 }
 
 DEVNI int collide_box_box(const real* pA, const real* RA, const real* hA, const real* pB, const real* RB, const real* hB, real margin, RawCon* out) {
@@ -695,7 +732,10 @@ DEVFN int collision(const Cx& cx, const Model& m, const Lay& L, real* w) {
       if (norm3(dc) <= (real)ga[12] + (real)gb[12] + margin) {
         real s1[3] = {(real)ga[9], (real)ga[10], (real)ga[11]}, s2[3] = {(real)gb[9], (real)gb[10], (real)gb[11]};
         int t1 = (int)ga[0], t2 = (int)gb[0];
-        if (t1 == D3G_BOX && t2 == D3G_BOX) myn = collide_box_box(p1, R1, s1, p2, R2, s2, margin, rc);
+        if (t1 == D3G_BOX && t2 == D3G_BOX) {
+          myn = m.g_slab[g1] ? collide_slab_box(p1, s1, p2, R2, s2, (real)gb[12], margin, rc) : -1;
+          if (myn < 0) myn = collide_box_box(p1, R1, s1, p2, R2, s2, margin, rc);
+        }
         else if (t1 == D3G_CYLINDER && t2 == D3G_BOX) myn = collide_cyl_box(p1, R1, s1, p2, R2, s2, margin, rc);
         else if (t1 == D3G_CYLINDER && t2 == D3G_CYLINDER) myn = collide_cyl_cyl(p1, R1, s1, p2, R2, s2, margin, rc);
       }
@@ -752,7 +792,7 @@ DEVFN real impedance(const real* solimp, real pos, real margin) {
 }
 
 // dof range touched by a geom's link: robot links reach dofs [0, own dof]; free bodies their 6 dofs; static: empty
-DEVFN void link_range(const Model& m, int li, int* lo, int* hi) {
+HDFN void link_range(const Model& m, int li, int* lo, int* hi) {
   if (li < 0) { *lo = 0; *hi = 0; return; }
   if (m.l_jtype[li] == 2) { *lo = m.l_dadr[li]; *hi = m.l_dadr[li] + 6; return; }
   *lo = m.d_bs[m.l_dadr[li]]; *hi = m.l_dadr[li] + 1;
@@ -769,54 +809,60 @@ DEVFN real jrow_dot(const real* Jrow, const real* v, int a0, int a1, int b0, int
 // compact-row entry of dof d (must lie in one of the ranges)
 DEVFN real jrow_at(const real* Jrow, int d, int a0, int a1, int b0) { return d < a1 && d >= a0 ? Jrow[d - a0] : Jrow[(a1 - a0) + d - b0]; }
 
-// Rows: joint limits first (one dof each), then dim rows per active contact (elliptic).  Returns nefc (all lanes);
-// *coupled is set when some contact joins two different kinematic-tree blocks (then H is not block diagonal).
+// Rows: joint limits first (one dof each), then 3 rows per active contact (elliptic, condim 3).  Returns nefc (all
+// lanes); *coupled is set when some active contact joins two different kinematic-tree blocks (then H is not block
+// diagonal).  Row numbers come from prefix counts over activity flags, so the row order is deterministic.
 template <int G>
 DEVFN int make_constraints(const Cx& cx, const Model& m, const Lay& L, real* w, int ncon, int* nlimit, int* coupled) {
   const int nv = m.nv;
-  // --- joint limit rows: deterministic order (link, side); every lane scans the same state
-  int ne = 0;
-  for (int i = 0; i < m.nlink; i++) {
-    if (!m.l_limited[i] || m.l_jtype[i] == 2) continue;
+  // --- activity flags: joint limit candidates k = (robot link, side), contacts
+  LANES(k, 2 * D3_NROB) {
+    int i = k >> 1, side = k & 1;
     const tab_t* Lk = m.link + D3_LINK_W * i;
     real q = w[L.qpos + m.l_qadr[i]];
-    for (int side = 0; side < 2; side++) {
-      real dist = side == 0 ? q - (real)Lk[23] : (real)Lk[24] - q;
-      if (dist >= 0) continue;
-      if (ne < m.maxrow) {
-        LANES(z, 1) {
-          real solref[2] = {(real)m.ctrl[D3C_JNT_SOLREF], (real)m.ctrl[D3C_JNT_SOLREF + 1]}, solimp[5];
-          for (int k = 0; k < 5; k++) solimp[k] = m.ctrl[D3C_JNT_SOLIMP + k];
-          real imp = impedance(solimp, dist, 0);
-          real kk = 1 / (solimp[1] * solimp[1] * solref[0] * solref[0] * solref[1] * solref[1]), bb = 2 / (solimp[1] * solref[0]);
-          real sg = side == 0 ? (real)1 : (real)-1;
-          real Rv = maxr((real)1e-15, (1 - imp) / imp * (real)Lk[27]);
-          w[L.D + ne] = 1 / Rv;
-          w[L.aref + ne] = -bb * sg * w[L.qvel + m.l_dadr[i]] - kk * imp * dist;
-          w[L.econ + ne] = (real)(side == 0 ? m.l_dadr[i] + 1 : -(m.l_dadr[i] + 1));     // limit rows: signed dof id (+lower / -upper)
-        }
-        ne++;
-      } else { LANES(z, 1) w[L.misc + ST_STATUS] = (real)(((int)w[L.misc + ST_STATUS]) | 2); }
-    }
+    real dist = side == 0 ? q - (real)Lk[23] : (real)Lk[24] - q;
+    w[L.limflag + k] = (m.l_limited[i] && dist < 0) ? (real)1 : (real)0;
   }
-  *nlimit = ne;
-  // --- contact rows: row0 by prefix over contact dims (every lane computes the same prefix), dof ranges per contact
-  int row = ne, cpl = 0;
-  for (int c = 0; c < ncon; c++) {
+  LANES(c, ncon) { const real* cc = w + L.con + D3_CON_W * c; w[L.cflag + c] = cc[12] < cc[13] ? (real)1 : (real)0; }
+  gsync<G>(cx);
+  int nl = 0;
+  for (int k = 0; k < 2 * D3_NROB; k++) nl += (int)w[L.limflag + k];
+  if (nl > m.maxrow) nl = m.maxrow;
+  LANES(k, 2 * D3_NROB) {
+    if (w[L.limflag + k] == 0) continue;
+    int ne = 0;
+    for (int j = 0; j < k; j++) ne += (int)w[L.limflag + j];
+    if (ne >= m.maxrow) continue;
+    int i = k >> 1, side = k & 1;
+    const tab_t* Lk = m.link + D3_LINK_W * i;
+    real q = w[L.qpos + m.l_qadr[i]];
+    real dist = side == 0 ? q - (real)Lk[23] : (real)Lk[24] - q;
+    real solref[2] = {(real)m.ctrl[D3C_JNT_SOLREF], (real)m.ctrl[D3C_JNT_SOLREF + 1]}, solimp[5];
+    for (int kk2 = 0; kk2 < 5; kk2++) solimp[kk2] = m.ctrl[D3C_JNT_SOLIMP + kk2];
+    real imp = impedance(solimp, dist, 0);
+    real kk = 1 / (solimp[1] * solimp[1] * solref[0] * solref[0] * solref[1] * solref[1]), bb = 2 / (solimp[1] * solref[0]);
+    real sg = side == 0 ? (real)1 : (real)-1;
+    real Rv = maxr((real)1e-15, (1 - imp) / imp * (real)Lk[27]);
+    w[L.D + ne] = 1 / Rv;
+    w[L.aref + ne] = -bb * sg * w[L.qvel + m.l_dadr[i]] - kk * imp * dist;
+    w[L.econ + ne] = (real)(side == 0 ? m.l_dadr[i] + 1 : -(m.l_dadr[i] + 1));     // signed dof id (+lower / -upper)
+  }
+  *nlimit = nl;
+  int row = nl, cpl = 0, overflow = 0;
+  LANES(c, ncon) {
     real* cc = w + L.con + D3_CON_W * c;
-    int dim = (int)cc[15];
-    int active = cc[12] < cc[13];
-    int l1 = (int)m.geom[D3_GEOM_W * (int)cc[16] + 1], l2 = (int)m.geom[D3_GEOM_W * (int)cc[17] + 1];
-    int a0, a1, b0, b1;
-    link_range(m, l1, &a0, &a1); link_range(m, l2, &b0, &b1);
-    if (a1 > a0 && b1 > b0) {
-      if (b0 < a0) { int t0 = a0, t1 = a1; a0 = b0; a1 = b1; b0 = t0; b1 = t1; }
-      if (b0 < a1) { a1 = a1 > b1 ? a1 : b1; b0 = b1 = 0; }                  // same tree: merge into one range
-      else if (active) cpl = 1;                                               // two different blocks
-    } else if (a1 == a0) { a0 = b0; a1 = b1; b0 = b1 = 0; }
-    if (active && row + dim <= m.maxrow) { LANES(z, 1) { cc[19] = (real)row; cc[20] = (real)a0; cc[21] = (real)a1; cc[22] = (real)b0; cc[23] = (real)b1; } row += dim; }
-    else { LANES(z, 1) { cc[19] = -1; if (active) w[L.misc + ST_STATUS] = (real)(((int)w[L.misc + ST_STATUS]) | 2); } }
+    if (w[L.cflag + c] == 0) { cc[19] = -1; continue; }
+    int idx = 0;
+    for (int j = 0; j < c; j++) idx += (int)w[L.cflag + j];
+    int r0 = nl + 3 * idx;
+    if (r0 + 3 > m.maxrow) { cc[19] = -1; overflow = 1; continue; }
+    int ip = (int)cc[18];
+    cc[19] = (real)r0; cc[20] = (real)m.p_rng[4 * ip]; cc[21] = (real)m.p_rng[4 * ip + 1]; cc[22] = (real)m.p_rng[4 * ip + 2]; cc[23] = (real)m.p_rng[4 * ip + 3];
+    if (m.p_cpl[ip]) cpl = 1;
   }
+  for (int c = 0; c < ncon; c++) if (w[L.cflag + c] != 0 && row + 3 <= m.maxrow) row += 3;
+  cpl = gori<G>(cx, cpl); overflow = gori<G>(cx, overflow);
+  if (overflow) { LANES(z, 1) w[L.misc + ST_STATUS] = (real)(((int)w[L.misc + ST_STATUS]) | 2); }
   *coupled = cpl;
   gsync<G>(cx);
   const real impratio = m.ctrl[D3C_IMPRATIO];

@@ -42,6 +42,7 @@ static inline bool d3il_build_model(const void* blob, size_t nbytes, Model& m, L
     double R[9] = {1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y), 2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x),
                    2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)};
     for (int k = 0; k < 9; k++) m.geomR[9 * i + k] = (tab_t)R[k];
+    m.g_slab[i] = ((int)p[0] == D3G_BOX && (int)p[1] < 0 && w == 1.0 && x == 0.0 && y == 0.0 && z == 0.0) ? 1 : 0;
   }
   int conmax = 0;
   for (int i = 0; i < m.npair; i++, p += D3_PAIR_W) {
@@ -74,6 +75,19 @@ static inline bool d3il_build_model(const void* blob, size_t nbytes, Model& m, L
   if (m.ndamp) {
     bool ok = m.ndamp <= 4 && m.damp_end - m.damp_first == m.ndamp && m.damp_end == m.d_be[m.damp_first];
     if (!ok) { err = "damped dofs must be the trailing dofs of their block"; return false; }
+  }
+  for (int ip = 0; ip < m.npair; ip++) {
+    int l1 = (int)m.geom[D3_GEOM_W * (int)m.pair[D3_PAIR_W * ip] + 1], l2 = (int)m.geom[D3_GEOM_W * (int)m.pair[D3_PAIR_W * ip + 1] + 1];
+    int a0, a1, b0, b1, cpl = 0;
+    link_range(m, l1, &a0, &a1); link_range(m, l2, &b0, &b1);
+    if (a1 > a0 && b1 > b0) {
+      if (b0 < a0) { int t0 = a0, t1 = a1; a0 = b0; a1 = b1; b0 = t0; b1 = t1; }
+      if (b0 < a1) { a1 = a1 > b1 ? a1 : b1; b0 = b1 = 0; }      // same tree: one merged range
+      else cpl = 1;                                               // two different blocks
+    } else if (a1 == a0) { a0 = b0; a1 = b1; b0 = b1 = 0; }
+    if ((a1 - a0) + (b1 - b0) > D3_JW) { err = "contact dof ranges exceed the compact Jacobian row width"; return false; }
+    m.p_rng[4 * ip] = (unsigned char)a0; m.p_rng[4 * ip + 1] = (unsigned char)a1; m.p_rng[4 * ip + 2] = (unsigned char)b0; m.p_rng[4 * ip + 3] = (unsigned char)b1;
+    m.p_cpl[ip] = (unsigned char)cpl;
   }
   { int e = 0; for (int i = 0; i < 16; i++) for (int j = 0; j <= i; j++) { m.tri_i[e] = (unsigned char)i; m.tri_j[e] = (unsigned char)j; e++; } }
   m.maxcon = conmax < 20 ? ((conmax + 3) & ~3) : 20;

@@ -79,3 +79,15 @@ int emu_probe(Emu* e, const char* what, double* out, int cap) {
 void emu_get_state(Emu* e, double* out) { d3il_pack_state(e->m, e->L, e->w.data(), e->ik, out); }
 void emu_set_state(Emu* e, const double* in) { d3il_unpack_state(e->m, e->L, e->w.data(), e->ik, in); }
 }
+
+// stand-alone narrow-phase probes of the kernel core (fast path vs general routine)
+extern "C" int emu_collide_boxes(const double* pA, const double* hA, const double* pB, const double* qB, const double* hB, int use_fast, double* out) {
+  real pa[3], ha[3], pb[3], qb[4], hb[3], RA[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, RB[9];
+  for (int k = 0; k < 3; k++) { pa[k] = (real)pA[k]; ha[k] = (real)hA[k]; pb[k] = (real)pB[k]; hb[k] = (real)hB[k]; }
+  for (int k = 0; k < 4; k++) qb[k] = (real)qB[k];
+  quat2mat(RB, qb);
+  RawCon rc[8];
+  int n = use_fast ? collide_slab_box(pa, ha, pb, RB, hb, sqrt(hb[0] * hb[0] + hb[1] * hb[1] + hb[2] * hb[2]), 0, rc) : collide_box_box(pa, RA, ha, pb, RB, hb, 0, rc);
+  for (int i = 0; i < n; i++) { for (int k = 0; k < 3; k++) { out[7 * i + k] = rc[i].pos[k]; out[7 * i + 3 + k] = rc[i].n[k]; } out[7 * i + 6] = rc[i].dist; }
+  return n;
+}
