@@ -1,0 +1,151 @@
+"""Host-side pieces that need no GPU: C-ABI exports, scene tables, metrics, sharding + gather (gloo, world_size 2)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    from d3il_b200 import lib
+    lib.build()
+    L = C.CDLL(lib.SO_PATH)
+    header = open(os.path.join(ROOT, "include", "d3il.h")).read()
+    declared = set(re.findall(r"\b(d3il_[a-z_]+)\s*\(", header))
+    assert declared == set(lib.EXPORTS), declared ^ set(lib.EXPORTS)
+    for name in declared:
+        assert hasattr(L, name), name
+
+
+def test_create_fails_loudly_without_gpu():
+    """No CPU fallback: on a machine without CUDA d3il_create must return an error, never a working handle."""
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from d3il_b200 import lib
+    from d3il_b200.scene.blob import load_scene
+    L = lib.lib()
+    blob, _ = load_scene("pushing")
+    h = C.c_void_p()
+    rc = L.d3il_create(C.byref(h), blob, len(blob), 4, 0)
+    assert rc != 0 and not h.value and b"CUDA" in L.d3il_last_error()
+    with pytest.raises(RuntimeError):
+        from d3il_b200.batched_env import BatchedEnv
+        BatchedEnv("pushing", 4, "cpu")
+
+
+def test_scene_tables_known_answers():
+    """Compiler output vs SURVEY §8c known answers (offline IK start pose) and App. A sizes."""
+    from d3il_b200.scene import blob as B
+    _, sc = B.load_scene("pushing")
+    h = sc.header
+    assert (h["nq"], h["nv"], h["nlink"], h["nobj"], h["n_substeps"], h["max_steps"], h["obs_dim"]) == (23, 21, 11, 2, 35, 400, 8)
+    init_qpos = sc.ctrl[B.C_INIT_QPOS:B.C_INIT_QPOS + 7]
+    assert np.allclose(init_qpos, [-0.356409, 0.429445, -0.135011, -2.054652, 0.093578, 2.480718, 0.232507], atol=2e-6)
+    # free boxes: invweight0 = (1/m, 1/I) for a 0.05 kg, 6 cm cube
+    box = sc.geom[3]
+    assert abs(box[13] - 20.0) < 1e-9 and abs(box[14] - 1.0 / (0.05 / 3 * 2 * 0.03 ** 2)) < 1e-3
+    # mixed box-table contact parameters (App. B.5): solref[0] = (0.002 + 0.02)/2, friction 1
+    pair = sc.pair[0]
+    assert abs(pair[8] - 0.011) < 1e-12 and pair[3] == 1.0 and int(pair[2]) == 3
+    _, av = B.load_scene("avoiding")
+    assert (av.header["nq"], av.header["nv"], av.header["npair"], av.header["max_steps"]) == (9, 9, 6, 250)
+
+
+def test_mode_entropy_matches_reference_loops():
+    """metrics.mode_entropy == the per-context Python loops of simulation/pushing_sim.py:140-167."""
+    from d3il_b200.simulation.metrics import avoiding_entropy, mode_entropy
+    g = torch.Generator().manual_seed(0)
+    n_ctx, n_traj, n_modes = 30, 8, 4
+    modes = torch.randint(-1, 4, (n_ctx, n_traj), generator=g).float()
+    succ = (torch.rand(n_ctx, n_traj, generator=g) > 0.4).float()
+    probs, ent = mode_entropy(modes, succ, n_modes)
+    ref = torch.zeros(n_ctx, n_modes)
+    for c in range(n_ctx):
+        ref[c, :] = torch.tensor([sum(modes[c, succ[c, :] == 1] == k) / n_traj for k in range(n_modes)])
+    ref /= (ref.sum(1).reshape(-1, 1) + 1e-12)
+    ent_ref = -(ref * torch.log(ref + 1e-12) / torch.log(torch.tensor(float(n_modes)))).sum(1).mean()
+    assert torch.allclose(probs, ref) and torch.allclose(ent, ent_ref)
+    # avoiding: numpy restatement of avoiding_sim.py:128-134
+    enc = (torch.rand(40, 9, generator=g) > 0.6).float()
+    s = (torch.rand(40, generator=g) > 0.3).float()
+    data = enc[s == 1].numpy()
+    dec = data.dot(1 << np.arange(9))
+    _, counts = np.unique(dec, return_counts=True)
+    dist = counts / counts.sum()
+    assert abs(float(avoiding_entropy(enc, s)[1]) - float(-np.sum(dist * (np.log(dist) / np.log(24))))) < 1e-6
+
+
+def test_agent_adapter_matches_single_sample_predict():
+    """Batched BC-style path == looping the agent's own predict() (bc_agent.py:241-271 restated on a stub agent)."""
+    from d3il_b200.simulation.agent_adapter import predict_batch
+
+    class Scaler:
+        def __init__(self):
+            self.x_mean, self.x_std = torch.linspace(-0.2, 0.3, 10), torch.linspace(0.5, 1.5, 10)
+            self.y_mean, self.y_std = torch.tensor([0.001, -0.002]), torch.tensor([0.004, 0.005])
+
+        def scale_input(self, x):
+            return ((x - self.x_mean) / (self.x_std + 1e-12)).float()
+
+        def inverse_scale_output(self, y):
+            return y * (self.y_std + 1e-12) + self.y_mean
+
+    class Agent:
+        def __init__(self):
+            torch.manual_seed(0)
+            self.model = torch.nn.Sequential(torch.nn.Linear(10, 32), torch.nn.Mish(), torch.nn.Linear(32, 2))
+            self.scaler, self.device = Scaler(), "cpu"
+            self.min_action, self.max_action = torch.tensor([-1.5, -1.5]), torch.tensor([1.5, 1.5])
+
+        @torch.no_grad()
+        def predict(self, state):
+            st = torch.from_numpy(state).float().unsqueeze(0).unsqueeze(0)
+            out = self.model(self.scaler.scale_input(st)).clamp_(self.min_action, self.max_action)
+            return self.scaler.inverse_scale_output(out).numpy()[0]
+
+        def reset(self):
+            pass
+
+    agent = Agent()
+    obs = torch.randn(17, 10)
+    batched = predict_batch(agent, obs)
+    looped = np.stack([agent.predict(o.numpy())[0] for o in obs])
+    assert np.allclose(batched.numpy(), looped, atol=1e-6)
+
+
+def _gloo_worker(rank, world, port, n_items, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from d3il_b200.simulation.base_sim import BaseSim
+    lo, hi = BaseSim.shard_range(n_items, rank, world)
+    rows = torch.arange(lo, hi, dtype=torch.float32).unsqueeze(1) * torch.tensor([[1.0, 10.0, 100.0]])
+    out = BaseSim.gather_rows(rows, n_items)
+    q.put((rank, lo, hi, out.numpy()))
+    dist.destroy_process_group()
+
+
+def test_sharding_and_gather_world_size_2():
+    """N>1 path of the rollout harness on CPU: contiguous (context, rollout) shards per rank + one gather of the
+    per-env result rows (gloo, world_size 2) — the replacement of the share_memory_() tensors in pushing_sim.py:97-99."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    n_items, world, port = 37, 2, 29500 + os.getpid() % 500
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, n_items, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    expect = np.arange(n_items, dtype=np.float32)[:, None] * np.array([[1.0, 10.0, 100.0]], dtype=np.float32)
+    ranges = sorted((lo, hi) for _, lo, hi, _ in res)
+    assert ranges[0][0] == 0 and ranges[-1][1] == n_items and ranges[0][1] == ranges[1][0]
+    for _, _, _, out in res:
+        assert np.array_equal(out, expect)
