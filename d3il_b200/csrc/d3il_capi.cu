@@ -47,13 +47,14 @@ struct DevCtx {
   int row, n, ws_stride;
   DevIk ik;
   float* traj;            // [ticks][21][n]
+  int* ik_flags;          // [n_ik_blocks] ticks published by each k_ik block (monotonic: launch_id * 64 + tick + 1)
   float tol; int max_iter;
 };
 
 struct d3il_env {
   Model m; Lay L;
   DevCtx d;
-  int device, n, max_ticks;
+  int device, n, max_ticks, n_ik_blocks, launch_id;
   long long launches;
   size_t smem_bytes;
   // pinned + device staging for the *_host calls
@@ -71,12 +72,17 @@ __device__ __forceinline__ void stage_model(Model* sm, const Model* gm) {
 
 // IK reference generator: one thread per env (a5/a6).  mode: 1 = take the set-point from `action` (env step),
 // 0 = keep the stored set-point (d3il_substep).  In joint-PD mode (after reset) the held set-point is replicated.
-__global__ void __launch_bounds__(128) k_ik(DevCtx c, const float* __restrict__ action, int n_ticks, int use_action) {
+__global__ void __launch_bounds__(128) k_ik(DevCtx c, const float* __restrict__ action, int n_ticks, int use_action, int flag_base) {
+  // Programmatic dependent launch: let the env-step kernel (next in the stream) start while this one is still running.
+  // It consumes our set-points tick by tick through the release flags below; we never wait on anything, and we are
+  // already resident when it is allowed to launch, so the hand-off cannot deadlock.
+  asm volatile("griddepcontrol.launch_dependents;");
   __shared__ tab_t sctrl[D3_CTRL_W];
   for (int i = threadIdx.x; i < D3_CTRL_W; i += blockDim.x) sctrl[i] = c.model->ctrl[i];
   __syncthreads();
-  int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= c.n) return;
+  const int e_raw = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = e_raw < c.n;               // threads past the batch shadow the last env (they must reach the barriers)
+  const int e = live ? e_raw : c.n - 1;
   const int n = c.n;
   const float* row = c.state + (size_t)e * c.row;
   IkState s;
@@ -88,7 +94,7 @@ __global__ void __launch_bounds__(128) k_ik(DevCtx c, const float* __restrict__ 
     float nq = rsqrtf(a[3] * a[3] + a[4] * a[4] + a[5] * a[5] + a[6] * a[6]);
     s.des_pos[0] = a[0]; s.des_pos[1] = a[1]; s.des_pos[2] = a[2];
     for (int k = 0; k < 4; k++) s.des_quat[k] = a[3 + k] * nq;
-    for (int k = 0; k < 7; k++) c.ik.des[k * n + e] = k < 3 ? s.des_pos[k] : s.des_quat[k - 3];
+    if (live) for (int k = 0; k < 7; k++) c.ik.des[k * n + e] = k < 3 ? s.des_pos[k] : s.des_quat[k - 3];
   } else {
     for (int k = 0; k < 3; k++) s.des_pos[k] = c.ik.des[k * n + e];
     for (int k = 0; k < 4; k++) s.des_quat[k] = c.ik.des[(3 + k) * n + e];
@@ -100,16 +106,24 @@ __global__ void __launch_bounds__(128) k_ik(DevCtx c, const float* __restrict__ 
   double V[36]; int vwarm = 0;              // eigenbasis carried across the IK iterations of this launch
   for (int t = 0; t < n_ticks; t++) {
     if (cart) ik_tick(sctrl, s, V, &vwarm);
-    float* tr = c.traj + (size_t)t * 21 * n + e;
-    for (int k = 0; k < 7; k++) { tr[k * n] = s.jt_q[k]; tr[(7 + k) * n] = s.jt_qlo[k]; tr[(14 + k) * n] = s.jt_qd[k]; }
+    if (live) {
+      float* tr = c.traj + (size_t)t * 21 * n + e;
+      for (int k = 0; k < 7; k++) { tr[k * n] = s.jt_q[k]; tr[(7 + k) * n] = s.jt_qlo[k]; tr[(14 + k) * n] = s.jt_qd[k]; }
+    }
+    // publish tick t of this block's 128 envs
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) *(volatile int*)(c.ik_flags + blockIdx.x) = flag_base + t + 1;
   }
-  for (int k = 0; k < 7; k++) { c.ik.q[k * n + e] = s.q[k]; c.ik.jt[k * n + e] = s.jt_q[k]; c.ik.jt[(7 + k) * n + e] = s.jt_qlo[k]; c.ik.jt[(14 + k) * n + e] = s.jt_qd[k]; }
-  c.ik.valid[e] = s.valid;
+  if (live) {
+    for (int k = 0; k < 7; k++) { c.ik.q[k * n + e] = s.q[k]; c.ik.jt[k * n + e] = s.jt_q[k]; c.ik.jt[(7 + k) * n + e] = s.jt_qlo[k]; c.ik.jt[(14 + k) * n + e] = s.jt_qd[k]; }
+    c.ik.valid[e] = s.valid;
+  }
 }
 
 // Env step: one warp per env.  gym = 1: GymEnvWrapper.step semantics around the ticks; gym = 0: bare ticks (substep).
 __global__ void __launch_bounds__(CTA_THREADS, (CTA_THREADS > 256 ? 1 : 2))
-k_env(DevCtx c, int n_ticks, int gym, float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ done, float* __restrict__ info) {
+k_env(DevCtx c, int n_ticks, int gym, int flag_base, float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ done, float* __restrict__ info) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Model* sm = (Model*)smem_raw;
   stage_model(sm, c.model);
@@ -122,14 +136,24 @@ k_env(DevCtx c, int n_ticks, int gym, float* __restrict__ obs, float* __restrict
   // every thread of the CTA reaches the phase barriers inside physics_tick.
   const int e_raw = blockIdx.x * ENVS_PER_CTA + warp;
   const int e = e_raw < c.n ? e_raw : c.n - 1;
+  // k_ik blocks (128 envs each) that feed this CTA's contiguous env range
+  const int e_first = blockIdx.x * ENVS_PER_CTA, e_last = min(e_first + ENVS_PER_CTA - 1, c.n - 1);
+  const int ikb0 = e_first / 128, ikb1 = e_last / 128;
   float* w = (float*)(smem_raw + ((sizeof(Model) + 127) & ~(size_t)127)) + (size_t)warp * c.ws_stride;
   float* row = c.state + (size_t)e * c.row;
   for (int i = cx.lane; i < L.n_state; i += G_LANES) w[i] = row[i];
   __syncwarp(cx.mask);
   if (gym) env_prestep<G_LANES>(cx, m, L, w, obs + (size_t)e * m.obs_dim, reward + e, done + e);
   for (int t = 0; t < n_ticks; t++) {
+    // acquire tick t of the IK reference (k_ik may still be running: programmatic dependent launch)
+    if (threadIdx.x == 0) {
+      const int want = flag_base + t + 1;
+      for (int b = ikb0; b <= ikb1; b++) while (*(volatile int*)(c.ik_flags + b) < want) __nanosleep(100);
+      __threadfence();
+    }
+    __syncthreads();
     const float* tr = c.traj + (size_t)t * 21 * c.n + e;
-    for (int k = cx.lane; k < 21; k += G_LANES) w[L.jt + k] = tr[(size_t)k * c.n];
+    for (int k = cx.lane; k < 21; k += G_LANES) w[L.jt + k] = __ldcg(tr + (size_t)k * c.n);
     __syncwarp(cx.mask);
     physics_tick<G_LANES, true>(cx, m, L, w, w + L.jt, w + L.jt + 7, w + L.jt + 14, c.tol, c.max_iter);
   }
@@ -203,6 +227,9 @@ extern "C" int d3il_create(d3il_env** out, const void* blob, size_t nbytes, int 
   CK(cudaMemset(d.ik.jt, 0, (size_t)21 * n_envs * sizeof(float)));
   CK(cudaMemset(d.ik.valid, 0, (size_t)n_envs * sizeof(int)));
   CK(cudaMalloc(&d.traj, (size_t)h->max_ticks * 21 * n_envs * sizeof(float)));
+  h->n_ik_blocks = (n_envs + 127) / 128; h->launch_id = 0;
+  CK(cudaMalloc(&d.ik_flags, (size_t)h->n_ik_blocks * sizeof(int)));
+  CK(cudaMemset(d.ik_flags, 0, (size_t)h->n_ik_blocks * sizeof(int)));
   h->smem_bytes = ((sizeof(Model) + 127) & ~(size_t)127) + (size_t)ENVS_PER_CTA * d.ws_stride * sizeof(float);
   if (h->smem_bytes > 227 * 1024) { g_err = "d3il_create: scene workspace does not fit in shared memory"; delete h; return -1; }
   CK(cudaFuncSetAttribute(k_env, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
@@ -228,7 +255,7 @@ extern "C" void d3il_destroy(d3il_env* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaFree((void*)h->d.model); cudaFree(h->d.state); cudaFree(h->d.ik.q); cudaFree(h->d.ik.des); cudaFree(h->d.ik.jt); cudaFree(h->d.ik.valid);
-  cudaFree(h->d.traj); cudaFreeHost(h->h_in); cudaFreeHost(h->h_out); cudaFreeHost(h->h_mask); cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_mask);
+  cudaFree(h->d.traj); cudaFree(h->d.ik_flags); cudaFreeHost(h->h_in); cudaFreeHost(h->h_out); cudaFreeHost(h->h_mask); cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_mask);
   cudaStreamDestroy(h->own_stream);
   delete h;
 }
@@ -259,6 +286,22 @@ extern "C" int d3il_get_profile(const d3il_env* h, double out_ms[2], long long* 
 
 static inline int env_grid(const d3il_env* h) { return (h->n + ENVS_PER_CTA - 1) / ENVS_PER_CTA; }
 
+// IK reference + env step: two launches on one stream, the second with programmatic stream serialization so that it
+// overlaps the first (per-tick hand-off through ik_flags).  If the driver serialises them anyway the result is the same.
+static cudaError_t launch_step(d3il_env* h, cudaStream_t s, const float* action, int n_ticks, int gym, float* obs, float* reward, uint8_t* done, float* info) {
+  h->launch_id = (h->launch_id + 1) & 0xffffff;
+  const int base = h->launch_id * 64;
+  k_ik<<<h->n_ik_blocks, 128, 0, s>>>(h->d, action, n_ticks, gym, base);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(env_grid(h)); cfg.blockDim = dim3(CTA_THREADS); cfg.dynamicSmemBytes = h->smem_bytes; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  h->launches += 2;
+  return cudaLaunchKernelEx(&cfg, k_env, h->d, n_ticks, gym, base, obs, reward, done, info);
+}
+
 extern "C" int d3il_reset(d3il_env* h, const float* ctx, const uint8_t* mask, float* obs, void* stream) {
   if (!h) { g_err = "d3il_reset: null handle"; return -1; }
   if (h->m.ctx_dim > 0 && !ctx) { g_err = "d3il_reset: this scene needs a context per env"; return -1; }
@@ -274,10 +317,8 @@ extern "C" int d3il_step(d3il_env* h, const float* action, float* obs, float* re
   CK(cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;
   if (h->profiling) CK(cudaEventRecord(h->ev[0], s));
-  k_ik<<<(h->n + 127) / 128, 128, 0, s>>>(h->d, action, h->m.n_substeps, 1);
   if (h->profiling) CK(cudaEventRecord(h->ev[1], s));
-  k_env<<<env_grid(h), CTA_THREADS, h->smem_bytes, s>>>(h->d, h->m.n_substeps, 1, obs, reward, done, info);
-  h->launches += 2;
+  CK(launch_step(h, s, action, h->m.n_substeps, 1, obs, reward, done, info));
   CK(cudaGetLastError());
   if (h->profiling) {
     // per-kernel device time on the launching stream (bench.py roofline); synchronises, so only for profiling passes
@@ -297,9 +338,7 @@ extern "C" int d3il_substep(d3il_env* h, int n, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   while (n > 0) {
     int k = n < h->max_ticks ? n : h->max_ticks;
-    k_ik<<<(h->n + 127) / 128, 128, 0, s>>>(h->d, nullptr, k, 0);
-    k_env<<<env_grid(h), CTA_THREADS, h->smem_bytes, s>>>(h->d, k, 0, nullptr, nullptr, nullptr, nullptr);
-    h->launches += 2;
+    CK(launch_step(h, s, nullptr, k, 0, nullptr, nullptr, nullptr, nullptr));
     n -= k;
   }
   CK(cudaGetLastError());
