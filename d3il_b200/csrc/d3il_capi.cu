@@ -72,7 +72,8 @@ __device__ __forceinline__ void stage_model(Model* sm, const Model* gm) {
 
 // IK reference generator: one thread per env (a5/a6).  mode: 1 = take the set-point from `action` (env step),
 // 0 = keep the stored set-point (d3il_substep).  In joint-PD mode (after reset) the held set-point is replicated.
-__global__ void __launch_bounds__(128) k_ik(DevCtx c, const float* __restrict__ action, int n_ticks, int use_action, int flag_base) {
+#define IK_THREADS 32    // one warp per k_ik block: 255 regs x 32 threads = 8 K registers, fits beside two resident k_env CTAs
+__global__ void __launch_bounds__(IK_THREADS) k_ik(DevCtx c, const float* __restrict__ action, int n_ticks, int use_action, int flag_base) {
   // Programmatic dependent launch: let the env-step kernel (next in the stream) start while this one is still running.
   // It consumes our set-points tick by tick through the release flags below; we never wait on anything, and we are
   // already resident when it is allowed to launch, so the hand-off cannot deadlock.
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(128) k_ik(DevCtx c, const float* __restrict__ 
       float* tr = c.traj + (size_t)t * 21 * n + e;
       for (int k = 0; k < 7; k++) { tr[k * n] = s.jt_q[k]; tr[(7 + k) * n] = s.jt_qlo[k]; tr[(14 + k) * n] = s.jt_qd[k]; }
     }
-    // publish tick t of this block's 128 envs
+    // publish tick t of this block's envs
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) *(volatile int*)(c.ik_flags + blockIdx.x) = flag_base + t + 1;
@@ -136,9 +137,9 @@ k_env(DevCtx c, int n_ticks, int gym, int flag_base, float* __restrict__ obs, fl
   // every thread of the CTA reaches the phase barriers inside physics_tick.
   const int e_raw = blockIdx.x * ENVS_PER_CTA + warp;
   const int e = e_raw < c.n ? e_raw : c.n - 1;
-  // k_ik blocks (128 envs each) that feed this CTA's contiguous env range
+  // k_ik blocks (IK_THREADS envs each) that feed this CTA's contiguous env range
   const int e_first = blockIdx.x * ENVS_PER_CTA, e_last = min(e_first + ENVS_PER_CTA - 1, c.n - 1);
-  const int ikb0 = e_first / 128, ikb1 = e_last / 128;
+  const int ikb0 = e_first / IK_THREADS, ikb1 = e_last / IK_THREADS;
   float* w = (float*)(smem_raw + ((sizeof(Model) + 127) & ~(size_t)127)) + (size_t)warp * c.ws_stride;
   float* row = c.state + (size_t)e * c.row;
   for (int i = cx.lane; i < L.n_state; i += G_LANES) w[i] = row[i];
@@ -146,11 +147,13 @@ k_env(DevCtx c, int n_ticks, int gym, int flag_base, float* __restrict__ obs, fl
   if (gym) env_prestep<G_LANES>(cx, m, L, w, obs + (size_t)e * m.obs_dim, reward + e, done + e);
   for (int t = 0; t < n_ticks; t++) {
     // acquire tick t of the IK reference (k_ik may still be running: programmatic dependent launch)
+    PHASE_T0();
     if (threadIdx.x == 0) {
       const int want = flag_base + t + 1;
       for (int b = ikb0; b <= ikb1; b++) while (*(volatile int*)(c.ik_flags + b) < want) __nanosleep(100);
       __threadfence();
     }
+    PHASE(16);
     __syncthreads();
     const float* tr = c.traj + (size_t)t * 21 * c.n + e;
     for (int k = cx.lane; k < 21; k += G_LANES) w[L.jt + k] = __ldcg(tr + (size_t)k * c.n);
@@ -227,7 +230,7 @@ extern "C" int d3il_create(d3il_env** out, const void* blob, size_t nbytes, int 
   CK(cudaMemset(d.ik.jt, 0, (size_t)21 * n_envs * sizeof(float)));
   CK(cudaMemset(d.ik.valid, 0, (size_t)n_envs * sizeof(int)));
   CK(cudaMalloc(&d.traj, (size_t)h->max_ticks * 21 * n_envs * sizeof(float)));
-  h->n_ik_blocks = (n_envs + 127) / 128; h->launch_id = 0;
+  h->n_ik_blocks = (n_envs + IK_THREADS - 1) / IK_THREADS; h->launch_id = 0;
   CK(cudaMalloc(&d.ik_flags, (size_t)h->n_ik_blocks * sizeof(int)));
   CK(cudaMemset(d.ik_flags, 0, (size_t)h->n_ik_blocks * sizeof(int)));
   h->smem_bytes = ((sizeof(Model) + 127) & ~(size_t)127) + (size_t)ENVS_PER_CTA * d.ws_stride * sizeof(float);
@@ -291,7 +294,7 @@ static inline int env_grid(const d3il_env* h) { return (h->n + ENVS_PER_CTA - 1)
 static cudaError_t launch_step(d3il_env* h, cudaStream_t s, const float* action, int n_ticks, int gym, float* obs, float* reward, uint8_t* done, float* info) {
   h->launch_id = (h->launch_id + 1) & 0xffffff;
   const int base = h->launch_id * 64;
-  k_ik<<<h->n_ik_blocks, 128, 0, s>>>(h->d, action, n_ticks, gym, base);
+  k_ik<<<h->n_ik_blocks, IK_THREADS, 0, s>>>(h->d, action, n_ticks, gym, base);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(env_grid(h)); cfg.blockDim = dim3(CTA_THREADS); cfg.dynamicSmemBytes = h->smem_bytes; cfg.stream = s;
   cudaLaunchAttribute attr[1];

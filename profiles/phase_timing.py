@@ -18,7 +18,7 @@ torch.cuda.synchronize()
 out = (C.c_ulonglong * 24)()
 lib.lib().d3il_debug_phase_cycles(out)
 names = {0: "ctrl+kinematics+tcp", 1: "dynamics", 2: "collision", 3: "make_constraints", 4: "chol(M)+solve", 5: "newton total", 6: "euler+integrate",
-         15: "newton: loop top", 8: "newton: jar+eval+grad", 9: "newton: H assembly", 10: "newton: chol(H)", 11: "newton: solve", 12: "newton: line search"}
+         15: "newton: loop top", 16: "wait for IK tick (thread 0)", 8: "newton: jar+eval+grad", 9: "newton: H assembly", 10: "newton: chol(H)", 11: "newton: solve", 12: "newton: line search"}
 ticks = steps * 35 + 1
 tot = sum(out[k] for k in range(7))
 for k in sorted(names):
