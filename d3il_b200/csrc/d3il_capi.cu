@@ -64,6 +64,16 @@ struct d3il_env {
 };
 
 // ------------------------------------------------------------------------------------------------ kernels
+#ifdef D3IL_PHASE_TIMING
+__device__ unsigned long long g_tl[4 * 4096];     // debug timeline: per block [t0, t1, smid, kind]
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned smid() { unsigned r; asm volatile("mov.u32 %0, %smid;" : "=r"(r)); return r; }
+#define TL_BEGIN(kind, idx) unsigned long long tl_t0 = gtime(); const int tl_i = (idx)
+#define TL_END(kind) do { if (threadIdx.x == 0 && tl_i < 4096) { g_tl[4 * tl_i] = tl_t0; g_tl[4 * tl_i + 1] = gtime(); g_tl[4 * tl_i + 2] = smid(); g_tl[4 * tl_i + 3] = kind; } } while (0)
+#else
+#define TL_BEGIN(kind, idx) ((void)0)
+#define TL_END(kind) ((void)0)
+#endif
 __device__ __forceinline__ void stage_model(Model* sm, const Model* gm) {
   const int* src = (const int*)gm; int* dst = (int*)sm;
   for (int i = threadIdx.x; i < (int)(sizeof(Model) / 4); i += blockDim.x) dst[i] = src[i];
@@ -78,6 +88,7 @@ __global__ void __launch_bounds__(IK_THREADS) k_ik(DevCtx c, const float* __rest
   // It consumes our set-points tick by tick through the release flags below; we never wait on anything, and we are
   // already resident when it is allowed to launch, so the hand-off cannot deadlock.
   asm volatile("griddepcontrol.launch_dependents;");
+  TL_BEGIN(1, 2048 + blockIdx.x);
   __shared__ tab_t sctrl[D3_CTRL_W];
   for (int i = threadIdx.x; i < D3_CTRL_W; i += blockDim.x) sctrl[i] = c.model->ctrl[i];
   __syncthreads();
@@ -104,9 +115,9 @@ __global__ void __launch_bounds__(IK_THREADS) k_ik(DevCtx c, const float* __rest
     for (int k = 0; k < 7; k++) s.q[k] = (double)row[c.lay.qpos + k] + (double)row[c.lay.qlo + k];
     s.valid = 1;
   }
-  double V[36]; int vwarm = 0;              // eigenbasis carried across the IK iterations of this launch
+  double V[36], sn[7], cs[7]; int vwarm = 0;   // eigenbasis and joint sines/cosines carried across the IK iterations of this launch
   for (int t = 0; t < n_ticks; t++) {
-    if (cart) ik_tick(sctrl, s, V, &vwarm);
+    if (cart) ik_tick(sctrl, s, V, &vwarm, sn, cs);
     if (live) {
       float* tr = c.traj + (size_t)t * 21 * n + e;
       for (int k = 0; k < 7; k++) { tr[k * n] = s.jt_q[k]; tr[(7 + k) * n] = s.jt_qlo[k]; tr[(14 + k) * n] = s.jt_qd[k]; }
@@ -120,12 +131,14 @@ __global__ void __launch_bounds__(IK_THREADS) k_ik(DevCtx c, const float* __rest
     for (int k = 0; k < 7; k++) { c.ik.q[k * n + e] = s.q[k]; c.ik.jt[k * n + e] = s.jt_q[k]; c.ik.jt[(7 + k) * n + e] = s.jt_qlo[k]; c.ik.jt[(14 + k) * n + e] = s.jt_qd[k]; }
     c.ik.valid[e] = s.valid;
   }
+  TL_END(1);
 }
 
 // Env step: one warp per env.  gym = 1: GymEnvWrapper.step semantics around the ticks; gym = 0: bare ticks (substep).
 __global__ void __launch_bounds__(CTA_THREADS, (CTA_THREADS > 256 ? 1 : 2))
 k_env(DevCtx c, int n_ticks, int gym, int flag_base, float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ done, float* __restrict__ info) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  TL_BEGIN(2, blockIdx.x);
   Model* sm = (Model*)smem_raw;
   stage_model(sm, c.model);
   const Model& m = *sm;
@@ -162,6 +175,7 @@ k_env(DevCtx c, int n_ticks, int gym, int flag_base, float* __restrict__ obs, fl
   }
   if (gym) env_poststep<G_LANES>(cx, m, L, w, info + (size_t)e * m.info_dim);
   if (e_raw < c.n) for (int i = cx.lane; i < L.n_state; i += G_LANES) row[i] = w[i];
+  TL_END(2);
 }
 
 __global__ void __launch_bounds__(CTA_THREADS, (CTA_THREADS > 256 ? 1 : 2))
@@ -237,6 +251,12 @@ extern "C" int d3il_create(d3il_env** out, const void* blob, size_t nbytes, int 
   if (h->smem_bytes > 227 * 1024) { g_err = "d3il_create: scene workspace does not fit in shared memory"; delete h; return -1; }
   CK(cudaFuncSetAttribute(k_env, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
   CK(cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  // k_ik needs almost no shared memory, but an SM keeps the L1/shared carve-out of whatever is resident: ask for the
+  // maximum shared carve-out everywhere so k_env CTAs can join SMs that still run a k_ik block (measured: without this
+  // 128 of 148 SMs refused k_env CTAs until their k_ik block had exited).
+  CK(cudaFuncSetAttribute(k_ik, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CK(cudaFuncSetAttribute(k_env, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CK(cudaFuncSetAttribute(k_reset, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   // staging for the host-buffer entry points
   const Model& m = h->m;
   h->in_floats = (size_t)n_envs * (m.act_dim > m.ctx_dim ? m.act_dim : m.ctx_dim);
@@ -463,6 +483,7 @@ extern "C" int d3il_set_state(d3il_env* h, const double* in, int e) {
 }
 
 #ifdef D3IL_PHASE_TIMING
+extern "C" int d3il_debug_timeline(unsigned long long* out) { return cudaMemcpyFromSymbol(out, g_tl, sizeof(unsigned long long) * 4 * 4096) == cudaSuccess ? 0 : -2; }
 extern "C" int d3il_debug_phase_cycles(unsigned long long* out24) {
   return cudaMemcpyFromSymbol(out24, g_phase_cycles, sizeof(unsigned long long) * 24) == cudaSuccess ? 0 : -2;
 }

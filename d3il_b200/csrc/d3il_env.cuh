@@ -43,9 +43,16 @@ DEVFN void ik_mat2quat(ikr* q, const ikr* R) {
   ikr n = 1 / sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
   q[0] *= n; q[1] *= n; q[2] *= n; q[3] *= n;
 }
+DEVFN ikr ik_rsqrt(ikr x) {
+#ifdef __CUDA_ARCH__
+  return rsqrt(x);
+#else
+  return 1.0 / sqrt(x);
+#endif
+}
 DEVFN ikr ik_clamp(ikr x, ikr lo, ikr hi) { return x < lo ? lo : (x > hi ? hi : x); }
 
-DEVFN void ik_fk(const tab_t* C, const ikr* q, ikr* pos, ikr* quat, ikr* J) {
+DEVFN void ik_fk(const tab_t* C, const ikr* sn, const ikr* cs, ikr* pos, ikr* quat, ikr* J) {
   ikr p[3] = {0, 0, 0}, R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, org[7][3], axs[7][3];
   for (int i = 0; i < 7; i++) {
     const tab_t* o = C + D3C_IK_ORIGIN + 12 * i;
@@ -53,7 +60,7 @@ DEVFN void ik_fk(const tab_t* C, const ikr* q, ikr* pos, ikr* quat, ikr* J) {
     for (int k = 0; k < 9; k++) oR[k] = o[3 + k];
     ik_mat_vec3(t, R, ov); p[0] += t[0]; p[1] += t[1]; p[2] += t[2];
     ik_mat_mul3(R, R, oR);
-    ikr c = cos(q[i]), s = sin(q[i]), Rz[9] = {c, -s, 0, s, c, 0, 0, 0, 1};
+    ikr c = cs[i], s = sn[i], Rz[9] = {c, -s, 0, s, c, 0, 0, 0, 1};
     ik_mat_mul3(R, R, Rz);
     org[i][0] = p[0]; org[i][1] = p[1]; org[i][2] = p[2];
     axs[i][0] = R[2]; axs[i][1] = R[5]; axs[i][2] = R[8];
@@ -82,19 +89,37 @@ DEVFN void jacobi6(ikr* A, ikr* wv, ikr* V, int warm) {
   } else {
     for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) V[i * 6 + j] = (i == j) ? 1.0 : 0.0;
   }
+  // Round-robin (tournament) ordering: 5 rounds of 3 rotations on disjoint index pairs.  The three rotations of a
+  // round are independent instruction streams, which is what a single fp64 thread needs to hide pipe latency.
+  const int PP[5][3] = {{0, 2, 3}, {0, 1, 4}, {0, 2, 1}, {0, 3, 1}, {0, 1, 2}};
+  const int QQ[5][3] = {{1, 5, 4}, {2, 3, 5}, {3, 4, 5}, {4, 5, 2}, {5, 4, 3}};
   for (int sweep = 0; sweep < 30; sweep++) {
     ikr off = 0, diag = 0;
     for (int i = 0; i < 6; i++) { diag += A[i * 6 + i] * A[i * 6 + i]; for (int j = i + 1; j < 6; j++) off += A[i * 6 + j] * A[i * 6 + j]; }
-    if (off <= 1e-28 * diag) break;
-    for (int p = 0; p < 5; p++) for (int q = p + 1; q < 6; q++) {
-      ikr apq = A[p * 6 + q];
-      if (apq == 0) continue;
-      ikr theta = (A[q * 6 + q] - A[p * 6 + p]) / (2 * apq);
-      ikr t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1));
-      ikr c = 1 / sqrt(t * t + 1), s = t * c;
-      for (int k = 0; k < 6; k++) { ikr akp = A[k * 6 + p], akq = A[k * 6 + q]; A[k * 6 + p] = c * akp - s * akq; A[k * 6 + q] = s * akp + c * akq; }
-      for (int k = 0; k < 6; k++) { ikr apk = A[p * 6 + k], aqk = A[q * 6 + k]; A[p * 6 + k] = c * apk - s * aqk; A[q * 6 + k] = s * apk + c * aqk; }
-      for (int k = 0; k < 6; k++) { ikr vkp = V[k * 6 + p], vkq = V[k * 6 + q]; V[k * 6 + p] = c * vkp - s * vkq; V[k * 6 + q] = s * vkp + c * vkq; }
+    if (off <= 1e-26 * diag) break;
+    for (int rd = 0; rd < 5; rd++) {
+      ikr cc[3], ss[3];
+      for (int u = 0; u < 3; u++) {
+        int p = PP[rd][u], q = QQ[rd][u];
+        ikr apq = A[p * 6 + q], d = A[q * 6 + q] - A[p * 6 + p];
+        // tan of the rotation angle: t = sign(d) * 2 apq / (|d| + sqrt(d^2 + 4 apq^2)); any t gives an orthogonal rotation
+        // (c, s) = (1, t) / sqrt(1 + t^2), so the angle only needs to be good enough for the quadratic convergence
+        ikr t = 0;
+        if (apq != 0) { ikr h = sqrt(d * d + 4 * apq * apq); t = 2 * apq / (d >= 0 ? d + h : d - h); }
+        ikr c = ik_rsqrt(1 + t * t);
+        cc[u] = c; ss[u] = t * c;
+      }
+      for (int u = 0; u < 3; u++) {
+        int p = PP[rd][u], q = QQ[rd][u];
+        ikr c = cc[u], s = ss[u];
+        for (int k = 0; k < 6; k++) { ikr akp = A[k * 6 + p], akq = A[k * 6 + q]; A[k * 6 + p] = c * akp - s * akq; A[k * 6 + q] = s * akp + c * akq; }
+        for (int k = 0; k < 6; k++) { ikr vkp = V[k * 6 + p], vkq = V[k * 6 + q]; V[k * 6 + p] = c * vkp - s * vkq; V[k * 6 + q] = s * vkp + c * vkq; }
+      }
+      for (int u = 0; u < 3; u++) {
+        int p = PP[rd][u], q = QQ[rd][u];
+        ikr c = cc[u], s = ss[u];
+        for (int k = 0; k < 6; k++) { ikr apk = A[p * 6 + k], aqk = A[q * 6 + k]; A[p * 6 + k] = c * apk - s * aqk; A[q * 6 + k] = s * apk + c * aqk; }
+      }
     }
   }
   for (int i = 0; i < 6; i++) wv[i] = A[i * 6 + i];
@@ -102,13 +127,14 @@ DEVFN void jacobi6(ikr* A, ikr* wv, ikr* V, int warm) {
 
 // One getControl() call of CartPosQuatImpedenceController: num_iter damped-least-squares iterations on the open-loop
 // joint reference; outputs the joint PD set-point (q_des as two floats, qd_des) for this physics tick.
-DEVFN void ik_tick(const tab_t* C, IkState& s, ikr* V, int* vwarm) {
+DEVFN void ik_tick(const tab_t* C, IkState& s, ikr* V, int* vwarm, ikr* sn, ikr* cs) {
   ikr q[7], des_quat[4] = {(ikr)s.des_quat[0], (ikr)s.des_quat[1], (ikr)s.des_quat[2], (ikr)s.des_quat[3]};
   for (int k = 0; k < 7; k++) q[k] = s.q[k];
+  if (!*vwarm) for (int k = 0; k < 7; k++) { sn[k] = sin(q[k]); cs[k] = cos(q[k]); }      // exact once per launch
   const int niter = (int)C[D3C_NUM_ITER];
   for (int it = 0; it < niter; it++) {
     ikr pos[3], cq[4], J[42];
-    ik_fk(C, q, pos, cq, J);
+    ik_fk(C, sn, cs, pos, cq, J);
     ikr dm = 0, dp = 0;
     for (int k = 0; k < 4; k++) { dm += (cq[k] - des_quat[k]) * (cq[k] - des_quat[k]); dp += (cq[k] + des_quat[k]) * (cq[k] + des_quat[k]); }
     if (dm > dp) for (int k = 0; k < 4; k++) des_quat[k] = -des_quat[k];
@@ -138,7 +164,17 @@ DEVFN void ik_tick(const tab_t* C, IkState& s, ikr* V, int* vwarm) {
     for (int k = 0; k < 7; k++) { ikr sum = qd_null[k]; for (int r = 0; r < 6; r++) sum += J[r * 7 + k] * x[r]; qd[k] = sum; nrm += sum * sum; }
     nrm = sqrt(nrm);
     if (nrm > 3) for (int k = 0; k < 7; k++) qd[k] *= 3 / nrm;
-    for (int k = 0; k < 7; k++) q[k] = ik_clamp(q[k] + (ikr)C[D3C_LRATE] * qd[k], (ikr)C[D3C_JMIN + k], (ikr)C[D3C_JMAX + k]);
+    for (int k = 0; k < 7; k++) {
+      ikr qn = ik_clamp(q[k] + (ikr)C[D3C_LRATE] * qd[k], (ikr)C[D3C_JMIN + k], (ikr)C[D3C_JMAX + k]);
+      // sin/cos by the angle-addition formulas with a short series in the increment (|dq| <= 3e-3: the dq^6 term is
+      // 1e-18), then one Newton step back onto the unit circle: 1e-16 per update instead of a software sincos
+      ikr dq = qn - q[k], d2 = dq * dq;
+      ikr sd = dq * (1 - d2 * (1.0 / 6.0) * (1 - d2 * 0.05)), cd = 1 - d2 * 0.5 * (1 - d2 * (1.0 / 12.0));
+      ikr s1 = sn[k] * cd + cs[k] * sd, c1 = cs[k] * cd - sn[k] * sd;
+      ikr nrm = 1.5 - 0.5 * (s1 * s1 + c1 * c1);
+      sn[k] = s1 * nrm; cs[k] = c1 * nrm;
+      q[k] = qn;
+    }
   }
   for (int k = 0; k < 7; k++) {
     s.jt_q[k] = (real)q[k];

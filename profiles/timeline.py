@@ -1,0 +1,30 @@
+"""Debug: block-level timeline of one env step (k_ik blocks + k_env CTAs), from %globaltimer (timing build only)."""
+import ctypes as C, os, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from d3il_b200.batched_env import BatchedEnv
+from d3il_b200 import lib
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+ctxs = np.load(os.path.join(os.path.dirname(__file__), "..", "d3il_b200", "data", "pushing_test_contexts.npy"))
+env = BatchedEnv("pushing", n, 0)
+env.reset(torch.tensor(ctxs[np.arange(n) % 60], dtype=torch.float32, device="cuda"))
+des = torch.cat([env.robot_state().clone(), torch.tensor([0.0, 1.0, 0.0, 0.0], device="cuda").repeat(n, 1)], 1)
+for k in range(40):
+    des[:, :2] += 0.001
+    env.step(des)
+torch.cuda.synchronize()
+buf = (C.c_ulonglong * (4 * 4096))()
+lib.lib().d3il_debug_timeline(buf)
+a = np.array(buf, dtype=np.uint64).reshape(4096, 4).astype(np.int64)
+env_b = a[(a[:, 3] == 2)]; ik_b = a[(a[:, 3] == 1)]
+t0 = min(env_b[:, 0].min(), ik_b[:, 0].min())
+print(f"k_ik blocks {len(ik_b)}: start {(ik_b[:,0].min()-t0)/1e6:.3f}..{(ik_b[:,0].max()-t0)/1e6:.3f} ms, end {(ik_b[:,1].min()-t0)/1e6:.3f}..{(ik_b[:,1].max()-t0)/1e6:.3f} ms")
+print(f"k_env CTAs {len(env_b)}: start {(env_b[:,0].min()-t0)/1e6:.3f}..{(env_b[:,0].max()-t0)/1e6:.3f} ms, end {(env_b[:,1].min()-t0)/1e6:.3f}..{(env_b[:,1].max()-t0)/1e6:.3f} ms")
+dur = (env_b[:, 1] - env_b[:, 0]) / 1e6
+st = (env_b[:, 0] - t0) / 1e6
+for lo, hi in ((0, 0.5), (0.5, 3), (3, 6), (6, 9), (9, 20)):
+    sel = (st >= lo) & (st < hi)
+    if sel.any():
+        print(f"  CTAs starting in [{lo},{hi}) ms: {sel.sum():4d}  duration mean {dur[sel].mean():.3f} min {dur[sel].min():.3f} max {dur[sel].max():.3f} ms")
+sm_counts = np.bincount(env_b[:, 2].astype(int), minlength=148)
+print("CTAs per SM: min", sm_counts.min(), "max", sm_counts.max(), " SMs hosting k_ik blocks:", len(set(ik_b[:, 2].tolist())))

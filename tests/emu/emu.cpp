@@ -9,7 +9,7 @@
 #include "../../d3il_b200/csrc/d3il_model.h"
 
 struct Emu {
-  Model m; Lay L; IkState ik; double V[36]; int vwarm;
+  Model m; Lay L; IkState ik; double V[36], sn[7], cs[7]; int vwarm;
   std::vector<real> w;
   real tol; int max_iter;
 };
@@ -37,7 +37,7 @@ static void tick(Emu* e) {
   real* w = e->w.data();
   if (w[e->L.misc + ST_CTRL_MODE] != 0) {
     if (!e->ik.valid) { for (int k = 0; k < 7; k++) e->ik.q[k] = (double)w[e->L.qpos + k] + (double)w[e->L.qlo + k]; e->ik.valid = 1; }
-    ik_tick(e->m.ctrl, e->ik, e->V, &e->vwarm);
+    ik_tick(e->m.ctrl, e->ik, e->V, &e->vwarm, e->sn, e->cs);
   }
   physics_tick<1, false>(CX, e->m, e->L, w, e->ik.jt_q, e->ik.jt_qlo, e->ik.jt_qd, e->tol, e->max_iter);
 }
