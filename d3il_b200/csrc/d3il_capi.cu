@@ -11,6 +11,7 @@
 //          k_env (warp per env: Gym pre-step sampling, n_ticks physics ticks, post-step info), k_reset (warp per env).
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <new>
 #include <vector>
@@ -320,7 +321,8 @@ static cudaError_t launch_step(d3il_env* h, cudaStream_t s, const float* action,
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  static const bool no_pdl = getenv("D3IL_NO_PDL") != nullptr;      // diagnosis: serialise the two kernels
+  cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
   h->launches += 2;
   return cudaLaunchKernelEx(&cfg, k_env, h->d, n_ticks, gym, base, obs, reward, done, info);
 }

@@ -99,12 +99,14 @@ __device__ unsigned long long g_phase_cycles[24];
 #define PHASE_T0() long long t_ph = clock64()
 __device__ __forceinline__ bool blockIdx_is0() { return blockIdx.x == 0 && threadIdx.x == 0; }
 __device__ __forceinline__ void count_iter() { g_phase_cycles[20] += 1; }
+__device__ __forceinline__ void count_stat(int k, int v) { atomicAdd(&g_phase_cycles[k], (unsigned long long)v); }
 #define PHASE(k) do { long long t_now = clock64(); if (blockIdx.x == 0 && threadIdx.x == 0) g_phase_cycles[k] += (unsigned long long)(t_now - t_ph); t_ph = t_now; } while (0)
 #else
 #define PHASE_T0() ((void)0)
 #define PHASE(k) ((void)0)
 DEVFN bool blockIdx_is0() { return false; }
 DEVFN void count_iter() {}
+DEVFN void count_stat(int, int) {}
 #endif
 
 // Register-distributed vectors: element i lives in slot i / G of lane i % G.
@@ -177,7 +179,7 @@ struct Lay {
   int xpos, xmat, S, I10, Ic, vel, cj, frc, F, M, mdinv, mpiv, H, hdinv, hpiv, bias, qfrc_smooth, qacc_smooth, qacc, qfrc_c, grad, pvec, Ma, tmpv;
   int act, jt, con, ncon_pair, limflag, cflag, J, aref, D, jar, frcE, Jp, hd, hb, etype, econ, total;
 };
-enum { ST_GRIP_SET = 0, ST_GRASP, ST_CTRL_MODE, ST_STEP, ST_TERM, ST_STATUS, ST_OBST, ST_TASK0, ST_TASK1, ST_TASK2, ST_TASK3, ST_NMISC = 16 };
+enum { ST_GRIP_SET = 0, ST_GRASP, ST_CTRL_MODE, ST_STEP, ST_TERM, ST_STATUS, ST_OBST, ST_TASK0, ST_TASK1, ST_TASK2, ST_TASK3, ST_COST_ITERS /* Newton iterations of the last env step */, ST_COST_COUPLED /* ticks with a tree-coupling contact */, ST_COST_NCON /* max contacts */, ST_NMISC = 16 };
 #define D3_CON_W 24    // per contact: pos3, frame9, dist, incl, mu, dim, g1, g2, pair, row0, dof ranges a0,a1,b0,b1
 
 #define D3_JW 16       // compact Jacobian row: entries of the contact's two dof ranges (<= 9 + 6), padded to 16
@@ -1306,6 +1308,9 @@ DEVFN void physics_tick(const Cx& cx, const Model& m, const Lay& L, real* w, con
   int nlimit = 0, coupled = 0;
   int ne = make_constraints<G>(cx, m, L, w, ncon, &nlimit, &coupled);
   PHASE(3);
+#ifdef D3IL_PHASE_TIMING
+  if (cx.lane == 0) { count_stat(21, coupled); count_stat(22, ncon); count_stat(23, 1); count_stat(19, ne); }
+#endif
   cta_sync<CS>();
   // --- smooth dynamics: qacc_smooth = M^-1 (passive - bias + actuation); M is block diagonal over the trees
   LANES(d, nv) {
@@ -1322,7 +1327,11 @@ DEVFN void physics_tick(const Cx& cx, const Model& m, const Lay& L, real* w, con
   chol_solve_part<G>(cx, w + L.M, nv, m.d_bs, m.d_be, false, m.maxblk, w + L.mdinv, w + L.qacc_smooth);
   PHASE(4);
   cta_sync<CS>();
-  solve_constraints<G, CS>(cx, m, L, w, ne, nlimit, ncon, coupled, tol, max_iter);
+  int iters = solve_constraints<G, CS>(cx, m, L, w, ne, nlimit, ncon, coupled, tol, max_iter);
+  LANES(z, 1) {      // per-env cost counters of the current env step (cost-aware scheduling, diagnostics)
+    w[L.misc + ST_COST_ITERS] += (real)iters; w[L.misc + ST_COST_COUPLED] += (real)coupled;
+    if ((real)ncon > w[L.misc + ST_COST_NCON]) w[L.misc + ST_COST_NCON] = (real)ncon;
+  }
   PHASE(5);
   cta_sync<CS>();
   LANES(d, nv) { w[L.warm + d] = w[L.qacc + d]; w[L.tmpv + d] = w[L.qfrc_smooth + d] + w[L.qfrc_c + d]; }

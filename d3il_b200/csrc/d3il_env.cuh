@@ -91,16 +91,18 @@ DEVFN void jacobi6(ikr* A, ikr* wv, ikr* V, int warm) {
   }
   // Round-robin (tournament) ordering: 5 rounds of 3 rotations on disjoint index pairs.  The three rotations of a
   // round are independent instruction streams, which is what a single fp64 thread needs to hide pipe latency.
-  const int PP[5][3] = {{0, 2, 3}, {0, 1, 4}, {0, 2, 1}, {0, 3, 1}, {0, 1, 2}};
-  const int QQ[5][3] = {{1, 5, 4}, {2, 3, 5}, {3, 4, 5}, {4, 5, 2}, {5, 4, 3}};
+  constexpr int PP[5][3] = {{0, 2, 3}, {0, 1, 4}, {0, 2, 1}, {0, 3, 1}, {0, 1, 2}};
+  constexpr int QQ[5][3] = {{1, 5, 4}, {2, 3, 5}, {3, 4, 5}, {4, 5, 2}, {5, 4, 3}};
   for (int sweep = 0; sweep < 30; sweep++) {
     ikr off = 0, diag = 0;
     for (int i = 0; i < 6; i++) { diag += A[i * 6 + i] * A[i * 6 + i]; for (int j = i + 1; j < 6; j++) off += A[i * 6 + j] * A[i * 6 + j]; }
     if (off <= 1e-26 * diag) break;
+#pragma unroll
     for (int rd = 0; rd < 5; rd++) {
       ikr cc[3], ss[3];
+#pragma unroll
       for (int u = 0; u < 3; u++) {
-        int p = PP[rd][u], q = QQ[rd][u];
+        const int p = PP[rd][u], q = QQ[rd][u];
         ikr apq = A[p * 6 + q], d = A[q * 6 + q] - A[p * 6 + p];
         // tan of the rotation angle: t = sign(d) * 2 apq / (|d| + sqrt(d^2 + 4 apq^2)); any t gives an orthogonal rotation
         // (c, s) = (1, t) / sqrt(1 + t^2), so the angle only needs to be good enough for the quadratic convergence
@@ -109,15 +111,20 @@ DEVFN void jacobi6(ikr* A, ikr* wv, ikr* V, int warm) {
         ikr c = ik_rsqrt(1 + t * t);
         cc[u] = c; ss[u] = t * c;
       }
+#pragma unroll
       for (int u = 0; u < 3; u++) {
-        int p = PP[rd][u], q = QQ[rd][u];
+        const int p = PP[rd][u], q = QQ[rd][u];
         ikr c = cc[u], s = ss[u];
+#pragma unroll
         for (int k = 0; k < 6; k++) { ikr akp = A[k * 6 + p], akq = A[k * 6 + q]; A[k * 6 + p] = c * akp - s * akq; A[k * 6 + q] = s * akp + c * akq; }
+#pragma unroll
         for (int k = 0; k < 6; k++) { ikr vkp = V[k * 6 + p], vkq = V[k * 6 + q]; V[k * 6 + p] = c * vkp - s * vkq; V[k * 6 + q] = s * vkp + c * vkq; }
       }
+#pragma unroll
       for (int u = 0; u < 3; u++) {
-        int p = PP[rd][u], q = QQ[rd][u];
+        const int p = PP[rd][u], q = QQ[rd][u];
         ikr c = cc[u], s = ss[u];
+#pragma unroll
         for (int k = 0; k < 6; k++) { ikr apk = A[p * 6 + k], aqk = A[q * 6 + k]; A[p * 6 + k] = c * apk - s * aqk; A[q * 6 + k] = s * apk + c * aqk; }
       }
     }
@@ -314,6 +321,7 @@ template <int G>
 DEVFN void env_prestep(const Cx& cx, const Model& m, const Lay& L, real* w, float* obs, float* reward, unsigned char* done) {
   LANES(z, 1) {
     w[L.misc + ST_GRIP_SET] = (real)0.04; w[L.misc + ST_GRASP] = 0; w[L.misc + ST_CTRL_MODE] = 1;
+    w[L.misc + ST_COST_ITERS] = 0; w[L.misc + ST_COST_COUPLED] = 0; w[L.misc + ST_COST_NCON] = 0;
     task_obs(m, L, w, obs);
     *reward = (float)task_reward(m, L, w);
     int early = task_early_term(m, L, w);

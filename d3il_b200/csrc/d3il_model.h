@@ -116,7 +116,8 @@ static inline void d3il_pack_state(const Model& m, const Lay& L, const T* w /*wo
   *p++ = ik.valid; *p++ = w[L.misc + ST_CTRL_MODE]; *p++ = w[L.misc + ST_GRIP_SET]; *p++ = w[L.misc + ST_GRASP]; *p++ = w[L.misc + ST_STEP];
   *p++ = w[L.misc + ST_TERM]; *p++ = w[L.misc + ST_STATUS]; *p++ = w[L.misc + ST_OBST];
   for (int k = 0; k < 4; k++) *p++ = w[L.misc + ST_TASK0 + k];
-  for (int k = 0; k < 4; k++) *p++ = 0;
+  for (int k = 0; k < 3; k++) *p++ = w[L.misc + ST_COST_ITERS + k];     // diagnostics only (the oracle keeps zeros here)
+  *p++ = 0;
 }
 template <class T>
 static inline void d3il_unpack_state(const Model& m, const Lay& L, T* w, IkState& ik, const double* in) {

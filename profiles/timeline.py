@@ -9,10 +9,20 @@ ctxs = np.load(os.path.join(os.path.dirname(__file__), "..", "d3il_b200", "data"
 env = BatchedEnv("pushing", n, 0)
 env.reset(torch.tensor(ctxs[np.arange(n) % 60], dtype=torch.float32, device="cuda"))
 des = torch.cat([env.robot_state().clone(), torch.tensor([0.0, 1.0, 0.0, 0.0], device="cuda").repeat(n, 1)], 1)
-for k in range(40):
-    des[:, :2] += 0.001
+nwarm = int(sys.argv[2]) if len(sys.argv) > 2 else 39
+g = torch.Generator(device='cuda').manual_seed(0)
+lo, hi = torch.tensor([0.3, -0.45], device='cuda'), torch.tensor([0.8, 0.45], device='cuda')
+for k in range(nwarm):
+    des[:, :2] = torch.minimum(torch.maximum(des[:, :2] + torch.rand(n, 2, generator=g, device='cuda') * 0.02 - 0.01, lo), hi)
     env.step(des)
 torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); env.step(des); e1.record(); torch.cuda.synchronize()
+print(f'last step by CUDA events: {e0.elapsed_time(e1):.3f} ms')
+e0.record()
+for k in range(10): env.step(des)
+e1.record(); torch.cuda.synchronize()
+print(f'10 more steps: {e0.elapsed_time(e1)/10:.3f} ms per step')
 buf = (C.c_ulonglong * (4 * 4096))()
 lib.lib().d3il_debug_timeline(buf)
 a = np.array(buf, dtype=np.uint64).reshape(4096, 4).astype(np.int64)
@@ -26,5 +36,6 @@ for lo, hi in ((0, 0.5), (0.5, 3), (3, 6), (6, 9), (9, 20)):
     sel = (st >= lo) & (st < hi)
     if sel.any():
         print(f"  CTAs starting in [{lo},{hi}) ms: {sel.sum():4d}  duration mean {dur[sel].mean():.3f} min {dur[sel].min():.3f} max {dur[sel].max():.3f} ms")
+print('CTA duration percentiles (ms): ' + ' '.join(f'p{p}={np.percentile(dur, p):.2f}' for p in (5, 25, 50, 75, 90, 95, 99, 100)))
 sm_counts = np.bincount(env_b[:, 2].astype(int), minlength=148)
 print("CTAs per SM: min", sm_counts.min(), "max", sm_counts.max(), " SMs hosting k_ik blocks:", len(set(ik_b[:, 2].tolist())))

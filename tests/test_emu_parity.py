@@ -20,7 +20,7 @@ def test_core_logic_equals_oracle_fp64(pushing_contexts, ctx_id):
     ctx = pushing_contexts[ctx_id]
     o, e = OracleEnv(blob, sc.header), EmuEnv(blob, sc.header, "f64")
     o.reset(ctx); e.reset(ctx)
-    assert np.abs(o.get_state() - e.get_state()).max() < 1e-6          # contexts pass through float32 on the kernel side
+    assert np.abs(o.get_state()[:-4] - e.get_state()[:-4]).max() < 1e-6     # contexts pass through float32 on the kernel side; last 4 words = kernel-side cost counters
     saw_coupled = False
     for a in scripted_push_actions(ctx, o.robot_state(), n_steps=100):
         e.set_state(o.get_state())
