@@ -49,6 +49,7 @@ struct DevCtx {
   DevIk ik;
   float* traj;            // [ticks][21][n]
   int* ik_flags;          // [n_ik_blocks] ticks published by each k_ik block (monotonic: launch_id * 64 + tick + 1)
+  int* perm;              // [n] env order of this step's k_env groups: most expensive envs (last step's Newton iterations) first
   float tol; int max_iter;
 };
 
@@ -83,6 +84,30 @@ __device__ __forceinline__ void stage_model(Model* sm, const Model* gm) {
 
 // IK reference generator: one thread per env (a5/a6).  mode: 1 = take the set-point from `action` (env step),
 // 0 = keep the stored set-point (d3il_substep).  In joint-PD mode (after reset) the held set-point is replicated.
+// Cost-aware scheduling.  Env steps differ in cost by ~3x (Newton iterations while a box is being pushed or is
+// rocking), CTAs are as slow as their slowest env (CTA-uniform loops, phase barriers) and the kernel as slow as its
+// last CTA.  So each step the envs are bucket-sorted by the Newton iterations of their previous step: expensive envs
+// share CTAs and are dispatched first.  The order only affects scheduling, never results (envs are independent).
+__global__ void __launch_bounds__(1024) k_sched(DevCtx c) {
+  __shared__ int hist[256], start[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  const int off = c.lay.misc + ST_COST_ITERS;
+  for (int e = threadIdx.x; e < c.n; e += blockDim.x) {
+    const float* row = c.state + (size_t)e * c.row;
+    int b = (int)(row[off] + 4.f * row[off + 1]) >> 1;
+    atomicAdd(&hist[b > 255 ? 255 : b], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) { int acc = 0; for (int b = 255; b >= 0; b--) { start[b] = acc; acc += hist[b]; } }
+  __syncthreads();
+  for (int e = threadIdx.x; e < c.n; e += blockDim.x) {
+    const float* row = c.state + (size_t)e * c.row;
+    int b = (int)(row[off] + 4.f * row[off + 1]) >> 1;
+    c.perm[atomicAdd(&start[b > 255 ? 255 : b], 1)] = e;
+  }
+}
+
 #define IK_THREADS 32    // one warp per k_ik block: 255 regs x 32 threads = 8 K registers, fits beside two resident k_env CTAs
 __global__ void __launch_bounds__(IK_THREADS) k_ik(DevCtx c, const float* __restrict__ action, int n_ticks, int use_action, int flag_base) {
   // Programmatic dependent launch: let the env-step kernel (next in the stream) start while this one is still running.
@@ -149,11 +174,8 @@ k_env(DevCtx c, int n_ticks, int gym, int flag_base, float* __restrict__ obs, fl
   cx.mask = G_LANES == 32 ? 0xffffffffu : (((1u << G_LANES) - 1u) << (((threadIdx.x & 31) / G_LANES) * G_LANES));
   // Groups past the end of the batch shadow the last env (same inputs, same control flow, identical outputs) so that
   // every thread of the CTA reaches the phase barriers inside physics_tick.
-  const int e_raw = blockIdx.x * ENVS_PER_CTA + warp;
-  const int e = e_raw < c.n ? e_raw : c.n - 1;
-  // k_ik blocks (IK_THREADS envs each) that feed this CTA's contiguous env range
-  const int e_first = blockIdx.x * ENVS_PER_CTA, e_last = min(e_first + ENVS_PER_CTA - 1, c.n - 1);
-  const int ikb0 = e_first / IK_THREADS, ikb1 = e_last / IK_THREADS;
+  const int e_raw = blockIdx.x * ENVS_PER_CTA + warp;          // position in this step's cost-sorted order
+  const int e = c.perm[e_raw < c.n ? e_raw : c.n - 1];
   float* w = (float*)(smem_raw + ((sizeof(Model) + 127) & ~(size_t)127)) + (size_t)warp * c.ws_stride;
   float* row = c.state + (size_t)e * c.row;
   for (int i = cx.lane; i < L.n_state; i += G_LANES) w[i] = row[i];
@@ -162,9 +184,9 @@ k_env(DevCtx c, int n_ticks, int gym, int flag_base, float* __restrict__ obs, fl
   for (int t = 0; t < n_ticks; t++) {
     // acquire tick t of the IK reference (k_ik may still be running: programmatic dependent launch)
     PHASE_T0();
-    if (threadIdx.x == 0) {
+    if (cx.lane == 0) {              // one lane per group waits for the k_ik block that owns its env
       const int want = flag_base + t + 1;
-      for (int b = ikb0; b <= ikb1; b++) while (*(volatile int*)(c.ik_flags + b) < want) __nanosleep(100);
+      while (*(volatile int*)(c.ik_flags + e / IK_THREADS) < want) __nanosleep(100);
       __threadfence();
     }
     PHASE(16);
@@ -247,6 +269,7 @@ extern "C" int d3il_create(d3il_env** out, const void* blob, size_t nbytes, int 
   CK(cudaMalloc(&d.traj, (size_t)h->max_ticks * 21 * n_envs * sizeof(float)));
   h->n_ik_blocks = (n_envs + IK_THREADS - 1) / IK_THREADS; h->launch_id = 0;
   CK(cudaMalloc(&d.ik_flags, (size_t)h->n_ik_blocks * sizeof(int)));
+  CK(cudaMalloc(&d.perm, (size_t)n_envs * sizeof(int)));
   CK(cudaMemset(d.ik_flags, 0, (size_t)h->n_ik_blocks * sizeof(int)));
   h->smem_bytes = ((sizeof(Model) + 127) & ~(size_t)127) + (size_t)ENVS_PER_CTA * d.ws_stride * sizeof(float);
   if (h->smem_bytes > 227 * 1024) { g_err = "d3il_create: scene workspace does not fit in shared memory"; delete h; return -1; }
@@ -279,7 +302,7 @@ extern "C" void d3il_destroy(d3il_env* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaFree((void*)h->d.model); cudaFree(h->d.state); cudaFree(h->d.ik.q); cudaFree(h->d.ik.des); cudaFree(h->d.ik.jt); cudaFree(h->d.ik.valid);
-  cudaFree(h->d.traj); cudaFree(h->d.ik_flags); cudaFreeHost(h->h_in); cudaFreeHost(h->h_out); cudaFreeHost(h->h_mask); cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_mask);
+  cudaFree(h->d.traj); cudaFree(h->d.ik_flags); cudaFree(h->d.perm); cudaFreeHost(h->h_in); cudaFreeHost(h->h_out); cudaFreeHost(h->h_mask); cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_mask);
   cudaStreamDestroy(h->own_stream);
   delete h;
 }
@@ -315,6 +338,7 @@ static inline int env_grid(const d3il_env* h) { return (h->n + ENVS_PER_CTA - 1)
 static cudaError_t launch_step(d3il_env* h, cudaStream_t s, const float* action, int n_ticks, int gym, float* obs, float* reward, uint8_t* done, float* info) {
   h->launch_id = (h->launch_id + 1) & 0xffffff;
   const int base = h->launch_id * 64;
+  k_sched<<<1, 1024, 0, s>>>(h->d);
   k_ik<<<h->n_ik_blocks, IK_THREADS, 0, s>>>(h->d, action, n_ticks, gym, base);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(env_grid(h)); cfg.blockDim = dim3(CTA_THREADS); cfg.dynamicSmemBytes = h->smem_bytes; cfg.stream = s;
@@ -323,7 +347,7 @@ static cudaError_t launch_step(d3il_env* h, cudaStream_t s, const float* action,
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   static const bool no_pdl = getenv("D3IL_NO_PDL") != nullptr;      // diagnosis: serialise the two kernels
   cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
-  h->launches += 2;
+  h->launches += 3;
   return cudaLaunchKernelEx(&cfg, k_env, h->d, n_ticks, gym, base, obs, reward, done, info);
 }
 

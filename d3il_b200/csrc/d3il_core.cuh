@@ -1138,7 +1138,8 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
     PHASE(8);
     if (blockIdx_is0()) count_iter();
     if (scale * gn < tol) done = 1;
-    if (iter > 0 && scale * (oldcost - cost) < tol * (real)1e-3) done = 1;
+    // improvement below what the cost can resolve in this precision: further iterations only chase rounding noise
+    if (iter > 0 && (scale * (oldcost - cost) < tol * (real)1e-3 || oldcost - cost <= (sizeof(real) == 4 ? (real)2e-6 : (real)1e-14) * absr(oldcost))) done = 1;
     }
     // all groups of the CTA iterate together (converged ones idle) so the Newton body stays fetch-shared
     if (!cta_any<CS>(!done)) break;

@@ -54,13 +54,14 @@ void emu_step(Emu* e, const double* action, float* obs, double* reward, int* don
   for (int k = 0; k < 3; k++) e->ik.des_pos[k] = (real)action[k];
   for (int k = 0; k < 4; k++) e->ik.des_quat[k] = (real)(action[3 + k] / n);
   float r; unsigned char d; float inf[16];
+  e->vwarm = 0;                 // like a kernel launch: exact sin/cos and a cold eigenbasis at the first IK iteration
   env_prestep<1>(CX, e->m, e->L, w, obs, &r, &d);
   for (int i = 0; i < e->m.n_substeps; i++) tick(e);
   env_poststep<1>(CX, e->m, e->L, w, inf);
   *reward = r; *done = d;
   for (int k = 0; k < e->m.info_dim; k++) info[k] = inf[k];
 }
-void emu_substep(Emu* e, int n) { for (int i = 0; i < n; i++) tick(e); }
+void emu_substep(Emu* e, int n) { e->vwarm = 0; for (int i = 0; i < n; i++) tick(e); }
 void emu_robot_state(Emu* e, double* tcp) { for (int k = 0; k < 3; k++) tcp[k] = e->w[e->L.tcp + k]; }
 void emu_get_obs(Emu* e, float* obs) { task_obs(e->m, e->L, e->w.data(), obs); }
 int emu_probe(Emu* e, const char* what, double* out, int cap) {
@@ -77,7 +78,7 @@ int emu_probe(Emu* e, const char* what, double* out, int cap) {
   return n;
 }
 void emu_get_state(Emu* e, double* out) { d3il_pack_state(e->m, e->L, e->w.data(), e->ik, out); }
-void emu_set_state(Emu* e, const double* in) { d3il_unpack_state(e->m, e->L, e->w.data(), e->ik, in); }
+void emu_set_state(Emu* e, const double* in) { d3il_unpack_state(e->m, e->L, e->w.data(), e->ik, in); e->vwarm = 0; }
 }
 
 // stand-alone narrow-phase probes of the kernel core (fast path vs general routine)
