@@ -157,7 +157,8 @@ struct Model {
   unsigned char p_rng[D3_MAXPAIR * 4];    // per pair: dof ranges [a0,a1) [b0,b1) touched by its two geoms (static)
   unsigned char p_cpl[D3_MAXPAIR];        // pair joins two different kinematic-tree blocks
   unsigned char g_slab[32];               // geom is a static, axis-aligned box (table top, support): eligible for the slab fast path
-  unsigned char tri_i[136], tri_j[136];   // row-major lower-triangle unranking table for n <= 16
+  int nblk, blk_s[8], blk_e[8];           // the kinematic-tree blocks as a list
+  unsigned char tri_i[300], tri_j[300];   // row-major lower-triangle unranking table for n <= 24
   unsigned char mp_a[D3_MAXV * 8], mp_b[D3_MAXV * 8];   // (a,b) list of related dof pairs, a >= b
   tab_t link[D3_MAXLINK * D3_LINK_W];
   tab_t geom[D3_MAXGEOM * D3_GEOM_W];
@@ -992,11 +993,12 @@ DEVNI real constraint_eval(const Cx& cx, const Model& m, const Lay& L, real* w, 
 // L; the running pivots live in piv[] (initialised by the caller with the diagonal), dinv[] receives 1 / L_kk.
 // Row i is owned by lane i % G.  Returns 1 if a pivot was not positive.
 template <int G>
-DEVNI int chol_factor_part(const Cx& cx, real* A, int n, const int* ps, const int* pe, bool whole, int maxsz, real* piv, real* dinv) {
+DEVNI int chol_factor_part(const Cx& cx, const Model& m, real* A, int n, bool whole, int maxsz, real* piv, real* dinv) {
   int bad = 0;
+  const int nb = whole ? 1 : m.nblk;
   for (int k = 0; k < maxsz; k++) {
     LANES(i, n) {
-      int c = (whole ? 0 : ps[i]) + k, e = whole ? n : pe[i];
+      int c = (whole ? 0 : m.d_bs[i]) + k, e = whole ? n : m.d_be[i];
       if (c >= e || i < c) continue;
       real p = piv[c];
       if (!(p > 0)) { bad = 1; p = 1; }
@@ -1004,12 +1006,16 @@ DEVNI int chol_factor_part(const Cx& cx, real* A, int n, const int* ps, const in
       if (i == c) dinv[c] = inv; else A[i * n + c] *= inv;
     }
     gsync<G>(cx);
-    LANES(i, n) {
-      int c = (whole ? 0 : ps[i]) + k, e = whole ? n : pe[i];
-      if (c >= e || i <= c) continue;
-      real lic = A[i * n + c];
-      for (int j = c + 1; j < i; j++) A[i * n + j] -= lic * A[j * n + c];
-      piv[i] -= lic * lic;
+    // rank-1 update of every block's trailing triangle, one (i, j) entry per lane step (lower-triangle table):
+    // the critical path is ceil(entries / G) independent updates instead of a serial walk along the longest row
+    for (int b = 0; b < nb; b++) {
+      const int c = (whole ? 0 : m.blk_s[b]) + k, e = whole ? n : m.blk_e[b], mb = e - c - 1;
+      if (mb <= 0) continue;
+      LANES(t, mb * (mb + 1) / 2) {
+        const int i = c + 1 + m.tri_i[t], j = c + 1 + m.tri_j[t];
+        const real v = A[i * n + c] * A[j * n + c];
+        if (i == j) piv[i] -= v; else A[i * n + j] -= v;
+      }
     }
     gsync<G>(cx);
   }
@@ -1019,44 +1025,39 @@ DEVNI int chol_factor_part(const Cx& cx, real* A, int n, const int* ps, const in
 // Solve L L^T x = b in place for the same partitioned factor.  x is pulled into registers (element i in lane i % G),
 // finished elements are broadcast with shuffles; no shared-memory traffic for x and no barriers inside the sweeps.
 template <int G>
-DEVNI void chol_solve_part(const Cx& cx, const real* A, int n, const int* ps, const int* pe, bool whole, int maxsz, const real* dinv, real* x) {
+DEVNI void chol_solve_part(const Cx& cx, const Model& m, const real* A, int n, bool whole, int maxsz, const real* dinv, real* x) {
   real xr[D3_SLOTS(G)];
+  int s0[D3_SLOTS(G)], e0[D3_SLOTS(G)];
 #pragma unroll
-  for (int sl = 0; sl < D3_SLOTS(G); sl++) { int i = sl * G + cx.lane; xr[sl] = i < n ? x[i] : (real)0; }
+  for (int sl = 0; sl < D3_SLOTS(G); sl++) {
+    int i = sl * G + cx.lane, ii = i < n ? i : n - 1;
+    xr[sl] = i < n ? x[i] : (real)0;
+    s0[sl] = whole ? 0 : m.d_bs[ii]; e0[sl] = whole ? n : m.d_be[ii];
+  }
   for (int k = 0; k < maxsz; k++) {
     real xcs[D3_SLOTS(G)];          // read phase first: every slot sees the pre-step values of x
 #pragma unroll
     for (int sl = 0; sl < D3_SLOTS(G); sl++) {
-      int i = sl * G + cx.lane;
-      int ii = i < n ? i : n - 1;
-      int c = (whole ? 0 : ps[ii]) + k, e = whole ? n : pe[ii];
-      int cc = c < e ? c : e - 1;
+      int c = s0[sl] + k, cc = c < e0[sl] ? c : e0[sl] - 1;
       xcs[sl] = elem_bcast<G>(cx, xr, cc) * dinv[cc];
     }
 #pragma unroll
     for (int sl = 0; sl < D3_SLOTS(G); sl++) {
-      int i = sl * G + cx.lane;
-      int ii = i < n ? i : n - 1;
-      int c = (whole ? 0 : ps[ii]) + k, e = whole ? n : pe[ii];
-      if (i < n && c < e) { if (i == c) xr[sl] = xcs[sl]; else if (i > c) xr[sl] -= A[i * n + c] * xcs[sl]; }
+      int i = sl * G + cx.lane, c = s0[sl] + k;
+      if (i < n && c < e0[sl]) { if (i == c) xr[sl] = xcs[sl]; else if (i > c) xr[sl] -= A[i * n + c] * xcs[sl]; }
     }
   }
   for (int k = maxsz - 1; k >= 0; k--) {
     real xcs[D3_SLOTS(G)];
 #pragma unroll
     for (int sl = 0; sl < D3_SLOTS(G); sl++) {
-      int i = sl * G + cx.lane;
-      int ii = i < n ? i : n - 1;
-      int s0 = whole ? 0 : ps[ii], c = s0 + k, e = whole ? n : pe[ii];
-      int cc = c < e ? c : e - 1;
+      int c = s0[sl] + k, cc = c < e0[sl] ? c : e0[sl] - 1;
       xcs[sl] = elem_bcast<G>(cx, xr, cc) * dinv[cc];
     }
 #pragma unroll
     for (int sl = 0; sl < D3_SLOTS(G); sl++) {
-      int i = sl * G + cx.lane;
-      int ii = i < n ? i : n - 1;
-      int s0 = whole ? 0 : ps[ii], c = s0 + k, e = whole ? n : pe[ii];
-      if (i < n && c < e) { if (i == c) xr[sl] = xcs[sl]; else if (i < c && i >= s0) xr[sl] -= A[c * n + i] * xcs[sl]; }
+      int i = sl * G + cx.lane, c = s0[sl] + k;
+      if (i < n && c < e0[sl]) { if (i == c) xr[sl] = xcs[sl]; else if (i < c && i >= s0[sl]) xr[sl] -= A[c * n + i] * xcs[sl]; }
     }
   }
 #pragma unroll
@@ -1098,7 +1099,7 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
     gsync<G>(cx);
   }
   real cost = 0, oldcost = 0;
-  int iter = 0;
+  int iter = 0, nsteps = 0;      // nsteps: Newton steps this env actually took (iter also counts idle CTA-uniform passes)
   PHASE_T0();
   for (; iter < max_iter; iter++) {
     PHASE(15);
@@ -1144,17 +1145,37 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
     // all groups of the CTA iterate together (converged ones idle) so the Newton body stays fetch-shared
     if (!cta_any<CS>(!done)) break;
     if (!done) {
+    nsteps++;
     // ---- H = M + J^T Hc J (lower triangle).  Block diagonal unless a contact couples two trees.
-    LANES(e, nv * nv) w[L.H + e] = 0;
+    // (A) every in-block entry is owned by one lane, which accumulates M, the limit rows and all contacts that live
+    //     inside that block in a register and writes H once: no barriers between contacts.
+    if (coupled) { LANES(e, nv * nv) w[L.H + e] = 0; gsync<G>(cx); }
+    for (int b = 0; b < m.nblk; b++) {
+      const int bs = m.blk_s[b], sz = m.blk_e[b] - bs;
+      LANES(t, sz * (sz + 1) / 2) {
+        const int gi = bs + m.tri_i[t], gj = bs + m.tri_j[t];
+        real acc = M[gj * nv + gi];
+        if (gi == gj) for (int i = 0; i < nlimit; i++) { int sd = (int)w[L.econ + i]; if ((sd > 0 ? sd : -sd) - 1 == gi) acc += w[L.hd + i]; }
+        for (int c = 0; c < ncon; c++) {
+          const real* cc = w + L.con + D3_CON_W * c;
+          const int r0 = (int)cc[19], a0 = (int)cc[20], a1 = (int)cc[21];
+          if (r0 < 0 || (int)cc[23] != (int)cc[22] || a0 != bs || gi >= a1) continue;      // gj <= gi < a1
+          const real* Hb = w + L.hb + 9 * c;
+          const real *J0 = w + L.J + r0 * D3_JW, *J1 = J0 + D3_JW, *J2 = J1 + D3_JW;
+          const int li = gi - a0, lj = gj - a0;
+          real i0 = J0[li], i1 = J1[li], i2 = J2[li];
+          real t0 = i0 * Hb[0] + i1 * Hb[3] + i2 * Hb[6], t1 = i0 * Hb[1] + i1 * Hb[4] + i2 * Hb[7], t2 = i0 * Hb[2] + i1 * Hb[5] + i2 * Hb[8];
+          acc += t0 * J0[lj] + t1 * J1[lj] + t2 * J2[lj];
+        }
+        w[L.H + gi * nv + gj] = acc;
+      }
+    }
     gsync<G>(cx);
-    LANES(e, m.nmpair) { int a = m.mp_a[e], b = m.mp_b[e]; w[L.H + a * nv + b] = M[b * nv + a]; }
-    gsync<G>(cx);
-    LANES(i, nlimit) { int sd = (int)w[L.econ + i]; int d = (sd > 0 ? sd : -sd) - 1; w[L.H + d * nv + d] += w[L.hd + i]; }
-    gsync<G>(cx);
-    for (int c = 0; c < ncon; c++) {
+    // (B) contacts that couple two blocks (rod-box, box-box): rare, added one after the other
+    if (coupled) for (int c = 0; c < ncon; c++) {
       const real* cc = w + L.con + D3_CON_W * c;
       int r0 = (int)cc[19];
-      if (r0 < 0) continue;
+      if (r0 < 0 || (int)cc[23] == (int)cc[22]) continue;
       int a0 = (int)cc[20], a1 = (int)cc[21], b0 = (int)cc[22], b1 = (int)cc[23], na = a1 - a0, nn = na + b1 - b0;
       const real* Hb = w + L.hb + 9 * c;
       const real *J0 = w + L.J + r0 * D3_JW, *J1 = J0 + D3_JW, *J2 = J1 + D3_JW;
@@ -1171,12 +1192,12 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
     LANES(d, nv) { w[L.hpiv + d] = w[L.H + d * nv + d]; w[L.pvec + d] = -w[L.grad + d]; }
     gsync<G>(cx);
     int maxsz = coupled ? nv : m.maxblk;
-    if (chol_factor_part<G>(cx, w + L.H, nv, m.d_bs, m.d_be, coupled != 0, maxsz, w + L.hpiv, w + L.hdinv)) {
+    if (chol_factor_part<G>(cx, m, w + L.H, nv, coupled != 0, maxsz, w + L.hpiv, w + L.hdinv)) {
       LANES(z, 1) w[L.misc + ST_STATUS] = (real)(((int)w[L.misc + ST_STATUS]) | 4);
       break;
     }
     PHASE(10);
-    chol_solve_part<G>(cx, w + L.H, nv, m.d_bs, m.d_be, coupled != 0, maxsz, w + L.hdinv, w + L.pvec);
+    chol_solve_part<G>(cx, m, w + L.H, nv, coupled != 0, maxsz, w + L.hdinv, w + L.pvec);
     PHASE(11);
     // ---- exact line search (safeguarded 1-D Newton / false position), quantities reduced across lanes
     eval_jar<G>(cx, m, L, w, nlimit, ncon, L.pvec, L.Jp, false);
@@ -1260,7 +1281,7 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
     w[L.qfrc_c + d] = s;
   }
   gsync<G>(cx);
-  return iter;
+  return nsteps;
 }
 
 // ------------------------------------------------------------------------------------------------ one physics tick
@@ -1324,8 +1345,8 @@ DEVFN void physics_tick(const Cx& cx, const Model& m, const Lay& L, real* w, con
   }
   LANES(e, m.nmpair) { int a = m.mp_a[e], b = m.mp_b[e]; if (a != b) w[L.M + a * nv + b] = w[L.M + b * nv + a]; }   // lower <- upper
   gsync<G>(cx);
-  if (chol_factor_part<G>(cx, w + L.M, nv, m.d_bs, m.d_be, false, m.maxblk, w + L.mpiv, w + L.mdinv)) { LANES(z, 1) w[L.misc + ST_STATUS] = (real)(((int)w[L.misc + ST_STATUS]) | 1); }
-  chol_solve_part<G>(cx, w + L.M, nv, m.d_bs, m.d_be, false, m.maxblk, w + L.mdinv, w + L.qacc_smooth);
+  if (chol_factor_part<G>(cx, m, w + L.M, nv, false, m.maxblk, w + L.mpiv, w + L.mdinv)) { LANES(z, 1) w[L.misc + ST_STATUS] = (real)(((int)w[L.misc + ST_STATUS]) | 1); }
+  chol_solve_part<G>(cx, m, w + L.M, nv, false, m.maxblk, w + L.mdinv, w + L.qacc_smooth);
   PHASE(4);
   cta_sync<CS>();
   int iters = solve_constraints<G, CS>(cx, m, L, w, ne, nlimit, ncon, coupled, tol, max_iter);
@@ -1361,7 +1382,7 @@ DEVFN void physics_tick(const Cx& cx, const Model& m, const Lay& L, real* w, con
     }
   }
   gsync<G>(cx);
-  chol_solve_part<G>(cx, w + L.M, nv, m.d_bs, m.d_be, false, m.maxblk, w + L.mdinv, w + L.tmpv);
+  chol_solve_part<G>(cx, m, w + L.M, nv, false, m.maxblk, w + L.mdinv, w + L.tmpv);
   LANES(d, nv) w[L.qvel + d] += h * w[L.tmpv + d];
   gsync<G>(cx);
   LANES(i, m.nlink) {

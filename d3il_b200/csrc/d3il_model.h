@@ -89,7 +89,10 @@ static inline bool d3il_build_model(const void* blob, size_t nbytes, Model& m, L
     m.p_rng[4 * ip] = (unsigned char)a0; m.p_rng[4 * ip + 1] = (unsigned char)a1; m.p_rng[4 * ip + 2] = (unsigned char)b0; m.p_rng[4 * ip + 3] = (unsigned char)b1;
     m.p_cpl[ip] = (unsigned char)cpl;
   }
-  { int e = 0; for (int i = 0; i < 16; i++) for (int j = 0; j <= i; j++) { m.tri_i[e] = (unsigned char)i; m.tri_j[e] = (unsigned char)j; e++; } }
+  { int e = 0; for (int i = 0; i < 24; i++) for (int j = 0; j <= i; j++) { m.tri_i[e] = (unsigned char)i; m.tri_j[e] = (unsigned char)j; e++; } }
+  m.nblk = 0;
+  for (int d = 0; d < m.nv; d++) if (m.d_bs[d] == d) { if (m.nblk >= 8) { err = "too many kinematic trees"; return false; } m.blk_s[m.nblk] = d; m.blk_e[m.nblk] = m.d_be[d]; m.nblk++; }
+  if (m.nv > 24) { err = "nv > 24 needs the long-row factorisation path (not built yet)"; return false; }
   m.maxcon = conmax < 20 ? ((conmax + 3) & ~3) : 20;
   m.maxrow = 3 * m.maxcon + 4;
   d3il_layout(m, L);
