@@ -17,15 +17,7 @@
 #include <vector>
 
 #include "../../include/d3il.h"
-#include "d3il_model.h"
-
-#ifndef G_LANES
-#define G_LANES 32          // lanes cooperating on one env (32 = one warp per env; 16 = two envs per warp)
-#endif
-#ifndef ENVS_PER_CTA
-#define ENVS_PER_CTA 7     // 2 CTAs/SM x 7 envs: 4096 envs = 1.98 waves on 148 SMs (13.3 KB of shared memory per env)
-#endif
-#define CTA_THREADS (G_LANES * ENVS_PER_CTA)
+#include "d3il_dev.h"
 
 static thread_local std::string g_err;
 extern "C" const char* d3il_last_error(void) { return g_err.c_str(); }
@@ -35,28 +27,10 @@ extern "C" const char* d3il_last_error(void) { return g_err.c_str(); }
     if (e_ != cudaSuccess) { g_err = std::string(#call) + ": " + cudaGetErrorString(e_); return -2; } \
   } while (0)
 
-struct DevIk {            // SoA views, [field][n]
-  double* q;              // [7][n]
-  float* des;             // [7][n]  des_pos(3), des_quat(4)
-  float* jt;              // [21][n] last set-point: q_hi(7), q_lo(7), qd(7)
-  int* valid;             // [n]
-};
-struct DevCtx {
-  const Model* model;     // global copy, staged into shared memory per CTA
-  Lay lay;
-  float* state;           // [n][row]
-  int row, n, ws_stride;
-  DevIk ik;
-  float* traj;            // [ticks][21][n]
-  int* ik_flags;          // [n_ik_blocks] ticks published by each k_ik block (monotonic: launch_id * 64 + tick + 1)
-  int* perm;              // [n] env order of this step's k_env groups: most expensive envs (last step's Newton iterations) first
-  float tol; int max_iter;
-};
-
 struct d3il_env {
   Model m; Lay L;
   DevCtx d;
-  int device, n, max_ticks, n_ik_blocks, launch_id;
+  int device, n, max_ticks, n_ik_blocks, launch_id, n_single;
   long long launches;
   size_t smem_bytes;
   // pinned + device staging for the *_host calls
@@ -65,9 +39,9 @@ struct d3il_env {
   int profiling; cudaEvent_t ev[3]; double prof_ms[2]; long long prof_n;
 };
 
-// ------------------------------------------------------------------------------------------------ kernels
+// ------------------------------------------------------------------------------------------------ kernels (scheduler, IK reference)
 #ifdef D3IL_PHASE_TIMING
-__device__ unsigned long long g_tl[4 * 4096];     // debug timeline: per block [t0, t1, smid, kind]
+static __device__ unsigned long long g_tl[4 * 4096];     // debug timeline of the k_ik blocks (k_env's lives in d3il_kernels_env.cu)
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ unsigned smid() { unsigned r; asm volatile("mov.u32 %0, %smid;" : "=r"(r)); return r; }
 #define TL_BEGIN(kind, idx) unsigned long long tl_t0 = gtime(); const int tl_i = (idx)
@@ -76,14 +50,6 @@ __device__ __forceinline__ unsigned smid() { unsigned r; asm volatile("mov.u32 %
 #define TL_BEGIN(kind, idx) ((void)0)
 #define TL_END(kind) ((void)0)
 #endif
-__device__ __forceinline__ void stage_model(Model* sm, const Model* gm) {
-  const int* src = (const int*)gm; int* dst = (int*)sm;
-  for (int i = threadIdx.x; i < (int)(sizeof(Model) / 4); i += blockDim.x) dst[i] = src[i];
-  __syncthreads();
-}
-
-// IK reference generator: one thread per env (a5/a6).  mode: 1 = take the set-point from `action` (env step),
-// 0 = keep the stored set-point (d3il_substep).  In joint-PD mode (after reset) the held set-point is replicated.
 // Cost-aware scheduling.  Env steps differ in cost by ~3x (Newton iterations while a box is being pushed or is
 // rocking), CTAs are as slow as their slowest env (CTA-uniform loops, phase barriers) and the kernel as slow as its
 // last CTA.  So each step the envs are bucket-sorted by the Newton iterations of their previous step: expensive envs
@@ -108,7 +74,6 @@ __global__ void __launch_bounds__(1024) k_sched(DevCtx c) {
   }
 }
 
-#define IK_THREADS 32    // one warp per k_ik block: 255 regs x 32 threads = 8 K registers, fits beside two resident k_env CTAs
 __global__ void __launch_bounds__(IK_THREADS) k_ik(DevCtx c, const float* __restrict__ action, int n_ticks, int use_action, int flag_base) {
   // Programmatic dependent launch: let the env-step kernel (next in the stream) start while this one is still running.
   // It consumes our set-points tick by tick through the release flags below; we never wait on anything, and we are
@@ -160,82 +125,6 @@ __global__ void __launch_bounds__(IK_THREADS) k_ik(DevCtx c, const float* __rest
   TL_END(1);
 }
 
-// Env step: one warp per env.  gym = 1: GymEnvWrapper.step semantics around the ticks; gym = 0: bare ticks (substep).
-__global__ void __launch_bounds__(CTA_THREADS, (CTA_THREADS > 256 ? 1 : 2))
-k_env(DevCtx c, int n_ticks, int gym, int flag_base, float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ done, float* __restrict__ info) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  TL_BEGIN(2, blockIdx.x);
-  Model* sm = (Model*)smem_raw;
-  stage_model(sm, c.model);
-  const Model& m = *sm;
-  const Lay& L = c.lay;
-  const int warp = threadIdx.x / G_LANES;
-  Cx cx; cx.lane = threadIdx.x % G_LANES;
-  cx.mask = G_LANES == 32 ? 0xffffffffu : (((1u << G_LANES) - 1u) << (((threadIdx.x & 31) / G_LANES) * G_LANES));
-  // Groups past the end of the batch shadow the last env (same inputs, same control flow, identical outputs) so that
-  // every thread of the CTA reaches the phase barriers inside physics_tick.
-  const int e_raw = blockIdx.x * ENVS_PER_CTA + warp;          // position in this step's cost-sorted order
-  const int e = c.perm[e_raw < c.n ? e_raw : c.n - 1];
-  float* w = (float*)(smem_raw + ((sizeof(Model) + 127) & ~(size_t)127)) + (size_t)warp * c.ws_stride;
-  float* row = c.state + (size_t)e * c.row;
-  for (int i = cx.lane; i < L.n_state; i += G_LANES) w[i] = row[i];
-  __syncwarp(cx.mask);
-  if (gym) env_prestep<G_LANES>(cx, m, L, w, obs + (size_t)e * m.obs_dim, reward + e, done + e);
-  for (int t = 0; t < n_ticks; t++) {
-    // acquire tick t of the IK reference (k_ik may still be running: programmatic dependent launch)
-    PHASE_T0();
-    if (cx.lane == 0) {              // one lane per group waits for the k_ik block that owns its env
-      const int want = flag_base + t + 1;
-      while (*(volatile int*)(c.ik_flags + e / IK_THREADS) < want) __nanosleep(100);
-      __threadfence();
-    }
-    PHASE(16);
-    __syncthreads();
-    const float* tr = c.traj + (size_t)t * 21 * c.n + e;
-    for (int k = cx.lane; k < 21; k += G_LANES) w[L.jt + k] = __ldcg(tr + (size_t)k * c.n);
-    __syncwarp(cx.mask);
-    physics_tick<G_LANES, true>(cx, m, L, w, w + L.jt, w + L.jt + 7, w + L.jt + 14, c.tol, c.max_iter);
-  }
-  if (gym) env_poststep<G_LANES>(cx, m, L, w, info + (size_t)e * m.info_dim);
-  if (e_raw < c.n) for (int i = cx.lane; i < L.n_state; i += G_LANES) row[i] = w[i];
-  TL_END(2);
-}
-
-__global__ void __launch_bounds__(CTA_THREADS, (CTA_THREADS > 256 ? 1 : 2))
-k_reset(DevCtx c, const float* __restrict__ ctx, const uint8_t* __restrict__ mask, float* __restrict__ obs) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  Model* sm = (Model*)smem_raw;
-  stage_model(sm, c.model);
-  const Model& m = *sm;
-  const Lay& L = c.lay;
-  const int warp = threadIdx.x / G_LANES;
-  Cx cx; cx.lane = threadIdx.x % G_LANES;
-  cx.mask = G_LANES == 32 ? 0xffffffffu : (((1u << G_LANES) - 1u) << (((threadIdx.x & 31) / G_LANES) * G_LANES));
-  const int e = blockIdx.x * ENVS_PER_CTA + warp;
-  if (e >= c.n) return;
-  if (mask && !mask[e]) return;
-  float* w = (float*)(smem_raw + ((sizeof(Model) + 127) & ~(size_t)127)) + (size_t)warp * c.ws_stride;
-  env_reset<G_LANES>(cx, m, L, w, (ctx && m.ctx_dim > 0) ? ctx + (size_t)e * m.ctx_dim : nullptr, c.tol, c.max_iter);
-  float* row = c.state + (size_t)e * c.row;
-  for (int i = cx.lane; i < L.n_state; i += G_LANES) row[i] = w[i];
-  const int n = c.n;
-  for (int k = cx.lane; k < 7; k += G_LANES) {
-    c.ik.q[k * n + e] = 0; c.ik.des[k * n + e] = 0;
-    c.ik.jt[k * n + e] = (float)m.ctrl[D3C_INIT_QPOS + k]; c.ik.jt[(7 + k) * n + e] = 0; c.ik.jt[(14 + k) * n + e] = 0;
-  }
-  if (cx.lane == 0) {
-    c.ik.valid[e] = 0;
-    if (obs) task_obs(m, L, w, obs + (size_t)e * m.obs_dim);
-  }
-}
-
-__global__ void k_robot_state(DevCtx c, float* __restrict__ tcp) {
-  int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= c.n) return;
-  const float* row = c.state + (size_t)e * c.row;
-  for (int k = 0; k < 3; k++) tcp[(size_t)e * 3 + k] = row[c.lay.tcp + k];
-}
-
 // ------------------------------------------------------------------------------------------------ C ABI
 extern "C" int d3il_create(d3il_env** out, const void* blob, size_t nbytes, int n_envs, int device) {
   if (!out || !blob || n_envs <= 0) { g_err = "d3il_create: bad arguments"; return -1; }
@@ -273,14 +162,12 @@ extern "C" int d3il_create(d3il_env** out, const void* blob, size_t nbytes, int 
   CK(cudaMemset(d.ik_flags, 0, (size_t)h->n_ik_blocks * sizeof(int)));
   h->smem_bytes = ((sizeof(Model) + 127) & ~(size_t)127) + (size_t)ENVS_PER_CTA * d.ws_stride * sizeof(float);
   if (h->smem_bytes > 227 * 1024) { g_err = "d3il_create: scene workspace does not fit in shared memory"; delete h; return -1; }
-  CK(cudaFuncSetAttribute(k_env, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-  CK(cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-  // k_ik needs almost no shared memory, but an SM keeps the L1/shared carve-out of whatever is resident: ask for the
-  // maximum shared carve-out everywhere so k_env CTAs can join SMs that still run a k_ik block (measured: without this
-  // 128 of 148 SMs refused k_env CTAs until their k_ik block had exited).
+  CK(d3il_env_kernels_configure(h->smem_bytes));
   CK(cudaFuncSetAttribute(k_ik, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  CK(cudaFuncSetAttribute(k_env, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  CK(cudaFuncSetAttribute(k_reset, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  CK(cudaFuncSetAttribute(k_sched, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  // the most expensive envs of each step run one per CTA (cost-sorted order, see k_sched / k_env)
+  h->n_single = (G_LANES == 32 && n_envs >= 512) ? 16 : 0;
+  if (const char* ev = getenv("D3IL_N_SINGLE")) { h->n_single = atoi(ev); if (h->n_single < 0 || h->n_single > n_envs / 2 || G_LANES != 32) h->n_single = 0; }
   // staging for the host-buffer entry points
   const Model& m = h->m;
   h->in_floats = (size_t)n_envs * (m.act_dim > m.ctx_dim ? m.act_dim : m.ctx_dim);
@@ -331,31 +218,24 @@ extern "C" int d3il_get_profile(const d3il_env* h, double out_ms[2], long long* 
   return 0;
 }
 
-static inline int env_grid(const d3il_env* h) { return (h->n + ENVS_PER_CTA - 1) / ENVS_PER_CTA; }
 
-// IK reference + env step: two launches on one stream, the second with programmatic stream serialization so that it
-// overlaps the first (per-tick hand-off through ik_flags).  If the driver serialises them anyway the result is the same.
+// Scheduler + IK reference + env step: three launches on one stream, the last one with programmatic stream serialization
+// so that it overlaps k_ik (per-tick hand-off through ik_flags).  If the driver serialises them anyway the result is the same.
 static cudaError_t launch_step(d3il_env* h, cudaStream_t s, const float* action, int n_ticks, int gym, float* obs, float* reward, uint8_t* done, float* info) {
   h->launch_id = (h->launch_id + 1) & 0xffffff;
   const int base = h->launch_id * 64;
+  static const bool no_pdl = getenv("D3IL_NO_PDL") != nullptr;      // diagnosis: serialise the kernels
   k_sched<<<1, 1024, 0, s>>>(h->d);
   k_ik<<<h->n_ik_blocks, IK_THREADS, 0, s>>>(h->d, action, n_ticks, gym, base);
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(env_grid(h)); cfg.blockDim = dim3(CTA_THREADS); cfg.dynamicSmemBytes = h->smem_bytes; cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  static const bool no_pdl = getenv("D3IL_NO_PDL") != nullptr;      // diagnosis: serialise the two kernels
-  cfg.attrs = attr; cfg.numAttrs = no_pdl ? 0 : 1;
   h->launches += 3;
-  return cudaLaunchKernelEx(&cfg, k_env, h->d, n_ticks, gym, base, obs, reward, done, info);
+  return d3il_launch_env(h->d, h->n_single, n_ticks, gym, base, obs, reward, done, info, h->smem_bytes, s, !no_pdl);
 }
 
 extern "C" int d3il_reset(d3il_env* h, const float* ctx, const uint8_t* mask, float* obs, void* stream) {
   if (!h) { g_err = "d3il_reset: null handle"; return -1; }
   if (h->m.ctx_dim > 0 && !ctx) { g_err = "d3il_reset: this scene needs a context per env"; return -1; }
   CK(cudaSetDevice(h->device));
-  k_reset<<<env_grid(h), CTA_THREADS, h->smem_bytes, (cudaStream_t)stream>>>(h->d, ctx, mask, obs);
+  d3il_launch_reset(h->d, ctx, mask, obs, h->smem_bytes, (cudaStream_t)stream);
   h->launches += 1;
   CK(cudaGetLastError());
   return 0;
@@ -398,7 +278,7 @@ extern "C" int d3il_substep(d3il_env* h, int n, void* stream) {
 extern "C" int d3il_robot_state(d3il_env* h, float* tcp, void* stream) {
   if (!h || !tcp) { g_err = "d3il_robot_state: null argument"; return -1; }
   CK(cudaSetDevice(h->device));
-  k_robot_state<<<(h->n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->d, tcp);
+  d3il_launch_robot_state(h->d, tcp, (cudaStream_t)stream);
   h->launches += 1;
   CK(cudaGetLastError());
   return 0;
@@ -509,8 +389,12 @@ extern "C" int d3il_set_state(d3il_env* h, const double* in, int e) {
 }
 
 #ifdef D3IL_PHASE_TIMING
-extern "C" int d3il_debug_timeline(unsigned long long* out) { return cudaMemcpyFromSymbol(out, g_tl, sizeof(unsigned long long) * 4 * 4096) == cudaSuccess ? 0 : -2; }
-extern "C" int d3il_debug_phase_cycles(unsigned long long* out24) {
-  return cudaMemcpyFromSymbol(out24, g_phase_cycles, sizeof(unsigned long long) * 24) == cudaSuccess ? 0 : -2;
+extern "C" int d3il_debug_timeline(unsigned long long* out) {
+  std::vector<unsigned long long> a(4 * 4096), b(4 * 4096);
+  if (cudaMemcpyFromSymbol(a.data(), g_tl, sizeof(unsigned long long) * 4 * 4096) != cudaSuccess) return -2;
+  if (d3il_debug_timeline_env(b.data())) return -2;
+  for (int i = 0; i < 4096; i++) for (int k = 0; k < 4; k++) out[4 * i + k] = i >= 2048 ? a[4 * i + k] : b[4 * i + k];
+  return 0;
 }
+extern "C" int d3il_debug_phase_cycles(unsigned long long* out24) { return d3il_debug_phase_cycles_env(out24); }
 #endif

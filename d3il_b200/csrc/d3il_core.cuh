@@ -31,7 +31,7 @@ typedef float tab_t;    // model tables are fp32 in shared memory
 #define DEVNI static inline
 #define HDFN static inline
 #define D3_RESTRICT
-struct Cx { int lane; unsigned mask; };
+struct Cx { int lane; unsigned mask; int cta_threads; };   // cta_threads: threads of this CTA that take part in the phase barriers
 template <int G> DEVFN void gsync(const Cx&) {}
 template <int G> DEVFN real gsum(const Cx&, real x) { return x; }
 template <int G> DEVFN real gmaxr(const Cx&, real x) { return x; }
@@ -40,9 +40,9 @@ template <int G> DEVFN int gori(const Cx&, int x) { return x; }
 #else
 #define DEVFN __device__ __forceinline__
 #define HDFN __host__ __device__ __forceinline__
-#define DEVNI __device__ __noinline__       // big, multiply-instantiated routines: the kernel is instruction-fetch bound
+#define DEVNI static __device__ __noinline__       // big, multiply-instantiated routines: the kernel is instruction-fetch bound
 #define D3_RESTRICT __restrict__
-struct Cx { int lane; unsigned mask; };
+struct Cx { int lane; unsigned mask; int cta_threads; };   // cta_threads: threads of this CTA that take part in the phase barriers
 template <int G> DEVFN void gsync(const Cx& cx) { __syncwarp(cx.mask); }
 template <int G> DEVFN real gsum(const Cx& cx, real x) {
 #pragma unroll
@@ -79,21 +79,26 @@ template <int G> DEVFN int gori(const Cx& cx, int x) {
 // CTA-wide barriers at fixed phase boundaries keep every warp of the CTA inside the same code region, so one
 // instruction fetch serves all of them.  CS = false (reset kernel with masked early exits, host emulation): no barriers.
 // CTA-wide "does anybody still need another iteration" vote (plain flag without CTA barriers)
-template <bool CS> DEVFN int cta_any(int pred) {
+template <bool CS> DEVFN int cta_any(const Cx& cx, int pred) {
 #if defined(__CUDA_ARCH__)
-  if (CS) return __syncthreads_or(pred);
+  if (CS) {
+    int out;
+    asm volatile("{ .reg .pred p, q; setp.ne.s32 p, %1, 0; bar.red.or.pred q, 1, %2, p; selp.s32 %0, 1, 0, q; }" : "=r"(out) : "r"(pred), "r"(cx.cta_threads) : "memory");
+    return out;
+  }
 #endif
   return pred;
 }
-template <bool CS> DEVFN void cta_sync() {
+// Named barrier 1 over the participating threads only (CTAs that carry fewer envs than warps let the spare warps exit)
+template <bool CS> DEVFN void cta_sync(const Cx& cx) {
 #if defined(__CUDA_ARCH__)
-  if (CS) __syncthreads();
+  if (CS) asm volatile("bar.sync 1, %0;" :: "r"(cx.cta_threads) : "memory");
 #endif
 }
 
 #if defined(D3IL_PHASE_TIMING) && !defined(D3IL_EMU)
 // debug build only: per-phase cycle counts of the group that owns env 0 (profiles/phase_timing.py)
-__device__ unsigned long long g_phase_cycles[24];
+static __device__ unsigned long long g_phase_cycles[24];
 #endif
 #if defined(D3IL_PHASE_TIMING) && defined(__CUDA_ARCH__)
 #define PHASE_T0() long long t_ph = clock64()
@@ -1143,7 +1148,7 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
     if (iter > 0 && (scale * (oldcost - cost) < tol * (real)1e-3 || oldcost - cost <= (sizeof(real) == 4 ? (real)2e-6 : (real)1e-14) * absr(oldcost))) done = 1;
     }
     // all groups of the CTA iterate together (converged ones idle) so the Newton body stays fetch-shared
-    if (!cta_any<CS>(!done)) break;
+    if (!cta_any<CS>(cx, !done)) break;
     if (!done) {
     nsteps++;
     // ---- H = M + J^T Hc J (lower triangle).  Block diagonal unless a contact couples two trees.
@@ -1318,22 +1323,22 @@ DEVFN void physics_tick(const Cx& cx, const Model& m, const Lay& L, real* w, con
     quat2mat(Rt, tq); mat_mul3(R, w + L.xmat + 54, Rt); mat2quat(w + L.tcp + 3, R);
   }
   PHASE(0);
-  cta_sync<CS>();
+  cta_sync<CS>(cx);
   LANES(e, nv * nv) w[L.M + e] = 0;     // unrelated dof pairs inside a block (the two fingers) must read as zero
   gsync<G>(cx);
   dynamics<G>(cx, m, L, w);
   PHASE(1);
-  cta_sync<CS>();
+  cta_sync<CS>(cx);
   int ncon = collision<G>(cx, m, L, w);
   PHASE(2);
-  cta_sync<CS>();
+  cta_sync<CS>(cx);
   int nlimit = 0, coupled = 0;
   int ne = make_constraints<G>(cx, m, L, w, ncon, &nlimit, &coupled);
   PHASE(3);
 #ifdef D3IL_PHASE_TIMING
   if (cx.lane == 0) { count_stat(21, coupled); count_stat(22, ncon); count_stat(23, 1); count_stat(19, ne); }
 #endif
-  cta_sync<CS>();
+  cta_sync<CS>(cx);
   // --- smooth dynamics: qacc_smooth = M^-1 (passive - bias + actuation); M is block diagonal over the trees
   LANES(d, nv) {
     int li = m.d_link[d];
@@ -1348,14 +1353,14 @@ DEVFN void physics_tick(const Cx& cx, const Model& m, const Lay& L, real* w, con
   if (chol_factor_part<G>(cx, m, w + L.M, nv, false, m.maxblk, w + L.mpiv, w + L.mdinv)) { LANES(z, 1) w[L.misc + ST_STATUS] = (real)(((int)w[L.misc + ST_STATUS]) | 1); }
   chol_solve_part<G>(cx, m, w + L.M, nv, false, m.maxblk, w + L.mdinv, w + L.qacc_smooth);
   PHASE(4);
-  cta_sync<CS>();
+  cta_sync<CS>(cx);
   int iters = solve_constraints<G, CS>(cx, m, L, w, ne, nlimit, ncon, coupled, tol, max_iter);
   LANES(z, 1) {      // per-env cost counters of the current env step (cost-aware scheduling, diagnostics)
     w[L.misc + ST_COST_ITERS] += (real)iters; w[L.misc + ST_COST_COUPLED] += (real)coupled;
     if ((real)ncon > w[L.misc + ST_COST_NCON]) w[L.misc + ST_COST_NCON] = (real)ncon;
   }
   PHASE(5);
-  cta_sync<CS>();
+  cta_sync<CS>(cx);
   LANES(d, nv) { w[L.warm + d] = w[L.qacc + d]; w[L.tmpv + d] = w[L.qfrc_smooth + d] + w[L.qfrc_c + d]; }
   LANES(k, D3_NROB) w[L.bias_prev + k] = w[L.bias + k];
   // --- mj_Euler with implicit joint damping: (M + h B) qacc* = qfrc_smooth + qfrc_constraint.  Only the trailing
@@ -1407,5 +1412,5 @@ DEVFN void physics_tick(const Cx& cx, const Model& m, const Lay& L, real* w, con
   }
   gsync<G>(cx);
   PHASE(6);
-  cta_sync<CS>();
+  cta_sync<CS>(cx);
 }

@@ -1,0 +1,49 @@
+// d3il_dev.h — declarations shared by the two CUDA translation units of libd3il.so:
+//   d3il_capi.cu        : C ABI, k_sched, k_ik (fp64 IK reference; compiled with the full register budget)
+//   d3il_kernels_env.cu : k_env, k_reset, k_robot_state (compiled with -maxrregcount=120 so that two 7-warp CTAs and
+//                         one k_ik warp fit the 64 K register file of an SM together)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "d3il_model.h"
+
+#ifndef G_LANES
+#define G_LANES 32          // lanes cooperating on one env (32 = one warp per env; 16 = two envs per warp)
+#endif
+#ifndef ENVS_PER_CTA
+#define ENVS_PER_CTA 7     // 2 CTAs/SM x 7 envs: 4096 envs = 1.98 waves on 148 SMs (13.3 KB of shared memory per env)
+#endif
+#define CTA_THREADS (G_LANES * ENVS_PER_CTA)
+#define IK_THREADS 32    // one warp per k_ik block: 255 regs x 32 threads = 8 K registers, fits beside two resident k_env CTAs
+
+struct DevIk {            // SoA views, [field][n]
+  double* q;              // [7][n]
+  float* des;             // [7][n]  des_pos(3), des_quat(4)
+  float* jt;              // [21][n] last set-point: q_hi(7), q_lo(7), qd(7)
+  int* valid;             // [n]
+};
+struct DevCtx {
+  const Model* model;     // global copy, staged into shared memory per CTA
+  Lay lay;
+  float* state;           // [n][row]
+  int row, n, ws_stride;
+  DevIk ik;
+  float* traj;            // [ticks][21][n]
+  int* ik_flags;          // [n_ik_blocks] ticks published by each k_ik block (monotonic: launch_id * 64 + tick + 1)
+  int* perm;              // [n] env order of this step's k_env groups: most expensive envs (last step's Newton iterations) first
+  float tol; int max_iter;
+};
+
+// host-side launchers of the kernels that live in d3il_kernels_env.cu
+cudaError_t d3il_env_kernels_configure(size_t smem_bytes);
+cudaError_t d3il_launch_env(const DevCtx& c, int n_single, int n_ticks, int gym, int flag_base, float* obs, float* reward, uint8_t* done, float* info,
+                            size_t smem_bytes, cudaStream_t s, bool programmatic);
+void d3il_launch_reset(const DevCtx& c, const float* ctx, const uint8_t* mask, float* obs, size_t smem_bytes, cudaStream_t s);
+void d3il_launch_robot_state(const DevCtx& c, float* tcp, cudaStream_t s);
+int d3il_env_grid(int n, int n_single);
+
+#ifdef D3IL_PHASE_TIMING
+int d3il_debug_timeline_env(unsigned long long* out4096x4);     // k_env CTA records (the k_ik ones live in d3il_capi.cu)
+int d3il_debug_phase_cycles_env(unsigned long long* out24);
+#endif

@@ -1,0 +1,145 @@
+// d3il_kernels_env.cu — the warp-per-env kernels: k_env (Gym pre-step sampling + n physics ticks + post-step info),
+// k_reset, k_robot_state, and their host launchers.  Compiled with -maxrregcount=120 (see d3il_dev.h).
+#include <stdio.h>
+
+#include "d3il_dev.h"
+
+// ------------------------------------------------------------------------------------------------ kernels
+#ifdef D3IL_PHASE_TIMING
+static __device__ unsigned long long g_tl[4 * 4096];     // debug timeline: per block [t0, t1, smid, kind]
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned smid() { unsigned r; asm volatile("mov.u32 %0, %smid;" : "=r"(r)); return r; }
+#define TL_BEGIN(kind, idx) unsigned long long tl_t0 = gtime(); const int tl_i = (idx)
+#define TL_END(kind) do { if (threadIdx.x == 0 && tl_i < 4096) { g_tl[4 * tl_i] = tl_t0; g_tl[4 * tl_i + 1] = gtime(); g_tl[4 * tl_i + 2] = smid(); g_tl[4 * tl_i + 3] = kind; } } while (0)
+#else
+#define TL_BEGIN(kind, idx) ((void)0)
+#define TL_END(kind) ((void)0)
+#endif
+__device__ __forceinline__ void stage_model(Model* sm, const Model* gm) {
+  const int* src = (const int*)gm; int* dst = (int*)sm;
+  for (int i = threadIdx.x; i < (int)(sizeof(Model) / 4); i += blockDim.x) dst[i] = src[i];
+  __syncthreads();
+}
+
+// IK reference generator: one thread per env (a5/a6).  mode: 1 = take the set-point from `action` (env step),
+// 0 = keep the stored set-point (d3il_substep).  In joint-PD mode (after reset) the held set-point is replicated.
+// Env step: one warp per env.  gym = 1: GymEnvWrapper.step semantics around the ticks; gym = 0: bare ticks (substep).
+__global__ void __launch_bounds__(CTA_THREADS, (CTA_THREADS > 256 ? 1 : 2))
+k_env(DevCtx c, int n_single, int n_ticks, int gym, int flag_base, float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ done, float* __restrict__ info) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  TL_BEGIN(2, blockIdx.x);
+  Model* sm = (Model*)smem_raw;
+  stage_model(sm, c.model);
+  const Model& m = *sm;
+  const Lay& L = c.lay;
+  const int warp = threadIdx.x / G_LANES;
+  Cx cx; cx.lane = threadIdx.x % G_LANES;
+  cx.mask = G_LANES == 32 ? 0xffffffffu : (((1u << G_LANES) - 1u) << (((threadIdx.x & 31) / G_LANES) * G_LANES));
+  // CTA composition: the first n_single CTAs carry ONE env each (the most expensive envs of the cost-sorted order run
+  // alone, at their own pace, and start first); the others carry ENVS_PER_CTA envs.  Spare warps of a single-env CTA
+  // exit here; the phase barriers count only the participating threads.
+  const int single = (int)blockIdx.x < n_single;
+  const int cnt = single ? 1 : ENVS_PER_CTA;
+  const int pos0 = single ? (int)blockIdx.x : n_single + ((int)blockIdx.x - n_single) * ENVS_PER_CTA;
+  if (warp >= cnt) return;
+  cx.cta_threads = cnt * G_LANES;
+  // Groups past the end of the batch shadow the last env (same inputs, same control flow, identical outputs) so that
+  // every thread of the CTA reaches the phase barriers inside physics_tick.
+  const int e_raw = pos0 + warp;                               // position in this step's cost-sorted order
+  const int e = c.perm[e_raw < c.n ? e_raw : c.n - 1];
+  float* w = (float*)(smem_raw + ((sizeof(Model) + 127) & ~(size_t)127)) + (size_t)warp * c.ws_stride;
+  float* row = c.state + (size_t)e * c.row;
+  for (int i = cx.lane; i < L.n_state; i += G_LANES) w[i] = row[i];
+  __syncwarp(cx.mask);
+  if (gym) env_prestep<G_LANES>(cx, m, L, w, obs + (size_t)e * m.obs_dim, reward + e, done + e);
+  for (int t = 0; t < n_ticks; t++) {
+    // acquire tick t of the IK reference (k_ik may still be running: programmatic dependent launch)
+    PHASE_T0();
+    if (cx.lane == 0) {              // one lane per group waits for the k_ik block that owns its env
+      const int want = flag_base + t + 1;
+      while (*(volatile int*)(c.ik_flags + e / IK_THREADS) < want) __nanosleep(100);
+      __threadfence();
+    }
+    PHASE(16);
+    cta_sync<true>(cx);
+    const float* tr = c.traj + (size_t)t * 21 * c.n + e;
+    for (int k = cx.lane; k < 21; k += G_LANES) w[L.jt + k] = __ldcg(tr + (size_t)k * c.n);
+    __syncwarp(cx.mask);
+    physics_tick<G_LANES, true>(cx, m, L, w, w + L.jt, w + L.jt + 7, w + L.jt + 14, c.tol, c.max_iter);
+  }
+  if (gym) env_poststep<G_LANES>(cx, m, L, w, info + (size_t)e * m.info_dim);
+  if (e_raw < c.n) for (int i = cx.lane; i < L.n_state; i += G_LANES) row[i] = w[i];
+  TL_END(2);
+}
+
+__global__ void __launch_bounds__(CTA_THREADS, (CTA_THREADS > 256 ? 1 : 2))
+k_reset(DevCtx c, const float* __restrict__ ctx, const uint8_t* __restrict__ mask, float* __restrict__ obs) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Model* sm = (Model*)smem_raw;
+  stage_model(sm, c.model);
+  const Model& m = *sm;
+  const Lay& L = c.lay;
+  const int warp = threadIdx.x / G_LANES;
+  Cx cx; cx.lane = threadIdx.x % G_LANES;
+  cx.mask = G_LANES == 32 ? 0xffffffffu : (((1u << G_LANES) - 1u) << (((threadIdx.x & 31) / G_LANES) * G_LANES));
+  const int e = blockIdx.x * ENVS_PER_CTA + warp;
+  if (e >= c.n) return;
+  cx.cta_threads = CTA_THREADS;
+  if (mask && !mask[e]) return;
+  float* w = (float*)(smem_raw + ((sizeof(Model) + 127) & ~(size_t)127)) + (size_t)warp * c.ws_stride;
+  env_reset<G_LANES>(cx, m, L, w, (ctx && m.ctx_dim > 0) ? ctx + (size_t)e * m.ctx_dim : nullptr, c.tol, c.max_iter);
+  float* row = c.state + (size_t)e * c.row;
+  for (int i = cx.lane; i < L.n_state; i += G_LANES) row[i] = w[i];
+  const int n = c.n;
+  for (int k = cx.lane; k < 7; k += G_LANES) {
+    c.ik.q[k * n + e] = 0; c.ik.des[k * n + e] = 0;
+    c.ik.jt[k * n + e] = (float)m.ctrl[D3C_INIT_QPOS + k]; c.ik.jt[(7 + k) * n + e] = 0; c.ik.jt[(14 + k) * n + e] = 0;
+  }
+  if (cx.lane == 0) {
+    c.ik.valid[e] = 0;
+    if (obs) task_obs(m, L, w, obs + (size_t)e * m.obs_dim);
+  }
+}
+
+__global__ void k_robot_state(DevCtx c, float* __restrict__ tcp) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= c.n) return;
+  const float* row = c.state + (size_t)e * c.row;
+  for (int k = 0; k < 3; k++) tcp[(size_t)e * 3 + k] = row[c.lay.tcp + k];
+}
+
+
+// ------------------------------------------------------------------------------------------------ host launchers
+int d3il_env_grid(int n, int n_single) { return n_single + (n - n_single + ENVS_PER_CTA - 1) / ENVS_PER_CTA; }
+
+cudaError_t d3il_env_kernels_configure(size_t smem_bytes) {
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(k_env, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)) != cudaSuccess) return e;
+  // an SM keeps the L1/shared carve-out of whatever is resident: every kernel of the step asks for the maximum shared
+  // carve-out so k_env CTAs can join SMs that still run a k_ik warp
+  if ((e = cudaFuncSetAttribute(k_env, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_reset, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
+cudaError_t d3il_launch_env(const DevCtx& c, int n_single, int n_ticks, int gym, int flag_base, float* obs, float* reward, uint8_t* done, float* info,
+                            size_t smem_bytes, cudaStream_t s, bool programmatic) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(d3il_env_grid(c.n, n_single)); cfg.blockDim = dim3(CTA_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = programmatic ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, k_env, c, n_single, n_ticks, gym, flag_base, obs, reward, done, info);
+}
+
+void d3il_launch_reset(const DevCtx& c, const float* ctx, const uint8_t* mask, float* obs, size_t smem_bytes, cudaStream_t s) {
+  k_reset<<<(c.n + ENVS_PER_CTA - 1) / ENVS_PER_CTA, CTA_THREADS, smem_bytes, s>>>(c, ctx, mask, obs);
+}
+
+void d3il_launch_robot_state(const DevCtx& c, float* tcp, cudaStream_t s) { k_robot_state<<<(c.n + 127) / 128, 128, 0, s>>>(c, tcp); }
+
+#ifdef D3IL_PHASE_TIMING
+int d3il_debug_timeline_env(unsigned long long* out) { return cudaMemcpyFromSymbol(out, g_tl, sizeof(unsigned long long) * 4 * 4096) == cudaSuccess ? 0 : -2; }
+int d3il_debug_phase_cycles_env(unsigned long long* out24) { return cudaMemcpyFromSymbol(out24, g_phase_cycles, sizeof(unsigned long long) * 24) == cudaSuccess ? 0 : -2; }
+#endif

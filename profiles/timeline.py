@@ -12,9 +12,16 @@ des = torch.cat([env.robot_state().clone(), torch.tensor([0.0, 1.0, 0.0, 0.0], d
 nwarm = int(sys.argv[2]) if len(sys.argv) > 2 else 39
 g = torch.Generator(device='cuda').manual_seed(0)
 lo, hi = torch.tensor([0.3, -0.45], device='cuda'), torch.tensor([0.8, 0.45], device='cuda')
+ctx_t = torch.tensor(ctxs[np.arange(n) % 60], dtype=torch.float32, device='cuda')
+tcp0 = env.robot_state().clone(); ids = torch.arange(n, device='cuda')
+stagger = len(sys.argv) > 3
 for k in range(nwarm):
     des[:, :2] = torch.minimum(torch.maximum(des[:, :2] + torch.rand(n, 2, generator=g, device='cuda') * 0.02 - 0.01, lo), hi)
-    env.step(des)
+    obs, rew, done, info = env.step(des)
+    if stagger:
+        force = ((ids % 400 == k % 400) | done.bool()).to(torch.uint8)
+        env.reset(ctx_t, force)
+        des[:, :3] = torch.where(force.bool().unsqueeze(1), tcp0, des[:, :3])
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); env.step(des); e1.record(); torch.cuda.synchronize()
