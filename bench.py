@@ -178,11 +178,14 @@ def run_gpu(args):
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     # synthetic action stream, resident in HBM before the timed region: deltas ~ U(-0.01, 0.01)^2 per env per step
     pool_len = 64
-    deltas = (torch.rand(pool_len, n, 2, generator=gen, device=dev) * 0.02 - 0.01)
+    deltas = (torch.rand(pool_len, n, 2, generator=gen, device=dev) * 0.02 - 0.01)      # host-path (e2e) stream
+
+    def next_delta():
+        return torch.rand(n, 2, generator=gen, device=dev) * 0.02 - 0.01
     returns = torch.zeros(n, 3, device=dev)          # per-env episode result rows (success, mode, mean_distance)
 
     def one_step(k):
-        des[:, :2] = torch.minimum(torch.maximum(des[:, :2] + deltas[k % pool_len], lo), hi)
+        des[:, :2] = torch.minimum(torch.maximum(des[:, :2] + next_delta(), lo), hi)
         obs, rew, done, info = env.step(des)
         # episode bookkeeping + auto-reset of finished envs (masked reset kernel; desired pose snaps back to the start pose)
         returns.copy_(torch.where(done.bool().unsqueeze(1), info[:, :3], returns))
@@ -195,7 +198,7 @@ def run_gpu(args):
     ep_len = env.max_steps_per_episode
     ids = torch.arange(n, device=dev)
     for k in range(ep_len if not args.no_preroll else 0):
-        des[:, :2] = torch.minimum(torch.maximum(des[:, :2] + deltas[k % pool_len], lo), hi)
+        des[:, :2] = torch.minimum(torch.maximum(des[:, :2] + next_delta(), lo), hi)
         env.step(des)
         force = (ids % ep_len == k).to(torch.uint8)
         env.reset(ctx_t, force)

@@ -166,7 +166,8 @@ extern "C" int d3il_create(d3il_env** out, const void* blob, size_t nbytes, int 
   CK(cudaFuncSetAttribute(k_ik, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CK(cudaFuncSetAttribute(k_sched, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   // the most expensive envs of each step run one per CTA (cost-sorted order, see k_sched / k_env)
-  h->n_single = (G_LANES == 32 && n_envs >= 512) ? 16 : 0;
+  // (more single-env CTAs shorten the tail CTA but add CTAs; at 4096 envs = 585 x 7 + 1 exactly one is free)
+  h->n_single = (G_LANES == 32 && n_envs >= 512) ? 1 + (n_envs - 1) % ENVS_PER_CTA : 0;
   if (const char* ev = getenv("D3IL_N_SINGLE")) { h->n_single = atoi(ev); if (h->n_single < 0 || h->n_single > n_envs / 2 || G_LANES != 32) h->n_single = 0; }
   // staging for the host-buffer entry points
   const Model& m = h->m;
