@@ -313,6 +313,10 @@ DEVFN void env_reset(const Cx& cx, const Model& m, const Lay& L, real* w, const 
   real jq[D3_NARM], jql[D3_NARM], jqd[D3_NARM];
   for (int k = 0; k < D3_NARM; k++) { jq[k] = m.ctrl[D3C_INIT_QPOS + k]; jql[k] = 0; jqd[k] = 0; }
   physics_tick<G, false>(cx, m, L, w, jq, jql, jqd, tol, max_iter);
+  // scheduling hint: the first env steps after a reset resolve the deep spawn penetration (16 contacts, many Newton
+  // iterations) and are among the most expensive ones, so a fresh env sorts to the front of the next step's order
+  LANES(z, 1) w[L.misc + ST_COST_ITERS] = 400;
+  gsync<G>(cx);
 }
 
 // pre-substep half of GymEnvWrapper.step (gym_env_wrapper.py:67-90): open fingers, Cartesian mode, sample obs /
