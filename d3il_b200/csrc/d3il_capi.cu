@@ -160,14 +160,18 @@ extern "C" int d3il_create(d3il_env** out, const void* blob, size_t nbytes, int 
   CK(cudaMalloc(&d.ik_flags, (size_t)h->n_ik_blocks * sizeof(int)));
   CK(cudaMalloc(&d.perm, (size_t)n_envs * sizeof(int)));
   CK(cudaMemset(d.ik_flags, 0, (size_t)h->n_ik_blocks * sizeof(int)));
-  h->smem_bytes = ((sizeof(Model) + 127) & ~(size_t)127) + (size_t)ENVS_PER_CTA * d.ws_stride * sizeof(float);
+  // envs per CTA: ENVS_PER_CTA (two CTAs per SM for the small scenes), fewer when the per-env workspace is large (Sorting-4/6)
+  const size_t model_bytes = (sizeof(Model) + 127) & ~(size_t)127, env_bytes = (size_t)d.ws_stride * sizeof(float);
+  d.epc = ENVS_PER_CTA;
+  while (d.epc > 1 && model_bytes + d.epc * env_bytes > 227 * 1024) d.epc--;
+  h->smem_bytes = model_bytes + (size_t)d.epc * env_bytes;
   if (h->smem_bytes > 227 * 1024) { g_err = "d3il_create: scene workspace does not fit in shared memory"; delete h; return -1; }
   CK(d3il_env_kernels_configure(h->smem_bytes));
   CK(cudaFuncSetAttribute(k_ik, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CK(cudaFuncSetAttribute(k_sched, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   // the most expensive envs of each step run one per CTA (cost-sorted order, see k_sched / k_env)
   // (more single-env CTAs shorten the tail CTA but add CTAs; at 4096 envs = 585 x 7 + 1 exactly one is free)
-  h->n_single = (G_LANES == 32 && n_envs >= 512) ? 1 + (n_envs - 1) % ENVS_PER_CTA : 0;
+  h->n_single = (G_LANES == 32 && n_envs >= 512) ? 1 + (n_envs - 1) % d.epc : 0;
   if (const char* ev = getenv("D3IL_N_SINGLE")) { h->n_single = atoi(ev); if (h->n_single < 0 || h->n_single > n_envs / 2 || G_LANES != 32) h->n_single = 0; }
   // staging for the host-buffer entry points
   const Model& m = h->m;

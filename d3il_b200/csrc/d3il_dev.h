@@ -28,6 +28,7 @@ struct DevCtx {
   Lay lay;
   float* state;           // [n][row]
   int row, n, ws_stride;
+  int epc;                // envs (warps) per CTA: ENVS_PER_CTA unless the scene's workspace needs more shared memory per env
   DevIk ik;
   float* traj;            // [ticks][21][n]
   int* ik_flags;          // [n_ik_blocks] ticks published by each k_ik block (monotonic: launch_id * 64 + tick + 1)
@@ -41,7 +42,7 @@ cudaError_t d3il_launch_env(const DevCtx& c, int n_single, int n_ticks, int gym,
                             size_t smem_bytes, cudaStream_t s, bool programmatic);
 void d3il_launch_reset(const DevCtx& c, const float* ctx, const uint8_t* mask, float* obs, size_t smem_bytes, cudaStream_t s);
 void d3il_launch_robot_state(const DevCtx& c, float* tcp, cudaStream_t s);
-int d3il_env_grid(int n, int n_single);
+int d3il_env_grid(const DevCtx& c, int n_single);
 
 #ifdef D3IL_PHASE_TIMING
 int d3il_debug_timeline_env(unsigned long long* out4096x4);     // k_env CTA records (the k_ik ones live in d3il_capi.cu)

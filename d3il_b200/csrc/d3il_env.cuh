@@ -208,9 +208,64 @@ DEVFN void task_obs(const Model& m, const Lay& L, const real* w, float* obs) {
     obs[0] = (float)w[L.tcp]; obs[1] = (float)w[L.tcp + 1];
     obs[2] = (float)b1[0]; obs[3] = (float)b1[1]; obs[4] = (float)tan_yaw(b1 + 3);
     obs[5] = (float)b2[0]; obs[6] = (float)b2[1]; obs[7] = (float)tan_yaw(b2 + 3);
+  } else if (m.task_id == D3T_SORTING) {      // sorting.py:308-390
+    obs[0] = (float)w[L.tcp]; obs[1] = (float)w[L.tcp + 1];
+    for (int i = 0; i < m.nobj; i++) {
+      const real* b = w + L.qpos + D3_NROB + 7 * i;
+      obs[2 + 3 * i] = (float)b[0]; obs[3 + 3 * i] = (float)b[1]; obs[4 + 3 * i] = (float)tan_yaw(b + 3);
+    }
+  } else if (m.task_id == D3T_ALIGNING) {     // aligning.py:205-235
+    const real* b = w + L.qpos + D3_NROB;
+    for (int k = 0; k < 3; k++) obs[k] = (float)w[L.tcp + k];
+    for (int k = 0; k < 7; k++) { obs[3 + k] = (float)b[k]; obs[10 + k] = (float)w[L.extra + k]; }
   } else {
     obs[0] = (float)w[L.tcp]; obs[1] = (float)w[L.tcp + 1];
   }
+}
+
+// ---- Sorting (sorting.py:460-543).  misc TASK0 = mode_step, TASK1 = bit i set <=> mode[i] == 0 (red), TASK2 = min_inds mask.
+// Slots are (red_1..3, blue_1..3); slots absent from the scene read the constant pose of the model's last body.
+DEVFN void sorting_slot_xy(const Model& m, const Lay& L, const real* w, int slot, real* xy) {
+  int half = m.nobj / 2, col = slot / 3, idx = slot - 3 * col;
+  if (idx < half) { const real* b = w + L.qpos + D3_NROB + 7 * (col * half + idx); xy[0] = b[0]; xy[1] = b[1]; }
+  else { xy[0] = (real)m.taskp[11]; xy[1] = (real)m.taskp[12]; }
+}
+DEVFN int sorting_in_bin(const Model& m, int col, const real* xy) {
+  const tab_t* T = m.taskp;
+  return xy[0] > (real)T[4 + 2 * col] && xy[0] < (real)T[5 + 2 * col] && xy[1] > (real)T[8] && xy[1] < (real)T[9];
+}
+DEVFN int sorting_all_binned(const Model& m, const Lay& L, const real* w) {
+  int half = m.nobj / 2;
+  for (int i = 0; i < m.nobj; i++) if (!sorting_in_bin(m, i / half, w + L.qpos + D3_NROB + 7 * i)) return 0;
+  return 1;
+}
+DEVFN int sorting_check_mode(const Model& m, const Lay& L, real* w) {
+  int step = (int)w[L.misc + ST_TASK0], zero = (int)w[L.misc + ST_TASK1], mins = (int)w[L.misc + ST_TASK2];
+  if (step <= 5) {
+    real best = 0, bxy[2] = {0, 0}; int bi = -1;
+    for (int s = 0; s < 6; s++) {
+      real xy[2]; sorting_slot_xy(m, L, w, s, xy);
+      real dx = xy[0] - (real)m.taskp[2 * (s / 3)], dy = xy[1] - (real)m.taskp[2 * (s / 3) + 1];
+      real d = ((mins >> s) & 1) ? (real)100000 : sqrt(dx * dx + dy * dy);
+      if (bi < 0 || d < best) { best = d; bi = s; bxy[0] = xy[0]; bxy[1] = xy[1]; }
+    }
+    if (sorting_in_bin(m, bi / 3, bxy)) {
+      if (bi < 3) zero |= 1 << step;
+      step++; mins |= 1 << bi;
+    }
+    w[L.misc + ST_TASK0] = (real)step; w[L.misc + ST_TASK1] = (real)zero; w[L.misc + ST_TASK2] = (real)mins;
+  }
+  int code = 0;
+  for (int i = 0; i < m.nobj; i++) if (!((zero >> i) & 1)) code |= 1 << (7 - i);
+  return code;
+}
+
+// ---- Aligning (aligning.py:21-30,295-352)
+DEVFN void aligning_dists(const Model& m, const Lay& L, const real* w, real* pd, real* rd) {
+  const real *b = w + L.qpos + D3_NROB, *t = w + L.extra;
+  *pd = dist3(b, t);
+  real d = absr(b[3] * t[3] + b[4] * t[4] + b[5] * t[5] + b[6] * t[6]);
+  *rd = 2 * acos(d > 1 ? (real)1 : d) * (real)0.3183098861837907;
 }
 
 DEVFN void pushing_dists(const Model& m, const Lay& L, const real* w, real* d4) {
@@ -227,6 +282,15 @@ DEVFN int task_early_term(const Model& m, const Lay& L, real* w) {
     if ((d[0] <= md && d[3] <= md) || (d[1] <= md && d[2] <= md)) { w[L.misc + ST_TERM] = 1; return 1; }
     return 0;
   }
+  if (m.task_id == D3T_SORTING) {
+    if (sorting_all_binned(m, L, w)) { w[L.misc + ST_TERM] = 1; return 1; }
+    return 0;
+  }
+  if (m.task_id == D3T_ALIGNING) {
+    real pd, rd; aligning_dists(m, L, w, &pd, &rd);
+    if (pd <= (real)m.taskp[0] && rd <= (real)m.taskp[1]) { w[L.misc + ST_TERM] = 1; return 1; }
+    return 0;
+  }
   int success = w[L.tcp + 1] > (real)m.taskp[3];
   if (success || w[L.misc + ST_OBST] != 0) { if (success) w[L.misc + ST_TASK1] = 1; w[L.misc + ST_TERM] = 1; return 1; }
   return 0;
@@ -239,6 +303,7 @@ DEVFN real task_reward(const Model& m, const Lay& L, const real* w) {
     real dx = w[L.tcp] - b1[0], dy = w[L.tcp + 1] - b1[1];
     return -(sqrt(dx * dx + dy * dy) + dist3(b1, g1));
   }
+  if (m.task_id == D3T_ALIGNING) { real pd, rd; aligning_dists(m, L, w, &pd, &rd); return -rd - (real)3.5 * pd; }
   return 0;
 }
 
@@ -256,6 +321,16 @@ DEVFN void task_post(const Model& m, const Lay& L, real* w, float* info) {
       if (fv == 0 && visit == 3) mode = 0; else if (fv == 3 && visit == 0) mode = 1; else if (fv == 1 && visit == 2) mode = 2; else if (fv == 2 && visit == 1) mode = 3;
     }
     info[0] = (float)success; info[1] = (float)mode; info[2] = (float)((real)0.5 * (minr(d[0], d[1]) + minr(d[2], d[3]))); info[3] = (float)w[L.misc + ST_STATUS];
+  } else if (m.task_id == D3T_SORTING) {      // info: success, packed mode, mode_step, status
+    int success = task_early_term(m, L, w);
+    int code = sorting_check_mode(m, L, w);
+    info[0] = (float)success; info[1] = (float)code; info[2] = (float)w[L.misc + ST_TASK0]; info[3] = (float)w[L.misc + ST_STATUS];
+  } else if (m.task_id == D3T_ALIGNING) {     // info: success, mode (0 inside / 1 outside push), mean_distance, status
+    int success = task_early_term(m, L, w);
+    real pd, rd; aligning_dists(m, L, w, &pd, &rd);
+    const real* b = w + L.qpos + D3_NROB;
+    real dx = b[0] - w[L.tcp], dy = b[1] - w[L.tcp + 1];
+    info[0] = (float)success; info[1] = sqrt(dx * dx + dy * dy) < (real)m.taskp[2] ? 0.f : 1.f; info[2] = (float)((real)0.5 * (pd + rd)); info[3] = (float)w[L.misc + ST_STATUS];
   } else {
     real x = w[L.tcp], y = w[L.tcp + 1];
     const tab_t* T = m.taskp;
@@ -291,7 +366,8 @@ DEVFN void env_reset(const Cx& cx, const Model& m, const Lay& L, real* w, const 
     real* q = w + L.qpos + m.l_qadr[D3_NROB + i];
     for (int k = 0; k < 7; k++) q[k] = Lk[2 + k];
   }
-  LANES(z, 1) { w[L.misc + ST_GRIP_SET] = (real)0.001; w[L.misc + ST_TASK0] = -1; }
+  LANES(z, 1) { w[L.misc + ST_GRIP_SET] = (real)0.001; if (m.task_id == D3T_PUSHING) w[L.misc + ST_TASK0] = -1; }
+  LANES(k, m.nextra) w[L.extra + k] = ctx ? (real)ctx[7 * m.nobj + k] : (real)m.taskp[3 + k];      // joint-less target body (Aligning)
   gsync<G>(cx);
   kinematics<G>(cx, m, L, w);
   LANES(z, 1) {

@@ -39,8 +39,8 @@ k_env(DevCtx c, int n_single, int n_ticks, int gym, int flag_base, float* __rest
   // alone, at their own pace, and start first); the others carry ENVS_PER_CTA envs.  Spare warps of a single-env CTA
   // exit here; the phase barriers count only the participating threads.
   const int single = (int)blockIdx.x < n_single;
-  const int cnt = single ? 1 : ENVS_PER_CTA;
-  const int pos0 = single ? (int)blockIdx.x : n_single + ((int)blockIdx.x - n_single) * ENVS_PER_CTA;
+  const int cnt = single ? 1 : c.epc;
+  const int pos0 = single ? (int)blockIdx.x : n_single + ((int)blockIdx.x - n_single) * c.epc;
   if (warp >= cnt) return;
   cx.cta_threads = cnt * G_LANES;
   // Groups past the end of the batch shadow the last env (same inputs, same control flow, identical outputs) so that
@@ -82,9 +82,9 @@ k_reset(DevCtx c, const float* __restrict__ ctx, const uint8_t* __restrict__ mas
   const int warp = threadIdx.x / G_LANES;
   Cx cx; cx.lane = threadIdx.x % G_LANES;
   cx.mask = G_LANES == 32 ? 0xffffffffu : (((1u << G_LANES) - 1u) << (((threadIdx.x & 31) / G_LANES) * G_LANES));
-  const int e = blockIdx.x * ENVS_PER_CTA + warp;
+  const int e = blockIdx.x * c.epc + warp;
   if (e >= c.n) return;
-  cx.cta_threads = CTA_THREADS;
+  cx.cta_threads = c.epc * G_LANES;
   if (mask && !mask[e]) return;
   float* w = (float*)(smem_raw + ((sizeof(Model) + 127) & ~(size_t)127)) + (size_t)warp * c.ws_stride;
   env_reset<G_LANES>(cx, m, L, w, (ctx && m.ctx_dim > 0) ? ctx + (size_t)e * m.ctx_dim : nullptr, c.tol, c.max_iter);
@@ -110,7 +110,7 @@ __global__ void k_robot_state(DevCtx c, float* __restrict__ tcp) {
 
 
 // ------------------------------------------------------------------------------------------------ host launchers
-int d3il_env_grid(int n, int n_single) { return n_single + (n - n_single + ENVS_PER_CTA - 1) / ENVS_PER_CTA; }
+int d3il_env_grid(const DevCtx& c, int n_single) { return n_single + (c.n - n_single + c.epc - 1) / c.epc; }
 
 cudaError_t d3il_env_kernels_configure(size_t smem_bytes) {
   cudaError_t e;
@@ -125,7 +125,7 @@ cudaError_t d3il_env_kernels_configure(size_t smem_bytes) {
 cudaError_t d3il_launch_env(const DevCtx& c, int n_single, int n_ticks, int gym, int flag_base, float* obs, float* reward, uint8_t* done, float* info,
                             size_t smem_bytes, cudaStream_t s, bool programmatic) {
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(d3il_env_grid(c.n, n_single)); cfg.blockDim = dim3(CTA_THREADS); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = s;
+  cfg.gridDim = dim3(d3il_env_grid(c, n_single)); cfg.blockDim = dim3(c.epc * G_LANES); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -134,7 +134,7 @@ cudaError_t d3il_launch_env(const DevCtx& c, int n_single, int n_ticks, int gym,
 }
 
 void d3il_launch_reset(const DevCtx& c, const float* ctx, const uint8_t* mask, float* obs, size_t smem_bytes, cudaStream_t s) {
-  k_reset<<<(c.n + ENVS_PER_CTA - 1) / ENVS_PER_CTA, CTA_THREADS, smem_bytes, s>>>(c, ctx, mask, obs);
+  k_reset<<<(c.n + c.epc - 1) / c.epc, c.epc * G_LANES, smem_bytes, s>>>(c, ctx, mask, obs);
 }
 
 void d3il_launch_robot_state(const DevCtx& c, float* tcp, cudaStream_t s) { k_robot_state<<<(c.n + 127) / 128, 128, 0, s>>>(c, tcp); }

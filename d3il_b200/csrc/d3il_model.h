@@ -16,9 +16,9 @@ static inline bool d3il_build_model(const void* blob, size_t nbytes, Model& m, L
   if (nbytes < 4 * D3SC_HDR_INTS || h[0] != D3SC_MAGIC || h[1] != 1) { err = "not a D3SC v1 scene blob"; return false; }
   memset(&m, 0, sizeof(m));
   m.task_id = h[2]; m.nlink = h[3]; m.nobj = h[4]; m.nq = h[5]; m.nv = h[6]; m.ngeom = h[7]; m.npair = h[8]; m.n_substeps = h[9];
-  m.max_steps = h[10]; m.obs_dim = h[11]; m.act_dim = h[12]; m.ctx_dim = h[13]; m.info_dim = h[14]; m.ctrl_kind = h[15]; m.ntaskp = h[16];
-  if (m.nlink > D3_MAXLINK || m.nq > D3_MAXQ || m.nv > D3_MAXV || m.ngeom > D3_MAXGEOM || m.npair > D3_MAXPAIR || m.ntaskp > 32) { err = "scene exceeds compiled table sizes"; return false; }
-  if (m.task_id != D3T_AVOIDING && m.task_id != D3T_PUSHING) { err = "task not supported by this build of the CUDA path"; return false; }
+  m.max_steps = h[10]; m.obs_dim = h[11]; m.act_dim = h[12]; m.ctx_dim = h[13]; m.info_dim = h[14]; m.ctrl_kind = h[15]; m.ntaskp = h[16]; m.nextra = h[17];
+  if (m.nlink > D3_MAXLINK || m.nq > D3_MAXQ || m.nv > D3_MAXV || m.ngeom > D3_MAXGEOM || m.npair > D3_MAXPAIR || m.ntaskp > 32 || m.nextra < 0 || m.nextra > 8) { err = "scene exceeds compiled table sizes"; return false; }
+  if (m.task_id != D3T_AVOIDING && m.task_id != D3T_PUSHING && m.task_id != D3T_ALIGNING && m.task_id != D3T_SORTING) { err = "task not supported by this build of the CUDA path"; return false; }
   size_t need = 4 * D3SC_HDR_INTS + 8 * ((size_t)m.nlink * D3_LINK_W + (size_t)m.ngeom * D3_GEOM_W + (size_t)m.npair * D3_PAIR_W + D3_CTRL_W + m.ntaskp);
   if (need != nbytes) { err = "scene blob size mismatch"; return false; }
   const double* p = (const double*)((const char*)blob + 4 * D3SC_HDR_INTS);
@@ -92,8 +92,9 @@ static inline bool d3il_build_model(const void* blob, size_t nbytes, Model& m, L
   { int e = 0; for (int i = 0; i < 24; i++) for (int j = 0; j <= i; j++) { m.tri_i[e] = (unsigned char)i; m.tri_j[e] = (unsigned char)j; e++; } }
   m.nblk = 0;
   for (int d = 0; d < m.nv; d++) if (m.d_bs[d] == d) { if (m.nblk >= 8) { err = "too many kinematic trees"; return false; } m.blk_s[m.nblk] = d; m.blk_e[m.nblk] = m.d_be[d]; m.nblk++; }
-  if (m.nv > 24) { err = "nv > 24 needs the long-row factorisation path (not built yet)"; return false; }
-  m.maxcon = conmax < 20 ? ((conmax + 3) & ~3) : 20;
+  // contact budget: 4 per free body resting on a support + 12 for transients (deep spawn penetration touches two supports,
+  // box-box / rod contacts); overflow raises status bit 2, never drops silently
+  { int cap = 4 * m.nobj + 12; m.maxcon = ((conmax < cap ? conmax : cap) + 3) & ~3; }
   m.maxrow = 3 * m.maxcon + 4;
   d3il_layout(m, L);
   m.ws_floats = L.total;
@@ -101,7 +102,7 @@ static inline bool d3il_build_model(const void* blob, size_t nbytes, Model& m, L
 }
 
 // ---- flat fp64 state, identical layout to oracle/d3il_oracle.c::d3o_get_state (nq + 2 nv + 60)
-static inline int d3il_state_dim(const Model& m) { return m.nq + 2 * m.nv + 60; }
+static inline int d3il_state_dim(const Model& m) { return m.nq + 2 * m.nv + 60 + m.nextra; }
 
 template <class T>
 static inline void d3il_pack_state(const Model& m, const Lay& L, const T* w /*workspace/state row*/, const IkState& ik, double* out) {
@@ -121,6 +122,7 @@ static inline void d3il_pack_state(const Model& m, const Lay& L, const T* w /*wo
   for (int k = 0; k < 4; k++) *p++ = w[L.misc + ST_TASK0 + k];
   for (int k = 0; k < 3; k++) *p++ = w[L.misc + ST_COST_ITERS + k];     // diagnostics only (the oracle keeps zeros here)
   *p++ = 0;
+  for (int k = 0; k < m.nextra; k++) *p++ = w[L.extra + k];
 }
 template <class T>
 static inline void d3il_unpack_state(const Model& m, const Lay& L, T* w, IkState& ik, const double* in) {
@@ -139,4 +141,6 @@ static inline void d3il_unpack_state(const Model& m, const Lay& L, T* w, IkState
   w[L.misc + ST_CTRL_MODE] = (T)*p++; w[L.misc + ST_GRIP_SET] = (T)*p++; w[L.misc + ST_GRASP] = (T)*p++; w[L.misc + ST_STEP] = (T)*p++;
   w[L.misc + ST_TERM] = (T)*p++; w[L.misc + ST_STATUS] = (T)*p++; w[L.misc + ST_OBST] = (T)*p++;
   for (int k = 0; k < 4; k++) w[L.misc + ST_TASK0 + k] = (T)*p++;
+  p += 4;
+  for (int k = 0; k < m.nextra; k++) w[L.extra + k] = (T)*p++;
 }

@@ -25,7 +25,7 @@ GEOM_TYPE_ID = {"plane": GEOM_PLANE, "sphere": GEOM_SPHERE, "cylinder": GEOM_CYL
 
 HDR_FIELDS = [
     "magic", "version", "task_id", "nlink", "nobj", "nq", "nv", "ngeom", "npair", "n_substeps",
-    "max_steps", "obs_dim", "act_dim", "ctx_dim", "info_dim", "ctrl_kind", "ntaskp",
+    "max_steps", "obs_dim", "act_dim", "ctx_dim", "info_dim", "ctrl_kind", "ntaskp", "nextra",
 ]
 
 # CTRL section offsets
@@ -68,7 +68,7 @@ class Scene:
     def pack(self) -> bytes:
         hdr = [0] * HDR_INTS
         for i, k in enumerate(HDR_FIELDS):
-            hdr[i] = int(self.header[k])
+            hdr[i] = int(self.header.get(k, 0))
         out = struct.pack(f"<{HDR_INTS}i", *hdr)
         for a in (self.link, self.geom, self.pair, self.ctrl, self.task):
             out += np.ascontiguousarray(a, dtype="<f8").tobytes()

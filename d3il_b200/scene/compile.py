@@ -213,6 +213,49 @@ def task_spec(task, ref):
             # l1_y, l2_y, l3_y, goal_y, l1_x, l2_top_x, l2_bottom_x, l3_top_x, l3_mid_x, l3_bottom_x  (avoiding.py:94-105)
             taskp=[y1, y1 + dy, y1 + 2 * dy, y1 + 2.5 * dy, mid, mid - off, mid + off, mid - 2 * off, mid, mid + 2 * off],
         )
+    if task.startswith("sorting"):   # envs/gym_sorting_env/.../objects/sorting_objects.py:13-220, sorting.py:193-306
+        k = int(task.split("_")[1])
+        assert k in (2, 4, 6)
+        box = lambda n: prim(n, "box", [0.03, 0.03, 0.03], [0.5, -0.1, 0.0], [0, 1, 0, 0], mass=0.05)
+        wall = lambda n, pos, size: prim(n, "box", size, pos, [0, 1, 0, 0], mass=0.05, static=True)
+        objs = [box(f"red_{i + 1}") for i in range(k // 2)] + [box(f"blue_{i + 1}") for i in range(k // 2)]
+        objs += [
+            wall("target_box_1", [0.4, 0.41, 0.0], [0.1, 0.01, 0.1]), wall("target_box_2", [0.3, 0.32, 0.0], [0.005, 0.1, 0.1]),
+            wall("target_box_3", [0.5, 0.32, 0.0], [0.005, 0.1, 0.1]), wall("target_box_4", [0.4, 0.22, 0.0], [0.1, 0.005, 0.1]),
+            wall("target_box_5", [0.625, 0.41, 0.0], [0.1, 0.01, 0.1]), wall("target_box_6", [0.525, 0.32, 0.0], [0.005, 0.1, 0.1]),
+            wall("target_box_7", [0.725, 0.32, 0.0], [0.005, 0.1, 0.1]), wall("target_box_8", [0.625, 0.22, 0.0], [0.1, 0.005, 0.1]),
+            # models/mj/common-objects/sorting/platform.xml, re-posed by SortingObject.mj_load (sorting_objects.py:15,73-79)
+            prim("platform", "box", [0.3, 0.3, 0.1], [0.5, -0.1, 0.0], [1, 0, 0, 0], mass=10, static=True, friction=[0.3, 0.001, 0.0001], priority=1),
+        ]
+        # absent boxes are read through mj_name2id = -1 -> the LAST body of the model, which is the joint-less
+        # `finger_joint2_tip_rb0` (robots are loaded last, mj_scene_parser.py:42): model.body_pos[-1] = its local offset
+        bogus = [0.0, -0.0085]
+        return dict(
+            rod=True, n_substeps=35, max_steps={2: 500, 4: 700, 6: 1200}[k], init_tcp=[0.525, -0.3, 0.25], ctrl_kind=0,
+            objects=objs, obs_dim=2 + 3 * k, act_dim=7, info_dim=4, spawn_z=0.05,
+            # red target xy, blue target xy, red bin x range, blue bin x range, bin y range, num_boxes, bogus xy  (sorting.py:300-306,477-536)
+            taskp=[0.4, 0.32, 0.625, 0.32, 0.3, 0.5, 0.525, 0.725, 0.22, 0.41, k, bogus[0], bogus[1]],
+        )
+    if task == "aligning":  # envs/gym_aligning_env/.../objects/aligning_objects.py:19-67, models/mj/common-objects/robot_push_box/*.xml
+        xml = os.path.join(ref, D3IL, "models/mj/common-objects/robot_push_box/robot_push_box.xml")
+        body = ET.parse(xml).getroot().find("worldbody").find("body")
+        parts = []
+        for g in body.findall("geom"):
+            prm = dict(M.GEOM_DEFAULTS)
+            if g.get("friction"):
+                prm["friction"] = [float(x) for x in g.get("friction").split()]
+            if g.get("priority"):
+                prm["priority"] = int(g.get("priority"))
+            parts.append(dict(type=g.get("type"), size=np.array([float(x) for x in g.get("size").split()]), pos=np.array([float(x) for x in g.get("pos").split()]),
+                              quat=np.array([1.0, 0, 0, 0]), mass=float(g.get("mass")), params=prm))
+        assert len(parts) == 5 and body.find("joint").get("type") == "free"
+        obj = dict(name="aligning_box", parts=parts, pos=np.array([0.6, 0.15, 0.0]), quat=np.array([1.0, 0, 0, 0]), static=False)
+        return dict(
+            rod=True, rod_hits_table=True, n_substeps=35, max_steps=400, init_tcp=[0.525, -0.35, 0.25], ctrl_kind=0,
+            objects=[obj], obs_dim=17, act_dim=7, info_dim=4, nextra=7,
+            # pos_min_dist, rot_min_dist, robot_box_dist (aligning.py:200-202); default target pose = XML pose of `target_box`
+            taskp=[0.018, 0.048, 0.051, 0.6, 0.15, 0.0, 1.0, 0.0, 0.0, 0.0],
+        )
     raise ValueError(f"task {task!r} not compiled yet")
 
 
@@ -261,7 +304,7 @@ def compile_task(task, ref):
     for o in objs:
         fake = M.Body(name=o["name"], pos=o["pos"], quat=o["quat"], parent=None)
         for prt in o["parts"]:
-            fake.geoms.append(M.Geom(name=o["name"] + ":geom", type=prt["type"], size=prt["size"], pos=prt["pos"], quat=prt["quat"], mass=prt["mass"], mesh=None, params=prt["params"]))
+            fake.geoms.append(M.Geom(name=o["name"] + ":geom", type=prt["type"], size=np.asarray(prt["size"], float), pos=prt["pos"], quat=prt["quat"], mass=prt["mass"], mesh=None, params=prt["params"]))
         M.finalize_inertia(fake)
         links.append(M.Link(name=o["name"], parent=-1, pos=o["pos"].copy(), quat=M.quat_normalize(o["quat"]), jtype=2, axis=np.zeros(3),
                             range=np.zeros(2), limited=False, damping=0.0, mass=fake.mass, ipos=fake.ipos, inertia=fake.inertia, members={o["name"]: (np.zeros(3), np.eye(3))}))
@@ -324,10 +367,12 @@ def compile_task(task, ref):
             pa, pb = a["params"], b["params"]
             if not ((pa["contype"] & pb["conaffinity"]) or (pb["contype"] & pa["conaffinity"])):
                 continue
-            if a["tag"] == 1 and a["link"] >= 0 and b["link"] == -1 and b["tag"] < 100:
-                continue                                        # rod vs table/support: unreachable at the harness' frozen tool height
-            if b["tag"] == 1 and a["link"] == -1 and a["tag"] < 100:
-                continue
+            if not spec.get("rod_hits_table"):
+                # rod vs static geoms: unreachable at the harness' frozen tool height (Avoiding's obstacle cylinders excepted)
+                if a["tag"] == 1 and a["link"] >= 0 and b["link"] == -1 and (b["tag"] < 100 or task != "avoiding"):
+                    continue
+                if b["tag"] == 1 and a["link"] == -1 and (a["tag"] < 100 or task != "avoiding"):
+                    continue
             # order by geom type like mj_collideGeoms (lower type id first)
             g1, g2 = (i, j) if B.GEOM_TYPE_ID[a["type"]] <= B.GEOM_TYPE_ID[b["type"]] else (j, i)
             condim, fr5, solref, solimp, margin, gap = mix_params(geoms[g1]["params"], geoms[g2]["params"])
@@ -395,9 +440,10 @@ def compile_task(task, ref):
     ctrl[B.C_INIT_TCP: B.C_INIT_TCP + 3] = spec["init_tcp"]
     ctrl[179] = np.trace(Mq0) / nv                               # stat.meaninertia
 
-    header = dict(magic=B.MAGIC, version=B.VERSION, task_id=B.TASK_IDS[task], nlink=nlink, nobj=nobj, nq=nq, nv=nv, ngeom=len(geoms),
+    header = dict(magic=B.MAGIC, version=B.VERSION, task_id=B.TASK_IDS[task.split("_")[0]], nlink=nlink, nobj=nobj, nq=nq, nv=nv, ngeom=len(geoms),
                   npair=len(pairs), n_substeps=spec["n_substeps"], max_steps=spec["max_steps"], obs_dim=spec["obs_dim"], act_dim=spec["act_dim"],
-                  ctx_dim=7 * nobj, info_dim=spec["info_dim"], ctrl_kind=spec["ctrl_kind"], ntaskp=len(spec["taskp"]))
+                  ctx_dim=7 * nobj + spec.get("nextra", 0), info_dim=spec["info_dim"], ctrl_kind=spec["ctrl_kind"], ntaskp=len(spec["taskp"]),
+                  nextra=spec.get("nextra", 0))
     scene = B.Scene(header, link_tab, geom_tab, pair_tab, ctrl, np.array(spec["taskp"], float))
     report = dict(
         task=task, header=header, links=[L.name for L in links], link_mass=[L.mass for L in links],
@@ -418,13 +464,33 @@ def export_contexts(ref, out_dir):
     np.save(os.path.join(out_dir, "pushing_test_contexts.npy"), arr)
     raw = np.array([[*r, *q, *g, *q2] for r, q, g, q2 in c], dtype=np.float64)
     np.save(os.path.join(out_dir, "pushing_test_contexts_raw.npy"), raw)
+    # Aligning (aligning.py:109-123): box at [x, y, 0] + quat, then the target pose [tx, ty, 0] + quat (written to model.body_pos/quat)
+    c = pickle.load(open(os.path.join(ref, "environments/dataset/data/aligning/test_contexts.pkl"), "rb"))
+    arr = np.array([[[p[0], p[1], 0.0, *q], [tp[0], tp[1], 0.0, *tq]] for p, q, tp, tq in c], dtype=np.float64)
+    np.save(os.path.join(out_dir, "aligning_test_contexts.npy"), arr)
+    # Sorting: `<k>_test_contexts.pkl` are NOT shipped -> drawn here from the six BlockContextManager boxes
+    # (sorting.py:52-74,88-119) with our own seeded generator; boxes are placed at z = 0.05 (sorting.py:130-181)
+    lows = np.array([[0.4, -0.15], [0.4, -0.05], [0.4, 0.05], [0.55, -0.15], [0.55, -0.05], [0.55, 0.05]])
+    highs = np.array([[0.5, -0.1], [0.5, 0.0], [0.5, 0.1], [0.65, -0.1], [0.65, 0.0], [0.65, 0.1]])
+    for k in (2, 4, 6):
+        rng = np.random.default_rng(42 + k)
+        out = np.zeros((60, k, 7))
+        for n in range(60):
+            xy = rng.uniform(lows, highs).astype(np.float32)
+            ang = rng.uniform(-90, 90, 6).astype(np.float32)
+            order = rng.permutation(6)
+            for i in range(k):
+                j = order[i]
+                a = float(ang[j]) * np.pi / 180
+                out[n, i] = [xy[j, 0], xy[j, 1], 0.05, np.cos(a / 2), 0.0, 0.0, np.sin(a / 2)]     # euler2quat([0, 0, a]) (geometric_transformation.py:73-89)
+        np.save(os.path.join(out_dir, f"sorting_{k}_contexts.npy"), out)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
     ap.add_argument("--out", default=os.path.join(os.path.dirname(__file__), "..", "scenes"))
-    ap.add_argument("--tasks", nargs="*", default=["avoiding", "pushing"])
+    ap.add_argument("--tasks", nargs="*", default=["avoiding", "pushing", "sorting_2", "sorting_4", "sorting_6", "aligning"])
     a = ap.parse_args()
     os.makedirs(a.out, exist_ok=True)
     for t in a.tasks:

@@ -41,14 +41,15 @@ enum { C_IK_ORIGIN = 0, C_IK_EE = 84, C_PGAIN_POS = 96, C_PGAIN_QUAT = 99, C_PGA
        C_JNT_SOLREF = 169, C_JNT_SOLIMP = 171, C_MEANINERTIA = 179 };
 
 enum { G_PLANE = 0, G_SPHERE = 2, G_CYLINDER = 5, G_BOX = 6 };
-enum { TASK_AVOIDING = 0, TASK_PUSHING = 1 };
+enum { TASK_AVOIDING = 0, TASK_PUSHING = 1, TASK_ALIGNING = 2, TASK_SORTING = 3 };
 
 #define MAXLINK 16
 #define MAXQ 64
 #define MAXV 48
 #define MAXGEOM 32
-#define MAXCON 64
-#define MAXEFC 256
+#define MAXCON 96
+#define MAXEFC 320
+#define MAXPAIR 128
 #define NARM 7
 #define NROB 9
 
@@ -68,10 +69,10 @@ typedef struct {
 
 typedef struct Env {
   /* model */
-  int task_id, nlink, nobj, nq, nv, ngeom, npair, n_substeps, max_steps, obs_dim, act_dim, ctx_dim, info_dim, ctrl_kind, ntaskp;
+  int task_id, nlink, nobj, nq, nv, ngeom, npair, n_substeps, max_steps, obs_dim, act_dim, ctx_dim, info_dim, ctrl_kind, ntaskp, nextra;
   Link link[MAXLINK];
   Geom geom[MAXGEOM];
-  Pair pair[64];
+  Pair pair[MAXPAIR];
   double ctrl[CTRL_W], taskp[32];
   int dof_link[MAXV];
   /* state (see d3o_get_state for the flat layout) */
@@ -81,6 +82,7 @@ typedef struct Env {
   int ik_valid, ctrl_mode, grasp_flag, step_count, terminated, status, obst_contact;
   double grip_set;
   double task_state[8];
+  double extra[8];            /* per-env task data outside qpos: Aligning target pose (model.body_pos/quat of `target_box`) */
   /* scratch of the last forward pass (exposed to tests) */
   double xpos[MAXLINK][3], xmat[MAXLINK][9];
   double S[MAXV][6];
@@ -190,8 +192,8 @@ Env* d3o_create(const void* blob, size_t nbytes) {
   Env* e = (Env*)calloc(1, sizeof(Env));
   e->task_id = h[2]; e->nlink = h[3]; e->nobj = h[4]; e->nq = h[5]; e->nv = h[6]; e->ngeom = h[7]; e->npair = h[8];
   e->n_substeps = h[9]; e->max_steps = h[10]; e->obs_dim = h[11]; e->act_dim = h[12]; e->ctx_dim = h[13]; e->info_dim = h[14];
-  e->ctrl_kind = h[15]; e->ntaskp = h[16];
-  if (e->nlink > MAXLINK || e->nq > MAXQ || e->nv > MAXV || e->ngeom > MAXGEOM || e->npair > 64 || e->ntaskp > 32) { g_err = "scene too large"; free(e); return NULL; }
+  e->ctrl_kind = h[15]; e->ntaskp = h[16]; e->nextra = h[17];
+  if (e->nlink > MAXLINK || e->nq > MAXQ || e->nv > MAXV || e->ngeom > MAXGEOM || e->npair > MAXPAIR || e->ntaskp > 32 || e->nextra > 8) { g_err = "scene too large"; free(e); return NULL; }
   size_t need = 4 * HDR_INTS + 8 * ((size_t)e->nlink * LINK_W + (size_t)e->ngeom * GEOM_W + (size_t)e->npair * PAIR_W + CTRL_W + e->ntaskp);
   if (need != nbytes) { g_err = "scene blob size mismatch"; free(e); return NULL; }
   const double* p = (const double*)((const char*)blob + 4 * HDR_INTS);
@@ -547,52 +549,40 @@ static int collide_cyl_box(const double* c, const double* Rc, const double* sz, 
     }
   }
 #undef TRY_AXIS
-  /* contact point from the support features in direction n */
-  const double EPS = 1e-4;
-  double na = dot3(n, a), pc[3];
-  int zero[3], nz = 0; double m[3];
-  for (int k = 0; k < 3; k++) { m[k] = -dot3(n, B[k]); zero[k] = fabs(m[k]) < EPS; nz += zero[k]; }
-  if (fabs(na) > 1 - 1e-8) {                                   /* cap disc: centre of the cap */
-    double s = na >= 0 ? 1 : -1; for (int k = 0; k < 3; k++) pc[k] = c[k] + s * h * a[k];
-  } else if (fabs(na) >= EPS) {                                /* rim point */
-    double s = na >= 0 ? 1 : -1, pr[3], l;
-    for (int k = 0; k < 3; k++) pr[k] = n[k] - na * a[k];
-    l = norm3(pr);
-    for (int k = 0; k < 3; k++) pc[k] = c[k] + s * h * a[k] + r * pr[k] / l;
-  } else {                                                     /* side line c + t a + r n, |t|<=h, against the box feature */
-    double t0 = -h, t1 = h, base[3];
-    for (int k = 0; k < 3; k++) base[k] = c[k] + r * n[k] - b[k];
-    if (nz >= 1) {
-      /* clip the line to the slab of every box axis lying in the support feature (face: 2 axes, edge: 1 axis) */
-      for (int k = 0; k < 3; k++) if (zero[k]) {
-        double x0 = dot3(base, B[k]), dx = dot3(a, B[k]);
-        if (fabs(dx) < 1e-12) continue;
-        double ta = (-e3[k] - x0) / dx, tb = (e3[k] - x0) / dx;
-        if (ta > tb) { double tmp = ta; ta = tb; tb = tmp; }
-        if (ta > t0) t0 = ta;
-        if (tb < t1) t1 = tb;
-      }
-      if (t0 > t1) { double mid = 0.5 * (t0 + t1); t0 = t1 = clampd(mid, -h, h); }
-    }
-    double ts;
-    if (nz == 2) ts = 0.5 * (t0 + t1);
-    else {
-      /* edge (nz==1) or vertex (nz==0): closest point of the (clipped) line to the supporting vertex / edge centre line */
-      double v[3] = {0, 0, 0};
-      for (int k = 0; k < 3; k++) if (!zero[k]) { double s = m[k] >= 0 ? 1 : -1; for (int cc = 0; cc < 3; cc++) v[cc] += s * e3[k] * B[k][cc]; }
-      if (nz == 1) {
-        int ke = zero[0] ? 0 : (zero[1] ? 1 : 2);
-        double bb = dot3(a, B[ke]), w0[3]; for (int k = 0; k < 3; k++) w0[k] = base[k] - v[k];
-        double dd = dot3(a, w0), ee = dot3(B[ke], w0), den = 1 - bb * bb;
-        ts = den > 1e-12 ? (bb * ee - dd) / den : 0.5 * (t0 + t1);
-      } else {
-        double w0[3]; for (int k = 0; k < 3; k++) w0[k] = v[k] - base[k];
-        ts = dot3(w0, a);
-      }
-      ts = clampd(ts, t0, t1);
-    }
-    for (int k = 0; k < 3; k++) pc[k] = c[k] + r * n[k] + ts * a[k];
+  /* Contact point, continuous in the relative pose (no feature thresholds).  Support point of the cylinder along n:
+   * cap rim at t = s h, radial direction u.  The contact patch extends from there along the side line
+   * x(t) = c + r u + t a (penetration best - |n.a| (h - s t), clipped to the box) and across the cap (penetration
+   * best - r |u-part| at the cap centre): take the penetration-weighted centroid along the line and move from the rim
+   * towards the cap centre as the cap flattens against the box.  Flush side contact -> midpoint of the overlap;
+   * tilted -> slides continuously towards the deep end; flat cap -> cap centre. */
+  double na = dot3(n, a), s = na >= 0 ? 1 : -1, pr[3], u[3] = {0, 0, 0}, pc[3];
+  for (int k = 0; k < 3; k++) pr[k] = n[k] - na * a[k];
+  double l = norm3(pr);
+  if (l > 1e-12) for (int k = 0; k < 3; k++) u[k] = pr[k] / l;
+  double t0 = -h, t1 = h, base[3]; int empty = 0;
+  for (int k = 0; k < 3; k++) base[k] = c[k] + r * u[k] - b[k];
+  for (int k = 0; k < 3; k++) {
+    double x0 = dot3(base, B[k]), dx = dot3(a, B[k]);
+    if (fabs(dx) < 1e-12) { if (fabs(x0) > e3[k]) empty = 1; continue; }
+    double ta = (-e3[k] - x0) / dx, tb = (e3[k] - x0) / dx;
+    if (ta > tb) { double tmp = ta; ta = tb; tb = tmp; }
+    if (ta > t0) t0 = ta;
+    if (tb < t1) t1 = tb;
   }
+  if (t0 > t1) empty = 1;
+  double ts = s * h;
+  if (!empty) {
+    double da = best - fabs(na) * (h - s * t0), db = best - fabs(na) * (h - s * t1);
+    if (da <= 0 && db <= 0) ts = db > da ? t1 : t0;
+    else {
+      if (da < 0) { t0 += (t1 - t0) * (-da) / (db - da); da = 0; }
+      if (db < 0) { t1 -= (t1 - t0) * (-db) / (da - db); db = 0; }
+      ts = t0 + (t1 - t0) * (da + 2 * db) / (3 * (da + db));
+    }
+  }
+  double dc = best - r * l, wcap = 1;
+  if (dc > 0) { double w = r * l / (4 * dc); if (w < 1) wcap = w; }
+  for (int k = 0; k < 3; k++) pc[k] = c[k] + ts * a[k] + r * wcap * u[k];
   for (int k = 0; k < 3; k++) { out->pos[k] = pc[k] - 0.5 * best * n[k]; out->n[k] = n[k]; }
   out->dist = -best;
   return out->dist < margin;
@@ -1033,7 +1023,71 @@ static void get_obs(const Env* e, float* obs) {
     obs[5] = (float)b2[0]; obs[6] = (float)b2[1]; obs[7] = (float)tan_yaw(b2 + 3);
   } else if (e->task_id == TASK_AVOIDING) {    /* avoiding.py:117-119 */
     obs[0] = (float)e->tcp_pos[0]; obs[1] = (float)e->tcp_pos[1];
+  } else if (e->task_id == TASK_SORTING) {     /* sorting.py:308-390: tcp xy, then (xy, tan yaw) of red_1.., blue_1.. */
+    obs[0] = (float)e->tcp_pos[0]; obs[1] = (float)e->tcp_pos[1];
+    for (int i = 0; i < e->nobj; i++) {
+      const double* b = e->qpos + NROB + 7 * i;
+      obs[2 + 3 * i] = (float)b[0]; obs[3 + 3 * i] = (float)b[1]; obs[4 + 3 * i] = (float)tan_yaw(b + 3);
+    }
+  } else if (e->task_id == TASK_ALIGNING) {    /* aligning.py:205-235: tcp xyz, box pos + quat (qpos), target pos + quat (model.body_pos/quat) */
+    const double* b = e->qpos + NROB;
+    for (int k = 0; k < 3; k++) obs[k] = (float)e->tcp_pos[k];
+    for (int k = 0; k < 7; k++) { obs[3 + k] = (float)b[k]; obs[10 + k] = (float)e->extra[k]; }
   }
+}
+
+/* ---- Sorting (sorting.py:460-543).  task_state: [0] mode_step, [1] bit i set <=> mode[i] == 0 (red), [2] bitmask of min_inds.
+ * Box slots are (red_1, red_2, red_3, blue_1, blue_2, blue_3); slots absent from the scene read the constant pose of the
+ * model's last body through mj_name2id = -1: taskp[11..12]. */
+static void sorting_slot_xy(const Env* e, int slot, double* xy) {
+  int half = e->nobj / 2, col = slot / 3, idx = slot % 3;
+  if (idx < half) { const double* b = e->qpos + NROB + 7 * (col * half + idx); xy[0] = b[0]; xy[1] = b[1]; }
+  else { xy[0] = e->taskp[11]; xy[1] = e->taskp[12]; }
+}
+static int sorting_in_bin(const Env* e, int col, const double* xy) {
+  const double* T = e->taskp;
+  return xy[0] > T[4 + 2 * col] && xy[0] < T[5 + 2 * col] && xy[1] > T[8] && xy[1] < T[9];
+}
+static int sorting_early_term(Env* e) {        /* sorting.py:509-543 */
+  int half = e->nobj / 2;
+  for (int i = 0; i < e->nobj; i++) if (!sorting_in_bin(e, i / half, e->qpos + NROB + 7 * i)) return 0;
+  e->terminated = 1;
+  return 1;
+}
+static int sorting_check_mode(Env* e) {         /* sorting.py:460-507 + decode_mode (np.packbits of mode[:k], -1 and 1 both pack as 1) */
+  int step = (int)e->task_state[0], zero = (int)e->task_state[1], mins = (int)e->task_state[2];
+  if (step <= 5) {
+    double best = 0; int bi = -1; double bxy[2] = {0, 0};
+    for (int s2 = 0; s2 < 6; s2++) {
+      double xy[2]; sorting_slot_xy(e, s2, xy);
+      const double* tg = e->taskp + 2 * (s2 / 3);
+      double d = (mins >> s2) & 1 ? 100000.0 : sqrt((xy[0] - tg[0]) * (xy[0] - tg[0]) + (xy[1] - tg[1]) * (xy[1] - tg[1]));
+      if (bi < 0 || d < best) { best = d; bi = s2; bxy[0] = xy[0]; bxy[1] = xy[1]; }
+    }
+    if (sorting_in_bin(e, bi / 3, bxy)) {
+      if (bi < 3) zero |= 1 << step;
+      step++; mins |= 1 << bi;
+    }
+    e->task_state[0] = step; e->task_state[1] = zero; e->task_state[2] = mins;
+  }
+  int code = 0;
+  for (int i = 0; i < e->nobj; i++) if (!((zero >> i) & 1)) code |= 1 << (7 - i);
+  return code;
+}
+
+/* ---- Aligning (aligning.py:21-30,295-352) */
+static double rotation_distance(const double* p, const double* q) {
+  double d = fabs(p[0] * q[0] + p[1] * q[1] + p[2] * q[2] + p[3] * q[3]);
+  return 2 * acos(d > 1 ? 1 : d);               /* numpy would return NaN for |p.q| = 1 + ulp; clamped here */
+}
+static void aligning_dists(const Env* e, double* pos_d, double* rot_d) {
+  const double* b = e->qpos + NROB;
+  *pos_d = dist3(b, e->extra); *rot_d = rotation_distance(b + 3, e->extra + 3) / 3.14159265358979323846;
+}
+static int aligning_early_term(Env* e) {
+  double pd, rd; aligning_dists(e, &pd, &rd);
+  if (pd <= e->taskp[0] && rd <= e->taskp[1]) { e->terminated = 1; return 1; }
+  return 0;
 }
 
 static int pushing_early_term(Env* e) {        /* pushing.py:440-459 */
@@ -1080,6 +1134,10 @@ static double get_reward(const Env* e) {
     double dx = e->tcp_pos[0] - b1[0], dy = e->tcp_pos[1] - b1[1];
     return -(sqrt(dx * dx + dy * dy) + dist3(b1, e->taskp));
   }
+  if (e->task_id == TASK_ALIGNING) {           /* aligning.py:321-332 */
+    double pd, rd; aligning_dists(e, &pd, &rd);
+    return -rd - 3.5 * pd;
+  }
   return 0;
 }
 
@@ -1091,13 +1149,16 @@ void d3o_reset(Env* e, const double* ctx) {
   for (int i = NROB; i < e->nlink; i++) { memcpy(e->qpos + e->link[i].qadr, e->link[i].pos, 24); memcpy(e->qpos + e->link[i].qadr + 3, e->link[i].quat, 32); }
   e->ik_valid = 0; e->ctrl_mode = 0; e->grasp_flag = 0; e->grip_set = 0.001;      /* Robots.py:127 */
   e->step_count = 0; e->terminated = 0; e->status = 0; e->obst_contact = 0;
-  memset(e->task_state, 0, sizeof e->task_state); e->task_state[0] = -1;
+  memset(e->task_state, 0, sizeof e->task_state);
+  if (e->task_id == TASK_PUSHING) e->task_state[0] = -1;
+  if (e->task_id == TASK_ALIGNING) memcpy(e->extra, e->taskp + 3, 56);           /* XML pose of `target_box` */
   /* set_q -> mj_forward at (init_qpos, 0): fresh tcp pose and qfrc_bias for the first command */
   kinematics(e); update_tcp(e); rne_bias(e);
   for (int k = 0; k < NROB; k++) e->bias_prev[k] = e->bias[k];
   memcpy(e->jt_q, e->qpos, 8 * NARM); memset(e->jt_qd, 0, sizeof e->jt_qd);       /* jointTrackingController.setSetPoint(init_qpos) */
   /* manager.start(context): raw qpos write, no mj_forward */
   if (ctx) for (int i = NROB; i < e->nlink; i++) memcpy(e->qpos + e->link[i].qadr, ctx + 7 * (i - NROB), 56);
+  if (ctx && e->nextra) memcpy(e->extra, ctx + 7 * e->nobj, 8 * e->nextra);        /* joint-less target body: model.body_pos/quat (MjScene.py:271-285) */
   physics_step(e);                                                                 /* scene.next_step(): exactly one tick */
 }
 
@@ -1108,7 +1169,8 @@ void d3o_step(Env* e, const double* action, float* obs, double* reward, int* don
   memcpy(e->des_pos, action, 24); for (int k = 0; k < 4; k++) e->des_quat[k] = action[3 + k] / n;   /* IKControllers.py:346-362 */
   e->ctrl_mode = 1;
   get_obs(e, obs); *reward = get_reward(e);
-  int early = e->task_id == TASK_PUSHING ? pushing_early_term(e) : avoiding_early_term(e);
+  int early = e->task_id == TASK_PUSHING ? pushing_early_term(e) : e->task_id == TASK_SORTING ? sorting_early_term(e)
+            : e->task_id == TASK_ALIGNING ? aligning_early_term(e) : avoiding_early_term(e);
   *done = e->terminated || early || e->step_count >= e->max_steps - 1;             /* :124-137 */
   for (int i = 0; i < e->n_substeps; i++) physics_step(e);
   e->step_count++;
@@ -1117,6 +1179,15 @@ void d3o_step(Env* e, const double* action, float* obs, double* reward, int* don
     int success = pushing_early_term(e), mode; double md;
     pushing_check_mode(e, &mode, &md);
     info[0] = success; info[1] = mode; info[2] = md; info[3] = e->status;
+  } else if (e->task_id == TASK_SORTING) {     /* sorting.py:444-458 */
+    int success = sorting_early_term(e);
+    info[0] = success; info[1] = sorting_check_mode(e); info[2] = e->task_state[0]; info[3] = e->status;
+  } else if (e->task_id == TASK_ALIGNING) {    /* aligning.py:289-319 */
+    int success = aligning_early_term(e);
+    double pd, rd; aligning_dists(e, &pd, &rd);
+    const double* b = e->qpos + NROB;
+    double rb = sqrt((b[0] - e->tcp_pos[0]) * (b[0] - e->tcp_pos[0]) + (b[1] - e->tcp_pos[1]) * (b[1] - e->tcp_pos[1]));
+    info[0] = success; info[1] = rb < e->taskp[2] ? 0 : 1; info[2] = 0.5 * (pd + rd); info[3] = e->status;
   } else {                                     /* avoiding.py:168-171 */
     avoiding_check_mode(e);
     info[0] = e->task_state[1];
@@ -1130,14 +1201,14 @@ void d3o_robot_state(const Env* e, double* tcp) { memcpy(tcp, e->tcp_pos, 24); }
 void d3o_get_obs(const Env* e, float* obs) { get_obs(e, obs); }
 
 /* ------------------------------------------------------------------ flat state (shared layout with the CUDA library's get/set_state) */
-int d3o_state_dim(const Env* e) { return e->nq + 2 * e->nv + 60; }
+int d3o_state_dim(const Env* e) { return e->nq + 2 * e->nv + 60 + e->nextra; }
 #define PUT(arr, n) do { memcpy(p, arr, 8 * (n)); p += (n); } while (0)
 #define GET(arr, n) do { memcpy(arr, p, 8 * (n)); p += (n); } while (0)
 void d3o_get_state(const Env* e, double* p) {
   PUT(e->qpos, e->nq); PUT(e->qvel, e->nv); PUT(e->warm, e->nv); PUT(e->bias_prev, 9); PUT(e->tcp_pos, 3); PUT(e->tcp_quat, 4);
   PUT(e->ik_q, 7); PUT(e->des_pos, 3); PUT(e->des_quat, 4); PUT(e->jt_q, 7); PUT(e->jt_qd, 7);
   double s[8] = {e->ik_valid, e->ctrl_mode, e->grip_set, e->grasp_flag, e->step_count, e->terminated, e->status, e->obst_contact};
-  PUT(s, 8); PUT(e->task_state, 8);
+  PUT(s, 8); PUT(e->task_state, 8); PUT(e->extra, e->nextra);
 }
 void d3o_set_state(Env* e, const double* p) {
   GET(e->qpos, e->nq); GET(e->qvel, e->nv); GET(e->warm, e->nv); GET(e->bias_prev, 9); GET(e->tcp_pos, 3); GET(e->tcp_quat, 4);
@@ -1145,7 +1216,7 @@ void d3o_set_state(Env* e, const double* p) {
   double s[8]; GET(s, 8);
   e->ik_valid = (int)s[0]; e->ctrl_mode = (int)s[1]; e->grip_set = s[2]; e->grasp_flag = (int)s[3]; e->step_count = (int)s[4];
   e->terminated = (int)s[5]; e->status = (int)s[6]; e->obst_contact = (int)s[7];
-  GET(e->task_state, 8);
+  GET(e->task_state, 8); GET(e->extra, e->nextra);
 }
 
 /* ------------------------------------------------------------------ probes for the invariant tests (tests/ only) */

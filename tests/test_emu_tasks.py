@@ -1,0 +1,114 @@
+"""CPU checks of the CUDA kernel core (one-lane host build, tests/emu) on the Sorting-k and Aligning scenes against the
+fp64 oracle: fp64 build = logic equivalence, fp32 build = the precision the GPU path delivers.  Contact-rich env steps
+in which a box is tipping on an edge are ill-conditioned (a 1e-7 perturbation changes the contact set), so the fp32
+bound is a quantile bound: >= 85 % of the teacher-forced env steps inside the tolerance box, none blown up."""
+import numpy as np
+import pytest
+
+from d3il_b200.scene.blob import load_scene
+from oracle.oracle import OracleEnv
+from tests.emu.emu import EmuEnv
+from tests.util import scripted_task_actions, step_errors, task_contexts
+
+TASKS = ["sorting_2", "sorting_4", "sorting_6", "aligning"]
+
+
+@pytest.mark.parametrize("task", TASKS)
+def test_new_task_logic_equals_oracle_fp64(task):
+    blob, sc = load_scene(task)
+    nq, nv, nx = sc.header["nq"], sc.header["nv"], sc.header.get("nextra", 0)
+    ctx = task_contexts(task)[1]
+    o, e = OracleEnv(blob, sc.header), EmuEnv(blob, sc.header, "f64")
+    oo, eo = o.reset(ctx), e.reset(ctx)
+    so, se = o.get_state(), e.get_state()
+    assert np.abs(so[:nq + 2 * nv + 56] - se[:nq + 2 * nv + 56]).max() < 3e-6      # contexts pass through float32 on the kernel side
+    if nx:
+        assert np.allclose(so[-nx:], se[-nx:], atol=1e-7)
+    assert np.allclose(oo, eo, rtol=1e-4, atol=1e-5)
+    touched = False
+    for a in scripted_task_actions(task, ctx, o.robot_state(), n_steps=50):
+        e.set_state(o.get_state())
+        ro, re = o.step(a), e.step(a)
+        so, se = o.get_state(), e.get_state()
+        assert np.abs(so[:nq] - se[:nq]).max() < 1e-8
+        assert np.abs(so[nq:nq + nv] - se[nq:nq + nv]).max() < 1e-6 * (1 + np.abs(so[nq:nq + nv]).max())
+        assert np.allclose(ro[0], re[0], rtol=1e-4, atol=1e-5) and ro[2] == re[2] and np.allclose(ro[3], re[3], atol=1e-6)
+        assert abs(ro[1] - re[1]) < 1e-6
+        con = o.probe("contacts").reshape(-1, 12)
+        touched |= bool(len(con)) and bool((con[:, 11] >= 0).any())
+    assert touched and so[-nx - 16 + 6] == 0          # status word: no overflow / solver fault
+
+
+@pytest.mark.parametrize("task", TASKS)
+def test_new_task_fp32_env_steps(task):
+    blob, sc = load_scene(task)
+    nq, nv = sc.header["nq"], sc.header["nv"]
+    ctx = task_contexts(task)[2]
+    o, e = OracleEnv(blob, sc.header), EmuEnv(blob, sc.header, "f32")
+    o.reset(ctx)
+    errs = []
+    for a in scripted_task_actions(task, ctx, o.robot_state(), n_steps=50):
+        e.set_state(o.get_state())
+        ro, re = o.step(a), e.step(a)
+        errs.append(step_errors(o.get_state(), e.get_state(), nq, nv))
+        assert ro[2] == re[2] and np.array_equal(ro[3][:2], re[3][:2]) and re[3][3] == 0
+    errs = np.array(errs)
+    assert (errs.max(axis=1) <= 1.0).mean() >= 0.85, errs
+    assert errs[:, 0].max() < 2e3            # nothing blows up: worst qpos error < 1e-2
+
+
+def test_sorting_boxes_settle_on_platform():
+    """C13: boxes spawn 80 mm inside the platform and are pushed out to rest on its top face (z = 0.10 + 0.03)."""
+    blob, sc = load_scene("sorting_4")
+    o = OracleEnv(blob, sc.header)
+    ctx = task_contexts("sorting_4")[0]
+    o.reset(ctx)
+    a = np.concatenate([o.robot_state(), [0, 1, 0, 0]])
+    for _ in range(12):
+        obs, r, done, info = o.step(a)
+    s = o.get_state()
+    z = s[9 + 2:sc.header["nq"]:7]
+    assert np.all(np.abs(z - 0.1299) < 2e-4), z
+    assert np.abs(s[sc.header["nq"] + 9:sc.header["nq"] + sc.header["nv"]]).max() < 1e-2          # still creeping into the soft contact
+    assert np.allclose(obs[2::3][:4], ctx[:, 0], atol=2e-3) and info[0] == 0 and info[1] == 240 and info[3] == 0
+
+
+def test_sorting_mode_bookkeeping():
+    """check_mode / decode_mode (sorting.py:460-507): teleport boxes into the bins and watch the packed mode word."""
+    blob, sc = load_scene("sorting_2")
+    o = OracleEnv(blob, sc.header)
+    o.reset(task_contexts("sorting_2")[0])
+    a = np.concatenate([o.robot_state(), [0, 1, 0, 0]])
+    s = o.get_state()
+    s[9:12] = [0.62, 0.3, 0.13]         # red box parked in the BLUE bin: nothing is sorted
+    s[16:19] = [0.62, 0.35, 0.03]       # blue box in the blue bin (on the table)
+    o.set_state(s)
+    obs, r, done, info = o.step(a)
+    assert info[0] == 0 and info[2] == 1 and info[1] == 0b11000000      # one entry, value 1 (blue) -> packbits keeps 1s
+    s = o.get_state()
+    s[9:12] = [0.4, 0.3, 0.03]
+    o.set_state(s)
+    obs, r, done, info = o.step(a)
+    assert info[0] == 1 and info[2] == 2 and info[1] == 0b10000000      # second entry red (0)
+    obs, r, done, info = o.step(a)
+    assert done                                                          # terminated flag seen by the next is_finished
+
+
+def test_aligning_box_rests_and_reports_target():
+    blob, sc = load_scene("aligning")
+    o = OracleEnv(blob, sc.header)
+    ctx = task_contexts("aligning")[0]
+    obs = o.reset(ctx)
+    a = np.concatenate([o.robot_state(), [0, 1, 0, 0]])
+    for _ in range(10):
+        obs, r, done, info = o.step(a)
+    assert np.allclose(obs[10:17], ctx[1], atol=1e-6)                    # target pose from model.body_pos/quat
+    assert abs(obs[5] - (-0.019 + 0.01)) < 3e-4                          # base plate (half height 0.01) on the table top z = -0.019
+    o.forward()
+    f = o.probe("efc_force")
+    con = o.probe("contacts").reshape(-1, 12)
+    normal = sum(f[int(c[11])] for c in con if c[11] >= 0)
+    assert abs(normal - 1.004 * 9.81) < 2e-3 * 9.81                      # four plate corners carry m g
+    assert np.allclose(con[:, 10], 0.3 / np.sqrt(3))                     # priority-1 plate friction wins over the table's
+    pd = np.linalg.norm(obs[3:6] - obs[10:13])
+    assert info[1] == 1 and abs(info[2] - 0.5 * (pd + 2 * np.arccos(abs(obs[6:10] @ obs[13:17])) / np.pi)) < 1e-4

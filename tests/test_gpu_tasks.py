@@ -1,0 +1,101 @@
+"""GPU parity tests for the Sorting-k and Aligning scenes (run on the B200 box): CUDA path through the C ABI vs the fp64
+oracle.  Same protocol as tests/test_gpu_parity.py; contact-rich env steps with a tipping box are ill-conditioned, so
+the teacher-forced env-step bound is a quantile bound (see tests/test_emu_tasks.py)."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from d3il_b200.scene.blob import load_scene          # noqa: E402
+from oracle.oracle import OracleEnv                   # noqa: E402
+from tests.util import oracle_rollout_states, scripted_task_actions, step_errors, task_contexts  # noqa: E402
+
+TASKS = ["sorting_2", "sorting_4", "sorting_6", "aligning"]
+
+
+def _benv(task, n):
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from d3il_b200.batched_env import BatchedEnv
+    return BatchedEnv(task, n, 0)
+
+
+@pytest.mark.parametrize("task", TASKS)
+def test_task_reset_matches_oracle(task):
+    """a12 for every committed context of the task: state install (+ Aligning target pose) and the single reset tick."""
+    blob, sc = load_scene(task)
+    nq, nv, nx = sc.header["nq"], sc.header["nv"], sc.header.get("nextra", 0)
+    ctxs = task_contexts(task)
+    n = len(ctxs)
+    env = _benv(task, n)
+    obs = env.reset(torch.tensor(ctxs, dtype=torch.float32, device="cuda")).cpu().numpy()
+    o = OracleEnv(blob, sc.header)
+    for i in range(n):
+        oo = o.reset(ctxs[i])
+        s_ref, s = o.get_state(), env.get_state(i)
+        assert np.allclose(s[:nq], s_ref[:nq], rtol=1e-4, atol=2e-6), (i, np.abs(s[:nq] - s_ref[:nq]).max())
+        # one tick of the spawn transient (80 mm inside the platform: ~200 m/s^2)
+        assert np.allclose(s[nq:nq + nv], s_ref[nq:nq + nv], rtol=1e-3, atol=2e-4), (i, np.abs(s[nq:nq + nv] - s_ref[nq:nq + nv]).max())
+        assert np.allclose(obs[i], oo, rtol=2e-4, atol=1e-5)
+        if nx:
+            assert np.allclose(s[-nx:], s_ref[-nx:], atol=1e-6)
+    env.close()
+
+
+@pytest.mark.parametrize("task", TASKS)
+def test_task_env_step_teacher_forced(task):
+    """(ii): full env steps from oracle states along a scripted push, all steps of the script in one batch."""
+    blob, sc = load_scene(task)
+    nq, nv = sc.header["nq"], sc.header["nv"]
+    ctx = task_contexts(task)[2]
+    o = OracleEnv(blob, sc.header)
+    o.reset(ctx)
+    acts = scripted_task_actions(task, ctx, o.robot_state(), n_steps=56)
+    _, states, outs = oracle_rollout_states(task, ctx, acts)
+    n = len(acts)
+    env = _benv(task, n)
+    env.reset(torch.tensor(np.repeat(ctx[None], n, 0), dtype=torch.float32, device="cuda"))
+    for i in range(n):
+        env.set_state(i, states[i])
+    obs, rew, done, info = (t.cpu().numpy() for t in env.step(torch.tensor(acts, dtype=torch.float32, device="cuda")))
+    o2 = OracleEnv(blob, sc.header)
+    errs = []
+    for i in range(n):
+        o2.set_state(states[i])
+        oo, rr, dd, ii = o2.step(acts[i])
+        errs.append(step_errors(o2.get_state(), env.get_state(i), nq, nv))
+        assert np.allclose(obs[i], oo, rtol=2e-4, atol=1e-5) and abs(rew[i] - rr) < 1e-4 and bool(done[i]) == dd      # sampled BEFORE the substeps
+        assert np.array_equal(info[i, :2], ii[:2]) and info[i, 3] == 0
+    errs = np.array(errs)
+    assert (errs.max(axis=1) <= 1.0).mean() >= 0.85, errs
+    assert errs[:, 0].max() < 2e3
+    env.close()
+
+
+def test_sorting4_full_size_properties():
+    """BASELINE config 3 size (8192 envs of Sorting-4): finite, no faults, boxes on the platform, envs sharing a context and
+    an action stream stay bit-identical, determinism across two runs."""
+    n = 8192
+    ctxs = task_contexts("sorting_4")
+    ctx = torch.tensor(ctxs[np.arange(n) % 60], dtype=torch.float32, device="cuda")
+    finals = []
+    for rep in range(2):
+        env = _benv("sorting_4", n)
+        env.reset(ctx)
+        tcp = env.robot_state().clone()
+        des = torch.cat([tcp, torch.tensor([0, 1, 0, 0], device="cuda").repeat(n, 1)], 1)
+        g = torch.Generator(device="cuda").manual_seed(0)
+        lo, hi = torch.tensor([0.3, -0.45], device="cuda"), torch.tensor([0.8, 0.45], device="cuda")
+        for k in range(30):
+            d = (torch.rand(60, 2, generator=g, device="cuda") * 0.02 - 0.01).repeat((n + 59) // 60, 1)[:n]
+            des[:, :2] = torch.minimum(torch.maximum(des[:, :2] + d, lo), hi)
+            obs, rew, done, info = env.step(des)
+        assert torch.isfinite(obs).all() and torch.isfinite(info).all()
+        assert (info[:, 3] == 0).all()
+        finals.append(np.array([env.get_state(i) for i in (5, 65, 8165, 100)]))
+        env.close()
+    assert np.array_equal(finals[0], finals[1])
+    assert np.array_equal(finals[0][0], finals[0][1]) and np.array_equal(finals[0][0], finals[0][2])
+    z = finals[0][:, 9 + 2:37:7]
+    assert np.all((z > 0.128) & (z < 0.132)), z

@@ -56,3 +56,37 @@ def with_setpoint(state, sc, action, grip=0.04):
     s[o + 44 + 2] = grip   # gripper set-point
     s[o + 44 + 3] = 0      # grasp flag
     return s
+
+
+TASK_CONTEXT_FILES = {"pushing": "pushing_test_contexts", "sorting_2": "sorting_2_contexts", "sorting_4": "sorting_4_contexts",
+                      "sorting_6": "sorting_6_contexts", "aligning": "aligning_test_contexts"}
+
+
+def task_contexts(task):
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    return np.load(os.path.join(root, "d3il_b200", "data", TASK_CONTEXT_FILES[task] + ".npy"))
+
+
+def scripted_task_actions(task, ctx, tcp0, n_steps=60, speed=0.008):
+    """Drive the rod from the start pose towards a point 10 cm beyond the first object (+y), lowering the tool for
+    Aligning (3-D action) so the rod meets the box walls: free motion, impact, pushing, box-box contacts."""
+    des = np.array(tcp0, dtype=np.float64).copy()
+    goal = np.asarray(ctx, dtype=np.float64).reshape(-1, 7)[0, :2] + np.array([0.0, 0.1])
+    out = []
+    for _ in range(n_steps):
+        d = goal - des[:2]
+        n = np.linalg.norm(d)
+        if n > 1e-12:
+            des[:2] += d / n * min(speed, n)
+        if task == "aligning":
+            des[2] += np.clip(0.13 - des[2], -speed, speed)
+        out.append(np.concatenate([des, [0, 1, 0, 0]]))
+    return np.array(out)
+
+
+def step_errors(ref, got, nq, nv):
+    """(qpos error in units of rtol 1e-4 + atol 5e-6, qvel error in units of rtol 1e-3 + atol 2e-4)."""
+    dq = np.abs(got[:nq] - ref[:nq]) / (1e-4 * np.abs(ref[:nq]) + 5e-6)
+    dv = np.abs(got[nq:nq + nv] - ref[nq:nq + nv]) / (1e-3 * np.abs(ref[nq:nq + nv]) + 2e-4)
+    return dq.max(), dv.max()
