@@ -17,6 +17,10 @@ def _is_bc_like(agent) -> bool:
     return all(hasattr(agent, a) for a in ("model", "scaler", "min_action", "max_action")) and not hasattr(agent, "obs_context")
 
 
+def _is_ddpm_like(agent) -> bool:
+    return all(hasattr(agent, a) for a in ("model", "scaler", "obs_context")) and not getattr(agent, "diffusion_kde", False)
+
+
 @torch.no_grad()
 def predict_batch(agent, obs: torch.Tensor) -> torch.Tensor:
     """obs: [N, obs_dim] float tensor (any device). Returns [N, act_dim] float32 on obs.device."""
@@ -31,5 +35,26 @@ def predict_batch(agent, obs: torch.Tensor) -> torch.Tensor:
         out = out.clamp_(agent.min_action, agent.max_action)
         out = agent.scaler.inverse_scale_output(out)
         return out[:, 0].to(obs.device, torch.float32)
+    if _is_ddpm_like(agent):
+        # DiffusionAgent.predict (agents/ddpm_agent.py:214-274) on N rows at once: scale, (window of past observations),
+        # EMA parameter swap, model = full reverse-diffusion sampler, restore, inverse scale.  agent.reset() clears the window.
+        dev = getattr(agent, "device", obs.device)
+        state = agent.scaler.scale_input(obs.to(dev).float())
+        if getattr(agent, "window_size", 1) > 1:
+            agent.obs_context.append(state)
+            inp = torch.stack(tuple(agent.obs_context), dim=1)
+        else:
+            inp = state
+        ema = getattr(agent, "use_ema", False)
+        if ema:
+            agent.ema_helper.store(agent.model.parameters())
+            agent.ema_helper.copy_to(agent.model.parameters())
+        agent.model.eval()
+        pred = agent.model(inp, None)
+        if pred.dim() == 3:
+            pred = pred[:, -1, :]
+        if ema:
+            agent.ema_helper.restore(agent.model.parameters())
+        return agent.scaler.inverse_scale_output(pred).to(obs.device, torch.float32)
     acts = [np.asarray(agent.predict(o))[0] for o in obs.detach().cpu().numpy()]
     return torch.as_tensor(np.stack(acts), dtype=torch.float32, device=obs.device)

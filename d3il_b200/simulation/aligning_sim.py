@@ -1,0 +1,56 @@
+"""``Aligning_Sim`` — drop-in for ``simulation/aligning_sim.py:29-204`` on the batched CUDA env (3-D Cartesian action)."""
+from __future__ import annotations
+
+import logging
+import os
+
+import numpy as np
+import torch
+
+from .base_sim import BaseSim, _wandb_log, cartesian_rollout
+from .metrics import mode_entropy
+
+log = logging.getLogger(__name__)
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "data")
+
+
+def load_test_contexts() -> np.ndarray:
+    """[60, 2, 7]: box pose and target pose (xyz + quat) from ``environments/dataset/data/aligning/test_contexts.pkl``."""
+    return np.load(os.path.join(_DATA, "aligning_test_contexts.npy"))
+
+
+class Aligning_Sim(BaseSim):
+    def __init__(self, seed: int, device: str, render: bool, n_cores: int = 1, n_contexts: int = 30, n_trajectories_per_context: int = 1,
+                 if_vision: bool = False):
+        super().__init__(seed, device, render, n_cores, if_vision)
+        self.n_contexts = n_contexts
+        self.n_trajectories_per_context = n_trajectories_per_context
+
+    def eval_agent(self, agent, items: np.ndarray):
+        """[n, 3] rows (mode, success, mean_distance) (``aligning_sim.py:46-120``)."""
+        dev_index = self._cuda_index()
+        ctx = torch.tensor(load_test_contexts()[items[:, 0]], dtype=torch.float32, device=f"cuda:{dev_index}")
+        info = cartesian_rollout(agent, "aligning", ctx, len(items), dev_index, self.seed, 3)
+        return torch.stack([info[:, 1], info[:, 0], info[:, 2]], 1)
+
+    def test_agent(self, agent):
+        log.info("Starting trained model evaluation")
+        n_items = self.n_contexts * self.n_trajectories_per_context
+        items = np.stack(np.meshgrid(np.arange(self.n_contexts), np.arange(self.n_trajectories_per_context), indexing="ij"), -1).reshape(-1, 2)
+        rank, world = self.dist_info()
+        lo, hi = self.shard_range(n_items, rank, world)
+        rows = self.gather_rows(self.eval_agent(agent, items[lo:hi]), n_items).cpu()
+        shape = (self.n_contexts, self.n_trajectories_per_context)
+        mode_encoding, successes, mean_distance = (rows[:, k].reshape(shape).clone() for k in range(3))
+        n_modes = 2
+        success_rate = torch.mean(successes).item()
+        mode_probs, entropy = mode_entropy(mode_encoding, successes, n_modes)
+        print(f"p(m|c) {mode_probs}")
+        _wandb_log({"score": 0.5 * (success_rate + entropy)})
+        _wandb_log({"Metrics/successes": success_rate})
+        _wandb_log({"Metrics/entropy": entropy})
+        _wandb_log({"Metrics/distance": mean_distance.mean().item()})
+        print(f"Mean Distance {mean_distance.mean().item()}")
+        print(f"Successrate {success_rate}")
+        print(f"entropy {entropy}")
+        return successes, mode_encoding, mean_distance

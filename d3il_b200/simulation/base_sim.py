@@ -76,3 +76,38 @@ class BaseSim(abc.ABC):
         if d.type != "cuda":
             raise RuntimeError("the batched simulation runs on CUDA devices only")
         return d.index if d.index is not None else torch.cuda.current_device()
+
+
+@torch.no_grad()
+def cartesian_rollout(agent, task: str, contexts: torch.Tensor | None, n: int, dev_index: int, seed: int, n_act: int, max_steps: int | None = None):
+    """The env loop shared by the Cartesian-action sims (``pushing_sim.py:55-85``, ``sorting_sim.py:99-136``,
+    ``aligning_sim.py:105-120``, ``avoiding_sim.py:45-76``), all (context, rollout) pairs in lock-step:
+    agent input = [last DESIRED tcp xy(z) || env obs], policy output = delta integrated on the last desired pose,
+    z frozen at the reset tcp height when the action is 2-D.  Returns the ``info`` row of every env at ITS final step."""
+    from ..batched_env import BatchedEnv
+    from .agent_adapter import predict_batch
+
+    dev = torch.device(f"cuda:{dev_index}")
+    env = BatchedEnv(task, n, dev_index)
+    torch.manual_seed(seed)
+    agent.reset()
+    obs = env.reset(contexts).clone()
+    tcp = env.robot_state().clone()
+    des = tcp[:, :n_act].clone()
+    tail = torch.cat([tcp[:, n_act:], torch.tensor([0.0, 1.0, 0.0, 0.0], device=dev).repeat(n, 1)], 1)
+    rows = torch.zeros(n, env.info_dim, device=dev)
+    active = torch.ones(n, dtype=torch.bool, device=dev)
+    cap = env.max_steps_per_episode if max_steps is None else min(int(max_steps), env.max_steps_per_episode)
+    for k in range(cap + 1):
+        agent_in = torch.cat([des, obs], 1)
+        delta = predict_batch(agent, agent_in)
+        des = torch.where(active.unsqueeze(1), delta + agent_in[:, :n_act], des)
+        obs_t, _, done, info = env.step(torch.cat([des, tail], 1))
+        obs = obs_t.clone()
+        done = done.bool() | (k >= cap - 1)             # a shorter episode cap than the compiled one (config max_steps_per_episode)
+        rows = torch.where((active & done).unsqueeze(1), info, rows)
+        active = active & ~done
+        if not bool(active.any()):
+            break
+    env.close()
+    return rows

@@ -31,3 +31,30 @@ def avoiding_entropy(mode_encoding: torch.Tensor, successes: torch.Tensor) -> tu
     probs = counts.float() / counts.sum()
     ent = -(probs * (torch.log(probs) / torch.log(torch.tensor(24.0)))).sum()
     return probs, ent
+
+
+def mode_kl(mode_encoding: torch.Tensor, successes: torch.Tensor, prior: dict | None):
+    """``sorting_sim.py:191-213``: p(mode | context) over successful rollouts for the modes listed in the prior
+    ({mode id: probability}, ``<k>_mode_prob.pkl``), contexts without a success dropped, entropy and KL to the prior in log
+    base n_mode.  ``prior=None`` (the pkl is not shipped): uniform prior over the modes observed in successful rollouts.
+
+    Returns (mode_probs [n_kept_contexts, n_mode], entropy, KL) as (tensor, float, float)."""
+    ok = successes == 1
+    if prior is None:
+        keys = torch.unique(mode_encoding[ok])
+        if keys.numel() == 0:
+            return torch.zeros(0, 0), 0.0, 0.0
+        prior_p = torch.full((keys.numel(),), 1.0 / keys.numel())
+    else:
+        keys = torch.tensor(list(prior.keys()), dtype=mode_encoding.dtype)
+        prior_p = torch.tensor([float(prior[k]) for k in prior.keys()])
+    n_mode, n_traj = keys.numel(), mode_encoding.shape[1]
+    probs = torch.stack([((mode_encoding == k) & ok).sum(1).float() / n_traj for k in keys], 1)
+    probs = probs / (probs.sum(1, keepdim=True) + 1e-12)
+    probs = probs[probs.sum(1) != 0]
+    if probs.shape[0] == 0:
+        return probs, 0.0, 0.0
+    base = torch.log(torch.tensor(float(max(n_mode, 2))))
+    entropy = -(probs * torch.log(probs + 1e-12) / base).sum(1).mean()
+    log_ = (probs * torch.log(prior_p + 1e-12) / base).sum(1).mean()
+    return probs, float(entropy), float(-entropy - log_)
