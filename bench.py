@@ -29,19 +29,32 @@ sys.path.insert(0, ROOT)
 
 METRIC = "env_steps_per_sec"
 UNIT = "env-steps/s"
-TASK = "pushing"
-N_ENVS = 4096            # per GPU (BASELINE.json configs[1])
 WORKSPACE_LO, WORKSPACE_HI = (0.3, -0.45), (0.8, 0.45)
 
+# BASELINE.json configs -> workloads.  The default (`pushing`) is the configuration the metric is quoted on (configs[1]:
+# Pushing, 4096 envs, random actions, 1 GPU); the others are the wider configs, run on request (--workload).
+WORKLOADS = {
+    "pushing": dict(task="pushing", envs=4096, ctx="pushing_test_contexts", policy=None, n_act=2),
+    "avoiding": dict(task="avoiding", envs=4096, ctx=None, policy=None, n_act=2),
+    "aligning": dict(task="aligning", envs=4096, ctx="aligning_test_contexts", policy=None, n_act=3),
+    "sorting2": dict(task="sorting_2", envs=4096, ctx="sorting_2_contexts", policy=None, n_act=2),
+    "sorting4-ddpm": dict(task="sorting_4", envs=8192, ctx="sorting_4_contexts", policy="ddpm", n_act=2),      # configs[2]
+    "sorting4": dict(task="sorting_4", envs=8192, ctx="sorting_4_contexts", policy=None, n_act=2),
+    "sorting6": dict(task="sorting_6", envs=4096, ctx="sorting_6_contexts", policy=None, n_act=2),
+    "stacking": dict(task="stacking", envs=4096, ctx="stacking_test_contexts", policy=None, n_act=7),          # configs[3]: 4096 envs / GPU
+}
+TASK = "pushing"
+N_ENVS = WORKLOADS["pushing"]["envs"]
 
-def load_contexts():
-    return np.load(os.path.join(ROOT, "d3il_b200", "data", "pushing_test_contexts.npy"))
+
+def load_contexts(name="pushing_test_contexts"):
+    return np.load(os.path.join(ROOT, "d3il_b200", "data", name + ".npy"))
 
 
 # ------------------------------------------------------------------------------------------------ CPU (oracle) arm
 def _cpu_worker(args):
-    """One env on one core: `n_steps` env steps of the Pushing workload; returns (env steps done, seconds)."""
-    wid, n_steps, seed = args
+    """One env on one core: `n_steps` env steps of the workload; returns (env steps done, seconds)."""
+    workload, wid, n_steps, seed = args
     try:
         os.sched_setaffinity(0, {wid % os.cpu_count()})
     except Exception:
@@ -49,25 +62,34 @@ def _cpu_worker(args):
     from d3il_b200.scene.blob import load_scene
     from oracle.oracle import OracleEnv          # bench.py's cpu_baseline / reference leg: allowed user of oracle/
 
-    blob, sc = load_scene(TASK)
-    ctxs = load_contexts()
+    wl = WORKLOADS[workload]
+    blob, sc = load_scene(wl["task"])
+    ctxs = load_contexts(wl["ctx"]) if wl["ctx"] else None
     env = OracleEnv(blob, sc.header)
     rng = np.random.default_rng(seed)
-    env.reset(ctxs[wid % 60])
-    des = env.robot_state().copy()
+    n_act, joint_space = wl["n_act"], sc.header["act_dim"] == 8
+    lo, hi = np.array([*WORKSPACE_LO, 0.02])[:n_act], np.array([*WORKSPACE_HI, 0.35])[:n_act]
+
+    def fresh(k):
+        env.reset(ctxs[(wid + k) % len(ctxs)] if ctxs is not None else None)
+        return np.concatenate([env.joint_state()[:7], [0.08]]) if joint_space else np.concatenate([env.robot_state(), [0.0, 1.0, 0.0, 0.0]])
+    des = fresh(0)
     t0 = time.perf_counter()
     for k in range(n_steps):
-        des[:2] = np.clip(des[:2] + rng.uniform(-0.01, 0.01, 2), WORKSPACE_LO, WORKSPACE_HI)
-        _, _, done, _ = env.step(np.concatenate([des, [0.0, 1.0, 0.0, 0.0]]))
+        if joint_space:
+            des[:7] += rng.uniform(-0.01, 0.01, 7)
+            des[7] = 0.08 if (k // 50) % 2 == 0 else 0.0
+        else:
+            des[:n_act] = np.clip(des[:n_act] + rng.uniform(-0.01, 0.01, n_act), lo, hi)
+        _, _, done, _ = env.step(des)
         if done:
-            env.reset(ctxs[(wid + k) % 60])
-            des = env.robot_state().copy()
+            des = fresh(k)
     return n_steps, time.perf_counter() - t0
 
 
-def cpu_sample(n_workers: int, steps_per_worker: int, pool=None):
+def cpu_sample(workload: str, n_workers: int, steps_per_worker: int, pool=None):
     """Bounded sample of the workload on `n_workers` cores; returns (env-steps/s aggregate, wall seconds)."""
-    jobs = [(w, steps_per_worker, 1000 + w) for w in range(n_workers)]
+    jobs = [(workload, w, steps_per_worker, 1000 + w) for w in range(n_workers)]
     t0 = time.perf_counter()
     if n_workers == 1:
         res = [_cpu_worker(jobs[0])]
@@ -85,23 +107,24 @@ def run_reference(args):
     import oracle.oracle as oo
     oo.build()
     cores = os.cpu_count() or 1
-    steps_per_worker = 256
+    task = WORKLOADS[args.workload]["task"]
+    steps_per_worker = 256 if task in ("pushing", "avoiding", "aligning", "sorting_2") else 64
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
         for _ in range(args.warmup):
-            cpu_sample(cores, 32, pool)
+            cpu_sample(args.workload, cores, 32, pool)
         t0 = time.perf_counter()
         tot = 0
         for _ in range(args.steps):
-            v, wall = cpu_sample(cores, steps_per_worker, pool)
+            v, wall = cpu_sample(args.workload, cores, steps_per_worker, pool)
             tot += steps_per_worker * cores
         dt = time.perf_counter() - t0
     value = tot / dt
-    sample = f"{cores} worker processes x {steps_per_worker} env steps of the Pushing workload per step (one fp64 oracle env per core)"
+    sample = f"{cores} worker processes x {steps_per_worker} env steps of the {args.workload} workload per step (one fp64 oracle env per core)"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "pushing-4096env-randomwalk (bounded CPU sample: one env per host core)", "task": TASK, "n_substeps": 35},
+        "config": {"workload": f"{args.workload}-randomwalk (bounded CPU sample: one env per host core)", "task": task},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -109,6 +132,11 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_env launch at the workload's default size, from the committed
+# `ncu --set full` captures (profiles/): filled in per task as captures are taken; None = not captured
+TRAFFIC_NCU = {"pushing": 35.5e6}
+
+
 class ClockSampler:
     FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
@@ -162,49 +190,68 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
-    n = args.envs
+    wl = WORKLOADS[args.workload]
+    task = wl["task"]
+    n = args.envs or wl["envs"]
     K, W = args.steps, max(args.warmup, 3)
 
-    ctxs = load_contexts()
-    ctx_ids = (np.arange(n) + rank * n) % 60
-    ctx_t = torch.tensor(ctxs[ctx_ids], dtype=torch.float32, device=dev)
-    env = BatchedEnv(TASK, n, local)
+    env = BatchedEnv(task, n, local)
+    ctxs = load_contexts(wl["ctx"]) if wl["ctx"] else None
+    ctx_ids = (np.arange(n) + rank * n) % (len(ctxs) if ctxs is not None else 1)
+    ctx_t = torch.tensor(ctxs[ctx_ids], dtype=torch.float32, device=dev) if ctxs is not None else None
     env.reset(ctx_t)
-    quat = torch.tensor([0.0, 1.0, 0.0, 0.0], device=dev).repeat(n, 1)
-    tcp0 = env.robot_state().clone()
-    des = torch.cat([tcp0, quat], 1).contiguous()
-    lo = torch.tensor(WORKSPACE_LO, device=dev)
-    hi = torch.tensor(WORKSPACE_HI, device=dev)
+    joint_space = env.act_dim == 8
+    n_act = wl["n_act"]
+    if joint_space:
+        # Stacking: q_des += U(-0.01, 0.01)^7, gripper command toggled every 50 steps
+        start = env.joint_state().clone()
+        start[:, 7] = 0.08
+    else:
+        quat = torch.tensor([0.0, 1.0, 0.0, 0.0], device=dev).repeat(n, 1)
+        start = torch.cat([env.robot_state().clone(), quat], 1).contiguous()
+    des = start.clone()
+    lo3 = torch.tensor([WORKSPACE_LO[0], WORKSPACE_LO[1], 0.02], device=dev)[:n_act]
+    hi3 = torch.tensor([WORKSPACE_HI[0], WORKSPACE_HI[1], 0.35], device=dev)[:n_act]
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    # synthetic action stream, resident in HBM before the timed region: deltas ~ U(-0.01, 0.01)^2 per env per step
+    policy = None
+    if wl["policy"] == "ddpm":
+        from d3il_b200.simulation.policies import SyntheticDDPMPolicy
+        policy = SyntheticDDPMPolicy(n_act + env.obs_dim, n_act, width=256, n_hidden_layers=8, n_timesteps=4, t_dim=8, device=dev, seed=rank)
     pool_len = 64
-    deltas = (torch.rand(pool_len, n, 2, generator=gen, device=dev) * 0.02 - 0.01)      # host-path (e2e) stream
+    deltas = (torch.rand(pool_len, n, n_act, generator=gen, device=dev) * 0.02 - 0.01)      # host-path (e2e) stream
+    returns = torch.zeros(n, 3, device=dev)          # per-env episode result rows (first three info words)
+    step_no = torch.zeros((), dtype=torch.long, device=dev)
+    last_obs = env.obs.clone()
 
-    def next_delta():
-        return torch.rand(n, 2, generator=gen, device=dev) * 0.02 - 0.01
-    returns = torch.zeros(n, 3, device=dev)          # per-env episode result rows (success, mode, mean_distance)
-
-    def one_step(k):
-        des[:, :2] = torch.minimum(torch.maximum(des[:, :2] + next_delta(), lo), hi)
+    def advance(force=None):
+        # synthetic action stream: policy output (config 3) or U(-0.01, 0.01) deltas integrated on the last DESIRED set-point
+        if policy is not None:
+            delta = policy.predict_batch(torch.cat([des[:, :n_act], last_obs], 1))
+        else:
+            delta = torch.rand(n, n_act, generator=gen, device=dev) * 0.02 - 0.01
+        if joint_space:
+            des[:, :7] += delta
+            des[:, 7] = torch.where((step_no // 50) % 2 == 0, 0.08, 0.0)
+        else:
+            des[:, :n_act] = torch.minimum(torch.maximum(des[:, :n_act] + delta, lo3), hi3)
         obs, rew, done, info = env.step(des)
-        # episode bookkeeping + auto-reset of finished envs (masked reset kernel; desired pose snaps back to the start pose)
-        returns.copy_(torch.where(done.bool().unsqueeze(1), info[:, :3], returns))
-        env.reset(ctx_t, done)
-        des[:, :3] = torch.where(done.bool().unsqueeze(1), tcp0, des[:, :3])
+        last_obs.copy_(obs)
+        step_no.add_(1)
+        # episode bookkeeping + auto-reset of finished envs (masked reset kernel; set-point snaps back to the start pose)
+        m = done if force is None else force
+        returns.copy_(torch.where(m.bool().unsqueeze(1), info[:, :3], returns))
+        env.reset(ctx_t, m)
+        des.copy_(torch.where(m.bool().unsqueeze(1), start, des))
 
-    # pre-roll (untimed, not part of W): spread the envs uniformly over the 400-step episode so the timed region sees
-    # the steady-state mix of episode phases (fresh resets, free motion, rod-box pushing) instead of 4096 synchronised
-    # envs; env i is force-reset once at pre-roll step i % 400.
+    # pre-roll (untimed, not part of W): spread the envs uniformly over the episode so the timed region sees the
+    # steady-state mix of episode phases (fresh resets, free motion, contact) instead of n synchronised envs;
+    # env i is force-reset once at pre-roll step i % ep_len.
     ep_len = env.max_steps_per_episode
     ids = torch.arange(n, device=dev)
     for k in range(ep_len if not args.no_preroll else 0):
-        des[:, :2] = torch.minimum(torch.maximum(des[:, :2] + next_delta(), lo), hi)
-        env.step(des)
-        force = (ids % ep_len == k).to(torch.uint8)
-        env.reset(ctx_t, force)
-        des[:, :3] = torch.where(force.bool().unsqueeze(1), tcp0, des[:, :3])
+        advance((ids % ep_len == k).to(torch.uint8))
     for k in range(W):
-        one_step(k)
+        advance()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -214,7 +261,7 @@ def run_gpu(args):
     torch.cuda.synchronize()
     ev0.record()
     for k in range(K):
-        one_step(W + k)
+        advance()
     ev1.record()
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
@@ -239,12 +286,11 @@ def run_gpu(args):
     # ---- per-kernel device time (CUDA events on the launching stream, inside the library) for the roofline object
     env.set_profiling(True)
     for k in range(8):
-        one_step(k)
+        advance()
     ik_ms, env_ms, nprof = env.get_profile()
     env.set_profiling(False)
     k_env_ms = env_ms / max(nprof, 1)
-    k_ik_ms = ik_ms / max(nprof, 1)
-    n_state = env.scene.header["nq"] + env.scene.header["nv"] * 2 + 9 + 9 + 7 + 16      # persistent fp32 words per env
+    n_state = env.scene.header["nq"] + env.scene.header["nv"] * 2 + 9 + 9 + 7 + 16 + env.scene.header.get("nextra", 0)      # persistent fp32 words per env
     alg_bytes_env = 2 * 4 * n_state + 4 * env.act_dim + 4 * env.obs_dim + 4 + 1 + 4 * env.info_dim
     alg_bytes_launch = alg_bytes_env * n
     peaks = {}
@@ -255,31 +301,43 @@ def run_gpu(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = alg_bytes_launch / (k_env_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                "traffic": TRAFFIC_NCU.get(task), "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                 "kernel": "k_env (+ overlapped k_ik, k_sched)", "kernel_ms": k_env_ms, "alg_bytes_per_env_step": alg_bytes_env,
-                "note": "fused 35-tick kernel is ALU/latency-bound, not HBM-bound (SURVEY §8d); see DESIGN.md for the fp32 issue-rate view"}
+                "note": "fused n_substeps-tick kernel is ALU/latency-bound, not HBM-bound (SURVEY §8d); see DESIGN.md for the fp32 issue-rate view"}
 
     # ---- e2e: same workload through the host-buffer C ABI (numpy in/out, H2D + D2H every step)
     e2e_steps = max(8, min(K, 64))
-    tcp_h = tcp0.cpu().numpy()
+    start_h = start.cpu().numpy().astype(np.float32)
     des_h = des.cpu().numpy().astype(np.float32)          # continue from the steady-state mix of the timed region
-    deltas_h = deltas[:, :, :].cpu().numpy()
-    ctx_h = ctxs[ctx_ids].astype(np.float32)
-    lo_h, hi_h = np.array(WORKSPACE_LO, np.float32), np.array(WORKSPACE_HI, np.float32)
+    deltas_h = deltas.cpu().numpy()
+    ctx_h = ctxs[ctx_ids].astype(np.float32) if ctxs is not None else None
+    lo_h, hi_h = lo3.cpu().numpy(), hi3.cpu().numpy()
     h2d = d2h = 0
+    obs_h = last_obs.cpu().numpy()
     for k in range(3):
         env.step_host(des_h)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for k in range(e2e_steps):
-        des_h[:, :2] = np.clip(des_h[:, :2] + deltas_h[k % pool_len], lo_h, hi_h)
+        if policy is not None:      # policy on the GPU: observations go up, deltas come down, every step
+            pin = torch.from_numpy(np.concatenate([des_h[:, :n_act], obs_h], 1)).to(dev)
+            delta_h = policy.predict_batch(pin).cpu().numpy()
+            h2d += pin.numel() * 4
+            d2h += delta_h.nbytes
+        else:
+            delta_h = deltas_h[k % pool_len]
+        if joint_space:
+            des_h[:, :7] += delta_h
+            des_h[:, 7] = 0.08 if (k // 50) % 2 == 0 else 0.0
+        else:
+            des_h[:, :n_act] = np.clip(des_h[:, :n_act] + delta_h, lo_h, hi_h)
         obs_h, rew_h, done_h, info_h = env.step_host(des_h)
         h2d += des_h.nbytes
         d2h += obs_h.nbytes + rew_h.nbytes + done_h.nbytes + info_h.nbytes
         if done_h.any():
             env.reset_host(ctx_h, done_h)
-            h2d += ctx_h.nbytes + done_h.nbytes
-            des_h[done_h.astype(bool), :3] = tcp_h[done_h.astype(bool)]
+            h2d += (ctx_h.nbytes if ctx_h is not None else 0) + done_h.nbytes
+            des_h[done_h.astype(bool)] = start_h[done_h.astype(bool)]
     dt = time.perf_counter() - t0
     e2e = {"value": n * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d // e2e_steps, "d2h_bytes_per_step": d2h // e2e_steps,
            "steps": e2e_steps, "n_gpus": 1}
@@ -288,20 +346,21 @@ def run_gpu(args):
     import oracle.oracle as oo
     oo.build()
     cores = os.cpu_count() or 1
-    spw = 192
+    spw = 192 if task in ("pushing", "avoiding", "aligning", "sorting_2") else 64
     with mp.get_context("fork").Pool(cores) as pool:
-        cpu_sample(cores, 16, pool)
-        cpu_val, cpu_wall = cpu_sample(cores, spw, pool)
-    one_val, one_wall = cpu_sample(1, 1500)
+        cpu_sample(args.workload, cores, 16, pool)
+        cpu_val, cpu_wall = cpu_sample(args.workload, cores, spw, pool)
+    one_val, one_wall = cpu_sample(args.workload, 1, 8 * spw)
     cpu_baseline = {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
-                    "sample": f"{cores} processes x {spw} env steps (one fp64 oracle env per core, {cpu_wall:.1f} s); single core: {one_val:.0f} env-steps/s over 1500 steps",
+                    "sample": f"{cores} processes x {spw} env steps of the {args.workload} workload (one fp64 oracle env per core, {cpu_wall:.1f} s); single core: {one_val:.0f} env-steps/s over {8 * spw} steps",
                     "single_core_value": one_val}
 
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"pushing-{n}env-per-gpu-randomwalk", "task": TASK, "envs_per_gpu": n, "n_substeps": 35, "episode_len": 400,
-                   "auto_reset": True, "preroll_steps": 0 if args.no_preroll else 400, "l2_note": "state+trajectory working set per step is rewritten every step (no cross-step reuse of inputs); timing is launch-to-launch on one stream"},
+        "config": {"workload": f"{args.workload}-{n}env-per-gpu-" + ("ddpm-mlp-in-loop" if policy is not None else "randomwalk"), "task": task, "envs_per_gpu": n,
+                   "n_substeps": env.n_substeps, "episode_len": ep_len, "auto_reset": True, "preroll_steps": 0 if args.no_preroll else ep_len,
+                   "l2_note": "state+trajectory working set per step is rewritten every step (no cross-step reuse of inputs); timing is launch-to-launch on one stream"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
         "target": {"env_steps_per_sec": 1.0e6, "met": bool(value >= 1.0e6)},
     }))
@@ -315,7 +374,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--envs", type=int, default=N_ENVS, help="envs per GPU")
+    ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the workload's BASELINE.json size)")
+    ap.add_argument("--workload", default="pushing", choices=sorted(WORKLOADS), help="default = the configuration the metric is quoted on")
     ap.add_argument("--no-preroll", action="store_true", help="skip the 400-step episode-phase pre-roll (debug)")
     args = ap.parse_args()
     if args.impl == "reference":

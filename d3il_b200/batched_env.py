@@ -42,6 +42,7 @@ class BatchedEnv:
             self.done = torch.zeros(n, dtype=torch.uint8, device=dev)
             self.info = torch.zeros(n, self.info_dim, device=dev)
             self.tcp = torch.zeros(n, 3, device=dev)
+            self.joints = torch.zeros(n, 8, device=dev)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -72,7 +73,7 @@ class BatchedEnv:
         return self.obs
 
     def step(self, action: torch.Tensor):
-        """action: [n_envs, 7] desired tcp xyz + quat wxyz (float32 CUDA). Returns (obs, reward, done, info) tensors (views
+        """action: [n_envs, act_dim] (float32 CUDA): desired tcp xyz + quat wxyz, or 7 joint set-points + gripper command (Stacking). Returns (obs, reward, done, info) tensors (views
         of the env's output buffers, overwritten by the next call)."""
         action = action.to(self.device, torch.float32).contiguous()
         assert action.shape == (self.n_envs, self.act_dim)
@@ -83,6 +84,11 @@ class BatchedEnv:
     def robot_state(self) -> torch.Tensor:
         _lib.check(self._L.d3il_robot_state(self._h, C.c_void_p(self.tcp.data_ptr()), self._stream()), "d3il_robot_state")
         return self.tcp
+
+    def joint_state(self) -> torch.Tensor:
+        """[n_envs, 8]: joint positions + gripper width (``CubeStacking_Env.robot_state``, stacking.py:218-226)."""
+        _lib.check(self._L.d3il_joint_state(self._h, C.c_void_p(self.joints.data_ptr()), self._stream()), "d3il_joint_state")
+        return self.joints
 
     # ---- host-buffer API (numpy in / numpy out; H2D + D2H inside the call) — the reference-facing end-to-end path
     def reset_host(self, contexts: np.ndarray | None = None, mask: np.ndarray | None = None) -> np.ndarray:
@@ -112,6 +118,11 @@ class BatchedEnv:
         t = np.empty((self.n_envs, 3), dtype=np.float32)
         _lib.check(self._L.d3il_robot_state_host(self._h, t.ctypes.data_as(C.c_void_p)), "d3il_robot_state_host")
         return t
+
+    def joint_state_host(self) -> np.ndarray:
+        j = np.empty((self.n_envs, 8), dtype=np.float32)
+        _lib.check(self._L.d3il_joint_state_host(self._h, j.ctypes.data_as(C.c_void_p)), "d3il_joint_state_host")
+        return j
 
     # ---- parity-test hooks
     def substep(self, n: int = 1):

@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(1024) k_sched(DevCtx c) {
   }
 }
 
-__global__ void __launch_bounds__(IK_THREADS) k_ik(DevCtx c, const float* __restrict__ action, int n_ticks, int use_action, int flag_base) {
+__global__ void __launch_bounds__(IK_THREADS) k_ik(DevCtx c, const float* __restrict__ action, int n_ticks, int use_action, int flag_base, int ctrl_kind, int act_dim) {
   // Programmatic dependent launch: let the env-step kernel (next in the stream) start while this one is still running.
   // It consumes our set-points tick by tick through the release flags below; we never wait on anything, and we are
   // already resident when it is allowed to launch, so the hand-off cannot deadlock.
@@ -91,9 +91,15 @@ __global__ void __launch_bounds__(IK_THREADS) k_ik(DevCtx c, const float* __rest
   IkState s;
   for (int k = 0; k < 7; k++) { s.q[k] = c.ik.q[k * n + e]; s.jt_q[k] = c.ik.jt[k * n + e]; s.jt_qlo[k] = c.ik.jt[(7 + k) * n + e]; s.jt_qd[k] = c.ik.jt[(14 + k) * n + e]; }
   s.valid = c.ik.valid[e];
-  int cart = use_action ? 1 : (row[c.lay.misc + ST_CTRL_MODE] != 0.f);
-  if (use_action) {
-    const float* a = action + (size_t)e * 7;
+  int cart = use_action ? 1 : (row[c.lay.misc + ST_CTRL_MODE] == 1.f);
+  if (use_action && ctrl_kind == 1) {
+    // joint-space action (Stacking): the set-point IS the action, held for the whole env step (Controller.py:99-127, zero
+    // desired velocity); no IK.  The gripper command action[7] is consumed by k_env's pre-step.
+    const float* a = action + (size_t)e * act_dim;
+    for (int k = 0; k < 7; k++) { s.jt_q[k] = a[k]; s.jt_qlo[k] = 0; s.jt_qd[k] = 0; }
+    cart = 0;
+  } else if (use_action) {
+    const float* a = action + (size_t)e * act_dim;
     float nq = rsqrtf(a[3] * a[3] + a[4] * a[4] + a[5] * a[5] + a[6] * a[6]);
     s.des_pos[0] = a[0]; s.des_pos[1] = a[1]; s.des_pos[2] = a[2];
     for (int k = 0; k < 4; k++) s.des_quat[k] = a[3 + k] * nq;
@@ -135,7 +141,7 @@ extern "C" int d3il_create(d3il_env** out, const void* blob, size_t nbytes, int 
   memset(&h->d, 0, sizeof(h->d));
   std::string err;
   if (!d3il_build_model(blob, nbytes, h->m, h->L, err)) { g_err = "d3il_create: " + err; delete h; return -1; }
-  if (h->m.act_dim != 7) { g_err = "d3il_create: only Cartesian (7-D) action scenes are supported"; delete h; return -1; }
+  if (!((h->m.ctrl_kind == 0 && h->m.act_dim == 7) || (h->m.ctrl_kind == 1 && h->m.act_dim == 8))) { g_err = "d3il_create: unsupported action layout"; delete h; return -1; }
   h->device = device; h->n = n_envs; h->launches = 0; h->max_ticks = h->m.n_substeps > 64 ? h->m.n_substeps : 64;
   CK(cudaSetDevice(device));
   DevCtx& d = h->d;
@@ -176,7 +182,7 @@ extern "C" int d3il_create(d3il_env** out, const void* blob, size_t nbytes, int 
   // staging for the host-buffer entry points
   const Model& m = h->m;
   h->in_floats = (size_t)n_envs * (m.act_dim > m.ctx_dim ? m.act_dim : m.ctx_dim);
-  h->out_floats = (size_t)n_envs * (m.obs_dim + 1 + m.info_dim + 3) + (n_envs + 3) / 4 + 8;
+  h->out_floats = (size_t)n_envs * (m.obs_dim + 1 + m.info_dim + 8) + (n_envs + 3) / 4 + 8;
   CK(cudaMallocHost(&h->h_in, h->in_floats * sizeof(float)));
   CK(cudaMallocHost(&h->h_out, h->out_floats * sizeof(float)));
   CK(cudaMallocHost(&h->h_mask, n_envs));
@@ -231,9 +237,9 @@ static cudaError_t launch_step(d3il_env* h, cudaStream_t s, const float* action,
   const int base = h->launch_id * 64;
   static const bool no_pdl = getenv("D3IL_NO_PDL") != nullptr;      // diagnosis: serialise the kernels
   k_sched<<<1, 1024, 0, s>>>(h->d);
-  k_ik<<<h->n_ik_blocks, IK_THREADS, 0, s>>>(h->d, action, n_ticks, gym, base);
+  k_ik<<<h->n_ik_blocks, IK_THREADS, 0, s>>>(h->d, action, n_ticks, gym, base, h->m.ctrl_kind, h->m.act_dim);
   h->launches += 3;
-  return d3il_launch_env(h->d, h->n_single, n_ticks, gym, base, obs, reward, done, info, h->smem_bytes, s, !no_pdl);
+  return d3il_launch_env(h->d, h->m.maxdim, h->n_single, n_ticks, gym, base, action, obs, reward, done, info, h->smem_bytes, s, !no_pdl);
 }
 
 extern "C" int d3il_reset(d3il_env* h, const float* ctx, const uint8_t* mask, float* obs, void* stream) {
@@ -284,6 +290,15 @@ extern "C" int d3il_robot_state(d3il_env* h, float* tcp, void* stream) {
   if (!h || !tcp) { g_err = "d3il_robot_state: null argument"; return -1; }
   CK(cudaSetDevice(h->device));
   d3il_launch_robot_state(h->d, tcp, (cudaStream_t)stream);
+  h->launches += 1;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int d3il_joint_state(d3il_env* h, float* j8, void* stream) {
+  if (!h || !j8) { g_err = "d3il_joint_state: null argument"; return -1; }
+  CK(cudaSetDevice(h->device));
+  d3il_launch_joint_state(h->d, j8, (cudaStream_t)stream);
   h->launches += 1;
   CK(cudaGetLastError());
   return 0;
@@ -340,6 +355,17 @@ extern "C" int d3il_robot_state_host(d3il_env* h, float* tcp) {
   CK(cudaMemcpyAsync(h->h_out, h->d_out, (size_t)h->n * 3 * sizeof(float), cudaMemcpyDeviceToHost, h->own_stream));
   CK(cudaStreamSynchronize(h->own_stream));
   memcpy(tcp, h->h_out, (size_t)h->n * 3 * sizeof(float));
+  return 0;
+}
+
+extern "C" int d3il_joint_state_host(d3il_env* h, float* j8) {
+  if (!h || !j8) { g_err = "d3il_joint_state_host: null argument"; return -1; }
+  CK(cudaSetDevice(h->device));
+  int rc = d3il_joint_state(h, h->d_out, h->own_stream);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(h->h_out, h->d_out, (size_t)h->n * 8 * sizeof(float), cudaMemcpyDeviceToHost, h->own_stream));
+  CK(cudaStreamSynchronize(h->own_stream));
+  memcpy(j8, h->h_out, (size_t)h->n * 8 * sizeof(float));
   return 0;
 }
 

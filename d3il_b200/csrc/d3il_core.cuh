@@ -146,13 +146,14 @@ enum { D3C_IK_ORIGIN = 0, D3C_IK_EE = 84, D3C_PGAIN_POS = 96, D3C_PGAIN_QUAT = 9
        D3C_NUM_ITER = 147, D3C_LRATE = 148, D3C_DT = 149, D3C_INIT_QPOS = 150, D3C_TCP_POS = 157, D3C_TCP_QUAT = 160,
        D3C_GRAVITY = 164, D3C_IMPRATIO = 167, D3C_TOL = 168, D3C_JNT_SOLREF = 169, D3C_JNT_SOLIMP = 171, D3C_MEANINERTIA = 179 };
 enum { D3G_CYLINDER = 5, D3G_BOX = 6 };
-enum { D3T_AVOIDING = 0, D3T_PUSHING = 1, D3T_ALIGNING = 2, D3T_SORTING = 3 };
+enum { D3T_AVOIDING = 0, D3T_PUSHING = 1, D3T_ALIGNING = 2, D3T_SORTING = 3, D3T_STACKING = 4 };
 
 struct Model {
   int task_id, nlink, nobj, nq, nv, ngeom, npair, n_substeps, max_steps, obs_dim, act_dim, ctx_dim, info_dim, ctrl_kind, ntaskp;
   int maxcon, maxrow, nmpair;            // workspace caps and number of structurally non-zero (a>=b) entries of M
   int ws_floats;                          // per-env workspace size
   int nextra;                             // per-env task words outside qpos (Aligning: target pose)
+  int maxdim;                             // largest contact dimension of the scene (3, or 4 with torsional friction: gripper pads)
   // per link
   int l_parent[D3_MAXLINK], l_jtype[D3_MAXLINK], l_qadr[D3_MAXLINK], l_dadr[D3_MAXLINK], l_ndof[D3_MAXLINK], l_limited[D3_MAXLINK];
   unsigned l_anc[D3_MAXLINK];             // bit j set: link j is an ancestor-or-self
@@ -211,7 +212,7 @@ static inline void d3il_layout(const Model& m, Lay& L) {
   const int x1 = o;
   o = x0;
   L.H = take(m.nv * m.nv); L.hdinv = take(m.nv); L.hpiv = take(m.nv); L.jar = take(m.maxrow); L.frcE = take(m.maxrow); L.Jp = take(m.maxrow);
-  L.hb = take(9 * m.maxcon); L.grad = take(m.nv); L.pvec = take(m.nv); L.Ma = take(m.nv); L.tmpv = take(m.nv);
+  L.hb = take(m.maxdim * m.maxdim * m.maxcon); L.grad = take(m.nv); L.pvec = take(m.nv); L.Ma = take(m.nv); L.tmpv = take(m.nv);
   if (x1 > o) o = x1;
   L.etype = 0;
   L.total = o;
@@ -513,16 +514,19 @@ DEVNI int collide_box_box(const real* pA, const real* RA, const real* hA, const 
     real l = norm3(ax);
     if (l < (real)1e-6) continue;
     ax[0] /= l; ax[1] /= l; ax[2] /= l;
-    real dist = dot3(ax, d), ra = 0, rb = 0;
+    real dist = dot3(ax, d), ra = 0, rb = 0, mx = 0;
     for (int k = 0; k < 3; k++) {
       real ak[3] = {RA[k], RA[3 + k], RA[6 + k]}, bk[3] = {RB[k], RB[3 + k], RB[6 + k]};
-      ra += hA[k] * absr(dot3(ax, ak)); rb += hB[k] * absr(dot3(ax, bk));
+      real da = absr(dot3(ax, ak)), db = absr(dot3(ax, bk));
+      ra += hA[k] * da; rb += hB[k] * db;
+      mx = maxr(mx, maxr(da, db));
     }
     real sep = absr(dist) - (ra + rb);
     if (sep > margin) return 0;
+    if (mx > (real)0.9994) continue;      // edge axis within 2 degrees of a face normal: covered by the face test (see oracle)
     if (sep > ebest) { ebest = sep; ecode = 3 * i + j; real sg = dist >= 0 ? (real)1 : (real)-1; en[0] = sg * ax[0]; en[1] = sg * ax[1]; en[2] = sg * ax[2]; }
   }
-  if (ecode >= 0 && ebest * (real)1.05 > best + (real)1e-9 && ebest > best) {
+  if (ecode >= 0 && ebest > best + (real)0.05 * absr(best) + (real)1e-6) {      // edges must beat faces by 5 % + 1 um (sign-symmetric)
     int i = ecode / 3, j = ecode % 3;
     real ca[3] = {pA[0], pA[1], pA[2]}, cb[3] = {pB[0], pB[1], pB[2]};
     for (int k = 0; k < 3; k++) {
@@ -810,7 +814,7 @@ DEVFN real jrow_at(const real* Jrow, int d, int a0, int a1, int b0) { return d <
 // Rows: joint limits first (one dof each), then 3 rows per active contact (elliptic, condim 3).  Returns nefc (all
 // lanes); *coupled is set when some active contact joins two different kinematic-tree blocks (then H is not block
 // diagonal).  Row numbers come from prefix counts over activity flags, so the row order is deterministic.
-template <int G>
+template <int G, int MD>
 DEVFN int make_constraints(const Cx& cx, const Model& m, const Lay& L, real* w, int ncon, int* nlimit, int* coupled) {
   const int nv = m.nv;
   // --- activity flags: joint limit candidates k = (robot link, side), contacts
@@ -850,15 +854,15 @@ DEVFN int make_constraints(const Cx& cx, const Model& m, const Lay& L, real* w, 
   LANES(c, ncon) {
     real* cc = w + L.con + D3_CON_W * c;
     if (w[L.cflag + c] == 0) { cc[19] = -1; continue; }
-    int idx = 0;
-    for (int j = 0; j < c; j++) idx += (int)w[L.cflag + j];
-    int r0 = nl + 3 * idx;
-    if (r0 + 3 > m.maxrow) { cc[19] = -1; overflow = 1; continue; }
+    int r0 = nl;
+    if (MD == 3) { int idx = 0; for (int j = 0; j < c; j++) idx += (int)w[L.cflag + j]; r0 += 3 * idx; }
+    else for (int j = 0; j < c; j++) if (w[L.cflag + j] != 0) r0 += (int)w[L.con + D3_CON_W * j + 15];
+    if (r0 + (MD == 3 ? 3 : (int)cc[15]) > m.maxrow) { cc[19] = -1; overflow = 1; continue; }
     int ip = (int)cc[18];
     cc[19] = (real)r0; cc[20] = (real)m.p_rng[4 * ip]; cc[21] = (real)m.p_rng[4 * ip + 1]; cc[22] = (real)m.p_rng[4 * ip + 2]; cc[23] = (real)m.p_rng[4 * ip + 3];
     if (m.p_cpl[ip]) cpl = 1;
   }
-  for (int c = 0; c < ncon; c++) if (w[L.cflag + c] != 0 && row + 3 <= m.maxrow) row += 3;
+  for (int c = 0; c < ncon; c++) { int dim = MD == 3 ? 3 : (int)w[L.con + D3_CON_W * c + 15]; if (w[L.cflag + c] != 0 && row + dim <= m.maxrow) row += dim; }
   cpl = gori<G>(cx, cpl); overflow = gori<G>(cx, overflow);
   if (overflow) { LANES(z, 1) w[L.misc + ST_STATUS] = (real)(((int)w[L.misc + ST_STATUS]) | 2); }
   *coupled = cpl;
@@ -943,7 +947,7 @@ DEVNI void eval_jar(const Cx& cx, const Model& m, const Lay& L, real* w, int nli
 // Constraint cost at jar (workspace offset jar_off): forces -> frc_off; HESS: per-limit-row curvature in hd and a 3x3
 // block per contact in hb (zero / diagonal / full for the top / bottom / middle zone of the elliptic cone).
 // Returns the group-wide cost.  One lane per limit row / per contact.
-template <int G, bool HESS>
+template <int G, bool HESS, int MD>
 DEVNI real constraint_eval(const Cx& cx, const Model& m, const Lay& L, real* w, int nlimit, int ncon, int jar_off, int frc_off) {
   real cost = 0;
   LANES(i, nlimit) {
@@ -955,30 +959,48 @@ DEVNI real constraint_eval(const Cx& cx, const Model& m, const Lay& L, real* w, 
     const real* cc = w + L.con + D3_CON_W * c;
     int i = (int)cc[19];
     if (i < 0) continue;
+    const int dim = MD == 3 ? 3 : (int)cc[15];
     const tab_t* pr = m.pair + D3_PAIR_W * (int)cc[18];
-    real mu = cc[14], U[3], fr[2] = {(real)pr[3], (real)pr[4]};
-    U[0] = w[jar_off + i] * mu; U[1] = w[jar_off + i + 1] * fr[0]; U[2] = w[jar_off + i + 2] * fr[1];
-    real T = sqrt(U[1] * U[1] + U[2] * U[2]), N = U[0];
-    real H9[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    real mu = cc[14], U[MD], fr[MD - 1], T2 = 0;
+    U[0] = w[jar_off + i] * mu;
+#pragma unroll
+    for (int j = 1; j < MD; j++) { fr[j - 1] = (real)pr[2 + j]; U[j] = j < dim ? w[jar_off + i + j] * fr[j - 1] : (real)0; T2 += U[j] * U[j]; }
+    real T = sqrt(T2), N = U[0];
+    real HB[MD * MD];
+#pragma unroll
+    for (int k = 0; k < MD * MD; k++) HB[k] = 0;
     if (N >= mu * T || (T <= 0 && N >= 0)) {
-      w[frc_off + i] = 0; w[frc_off + i + 1] = 0; w[frc_off + i + 2] = 0;
+#pragma unroll
+      for (int j = 0; j < MD; j++) if (j < dim) w[frc_off + i + j] = 0;
     } else if (mu * N + T <= 0 || (T <= 0 && N < 0)) {
-      for (int j = 0; j < 3; j++) { real Dv = w[L.D + i + j], jj = w[jar_off + i + j]; cost += (real)0.5 * Dv * jj * jj; w[frc_off + i + j] = -Dv * jj; H9[4 * j] = Dv; }
+#pragma unroll
+      for (int j = 0; j < MD; j++) if (j < dim) { real Dv = w[L.D + i + j], jj = w[jar_off + i + j]; cost += (real)0.5 * Dv * jj * jj; w[frc_off + i + j] = -Dv * jj; HB[(MD + 1) * j] = Dv; }
     } else {
       real Dm = w[L.D + i] / maxr((real)1e-15, mu * mu * (1 + mu * mu)), NmT = N - mu * T;
       cost += (real)0.5 * Dm * NmT * NmT;
       real f0 = -Dm * NmT * mu;
-      w[frc_off + i] = f0; w[frc_off + i + 1] = -f0 / T * U[1] * fr[0]; w[frc_off + i + 2] = -f0 / T * U[2] * fr[1];
+      w[frc_off + i] = f0;
+#pragma unroll
+      for (int j = 1; j < MD; j++) if (j < dim) w[frc_off + i + j] = -f0 / T * U[j] * fr[j - 1];
       if (HESS) {
-        real g[3]; g[0] = mu; g[1] = -mu * fr[0] * U[1] / T; g[2] = -mu * fr[1] * U[2] / T;
-        for (int a = 0; a < 3; a++) for (int b2 = 0; b2 < 3; b2++) {
-          real v = g[a] * g[b2];
-          if (a > 0 && b2 > 0) v -= mu * NmT / T * fr[a - 1] * fr[b2 - 1] * ((a == b2 ? (real)1 : (real)0) - U[a] * U[b2] / (T * T));
-          H9[3 * a + b2] = Dm * v;
-        }
+        real g[MD]; g[0] = mu;
+#pragma unroll
+        for (int j = 1; j < MD; j++) g[j] = -mu * fr[j - 1] * U[j] / T;         // rows >= dim: U = 0
+#pragma unroll
+        for (int a = 0; a < MD; a++)
+#pragma unroll
+          for (int b2 = 0; b2 < MD; b2++) {
+            if (a >= dim || b2 >= dim) continue;
+            real v = g[a] * g[b2];
+            if (a > 0 && b2 > 0) v -= mu * NmT / T * fr[a - 1] * fr[b2 - 1] * ((a == b2 ? (real)1 : (real)0) - U[a] * U[b2] / (T * T));
+            HB[MD * a + b2] = Dm * v;
+          }
       }
     }
-    if (HESS) for (int k = 0; k < 9; k++) w[L.hb + 9 * c + k] = H9[k];
+    if (HESS) {
+#pragma unroll
+      for (int k = 0; k < MD * MD; k++) w[L.hb + MD * MD * c + k] = HB[k];
+    }
   }
   return gsum<G>(cx, cost);
 }
@@ -1081,7 +1103,7 @@ DEVFN real mrow_dot(const Model& m, const real* M, int nv, int d, const real* v,
 }
 
 // Newton solver on the primal problem: result in qacc / frcE / qfrc_c.  Returns iterations.
-template <int G, bool CS>
+template <int G, bool CS, int MD>
 DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w, int ne, int nlimit, int ncon, int coupled, real tol, int max_iter) {
   const int nv = m.nv;
   // Envs without active rows take qacc = qacc_smooth but keep walking the (CTA-uniform) iteration loop below.
@@ -1092,18 +1114,18 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
   // ---- warm start: cheaper of qacc_warmstart and qacc_smooth
   if (!done) {
     eval_jar<G>(cx, m, L, w, nlimit, ncon, L.warm, L.jar, true);
-    real cw = constraint_eval<G, false>(cx, m, L, w, nlimit, ncon, L.jar, L.frcE);
+    real cw = constraint_eval<G, false, MD>(cx, m, L, w, nlimit, ncon, L.jar, L.frcE);
     real part = 0;
     LANES(d, nv) part += (real)0.5 * (w[L.warm + d] - w[L.qacc_smooth + d]) * mrow_dot(m, M, nv, d, w + L.warm, w + L.qacc_smooth);
     cw += gsum<G>(cx, part);
     gsync<G>(cx);
     eval_jar<G>(cx, m, L, w, nlimit, ncon, L.qacc_smooth, L.jar, true);
-    real cs = constraint_eval<G, false>(cx, m, L, w, nlimit, ncon, L.jar, L.frcE);
+    real cs = constraint_eval<G, false, MD>(cx, m, L, w, nlimit, ncon, L.jar, L.frcE);
     gsync<G>(cx);
     LANES(d, nv) w[L.qacc + d] = cw < cs ? w[L.warm + d] : w[L.qacc_smooth + d];
     gsync<G>(cx);
   }
-  real cost = 0, oldcost = 0;
+  real cost = 0, oldcost = 0, gn_prev = 0;
   int iter = 0, nsteps = 0;      // nsteps: Newton steps this env actually took (iter also counts idle CTA-uniform passes)
   PHASE_T0();
   for (; iter < max_iter; iter++) {
@@ -1111,7 +1133,7 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
     if (!done) {
     eval_jar<G>(cx, m, L, w, nlimit, ncon, L.qacc, L.jar, true);
     oldcost = cost;
-    cost = constraint_eval<G, true>(cx, m, L, w, nlimit, ncon, L.jar, L.frcE);
+    cost = constraint_eval<G, true, MD>(cx, m, L, w, nlimit, ncon, L.jar, L.frcE);
     real part = 0;
     LANES(d, nv) {
       real s = mrow_dot(m, M, nv, d, w + L.qacc, w + L.qacc_smooth);
@@ -1132,6 +1154,7 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
         if ((d >= a0 && d < a1) || (d >= b0 && d < b1)) {
           const real* Jr = w + L.J + i * D3_JW + (d < a1 && d >= a0 ? d - a0 : (a1 - a0) + d - b0);
           s -= Jr[0] * w[L.frcE + i] + Jr[D3_JW] * w[L.frcE + i + 1] + Jr[2 * D3_JW] * w[L.frcE + i + 2];
+          if (MD == 4 && (int)cc[15] == 4) s -= Jr[3 * D3_JW] * w[L.frcE + i + 3];
         }
       }
       w[L.grad + d] = s; g2 += s * s;
@@ -1146,7 +1169,12 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
     if (scale * gn < tol) done = 1;
     // improvement below what the cost can resolve in this precision: further iterations only chase rounding noise
     // (a gradient-stall test on top of this was measured: +3 % Newton steps, no accuracy gain)
-    if (iter > 0 && (scale * (oldcost - cost) < tol * (real)1e-3 || oldcost - cost <= (sizeof(real) == 4 ? (real)2e-6 : (real)1e-14) * absr(oldcost))) done = 1;
+    // When the cost is large (impacts, deep spawn penetration, a grasp) its fp32 resolution (2e-6 |cost|) is blind to the
+    // light dofs - a box's rotation has inertia 3e-5 kg m^2 - whose accelerations keep converging long after the cost
+    // has gone flat: there the loop also waits for the gradient to stall.  Small costs (boxes at rest: ~5) stop on the cost alone.
+    if (iter > 0 && (absr(cost) < (real)20 || gn > (real)0.5 * gn_prev) &&
+        (scale * (oldcost - cost) < tol * (real)1e-3 || oldcost - cost <= (sizeof(real) == 4 ? (real)2e-6 : (real)1e-14) * absr(oldcost))) done = 1;
+    gn_prev = gn;
     }
     // all groups of the CTA iterate together (converged ones idle) so the Newton body stays fetch-shared
     if (!cta_any<CS>(cx, !done)) break;
@@ -1166,12 +1194,20 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
           const real* cc = w + L.con + D3_CON_W * c;
           const int r0 = (int)cc[19], a0 = (int)cc[20], a1 = (int)cc[21];
           if (r0 < 0 || (int)cc[23] != (int)cc[22] || a0 != bs || gi >= a1) continue;      // gj <= gi < a1
-          const real* Hb = w + L.hb + 9 * c;
+          const real* Hb = w + L.hb + MD * MD * c;
           const real *J0 = w + L.J + r0 * D3_JW, *J1 = J0 + D3_JW, *J2 = J1 + D3_JW;
           const int li = gi - a0, lj = gj - a0;
           real i0 = J0[li], i1 = J1[li], i2 = J2[li];
-          real t0 = i0 * Hb[0] + i1 * Hb[3] + i2 * Hb[6], t1 = i0 * Hb[1] + i1 * Hb[4] + i2 * Hb[7], t2 = i0 * Hb[2] + i1 * Hb[5] + i2 * Hb[8];
-          acc += t0 * J0[lj] + t1 * J1[lj] + t2 * J2[lj];
+          if (MD == 3) {
+            real t0 = i0 * Hb[0] + i1 * Hb[3] + i2 * Hb[6], t1 = i0 * Hb[1] + i1 * Hb[4] + i2 * Hb[7], t2 = i0 * Hb[2] + i1 * Hb[5] + i2 * Hb[8];
+            acc += t0 * J0[lj] + t1 * J1[lj] + t2 * J2[lj];
+          } else {           // 4 x 4 cone block; the block's row/column 3 is zero for condim-3 contacts
+            const bool d4 = (int)cc[15] == 4;
+            real i3 = d4 ? J2[D3_JW + li] : (real)0, j3 = d4 ? J2[D3_JW + lj] : (real)0;
+            real t0 = i0 * Hb[0] + i1 * Hb[4] + i2 * Hb[8] + i3 * Hb[12], t1 = i0 * Hb[1] + i1 * Hb[5] + i2 * Hb[9] + i3 * Hb[13];
+            real t2 = i0 * Hb[2] + i1 * Hb[6] + i2 * Hb[10] + i3 * Hb[14], t3 = i0 * Hb[3] + i1 * Hb[7] + i2 * Hb[11] + i3 * Hb[15];
+            acc += t0 * J0[lj] + t1 * J1[lj] + t2 * J2[lj] + t3 * j3;
+          }
         }
         w[L.H + gi * nv + gj] = acc;
       }
@@ -1183,14 +1219,22 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
       int r0 = (int)cc[19];
       if (r0 < 0 || (int)cc[23] == (int)cc[22]) continue;
       int a0 = (int)cc[20], a1 = (int)cc[21], b0 = (int)cc[22], b1 = (int)cc[23], na = a1 - a0, nn = na + b1 - b0;
-      const real* Hb = w + L.hb + 9 * c;
+      const real* Hb = w + L.hb + MD * MD * c;
       const real *J0 = w + L.J + r0 * D3_JW, *J1 = J0 + D3_JW, *J2 = J1 + D3_JW;
+      const bool d4 = MD == 4 && (int)cc[15] == 4;
       LANES(e, nn * (nn + 1) / 2) {
         int li = m.tri_i[e], lj = m.tri_j[e];
         int gi = li < na ? a0 + li : b0 + li - na, gj = lj < na ? a0 + lj : b0 + lj - na;
         real i0 = J0[li], i1 = J1[li], i2 = J2[li];
-        real t0 = i0 * Hb[0] + i1 * Hb[3] + i2 * Hb[6], t1 = i0 * Hb[1] + i1 * Hb[4] + i2 * Hb[7], t2 = i0 * Hb[2] + i1 * Hb[5] + i2 * Hb[8];
-        w[L.H + gi * nv + gj] += t0 * J0[lj] + t1 * J1[lj] + t2 * J2[lj];
+        if (MD == 3) {
+          real t0 = i0 * Hb[0] + i1 * Hb[3] + i2 * Hb[6], t1 = i0 * Hb[1] + i1 * Hb[4] + i2 * Hb[7], t2 = i0 * Hb[2] + i1 * Hb[5] + i2 * Hb[8];
+          w[L.H + gi * nv + gj] += t0 * J0[lj] + t1 * J1[lj] + t2 * J2[lj];
+        } else {
+          real i3 = d4 ? J2[D3_JW + li] : (real)0, j3 = d4 ? J2[D3_JW + lj] : (real)0;
+          real t0 = i0 * Hb[0] + i1 * Hb[4] + i2 * Hb[8] + i3 * Hb[12], t1 = i0 * Hb[1] + i1 * Hb[5] + i2 * Hb[9] + i3 * Hb[13];
+          real t2 = i0 * Hb[2] + i1 * Hb[6] + i2 * Hb[10] + i3 * Hb[14], t3 = i0 * Hb[3] + i1 * Hb[7] + i2 * Hb[11] + i3 * Hb[15];
+          w[L.H + gi * nv + gj] += t0 * J0[lj] + t1 * J1[lj] + t2 * J2[lj] + t3 * j3;
+        }
       }
       gsync<G>(cx);
     }
@@ -1226,18 +1270,23 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
         int i = (int)cc[19];
         if (i < 0) continue;
         const tab_t* pr = m.pair + D3_PAIR_W * (int)cc[18];
-        real mu = cc[14], U[3], V[3], jl[3], fr[2] = {(real)pr[3], (real)pr[4]};
-        for (int j = 0; j < 3; j++) jl[j] = w[L.jar + i + j] + alpha * w[L.Jp + i + j];
-        U[0] = jl[0] * mu; V[0] = w[L.Jp + i] * mu;
-        U[1] = jl[1] * fr[0]; V[1] = w[L.Jp + i + 1] * fr[0]; U[2] = jl[2] * fr[1]; V[2] = w[L.Jp + i + 2] * fr[1];
-        real T = sqrt(U[1] * U[1] + U[2] * U[2]), N = U[0];
+        const int dim = MD == 3 ? 3 : (int)cc[15];
+        real mu = cc[14], U[MD], V[MD], jl[MD], UV = 0, VV = 0, T2 = 0;
+#pragma unroll
+        for (int j = 0; j < MD; j++) {
+          real fj = j == 0 ? mu : (real)pr[2 + j];
+          jl[j] = j < dim ? w[L.jar + i + j] + alpha * w[L.Jp + i + j] : (real)0;
+          U[j] = jl[j] * fj; V[j] = j < dim ? w[L.Jp + i + j] * fj : (real)0;
+          if (j > 0) { T2 += U[j] * U[j]; UV += U[j] * V[j]; VV += V[j] * V[j]; }
+        }
+        real T = sqrt(T2), N = U[0];
         if (N >= mu * T || (T <= 0 && N >= 0)) {
         } else if (mu * N + T <= 0 || (T <= 0 && N < 0)) {
-          for (int j = 0; j < 3; j++) { real Dv = w[L.D + i + j], jp = w[L.Jp + i + j]; d1p += Dv * jl[j] * jp; d2p += Dv * jp * jp; }
+#pragma unroll
+          for (int j = 0; j < MD; j++) if (j < dim) { real Dv = w[L.D + i + j], jp = w[L.Jp + i + j]; d1p += Dv * jl[j] * jp; d2p += Dv * jp * jp; }
         } else {
           // s = 0.5 Dm (N - mu T)^2 along the line: dN = V0, dT = (U_t . V_t)/T, d2T = (|V_t|^2 - dT^2)/T
           real Dm = w[L.D + i] / maxr((real)1e-15, mu * mu * (1 + mu * mu)), NmT = N - mu * T;
-          real UV = U[1] * V[1] + U[2] * V[2], VV = V[1] * V[1] + V[2] * V[2];
           real dT = UV / T, d2T = (VV - dT * dT) / T, dn = V[0] - mu * dT;
           d1p += Dm * NmT * dn;
           d2p += Dm * (dn * dn - NmT * mu * d2T);
@@ -1267,7 +1316,7 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
   if (ne > 0 && !done) {
     // final force evaluation at the last iterate
     eval_jar<G>(cx, m, L, w, nlimit, ncon, L.qacc, L.jar, true);
-    constraint_eval<G, false>(cx, m, L, w, nlimit, ncon, L.jar, L.frcE);
+    constraint_eval<G, false, MD>(cx, m, L, w, nlimit, ncon, L.jar, L.frcE);
     gsync<G>(cx);
   }
   // qfrc_constraint = J^T f
@@ -1282,6 +1331,7 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
       if ((d >= a0 && d < a1) || (d >= b0 && d < b1)) {
         const real* Jr = w + L.J + i * D3_JW + (d < a1 && d >= a0 ? d - a0 : (a1 - a0) + d - b0);
         s += Jr[0] * w[L.frcE + i] + Jr[D3_JW] * w[L.frcE + i + 1] + Jr[2 * D3_JW] * w[L.frcE + i + 2];
+        if (MD == 4 && (int)cc[15] == 4) s += Jr[3 * D3_JW] * w[L.frcE + i + 3];
       }
     }
     w[L.qfrc_c + d] = s;
@@ -1292,7 +1342,7 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
 
 // ------------------------------------------------------------------------------------------------ one physics tick
 // jt_q / jt_qlo / jt_qd: joint set-point for this tick (from the IK reference in Cartesian mode, or the held pose).
-template <int G, bool CS>
+template <int G, bool CS, int MD>
 DEVFN void physics_tick(const Cx& cx, const Model& m, const Lay& L, real* w, const real* jt_q, const real* jt_qlo, const real* jt_qd, real tol, int max_iter) {
   const int nv = m.nv;
   const real h = m.ctrl[D3C_DT];
@@ -1334,7 +1384,7 @@ DEVFN void physics_tick(const Cx& cx, const Model& m, const Lay& L, real* w, con
   PHASE(2);
   cta_sync<CS>(cx);
   int nlimit = 0, coupled = 0;
-  int ne = make_constraints<G>(cx, m, L, w, ncon, &nlimit, &coupled);
+  int ne = make_constraints<G, MD>(cx, m, L, w, ncon, &nlimit, &coupled);
   PHASE(3);
 #ifdef D3IL_PHASE_TIMING
   if (cx.lane == 0) { count_stat(21, coupled); count_stat(22, ncon); count_stat(23, 1); count_stat(19, ne); }
@@ -1355,7 +1405,7 @@ DEVFN void physics_tick(const Cx& cx, const Model& m, const Lay& L, real* w, con
   chol_solve_part<G>(cx, m, w + L.M, nv, false, m.maxblk, w + L.mdinv, w + L.qacc_smooth);
   PHASE(4);
   cta_sync<CS>(cx);
-  int iters = solve_constraints<G, CS>(cx, m, L, w, ne, nlimit, ncon, coupled, tol, max_iter);
+  int iters = solve_constraints<G, CS, MD>(cx, m, L, w, ne, nlimit, ncon, coupled, tol, max_iter);
   LANES(z, 1) {      // per-env cost counters of the current env step (cost-aware scheduling, diagnostics)
     w[L.misc + ST_COST_ITERS] += (real)iters; w[L.misc + ST_COST_COUPLED] += (real)coupled;
     if ((real)ncon > w[L.misc + ST_COST_NCON]) w[L.misc + ST_COST_NCON] = (real)ncon;

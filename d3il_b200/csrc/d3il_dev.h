@@ -38,10 +38,11 @@ struct DevCtx {
 
 // host-side launchers of the kernels that live in d3il_kernels_env.cu
 cudaError_t d3il_env_kernels_configure(size_t smem_bytes);
-cudaError_t d3il_launch_env(const DevCtx& c, int n_single, int n_ticks, int gym, int flag_base, float* obs, float* reward, uint8_t* done, float* info,
+cudaError_t d3il_launch_env(const DevCtx& c, int maxdim, int n_single, int n_ticks, int gym, int flag_base, const float* action, float* obs, float* reward, uint8_t* done, float* info,
                             size_t smem_bytes, cudaStream_t s, bool programmatic);
 void d3il_launch_reset(const DevCtx& c, const float* ctx, const uint8_t* mask, float* obs, size_t smem_bytes, cudaStream_t s);
 void d3il_launch_robot_state(const DevCtx& c, float* tcp, cudaStream_t s);
+void d3il_launch_joint_state(const DevCtx& c, float* j8, cudaStream_t s);
 int d3il_env_grid(const DevCtx& c, int n_single);
 
 #ifdef D3IL_PHASE_TIMING

@@ -214,6 +214,11 @@ DEVFN void task_obs(const Model& m, const Lay& L, const real* w, float* obs) {
       const real* b = w + L.qpos + D3_NROB + 7 * i;
       obs[2 + 3 * i] = (float)b[0]; obs[3 + 3 * i] = (float)b[1]; obs[4 + 3 * i] = (float)tan_yaw(b + 3);
     }
+  } else if (m.task_id == D3T_STACKING) {     // stacking.py:228-277
+    for (int i = 0; i < 3; i++) {
+      const real* b = w + L.qpos + D3_NROB + 7 * i;
+      obs[4 * i] = (float)b[0]; obs[4 * i + 1] = (float)b[1]; obs[4 * i + 2] = (float)b[2]; obs[4 * i + 3] = (float)tan_yaw(b + 3);
+    }
   } else if (m.task_id == D3T_ALIGNING) {     // aligning.py:205-235
     const real* b = w + L.qpos + D3_NROB;
     for (int k = 0; k < 3; k++) obs[k] = (float)w[L.tcp + k];
@@ -260,6 +265,20 @@ DEVFN int sorting_check_mode(const Model& m, const Lay& L, real* w) {
   return code;
 }
 
+// ---- Stacking (stacking.py:395-447).  misc TASK0 = len(mode_encoding), TASK1 = mode string in base-4 digits (r 1, g 2, b 3),
+// TASK2 = min_inds mask.  taskp: target xy, pos_min_dist, min z gap, gripper-open threshold.
+DEVFN real hypot2(real x, real y) { return sqrt(x * x + y * y); }
+DEVFN real stacking_check_mode(const Model& m, const Lay& L, real* w) {
+  const tab_t* T = m.taskp;
+  int len = (int)w[L.misc + ST_TASK0], code = (int)w[L.misc + ST_TASK1], mins = (int)w[L.misc + ST_TASK2];
+  real d[3], mean = 0, best = 0; int bi = -1;
+  for (int i = 0; i < 3; i++) { const real* b = w + L.qpos + D3_NROB + 7 * i; d[i] = hypot2(b[0] - (real)T[0], b[1] - (real)T[1]); mean += d[i] / 3; }
+  for (int i = 0; i < 3; i++) { real di = ((mins >> i) & 1) ? (real)100000 : d[i]; if (bi < 0 || di < best) { best = di; bi = i; } }
+  if (best <= (real)T[2]) { int p4 = 1; for (int k = 0; k < len; k++) p4 *= 4; code += (bi + 1) * p4; len++; mins |= 1 << bi; }
+  w[L.misc + ST_TASK0] = (real)len; w[L.misc + ST_TASK1] = (real)code; w[L.misc + ST_TASK2] = (real)mins;
+  return mean;
+}
+
 // ---- Aligning (aligning.py:21-30,295-352)
 DEVFN void aligning_dists(const Model& m, const Lay& L, const real* w, real* pd, real* rd) {
   const real *b = w + L.qpos + D3_NROB, *t = w + L.extra;
@@ -289,6 +308,13 @@ DEVFN int task_early_term(const Model& m, const Lay& L, real* w) {
   if (m.task_id == D3T_ALIGNING) {
     real pd, rd; aligning_dists(m, L, w, &pd, &rd);
     if (pd <= (real)m.taskp[0] && rd <= (real)m.taskp[1]) { w[L.misc + ST_TERM] = 1; return 1; }
+    return 0;
+  }
+  if (m.task_id == D3T_STACKING) {
+    const real *r = w + L.qpos + D3_NROB, *g = r + 7, *b = g + 7; const tab_t* T = m.taskp;
+    real dz = minr(absr(r[2] - g[2]), minr(absr(r[2] - b[2]), absr(g[2] - b[2])));
+    real dr = hypot2(r[0] - (real)T[0], r[1] - (real)T[1]), dg = hypot2(g[0] - (real)T[0], g[1] - (real)T[1]), db = hypot2(b[0] - (real)T[0], b[1] - (real)T[1]);
+    if (dr <= (real)T[2] && dg <= (real)T[2] && db <= (real)T[2] && dz > (real)T[3]) { w[L.misc + ST_TERM] = 1; return 1; }
     return 0;
   }
   int success = w[L.tcp + 1] > (real)m.taskp[3];
@@ -325,6 +351,10 @@ DEVFN void task_post(const Model& m, const Lay& L, real* w, float* info) {
     int success = task_early_term(m, L, w);
     int code = sorting_check_mode(m, L, w);
     info[0] = (float)success; info[1] = (float)code; info[2] = (float)w[L.misc + ST_TASK0]; info[3] = (float)w[L.misc + ST_STATUS];
+  } else if (m.task_id == D3T_STACKING) {     // info: success, mode string (base-4 digits), mean_distance, len(mode), status
+    int success = task_early_term(m, L, w);
+    real md = stacking_check_mode(m, L, w);
+    info[0] = (float)success; info[1] = (float)w[L.misc + ST_TASK1]; info[2] = (float)md; info[3] = (float)w[L.misc + ST_TASK0]; info[4] = (float)w[L.misc + ST_STATUS];
   } else if (m.task_id == D3T_ALIGNING) {     // info: success, mode (0 inside / 1 outside push), mean_distance, status
     int success = task_early_term(m, L, w);
     real pd, rd; aligning_dists(m, L, w, &pd, &rd);
@@ -386,9 +416,11 @@ DEVFN void env_reset(const Cx& cx, const Model& m, const Lay& L, real* w, const 
     LANES(d, 7 * m.nobj) w[L.qpos + D3_NROB + d] = ctx[d];
     gsync<G>(cx);
   }
+  if (m.task_id == D3T_STACKING) { LANES(z, 1) w[L.misc + ST_GRIP_SET] = (real)0.04; gsync<G>(cx); }      // stacking.py:474 open_fingers() before the reset tick
   real jq[D3_NARM], jql[D3_NARM], jqd[D3_NARM];
   for (int k = 0; k < D3_NARM; k++) { jq[k] = m.ctrl[D3C_INIT_QPOS + k]; jql[k] = 0; jqd[k] = 0; }
-  physics_tick<G, false>(cx, m, L, w, jq, jql, jqd, tol, max_iter);
+  if (m.maxdim == 4) physics_tick<G, false, 4>(cx, m, L, w, jq, jql, jqd, tol, max_iter);
+  else physics_tick<G, false, 3>(cx, m, L, w, jq, jql, jqd, tol, max_iter);
   // scheduling hint: the first env steps after a reset resolve the deep spawn penetration (16 contacts, many Newton
   // iterations) and are among the most expensive ones, so a fresh env sorts to the front of the next step's order
   LANES(z, 1) w[L.misc + ST_COST_ITERS] = 400;
@@ -398,9 +430,12 @@ DEVFN void env_reset(const Cx& cx, const Model& m, const Lay& L, real* w, const 
 // pre-substep half of GymEnvWrapper.step (gym_env_wrapper.py:67-90): open fingers, Cartesian mode, sample obs /
 // reward / done BEFORE the substeps.
 template <int G>
-DEVFN void env_prestep(const Cx& cx, const Model& m, const Lay& L, real* w, float* obs, float* reward, unsigned char* done) {
+DEVFN void env_prestep(const Cx& cx, const Model& m, const Lay& L, real* w, const float* action, float* obs, float* reward, unsigned char* done) {
   LANES(z, 1) {
-    w[L.misc + ST_GRIP_SET] = (real)0.04; w[L.misc + ST_GRASP] = 0; w[L.misc + ST_CTRL_MODE] = 1;
+    if (m.ctrl_kind == 1) {        // CubeStacking_Env.step (stacking.py:337-346): gripper command in action[7], joint-space set-point
+      const bool open = action[7] > (float)m.taskp[4];
+      w[L.misc + ST_GRIP_SET] = open ? (real)0.04 : (real)0; w[L.misc + ST_GRASP] = open ? (real)0 : (real)1; w[L.misc + ST_CTRL_MODE] = 2;
+    } else { w[L.misc + ST_GRIP_SET] = (real)0.04; w[L.misc + ST_GRASP] = 0; w[L.misc + ST_CTRL_MODE] = 1; }
     w[L.misc + ST_COST_ITERS] = 0; w[L.misc + ST_COST_COUPLED] = 0; w[L.misc + ST_COST_NCON] = 0;
     task_obs(m, L, w, obs);
     *reward = (float)task_reward(m, L, w);

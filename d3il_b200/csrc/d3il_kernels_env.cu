@@ -24,8 +24,9 @@ __device__ __forceinline__ void stage_model(Model* sm, const Model* gm) {
 // IK reference generator: one thread per env (a5/a6).  mode: 1 = take the set-point from `action` (env step),
 // 0 = keep the stored set-point (d3il_substep).  In joint-PD mode (after reset) the held set-point is replicated.
 // Env step: one warp per env.  gym = 1: GymEnvWrapper.step semantics around the ticks; gym = 0: bare ticks (substep).
+template <int MD>
 __global__ void __launch_bounds__(CTA_THREADS, (CTA_THREADS > 256 ? 1 : 2))
-k_env(DevCtx c, int n_single, int n_ticks, int gym, int flag_base, float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ done, float* __restrict__ info) {
+k_env(DevCtx c, int n_single, int n_ticks, int gym, int flag_base, const float* __restrict__ action, float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ done, float* __restrict__ info) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TL_BEGIN(2, blockIdx.x);
   Model* sm = (Model*)smem_raw;
@@ -51,7 +52,7 @@ k_env(DevCtx c, int n_single, int n_ticks, int gym, int flag_base, float* __rest
   float* row = c.state + (size_t)e * c.row;
   for (int i = cx.lane; i < L.n_state; i += G_LANES) w[i] = row[i];
   __syncwarp(cx.mask);
-  if (gym) env_prestep<G_LANES>(cx, m, L, w, obs + (size_t)e * m.obs_dim, reward + e, done + e);
+  if (gym) env_prestep<G_LANES>(cx, m, L, w, action + (size_t)e * m.act_dim, obs + (size_t)e * m.obs_dim, reward + e, done + e);
   for (int t = 0; t < n_ticks; t++) {
     // acquire tick t of the IK reference (k_ik may still be running: programmatic dependent launch)
     PHASE_T0();
@@ -65,7 +66,7 @@ k_env(DevCtx c, int n_single, int n_ticks, int gym, int flag_base, float* __rest
     const float* tr = c.traj + (size_t)t * 21 * c.n + e;
     for (int k = cx.lane; k < 21; k += G_LANES) w[L.jt + k] = __ldcg(tr + (size_t)k * c.n);
     __syncwarp(cx.mask);
-    physics_tick<G_LANES, true>(cx, m, L, w, w + L.jt, w + L.jt + 7, w + L.jt + 14, c.tol, c.max_iter);
+    physics_tick<G_LANES, true, MD>(cx, m, L, w, w + L.jt, w + L.jt + 7, w + L.jt + 14, c.tol, c.max_iter);
   }
   if (gym) env_poststep<G_LANES>(cx, m, L, w, info + (size_t)e * m.info_dim);
   if (e_raw < c.n) for (int i = cx.lane; i < L.n_state; i += G_LANES) row[i] = w[i];
@@ -114,15 +115,17 @@ int d3il_env_grid(const DevCtx& c, int n_single) { return n_single + (c.n - n_si
 
 cudaError_t d3il_env_kernels_configure(size_t smem_bytes) {
   cudaError_t e;
-  if ((e = cudaFuncSetAttribute(k_env, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_env<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_env<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_env<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)) != cudaSuccess) return e;
   // an SM keeps the L1/shared carve-out of whatever is resident: every kernel of the step asks for the maximum shared
   // carve-out so k_env CTAs can join SMs that still run a k_ik warp
-  if ((e = cudaFuncSetAttribute(k_env, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(k_env<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return e;
   return cudaFuncSetAttribute(k_reset, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
-cudaError_t d3il_launch_env(const DevCtx& c, int n_single, int n_ticks, int gym, int flag_base, float* obs, float* reward, uint8_t* done, float* info,
+cudaError_t d3il_launch_env(const DevCtx& c, int maxdim, int n_single, int n_ticks, int gym, int flag_base, const float* action, float* obs, float* reward, uint8_t* done, float* info,
                             size_t smem_bytes, cudaStream_t s, bool programmatic) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(d3il_env_grid(c, n_single)); cfg.blockDim = dim3(c.epc * G_LANES); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = s;
@@ -130,7 +133,8 @@ cudaError_t d3il_launch_env(const DevCtx& c, int n_single, int n_ticks, int gym,
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = programmatic ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, k_env, c, n_single, n_ticks, gym, flag_base, obs, reward, done, info);
+  if (maxdim == 4) return cudaLaunchKernelEx(&cfg, k_env<4>, c, n_single, n_ticks, gym, flag_base, action, obs, reward, done, info);
+  return cudaLaunchKernelEx(&cfg, k_env<3>, c, n_single, n_ticks, gym, flag_base, action, obs, reward, done, info);
 }
 
 void d3il_launch_reset(const DevCtx& c, const float* ctx, const uint8_t* mask, float* obs, size_t smem_bytes, cudaStream_t s) {
@@ -138,6 +142,16 @@ void d3il_launch_reset(const DevCtx& c, const float* ctx, const uint8_t* mask, f
 }
 
 void d3il_launch_robot_state(const DevCtx& c, float* tcp, cudaStream_t s) { k_robot_state<<<(c.n + 127) / 128, 128, 0, s>>>(c, tcp); }
+
+// CubeStacking_Env.robot_state (stacking.py:218-226): 7 joint positions + gripper width (sum of the two finger joints)
+__global__ void k_joint_state(DevCtx c, float* __restrict__ j8) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= c.n) return;
+  const float* row = c.state + (size_t)e * c.row;
+  for (int k = 0; k < 7; k++) j8[(size_t)e * 8 + k] = (float)((double)row[c.lay.qpos + k] + (double)row[c.lay.qlo + k]);
+  j8[(size_t)e * 8 + 7] = row[c.lay.qpos + 7] + row[c.lay.qpos + 8];
+}
+void d3il_launch_joint_state(const DevCtx& c, float* j8, cudaStream_t s) { k_joint_state<<<(c.n + 127) / 128, 128, 0, s>>>(c, j8); }
 
 #ifdef D3IL_PHASE_TIMING
 int d3il_debug_timeline_env(unsigned long long* out) { return cudaMemcpyFromSymbol(out, g_tl, sizeof(unsigned long long) * 4 * 4096) == cudaSuccess ? 0 : -2; }

@@ -17,8 +17,9 @@ static inline bool d3il_build_model(const void* blob, size_t nbytes, Model& m, L
   memset(&m, 0, sizeof(m));
   m.task_id = h[2]; m.nlink = h[3]; m.nobj = h[4]; m.nq = h[5]; m.nv = h[6]; m.ngeom = h[7]; m.npair = h[8]; m.n_substeps = h[9];
   m.max_steps = h[10]; m.obs_dim = h[11]; m.act_dim = h[12]; m.ctx_dim = h[13]; m.info_dim = h[14]; m.ctrl_kind = h[15]; m.ntaskp = h[16]; m.nextra = h[17];
+  const int hdr_maxcon = h[18];
   if (m.nlink > D3_MAXLINK || m.nq > D3_MAXQ || m.nv > D3_MAXV || m.ngeom > D3_MAXGEOM || m.npair > D3_MAXPAIR || m.ntaskp > 32 || m.nextra < 0 || m.nextra > 8) { err = "scene exceeds compiled table sizes"; return false; }
-  if (m.task_id != D3T_AVOIDING && m.task_id != D3T_PUSHING && m.task_id != D3T_ALIGNING && m.task_id != D3T_SORTING) { err = "task not supported by this build of the CUDA path"; return false; }
+  if (m.task_id != D3T_AVOIDING && m.task_id != D3T_PUSHING && m.task_id != D3T_ALIGNING && m.task_id != D3T_SORTING && m.task_id != D3T_STACKING) { err = "task not supported by this build of the CUDA path"; return false; }
   size_t need = 4 * D3SC_HDR_INTS + 8 * ((size_t)m.nlink * D3_LINK_W + (size_t)m.ngeom * D3_GEOM_W + (size_t)m.npair * D3_PAIR_W + D3_CTRL_W + m.ntaskp);
   if (need != nbytes) { err = "scene blob size mismatch"; return false; }
   const double* p = (const double*)((const char*)blob + 4 * D3SC_HDR_INTS);
@@ -49,7 +50,8 @@ static inline bool d3il_build_model(const void* blob, size_t nbytes, Model& m, L
     for (int k = 0; k < D3_PAIR_W; k++) m.pair[D3_PAIR_W * i + k] = (tab_t)p[k];
     int t1 = (int)m.geom[D3_GEOM_W * (int)p[0]], t2 = (int)m.geom[D3_GEOM_W * (int)p[1]];
     conmax += (t1 == D3G_BOX && t2 == D3G_BOX) ? 8 : 1;
-    if ((int)p[2] != 3) { err = "only condim 3 contacts are supported by this build of the CUDA path"; return false; }
+    if ((int)p[2] != 3 && (int)p[2] != 4) { err = "only condim 3 / 4 contacts are supported by the CUDA path"; return false; }
+    if ((int)p[2] > m.maxdim) m.maxdim = (int)p[2];
   }
   for (int k = 0; k < D3_CTRL_W; k++) m.ctrl[k] = (tab_t)p[k];
   p += D3_CTRL_W;
@@ -94,8 +96,9 @@ static inline bool d3il_build_model(const void* blob, size_t nbytes, Model& m, L
   for (int d = 0; d < m.nv; d++) if (m.d_bs[d] == d) { if (m.nblk >= 8) { err = "too many kinematic trees"; return false; } m.blk_s[m.nblk] = d; m.blk_e[m.nblk] = m.d_be[d]; m.nblk++; }
   // contact budget: 4 per free body resting on a support + 12 for transients (deep spawn penetration touches two supports,
   // box-box / rod contacts); overflow raises status bit 2, never drops silently
-  { int cap = 4 * m.nobj + 12; m.maxcon = ((conmax < cap ? conmax : cap) + 3) & ~3; }
-  m.maxrow = 3 * m.maxcon + 4;
+  { int cap = hdr_maxcon > 0 ? hdr_maxcon : 4 * m.nobj + 12; m.maxcon = ((conmax < cap ? conmax : cap) + 3) & ~3; }
+  if (m.maxdim < 3) m.maxdim = 3;
+  m.maxrow = m.maxdim * m.maxcon + 4;
   d3il_layout(m, L);
   m.ws_floats = L.total;
   return true;

@@ -25,7 +25,7 @@ GEOM_TYPE_ID = {"plane": GEOM_PLANE, "sphere": GEOM_SPHERE, "cylinder": GEOM_CYL
 
 HDR_FIELDS = [
     "magic", "version", "task_id", "nlink", "nobj", "nq", "nv", "ngeom", "npair", "n_substeps",
-    "max_steps", "obs_dim", "act_dim", "ctx_dim", "info_dim", "ctrl_kind", "ntaskp", "nextra",
+    "max_steps", "obs_dim", "act_dim", "ctx_dim", "info_dim", "ctrl_kind", "ntaskp", "nextra", "maxcon",
 ]
 
 # CTRL section offsets

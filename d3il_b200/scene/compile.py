@@ -256,6 +256,16 @@ def task_spec(task, ref):
             # pos_min_dist, rot_min_dist, robot_box_dist (aligning.py:200-202); default target pose = XML pose of `target_box`
             taskp=[0.018, 0.048, 0.051, 0.6, 0.15, 0.0, 1.0, 0.0, 0.0, 0.0],
         )
+    if task == "stacking":  # envs/gym_stacking_env/.../objects/stacking_objects.py:13-62, stacking.py:135-226
+        box = lambda n, pos, size: prim(n, "box", size, pos, [0, 1, 0, 0], mass=0.05)
+        return dict(
+            rod=False, gripper=True, n_substeps=30, max_steps=1000, init_tcp=[0.525, 0.0, 0.3], ctrl_kind=1,
+            objects=[box("red_box", [0.5, -0.1, 0.0], [0.03, 0.03, 0.03]), box("green_box", [0.5, 0.0, 0.0], [0.03, 0.03, 0.03]),
+                     box("blue_box", [0.5, 0.0, 0.0], [0.03, 0.05, 0.03])],
+            obs_dim=12, act_dim=8, info_dim=5, maxcon=40,
+            # target_box xy (static, visual only), pos_min_dist, min z gap, gripper-open threshold (stacking.py:202,337-341,425-447)
+            taskp=[0.5, 0.2, 0.06, 0.03, 0.075],
+        )
     raise ValueError(f"task {task!r} not compiled yet")
 
 
@@ -351,6 +361,30 @@ def compile_task(task, ref):
         li, p, R = info["rel"]["rod"]
         invw = body_invweight(li, p + R @ rod.ipos)
         add_geom("rod:geom_rb0", g.type, li, p + R @ g.pos, R @ M.quat2mat(g.quat), g.size, g.params, invw, tag=1)
+    if spec.get("gripper"):
+        # Collision geometry of the gripper.  The two finger-tip pads are real boxes; the finger and hand
+        # MESH geoms are collided as the oriented bounding boxes of their convex hulls (DESIGN.md "deviations": no
+        # general convex-hull narrow phase on this path yet).  Tag 2 = tip pad, 3 = finger hull box, 4 = hand hull box.
+        def mesh_obb(name):
+            import struct
+            raw = open(os.path.join(ref, D3IL, "models/mj/robot/assets", name + ".stl"), "rb").read()
+            ntri = struct.unpack("<I", raw[80:84])[0]
+            tri = np.frombuffer(raw[84:84 + 50 * ntri], dtype=np.dtype([("n", "<f4", 3), ("v", "<f4", (3, 3)), ("a", "<u2")]))
+            v = tri["v"].reshape(-1, 3).astype(np.float64)
+            return 0.5 * (v.min(0) + v.max(0)), 0.5 * (v.max(0) - v.min(0))
+        for bname, tag in (("finger_joint1_tip", 2), ("finger_joint2_tip", 2), ("panda_leftfinger", 3), ("panda_rightfinger", 3), ("panda_hand", 4)):
+            b = body_by_name[bname]
+            li, p, R = info["rel"][bname]
+            invw = body_invweight(li, p + R @ b.ipos)
+            for g in b.geoms:
+                if g.params["contype"] == 0 and g.params["conaffinity"] == 0:
+                    continue                                       # visual copies (`*:geom1`)
+                Rg = R @ M.quat2mat(g.quat)
+                if g.type == "mesh":
+                    c, half = mesh_obb(g.mesh)
+                    add_geom(g.name + "_rb0", "box", li, p + R @ g.pos + Rg @ c, Rg, half, g.params, invw, tag=tag)
+                else:
+                    add_geom(g.name + "_rb0", g.type, li, p + R @ g.pos, Rg, g.size, g.params, invw, tag=tag)
     for k, o in enumerate(objs):
         li = 9 + k
         invw = body_invweight(li, links[li].ipos)
@@ -364,6 +398,13 @@ def compile_task(task, ref):
             a, b = geoms[i], geoms[j]
             if a["link"] == b["link"]:
                 continue                                        # same body / both static
+            if a["link"] >= 0 and b["link"] >= 0 and a["link"] < 9 and b["link"] < 9:
+                # gripper self-pairs: finger bodies are children of the hand (parent filter); of the finger-finger pairs only
+                # tip pad vs tip pad is kept (the hull boxes of two fingers touch face to face when the gripper is shut)
+                if not (a["tag"] == 2 and b["tag"] == 2):
+                    continue
+            if min(a["link"], b["link"]) == -1 and max(a["link"], b["link"]) < 9 and 4 in (a["tag"], b["tag"]):
+                continue                                        # hand vs table: unreachable before the fingers are 4 cm deep
             pa, pb = a["params"], b["params"]
             if not ((pa["contype"] & pb["conaffinity"]) or (pb["contype"] & pa["conaffinity"])):
                 continue
@@ -443,7 +484,7 @@ def compile_task(task, ref):
     header = dict(magic=B.MAGIC, version=B.VERSION, task_id=B.TASK_IDS[task.split("_")[0]], nlink=nlink, nobj=nobj, nq=nq, nv=nv, ngeom=len(geoms),
                   npair=len(pairs), n_substeps=spec["n_substeps"], max_steps=spec["max_steps"], obs_dim=spec["obs_dim"], act_dim=spec["act_dim"],
                   ctx_dim=7 * nobj + spec.get("nextra", 0), info_dim=spec["info_dim"], ctrl_kind=spec["ctrl_kind"], ntaskp=len(spec["taskp"]),
-                  nextra=spec.get("nextra", 0))
+                  nextra=spec.get("nextra", 0), maxcon=spec.get("maxcon", 0))
     scene = B.Scene(header, link_tab, geom_tab, pair_tab, ctrl, np.array(spec["taskp"], float))
     report = dict(
         task=task, header=header, links=[L.name for L in links], link_mass=[L.mass for L in links],
@@ -468,6 +509,10 @@ def export_contexts(ref, out_dir):
     c = pickle.load(open(os.path.join(ref, "environments/dataset/data/aligning/test_contexts.pkl"), "rb"))
     arr = np.array([[[p[0], p[1], 0.0, *q], [tp[0], tp[1], 0.0, *tq]] for p, q, tp, tq in c], dtype=np.float64)
     np.save(os.path.join(out_dir, "aligning_test_contexts.npy"), arr)
+    # Stacking (stacking.py:99-129): red / green / blue boxes at [x, y, 0] + quat; the 4th entry (target) is never applied
+    c = pickle.load(open(os.path.join(ref, "environments/dataset/data/stacking/test_contexts.pkl"), "rb"))
+    arr = np.array([[[e[0][0], e[0][1], 0.0, *e[1]] for e in ctx[:3]] for ctx in c], dtype=np.float64)
+    np.save(os.path.join(out_dir, "stacking_test_contexts.npy"), arr)
     # Sorting: `<k>_test_contexts.pkl` are NOT shipped -> drawn here from the six BlockContextManager boxes
     # (sorting.py:52-74,88-119) with our own seeded generator; boxes are placed at z = 0.05 (sorting.py:130-181)
     lows = np.array([[0.4, -0.15], [0.4, -0.05], [0.4, 0.05], [0.55, -0.15], [0.55, -0.05], [0.55, 0.05]])
@@ -490,7 +535,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
     ap.add_argument("--out", default=os.path.join(os.path.dirname(__file__), "..", "scenes"))
-    ap.add_argument("--tasks", nargs="*", default=["avoiding", "pushing", "sorting_2", "sorting_4", "sorting_6", "aligning"])
+    ap.add_argument("--tasks", nargs="*", default=["avoiding", "pushing", "sorting_2", "sorting_4", "sorting_6", "aligning", "stacking"])
     a = ap.parse_args()
     os.makedirs(a.out, exist_ok=True)
     for t in a.tasks:

@@ -42,14 +42,20 @@ int d3il_reset(d3il_env* env, const float* ctx, const uint8_t* mask, float* obs,
 
 /* Replaces GymEnvWrapper.step + task overrides (gyms/gym_env_wrapper.py:45-100, pushing.py:335-339,
  * avoiding.py:168-171): one env step = n_substeps physics ticks of Scene.next_step (core/Scene.py:121-138).
- * action: dev [n_envs, act_dim] (desired tcp xyz + quat wxyz).  Outputs (dev): obs [n_envs, obs_dim] f32,
+ * action: dev [n_envs, act_dim]: desired tcp xyz + quat wxyz (act_dim 7: Avoiding, Pushing, Sorting, Aligning), or
+ * 7 joint set-points + gripper command (act_dim 8: CubeStacking_Env.step, stacking.py:331-393).  Outputs (dev): obs [n_envs, obs_dim] f32,
  * reward [n_envs] f32, done [n_envs] u8 (all three sampled BEFORE the substeps, as the reference does),
  * info [n_envs, info_dim] f32 sampled after them (pushing: success, mode, mean_distance, status;
- * avoiding: success, 9 mode bits, status).  status != 0 flags a per-env numerical fault / contact overflow. */
+ * avoiding: success, 9 mode bits, status; sorting: success, packed mode, mode_step, status; aligning: success, mode,
+ * mean_distance, status; stacking: success, mode string in base-4 digits, mean_distance, len(mode), status).  status != 0 flags a per-env numerical fault / contact overflow. */
 int d3il_step(d3il_env* env, const float* action, float* obs, float* reward, uint8_t* done, float* info, void* cu_stream);
 
 /* Replaces GymEnvWrapper.robot_state() (gym_env_wrapper.py:160-189): tcp position, dev [n_envs, 3]. */
 int d3il_robot_state(d3il_env* env, float* tcp, void* cu_stream);
+
+/* Replaces CubeStacking_Env.robot_state() (stacking.py:218-226; MjRobot.receiveState MjRobot.py:140-183): 7 joint
+ * positions + gripper width, dev [n_envs, 8]. */
+int d3il_joint_state(d3il_env* env, float* j8, void* cu_stream);
 
 /* Host-buffer variants: the same calls with HOST pointers; inputs are staged through pinned memory, copied to the
  * device, the kernels run, outputs are copied back and the call returns after synchronising (this is the
@@ -57,10 +63,11 @@ int d3il_robot_state(d3il_env* env, float* tcp, void* cu_stream);
 int d3il_reset_host(d3il_env* env, const float* ctx, const uint8_t* mask, float* obs);
 int d3il_step_host(d3il_env* env, const float* action, float* obs, float* reward, uint8_t* done, float* info);
 int d3il_robot_state_host(d3il_env* env, float* tcp);
+int d3il_joint_state_host(d3il_env* env, float* j8);
 
 /* Parity-test hooks: n physics ticks under the current controller / flat fp64 state of one env (layout shared with
  * oracle/d3il_oracle.c::d3o_get_state: qpos, qvel, qacc_warmstart, qfrc_bias[9], tcp[7], ik_q[7], des pose[7],
- * joint set-point q[7] qd[7], 8 scalars, 8 task words).  These synchronise the device. */
+ * joint set-point q[7] qd[7], 8 scalars, 8 task words, then the scene's extra words, e.g. Aligning's target pose).  These synchronise the device. */
 int d3il_substep(d3il_env* env, int n, void* cu_stream);
 int d3il_get_state(d3il_env* env, double* out_host, int env_index);
 int d3il_set_state(d3il_env* env, const double* in_host, int env_index);

@@ -41,7 +41,7 @@ enum { C_IK_ORIGIN = 0, C_IK_EE = 84, C_PGAIN_POS = 96, C_PGAIN_QUAT = 99, C_PGA
        C_JNT_SOLREF = 169, C_JNT_SOLIMP = 171, C_MEANINERTIA = 179 };
 
 enum { G_PLANE = 0, G_SPHERE = 2, G_CYLINDER = 5, G_BOX = 6 };
-enum { TASK_AVOIDING = 0, TASK_PUSHING = 1, TASK_ALIGNING = 2, TASK_SORTING = 3 };
+enum { TASK_AVOIDING = 0, TASK_PUSHING = 1, TASK_ALIGNING = 2, TASK_SORTING = 3, TASK_STACKING = 4 };
 
 #define MAXLINK 16
 #define MAXQ 64
@@ -423,16 +423,23 @@ static int collide_box_box(const double* pA, const double* RA, const double* hA,
     double l = norm3(ax);
     if (l < 1e-6) continue;
     for (int k = 0; k < 3; k++) ax[k] /= l;
-    double dist = dot3(ax, d), ra = 0, rb = 0;
+    double dist = dot3(ax, d), ra = 0, rb = 0, mx = 0;
     for (int k = 0; k < 3; k++) {
       double ak[3] = {RA[k], RA[3 + k], RA[6 + k]}, bk[3] = {RB[k], RB[3 + k], RB[6 + k]};
-      ra += hA[k] * fabs(dot3(ax, ak)); rb += hB[k] * fabs(dot3(ax, bk));
+      double da = fabs(dot3(ax, ak)), db = fabs(dot3(ax, bk));
+      ra += hA[k] * da; rb += hB[k] * db;
+      if (da > mx) mx = da;
+      if (db > mx) mx = db;
     }
     double sep = fabs(dist) - (ra + rb);
     if (sep > margin) return 0;
+    /* an edge axis within 2 degrees of a face normal (nearly parallel boxes) is that face contact in disguise: between
+       two such axes the SAT would be decided by rounding noise, with 1 contact on one side and 4 on the other */
+    if (mx > 0.9994) continue;
     if (sep > ebest) { ebest = sep; ecode = 3 * i + j; double sg = dist >= 0 ? 1 : -1; for (int k = 0; k < 3; k++) en[k] = sg * ax[k]; }
   }
-  if (ecode >= 0 && ebest * 1.05 > best + 1e-9 && ebest > best) {
+  /* an edge-edge axis must beat the best face axis by 5 % + 1 um (sign-symmetric: margin contacts have positive separations) */
+  if (ecode >= 0 && ebest > best + 0.05 * fabs(best) + 1e-6) {
     /* edge-edge: one contact at the closest points of the two supporting edges */
     int i = ecode / 3, j = ecode % 3;
     double ca[3], cb[3];
@@ -1029,6 +1036,11 @@ static void get_obs(const Env* e, float* obs) {
       const double* b = e->qpos + NROB + 7 * i;
       obs[2 + 3 * i] = (float)b[0]; obs[3 + 3 * i] = (float)b[1]; obs[4 + 3 * i] = (float)tan_yaw(b + 3);
     }
+  } else if (e->task_id == TASK_STACKING) {    /* stacking.py:228-277: (pos xyz, tan yaw) of red, green, blue */
+    for (int i = 0; i < 3; i++) {
+      const double* b = e->qpos + NROB + 7 * i;
+      obs[4 * i] = (float)b[0]; obs[4 * i + 1] = (float)b[1]; obs[4 * i + 2] = (float)b[2]; obs[4 * i + 3] = (float)tan_yaw(b + 3);
+    }
   } else if (e->task_id == TASK_ALIGNING) {    /* aligning.py:205-235: tcp xyz, box pos + quat (qpos), target pos + quat (model.body_pos/quat) */
     const double* b = e->qpos + NROB;
     for (int k = 0; k < 3; k++) obs[k] = (float)e->tcp_pos[k];
@@ -1073,6 +1085,26 @@ static int sorting_check_mode(Env* e) {         /* sorting.py:460-507 + decode_m
   int code = 0;
   for (int i = 0; i < e->nobj; i++) if (!((zero >> i) & 1)) code |= 1 << (7 - i);
   return code;
+}
+
+/* ---- Stacking (stacking.py:395-447).  task_state: [0] len(mode_encoding), [1] mode string as base-4 digits (r 1, g 2, b 3;
+ * first arrival in the lowest digit), [2] bitmask of min_inds.  taskp: target xy, pos_min_dist, min z gap, gripper threshold. */
+static int stacking_early_term(Env* e) {
+  const double *r = e->qpos + NROB, *g = r + 7, *b = g + 7, *T = e->taskp;
+  double dz = fmin(fabs(r[2] - g[2]), fmin(fabs(r[2] - b[2]), fabs(g[2] - b[2])));
+  double dr = hypot(r[0] - T[0], r[1] - T[1]), dg = hypot(g[0] - T[0], g[1] - T[1]), db = hypot(b[0] - T[0], b[1] - T[1]);
+  if (dr <= T[2] && dg <= T[2] && db <= T[2] && dz > T[3]) { e->terminated = 1; return 1; }
+  return 0;
+}
+static double stacking_check_mode(Env* e) {     /* returns mean_distance; appends to the mode string */
+  const double* T = e->taskp;
+  int len = (int)e->task_state[0], code = (int)e->task_state[1], mins = (int)e->task_state[2];
+  double d[3], mean = 0, best = 0; int bi = -1;
+  for (int i = 0; i < 3; i++) { const double* b = e->qpos + NROB + 7 * i; d[i] = hypot(b[0] - T[0], b[1] - T[1]); mean += d[i] / 3; }
+  for (int i = 0; i < 3; i++) { double di = (mins >> i) & 1 ? 100000.0 : d[i]; if (bi < 0 || di < best) { best = di; bi = i; } }
+  if (best <= T[2]) { int p4 = 1; for (int k = 0; k < len; k++) p4 *= 4; code += (bi + 1) * p4; len++; mins |= 1 << bi; }
+  e->task_state[0] = len; e->task_state[1] = code; e->task_state[2] = mins;
+  return mean;
 }
 
 /* ---- Aligning (aligning.py:21-30,295-352) */
@@ -1158,19 +1190,28 @@ void d3o_reset(Env* e, const double* ctx) {
   memcpy(e->jt_q, e->qpos, 8 * NARM); memset(e->jt_qd, 0, sizeof e->jt_qd);       /* jointTrackingController.setSetPoint(init_qpos) */
   /* manager.start(context): raw qpos write, no mj_forward */
   if (ctx) for (int i = NROB; i < e->nlink; i++) memcpy(e->qpos + e->link[i].qadr, ctx + 7 * (i - NROB), 56);
+  if (e->task_id == TASK_STACKING) e->grip_set = 0.04;                             /* stacking.py:474 robot.open_fingers() before the reset tick */
   if (ctx && e->nextra) memcpy(e->extra, ctx + 7 * e->nobj, 8 * e->nextra);        /* joint-less target body: model.body_pos/quat (MjScene.py:271-285) */
   physics_step(e);                                                                 /* scene.next_step(): exactly one tick */
 }
 
 /* GymEnvWrapper.step — gyms/gym_env_wrapper.py:45-100 + task overrides */
 void d3o_step(Env* e, const double* action, float* obs, double* reward, int* done, double* info) {
-  e->grip_set = 0.04; e->grasp_flag = 0;                                           /* :67 robot.open_fingers() */
-  double n = sqrt(action[3] * action[3] + action[4] * action[4] + action[5] * action[5] + action[6] * action[6]);
-  memcpy(e->des_pos, action, 24); for (int k = 0; k < 4; k++) e->des_quat[k] = action[3 + k] / n;   /* IKControllers.py:346-362 */
-  e->ctrl_mode = 1;
+  if (e->ctrl_kind == 1) {
+    /* CubeStacking_Env.step (stacking.py:331-393): 8-D action = joint set-point + gripper command; joint PD (zero FF) */
+    if (action[7] > e->taskp[4]) { e->grip_set = 0.04; e->grasp_flag = 0; }        /* open_fingers() */
+    else { e->grip_set = 0.0; e->grasp_flag = 1; }                                 /* close_fingers(duration=0) Robots.py:430-435 */
+    memcpy(e->jt_q, action, 8 * NARM); memset(e->jt_qd, 0, sizeof e->jt_qd);       /* Controller.py:99-127 setSetPoint(q, 0, 0) */
+    e->ctrl_mode = 2;
+  } else {
+    e->grip_set = 0.04; e->grasp_flag = 0;                                         /* :67 robot.open_fingers() */
+    double n = sqrt(action[3] * action[3] + action[4] * action[4] + action[5] * action[5] + action[6] * action[6]);
+    memcpy(e->des_pos, action, 24); for (int k = 0; k < 4; k++) e->des_quat[k] = action[3 + k] / n;   /* IKControllers.py:346-362 */
+    e->ctrl_mode = 1;
+  }
   get_obs(e, obs); *reward = get_reward(e);
   int early = e->task_id == TASK_PUSHING ? pushing_early_term(e) : e->task_id == TASK_SORTING ? sorting_early_term(e)
-            : e->task_id == TASK_ALIGNING ? aligning_early_term(e) : avoiding_early_term(e);
+            : e->task_id == TASK_ALIGNING ? aligning_early_term(e) : e->task_id == TASK_STACKING ? stacking_early_term(e) : avoiding_early_term(e);
   *done = e->terminated || early || e->step_count >= e->max_steps - 1;             /* :124-137 */
   for (int i = 0; i < e->n_substeps; i++) physics_step(e);
   e->step_count++;
@@ -1182,6 +1223,10 @@ void d3o_step(Env* e, const double* action, float* obs, double* reward, int* don
   } else if (e->task_id == TASK_SORTING) {     /* sorting.py:444-458 */
     int success = sorting_early_term(e);
     info[0] = success; info[1] = sorting_check_mode(e); info[2] = e->task_state[0]; info[3] = e->status;
+  } else if (e->task_id == TASK_STACKING) {    /* stacking.py:381-393: success, mode string, mean_distance, len(mode) (success_1/2 = len > 0 / > 1) */
+    int success = stacking_early_term(e);
+    double md = stacking_check_mode(e);
+    info[0] = success; info[1] = e->task_state[1]; info[2] = md; info[3] = e->task_state[0]; info[4] = e->status;
   } else if (e->task_id == TASK_ALIGNING) {    /* aligning.py:289-319 */
     int success = aligning_early_term(e);
     double pd, rd; aligning_dists(e, &pd, &rd);
@@ -1198,6 +1243,8 @@ void d3o_step(Env* e, const double* action, float* obs, double* reward, int* don
 }
 
 void d3o_robot_state(const Env* e, double* tcp) { memcpy(tcp, e->tcp_pos, 24); }
+/* CubeStacking_Env.robot_state (stacking.py:218-226): joint positions + gripper width (MjRobot.py:176-183: sum of the finger joints) */
+void d3o_joint_state(const Env* e, double* j8) { memcpy(j8, e->qpos, 8 * NARM); j8[7] = e->qpos[7] + e->qpos[8]; }
 void d3o_get_obs(const Env* e, float* obs) { get_obs(e, obs); }
 
 /* ------------------------------------------------------------------ flat state (shared layout with the CUDA library's get/set_state) */

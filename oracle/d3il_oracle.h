@@ -13,6 +13,7 @@ void d3o_reset(Env* e, const double* ctx /* [nobj*7] xyz+quat per free object, o
 void d3o_step(Env* e, const double* action, float* obs, double* reward, int* done, double* info);
 void d3o_substep(Env* e, int n);
 void d3o_robot_state(const Env* e, double* tcp3);
+void d3o_joint_state(const Env* e, double* j8);
 void d3o_get_obs(const Env* e, float* obs);
 int d3o_state_dim(const Env* e);
 void d3o_get_state(const Env* e, double* out);

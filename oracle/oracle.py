@@ -36,6 +36,7 @@ def lib():
         L.d3o_step.argtypes = [vp, dp, fp, dp, ip, dp]
         L.d3o_substep.argtypes = [vp, C.c_int]
         L.d3o_robot_state.argtypes = [vp, dp]
+        L.d3o_joint_state.argtypes = [vp, dp]
         L.d3o_get_obs.argtypes = [vp, fp]
         L.d3o_state_dim.argtypes = [vp]
         L.d3o_state_dim.restype = C.c_int
@@ -97,6 +98,11 @@ class OracleEnv:
 
     def substep(self, n=1):
         self.L.d3o_substep(self.h, n)
+
+    def joint_state(self):
+        j = np.zeros(8)
+        self.L.d3o_joint_state(self.h, _dp(j))
+        return j
 
     def robot_state(self):
         t = np.zeros(3)

@@ -35,11 +35,12 @@ int emu_state_dim(Emu* e) { return d3il_state_dim(e->m); }
 
 static void tick(Emu* e) {
   real* w = e->w.data();
-  if (w[e->L.misc + ST_CTRL_MODE] != 0) {
+  if (w[e->L.misc + ST_CTRL_MODE] == 1) {
     if (!e->ik.valid) { for (int k = 0; k < 7; k++) e->ik.q[k] = (double)w[e->L.qpos + k] + (double)w[e->L.qlo + k]; e->ik.valid = 1; }
     ik_tick(e->m.ctrl, e->ik, e->V, &e->vwarm, e->sn, e->cs);
   }
-  physics_tick<1, false>(CX, e->m, e->L, w, e->ik.jt_q, e->ik.jt_qlo, e->ik.jt_qd, e->tol, e->max_iter);
+  if (e->m.maxdim == 4) physics_tick<1, false, 4>(CX, e->m, e->L, w, e->ik.jt_q, e->ik.jt_qlo, e->ik.jt_qd, e->tol, e->max_iter);
+  else physics_tick<1, false, 3>(CX, e->m, e->L, w, e->ik.jt_q, e->ik.jt_qlo, e->ik.jt_qd, e->tol, e->max_iter);
 }
 void emu_reset(Emu* e, const double* ctx) {
   std::vector<float> c(e->m.ctx_dim > 0 ? e->m.ctx_dim : 1);
@@ -50,12 +51,18 @@ void emu_reset(Emu* e, const double* ctx) {
 }
 void emu_step(Emu* e, const double* action, float* obs, double* reward, int* done, double* info) {
   real* w = e->w.data();
-  double n = sqrt(action[3] * action[3] + action[4] * action[4] + action[5] * action[5] + action[6] * action[6]);
-  for (int k = 0; k < 3; k++) e->ik.des_pos[k] = (real)action[k];
-  for (int k = 0; k < 4; k++) e->ik.des_quat[k] = (real)(action[3 + k] / n);
+  float act[8];
+  for (int k = 0; k < e->m.act_dim; k++) act[k] = (float)action[k];
+  if (e->m.ctrl_kind == 1) {      // joint-space set-point (k_ik's ctrl_kind == 1 branch); float32 like the device action buffer
+    for (int k = 0; k < 7; k++) { e->ik.jt_q[k] = (real)act[k]; e->ik.jt_qlo[k] = 0; e->ik.jt_qd[k] = 0; }
+  } else {
+    double n = sqrt(action[3] * action[3] + action[4] * action[4] + action[5] * action[5] + action[6] * action[6]);
+    for (int k = 0; k < 3; k++) e->ik.des_pos[k] = (real)action[k];
+    for (int k = 0; k < 4; k++) e->ik.des_quat[k] = (real)(action[3 + k] / n);
+  }
   float r; unsigned char d; float inf[16];
   e->vwarm = 0;                 // like a kernel launch: exact sin/cos and a cold eigenbasis at the first IK iteration
-  env_prestep<1>(CX, e->m, e->L, w, obs, &r, &d);
+  env_prestep<1>(CX, e->m, e->L, w, act, obs, &r, &d);
   for (int i = 0; i < e->m.n_substeps; i++) tick(e);
   env_poststep<1>(CX, e->m, e->L, w, inf);
   *reward = r; *done = d;

@@ -112,3 +112,60 @@ def test_aligning_box_rests_and_reports_target():
     assert np.allclose(con[:, 10], 0.3 / np.sqrt(3))                     # priority-1 plate friction wins over the table's
     pd = np.linalg.norm(obs[3:6] - obs[10:13])
     assert info[1] == 1 and abs(info[2] - 0.5 * (pd + 2 * np.arccos(abs(obs[6:10] @ obs[13:17])) / np.pi)) < 1e-4
+
+
+def test_stacking_grasp_and_lift_fp64_and_fp32():
+    """Joint-space action + gripper (ctrl_kind 1), condim-4 pad / finger-hull contacts, 4 x 4 cone blocks: the scripted
+    grasp lifts the red box 14 cm in the oracle; the kernel core follows teacher-forced, fp64 to 1e-8, fp32 inside the
+    tolerance box for >= 85 % of the env steps."""
+    from tests.util import scripted_grasp_actions
+    blob, sc = load_scene("stacking")
+    nq, nv = sc.header["nq"], sc.header["nv"]
+    ctx = task_contexts("stacking")[1]
+    o = OracleEnv(blob, sc.header)
+    obs0 = o.reset(ctx)
+    acts = scripted_grasp_actions(sc, ctx, o.robot_state(), o.joint_state()[:7], obs0)
+    emus = {p: EmuEnv(blob, sc.header, p) for p in ("f64", "f32")}
+    for e in emus.values():
+        e.reset(ctx)
+    assert np.abs(o.get_state()[:nq + 2 * nv + 56] - emus["f64"].get_state()[:nq + 2 * nv + 56]).max() < 1e-6
+    errs, max_rows = [], 0
+    for a in acts:
+        s0 = o.get_state()
+        ro = o.step(a)
+        max_rows = max(max_rows, o.probe("counts")[1])
+        for prec, e in emus.items():
+            e.set_state(s0)
+            re = e.step(a)
+            assert ro[2] == re[2] and np.allclose(ro[3][:4], re[3][:4], atol=1e-4) and re[3][4] == 0
+            assert np.allclose(ro[0], re[0], rtol=1e-3, atol=1e-4)
+            if prec == "f64":
+                assert np.abs(o.get_state()[:nq] - e.get_state()[:nq]).max() < 1e-7          # actions pass through float32 on the kernel side
+            else:
+                errs.append(step_errors(o.get_state(), e.get_state(), nq, nv))
+    errs = np.array(errs)
+    assert (errs.max(axis=1) <= 1.0).mean() >= 0.85, errs
+    assert ro[0][2] > 0.14 and abs(o.joint_state()[7] - 0.0613) < 2e-3            # red box lifted, gripper closed on a 6 cm box
+    assert max_rows >= 80                                                          # the grasp is a >= 80-row problem with condim-4 rows
+
+
+def test_stacking_mode_and_success_bookkeeping():
+    """check_mode / _check_early_termination (stacking.py:395-447) with teleported boxes."""
+    blob, sc = load_scene("stacking")
+    o = OracleEnv(blob, sc.header)
+    ctx = task_contexts("stacking")[0]
+    o.reset(ctx)
+    hold = np.concatenate([o.joint_state()[:7], [0.08]])
+    s = o.get_state()
+    s[16:19] = [0.5, 0.2, 0.011]                        # green box on the target
+    o.set_state(s)
+    obs, r, done, info = o.step(hold)
+    assert info[0] == 0 and info[1] == 2 and info[3] == 1              # mode "g"
+    s = o.get_state()
+    s[9:12] = [0.5, 0.2, 0.071]                         # red stacked on green
+    s[23:26] = [0.5, 0.2, 0.131]                        # blue on top
+    o.set_state(s)
+    obs, r, done, info = o.step(hold)
+    assert info[3] == 2 and info[1] in (2 + 4 * 1, 2 + 4 * 3) and info[0] == 1     # second arrival appended; all three within 6 cm, z gaps > 3 cm
+    obs, r, done, info = o.step(hold)
+    assert done and info[3] == 3

