@@ -1111,36 +1111,37 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
   if (done) { LANES(d, nv) { w[L.qacc + d] = w[L.qacc_smooth + d]; w[L.qfrc_c + d] = 0; } gsync<G>(cx); }
   const real scale = 1 / ((real)m.ctrl[D3C_MEANINERTIA] * (real)(nv > 1 ? nv : 1));
   const real* M = w + L.M;
-  // ---- warm start: cheaper of qacc_warmstart and qacc_smooth
+  // ---- warm start: cheaper of qacc_warmstart and qacc_smooth.  The evaluation at the warm start (jar, forces, cone
+  //      Hessian blocks, M (a - a_s)) is iteration 0's evaluation when the warm start wins - the usual case.
+  real cost = 0, oldcost = 0, gn_prev = 0;
   if (!done) {
-    eval_jar<G>(cx, m, L, w, nlimit, ncon, L.warm, L.jar, true);
-    real cw = constraint_eval<G, false, MD>(cx, m, L, w, nlimit, ncon, L.jar, L.frcE);
-    real part = 0;
-    LANES(d, nv) part += (real)0.5 * (w[L.warm + d] - w[L.qacc_smooth + d]) * mrow_dot(m, M, nv, d, w + L.warm, w + L.qacc_smooth);
-    cw += gsum<G>(cx, part);
-    gsync<G>(cx);
     eval_jar<G>(cx, m, L, w, nlimit, ncon, L.qacc_smooth, L.jar, true);
     real cs = constraint_eval<G, false, MD>(cx, m, L, w, nlimit, ncon, L.jar, L.frcE);
     gsync<G>(cx);
-    LANES(d, nv) w[L.qacc + d] = cw < cs ? w[L.warm + d] : w[L.qacc_smooth + d];
+    eval_jar<G>(cx, m, L, w, nlimit, ncon, L.warm, L.jar, true);
+    real cw = constraint_eval<G, true, MD>(cx, m, L, w, nlimit, ncon, L.jar, L.frcE);
+    real part = 0;
+    LANES(d, nv) {
+      real sM = mrow_dot(m, M, nv, d, w + L.warm, w + L.qacc_smooth);
+      w[L.Ma + d] = sM; part += (real)0.5 * (w[L.warm + d] - w[L.qacc_smooth + d]) * sM;
+    }
+    cw += gsum<G>(cx, part);
+    gsync<G>(cx);
+    if (cw < cs) { LANES(d, nv) w[L.qacc + d] = w[L.warm + d]; cost = cw; }
+    else {
+      LANES(d, nv) { w[L.qacc + d] = w[L.qacc_smooth + d]; w[L.Ma + d] = 0; }
+      gsync<G>(cx);
+      eval_jar<G>(cx, m, L, w, nlimit, ncon, L.qacc_smooth, L.jar, true);
+      cost = constraint_eval<G, true, MD>(cx, m, L, w, nlimit, ncon, L.jar, L.frcE);
+    }
     gsync<G>(cx);
   }
-  real cost = 0, oldcost = 0, gn_prev = 0;
   int iter = 0, nsteps = 0;      // nsteps: Newton steps this env actually took (iter also counts idle CTA-uniform passes)
+  int grad_fresh = 0;            // grad / Ma / frcE all belong to the current iterate (then J^T f = Ma - grad)
   PHASE_T0();
   for (; iter < max_iter; iter++) {
     PHASE(15);
     if (!done) {
-    eval_jar<G>(cx, m, L, w, nlimit, ncon, L.qacc, L.jar, true);
-    oldcost = cost;
-    cost = constraint_eval<G, true, MD>(cx, m, L, w, nlimit, ncon, L.jar, L.frcE);
-    real part = 0;
-    LANES(d, nv) {
-      real s = mrow_dot(m, M, nv, d, w + L.qacc, w + L.qacc_smooth);
-      w[L.Ma + d] = s; part += (real)0.5 * (w[L.qacc + d] - w[L.qacc_smooth + d]) * s;
-    }
-    cost += gsum<G>(cx, part);
-    gsync<G>(cx);
     // grad = M (a - a_s) - J^T f : lane per dof, contacts filtered by their dof ranges
     real g2 = 0;
     LANES(d, nv) {
@@ -1161,14 +1162,14 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
     }
     real gn = sqrt(gsum<G>(cx, g2));
     gsync<G>(cx);
+    grad_fresh = 1;
 #ifdef D3IL_DEBUG_SOLVER
     printf("  newton it %d cost %.12g gn %.6g\n", iter, (double)cost, (double)gn);
 #endif
     PHASE(8);
     if (blockIdx_is0()) count_iter();
     if (scale * gn < tol) done = 1;
-    // improvement below what the cost can resolve in this precision: further iterations only chase rounding noise
-    // (a gradient-stall test on top of this was measured: +3 % Newton steps, no accuracy gain)
+    // Improvement below what the cost can resolve in this precision: further iterations only chase rounding noise.
     // When the cost is large (impacts, deep spawn penetration, a grasp) its fp32 resolution (2e-6 |cost|) is blind to the
     // light dofs - a box's rotation has inertia 3e-5 kg m^2 - whose accelerations keep converging long after the cost
     // has gone flat: there the loop also waits for the gradient to stall.  Small costs (boxes at rest: ~5) stop on the cost alone.
@@ -1254,6 +1255,7 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
     real a1s = 0, a2s = 0, a3s = 0;
     LANES(d, nv) {
       real s = mrow_dot(m, M, nv, d, w + L.pvec, nullptr);
+      w[L.tmpv + d] = s;                                             // M p (tmpv is free until the Euler stage)
       a1s += w[L.pvec + d] * s; a2s += w[L.pvec + d] * w[L.Ma + d]; a3s += w[L.grad + d] * w[L.pvec + d];
     }
     real pMp = gsum<G>(cx, a1s), pMa = gsum<G>(cx, a2s), d0 = gsum<G>(cx, a3s);
@@ -1308,19 +1310,24 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
       }
       alpha = next;
     }
-    LANES(d, nv) w[L.qacc + d] += alpha * w[L.pvec + d];
+    // step: everything linear in the iterate moves incrementally (jar = J a - aref, Ma = M (a - a_s)); then the
+    // evaluation of the NEXT iteration (cost, forces, cone Hessian blocks) at the new iterate
+    LANES(d, nv) { w[L.qacc + d] += alpha * w[L.pvec + d]; w[L.Ma + d] += alpha * w[L.tmpv + d]; }
+    LANES(i, ne) w[L.jar + i] += alpha * w[L.Jp + i];
     gsync<G>(cx);
+    oldcost = cost;
+    cost = constraint_eval<G, true, MD>(cx, m, L, w, nlimit, ncon, L.jar, L.frcE);
+    real partc = 0;
+    LANES(d, nv) partc += (real)0.5 * (w[L.qacc + d] - w[L.qacc_smooth + d]) * w[L.Ma + d];
+    cost += gsum<G>(cx, partc);
+    gsync<G>(cx);
+    grad_fresh = 0;
     PHASE(12);
     }
   }
-  if (ne > 0 && !done) {
-    // final force evaluation at the last iterate
-    eval_jar<G>(cx, m, L, w, nlimit, ncon, L.qacc, L.jar, true);
-    constraint_eval<G, false, MD>(cx, m, L, w, nlimit, ncon, L.jar, L.frcE);
-    gsync<G>(cx);
-  }
-  // qfrc_constraint = J^T f
-  if (ne > 0) LANES(d, nv) {
+  // qfrc_constraint = J^T f = M (a - a_s) - grad when the gradient belongs to the final iterate (converged exit)
+  if (ne > 0 && grad_fresh) { LANES(d, nv) w[L.qfrc_c + d] = w[L.Ma + d] - w[L.grad + d]; }
+  else if (ne > 0) LANES(d, nv) {
     real s = 0;
     for (int i = 0; i < nlimit; i++) { int sd = (int)w[L.econ + i]; if (sd == d + 1) s += w[L.frcE + i]; else if (sd == -(d + 1)) s -= w[L.frcE + i]; }
     for (int c = 0; c < ncon; c++) {
