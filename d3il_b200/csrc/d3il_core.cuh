@@ -119,14 +119,15 @@ DEVFN void count_stat(int, int) {}
 
 // Register-distributed vectors: element i lives in slot i / G of lane i % G.
 #define D3_SLOTS(G) ((D3_MAXV + (G) - 1) / (G))
-template <int G>
+template <int G, int NS>
 DEVFN real elem_bcast(const Cx& cx, const real* xr, int c) {
 #ifdef D3IL_EMU
   return xr[c];
 #else
+  if (NS == 1) return __shfl_sync(cx.mask, xr[0], c, G);
   real v = 0;
 #pragma unroll
-  for (int sl = 0; sl < D3_SLOTS(G); sl++) { real t = __shfl_sync(cx.mask, xr[sl], c % G, G); if (sl == c / G) v = t; }
+  for (int sl = 0; sl < NS; sl++) { real t = __shfl_sync(cx.mask, xr[sl], c % G, G); if (sl == c / G) v = t; }
   return v;
 #endif
 }
@@ -869,14 +870,14 @@ DEVFN int make_constraints(const Cx& cx, const Model& m, const Lay& L, real* w, 
   gsync<G>(cx);
   const real impratio = m.ctrl[D3C_IMPRATIO];
   // Jacobian rows: one (contact, dof) item per lane step; entries outside the contact's dof ranges are never read
-  LANES(item, ncon * nv) {
-    int c = item / nv, d = item - c * nv;
+  LANES(item, ncon * D3_JW) {
+    int c = item / D3_JW, loc = item - c * D3_JW;                   // one compact-row slot per lane step (D3_JW = 16: shifts)
     const real* cc = w + L.con + D3_CON_W * c;
     int row0 = (int)cc[19];
     if (row0 < 0) continue;
     int a0 = (int)cc[20], a1 = (int)cc[21], b0 = (int)cc[22], b1 = (int)cc[23];
-    if (!((d >= a0 && d < a1) || (d >= b0 && d < b1))) continue;
-    int loc = d < a1 && d >= a0 ? d - a0 : (a1 - a0) + d - b0;
+    if (loc >= (a1 - a0) + (b1 - b0)) continue;
+    int d = loc < a1 - a0 ? a0 + loc : b0 + loc - (a1 - a0);
     int dim = (int)cc[15];
     int l1 = (int)m.geom[D3_GEOM_W * (int)cc[16] + 1], l2 = (int)m.geom[D3_GEOM_W * (int)cc[17] + 1];
     int dl = m.d_link[d];
@@ -1051,45 +1052,56 @@ DEVNI int chol_factor_part(const Cx& cx, const Model& m, real* A, int n, bool wh
 
 // Solve L L^T x = b in place for the same partitioned factor.  x is pulled into registers (element i in lane i % G),
 // finished elements are broadcast with shuffles; no shared-memory traffic for x and no barriers inside the sweeps.
-template <int G>
-DEVNI void chol_solve_part(const Cx& cx, const Model& m, const real* A, int n, bool whole, int maxsz, const real* dinv, real* x) {
-  real xr[D3_SLOTS(G)];
-  int s0[D3_SLOTS(G)], e0[D3_SLOTS(G)];
+template <int G, int NS>
+DEVNI void chol_solve_slots(const Cx& cx, const Model& m, const real* A, int n, bool whole, int maxsz, const real* dinv, real* x) {
+  real xr[NS];
+  int s0[NS], e0[NS];
 #pragma unroll
-  for (int sl = 0; sl < D3_SLOTS(G); sl++) {
+  for (int sl = 0; sl < NS; sl++) {
     int i = sl * G + cx.lane, ii = i < n ? i : n - 1;
     xr[sl] = i < n ? x[i] : (real)0;
     s0[sl] = whole ? 0 : m.d_bs[ii]; e0[sl] = whole ? n : m.d_be[ii];
   }
   for (int k = 0; k < maxsz; k++) {
-    real xcs[D3_SLOTS(G)];          // read phase first: every slot sees the pre-step values of x
+    real xcs[NS];          // read phase first: every slot sees the pre-step values of x
 #pragma unroll
-    for (int sl = 0; sl < D3_SLOTS(G); sl++) {
+    for (int sl = 0; sl < NS; sl++) {
       int c = s0[sl] + k, cc = c < e0[sl] ? c : e0[sl] - 1;
-      xcs[sl] = elem_bcast<G>(cx, xr, cc) * dinv[cc];
+      xcs[sl] = elem_bcast<G, NS>(cx, xr, cc) * dinv[cc];
     }
 #pragma unroll
-    for (int sl = 0; sl < D3_SLOTS(G); sl++) {
+    for (int sl = 0; sl < NS; sl++) {
       int i = sl * G + cx.lane, c = s0[sl] + k;
       if (i < n && c < e0[sl]) { if (i == c) xr[sl] = xcs[sl]; else if (i > c) xr[sl] -= A[i * n + c] * xcs[sl]; }
     }
   }
   for (int k = maxsz - 1; k >= 0; k--) {
-    real xcs[D3_SLOTS(G)];
+    real xcs[NS];
 #pragma unroll
-    for (int sl = 0; sl < D3_SLOTS(G); sl++) {
+    for (int sl = 0; sl < NS; sl++) {
       int c = s0[sl] + k, cc = c < e0[sl] ? c : e0[sl] - 1;
-      xcs[sl] = elem_bcast<G>(cx, xr, cc) * dinv[cc];
+      xcs[sl] = elem_bcast<G, NS>(cx, xr, cc) * dinv[cc];
     }
 #pragma unroll
-    for (int sl = 0; sl < D3_SLOTS(G); sl++) {
+    for (int sl = 0; sl < NS; sl++) {
       int i = sl * G + cx.lane, c = s0[sl] + k;
       if (i < n && c < e0[sl]) { if (i == c) xr[sl] = xcs[sl]; else if (i < c && i >= s0[sl]) xr[sl] -= A[c * n + i] * xcs[sl]; }
     }
   }
 #pragma unroll
-  for (int sl = 0; sl < D3_SLOTS(G); sl++) { int i = sl * G + cx.lane; if (i < n) x[i] = xr[sl]; }
+  for (int sl = 0; sl < NS; sl++) { int i = sl * G + cx.lane; if (i < n) x[i] = xr[sl]; }
   gsync<G>(cx);
+}
+
+// NS = register slots per lane for the distributed vector: one when the system fits the group (n <= G)
+template <int G>
+DEVFN void chol_solve_part(const Cx& cx, const Model& m, const real* A, int n, bool whole, int maxsz, const real* dinv, real* x) {
+#ifdef D3IL_EMU
+  chol_solve_slots<G, D3_SLOTS(G)>(cx, m, A, n, whole, maxsz, dinv, x);
+#else
+  if (n <= G) chol_solve_slots<G, 1>(cx, m, A, n, whole, maxsz, dinv, x);
+  else chol_solve_slots<G, D3_SLOTS(G)>(cx, m, A, n, whole, maxsz, dinv, x);
+#endif
 }
 
 // y_d = sum_k M[d][k] v[k] within the dof's block (M stored in the upper triangle + diagonal of the M buffer)
