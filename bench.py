@@ -43,6 +43,7 @@ WORKLOADS = {
     "sorting6": dict(task="sorting_6", envs=4096, ctx="sorting_6_contexts", policy=None, n_act=2),
     "stacking": dict(task="stacking", envs=4096, ctx="stacking_test_contexts", policy=None, n_act=7),          # configs[3]: 4096 envs / GPU
 }
+MIXED7 = ["avoiding", "aligning", "pushing", "sorting2", "sorting4", "sorting6", "stacking"]      # configs[4]: 8192 envs / GPU over the 7 state-based configs
 TASK = "pushing"
 N_ENVS = WORKLOADS["pushing"]["envs"]
 
@@ -175,6 +176,88 @@ class ClockSampler:
         out["reasons"] = sorted(reasons)
         out["samples"] = len(sm)
         return out
+
+
+def run_mixed(args):
+    """--workload mixed7 (BASELINE.json configs[4]): 8192 envs per GPU split over the seven state-based task configs, one
+    BatchedEnv + CUDA stream per task, random-walk set-points, auto-reset; value = total env steps of all tasks / time."""
+    import torch
+    import torch.distributed as dist
+
+    from d3il_b200.mixed import MixedBatch
+
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    n = args.envs or 8192
+    K, W = args.steps, max(args.warmup, 3)
+    wls = [WORKLOADS[w] for w in MIXED7]
+    mb = MixedBatch(n, local, tasks=[w["task"] for w in wls])
+    gen = torch.Generator(device=dev).manual_seed(99 + rank)
+    ctxs, starts, des = [], [], []
+    for e, w in zip(mb.envs, wls):
+        c = load_contexts(w["ctx"]) if w["ctx"] else None
+        ctxs.append(torch.tensor(c[(np.arange(e.n_envs) + rank * e.n_envs) % len(c)], dtype=torch.float32, device=dev) if c is not None else None)
+    mb.reset(ctxs)
+    for e in mb.envs:
+        if e.act_dim == 8:
+            st = e.joint_state().clone(); st[:, 7] = 0.08
+        else:
+            st = torch.cat([e.robot_state().clone(), torch.tensor([0.0, 1.0, 0.0, 0.0], device=dev).repeat(e.n_envs, 1)], 1)
+        starts.append(st.contiguous()); des.append(st.clone())
+    lo3, hi3 = torch.tensor([*WORKSPACE_LO, 0.02], device=dev), torch.tensor([*WORKSPACE_HI, 0.35], device=dev)
+    returns = [torch.zeros(e.n_envs, 3, device=dev) for e in mb.envs]
+
+    def advance(k):
+        for e, w, d in zip(mb.envs, wls, des):
+            na = w["n_act"]
+            delta = torch.rand(e.n_envs, na, generator=gen, device=dev) * 0.02 - 0.01
+            if e.act_dim == 8:
+                d[:, :7] += delta; d[:, 7] = 0.08 if (k // 50) % 2 == 0 else 0.0
+            else:
+                d[:, :na] = torch.minimum(torch.maximum(d[:, :na] + delta, lo3[:na]), hi3[:na])
+        outs = mb.step(des)
+        masks = []
+        for (obs, rew, done, info), r, d, st in zip(outs, returns, des, starts):
+            r.copy_(torch.where(done.bool().unsqueeze(1), info[:, :3], r))
+            d.copy_(torch.where(done.bool().unsqueeze(1), st, d))
+            masks.append(done)
+        mb.reset(ctxs, masks)
+
+    # pre-roll: 300 steps with staggered forced resets would need per-task episode lengths; a plain 150-step run-in is used
+    for k in range(150 if not args.no_preroll else 0):
+        advance(k)
+    for k in range(W):
+        advance(k)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = mb.kernel_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for k in range(K):
+        advance(W + k)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
+        allr = torch.cat(returns, 0)
+        gathered = [torch.zeros_like(allr) for _ in range(world)] if rank == 0 else None
+        dist.gather(allr, gathered, dst=0)
+    clocks = sampler.stop() if sampler else None
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": world * mb.n_envs * K / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"mixed7-{mb.n_envs}env-per-gpu-randomwalk", "tasks": list(mb.tasks), "envs_per_task": mb.counts, "auto_reset": True, "run_in_steps": 150},
+            "clocks": clocks, "gpu_launches": int(mb.kernel_launches - l0),
+        }))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def run_gpu(args):
@@ -375,11 +458,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the workload's BASELINE.json size)")
-    ap.add_argument("--workload", default="pushing", choices=sorted(WORKLOADS), help="default = the configuration the metric is quoted on")
+    ap.add_argument("--workload", default="pushing", choices=sorted(WORKLOADS) + ["mixed7"], help="default = the configuration the metric is quoted on")
     ap.add_argument("--no-preroll", action="store_true", help="skip the 400-step episode-phase pre-roll (debug)")
     args = ap.parse_args()
     if args.impl == "reference":
+        if args.workload == "mixed7":
+            args.workload = "pushing"
         run_reference(args)
+    elif args.workload == "mixed7":
+        run_mixed(args)
     else:
         run_gpu(args)
 

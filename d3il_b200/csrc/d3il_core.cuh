@@ -168,6 +168,8 @@ struct Model {
   unsigned char p_cpl[D3_MAXPAIR];        // pair joins two different kinematic-tree blocks
   unsigned char g_slab[32];               // geom is a static, axis-aligned box (table top, support): eligible for the slab fast path
   int nblk, blk_s[8], blk_e[8];           // the kinematic-tree blocks as a list
+  unsigned diag_blk;                      // bit b: block b of M is diagonal (free body, CoM at its origin, principal axes = body axes)
+  int nzp; unsigned char zp_a[8], zp_b[8]; // in-block dof pairs that CRBA never writes (the two fingers): must read as zero
   unsigned char tri_i[300], tri_j[300];   // row-major lower-triangle unranking table for n <= 24
   unsigned char mp_a[D3_MAXV * 8], mp_b[D3_MAXV * 8];   // (a,b) list of related dof pairs, a >= b
   tab_t link[D3_MAXLINK * D3_LINK_W];
@@ -1011,7 +1013,7 @@ DEVNI real constraint_eval(const Cx& cx, const Model& m, const Lay& L, real* w, 
 // L; the running pivots live in piv[] (initialised by the caller with the diagonal), dinv[] receives 1 / L_kk.
 // Row i is owned by lane i % G.  Returns 1 if a pivot was not positive.
 template <int G>
-DEVNI int chol_factor_part(const Cx& cx, const Model& m, real* A, int n, bool whole, int maxsz, real* piv, real* dinv) {
+DEVNI int chol_factor_part(const Cx& cx, const Model& m, real* A, int n, bool whole, int maxsz, real* piv, real* dinv, unsigned skip = 0u) {
   int bad = 0;
   const int nb = whole ? 1 : m.nblk;
   for (int k = 0; k < maxsz; k++) {
@@ -1028,7 +1030,7 @@ DEVNI int chol_factor_part(const Cx& cx, const Model& m, real* A, int n, bool wh
     // the critical path is ceil(entries / G) independent updates instead of a serial walk along the longest row
     for (int b = 0; b < nb; b++) {
       const int c = (whole ? 0 : m.blk_s[b]) + k, e = whole ? n : m.blk_e[b], mb = e - c - 1;
-      if (mb <= 0) continue;
+      if (mb <= 0 || ((skip >> b) & 1u)) continue;                   // diagonal blocks have no trailing update
       if (mb <= 24) {
         LANES(t, mb * (mb + 1) / 2) {
           const int i = c + 1 + m.tri_i[t], j = c + 1 + m.tri_j[t];
@@ -1394,8 +1396,7 @@ DEVFN void physics_tick(const Cx& cx, const Model& m, const Lay& L, real* w, con
   }
   PHASE(0);
   cta_sync<CS>(cx);
-  LANES(e, nv * nv) w[L.M + e] = 0;     // unrelated dof pairs inside a block (the two fingers) must read as zero
-  gsync<G>(cx);
+  LANES(e, m.nzp) { int a = m.zp_a[e], b = m.zp_b[e]; w[L.M + a * nv + b] = 0; w[L.M + b * nv + a] = 0; }     // in-block pairs CRBA never writes (the two fingers)
   dynamics<G>(cx, m, L, w);
   PHASE(1);
   cta_sync<CS>(cx);
@@ -1420,7 +1421,7 @@ DEVFN void physics_tick(const Cx& cx, const Model& m, const Lay& L, real* w, con
   }
   LANES(e, m.nmpair) { int a = m.mp_a[e], b = m.mp_b[e]; if (a != b) w[L.M + a * nv + b] = w[L.M + b * nv + a]; }   // lower <- upper
   gsync<G>(cx);
-  if (chol_factor_part<G>(cx, m, w + L.M, nv, false, m.maxblk, w + L.mpiv, w + L.mdinv)) { LANES(z, 1) w[L.misc + ST_STATUS] = (real)(((int)w[L.misc + ST_STATUS]) | 1); }
+  if (chol_factor_part<G>(cx, m, w + L.M, nv, false, m.maxblk, w + L.mpiv, w + L.mdinv, m.diag_blk)) { LANES(z, 1) w[L.misc + ST_STATUS] = (real)(((int)w[L.misc + ST_STATUS]) | 1); }
   chol_solve_part<G>(cx, m, w + L.M, nv, false, m.maxblk, w + L.mdinv, w + L.qacc_smooth);
   PHASE(4);
   cta_sync<CS>(cx);

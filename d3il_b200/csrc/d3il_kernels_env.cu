@@ -115,6 +115,12 @@ int d3il_env_grid(const DevCtx& c, int n_single) { return n_single + (c.n - n_si
 
 cudaError_t d3il_env_kernels_configure(size_t smem_bytes) {
   cudaError_t e;
+  // The dynamic shared-memory limit is an attribute of the FUNCTION (per device), shared by every handle of the process:
+  // several scenes side by side (MixedBatch) need the largest request, so the limit only ever grows.
+  static size_t configured[64] = {0};
+  int dev = 0;
+  if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+  if (dev >= 0 && dev < 64) { if (smem_bytes <= configured[dev]) return cudaSuccess; configured[dev] = smem_bytes; }
   if ((e = cudaFuncSetAttribute(k_env<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k_env<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(k_env<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return e;

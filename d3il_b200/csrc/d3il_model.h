@@ -92,8 +92,19 @@ static inline bool d3il_build_model(const void* blob, size_t nbytes, Model& m, L
     m.p_cpl[ip] = (unsigned char)cpl;
   }
   { int e = 0; for (int i = 0; i < 24; i++) for (int j = 0; j <= i; j++) { m.tri_i[e] = (unsigned char)i; m.tri_j[e] = (unsigned char)j; e++; } }
-  m.nblk = 0;
-  for (int d = 0; d < m.nv; d++) if (m.d_bs[d] == d) { if (m.nblk >= 8) { err = "too many kinematic trees"; return false; } m.blk_s[m.nblk] = d; m.blk_e[m.nblk] = m.d_be[d]; m.nblk++; }
+  m.nblk = 0; m.diag_blk = 0; m.nzp = 0;
+  for (int d = 0; d < m.nv; d++) if (m.d_bs[d] == d) { if (m.nblk >= 8) { err = "too many kinematic trees"; return false; } m.blk_s[m.nblk] = d; m.blk_e[m.nblk] = m.d_be[d];
+    {
+      const int li = m.d_link[d]; const tab_t* Lk = m.link + D3_LINK_W * li;
+      if (m.l_jtype[li] == 2 && Lk[13] == 0 && Lk[14] == 0 && Lk[15] == 0 && Lk[19] == 0 && Lk[20] == 0 && Lk[21] == 0) m.diag_blk |= 1u << m.nblk;
+    }
+    m.nblk++; }
+  // in-block (a > b) dof pairs that are not ancestor-related: CRBA never writes them
+  for (int a = 0; a < m.nv; a++) for (int b = m.d_bs[a]; b < a; b++)
+    if (!((m.l_anc[m.d_link[a]] >> m.d_link[b]) & 1u)) {
+      if (m.nzp >= 8) { err = "too many unrelated in-block dof pairs"; return false; }
+      m.zp_a[m.nzp] = (unsigned char)a; m.zp_b[m.nzp] = (unsigned char)b; m.nzp++;
+    }
   // contact budget: 4 per free body resting on a support + 12 for transients (deep spawn penetration touches two supports,
   // box-box / rod contacts); overflow raises status bit 2, never drops silently
   { int cap = hdr_maxcon > 0 ? hdr_maxcon : 4 * m.nobj + 12; m.maxcon = ((conmax < cap ? conmax : cap) + 3) & ~3; }

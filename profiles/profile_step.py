@@ -16,8 +16,15 @@ ctx = torch.tensor(ctxs[np.arange(n) % 60], dtype=torch.float32, device="cuda")
 env.reset(ctx)
 des = torch.cat([env.robot_state().clone(), torch.tensor([0.0, 1.0, 0.0, 0.0], device="cuda").repeat(n, 1)], 1)
 g = torch.Generator(device="cuda").manual_seed(0)
-for k in range(steps):
-    des[:, :2] += torch.rand(n, 2, generator=g, device="cuda") * 0.02 - 0.01
-    env.step(des)
+lo, hi = torch.tensor([0.3, -0.45], device="cuda"), torch.tensor([0.8, 0.45], device="cuda")
+tcp0 = env.robot_state().clone()
+ids = torch.arange(n, device="cuda")
+preroll = int(sys.argv[3]) if len(sys.argv) > 3 else 0      # 400 = bench.py's steady-state mix of episode phases
+for k in range(preroll + steps):
+    des[:, :2] = torch.minimum(torch.maximum(des[:, :2] + torch.rand(n, 2, generator=g, device="cuda") * 0.02 - 0.01, lo), hi)
+    o, r, d, i = env.step(des)
+    m = (ids % 400 == k).to(torch.uint8) if k < preroll else d
+    env.reset(ctx, m)
+    des[:, :3] = torch.where(m.bool().unsqueeze(1), tcp0, des[:, :3])
 torch.cuda.synchronize()
 print("done", env.kernel_launches)

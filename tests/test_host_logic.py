@@ -149,3 +149,44 @@ def test_sharding_and_gather_world_size_2():
     assert ranges[0][0] == 0 and ranges[-1][1] == n_items and ranges[0][1] == ranges[1][0]
     for _, _, _, out in res:
         assert np.array_equal(out, expect)
+
+
+def test_mode_kl_matches_reference_loops():
+    """``Sorting_Sim`` metrics (sorting_sim.py:191-213) restated with the reference's Python loops vs the vectorised form."""
+    from d3il_b200.simulation.metrics import mode_kl
+
+    torch.manual_seed(1)
+    prior = {192: 0.5, 64: 0.3, 128: 0.2}
+    keys = torch.tensor(list(prior.keys()), dtype=torch.float32)
+    n_ctx, n_traj = 7, 12
+    mode_encoding = keys[torch.randint(0, 3, (n_ctx, n_traj))]
+    successes = (torch.rand(n_ctx, n_traj) > 0.4).float()
+    successes[3] = 0                                    # a context without any success is dropped
+    probs, entropy, KL = mode_kl(mode_encoding, successes, prior)
+    n_mode = 3
+    ref = torch.zeros(n_ctx, n_mode)
+    for c in range(n_ctx):
+        for num in range(n_mode):
+            ref[c, num] = sum(mode_encoding[c, successes[c, :] == 1] == keys[num]) / n_traj
+    ref /= (ref.sum(1).reshape(-1, 1) + 1e-12)
+    ref = ref[torch.nonzero(ref.sum(1), as_tuple=True)[0]]
+    prior_t = torch.tensor(list(prior.values()))
+    ent_ref = -(ref * torch.log(ref + 1e-12) / torch.log(torch.tensor(float(n_mode)))).sum(1).mean()
+    log_ = (ref * torch.log(prior_t + 1e-12) / torch.log(torch.tensor(float(n_mode)))).sum(1).mean()
+    assert torch.allclose(probs, ref, atol=1e-6) and abs(entropy - ent_ref.item()) < 1e-6 and abs(KL - (-ent_ref - log_).item()) < 1e-6
+
+
+def test_stacking_mode_string_round_trip_and_synthetic_policies():
+    from d3il_b200.simulation.policies import SyntheticBCPolicy, SyntheticDDPMPolicy
+    from d3il_b200.simulation.stacking_sim import MODE_3, decode_mode
+
+    for s in MODE_3:
+        code = sum(("rgb".index(ch) + 1) * 4 ** k for k, ch in enumerate(s))
+        assert decode_mode(code, 3) == s and decode_mode(code, 2) == s[:2]
+    assert decode_mode(0, 0) == ""
+    p = SyntheticDDPMPolicy(16, 2, device="cpu", seed=3)
+    assert sum(x.numel() for x in p.eps_net.parameters()) == 533762      # DDPM-MLP of scripts/sorting_4/ddpm_benchmark.sh (SURVEY A.9: ~0.53 M)
+    a = p.predict_batch(torch.randn(9, 16))
+    assert a.shape == (9, 2) and torch.isfinite(a).all() and a.abs().max() <= 0.01 + 1e-9
+    b = SyntheticBCPolicy(4, 2, device="cpu")
+    assert b.predict(np.zeros(4, np.float32)).shape == (1, 2)
