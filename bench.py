@@ -135,7 +135,7 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------ GPU arm
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_env launch at the workload's default size, from the committed
 # `ncu --set full` captures (profiles/): filled in per task as captures are taken; None = not captured
-TRAFFIC_NCU = {"pushing": 35.5e6}
+TRAFFIC_NCU = {"pushing": 36.6e6}       # profiles/r1_summary.md: 29.48 MB read + 7.12 MB written per k_env launch (4096 envs)
 
 
 class ClockSampler:
@@ -361,11 +361,6 @@ def run_gpu(args):
     clocks = sampler.stop() if sampler else None
     value = world * n * K / (ms * 1e-3)
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-
     # ---- per-kernel device time (CUDA events on the launching stream, inside the library) for the roofline object
     env.set_profiling(True)
     for k in range(8):
@@ -400,6 +395,8 @@ def run_gpu(args):
     for k in range(3):
         env.step_host(des_h)
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     t0 = time.perf_counter()
     for k in range(e2e_steps):
         if policy is not None:      # policy on the GPU: observations go up, deltas come down, every step
@@ -422,8 +419,16 @@ def run_gpu(args):
             h2d += (ctx_h.nbytes if ctx_h is not None else 0) + done_h.nbytes
             des_h[done_h.astype(bool)] = start_h[done_h.astype(bool)]
     dt = time.perf_counter() - t0
-    e2e = {"value": n * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d // e2e_steps, "d2h_bytes_per_step": d2h // e2e_steps,
-           "steps": e2e_steps, "n_gpus": 1}
+    if world > 1:          # every rank drives its own GPU through the host API at the same time; slowest rank sets the rate
+        t = torch.tensor([dt], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    e2e = {"value": world * n * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": world * (h2d // e2e_steps), "d2h_bytes_per_step": world * (d2h // e2e_steps),
+           "steps": e2e_steps, "n_gpus": world}
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- CPU baseline beside it: the oracle port on this box's host cores, bounded sample
     import oracle.oracle as oo
