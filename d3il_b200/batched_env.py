@@ -90,6 +90,15 @@ class BatchedEnv:
         _lib.check(self._L.d3il_joint_state(self._h, C.c_void_p(self.joints.data_ptr()), self._stream()), "d3il_joint_state")
         return self.joints
 
+    def object_poses(self) -> torch.Tensor:
+        """[n_envs, n_obj, 7] xyz + quat wxyz of the free objects (``Scene.get_obj_pos`` / ``get_obj_quat``)."""
+        n_obj = self.scene.header["nobj"]
+        if not hasattr(self, "_obj_poses"):
+            self._obj_poses = torch.zeros(self.n_envs, n_obj, 7, device=self.device)
+        if n_obj:
+            _lib.check(self._L.d3il_object_poses(self._h, C.c_void_p(self._obj_poses.data_ptr()), self._stream()), "d3il_object_poses")
+        return self._obj_poses
+
     # ---- host-buffer API (numpy in / numpy out; H2D + D2H inside the call) — the reference-facing end-to-end path
     def reset_host(self, contexts: np.ndarray | None = None, mask: np.ndarray | None = None) -> np.ndarray:
         obs = np.zeros((self.n_envs, self.obs_dim), dtype=np.float32)

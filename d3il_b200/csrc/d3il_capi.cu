@@ -304,6 +304,15 @@ extern "C" int d3il_joint_state(d3il_env* h, float* j8, void* stream) {
   return 0;
 }
 
+extern "C" int d3il_object_poses(d3il_env* h, float* out, void* stream) {
+  if (!h || !out) { g_err = "d3il_object_poses: null argument"; return -1; }
+  CK(cudaSetDevice(h->device));
+  d3il_launch_object_poses(h->d, h->m.nobj, out, (cudaStream_t)stream);
+  h->launches += 1;
+  CK(cudaGetLastError());
+  return 0;
+}
+
 // ---- host-buffer variants (end-to-end path: pinned staging, H2D, kernels, D2H, sync)
 extern "C" int d3il_reset_host(d3il_env* h, const float* ctx, const uint8_t* mask, float* obs) {
   if (!h) { g_err = "d3il_reset_host: null handle"; return -1; }

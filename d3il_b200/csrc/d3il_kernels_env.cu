@@ -157,6 +157,16 @@ __global__ void k_joint_state(DevCtx c, float* __restrict__ j8) {
   for (int k = 0; k < 7; k++) j8[(size_t)e * 8 + k] = (float)((double)row[c.lay.qpos + k] + (double)row[c.lay.qlo + k]);
   j8[(size_t)e * 8 + 7] = row[c.lay.qpos + 7] + row[c.lay.qpos + 8];
 }
+// MjScene._get_obj_pos_and_quat (MjScene.py:233-247) for every free object: qpos words (x, y, z, qw, qx, qy, qz)
+__global__ void k_object_poses(DevCtx c, int nobj, float* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.n * nobj * 7) return;
+  int e = i / (nobj * 7), k = i - e * nobj * 7;
+  out[i] = c.state[(size_t)e * c.row + c.lay.qpos + D3_NROB + k];
+}
+void d3il_launch_object_poses(const DevCtx& c, int nobj, float* out, cudaStream_t s) {
+  if (nobj > 0) k_object_poses<<<(c.n * nobj * 7 + 255) / 256, 256, 0, s>>>(c, nobj, out);
+}
 void d3il_launch_joint_state(const DevCtx& c, float* j8, cudaStream_t s) { k_joint_state<<<(c.n + 127) / 128, 128, 0, s>>>(c, j8); }
 
 #ifdef D3IL_PHASE_TIMING

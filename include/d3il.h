@@ -57,6 +57,11 @@ int d3il_robot_state(d3il_env* env, float* tcp, void* cu_stream);
  * positions + gripper width, dev [n_envs, 8]. */
 int d3il_joint_state(d3il_env* env, float* j8, void* cu_stream);
 
+/* Replaces Scene.get_obj_pos / get_obj_quat (MjScene._get_obj_pos_and_quat, sims/mj_beta/MjScene.py:233-247) for every free
+ * object of the scene: dev [n_envs, n_obj, 7] = (x, y, z, qw, qx, qy, qz) read from qpos (what the reference's ObjectLogger
+ * records for the datasets, core/logger.py). */
+int d3il_object_poses(d3il_env* env, float* out, void* cu_stream);
+
 /* Host-buffer variants: the same calls with HOST pointers; inputs are staged through pinned memory, copied to the
  * device, the kernels run, outputs are copied back and the call returns after synchronising (this is the
  * reference-facing end-to-end path: one Python call per env step, numpy in / numpy out). */

@@ -54,3 +54,30 @@ def test_mixed_batch_steps_all_seven_configs():
     for (obs, rew, done, info), e in zip(outs, mb.envs):
         assert obs.shape == (e.n_envs, e.obs_dim) and torch.isfinite(obs).all() and (info[:, -1] == 0).all()
     mb.close()
+
+
+def test_trajectory_recorder_matches_dataset_format():
+    """The recorded env_state dicts feed the reference's Pushing dataset arithmetic (pushing_dataset.py:55-77) unchanged."""
+    _need_gpu()
+    from d3il_b200.batched_env import BatchedEnv
+    from d3il_b200.simulation.recorder import TrajectoryRecorder
+    from tests.util import task_contexts
+
+    n = 4
+    env = BatchedEnv("pushing", n, 0)
+    ctx = task_contexts("pushing")[:n]
+    env.reset(torch.tensor(ctx, dtype=torch.float32, device="cuda"))
+    rec = TrajectoryRecorder(env)
+    des = torch.cat([env.robot_state().clone(), torch.tensor([0.0, 1.0, 0.0, 0.0], device="cuda").repeat(n, 1)], 1)
+    for k in range(6):
+        des[:, 1] += 0.005
+        rec.record(des)
+        env.step(des)
+    states = rec.env_states()
+    assert len(states) == n
+    st = states[1]
+    assert st["robot"]["des_c_pos"].shape == (6, 3) and st["red-box"]["quat"].shape == (6, 4) and st["green-target"]["pos"].shape == (6, 3)
+    assert np.allclose(st["red-box"]["pos"][0, :2], ctx[1, 0, :2], atol=1e-3) and abs(st["red-box"]["pos"][-1, 2] - 0.011) < 1e-3
+    vel = st["robot"]["des_c_pos"][1:, :2] - st["robot"]["des_c_pos"][:-1, :2]           # the dataset's action definition
+    assert np.allclose(vel, [[0.0, 0.005]] * 5, atol=1e-6)
+    env.close()
