@@ -371,7 +371,7 @@ def run_gpu(args):
         advance()
     ik_ms, env_ms, nprof = env.get_profile()
     env.set_profiling(False)
-    k_env_ms = env_ms / max(nprof, 1)
+    k_env_ms = (ik_ms + env_ms) / max(nprof, 1)      # k_sched + k_ik + k_env of one env step (k_ik overlaps k_env: programmatic dependent launch)
     n_state = env.scene.header["nq"] + env.scene.header["nv"] * 2 + 9 + 9 + 7 + 16 + env.scene.header.get("nextra", 0)      # persistent fp32 words per env
     alg_bytes_env = 2 * 4 * n_state + 4 * env.act_dim + 4 * env.obs_dim + 4 + 1 + 4 * env.info_dim
     alg_bytes_launch = alg_bytes_env * n
@@ -384,7 +384,7 @@ def run_gpu(args):
     achieved = alg_bytes_launch / (k_env_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": TRAFFIC_NCU.get(task), "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
-                "kernel": "k_env (+ overlapped k_ik, k_sched)", "kernel_ms": k_env_ms, "alg_bytes_per_env_step": alg_bytes_env,
+                "kernel": "k_env (+ overlapped k_ik, k_sched)", "kernel_ms": k_env_ms, "k_ik_done_ms": ik_ms / max(nprof, 1), "alg_bytes_per_env_step": alg_bytes_env,
                 "note": "fused n_substeps-tick kernel is ALU/latency-bound, not HBM-bound (SURVEY §8d); see DESIGN.md for the fp32 issue-rate view"}
 
     # ---- e2e: same workload through the host-buffer C ABI (numpy in/out, H2D + D2H every step)

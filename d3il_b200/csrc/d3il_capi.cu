@@ -55,6 +55,7 @@ __device__ __forceinline__ unsigned smid() { unsigned r; asm volatile("mov.u32 %
 // last CTA.  So each step the envs are bucket-sorted by the Newton iterations of their previous step: expensive envs
 // share CTAs and are dispatched first.  The order only affects scheduling, never results (envs are independent).
 __global__ void __launch_bounds__(1024) k_sched(DevCtx c) {
+  TL_BEGIN(3, 4095);
   __shared__ int hist[256], start[256];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
   __syncthreads();
@@ -72,6 +73,7 @@ __global__ void __launch_bounds__(1024) k_sched(DevCtx c) {
     int b = (int)(row[off] + 4.f * row[off + 1]) >> 1;
     c.perm[atomicAdd(&start[b > 255 ? 255 : b], 1)] = e;
   }
+  TL_END(3);
 }
 
 __global__ void __launch_bounds__(IK_THREADS) k_ik(DevCtx c, const float* __restrict__ action, int n_ticks, int use_action, int flag_base, int ctrl_kind, int act_dim) {
@@ -167,7 +169,8 @@ extern "C" int d3il_create(d3il_env** out, const void* blob, size_t nbytes, int 
   CK(cudaMalloc(&d.perm, (size_t)n_envs * sizeof(int)));
   CK(cudaMemset(d.ik_flags, 0, (size_t)h->n_ik_blocks * sizeof(int)));
   // envs per CTA: ENVS_PER_CTA (two CTAs per SM for the small scenes), fewer when the per-env workspace is large (Sorting-4/6)
-  const size_t model_bytes = (sizeof(Model) + 127) & ~(size_t)127, env_bytes = (size_t)d.ws_stride * sizeof(float);
+  const size_t model_bytes = d3il_model_bytes(h->m), env_bytes = (size_t)d.ws_stride * sizeof(float);
+  d.model_bytes = (int)model_bytes;
   d.epc = ENVS_PER_CTA;
   while (d.epc > 1 && model_bytes + d.epc * env_bytes > 227 * 1024) d.epc--;
   h->smem_bytes = model_bytes + (size_t)d.epc * env_bytes;
@@ -232,13 +235,14 @@ extern "C" int d3il_get_profile(const d3il_env* h, double out_ms[2], long long* 
 
 // Scheduler + IK reference + env step: three launches on one stream, the last one with programmatic stream serialization
 // so that it overlaps k_ik (per-tick hand-off through ik_flags).  If the driver serialises them anyway the result is the same.
-static cudaError_t launch_step(d3il_env* h, cudaStream_t s, const float* action, int n_ticks, int gym, float* obs, float* reward, uint8_t* done, float* info) {
+static cudaError_t launch_step(d3il_env* h, cudaStream_t s, const float* action, int n_ticks, int gym, float* obs, float* reward, uint8_t* done, float* info, cudaEvent_t after_ik = nullptr) {
   h->launch_id = (h->launch_id + 1) & 0xffffff;
   const int base = h->launch_id * 64;
   static const bool no_pdl = getenv("D3IL_NO_PDL") != nullptr;      // diagnosis: serialise the kernels
   k_sched<<<1, 1024, 0, s>>>(h->d);
   k_ik<<<h->n_ik_blocks, IK_THREADS, 0, s>>>(h->d, action, n_ticks, gym, base, h->m.ctrl_kind, h->m.act_dim);
   h->launches += 3;
+  if (after_ik) cudaEventRecord(after_ik, s);        // completes when k_ik has finished (k_env may already be running: PDL)
   return d3il_launch_env(h->d, h->m.maxdim, h->n_single, n_ticks, gym, base, action, obs, reward, done, info, h->smem_bytes, s, !no_pdl);
 }
 
@@ -257,8 +261,7 @@ extern "C" int d3il_step(d3il_env* h, const float* action, float* obs, float* re
   CK(cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;
   if (h->profiling) CK(cudaEventRecord(h->ev[0], s));
-  if (h->profiling) CK(cudaEventRecord(h->ev[1], s));
-  CK(launch_step(h, s, action, h->m.n_substeps, 1, obs, reward, done, info));
+  CK(launch_step(h, s, action, h->m.n_substeps, 1, obs, reward, done, info, h->profiling ? h->ev[1] : nullptr));
   CK(cudaGetLastError());
   if (h->profiling) {
     // per-kernel device time on the launching stream (bench.py roofline); synchronises, so only for profiling passes

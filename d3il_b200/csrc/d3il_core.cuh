@@ -175,10 +175,14 @@ struct Model {
   tab_t link[D3_MAXLINK * D3_LINK_W];
   tab_t geom[D3_MAXGEOM * D3_GEOM_W];
   tab_t geomR[D3_MAXGEOM * 9];
-  tab_t pair[D3_MAXPAIR * D3_PAIR_W];
   tab_t ctrl[D3_CTRL_W];
   tab_t taskp[32];
+  tab_t pair[D3_MAXPAIR * D3_PAIR_W];      // LAST: only the first npair rows are staged into shared memory (d3il_model_bytes)
 };
+// bytes of the Model a CTA stages into shared memory: everything up to the scene's last candidate pair
+static inline size_t d3il_model_bytes(const Model& m) {
+  return (((size_t)((const char*)m.pair - (const char*)&m) + sizeof(tab_t) * D3_PAIR_W * (size_t)m.npair) + 127) & ~(size_t)127;
+}
 
 // ------------------------------------------------------------------------------------------------ per-env workspace
 // Offsets (in reals) into the env's slice of shared memory.  Persistent state first (mirrors the HBM row), then

@@ -15,7 +15,10 @@
 #define ENVS_PER_CTA 7     // 2 CTAs/SM x 7 envs: 4096 envs = 1.98 waves on 148 SMs (13.3 KB of shared memory per env)
 #endif
 #define CTA_THREADS (G_LANES * ENVS_PER_CTA)
-#define IK_THREADS 32    // one warp per k_ik block: 255 regs x 32 threads = 8 K registers, fits beside two resident k_env CTAs
+#ifndef IK_THREADS
+#define IK_THREADS 128   // 32 k_ik blocks at 4096 envs: an SM that hosts one (4 warps x 255 regs) still takes one k_env CTA; with one warp per
+                         // block the 128 blocks spread over 128 SMs and each of them lost its second k_env CTA until k_ik left (-12 %)
+#endif
 
 struct DevIk {            // SoA views, [field][n]
   double* q;              // [7][n]
@@ -28,6 +31,7 @@ struct DevCtx {
   Lay lay;
   float* state;           // [n][row]
   int row, n, ws_stride;
+  int model_bytes;        // staged prefix of the Model (d3il_model_bytes), multiple of 128
   int epc;                // envs (warps) per CTA: ENVS_PER_CTA unless the scene's workspace needs more shared memory per env
   DevIk ik;
   float* traj;            // [ticks][21][n]

@@ -15,22 +15,25 @@ __device__ __forceinline__ unsigned smid() { unsigned r; asm volatile("mov.u32 %
 #define TL_BEGIN(kind, idx) ((void)0)
 #define TL_END(kind) ((void)0)
 #endif
-__device__ __forceinline__ void stage_model(Model* sm, const Model* gm) {
-  const int* src = (const int*)gm; int* dst = (int*)sm;
-  for (int i = threadIdx.x; i < (int)(sizeof(Model) / 4); i += blockDim.x) dst[i] = src[i];
+__device__ __forceinline__ void stage_model(Model* sm, const Model* gm, int bytes) {
+  const int4* src = (const int4*)gm; int4* dst = (int4*)sm;
+  for (int i = threadIdx.x; i < bytes / 16; i += blockDim.x) dst[i] = src[i];
   __syncthreads();
 }
 
 // IK reference generator: one thread per env (a5/a6).  mode: 1 = take the set-point from `action` (env step),
 // 0 = keep the stored set-point (d3il_substep).  In joint-PD mode (after reset) the held set-point is replicated.
 // Env step: one warp per env.  gym = 1: GymEnvWrapper.step semantics around the ticks; gym = 0: bare ticks (substep).
+// 120 registers: two 7-warp k_env CTAs (2 x 224 x 120) and one k_ik warp (32 x 255) share the SM's 64 K registers, so the
+// env step can start on the SMs that still run the IK reference.  (__launch_bounds__ with a min-blocks hint would let
+// ptxas go to 146 and override -maxrregcount: at 125 registers the second CTA waited for k_ik to leave.)
 template <int MD>
-__global__ void __launch_bounds__(CTA_THREADS, (CTA_THREADS > 256 ? 1 : 2))
+__global__ void __maxnreg__(120)
 k_env(DevCtx c, int n_single, int n_ticks, int gym, int flag_base, const float* __restrict__ action, float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ done, float* __restrict__ info) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TL_BEGIN(2, blockIdx.x);
   Model* sm = (Model*)smem_raw;
-  stage_model(sm, c.model);
+  stage_model(sm, c.model, c.model_bytes);
   const Model& m = *sm;
   const Lay& L = c.lay;
   const int warp = threadIdx.x / G_LANES;
@@ -48,7 +51,7 @@ k_env(DevCtx c, int n_single, int n_ticks, int gym, int flag_base, const float* 
   // every thread of the CTA reaches the phase barriers inside physics_tick.
   const int e_raw = pos0 + warp;                               // position in this step's cost-sorted order
   const int e = c.perm[e_raw < c.n ? e_raw : c.n - 1];
-  float* w = (float*)(smem_raw + ((sizeof(Model) + 127) & ~(size_t)127)) + (size_t)warp * c.ws_stride;
+  float* w = (float*)(smem_raw + c.model_bytes) + (size_t)warp * c.ws_stride;
   float* row = c.state + (size_t)e * c.row;
   for (int i = cx.lane; i < L.n_state; i += G_LANES) w[i] = row[i];
   __syncwarp(cx.mask);
@@ -77,7 +80,7 @@ __global__ void __launch_bounds__(CTA_THREADS, (CTA_THREADS > 256 ? 1 : 2))
 k_reset(DevCtx c, const float* __restrict__ ctx, const uint8_t* __restrict__ mask, float* __restrict__ obs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Model* sm = (Model*)smem_raw;
-  stage_model(sm, c.model);
+  stage_model(sm, c.model, c.model_bytes);
   const Model& m = *sm;
   const Lay& L = c.lay;
   const int warp = threadIdx.x / G_LANES;
@@ -87,7 +90,7 @@ k_reset(DevCtx c, const float* __restrict__ ctx, const uint8_t* __restrict__ mas
   if (e >= c.n) return;
   cx.cta_threads = c.epc * G_LANES;
   if (mask && !mask[e]) return;
-  float* w = (float*)(smem_raw + ((sizeof(Model) + 127) & ~(size_t)127)) + (size_t)warp * c.ws_stride;
+  float* w = (float*)(smem_raw + c.model_bytes) + (size_t)warp * c.ws_stride;
   env_reset<G_LANES>(cx, m, L, w, (ctx && m.ctx_dim > 0) ? ctx + (size_t)e * m.ctx_dim : nullptr, c.tol, c.max_iter);
   float* row = c.state + (size_t)e * c.row;
   for (int i = cx.lane; i < L.n_state; i += G_LANES) row[i] = w[i];

@@ -33,8 +33,9 @@ print(f'10 more steps: {e0.elapsed_time(e1)/10:.3f} ms per step')
 buf = (C.c_ulonglong * (4 * 4096))()
 lib.lib().d3il_debug_timeline(buf)
 a = np.array(buf, dtype=np.uint64).reshape(4096, 4).astype(np.int64)
-env_b = a[(a[:, 3] == 2)]; ik_b = a[(a[:, 3] == 1)]
+env_b = a[(a[:, 3] == 2)]; ik_b = a[(a[:, 3] == 1)]; sch = a[(a[:, 3] == 3)]
 t0 = min(env_b[:, 0].min(), ik_b[:, 0].min())
+if len(sch): print(f"k_sched: start {(sch[0,0]-t0)/1e6:.3f} end {(sch[0,1]-t0)/1e6:.3f} ms (relative to the first k_ik block)")
 print(f"k_ik blocks {len(ik_b)}: start {(ik_b[:,0].min()-t0)/1e6:.3f}..{(ik_b[:,0].max()-t0)/1e6:.3f} ms, end {(ik_b[:,1].min()-t0)/1e6:.3f}..{(ik_b[:,1].max()-t0)/1e6:.3f} ms")
 print(f"k_env CTAs {len(env_b)}: start {(env_b[:,0].min()-t0)/1e6:.3f}..{(env_b[:,0].max()-t0)/1e6:.3f} ms, end {(env_b[:,1].min()-t0)/1e6:.3f}..{(env_b[:,1].max()-t0)/1e6:.3f} ms")
 dur = (env_b[:, 1] - env_b[:, 0]) / 1e6
@@ -46,3 +47,15 @@ for lo, hi in ((0, 0.5), (0.5, 3), (3, 6), (6, 9), (9, 20)):
 print('CTA duration percentiles (ms): ' + ' '.join(f'p{p}={np.percentile(dur, p):.2f}' for p in (5, 25, 50, 75, 90, 95, 99, 100)))
 sm_counts = np.bincount(env_b[:, 2].astype(int), minlength=148)
 print("CTAs per SM: min", sm_counts.min(), "max", sm_counts.max(), " SMs hosting k_ik blocks:", len(set(ik_b[:, 2].tolist())))
+# finer view: start-time histogram and how many k_env CTAs run beside a k_ik block at t = 0.3 ms
+edges = np.arange(0, 8.01, 0.25)
+hist, _ = np.histogram(st, bins=edges)
+print("k_env CTA starts per 0.25 ms:", " ".join(f"{h}" for h in hist))
+en = (env_b[:, 1] - t0) / 1e6
+ik_sms = set(ik_b[:, 2].tolist())
+for t in (0.3, 1.0, 2.0):
+    running = (st <= t) & (en > t)
+    per_sm = np.bincount(env_b[running, 2].astype(int), minlength=148)
+    on_ik = [per_sm[s] for s in range(148) if s in ik_sms]
+    off_ik = [per_sm[s] for s in range(148) if s not in ik_sms]
+    print(f"t={t} ms: running k_env CTAs {running.sum()}; per SM with k_ik: {np.bincount(on_ik, minlength=3)}; without: {np.bincount(off_ik, minlength=3) if off_ik else []}")
