@@ -174,5 +174,6 @@ void d3il_launch_joint_state(const DevCtx& c, float* j8, cudaStream_t s) { k_joi
 
 #ifdef D3IL_PHASE_TIMING
 int d3il_debug_timeline_env(unsigned long long* out) { return cudaMemcpyFromSymbol(out, g_tl, sizeof(unsigned long long) * 4 * 4096) == cudaSuccess ? 0 : -2; }
+extern "C" int d3il_debug_iter_hist(unsigned long long* out40) { return cudaMemcpyFromSymbol(out40, g_iter_hist, sizeof(unsigned long long) * 40) == cudaSuccess ? 0 : -2; }
 int d3il_debug_phase_cycles_env(unsigned long long* out24) { return cudaMemcpyFromSymbol(out24, g_phase_cycles, sizeof(unsigned long long) * 24) == cudaSuccess ? 0 : -2; }
 #endif

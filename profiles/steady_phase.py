@@ -49,3 +49,11 @@ it, cp, nc = rows[:, 4], rows[:, 5], rows[:, 6]
 print("newton steps per env step: mean %.1f p10 %.0f p50 %.0f p90 %.0f p99 %.0f max %.0f" % (it.mean(), *np.percentile(it, [10, 50, 90, 99, 100])))
 print("coupled ticks per env step: frac envs >0: %.3f" % ((cp > 0).mean()))
 print("max contacts per env: mean %.1f; hist" % nc.mean(), np.bincount(nc.astype(int)))
+
+if hasattr(lib.lib(), "d3il_debug_iter_hist"):
+    h = (C.c_ulonglong * 40)(); lib.lib().d3il_debug_iter_hist(h); h = np.array(list(h), dtype=np.float64)
+    tot = h[:16].sum()
+    print("Newton steps per tick, all ticks since start (%):", " ".join(f"{100*x/tot:.2f}" for x in h[:16]))
+    print("  ... ticks with a coupling contact (% of all ticks):", " ".join(f"{100*x/tot:.3f}" for x in h[16:32]))
+    print("  work share by steps/tick (%):", " ".join(f"{100*k*x/max((np.arange(16)*h[:16]).sum(),1):.1f}" for k, x in enumerate(h[:16])))
+    print("  ticks with >= 8 steps: mean contacts %.1f" % (h[32] / max(h[33], 1)))
