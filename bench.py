@@ -135,7 +135,7 @@ def run_reference(args):
 # ------------------------------------------------------------------------------------------------ GPU arm
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_env launch at the workload's default size, from the committed
 # `ncu --set full` captures (profiles/): filled in per task as captures are taken; None = not captured
-TRAFFIC_NCU = {"pushing": 36.6e6}       # profiles/r1_summary.md: 29.48 MB read + 7.12 MB written per k_env launch (4096 envs)
+TRAFFIC_NCU = {"pushing": 38.1e6}       # profiles/r1_summary.md: 29.50 MB read + 8.57 MB written per k_env launch (4096 envs)
 
 
 class ClockSampler:

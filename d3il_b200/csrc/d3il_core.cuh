@@ -99,6 +99,7 @@ template <bool CS> DEVFN void cta_sync(const Cx& cx) {
 #if defined(D3IL_PHASE_TIMING) && !defined(D3IL_EMU)
 // debug build only: per-phase cycle counts of the group that owns env 0 (profiles/phase_timing.py)
 static __device__ unsigned long long g_phase_cycles[24];
+static __device__ unsigned long long g_iter_hist[40];      // [0..15] Newton steps per tick, [16..31] same for ticks with a coupling contact, [32] sum ncon / [33] count of ticks with >= 8 steps
 #endif
 #if defined(D3IL_PHASE_TIMING) && defined(__CUDA_ARCH__)
 #define PHASE_T0() long long t_ph = clock64()
@@ -1412,6 +1413,7 @@ DEVFN void physics_tick(const Cx& cx, const Model& m, const Lay& L, real* w, con
   PHASE(3);
 #ifdef D3IL_PHASE_TIMING
   if (cx.lane == 0) { count_stat(21, coupled); count_stat(22, ncon); count_stat(23, 1); count_stat(19, ne); }
+#define D3IL_ITER_HIST 1
 #endif
   cta_sync<CS>(cx);
   // --- smooth dynamics: qacc_smooth = M^-1 (passive - bias + actuation); M is block diagonal over the trees
@@ -1430,6 +1432,13 @@ DEVFN void physics_tick(const Cx& cx, const Model& m, const Lay& L, real* w, con
   PHASE(4);
   cta_sync<CS>(cx);
   int iters = solve_constraints<G, CS, MD>(cx, m, L, w, ne, nlimit, ncon, coupled, tol, max_iter);
+#if defined(D3IL_ITER_HIST) && defined(__CUDA_ARCH__)
+  if (cx.lane == 0) {
+    int b = iters > 15 ? 15 : iters;
+    atomicAdd(&g_iter_hist[b], 1ull); if (coupled) atomicAdd(&g_iter_hist[16 + b], 1ull);
+    if (iters >= 8) { atomicAdd(&g_iter_hist[32], (unsigned long long)ncon); atomicAdd(&g_iter_hist[33], 1ull); }
+  }
+#endif
   LANES(z, 1) {      // per-env cost counters of the current env step (cost-aware scheduling, diagnostics)
     w[L.misc + ST_COST_ITERS] += (real)iters; w[L.misc + ST_COST_COUPLED] += (real)coupled;
     if ((real)ncon > w[L.misc + ST_COST_NCON]) w[L.misc + ST_COST_NCON] = (real)ncon;
