@@ -305,6 +305,7 @@ def run_gpu(args):
     returns = torch.zeros(n, 3, device=dev)          # per-env episode result rows (first three info words)
     faults = torch.zeros((), dtype=torch.long, device=dev)      # env steps that raised a status bit (solver fault / contact or row overflow)
     step_no = torch.zeros((), dtype=torch.long, device=dev)
+    fault_bits = torch.zeros((), dtype=torch.int32, device=dev)
     last_obs = env.obs.clone()
 
     def advance(force=None):
@@ -322,6 +323,7 @@ def run_gpu(args):
         last_obs.copy_(obs)
         step_no.add_(1)
         faults.add_((info[:, -1] != 0).sum())
+        fault_bits.bitwise_or_(info[:, -1].to(torch.int32).max())        # status bits: 1 M not PD / NaN, 2 contact or row budget overflow, 4 Newton Hessian not PD
         # episode bookkeeping + auto-reset of finished envs (masked reset kernel; set-point snaps back to the start pose)
         m = done if force is None else force
         returns.copy_(torch.where(m.bool().unsqueeze(1), info[:, :3], returns))
@@ -342,7 +344,7 @@ def run_gpu(args):
         dist.barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     launches0 = env.kernel_launches
-    faults.zero_()
+    faults.zero_(); fault_bits.zero_()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     ev0.record()
@@ -453,7 +455,7 @@ def run_gpu(args):
         "config": {"workload": f"{args.workload}-{n}env-per-gpu-" + ("ddpm-mlp-in-loop" if policy is not None else "randomwalk"), "task": task, "envs_per_gpu": n,
                    "n_substeps": env.n_substeps, "episode_len": ep_len, "auto_reset": True, "preroll_steps": 0 if args.no_preroll else ep_len,
                    "l2_note": "state+trajectory working set per step is rewritten every step (no cross-step reuse of inputs); timing is launch-to-launch on one stream"},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "env_step_faults": n_faults, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "env_step_faults": n_faults, "env_step_fault_bits": int(fault_bits.item()), "roofline": roofline, "cpu_baseline": cpu_baseline,
         "target": {"env_steps_per_sec": 1.0e6, "met": bool(value >= 1.0e6)},
     }))
     if world > 1:

@@ -7,7 +7,7 @@ for w in "$@"; do
 import json
 try:
     d = json.load(open("gpurun_out/bench_$w.json"))
-    print("$w", "value", round(d["value"]), "ms/step", round(d["ms_per_step"], 2), "e2e", round(d["e2e"]["value"]), "k_env ms", round(d["roofline"]["kernel_ms"], 2), "cpu(all cores)", round(d["cpu_baseline"]["value"]), "cores", d["cpu_baseline"]["cores"], "clk", d["clocks"]["sm_mhz"], "faults", d.get("env_step_faults"))
+    print("$w", "value", round(d["value"]), "ms/step", round(d["ms_per_step"], 2), "e2e", round(d["e2e"]["value"]), "k_env ms", round(d["roofline"]["kernel_ms"], 2), "cpu(all cores)", round(d["cpu_baseline"]["value"]), "cores", d["cpu_baseline"]["cores"], "clk", d["clocks"]["sm_mhz"], "faults", d.get("env_step_faults"), "bits", d.get("env_step_fault_bits"))
 except Exception as e:
     print("$w failed", e)
 PY
