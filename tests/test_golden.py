@@ -1,0 +1,55 @@
+"""Committed regression vectors (tests/golden/oracle_rollouts.npz, made by tests/golden/make_golden.py): the oracle must
+reproduce them teacher-forced per env step (CPU), and the CUDA path must follow them (GPU, through the C ABI).  See the
+generator's docstring for what these vectors are - oracle regression fixtures, not reference outputs."""
+import os
+
+import numpy as np
+import pytest
+
+from d3il_b200.scene.blob import load_scene
+from oracle.oracle import OracleEnv
+from tests.util import step_errors
+
+SCENES = ["avoiding", "pushing", "aligning", "sorting_2", "sorting_4", "sorting_6", "stacking"]
+GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_rollouts.npz"))
+
+
+@pytest.mark.parametrize("task", SCENES)
+def test_oracle_reproduces_golden_rollouts(task):
+    blob, sc = load_scene(task)
+    o = OracleEnv(blob, sc.header)
+    acts, states, obs, info = (GOLD[f"{task}/{k}"] for k in ("actions", "states", "obs", "info"))
+    assert states.shape[1] == o.state_dim
+    o.reset(None)
+    for k, a in enumerate(acts):
+        o.set_state(states[k])
+        ob, r, d, inf = o.step(a)
+        assert np.allclose(o.get_state(), states[k + 1], rtol=1e-9, atol=1e-10), (task, k, np.abs(o.get_state() - states[k + 1]).max())
+        assert np.allclose(ob, obs[k + 1], rtol=1e-6, atol=1e-7) or k == 0        # obs[k+1] is sampled before step k+1's substeps = after step k
+        assert np.allclose(np.concatenate([[r, float(d)], inf]), info[k], rtol=1e-9, atol=1e-10)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("task", SCENES)
+def test_gpu_follows_golden_rollouts(task):
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from d3il_b200.batched_env import BatchedEnv
+    blob, sc = load_scene(task)
+    nq, nv = sc.header["nq"], sc.header["nv"]
+    acts, states, info = (GOLD[f"{task}/{k}"] for k in ("actions", "states", "info"))
+    n = len(acts)
+    env = BatchedEnv(task, n, 0)
+    if sc.header["ctx_dim"]:
+        env.reset(torch.zeros(n, sc.header["ctx_dim"], device="cuda") + torch.tensor([0.5, 0.0, 0.05, 1.0, 0.0, 0.0, 0.0], device="cuda").repeat(sc.header["ctx_dim"] // 7))
+    else:
+        env.reset()
+    for i in range(n):
+        env.set_state(i, states[i])
+    o, r, d, inf = (t.cpu().numpy() for t in env.step(torch.tensor(acts, dtype=torch.float32, device="cuda")))
+    errs = np.array([step_errors(states[i + 1], env.get_state(i), nq, nv) for i in range(n)])
+    assert (errs.max(axis=1) <= 1.0).mean() >= 0.85, errs          # quantile bound: see tests/test_emu_tasks.py
+    assert np.array_equal(d.astype(float), info[:, 1]) and np.allclose(inf[:, 0], info[:, 2])      # done flags and success
+    assert (inf[:, -1] == 0).all()
+    env.close()
