@@ -41,6 +41,7 @@ WORKLOADS = {
     "sorting4-ddpm": dict(task="sorting_4", envs=8192, ctx="sorting_4_contexts", policy="ddpm", n_act=2),      # configs[2]
     "sorting4": dict(task="sorting_4", envs=8192, ctx="sorting_4_contexts", policy=None, n_act=2),
     "sorting6": dict(task="sorting_6", envs=4096, ctx="sorting_6_contexts", policy=None, n_act=2),
+    "inserting": dict(task="inserting", envs=4096, ctx="inserting_contexts", policy=None, n_act=2),
     "stacking": dict(task="stacking", envs=4096, ctx="stacking_test_contexts", policy=None, n_act=7),          # configs[3]: 4096 envs / GPU
 }
 MIXED7 = ["avoiding", "aligning", "pushing", "sorting2", "sorting4", "sorting6", "stacking"]      # configs[4]: 8192 envs / GPU over the 7 state-based configs

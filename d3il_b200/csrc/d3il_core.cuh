@@ -148,7 +148,7 @@ enum { D3C_IK_ORIGIN = 0, D3C_IK_EE = 84, D3C_PGAIN_POS = 96, D3C_PGAIN_QUAT = 9
        D3C_NUM_ITER = 147, D3C_LRATE = 148, D3C_DT = 149, D3C_INIT_QPOS = 150, D3C_TCP_POS = 157, D3C_TCP_QUAT = 160,
        D3C_GRAVITY = 164, D3C_IMPRATIO = 167, D3C_TOL = 168, D3C_JNT_SOLREF = 169, D3C_JNT_SOLIMP = 171, D3C_MEANINERTIA = 179 };
 enum { D3G_CYLINDER = 5, D3G_BOX = 6 };
-enum { D3T_AVOIDING = 0, D3T_PUSHING = 1, D3T_ALIGNING = 2, D3T_SORTING = 3, D3T_STACKING = 4 };
+enum { D3T_AVOIDING = 0, D3T_PUSHING = 1, D3T_ALIGNING = 2, D3T_SORTING = 3, D3T_STACKING = 4, D3T_INSERTING = 5 };
 
 struct Model {
   int task_id, nlink, nobj, nq, nv, ngeom, npair, n_substeps, max_steps, obs_dim, act_dim, ctx_dim, info_dim, ctrl_kind, ntaskp;

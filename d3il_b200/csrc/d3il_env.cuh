@@ -203,7 +203,13 @@ DEVFN real tan_yaw(const real* q) {
 }
 
 DEVFN void task_obs(const Model& m, const Lay& L, const real* w, float* obs) {
-  if (m.task_id == D3T_PUSHING) {
+  if (m.task_id == D3T_INSERTING) {           // gate_insertion.py:288-320 (same layout as Sorting: tcp xy, then xy + tan yaw per box)
+    obs[0] = (float)w[L.tcp]; obs[1] = (float)w[L.tcp + 1];
+    for (int i = 0; i < 3; i++) {
+      const real* b = w + L.qpos + D3_NROB + 7 * i;
+      obs[2 + 3 * i] = (float)b[0]; obs[3 + 3 * i] = (float)b[1]; obs[4 + 3 * i] = (float)tan_yaw(b + 3);
+    }
+  } else if (m.task_id == D3T_PUSHING) {
     const real *b1 = w + L.qpos + 9, *b2 = w + L.qpos + 16;
     obs[0] = (float)w[L.tcp]; obs[1] = (float)w[L.tcp + 1];
     obs[2] = (float)b1[0]; obs[3] = (float)b1[1]; obs[4] = (float)tan_yaw(b1 + 3);
@@ -279,6 +285,11 @@ DEVFN real stacking_check_mode(const Model& m, const Lay& L, real* w) {
   return mean;
 }
 
+// ---- Inserting (gate_insertion.py:396-470).  misc TASK0 = len(modes), TASK1 = arrival order in base-4 digits, TASK2 = seen mask.
+DEVFN void inserting_dists(const Model& m, const Lay& L, const real* w, real* d3) {
+  for (int i = 0; i < 3; i++) { real t[3] = {(real)m.taskp[3 * i], (real)m.taskp[3 * i + 1], (real)m.taskp[3 * i + 2]}; d3[i] = dist3(w + L.qpos + D3_NROB + 7 * i, t); }
+}
+
 // ---- Aligning (aligning.py:21-30,295-352)
 DEVFN void aligning_dists(const Model& m, const Lay& L, const real* w, real* pd, real* rd) {
   const real *b = w + L.qpos + D3_NROB, *t = w + L.extra;
@@ -303,6 +314,11 @@ DEVFN int task_early_term(const Model& m, const Lay& L, real* w) {
   }
   if (m.task_id == D3T_SORTING) {
     if (sorting_all_binned(m, L, w)) { w[L.misc + ST_TERM] = 1; return 1; }
+    return 0;
+  }
+  if (m.task_id == D3T_INSERTING) {
+    real d[3]; inserting_dists(m, L, w, d);
+    if (d[0] <= (real)m.taskp[9] && d[1] <= (real)m.taskp[9] && d[2] <= (real)m.taskp[9]) { w[L.misc + ST_TERM] = 1; return 1; }
     return 0;
   }
   if (m.task_id == D3T_ALIGNING) {
@@ -330,6 +346,11 @@ DEVFN real task_reward(const Model& m, const Lay& L, const real* w) {
     return -(sqrt(dx * dx + dy * dy) + dist3(b1, g1));
   }
   if (m.task_id == D3T_ALIGNING) { real pd, rd; aligning_dists(m, L, w, &pd, &rd); return -rd - (real)3.5 * pd; }
+  if (m.task_id == D3T_INSERTING) {
+    real d[3], mn = (real)1e30; inserting_dists(m, L, w, d);
+    for (int i = 0; i < 3; i++) { const real* b = w + L.qpos + D3_NROB + 7 * i; real dx = w[L.tcp] - b[0], dy = w[L.tcp + 1] - b[1], r = sqrt(dx * dx + dy * dy); if (r < mn) mn = r; }
+    return -(mn + d[0] + d[1] + d[2]);
+  }
   return 0;
 }
 
@@ -351,6 +372,18 @@ DEVFN void task_post(const Model& m, const Lay& L, real* w, float* info) {
     int success = task_early_term(m, L, w);
     int code = sorting_check_mode(m, L, w);
     info[0] = (float)success; info[1] = (float)code; info[2] = (float)w[L.misc + ST_TASK0]; info[3] = (float)w[L.misc + ST_STATUS];
+  } else if (m.task_id == D3T_INSERTING) {    // info: success, mode id (mode_dict, 0 unless three boxes arrived), mean_distance, len(modes), status
+    int success = task_early_term(m, L, w);
+    real d[3]; inserting_dists(m, L, w, d);
+    int len = (int)w[L.misc + ST_TASK0], code = (int)w[L.misc + ST_TASK1], seen = (int)w[L.misc + ST_TASK2];
+    for (int i = 0; i < 3; i++) if (d[i] <= (real)m.taskp[9] && !((seen >> i) & 1)) {
+      int p4 = 1; for (int k = 0; k < len; k++) p4 *= 4;
+      code += (i + 1) * p4; len++; seen |= 1 << i;
+    }
+    w[L.misc + ST_TASK0] = (real)len; w[L.misc + ST_TASK1] = (real)code; w[L.misc + ST_TASK2] = (real)seen;
+    int a = code % 4, b = (code / 4) % 4;
+    int id = len != 3 ? 0 : (a == 1 ? (b == 2 ? 1 : 2) : a == 2 ? (b == 1 ? 3 : 4) : (b == 1 ? 5 : 6));
+    info[0] = (float)success; info[1] = (float)id; info[2] = (float)((d[0] + d[1] + d[2]) / 3); info[3] = (float)len; info[4] = (float)w[L.misc + ST_STATUS];
   } else if (m.task_id == D3T_STACKING) {     // info: success, mode string (base-4 digits), mean_distance, len(mode), status
     int success = task_early_term(m, L, w);
     real md = stacking_check_mode(m, L, w);

@@ -19,7 +19,7 @@ static inline bool d3il_build_model(const void* blob, size_t nbytes, Model& m, L
   m.max_steps = h[10]; m.obs_dim = h[11]; m.act_dim = h[12]; m.ctx_dim = h[13]; m.info_dim = h[14]; m.ctrl_kind = h[15]; m.ntaskp = h[16]; m.nextra = h[17];
   const int hdr_maxcon = h[18];
   if (m.nlink > D3_MAXLINK || m.nq > D3_MAXQ || m.nv > D3_MAXV || m.ngeom > D3_MAXGEOM || m.npair > D3_MAXPAIR || m.ntaskp > 32 || m.nextra < 0 || m.nextra > 8) { err = "scene exceeds compiled table sizes"; return false; }
-  if (m.task_id != D3T_AVOIDING && m.task_id != D3T_PUSHING && m.task_id != D3T_ALIGNING && m.task_id != D3T_SORTING && m.task_id != D3T_STACKING) { err = "task not supported by this build of the CUDA path"; return false; }
+  if (m.task_id != D3T_AVOIDING && m.task_id != D3T_PUSHING && m.task_id != D3T_ALIGNING && m.task_id != D3T_SORTING && m.task_id != D3T_STACKING && m.task_id != D3T_INSERTING) { err = "task not supported by this build of the CUDA path"; return false; }
   size_t need = 4 * D3SC_HDR_INTS + 8 * ((size_t)m.nlink * D3_LINK_W + (size_t)m.ngeom * D3_GEOM_W + (size_t)m.npair * D3_PAIR_W + D3_CTRL_W + m.ntaskp);
   if (need != nbytes) { err = "scene blob size mismatch"; return false; }
   const double* p = (const double*)((const char*)blob + 4 * D3SC_HDR_INTS);

@@ -267,6 +267,23 @@ def task_spec(task, ref):
             # target_box xy (static, visual only), pos_min_dist, min z gap, gripper-open threshold (stacking.py:202,337-341,425-447)
             taskp=[0.5, 0.2, 0.06, 0.03, 0.075],
         )
+    if task == "inserting":  # envs/gym_inserting_env/.../objects/gate_insertion_objects.py, gate_insertion.py:154-286
+        src = open(os.path.join(ref, D3IL, "envs/gym_inserting_env/gym_inserting/envs/objects/gate_insertion_objects.py")).read()
+        num = lambda txt: [float(x) for x in txt.split(",")]
+        maze = {}
+        for mm in re.finditer(r'maze_(\d+) = Box\(\s*name="maze_\d+",\s*init_pos=\[([^\]]*)\],\s*init_quat=\[([^\]]*)\],.*?size=\[([^\]]*)\],\s*static=True', src, re.S):
+            maze[int(mm.group(1))] = (num(mm.group(2)), num(mm.group(3)), num(mm.group(4)))
+        assert sorted(maze) == list(range(1, 20)), sorted(maze)
+        box = lambda n, pos: prim(n, "box", [0.025, 0.025, 0.025], pos, [0, 1, 0, 0], mass=0.05)
+        objs = [box("push_box1", [0.4, -0.3, -0.0072]), box("push_box2", [0.55, -0.3, -0.0072]), box("push_box3", [0.5, -0.35, -0.0072])]
+        # the env adds maze_3 .. maze_19 to the scene; maze_1 and maze_2 are created but never added (gate_insertion.py:229-255)
+        objs += [prim(f"maze_{k}", "box", maze[k][2], maze[k][0], maze[k][1], mass=0.05, static=True) for k in range(3, 20)]
+        return dict(
+            rod=True, n_substeps=35, max_steps=2000, init_tcp=[0.525, -0.28, 0.12], ctrl_kind=0,
+            objects=objs, obs_dim=11, act_dim=7, info_dim=5, maxcon=36,
+            # target_box1..3 positions (visual only), target_min_dist (gate_insertion.py:281)
+            taskp=[0.3575, 0.276, 0.0, 0.525, 0.4535, 0.0, 0.6925, 0.276, 0.0, 0.01],
+        )
     raise ValueError(f"task {task!r} not compiled yet")
 
 
@@ -514,6 +531,16 @@ def export_contexts(ref, out_dir):
     c = pickle.load(open(os.path.join(ref, "environments/dataset/data/stacking/test_contexts.pkl"), "rb"))
     arr = np.array([[[e[0][0], e[0][1], 0.0, *e[1]] for e in ctx[:3]] for ctx in c], dtype=np.float64)
     np.save(os.path.join(out_dir, "stacking_test_contexts.npy"), arr)
+    # Inserting: no dataset / contexts in the reference; drawn from BlockContextManager's three boxes (gate_insertion.py:49-62), z = 0
+    rng = np.random.default_rng(4242)
+    lows, highs = np.array([[0.35, -0.2], [0.55, -0.1], [0.35, 0.0]]), np.array([[0.5, -0.15], [0.7, -0.05], [0.5, 0.05]])
+    out = np.zeros((60, 3, 7))
+    for n in range(60):
+        xy = rng.uniform(lows, highs).astype(np.float32)
+        ang = rng.uniform(-90, 90, 3).astype(np.float32) * np.pi / 180
+        for i in range(3):
+            out[n, i] = [xy[i, 0], xy[i, 1], 0.0, np.cos(ang[i] / 2), 0.0, 0.0, np.sin(ang[i] / 2)]
+    np.save(os.path.join(out_dir, "inserting_contexts.npy"), out)
     # Sorting: `<k>_test_contexts.pkl` are NOT shipped -> drawn here from the six BlockContextManager boxes
     # (sorting.py:52-74,88-119) with our own seeded generator; boxes are placed at z = 0.05 (sorting.py:130-181)
     lows = np.array([[0.4, -0.15], [0.4, -0.05], [0.4, 0.05], [0.55, -0.15], [0.55, -0.05], [0.55, 0.05]])
@@ -536,7 +563,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
     ap.add_argument("--out", default=os.path.join(os.path.dirname(__file__), "..", "scenes"))
-    ap.add_argument("--tasks", nargs="*", default=["avoiding", "pushing", "sorting_2", "sorting_4", "sorting_6", "aligning", "stacking"])
+    ap.add_argument("--tasks", nargs="*", default=["avoiding", "pushing", "sorting_2", "sorting_4", "sorting_6", "aligning", "stacking", "inserting"])
     a = ap.parse_args()
     os.makedirs(a.out, exist_ok=True)
     for t in a.tasks:

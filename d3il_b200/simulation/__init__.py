@@ -5,3 +5,4 @@ from .base_sim import BaseSim  # noqa: F401
 from .pushing_sim import Pushing_Sim  # noqa: F401
 from .sorting_sim import Sorting_Sim  # noqa: F401
 from .stacking_sim import Stacking_Sim  # noqa: F401
+from .inserting_sim import Inserting_Sim  # noqa: F401

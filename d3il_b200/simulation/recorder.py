@@ -21,6 +21,7 @@ OBJECT_KEYS = {
     "sorting_4": (["red-box1", "red-box2", "blue-box1", "blue-box2"], {}),
     "sorting_6": (["red-box1", "red-box2", "red-box3", "blue-box1", "blue-box2", "blue-box3"], {}),
     "stacking": (["red-box", "green-box", "blue-box"], {"target-box": [0.5, 0.2, 0.0]}),
+    "inserting": (["push-box1", "push-box2", "push-box3"], {}),
     "avoiding": ([], {}),
 }
 

@@ -41,7 +41,7 @@ enum { C_IK_ORIGIN = 0, C_IK_EE = 84, C_PGAIN_POS = 96, C_PGAIN_QUAT = 99, C_PGA
        C_JNT_SOLREF = 169, C_JNT_SOLIMP = 171, C_MEANINERTIA = 179 };
 
 enum { G_PLANE = 0, G_SPHERE = 2, G_CYLINDER = 5, G_BOX = 6 };
-enum { TASK_AVOIDING = 0, TASK_PUSHING = 1, TASK_ALIGNING = 2, TASK_SORTING = 3, TASK_STACKING = 4 };
+enum { TASK_AVOIDING = 0, TASK_PUSHING = 1, TASK_ALIGNING = 2, TASK_SORTING = 3, TASK_STACKING = 4, TASK_INSERTING = 5 };
 
 #define MAXLINK 16
 #define MAXQ 64
@@ -1036,6 +1036,12 @@ static void get_obs(const Env* e, float* obs) {
       const double* b = e->qpos + NROB + 7 * i;
       obs[2 + 3 * i] = (float)b[0]; obs[3 + 3 * i] = (float)b[1]; obs[4 + 3 * i] = (float)tan_yaw(b + 3);
     }
+  } else if (e->task_id == TASK_INSERTING) {   /* gate_insertion.py:288-320: tcp xy, then (xy, tan yaw) of push_box1..3 */
+    obs[0] = (float)e->tcp_pos[0]; obs[1] = (float)e->tcp_pos[1];
+    for (int i = 0; i < 3; i++) {
+      const double* b = e->qpos + NROB + 7 * i;
+      obs[2 + 3 * i] = (float)b[0]; obs[3 + 3 * i] = (float)b[1]; obs[4 + 3 * i] = (float)tan_yaw(b + 3);
+    }
   } else if (e->task_id == TASK_STACKING) {    /* stacking.py:228-277: (pos xyz, tan yaw) of red, green, blue */
     for (int i = 0; i < 3; i++) {
       const double* b = e->qpos + NROB + 7 * i;
@@ -1107,6 +1113,31 @@ static double stacking_check_mode(Env* e) {     /* returns mean_distance; append
   return mean;
 }
 
+/* ---- Inserting (gate_insertion.py:396-470).  task_state: [0] len(modes), [1] arrival order in base-4 digits (r 1, g 2, b 3),
+ * [2] bitmask of boxes already listed.  taskp: three target positions (xyz), target_min_dist.  Distances are 3-D (C11). */
+static void inserting_dists(const Env* e, double* d3) {
+  for (int i = 0; i < 3; i++) d3[i] = dist3(e->qpos + NROB + 7 * i, e->taskp + 3 * i);
+}
+static int inserting_early_term(Env* e) {
+  double d[3]; inserting_dists(e, d);
+  if (d[0] <= e->taskp[9] && d[1] <= e->taskp[9] && d[2] <= e->taskp[9]) { e->terminated = 1; return 1; }
+  return 0;
+}
+static void inserting_check_mode(Env* e) {
+  double d[3]; inserting_dists(e, d);
+  int len = (int)e->task_state[0], code = (int)e->task_state[1], seen = (int)e->task_state[2];
+  for (int i = 0; i < 3; i++) if (d[i] <= e->taskp[9] && !((seen >> i) & 1)) {
+    int p4 = 1; for (int k = 0; k < len; k++) p4 *= 4;
+    code += (i + 1) * p4; len++; seen |= 1 << i;
+  }
+  e->task_state[0] = len; e->task_state[1] = code; e->task_state[2] = seen;
+}
+static int inserting_mode_id(int code, int len) {      /* mode_dict {'rgb':1,'rbg':2,'grb':3,'gbr':4,'brg':5,'bgr':6}, 0 unless all three arrived */
+  if (len != 3) return 0;
+  int a = code % 4, b = (code / 4) % 4;
+  return a == 1 ? (b == 2 ? 1 : 2) : a == 2 ? (b == 1 ? 3 : 4) : (b == 1 ? 5 : 6);
+}
+
 /* ---- Aligning (aligning.py:21-30,295-352) */
 static double rotation_distance(const double* p, const double* q) {
   double d = fabs(p[0] * q[0] + p[1] * q[1] + p[2] * q[2] + p[3] * q[3]);
@@ -1166,6 +1197,11 @@ static double get_reward(const Env* e) {
     double dx = e->tcp_pos[0] - b1[0], dy = e->tcp_pos[1] - b1[1];
     return -(sqrt(dx * dx + dy * dy) + dist3(b1, e->taskp));
   }
+  if (e->task_id == TASK_INSERTING) {          /* gate_insertion.py:427-449 */
+    double d[3], mn = 1e300; inserting_dists(e, d);
+    for (int i = 0; i < 3; i++) { const double* b = e->qpos + NROB + 7 * i; double r = hypot(e->tcp_pos[0] - b[0], e->tcp_pos[1] - b[1]); if (r < mn) mn = r; }
+    return -(mn + d[0] + d[1] + d[2]);
+  }
   if (e->task_id == TASK_ALIGNING) {           /* aligning.py:321-332 */
     double pd, rd; aligning_dists(e, &pd, &rd);
     return -rd - 3.5 * pd;
@@ -1211,7 +1247,7 @@ void d3o_step(Env* e, const double* action, float* obs, double* reward, int* don
   }
   get_obs(e, obs); *reward = get_reward(e);
   int early = e->task_id == TASK_PUSHING ? pushing_early_term(e) : e->task_id == TASK_SORTING ? sorting_early_term(e)
-            : e->task_id == TASK_ALIGNING ? aligning_early_term(e) : e->task_id == TASK_STACKING ? stacking_early_term(e) : avoiding_early_term(e);
+            : e->task_id == TASK_ALIGNING ? aligning_early_term(e) : e->task_id == TASK_STACKING ? stacking_early_term(e) : e->task_id == TASK_INSERTING ? inserting_early_term(e) : avoiding_early_term(e);
   *done = e->terminated || early || e->step_count >= e->max_steps - 1;             /* :124-137 */
   for (int i = 0; i < e->n_substeps; i++) physics_step(e);
   e->step_count++;
@@ -1223,6 +1259,12 @@ void d3o_step(Env* e, const double* action, float* obs, double* reward, int* don
   } else if (e->task_id == TASK_SORTING) {     /* sorting.py:444-458 */
     int success = sorting_early_term(e);
     info[0] = success; info[1] = sorting_check_mode(e); info[2] = e->task_state[0]; info[3] = e->status;
+  } else if (e->task_id == TASK_INSERTING) {   /* gate_insertion.py:366-394: success, mode id (0 unless three boxes arrived), mean_distance, len(modes) */
+    int success = inserting_early_term(e);
+    inserting_check_mode(e);
+    double d[3]; inserting_dists(e, d);
+    info[0] = success; info[1] = inserting_mode_id((int)e->task_state[1], (int)e->task_state[0]); info[2] = (d[0] + d[1] + d[2]) / 3;
+    info[3] = e->task_state[0]; info[4] = e->status;
   } else if (e->task_id == TASK_STACKING) {    /* stacking.py:381-393: success, mode string, mean_distance, len(mode) (success_1/2 = len > 0 / > 1) */
     int success = stacking_early_term(e);
     double md = stacking_check_mode(e);

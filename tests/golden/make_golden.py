@@ -20,8 +20,8 @@ from d3il_b200.scene.blob import load_scene          # noqa: E402
 from oracle.oracle import OracleEnv                  # noqa: E402
 from tests.util import scripted_grasp_actions, scripted_push_actions, scripted_task_actions, task_contexts  # noqa: E402
 
-SCENES = ["avoiding", "pushing", "aligning", "sorting_2", "sorting_4", "sorting_6", "stacking"]
-N_STEPS = {"avoiding": 40, "pushing": 100, "aligning": 50, "sorting_2": 50, "sorting_4": 50, "sorting_6": 40, "stacking": 66}
+SCENES = ["avoiding", "pushing", "aligning", "sorting_2", "sorting_4", "sorting_6", "stacking", "inserting"]
+N_STEPS = {"avoiding": 40, "pushing": 100, "aligning": 50, "sorting_2": 50, "sorting_4": 50, "sorting_6": 40, "stacking": 66, "inserting": 50}
 
 
 def rollout(task):

@@ -10,7 +10,7 @@ from oracle.oracle import OracleEnv
 from tests.emu.emu import EmuEnv
 from tests.util import scripted_task_actions, step_errors, task_contexts
 
-TASKS = ["sorting_2", "sorting_4", "sorting_6", "aligning"]
+TASKS = ["sorting_2", "sorting_4", "sorting_6", "aligning", "inserting"]
 
 
 @pytest.mark.parametrize("task", TASKS)

@@ -10,7 +10,7 @@ from d3il_b200.scene.blob import load_scene
 from oracle.oracle import OracleEnv
 from tests.util import step_errors
 
-SCENES = ["avoiding", "pushing", "aligning", "sorting_2", "sorting_4", "sorting_6", "stacking"]
+SCENES = ["avoiding", "pushing", "aligning", "sorting_2", "sorting_4", "sorting_6", "stacking", "inserting"]
 GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_rollouts.npz"))
 
 

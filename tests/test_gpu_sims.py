@@ -26,6 +26,9 @@ def test_sims_run_with_synthetic_policies():
     sr, m = Sorting_Sim(seed=0, device="cuda:0", render=False, n_contexts=3, n_trajectories_per_context=2, num_box=4, max_steps_per_episode=60).test_agent(
         SyntheticDDPMPolicy(16, 2))
     assert m.shape == (3, 2) and 0.0 <= sr <= 1.0 and (m == 240).all()          # nothing sorted in 60 random steps: mode bits all "unset"
+    from d3il_b200.simulation import Inserting_Sim
+    s, m, d = Inserting_Sim(seed=0, device="cuda:0", render=False, n_contexts=3, n_trajectories_per_context=2, max_steps_per_episode=40).test_agent(SyntheticBCPolicy(13, 2))
+    assert s.shape == (3, 2) and (s == 0).all() and (d > 0.2).all()
     s, m = Stacking_Sim(seed=0, device="cuda:0", render=False, n_contexts=3, n_trajectories_per_context=2, max_steps_per_episode=40).test_agent(
         SyntheticBCPolicy(20, 8, width=256, n_hidden_layers=8))
     assert s.shape == (3, 2) and (s == 0).all()

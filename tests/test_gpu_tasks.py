@@ -11,7 +11,7 @@ from d3il_b200.scene.blob import load_scene          # noqa: E402
 from oracle.oracle import OracleEnv                   # noqa: E402
 from tests.util import oracle_rollout_states, scripted_task_actions, step_errors, task_contexts  # noqa: E402
 
-TASKS = ["sorting_2", "sorting_4", "sorting_6", "aligning"]
+TASKS = ["sorting_2", "sorting_4", "sorting_6", "aligning", "inserting"]
 
 
 def _benv(task, n):

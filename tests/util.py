@@ -93,6 +93,7 @@ def step_errors(ref, got, nq, nv):
 
 
 TASK_CONTEXT_FILES["stacking"] = "stacking_test_contexts"
+TASK_CONTEXT_FILES["inserting"] = "inserting_contexts"
 
 
 def _panda_ik(sc):
