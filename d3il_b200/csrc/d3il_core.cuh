@@ -659,7 +659,12 @@ DEVNI int collide_cyl_box(const real* c, const real* Rc, const real* sz, const r
     if (tb < t1) t1 = tb;
   }
   if (t0 > t1) empty = 1;
-  real ts = s * h;
+  real ts;           // default (the side line misses the box: edge / corner contacts): midpoint of the axial overlap
+  {
+    real ca = dot3(d, a), ha = e3[0] * absr(dot3(a, B[0])) + e3[1] * absr(dot3(a, B[1])) + e3[2] * absr(dot3(a, B[2]));
+    real lo = maxr(-h, ca - ha), hi = minr(h, ca + ha);
+    ts = lo <= hi ? (real)0.5 * (lo + hi) : clampr(ca, -h, h);
+  }
   if (!empty) {
     real da = best - absr(na) * (h - s * t0), db = best - absr(na) * (h - s * t1);
     if (da <= 0 && db <= 0) ts = db > da ? t1 : t0;
@@ -669,6 +674,7 @@ DEVNI int collide_cyl_box(const real* c, const real* Rc, const real* sz, const r
       ts = t0 + (t1 - t0) * (da + 2 * db) / (3 * (da + db));
     }
   }
+  ts = s * h + (ts - s * h) * l * l;        // side contacts (l -> 1) take the centroid, a flat cap (l -> 0) keeps its plane
   real dc = best - r * l, wcap = 1;
   if (dc > 0) { real w = r * l / (4 * dc); if (w < 1) wcap = w; }
   for (int k = 0; k < 3; k++) pc[k] = c[k] + ts * a[k] + r * wcap * u[k];

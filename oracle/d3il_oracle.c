@@ -577,7 +577,13 @@ static int collide_cyl_box(const double* c, const double* Rc, const double* sz, 
     if (tb < t1) t1 = tb;
   }
   if (t0 > t1) empty = 1;
-  double ts = s * h;
+  /* default (the side line misses the box: edge / corner contacts): midpoint of the axial overlap of cylinder and box */
+  double ts;
+  {
+    double ca = dot3(d, a), ha = e3[0] * fabs(dot3(a, B[0])) + e3[1] * fabs(dot3(a, B[1])) + e3[2] * fabs(dot3(a, B[2]));
+    double lo = fmax(-h, ca - ha), hi = fmin(h, ca + ha);
+    ts = lo <= hi ? 0.5 * (lo + hi) : clampd(ca, -h, h);
+  }
   if (!empty) {
     double da = best - fabs(na) * (h - s * t0), db = best - fabs(na) * (h - s * t1);
     if (da <= 0 && db <= 0) ts = db > da ? t1 : t0;
@@ -587,6 +593,7 @@ static int collide_cyl_box(const double* c, const double* Rc, const double* sz, 
       ts = t0 + (t1 - t0) * (da + 2 * db) / (3 * (da + db));
     }
   }
+  ts = s * h + (ts - s * h) * l * l;        /* the shift along the axis only means something for side contacts (l -> 1); a flat cap (l -> 0) keeps its plane */
   double dc = best - r * l, wcap = 1;
   if (dc > 0) { double w = r * l / (4 * dc); if (w < 1) wcap = w; }
   for (int k = 0; k < 3; k++) pc[k] = c[k] + ts * a[k] + r * wcap * u[k];
