@@ -280,3 +280,71 @@ def test_cyl_cyl_parallel():
     c = collide(G_CYL, [0.5, -0.136, 0.152], q, [0.01, 0.15], G_CYL, [0.5, -0.1, 0.0], q, [0.03, 0.07])
     assert c.shape == (1, 7) and abs(c[0, 6] + 0.004) < 1e-12 and np.allclose(c[0, 3:6], [0, 1, 0])
     assert collide(G_CYL, [0.5, -0.1401, 0.152], q, [0.01, 0.15], G_CYL, [0.5, -0.1, 0.0], q, [0.03, 0.07]).shape[0] == 0
+
+
+def _yaw_tilt_quat(yaw, tx, ty):
+    q = np.array([np.cos(yaw / 2), tx / 2, ty / 2, np.sin(yaw / 2)])
+    return q / np.linalg.norm(q)
+
+
+def test_cyl_box_contact_point_is_continuous_in_tilt():
+    """The contact point of the cylinder-box rule must not jump when the relative tilt moves through zero (the first rule
+    classified features with 1e-4 thresholds and jumped by centimetres; a rod-end fallback flipped ends with the sign of a
+    1e-17 dot product).  Vertical rod pushing a box face / a box edge, rod end pressing on a box top."""
+    from oracle.oracle import collide
+    rng = np.random.default_rng(5)
+    G_CYL, G_BOX = 5, 6
+    worst = 0.0
+    for trial in range(300):
+        kind = trial % 3
+        yaw = rng.uniform(-np.pi, np.pi) if kind != 1 else np.pi / 4 + rng.uniform(-0.02, 0.02)      # kind 1: rod against a vertical box edge
+        box_p = np.array([0.5, 0.0, 0.13])
+        if kind < 2:        # side contact: rod beside the box, 0.3 .. 1.5 mm deep, overlapping the box's z range partially
+            d = np.array([np.cos(yaw), np.sin(yaw)]) if kind == 0 else np.array([1.0, 0.0])
+            reach = 0.03 if kind == 0 else 0.03 * np.sqrt(2) * np.cos(yaw - np.pi / 4)
+            rod_p = np.array([*(box_p[:2] + d * (reach + 0.01 - rng.uniform(3e-4, 1.5e-3))), 0.13 + 0.15 - rng.uniform(0.0, 0.03)])
+        else:               # cap contact: rod end pressing 1 .. 3 mm into the box top
+            rod_p = np.array([box_p[0] + rng.uniform(-0.015, 0.015), box_p[1] + rng.uniform(-0.015, 0.015), 0.16 + 0.15 - rng.uniform(1e-3, 3e-3)])
+        tilts = [(-2e-5, 1e-5), (0.0, 0.0), (2e-5, -1e-5), (1e-4, 5e-5), (2e-4, 1e-4)]
+        pts = []
+        for tx, ty in tilts:
+            c = collide(G_CYL, rod_p, _yaw_tilt_quat(0.0, tx, ty), [0.01, 0.15], G_BOX, box_p, _yaw_tilt_quat(yaw, 0, 0), [0.03, 0.03, 0.03])
+            assert len(c) == 1, (trial, kind, tx, c)
+            pts.append(c[0, :3])
+        pts = np.array(pts)
+        # tilt steps of <= 1e-4 rad move the contact point by at most a few centimetres per radian x the lever arms involved:
+        # bound 2 mm (the old rules jumped by 10 - 300 mm)
+        step = np.abs(np.diff(pts, axis=0)).max()
+        worst = max(worst, step)
+        assert step < 2e-3, (trial, kind, pts)
+    assert worst > 0      # the point does move, smoothly
+
+
+def test_box_box_nearly_parallel_faces_give_face_contacts_in_both_precisions():
+    """Pad-on-face configurations (a small box pressed flat on a big one with a tilt of 1e-5 .. 5e-3 rad, penetrating or
+    inside the margin): the SAT must pick the FACE (4 contacts) in the fp64 oracle and in the fp32 kernel core alike -
+    an edge axis within 2 degrees of a face normal is that face contact in disguise and used to be chosen by rounding noise."""
+    import ctypes as C
+    from oracle.oracle import collide
+    from tests.emu.emu import lib
+    L = lib("f32")
+    dp = C.POINTER(C.c_double)
+    L.emu_collide_boxes.argtypes = [dp, dp, dp, dp, dp, C.c_int, dp]
+    L.emu_collide_boxes.restype = C.c_int
+    d = lambda a: np.ascontiguousarray(a, dtype=np.float64).ctypes.data_as(dp)   # noqa: E731
+    rng = np.random.default_rng(11)
+    for trial in range(400):
+        pA, hA = np.array([0.4, -0.2, 0.03]), np.array([0.03, 0.03, 0.03])
+        hB = np.array([0.008, 0.004, 0.008])
+        tilt = 10 ** rng.uniform(-5, -2.3) * rng.choice([-1, 1], 2)
+        pB = pA + np.array([rng.uniform(-0.01, 0.01), rng.uniform(-0.01, 0.01), hA[2] + hB[1] - rng.uniform(5e-5, 6e-4)])
+        w, x, y, z = np.cos(np.pi / 4), np.sin(np.pi / 4), 0.0, 0.0                  # pad lying on its broad face: its thin axis points up
+
+        tq = _yaw_tilt_quat(rng.uniform(-0.3, 0.3), *tilt)
+        q = np.array([tq[0] * w - tq[1] * x - tq[2] * y - tq[3] * z, tq[0] * x + tq[1] * w + tq[2] * z - tq[3] * y,
+                      tq[0] * y - tq[1] * z + tq[2] * w + tq[3] * x, tq[0] * z + tq[1] * y - tq[2] * x + tq[3] * w])
+        ref = collide(6, pA, [1, 0, 0, 0], hA, 6, pB, q, hB)
+        out = np.zeros(56)
+        n32 = L.emu_collide_boxes(d(pA), d(hA), d(pB), d(q), d(hB), 0, d(out))
+        assert len(ref) == n32 and len(ref) >= 3, (trial, len(ref), n32, tilt)
+        assert np.allclose(out[:7 * n32].reshape(-1, 7)[:, :3], ref[:, :3], atol=2e-6)
