@@ -79,14 +79,16 @@ k_env(DevCtx c, int n_single, int n_ticks, int gym, int flag_base, const float* 
 __global__ void __launch_bounds__(CTA_THREADS, (CTA_THREADS > 256 ? 1 : 2))
 k_reset(DevCtx c, const float* __restrict__ ctx, const uint8_t* __restrict__ mask, float* __restrict__ obs) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int warp = threadIdx.x / G_LANES;
+  const int e = blockIdx.x * c.epc + warp;
+  // masked reset (auto-reset of the ~1 % of envs that finished): CTAs without a masked env leave before staging the tables
+  if (!__syncthreads_or(e < c.n && (!mask || mask[e]))) return;
   Model* sm = (Model*)smem_raw;
   stage_model(sm, c.model, c.model_bytes);
   const Model& m = *sm;
   const Lay& L = c.lay;
-  const int warp = threadIdx.x / G_LANES;
   Cx cx; cx.lane = threadIdx.x % G_LANES;
   cx.mask = G_LANES == 32 ? 0xffffffffu : (((1u << G_LANES) - 1u) << (((threadIdx.x & 31) / G_LANES) * G_LANES));
-  const int e = blockIdx.x * c.epc + warp;
   if (e >= c.n) return;
   cx.cta_threads = c.epc * G_LANES;
   if (mask && !mask[e]) return;
