@@ -176,6 +176,7 @@ struct Model {
   tab_t link[D3_MAXLINK * D3_LINK_W];
   tab_t geom[D3_MAXGEOM * D3_GEOM_W];
   tab_t geomR[D3_MAXGEOM * 9];
+  tab_t linkR[D3_MAXLINK * 9];             // constant rotation of each link frame in its parent (quat2mat of the table's quaternion)
   tab_t ctrl[D3_CTRL_W];
   tab_t taskp[32];
   tab_t pair[D3_MAXPAIR * D3_PAIR_W];      // LAST: only the first npair rows are staged into shared memory (d3il_model_bytes)
@@ -310,13 +311,19 @@ DEVNI void kinematics(const Cx& cx, const Model& m, const Lay& L, real* w) {
       for (int j = 0; j <= i; j++) {
         if (!((anc >> j) & 1u)) continue;
         const tab_t* Lk = m.link + D3_LINK_W * j;
-        real off[3], lp[3] = {(real)Lk[2], (real)Lk[3], (real)Lk[4]}, lq[4] = {(real)Lk[5], (real)Lk[6], (real)Lk[7], (real)Lk[8]};
+        real off[3], lp[3] = {(real)Lk[2], (real)Lk[3], (real)Lk[4]};
         mat_vec3(off, R, lp);
         p[0] += off[0]; p[1] += off[1]; p[2] += off[2];
-        real Rq[9]; quat2mat(Rq, lq); mat_mul3(R, R, Rq);
+        real Rq[9];
+        for (int k = 0; k < 9; k++) Rq[k] = (real)m.linkR[9 * j + k];
+        mat_mul3(R, R, Rq);
         real q = w[L.qpos + m.l_qadr[j]];
         real ax[3] = {(real)Lk[9], (real)Lk[10], (real)Lk[11]};
-        if (m.l_jtype[j] == 0) {
+        if (m.l_jtype[j] == 0 && ax[0] == 0 && ax[1] == 0 && ax[2] == 1) {
+          // hinge about the link's z axis (every Panda joint): R <- R Rz(q) mixes the first two columns
+          real s, c; sincos_small(q, &s, &c);
+          for (int r = 0; r < 3; r++) { real x0 = R[3 * r], x1 = R[3 * r + 1]; R[3 * r] = c * x0 + s * x1; R[3 * r + 1] = c * x1 - s * x0; }
+        } else if (m.l_jtype[j] == 0) {
           real s, c; sincos_small((real)0.5 * q, &s, &c);
           real hq[4] = {c, s * ax[0], s * ax[1], s * ax[2]}, Rj[9];
           quat2mat(Rj, hq); mat_mul3(R, R, Rj);

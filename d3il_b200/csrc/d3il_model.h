@@ -27,6 +27,13 @@ static inline bool d3il_build_model(const void* blob, size_t nbytes, Model& m, L
     for (int k = 0; k < D3_LINK_W; k++) m.link[D3_LINK_W * i + k] = (tab_t)p[k];
     m.l_parent[i] = (int)p[0]; m.l_jtype[i] = (int)p[1]; m.l_limited[i] = (int)p[22]; m.l_qadr[i] = (int)p[29]; m.l_dadr[i] = (int)p[30];
     m.l_ndof[i] = m.l_jtype[i] == 2 ? 6 : 1;
+    {
+      double n = sqrt(p[5] * p[5] + p[6] * p[6] + p[7] * p[7] + p[8] * p[8]);
+      double w = p[5] / n, x = p[6] / n, y = p[7] / n, z = p[8] / n;
+      double R[9] = {1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y), 2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x),
+                     2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)};
+      for (int k = 0; k < 9; k++) m.linkR[9 * i + k] = (tab_t)R[k];
+    }
     m.l_anc[i] = (1u << i) | (m.l_parent[i] >= 0 ? m.l_anc[m.l_parent[i]] : 0u);
     for (int k = 0; k < m.l_ndof[i]; k++) m.d_link[m.l_dadr[i] + k] = i;
   }
