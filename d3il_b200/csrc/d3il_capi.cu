@@ -134,6 +134,8 @@ __global__ void __launch_bounds__(IK_THREADS) k_ik(DevCtx c, const float* __rest
 }
 
 // ------------------------------------------------------------------------------------------------ C ABI
+static int create_impl(d3il_env* h, const void* blob, size_t nbytes, int n_envs, int device);
+
 extern "C" int d3il_create(d3il_env** out, const void* blob, size_t nbytes, int n_envs, int device) {
   if (!out || !blob || n_envs <= 0) { g_err = "d3il_create: bad arguments"; return -1; }
   int ndev = 0;
@@ -141,9 +143,17 @@ extern "C" int d3il_create(d3il_env** out, const void* blob, size_t nbytes, int 
   d3il_env* h = new (std::nothrow) d3il_env();
   if (!h) { g_err = "out of memory"; return -1; }
   memset(&h->d, 0, sizeof(h->d));
+  h->device = device;
+  const int rc = create_impl(h, blob, nbytes, n_envs, device);
+  if (rc != 0) { const std::string keep = g_err; d3il_destroy(h); g_err = keep; return rc; }      // every allocation made so far is released
+  *out = h;
+  return 0;
+}
+
+static int create_impl(d3il_env* h, const void* blob, size_t nbytes, int n_envs, int device) {
   std::string err;
-  if (!d3il_build_model(blob, nbytes, h->m, h->L, err)) { g_err = "d3il_create: " + err; delete h; return -1; }
-  if (!((h->m.ctrl_kind == 0 && h->m.act_dim == 7) || (h->m.ctrl_kind == 1 && h->m.act_dim == 8))) { g_err = "d3il_create: unsupported action layout"; delete h; return -1; }
+  if (!d3il_build_model(blob, nbytes, h->m, h->L, err)) { g_err = "d3il_create: " + err; return -1; }
+  if (!((h->m.ctrl_kind == 0 && h->m.act_dim == 7) || (h->m.ctrl_kind == 1 && h->m.act_dim == 8))) { g_err = "d3il_create: unsupported action layout"; return -1; }
   h->device = device; h->n = n_envs; h->launches = 0; h->max_ticks = h->m.n_substeps > 64 ? h->m.n_substeps : 64;
   CK(cudaSetDevice(device));
   DevCtx& d = h->d;
@@ -174,7 +184,7 @@ extern "C" int d3il_create(d3il_env** out, const void* blob, size_t nbytes, int 
   d.epc = ENVS_PER_CTA;
   while (d.epc > 1 && model_bytes + d.epc * env_bytes > 227 * 1024) d.epc--;
   h->smem_bytes = model_bytes + (size_t)d.epc * env_bytes;
-  if (h->smem_bytes > 227 * 1024) { g_err = "d3il_create: scene workspace does not fit in shared memory"; delete h; return -1; }
+  if (h->smem_bytes > 227 * 1024) { g_err = "d3il_create: scene workspace does not fit in shared memory"; return -1; }
   CK(d3il_env_kernels_configure(h->smem_bytes));
   CK(cudaFuncSetAttribute(k_ik, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CK(cudaFuncSetAttribute(k_sched, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -195,7 +205,6 @@ extern "C" int d3il_create(d3il_env** out, const void* blob, size_t nbytes, int 
   CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   h->profiling = 0; h->prof_ms[0] = h->prof_ms[1] = 0; h->prof_n = 0;
   for (int i = 0; i < 3; i++) CK(cudaEventCreate(&h->ev[i]));
-  *out = h;
   return 0;
 }
 
@@ -204,7 +213,8 @@ extern "C" void d3il_destroy(d3il_env* h) {
   cudaSetDevice(h->device);
   cudaFree((void*)h->d.model); cudaFree(h->d.state); cudaFree(h->d.ik.q); cudaFree(h->d.ik.des); cudaFree(h->d.ik.jt); cudaFree(h->d.ik.valid);
   cudaFree(h->d.traj); cudaFree(h->d.ik_flags); cudaFree(h->d.perm); cudaFreeHost(h->h_in); cudaFreeHost(h->h_out); cudaFreeHost(h->h_mask); cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_mask);
-  cudaStreamDestroy(h->own_stream);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  for (int i = 0; i < 3; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   delete h;
 }
 
