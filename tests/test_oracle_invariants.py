@@ -348,3 +348,40 @@ def test_box_box_nearly_parallel_faces_give_face_contacts_in_both_precisions():
         n32 = L.emu_collide_boxes(d(pA), d(hA), d(pB), d(q), d(hB), 0, d(out))
         assert len(ref) == n32 and len(ref) >= 3, (trial, len(ref), n32, tilt)
         assert np.allclose(out[:7 * n32].reshape(-1, 7)[:, :3], ref[:, :3], atol=2e-6)
+
+
+def test_grasp_holds_the_box_kkt_and_torsional_cone():
+    """Stacking, condim-4 rows: after the scripted grasp-and-lift the box hangs between the pads — KKT stationarity of the
+    Newton result, every contact force inside its (regularised) elliptic cone incl. the torsional component, and the
+    contact forces on the box balance its weight and inertia (J^T f restricted to the box's linear dofs = m (a + g))."""
+    from d3il_b200.scene.blob import load_scene
+    from tests.util import scripted_grasp_actions, task_contexts
+    blob, sc = load_scene("stacking")
+    nv = sc.header["nv"]
+    o = OracleEnv(blob, sc.header)
+    ctx = task_contexts("stacking")[1]
+    obs0 = o.reset(ctx)
+    for a in scripted_grasp_actions(sc, ctx, o.robot_state(), o.joint_state()[:7], obs0):
+        obs, r, d, info = o.step(a)
+    assert obs[2] > 0.14                                   # red box in the air
+    o.substep(1)
+    M = o.probe("M").reshape(nv, nv); J = o.probe("efc_J").reshape(-1, nv)
+    f = o.probe("efc_force"); qacc = o.probe("qacc"); qs = o.probe("qacc_smooth")
+    assert np.abs(M @ (qacc - qs) - J.T @ f).max() < 1e-6
+    con = o.probe("contacts").reshape(-1, 12)
+    fr4 = np.array([2.0, 2.0, 0.05])                       # pad-box pair: friction (tangent, tangent, torsion) = max of the geoms'
+    n4 = 0
+    for c in con:
+        e0, dim, mu = int(c[11]), int(c[7]), c[10]
+        if e0 < 0:
+            continue
+        assert f[e0] >= -1e-12
+        if dim == 4 and f[e0] > 1e-6 and (int(c[8]) in (2, 3)):      # finger-tip pads vs the red box
+            n4 += 1
+            t = np.sqrt(sum((f[e0 + 1 + j] / fr4[j]) ** 2 for j in range(3)))
+            assert t <= f[e0] / mu * (1 + 1e-9) + 1e-9
+    assert n4 >= 4
+    # Newton's second law for the held box (dofs 9..11 = world-frame linear acceleration of the red box)
+    lin = slice(9, 12)
+    assert np.allclose((J.T @ f)[lin], 0.05 * (qacc[lin] + np.array([0, 0, 9.81])), atol=1e-6)
+    assert abs(qacc[11]) < 2.0                             # and it is (nearly) held: far from free fall
