@@ -370,7 +370,10 @@ def run_gpu(args):
 
     # ---- per-kernel device time (CUDA events on the launching stream, inside the library) for the roofline object
     env.set_profiling(True)
-    for k in range(8):
+    for k in range(4):          # the library synchronises after every profiled step: let the stream settle first
+        advance()
+    env.set_profiling(True)     # (re-arming clears the accumulators)
+    for k in range(24):
         advance()
     ik_ms, env_ms, nprof = env.get_profile()
     env.set_profiling(False)
@@ -441,13 +444,14 @@ def run_gpu(args):
     import oracle.oracle as oo
     oo.build()
     cores = os.cpu_count() or 1
-    spw = 192 if task in ("pushing", "avoiding", "aligning", "sorting_2") else 64
     with mp.get_context("fork").Pool(cores) as pool:
-        cpu_sample(args.workload, cores, 16, pool)
+        probe_val, _ = cpu_sample(args.workload, cores, 32, pool)
+        # bounded sample: ~20 s of CPU work in total (all cores for ~1.3 s each), sized from the probe's rate
+        spw = int(min(4096, max(64, 1.3 * probe_val / cores)))
         cpu_val, cpu_wall = cpu_sample(args.workload, cores, spw, pool)
-    one_val, one_wall = cpu_sample(args.workload, 1, 8 * spw)
+    one_val, one_wall = cpu_sample(args.workload, 1, 2 * spw)
     cpu_baseline = {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
-                    "sample": f"{cores} processes x {spw} env steps of the {args.workload} workload (one fp64 oracle env per core, {cpu_wall:.1f} s); single core: {one_val:.0f} env-steps/s over {8 * spw} steps",
+                    "sample": f"{cores} processes x {spw} env steps of the {args.workload} workload (one fp64 oracle env per core, {cpu_wall:.1f} s); single core: {one_val:.0f} env-steps/s over {2 * spw} steps",
                     "single_core_value": one_val}
 
     print(json.dumps({
