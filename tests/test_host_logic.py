@@ -190,3 +190,26 @@ def test_stacking_mode_string_round_trip_and_synthetic_policies():
     assert a.shape == (9, 2) and torch.isfinite(a).all() and a.abs().max() <= 0.01 + 1e-9
     b = SyntheticBCPolicy(4, 2, device="cpu")
     assert b.predict(np.zeros(4, np.float32)).shape == (1, 2)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the oracle port on the host cores) prints ONE JSON line with the contract's keys; a
+    non-zero rank under torchrun prints nothing and exits 0."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-500:]
+    line = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
+    assert len(line) == 1
+    d = json.loads(line[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["metric"] == "env_steps_per_sec" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"] and d["cpu_baseline"]["cores"] == (os.cpu_count() or 1)
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=120, cwd=root, env=env)
+    assert out.returncode == 0 and out.stdout.strip() == ""
