@@ -184,6 +184,10 @@ static int create_impl(d3il_env* h, const void* blob, size_t nbytes, int n_envs,
   d.epc = ENVS_PER_CTA;
   while (d.epc > 1 && model_bytes + d.epc * env_bytes > 227 * 1024) d.epc--;
   h->smem_bytes = model_bytes + (size_t)d.epc * env_bytes;
+  if (const char* ev = getenv("D3IL_SMEM_PAD_KB")) {      // diagnosis: pad the request so fewer CTAs share an SM
+    const size_t padded = h->smem_bytes + (size_t)atoi(ev) * 1024;
+    if (padded <= 227 * 1024) h->smem_bytes = padded;
+  }
   if (h->smem_bytes > 227 * 1024) { g_err = "d3il_create: scene workspace does not fit in shared memory"; return -1; }
   CK(d3il_env_kernels_configure(h->smem_bytes));
   CK(cudaFuncSetAttribute(k_ik, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
