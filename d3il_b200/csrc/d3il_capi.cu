@@ -94,13 +94,17 @@ __global__ void __launch_bounds__(IK_THREADS) k_ik(DevCtx c, const float* __rest
   for (int k = 0; k < 7; k++) { s.q[k] = c.ik.q[k * n + e]; s.jt_q[k] = c.ik.jt[k * n + e]; s.jt_qlo[k] = c.ik.jt[(7 + k) * n + e]; s.jt_qd[k] = c.ik.jt[(14 + k) * n + e]; }
   s.valid = c.ik.valid[e];
   int cart = use_action ? 1 : (row[c.lay.misc + ST_CTRL_MODE] == 1.f);
+  // an unusable action (NaN / inf / zero quaternion) keeps the previous set-point; k_env's pre-step raises the status bit
+  const bool aok = use_action && action_ok(action + (size_t)e * act_dim, act_dim, ctrl_kind);
   if (use_action && ctrl_kind == 1) {
+    cart = 0;
+    if (aok) {
     // joint-space action (Stacking): the set-point IS the action, held for the whole env step (Controller.py:99-127, zero
     // desired velocity); no IK.  The gripper command action[7] is consumed by k_env's pre-step.
     const float* a = action + (size_t)e * act_dim;
     for (int k = 0; k < 7; k++) { s.jt_q[k] = a[k]; s.jt_qlo[k] = 0; s.jt_qd[k] = 0; }
-    cart = 0;
-  } else if (use_action) {
+    }
+  } else if (aok) {
     const float* a = action + (size_t)e * act_dim;
     float nq = rsqrtf(a[3] * a[3] + a[4] * a[4] + a[5] * a[5] + a[6] * a[6]);
     s.des_pos[0] = a[0]; s.des_pos[1] = a[1]; s.des_pos[2] = a[2];
@@ -109,6 +113,8 @@ __global__ void __launch_bounds__(IK_THREADS) k_ik(DevCtx c, const float* __rest
   } else {
     for (int k = 0; k < 3; k++) s.des_pos[k] = c.ik.des[k * n + e];
     for (int k = 0; k < 4; k++) s.des_quat[k] = c.ik.des[(3 + k) * n + e];
+    // held set-point that was never installed (bad action on the first step after a reset): stay under the joint PD hold
+    if (use_action && s.des_quat[0] == 0.f && s.des_quat[1] == 0.f && s.des_quat[2] == 0.f && s.des_quat[3] == 0.f) cart = 0;
   }
   if (cart && !s.valid) {                      // IKControllers.py:168-169: old_q NaN -> measured joints
     for (int k = 0; k < 7; k++) s.q[k] = (double)row[c.lay.qpos + k] + (double)row[c.lay.qlo + k];
@@ -184,10 +190,12 @@ static int create_impl(d3il_env* h, const void* blob, size_t nbytes, int n_envs,
   d.epc = ENVS_PER_CTA;
   while (d.epc > 1 && model_bytes + d.epc * env_bytes > 227 * 1024) d.epc--;
   h->smem_bytes = model_bytes + (size_t)d.epc * env_bytes;
-  if (const char* ev = getenv("D3IL_SMEM_PAD_KB")) {      // diagnosis: pad the request so fewer CTAs share an SM
+#ifdef D3IL_DIAG
+  if (const char* ev = getenv("D3IL_SMEM_PAD_KB")) {      // diagnosis build only: pad the request so fewer CTAs share an SM
     const size_t padded = h->smem_bytes + (size_t)atoi(ev) * 1024;
     if (padded <= 227 * 1024) h->smem_bytes = padded;
   }
+#endif
   if (h->smem_bytes > 227 * 1024) { g_err = "d3il_create: scene workspace does not fit in shared memory"; return -1; }
   CK(d3il_env_kernels_configure(h->smem_bytes));
   CK(cudaFuncSetAttribute(k_ik, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -195,7 +203,9 @@ static int create_impl(d3il_env* h, const void* blob, size_t nbytes, int n_envs,
   // the most expensive envs of each step run one per CTA (cost-sorted order, see k_sched / k_env)
   // (more single-env CTAs shorten the tail CTA but add CTAs; at 4096 envs = 585 x 7 + 1 exactly one is free)
   h->n_single = (G_LANES == 32 && n_envs >= 512) ? 1 + (n_envs - 1) % d.epc : 0;
+#ifdef D3IL_DIAG
   if (const char* ev = getenv("D3IL_N_SINGLE")) { h->n_single = atoi(ev); if (h->n_single < 0 || h->n_single > n_envs / 2 || G_LANES != 32) h->n_single = 0; }
+#endif
   // staging for the host-buffer entry points
   const Model& m = h->m;
   h->in_floats = (size_t)n_envs * (m.act_dim > m.ctx_dim ? m.act_dim : m.ctx_dim);
@@ -251,8 +261,15 @@ extern "C" int d3il_get_profile(const d3il_env* h, double out_ms[2], long long* 
 // so that it overlaps k_ik (per-tick hand-off through ik_flags).  If the driver serialises them anyway the result is the same.
 static cudaError_t launch_step(d3il_env* h, cudaStream_t s, const float* action, int n_ticks, int gym, float* obs, float* reward, uint8_t* done, float* info, cudaEvent_t after_ik = nullptr) {
   h->launch_id = (h->launch_id + 1) & 0xffffff;
+  // the release flags are monotonic (launch_id * 64 + tick + 1): when the id wraps they restart from zero, in stream order
+  // (every earlier k_env has finished by then), otherwise k_env would see stale larger values and stop waiting for k_ik
+  if (h->launch_id == 0) { cudaError_t e = cudaMemsetAsync(h->d.ik_flags, 0, (size_t)h->n_ik_blocks * sizeof(int), s); if (e != cudaSuccess) return e; }
   const int base = h->launch_id * 64;
-  static const bool no_pdl = getenv("D3IL_NO_PDL") != nullptr;      // diagnosis: serialise the kernels
+#ifdef D3IL_DIAG
+  static const bool no_pdl = getenv("D3IL_NO_PDL") != nullptr;      // diagnosis build only: serialise the kernels
+#else
+  const bool no_pdl = false;
+#endif
   k_sched<<<1, 1024, 0, s>>>(h->d);
   k_ik<<<h->n_ik_blocks, IK_THREADS, 0, s>>>(h->d, action, n_ticks, gym, base, h->m.ctrl_kind, h->m.act_dim);
   h->launches += 3;

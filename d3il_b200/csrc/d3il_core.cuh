@@ -199,6 +199,9 @@ struct Lay {
   int act, jt, con, ncon_pair, limflag, cflag, J, aref, D, jar, frcE, Jp, hd, hb, etype, econ, total;
 };
 enum { ST_GRIP_SET = 0, ST_GRASP, ST_CTRL_MODE, ST_STEP, ST_TERM, ST_STATUS, ST_OBST, ST_TASK0, ST_TASK1, ST_TASK2, ST_TASK3, ST_COST_ITERS /* Newton iterations of the last env step */, ST_COST_COUPLED /* ticks with a tree-coupling contact */, ST_COST_NCON /* max contacts */, ST_NMISC = 16 };
+// per-env fault word (misc[ST_STATUS], last column of `info`; sticky until the env is reset)
+enum { D3_STATUS_M_NOT_PD = 1, D3_STATUS_OVERFLOW = 2 /* contact / row budget exceeded: contacts dropped */, D3_STATUS_H_NOT_PD = 4,
+       D3_STATUS_ITER_CAP = 8 /* Newton loop left at max_iter without passing the convergence test */, D3_STATUS_BAD_ACTION = 16 /* non-finite action or zero quaternion: last set-point held */ };
 #define D3_CON_W 24    // per contact: pos3, frame9, dist, incl, mu, dim, g1, g2, pair, row0, dof ranges a0,a1,b0,b1
 
 #define D3_JW 16       // compact Jacobian row: entries of the contact's two dof ranges (<= 9 + 6), padded to 16
@@ -1275,11 +1278,13 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
     LANES(d, nv) { w[L.hpiv + d] = w[L.H + d * nv + d]; w[L.pvec + d] = -w[L.grad + d]; }
     gsync<G>(cx);
     int maxsz = coupled ? nv : m.maxblk;
-    if (chol_factor_part<G>(cx, m, w + L.H, nv, coupled != 0, maxsz, w + L.hpiv, w + L.hdinv)) {
-      LANES(z, 1) w[L.misc + ST_STATUS] = (real)(((int)w[L.misc + ST_STATUS]) | 4);
-      break;
-    }
+    // A Hessian that is not positive definite (NaN inputs included) ends this env's solve with status bit 4.  The env must
+    // NOT leave the loop on its own: the iteration is CTA-uniform (cta_any above is a barrier every warp of the CTA has to
+    // reach), so it turns `done` and idles through the remaining passes like a converged env.
+    const int hfail = chol_factor_part<G>(cx, m, w + L.H, nv, coupled != 0, maxsz, w + L.hpiv, w + L.hdinv);
+    if (hfail) { LANES(z, 1) w[L.misc + ST_STATUS] = (real)(((int)w[L.misc + ST_STATUS]) | D3_STATUS_H_NOT_PD); done = 1; gsync<G>(cx); }
     PHASE(10);
+    if (!hfail) {
     chol_solve_part<G>(cx, m, w + L.H, nv, coupled != 0, maxsz, w + L.hdinv, w + L.pvec);
     PHASE(11);
     // ---- exact line search (safeguarded 1-D Newton / false position), quantities reduced across lanes
@@ -1356,7 +1361,10 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
     grad_fresh = 0;
     PHASE(12);
     }
+    }
   }
+  // iteration cap reached without the convergence test passing: reported, never silent (the oracle flags its own cap the same way)
+  if (!done) { LANES(z, 1) w[L.misc + ST_STATUS] = (real)(((int)w[L.misc + ST_STATUS]) | D3_STATUS_ITER_CAP); }
   // qfrc_constraint = J^T f = M (a - a_s) - grad when the gradient belongs to the final iterate (converged exit)
   if (ne > 0 && grad_fresh) { LANES(d, nv) w[L.qfrc_c + d] = w[L.Ma + d] - w[L.grad + d]; }
   else if (ne > 0) LANES(d, nv) {

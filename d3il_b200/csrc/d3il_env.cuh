@@ -132,12 +132,68 @@ DEVFN void jacobi6(ikr* A, ikr* wv, ikr* V, int warm) {
   for (int i = 0; i < 6; i++) wv[i] = A[i * 6 + i];
 }
 
+// Clipped-spectrum solve, fast path.  The controller applies A^-1 with the eigenvalues of A = J J^T + reg I clipped to
+// [lo, hi] (IKControllers.py: np.linalg.svd + np.clip).  When the whole spectrum already lies inside the clip range the
+// result is simply A^-1 rhs, and that is decidable without an eigen-decomposition: lambda_max <= trace(A) < hi, and
+// lambda_min > lo  <=>  A - lo I is positive definite  <=>  its Cholesky factorisation finds positive pivots only.
+// Pass 0 factors A - lo I (the test), pass 1 factors A and solves.  Returns 0 (x untouched) when clipping may be active;
+// the caller then takes the Jacobi path.  At the boundary both paths agree (the clipped inverse is continuous), so the
+// test needs no margin.  Panda poses over the tabletop workspace have lambda in [0.03, 4]: the fast path is the rule.
+DEVFN int ik_solve_unclipped(const ikr* A, const ikr* rhs, ikr lo, ikr hi, ikr* x) {
+  if (!(A[0] + A[7] + A[14] + A[21] + A[28] + A[35] < hi)) return 0;
+  ikr Lf[36], dinv[6];
+#pragma unroll
+  for (int pass = 0; pass < 2; pass++) {
+    const ikr shift = pass == 0 ? lo : (ikr)0;
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+      ikr sd = A[j * 6 + j] - shift;
+#pragma unroll
+      for (int k = 0; k < j; k++) sd -= Lf[j * 6 + k] * Lf[j * 6 + k];
+      if (!(sd > 1e-14)) return 0;
+      const ikr d = ik_rsqrt(sd);
+      dinv[j] = d;
+#pragma unroll
+      for (int i = j + 1; i < 6; i++) {
+        ikr so = A[i * 6 + j];
+#pragma unroll
+        for (int k = 0; k < j; k++) so -= Lf[i * 6 + k] * Lf[j * 6 + k];
+        Lf[i * 6 + j] = so * d;
+      }
+    }
+  }
+  ikr y[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) { ikr so = rhs[i];
+#pragma unroll
+    for (int k = 0; k < i; k++) so -= Lf[i * 6 + k] * y[k];
+    y[i] = so * dinv[i]; }
+#pragma unroll
+  for (int i = 5; i >= 0; i--) { ikr so = y[i];
+#pragma unroll
+    for (int k = i + 1; k < 6; k++) so -= Lf[k * 6 + i] * x[k];
+    x[i] = so * dinv[i]; }
+  return 1;
+}
+
+// Slow path of the same solve: eigen-decomposition (warm-started Jacobi) and the clipped spectrum.  Deliberately NOT
+// inlined: its 72 doubles of A / V then live in local memory on this rare path only, instead of pushing the fast path's
+// working set out of the register file.
+DEVNI void ik_solve_clipped(const ikr* Ain, const ikr* rhs, ikr* V, int warm, ikr lo, ikr hi, ikr* x) {
+  ikr A[36], wv[6], y[6];
+  for (int k = 0; k < 36; k++) A[k] = Ain[k];
+  jacobi6(A, wv, V, warm);
+  for (int c = 0; c < 6; c++) { ikr sum = 0; for (int r = 0; r < 6; r++) sum += V[r * 6 + c] * rhs[r]; y[c] = sum / ik_clamp(fabs(wv[c]), lo, hi); }
+  for (int r = 0; r < 6; r++) { ikr sum = 0; for (int c = 0; c < 6; c++) sum += V[r * 6 + c] * y[c]; x[r] = sum; }
+}
+
 // One getControl() call of CartPosQuatImpedenceController: num_iter damped-least-squares iterations on the open-loop
 // joint reference; outputs the joint PD set-point (q_des as two floats, qd_des) for this physics tick.
 DEVFN void ik_tick(const tab_t* C, IkState& s, ikr* V, int* vwarm, ikr* sn, ikr* cs) {
   ikr q[7], des_quat[4] = {(ikr)s.des_quat[0], (ikr)s.des_quat[1], (ikr)s.des_quat[2], (ikr)s.des_quat[3]};
   for (int k = 0; k < 7; k++) q[k] = s.q[k];
-  if (!*vwarm) for (int k = 0; k < 7; k++) { sn[k] = sin(q[k]); cs[k] = cos(q[k]); }      // exact once per launch
+  // *vwarm: bit 0 = sn/cs hold the sines/cosines of q, bit 1 = V holds an eigenbasis of an earlier Jacobi call
+  if (!(*vwarm & 1)) { for (int k = 0; k < 7; k++) { sn[k] = sin(q[k]); cs[k] = cos(q[k]); } *vwarm |= 1; }      // exact once per launch
   const int niter = (int)C[D3C_NUM_ITER];
   for (int it = 0; it < niter; it++) {
     ikr pos[3], cq[4], J[42];
@@ -153,20 +209,23 @@ DEVFN void ik_tick(const tab_t* C, IkState& s, ikr* V, int* vwarm, ikr* sn, ikr*
       acc[k] = (ikr)C[D3C_PGAIN_POS + k] * ik_clamp((ikr)s.des_pos[k] - pos[k], -0.01, 0.01);
       acc[3 + k] = (ikr)C[D3C_PGAIN_QUAT + k] * ik_clamp(qe[k], -0.1, 0.1);
     }
-    ikr A[36], wv[6];
+    ikr A[36];
     for (int r = 0; r < 6; r++) for (int c = r; c < 6; c++) {
       ikr sum = 0;
       for (int k = 0; k < 7; k++) sum += J[r * 7 + k] * J[c * 7 + k];
       if (r == c) sum += (ikr)C[D3C_JREG];
       A[r * 6 + c] = sum; A[c * 6 + r] = sum;
     }
-    jacobi6(A, wv, V, *vwarm);
-    *vwarm = 1;
-    ikr qd_null[7], rhs[6], y[6], x[6];
+    ikr qd_null[7], rhs[6], x[6];
     for (int k = 0; k < 7; k++) qd_null[k] = (ikr)C[D3C_PGAIN_NULL + k] * ik_clamp((ikr)C[D3C_REST + k] - q[k], -0.2, 0.2);
     for (int r = 0; r < 6; r++) { ikr sum = acc[r]; for (int k = 0; k < 7; k++) sum -= J[r * 7 + k] * qd_null[k]; rhs[r] = sum; }
-    for (int c = 0; c < 6; c++) { ikr sum = 0; for (int r = 0; r < 6; r++) sum += V[r * 6 + c] * rhs[r]; y[c] = sum / ik_clamp(fabs(wv[c]), (ikr)C[D3C_SVD_MIN], (ikr)C[D3C_SVD_MAX]); }
-    for (int r = 0; r < 6; r++) { ikr sum = 0; for (int c = 0; c < 6; c++) sum += V[r * 6 + c] * y[c]; x[r] = sum; }
+    if (!ik_solve_unclipped(A, rhs, (ikr)C[D3C_SVD_MIN], (ikr)C[D3C_SVD_MAX], x)) {
+      // some eigenvalue is (or may be) outside the clip range: eigen-decomposition, clipped spectrum
+      ikr A2[36];
+      for (int k = 0; k < 36; k++) A2[k] = A[k];
+      ik_solve_clipped(A2, rhs, V, *vwarm & 2, (ikr)C[D3C_SVD_MIN], (ikr)C[D3C_SVD_MAX], x);
+      *vwarm |= 2;
+    }
     ikr qd[7], nrm = 0;
     for (int k = 0; k < 7; k++) { ikr sum = qd_null[k]; for (int r = 0; r < 6; r++) sum += J[r * 7 + k] * x[r]; qd[k] = sum; nrm += sum * sum; }
     nrm = sqrt(nrm);
@@ -460,14 +519,29 @@ DEVFN void env_reset(const Cx& cx, const Model& m, const Lay& L, real* w, const 
   gsync<G>(cx);
 }
 
+// An action the controllers cannot take as a set-point: a non-finite component, or (Cartesian scenes) a quaternion of zero
+// norm.  The reference would propagate NaN into MuJoCo and warn; here the env keeps its previous set-point for this env step
+// and raises D3_STATUS_BAD_ACTION.  Evaluated identically by k_ik (set-point) and env_prestep (status bit, gripper command).
+DEVFN bool action_ok(const float* a, int act_dim, int ctrl_kind) {
+  bool ok = true;
+  for (int k = 0; k < act_dim; k++) ok = ok && (absr((real)a[k]) <= (real)3.0e38);      // false for NaN and +-inf
+  if (ctrl_kind == 0) ok = ok && (a[3] * a[3] + a[4] * a[4] + a[5] * a[5] + a[6] * a[6] > 1e-12f);
+  return ok;
+}
+
 // pre-substep half of GymEnvWrapper.step (gym_env_wrapper.py:67-90): open fingers, Cartesian mode, sample obs /
 // reward / done BEFORE the substeps.
 template <int G>
 DEVFN void env_prestep(const Cx& cx, const Model& m, const Lay& L, real* w, const float* action, float* obs, float* reward, unsigned char* done) {
   LANES(z, 1) {
+    const bool aok = action_ok(action, m.act_dim, m.ctrl_kind);
+    if (!aok) w[L.misc + ST_STATUS] = (real)(((int)w[L.misc + ST_STATUS]) | D3_STATUS_BAD_ACTION);
     if (m.ctrl_kind == 1) {        // CubeStacking_Env.step (stacking.py:337-346): gripper command in action[7], joint-space set-point
-      const bool open = action[7] > (float)m.taskp[4];
-      w[L.misc + ST_GRIP_SET] = open ? (real)0.04 : (real)0; w[L.misc + ST_GRASP] = open ? (real)0 : (real)1; w[L.misc + ST_CTRL_MODE] = 2;
+      if (aok) {
+        const bool open = action[7] > (float)m.taskp[4];
+        w[L.misc + ST_GRIP_SET] = open ? (real)0.04 : (real)0; w[L.misc + ST_GRASP] = open ? (real)0 : (real)1;
+      }
+      w[L.misc + ST_CTRL_MODE] = 2;
     } else { w[L.misc + ST_GRIP_SET] = (real)0.04; w[L.misc + ST_GRASP] = 0; w[L.misc + ST_CTRL_MODE] = 1; }
     w[L.misc + ST_COST_ITERS] = 0; w[L.misc + ST_COST_COUPLED] = 0; w[L.misc + ST_COST_NCON] = 0;
     task_obs(m, L, w, obs);

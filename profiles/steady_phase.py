@@ -1,6 +1,8 @@
 """Debug: per-phase cycle counts of one CTA and all-env cost statistics in the STEADY-STATE episode mix of bench.py
 (build with make EXTRA='-DD3IL_PHASE_TIMING -DD3IL_PHASE_BLOCK="(gridDim.x/2)"')."""
 import ctypes as C, os, sys
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import _variant  # noqa: F401  (D3IL_VARIANT=<name> selects a diagnostic build)
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from d3il_b200.batched_env import BatchedEnv

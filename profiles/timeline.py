@@ -1,5 +1,7 @@
 """Debug: block-level timeline of one env step (k_ik blocks + k_env CTAs), from %globaltimer (timing build only)."""
 import ctypes as C, os, sys
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import _variant  # noqa: F401  (D3IL_VARIANT=<name> selects a diagnostic build)
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from d3il_b200.batched_env import BatchedEnv

@@ -104,3 +104,30 @@ def test_slab_fast_path_equals_general_box_box():
         used += 1
         assert n1 == n2 and np.allclose(o1[:7 * n2], o2[:7 * n2], atol=1e-12)
     assert used > 5000
+
+
+def test_ik_fast_path_and_clipped_spectrum_fallback():
+    """ik_solve_unclipped (Cholesky of A and of A - svd_min I) replaces the eigen-decomposition whenever the spectrum of
+    J J^T lies inside the clip range; towards the edge of the arm's reach lambda_min drops below svd_min = 1e-2 and the
+    Jacobi path with the clipped spectrum takes over.  Both regimes (and the hand-over) must track the oracle, which
+    always eigen-decomposes (IKControllers.py:239-262)."""
+    blob, sc = load_scene("avoiding")
+    o, e = OracleEnv(blob, sc.header), EmuEnv(blob, sc.header, "f64")
+    o.reset(); e.reset()
+    des = o.robot_state().copy()
+    lam_min = []
+    for k in range(140):
+        des[0] += 0.004                      # straight out along +x: reach limit at ~0.85 m
+        des[1] += 0.001
+        a = np.concatenate([des, [0, 1, 0, 0]])
+        ro, re = o.step(a), e.step(a)
+        so, se = o.get_state(), e.get_state()
+        assert np.abs(so[:9] - se[:9]).max() < 1e-9, k
+        off = 9 + 2 * 9
+        ikq = so[off + 16: off + 23]
+        _, _, J = o.ik_fk(ikq)
+        lam_min.append(np.linalg.eigvalsh(J @ J.T + 1e-12 * np.eye(6))[0])
+        if ro[2]:
+            break
+    lam_min = np.array(lam_min)
+    assert lam_min[0] > 1e-2 and lam_min.min() < 5e-3, (lam_min[0], lam_min.min())     # both regimes were visited
