@@ -17,6 +17,10 @@
 #include <vector>
 
 #include "../../include/d3il.h"
+#ifndef IK_THREADS
+#define IK_THREADS 128
+#endif
+#define IK_JSTRIDE IK_THREADS      // k_ik keeps the Jacobians of its block in shared memory as J[k][thread]
 #include "d3il_dev.h"
 
 static thread_local std::string g_err;
@@ -30,7 +34,7 @@ extern "C" const char* d3il_last_error(void) { return g_err.c_str(); }
 struct d3il_env {
   Model m; Lay L;
   DevCtx d;
-  int device, n, max_ticks, n_ik_blocks, launch_id, n_single;
+  int device, n, max_ticks, n_ik_blocks, n_ik_flags, launch_id, n_single;
   long long launches;
   size_t smem_bytes;
   // pinned + device staging for the *_host calls
@@ -82,8 +86,13 @@ __global__ void __launch_bounds__(IK_THREADS) k_ik(DevCtx c, const float* __rest
   // already resident when it is allowed to launch, so the hand-off cannot deadlock.
   asm volatile("griddepcontrol.launch_dependents;");
   TL_BEGIN(1, 2048 + blockIdx.x);
-  __shared__ tab_t sctrl[D3_CTRL_W];
-  for (int i = threadIdx.x; i < D3_CTRL_W; i += blockDim.x) sctrl[i] = c.model->ctrl[i];
+  extern __shared__ __align__(16) double ik_smem[];      // IK_SMEM_BYTES: controller table (as doubles), Jacobians J[k][thread], per-warp cooperative scratch
+  double* sctrl = ik_smem;
+  double* sJ = sctrl + D3_CTRL_W;
+  double* coop_all = sJ + 42 * IK_THREADS;
+  double* coop = coop_all + 160 * (threadIdx.x / 32);
+  Cx cx; cx.lane = threadIdx.x & 31; cx.mask = 0xffffffffu; cx.cta_threads = IK_THREADS;
+  for (int i = threadIdx.x; i < D3_CTRL_W; i += blockDim.x) sctrl[i] = (double)c.model->ctrl[i];
   __syncthreads();
   const int e_raw = blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = e_raw < c.n;               // threads past the batch shadow the last env (they must reach the barriers)
@@ -120,17 +129,17 @@ __global__ void __launch_bounds__(IK_THREADS) k_ik(DevCtx c, const float* __rest
     for (int k = 0; k < 7; k++) s.q[k] = (double)row[c.lay.qpos + k] + (double)row[c.lay.qlo + k];
     s.valid = 1;
   }
-  double V[36], sn[7], cs[7]; int vwarm = 0;   // eigenbasis and joint sines/cosines carried across the IK iterations of this launch
+  double V[42], sn[7], cs[7]; int vwarm = 0;   // eigenbasis and joint sines/cosines carried across the IK iterations of this launch
   for (int t = 0; t < n_ticks; t++) {
-    if (cart) ik_tick(sctrl, s, V, &vwarm, sn, cs);
+    ik_tick<32>(cx, sctrl, s, cart, V, &vwarm, sn, cs, sJ + threadIdx.x, coop);
     if (live) {
       float* tr = c.traj + (size_t)t * 21 * n + e;
       for (int k = 0; k < 7; k++) { tr[k * n] = s.jt_q[k]; tr[(7 + k) * n] = s.jt_qlo[k]; tr[(14 + k) * n] = s.jt_qd[k]; }
     }
     // publish tick t of this block's envs
     __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) *(volatile int*)(c.ik_flags + blockIdx.x) = flag_base + t + 1;
+    __syncwarp();
+    if (cx.lane == 0) *(volatile int*)(c.ik_flags + (blockIdx.x * blockDim.x + threadIdx.x) / IK_FLAG_ENVS) = flag_base + t + 1;
   }
   if (live) {
     for (int k = 0; k < 7; k++) { c.ik.q[k * n + e] = s.q[k]; c.ik.jt[k * n + e] = s.jt_q[k]; c.ik.jt[(7 + k) * n + e] = s.jt_qlo[k]; c.ik.jt[(14 + k) * n + e] = s.jt_qd[k]; }
@@ -138,6 +147,8 @@ __global__ void __launch_bounds__(IK_THREADS) k_ik(DevCtx c, const float* __rest
   }
   TL_END(1);
 }
+
+#define IK_SMEM_BYTES ((int)sizeof(double) * (D3_CTRL_W + 42 * IK_THREADS + 160 * (IK_THREADS / 32)))
 
 // ------------------------------------------------------------------------------------------------ C ABI
 static int create_impl(d3il_env* h, const void* blob, size_t nbytes, int n_envs, int device);
@@ -181,9 +192,10 @@ static int create_impl(d3il_env* h, const void* blob, size_t nbytes, int n_envs,
   CK(cudaMemset(d.ik.valid, 0, (size_t)n_envs * sizeof(int)));
   CK(cudaMalloc(&d.traj, (size_t)h->max_ticks * 21 * n_envs * sizeof(float)));
   h->n_ik_blocks = (n_envs + IK_THREADS - 1) / IK_THREADS; h->launch_id = 0;
-  CK(cudaMalloc(&d.ik_flags, (size_t)h->n_ik_blocks * sizeof(int)));
+  h->n_ik_flags = h->n_ik_blocks * (IK_THREADS / IK_FLAG_ENVS);
+  CK(cudaMalloc(&d.ik_flags, (size_t)h->n_ik_flags * sizeof(int)));
   CK(cudaMalloc(&d.perm, (size_t)n_envs * sizeof(int)));
-  CK(cudaMemset(d.ik_flags, 0, (size_t)h->n_ik_blocks * sizeof(int)));
+  CK(cudaMemset(d.ik_flags, 0, (size_t)h->n_ik_flags * sizeof(int)));
   // envs per CTA: ENVS_PER_CTA (two CTAs per SM for the small scenes), fewer when the per-env workspace is large (Sorting-4/6)
   const size_t model_bytes = d3il_model_bytes(h->m), env_bytes = (size_t)d.ws_stride * sizeof(float);
   d.model_bytes = (int)model_bytes;
@@ -198,6 +210,7 @@ static int create_impl(d3il_env* h, const void* blob, size_t nbytes, int n_envs,
 #endif
   if (h->smem_bytes > 227 * 1024) { g_err = "d3il_create: scene workspace does not fit in shared memory"; return -1; }
   CK(d3il_env_kernels_configure(h->smem_bytes));
+  CK(cudaFuncSetAttribute(k_ik, cudaFuncAttributeMaxDynamicSharedMemorySize, IK_SMEM_BYTES));
   CK(cudaFuncSetAttribute(k_ik, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CK(cudaFuncSetAttribute(k_sched, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   // the most expensive envs of each step run one per CTA (cost-sorted order, see k_sched / k_env)
@@ -263,7 +276,7 @@ static cudaError_t launch_step(d3il_env* h, cudaStream_t s, const float* action,
   h->launch_id = (h->launch_id + 1) & 0xffffff;
   // the release flags are monotonic (launch_id * 64 + tick + 1): when the id wraps they restart from zero, in stream order
   // (every earlier k_env has finished by then), otherwise k_env would see stale larger values and stop waiting for k_ik
-  if (h->launch_id == 0) { cudaError_t e = cudaMemsetAsync(h->d.ik_flags, 0, (size_t)h->n_ik_blocks * sizeof(int), s); if (e != cudaSuccess) return e; }
+  if (h->launch_id == 0) { cudaError_t e = cudaMemsetAsync(h->d.ik_flags, 0, (size_t)h->n_ik_flags * sizeof(int), s); if (e != cudaSuccess) return e; }
   const int base = h->launch_id * 64;
 #ifdef D3IL_DIAG
   static const bool no_pdl = getenv("D3IL_NO_PDL") != nullptr;      // diagnosis build only: serialise the kernels
@@ -271,7 +284,7 @@ static cudaError_t launch_step(d3il_env* h, cudaStream_t s, const float* action,
   const bool no_pdl = false;
 #endif
   k_sched<<<1, 1024, 0, s>>>(h->d);
-  k_ik<<<h->n_ik_blocks, IK_THREADS, 0, s>>>(h->d, action, n_ticks, gym, base, h->m.ctrl_kind, h->m.act_dim);
+  k_ik<<<h->n_ik_blocks, IK_THREADS, IK_SMEM_BYTES, s>>>(h->d, action, n_ticks, gym, base, h->m.ctrl_kind, h->m.act_dim);
   h->launches += 3;
   if (after_ik) cudaEventRecord(after_ik, s);        // completes when k_ik has finished (k_env may already be running: PDL)
   return d3il_launch_env(h->d, h->m.maxdim, h->n_single, n_ticks, gym, base, action, obs, reward, done, info, h->smem_bytes, s, !no_pdl);

@@ -37,6 +37,7 @@ template <int G> DEVFN real gsum(const Cx&, real x) { return x; }
 template <int G> DEVFN real gmaxr(const Cx&, real x) { return x; }
 template <int G> DEVFN int gsumi(const Cx&, int x) { return x; }
 template <int G> DEVFN int gori(const Cx&, int x) { return x; }
+template <int G> DEVFN double gsumd(const Cx&, double x) { return x; }
 #else
 #define DEVFN __device__ __forceinline__
 #define HDFN __host__ __device__ __forceinline__
@@ -62,6 +63,11 @@ template <int G> DEVFN int gsumi(const Cx& cx, int x) {
 template <int G> DEVFN int gori(const Cx& cx, int x) {
 #pragma unroll
   for (int o = G / 2; o > 0; o >>= 1) x |= __shfl_xor_sync(cx.mask, x, o, G);
+  return x;
+}
+template <int G> DEVFN double gsumd(const Cx& cx, double x) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) x += __shfl_xor_sync(cx.mask, x, o, G);
   return x;
 }
 #endif

@@ -17,10 +17,11 @@
 #endif
 #define CTA_THREADS (G_LANES * ENVS_PER_CTA)
 #ifndef IK_THREADS
-#define IK_THREADS 128   // 32 k_ik blocks at 4096 envs: an SM that hosts one (4 warps x 255 regs) still takes one k_env CTA; with one warp per
-                         // block the 128 blocks spread over 128 SMs and each of them lost its second k_env CTA until k_ik left (-12 %)
+#define IK_THREADS 128   // 32 k_ik blocks at 4096 envs.  Registers are allocated to a CTA in units of 4 warps, so a k_ik block always costs
+                         // >= 4 x 32 x 255 registers: an SM that hosts one takes only ONE k_env CTA (2 x 8-warp units) until it leaves.
+                         // Four warps per block keep the number of such SMs at 32 (one-warp blocks: 128 SMs, measured -14 %).
 #endif
-
+#define IK_FLAG_ENVS 32  // release flags are per k_ik WARP: a warp whose envs need the slow clipped-spectrum path does not hold back the others
 struct DevIk {            // SoA views, [field][n]
   double* q;              // [7][n]
   float* des;             // [7][n]  des_pos(3), des_quat(4)
@@ -36,7 +37,7 @@ struct DevCtx {
   int epc;                // envs (warps) per CTA: ENVS_PER_CTA unless the scene's workspace needs more shared memory per env
   DevIk ik;
   float* traj;            // [ticks][21][n]
-  int* ik_flags;          // [n_ik_blocks] ticks published by each k_ik block (monotonic: launch_id * 64 + tick + 1)
+  int* ik_flags;          // [ceil(n / IK_FLAG_ENVS)] ticks published by each k_ik warp (monotonic: launch_id * 64 + tick + 1)
   int* perm;              // [n] env order of this step's k_env groups: most expensive envs (last step's Newton iterations) first
   float tol; int max_iter;
 };

@@ -21,6 +21,14 @@ struct IkState {
 // otherwise fp32): with fp32 forward kinematics the 1e-7 m position noise is amplified by gain/dt into ~1e-3 N m of PD
 // torque noise, which is what dominated the kernel-vs-oracle velocity error.
 typedef double ikr;
+// The controller table is handed to the IK routines as DOUBLES (k_ik converts the fp32 model table once per block into shared
+// memory): with a float table the compiler hoists ~100 float->double conversions out of the iteration loops and spills them.
+// The 6x7 Jacobian of an env is addressed with a stride: 1 on the host (plain array), the block size in k_ik, where it lives
+// in shared memory as J[k][thread] (conflict-free, and 84 registers less per thread: no spills).
+#ifndef IK_JSTRIDE
+#define IK_JSTRIDE 1
+#endif
+#define IKJ(J, k) (J)[(k) * IK_JSTRIDE]
 DEVFN void ik_cross3(ikr* o, const ikr* a, const ikr* b) {
   ikr x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
   o[0] = x; o[1] = y; o[2] = z;
@@ -52,84 +60,44 @@ DEVFN ikr ik_rsqrt(ikr x) {
 }
 DEVFN ikr ik_clamp(ikr x, ikr lo, ikr hi) { return x < lo ? lo : (x > hi ? hi : x); }
 
-DEVFN void ik_fk(const tab_t* C, const ikr* sn, const ikr* cs, ikr* pos, ikr* quat, ikr* J) {
+// Forward kinematics + geometric Jacobian of the URDF chain (core/Model.py:37-66).  Everything is unrolled and
+// statically indexed so that the 42 Jacobian doubles live in registers (k_ik is one thread per env).
+DEVFN void ik_fk(const ikr* C, const ikr* sn, const ikr* cs, ikr* pos, ikr* quat, ikr* J) {
   ikr p[3] = {0, 0, 0}, R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, org[7][3], axs[7][3];
+#pragma unroll
   for (int i = 0; i < 7; i++) {
-    const tab_t* o = C + D3C_IK_ORIGIN + 12 * i;
-    ikr ov[3] = {(ikr)o[0], (ikr)o[1], (ikr)o[2]}, oR[9], t[3];
-    for (int k = 0; k < 9; k++) oR[k] = o[3 + k];
-    ik_mat_vec3(t, R, ov); p[0] += t[0]; p[1] += t[1]; p[2] += t[2];
-    ik_mat_mul3(R, R, oR);
-    ikr c = cs[i], s = sn[i], Rz[9] = {c, -s, 0, s, c, 0, 0, 0, 1};
-    ik_mat_mul3(R, R, Rz);
+    const ikr* o = C + D3C_IK_ORIGIN + 12 * i;
+    const ikr c = cs[i], s = sn[i];
+    ikr Rn[9];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      p[r] += R[3 * r] * (ikr)o[0] + R[3 * r + 1] * (ikr)o[1] + R[3 * r + 2] * (ikr)o[2];
+      // R <- R oR Rz(q): first R oR, then mix its first two columns
+      const ikr m0 = R[3 * r] * (ikr)o[3] + R[3 * r + 1] * (ikr)o[6] + R[3 * r + 2] * (ikr)o[9];
+      const ikr m1 = R[3 * r] * (ikr)o[4] + R[3 * r + 1] * (ikr)o[7] + R[3 * r + 2] * (ikr)o[10];
+      const ikr m2 = R[3 * r] * (ikr)o[5] + R[3 * r + 1] * (ikr)o[8] + R[3 * r + 2] * (ikr)o[11];
+      Rn[3 * r] = m0 * c + m1 * s; Rn[3 * r + 1] = m1 * c - m0 * s; Rn[3 * r + 2] = m2;
+    }
+#pragma unroll
+    for (int k = 0; k < 9; k++) R[k] = Rn[k];
     org[i][0] = p[0]; org[i][1] = p[1]; org[i][2] = p[2];
     axs[i][0] = R[2]; axs[i][1] = R[5]; axs[i][2] = R[8];
   }
-  const tab_t* o = C + D3C_IK_EE;
-  ikr ov[3] = {(ikr)o[0], (ikr)o[1], (ikr)o[2]}, oR[9], t[3], Re[9];
-  for (int k = 0; k < 9; k++) oR[k] = o[3 + k];
-  ik_mat_vec3(t, R, ov);
-  pos[0] = p[0] + t[0]; pos[1] = p[1] + t[1]; pos[2] = p[2] + t[2];
-  ik_mat_mul3(Re, R, oR); ik_mat2quat(quat, Re);
+  const ikr* o = C + D3C_IK_EE;
+  ikr Re[9];
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    pos[r] = p[r] + (R[3 * r] * (ikr)o[0] + R[3 * r + 1] * (ikr)o[1] + R[3 * r + 2] * (ikr)o[2]);
+#pragma unroll
+    for (int c = 0; c < 3; c++) Re[3 * r + c] = R[3 * r] * (ikr)o[3 + c] + R[3 * r + 1] * (ikr)o[6 + c] + R[3 * r + 2] * (ikr)o[9 + c];
+  }
+  ik_mat2quat(quat, Re);
+#pragma unroll
   for (int i = 0; i < 7; i++) {
-    ikr r[3] = {pos[0] - org[i][0], pos[1] - org[i][1], pos[2] - org[i][2]}, l[3];
-    ik_cross3(l, axs[i], r);
-    for (int k = 0; k < 3; k++) { J[k * 7 + i] = l[k]; J[(3 + k) * 7 + i] = axs[i][k]; }
+    const ikr r0 = pos[0] - org[i][0], r1 = pos[1] - org[i][1], r2 = pos[2] - org[i][2];
+    IKJ(J, i) = axs[i][1] * r2 - axs[i][2] * r1; IKJ(J, 7 + i) = axs[i][2] * r0 - axs[i][0] * r2; IKJ(J, 14 + i) = axs[i][0] * r1 - axs[i][1] * r0;
+    IKJ(J, 21 + i) = axs[i][0]; IKJ(J, 28 + i) = axs[i][1]; IKJ(J, 35 + i) = axs[i][2];
   }
-}
-
-// Cyclic Jacobi eigen-decomposition of a symmetric 6x6 (np.linalg.svd of the SPD matrix J J^T + reg I).
-// `V` carries the eigenbasis of the previous call when `warm` is set: A changes by O(1e-3) per IK iteration, so
-// rotating into the old basis first leaves a nearly diagonal matrix and one or two sweeps finish it (instead of ~7).
-DEVFN void jacobi6(ikr* A, ikr* wv, ikr* V, int warm) {
-  if (warm) {
-    ikr T[36];
-    for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) { ikr s = 0; for (int k = 0; k < 6; k++) s += A[i * 6 + k] * V[k * 6 + j]; T[i * 6 + j] = s; }
-    for (int i = 0; i < 6; i++) for (int j = i; j < 6; j++) { ikr s = 0; for (int k = 0; k < 6; k++) s += V[k * 6 + i] * T[k * 6 + j]; A[i * 6 + j] = s; A[j * 6 + i] = s; }
-  } else {
-    for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) V[i * 6 + j] = (i == j) ? 1.0 : 0.0;
-  }
-  // Round-robin (tournament) ordering: 5 rounds of 3 rotations on disjoint index pairs.  The three rotations of a
-  // round are independent instruction streams, which is what a single fp64 thread needs to hide pipe latency.
-  constexpr int PP[5][3] = {{0, 2, 3}, {0, 1, 4}, {0, 2, 1}, {0, 3, 1}, {0, 1, 2}};
-  constexpr int QQ[5][3] = {{1, 5, 4}, {2, 3, 5}, {3, 4, 5}, {4, 5, 2}, {5, 4, 3}};
-  for (int sweep = 0; sweep < 30; sweep++) {
-    ikr off = 0, diag = 0;
-    for (int i = 0; i < 6; i++) { diag += A[i * 6 + i] * A[i * 6 + i]; for (int j = i + 1; j < 6; j++) off += A[i * 6 + j] * A[i * 6 + j]; }
-    if (off <= 1e-26 * diag) break;
-#pragma unroll
-    for (int rd = 0; rd < 5; rd++) {
-      ikr cc[3], ss[3];
-#pragma unroll
-      for (int u = 0; u < 3; u++) {
-        const int p = PP[rd][u], q = QQ[rd][u];
-        ikr apq = A[p * 6 + q], d = A[q * 6 + q] - A[p * 6 + p];
-        // tan of the rotation angle: t = sign(d) * 2 apq / (|d| + sqrt(d^2 + 4 apq^2)); any t gives an orthogonal rotation
-        // (c, s) = (1, t) / sqrt(1 + t^2), so the angle only needs to be good enough for the quadratic convergence
-        ikr t = 0;
-        if (apq != 0) { ikr h = sqrt(d * d + 4 * apq * apq); t = 2 * apq / (d >= 0 ? d + h : d - h); }
-        ikr c = ik_rsqrt(1 + t * t);
-        cc[u] = c; ss[u] = t * c;
-      }
-#pragma unroll
-      for (int u = 0; u < 3; u++) {
-        const int p = PP[rd][u], q = QQ[rd][u];
-        ikr c = cc[u], s = ss[u];
-#pragma unroll
-        for (int k = 0; k < 6; k++) { ikr akp = A[k * 6 + p], akq = A[k * 6 + q]; A[k * 6 + p] = c * akp - s * akq; A[k * 6 + q] = s * akp + c * akq; }
-#pragma unroll
-        for (int k = 0; k < 6; k++) { ikr vkp = V[k * 6 + p], vkq = V[k * 6 + q]; V[k * 6 + p] = c * vkp - s * vkq; V[k * 6 + q] = s * vkp + c * vkq; }
-      }
-#pragma unroll
-      for (int u = 0; u < 3; u++) {
-        const int p = PP[rd][u], q = QQ[rd][u];
-        ikr c = cc[u], s = ss[u];
-#pragma unroll
-        for (int k = 0; k < 6; k++) { ikr apk = A[p * 6 + k], aqk = A[q * 6 + k]; A[p * 6 + k] = c * apk - s * aqk; A[q * 6 + k] = s * apk + c * aqk; }
-      }
-    }
-  }
-  for (int i = 0; i < 6; i++) wv[i] = A[i * 6 + i];
 }
 
 // Clipped-spectrum solve, fast path.  The controller applies A^-1 with the eigenvalues of A = J J^T + reg I clipped to
@@ -139,110 +107,299 @@ DEVFN void jacobi6(ikr* A, ikr* wv, ikr* V, int warm) {
 // Pass 0 factors A - lo I (the test), pass 1 factors A and solves.  Returns 0 (x untouched) when clipping may be active;
 // the caller then takes the Jacobi path.  At the boundary both paths agree (the clipped inverse is continuous), so the
 // test needs no margin.  Panda poses over the tabletop workspace have lambda in [0.03, 4]: the fast path is the rule.
-DEVFN int ik_solve_unclipped(const ikr* A, const ikr* rhs, ikr lo, ikr hi, ikr* x) {
-  if (!(A[0] + A[7] + A[14] + A[21] + A[28] + A[35] < hi)) return 0;
-  ikr Lf[36], dinv[6];
+// Packed lower triangle: element (i, j), j <= i, at i (i + 1) / 2 + j.
+#define IK_TRI(i, j) ((i) * ((i) + 1) / 2 + (j))
+DEVFN void ik_gram(const ikr* J, ikr diag_add, ikr* A21) {      // A = J J^T + diag_add I
 #pragma unroll
-  for (int pass = 0; pass < 2; pass++) {
-    const ikr shift = pass == 0 ? lo : (ikr)0;
+  for (int i = 0; i < 6; i++)
 #pragma unroll
-    for (int j = 0; j < 6; j++) {
-      ikr sd = A[j * 6 + j] - shift;
+    for (int j = 0; j <= i; j++) {
+      ikr s = i == j ? diag_add : (ikr)0;
 #pragma unroll
-      for (int k = 0; k < j; k++) sd -= Lf[j * 6 + k] * Lf[j * 6 + k];
-      if (!(sd > 1e-14)) return 0;
-      const ikr d = ik_rsqrt(sd);
-      dinv[j] = d;
+      for (int k = 0; k < 7; k++) s += IKJ(J, i * 7 + k) * IKJ(J, j * 7 + k);
+      A21[IK_TRI(i, j)] = s;
+    }
+}
+DEVFN int ik_chol21(ikr* A21, ikr* dinv) {      // in place: A21 <- L (strict lower part), dinv <- 1 / L_jj; 0 if a pivot is not positive
 #pragma unroll
-      for (int i = j + 1; i < 6; i++) {
-        ikr so = A[i * 6 + j];
+  for (int j = 0; j < 6; j++) {
+    ikr sd = A21[IK_TRI(j, j)];
 #pragma unroll
-        for (int k = 0; k < j; k++) so -= Lf[i * 6 + k] * Lf[j * 6 + k];
-        Lf[i * 6 + j] = so * d;
-      }
+    for (int k = 0; k < j; k++) sd -= A21[IK_TRI(j, k)] * A21[IK_TRI(j, k)];
+    if (!(sd > 1e-14)) return 0;
+    const ikr d = ik_rsqrt(sd);
+    dinv[j] = d;
+#pragma unroll
+    for (int i = j + 1; i < 6; i++) {
+      ikr so = A21[IK_TRI(i, j)];
+#pragma unroll
+      for (int k = 0; k < j; k++) so -= A21[IK_TRI(i, k)] * A21[IK_TRI(j, k)];
+      A21[IK_TRI(i, j)] = so * d;
     }
   }
+  return 1;
+}
+// Inertia of a symmetric matrix by LDL^T without pivoting (Sylvester): *nneg = number of negative pivots = number of
+// negative eigenvalues.  Returns 0 when a pivot is too small to trust its sign.
+DEVFN int ik_ldl_inertia(ikr* A21, int* nneg) {
+  ikr dd[6];
+  int neg = 0;
+#pragma unroll
+  for (int j = 0; j < 6; j++) {
+    ikr sd = A21[IK_TRI(j, j)];
+#pragma unroll
+    for (int k = 0; k < j; k++) sd -= A21[IK_TRI(j, k)] * A21[IK_TRI(j, k)] * dd[k];
+    if (!(fabs(sd) > 1e-12)) return 0;
+    dd[j] = sd; neg += sd < 0;
+    const ikr inv = 1 / sd;
+#pragma unroll
+    for (int i = j + 1; i < 6; i++) {
+      ikr so = A21[IK_TRI(i, j)];
+#pragma unroll
+      for (int k = 0; k < j; k++) so -= A21[IK_TRI(i, k)] * A21[IK_TRI(j, k)] * dd[k];
+      A21[IK_TRI(i, j)] = so * inv;
+    }
+  }
+  *nneg = neg;
+  return 1;
+}
+DEVFN void ik_chol_solve21(const ikr* L21, const ikr* dinv, const ikr* b, ikr* x) {      // x = (L L^T)^-1 b
   ikr y[6];
 #pragma unroll
-  for (int i = 0; i < 6; i++) { ikr so = rhs[i];
+  for (int i = 0; i < 6; i++) { ikr so = b[i];
 #pragma unroll
-    for (int k = 0; k < i; k++) so -= Lf[i * 6 + k] * y[k];
+    for (int k = 0; k < i; k++) so -= L21[IK_TRI(i, k)] * y[k];
     y[i] = so * dinv[i]; }
 #pragma unroll
   for (int i = 5; i >= 0; i--) { ikr so = y[i];
 #pragma unroll
-    for (int k = i + 1; k < 6; k++) so -= Lf[k * 6 + i] * x[k];
+    for (int k = i + 1; k < 6; k++) so -= L21[IK_TRI(k, i)] * x[k];
     x[i] = so * dinv[i]; }
+}
+// x = V clip(Lambda, lo, hi)^-1 V^T rhs for A = J J^T + reg I WITHOUT an eigen-decomposition, in the two cases that cover the
+// tabletop workspace (measured on the random-walk workload: 98 % / 2 % / none):
+//   (0) no eigenvalue outside [lo, hi]:  x = A^-1 rhs.  Decided by lambda_max <= trace(A) < hi and a Cholesky factorisation
+//       of A - lo I (positive pivots only  <=>  lambda_min > lo).
+//   (1) exactly ONE eigenvalue below lo (the arm near the edge of its reach: the elbow singularity; the next eigenvalue
+//       is ~0.2, 20x larger):  x = A^-1 rhs + (1/lo - 1/lambda_1) (v_1 . rhs) v_1, with (lambda_1, v_1) from inverse
+//       iteration on the Cholesky factor of A (convergence factor lambda_1 / lambda_2 <= 0.05 per step), warm-started from
+//       the previous call's v_1.  "Exactly one" is the inertia of A - lo I (LDL^T pivot signs).
+// Anything else (two small eigenvalues, an untrustworthy pivot, no convergence) returns 0 and the caller falls back to the
+// Jacobi eigen-decomposition.  The clipped inverse is continuous in A, so the case boundaries need no margins.
+DEVFN int ik_solve_spd(const ikr* J, ikr reg, const ikr* rhs, ikr lo, ikr hi, ikr* x, ikr* v1 /*6*/, int* v1_valid) {
+  ikr A[21], dinv[6];
+  ik_gram(J, reg - lo, A);
+  if (!(A[IK_TRI(0, 0)] + A[IK_TRI(1, 1)] + A[IK_TRI(2, 2)] + A[IK_TRI(3, 3)] + A[IK_TRI(4, 4)] + A[IK_TRI(5, 5)] + 6 * lo < hi)) return 0;
+  const int none_below = ik_chol21(A, dinv);
+  if (!none_below) {
+    int nneg = 0;
+    ik_gram(J, reg - lo, A);
+    if (!ik_ldl_inertia(A, &nneg) || nneg != 1) return 0;
+  }
+  ik_gram(J, reg, A);                                            // A itself (rebuilt: cheaper than keeping a copy in registers)
+  if (!ik_chol21(A, dinv)) return 0;
+  ik_chol_solve21(A, dinv, rhs, x);
+  if (none_below) return 1;
+  ikr v[6], u[6];
+#pragma unroll
+  for (int k = 0; k < 6; k++) v[k] = *v1_valid ? v1[k] : (ikr)0.40824829046386302;
+  int conv = 0;
+  for (int itn = 0; itn < 48 && !conv; itn++) {
+    ik_chol_solve21(A, dinv, v, u);
+    ikr n2 = 0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) n2 += u[k] * u[k];
+    const ikr inv = ik_rsqrt(n2);
+    ikr d2 = 0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) { const ikr vn = u[k] * inv; d2 += (vn - v[k]) * (vn - v[k]); v[k] = vn; }
+    conv = d2 < 1e-28;
+  }
+  if (!conv) return 0;
+  ik_chol_solve21(A, dinv, v, u);                               // Rayleigh quotient of A^-1: 1 / lambda_1 = v . A^-1 v
+  ikr il = 0, vr = 0;
+#pragma unroll
+  for (int k = 0; k < 6; k++) { il += v[k] * u[k]; vr += v[k] * rhs[k]; }
+  const ikr coef = (1 / lo - il) * vr;
+  if (il > 1 / lo) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) x[k] += coef * v[k];
+  }
+#pragma unroll
+  for (int k = 0; k < 6; k++) v1[k] = v[k];
+  *v1_valid = 1;
   return 1;
 }
 
-// Slow path of the same solve: eigen-decomposition (warm-started Jacobi) and the clipped spectrum.  Deliberately NOT
-// inlined: its 72 doubles of A / V then live in local memory on this rare path only, instead of pushing the fast path's
-// working set out of the register file.
-DEVNI void ik_solve_clipped(const ikr* Ain, const ikr* rhs, ikr* V, int warm, ikr lo, ikr hi, ikr* x) {
-  ikr A[36], wv[6], y[6];
-  for (int k = 0; k < 36; k++) A[k] = Ain[k];
-  jacobi6(A, wv, V, warm);
-  for (int c = 0; c < 6; c++) { ikr sum = 0; for (int r = 0; r < 6; r++) sum += V[r * 6 + c] * rhs[r]; y[c] = sum / ik_clamp(fabs(wv[c]), lo, hi); }
+// Slow path of the same solve: symmetric eigen-decomposition by parallel-ordered Jacobi rotations, clipped spectrum.
+// `V` (persistent within the launch) carries the eigenbasis of the previous call when `warm` is set: A changes by
+// O(1e-3) per IK iteration, so rotating into the old basis first leaves a nearly diagonal matrix and two or three sweeps
+// finish it.  A sweep = 5 rounds of 3 rotations on disjoint index pairs (round-robin ordering); the three rotations of a
+// round commute, so the round is ONE similarity transform A <- G^T A G, V <- V G with two non-zeros per column of G:
+// one lane per matrix entry, results into the B1 / B2 buffers, copied back after the barrier.
+// In k_ik (one THREAD per env) this is the warp-cooperative service routine: the warp's 32 lanes decompose the matrix of one
+// env that needs it (ik_tick's ballot loop) in ~1/6 of the instructions a single lane would spend; the host build runs it with G = 1.
+template <int G>
+DEVNI void ik_solve_clipped_lanes(const Cx& cx, ikr* A, const ikr* rhs, ikr* V, ikr* B1, ikr* B2, ikr* csb, int warm, ikr lo, ikr hi, ikr* x) {
+  if (warm) {
+    LANES(e, 36) { const int i = e / 6, j = e - 6 * i; ikr s = 0; for (int k = 0; k < 6; k++) s += A[i * 6 + k] * V[k * 6 + j]; B1[e] = s; }
+    gsync<G>(cx);
+    LANES(e, 36) {      // V^T (A V); (i, j) and (j, i) evaluate the same expression: exactly symmetric
+      const int i = e / 6, j = e - 6 * i, a = i < j ? i : j, b = i < j ? j : i;
+      ikr s = 0; for (int k = 0; k < 6; k++) s += V[k * 6 + a] * B1[k * 6 + b];
+      A[e] = s;
+    }
+  } else {
+    LANES(e, 36) V[e] = (e / 6 == e % 6) ? 1.0 : 0.0;
+  }
+  gsync<G>(cx);
+  constexpr int PP[5][3] = {{0, 2, 3}, {0, 1, 4}, {0, 2, 1}, {0, 3, 1}, {0, 1, 2}};
+  constexpr int QQ[5][3] = {{1, 5, 4}, {2, 3, 5}, {3, 4, 5}, {4, 5, 2}, {5, 4, 3}};
+  for (int sweep = 0; sweep < 30; sweep++) {
+    ikr po = 0, pd = 0;
+    LANES(e, 36) { const int i = e / 6, j = e - 6 * i; const ikr a = A[e]; if (i == j) pd += a * a; else if (j > i) po += a * a; }
+    const ikr off = gsumd<G>(cx, po), diag = gsumd<G>(cx, pd);
+    if (off <= 1e-22 * diag) break;      // sums of squares: off-diagonal entries below 1e-11 of the diagonal scale (x is then good to ~1e-10)
+    for (int rd = 0; rd < 5; rd++) {
+      LANES(u, 3) {
+        const int p = PP[rd][u], q = QQ[rd][u];
+        const ikr apq = A[p * 6 + q], d = A[q * 6 + q] - A[p * 6 + p];
+        // tan of the rotation angle: t = sign(d) * 2 apq / (|d| + sqrt(d^2 + 4 apq^2)); (c, s) = (1, t) / sqrt(1 + t^2).
+        // ANY t gives an exactly orthogonal rotation once (c, s) are formed in fp64, so t itself is computed in fp32 (its
+        // 1e-7 relative error leaves a_pq' ~ 1e-7 a_pq, below what the quadratic convergence delivers anyway) — an fp64
+        // sqrt + divide here is a ~1000-cycle dependent chain, five times per sweep.
+        float tf = 0.f;
+        if (apq != 0) { const float df = (float)d, af = (float)apq; const float hf = sqrtf(df * df + 4.f * af * af); tf = 2.f * af / (df >= 0.f ? df + hf : df - hf); }
+        const ikr t = (ikr)tf;
+        const ikr c = ik_rsqrt(1 + t * t);
+        csb[2 * u] = c; csb[2 * u + 1] = t * c;
+      }
+      gsync<G>(cx);
+      LANES(e, 36) {
+        const int i0 = e / 6, j0 = e - 6 * i0, i = i0 < j0 ? i0 : j0, j = i0 < j0 ? j0 : i0;
+        // index k of the round: partner pk, new column k = ak * old column k + bk * old column pk  (p: c, -s ; q: c, +s)
+        int pi = 0, pj = 0, pj0 = 0; ikr ai = 1, bi = 0, aj = 1, bj = 0, aj0 = 1, bj0 = 0;
+        for (int u = 0; u < 3; u++) {
+          const int p = PP[rd][u], q = QQ[rd][u]; const ikr c = csb[2 * u], s = csb[2 * u + 1];
+          if (i == p) { pi = q; ai = c; bi = -s; } else if (i == q) { pi = p; ai = c; bi = s; }
+          if (j == p) { pj = q; aj = c; bj = -s; } else if (j == q) { pj = p; aj = c; bj = s; }
+          if (j0 == p) { pj0 = q; aj0 = c; bj0 = -s; } else if (j0 == q) { pj0 = p; aj0 = c; bj0 = s; }
+        }
+        B1[e] = (ai * aj) * A[i * 6 + j] + (ai * bj) * A[i * 6 + pj] + (bi * aj) * A[pi * 6 + j] + (bi * bj) * A[pi * 6 + pj];
+        B2[e] = aj0 * V[i0 * 6 + j0] + bj0 * V[i0 * 6 + pj0];
+      }
+      gsync<G>(cx);
+      LANES(e, 36) { A[e] = B1[e]; V[e] = B2[e]; }
+      gsync<G>(cx);
+    }
+  }
+  ikr y[6];
+  for (int c = 0; c < 6; c++) { ikr sum = 0; for (int r = 0; r < 6; r++) sum += V[r * 6 + c] * rhs[r]; y[c] = sum / ik_clamp(fabs(A[c * 6 + c]), lo, hi); }
   for (int r = 0; r < 6; r++) { ikr sum = 0; for (int c = 0; c < 6; c++) sum += V[r * 6 + c] * y[c]; x[r] = sum; }
 }
 
+
 // One getControl() call of CartPosQuatImpedenceController: num_iter damped-least-squares iterations on the open-loop
 // joint reference; outputs the joint PD set-point (q_des as two floats, qd_des) for this physics tick.
-DEVFN void ik_tick(const tab_t* C, IkState& s, ikr* V, int* vwarm, ikr* sn, ikr* cs) {
+// `active` = 0: the thread only takes part in the warp-cooperative section (its own outputs are discarded).
+// coop: 160 doubles of scratch shared by the lane group (k_ik: shared memory per warp; host: a local array).
+template <int G>
+DEVFN void ik_tick(const Cx& cx, const ikr* C, IkState& s, int active, ikr* V, int* vwarm, ikr* sn, ikr* cs, ikr* J /*42 * IK_JSTRIDE*/, ikr* coop) {
   ikr q[7], des_quat[4] = {(ikr)s.des_quat[0], (ikr)s.des_quat[1], (ikr)s.des_quat[2], (ikr)s.des_quat[3]};
   for (int k = 0; k < 7; k++) q[k] = s.q[k];
-  // *vwarm: bit 0 = sn/cs hold the sines/cosines of q, bit 1 = V holds an eigenbasis of an earlier Jacobi call
+  // *vwarm: bit 0 = sn/cs hold the sines/cosines of q, bit 1 = V[0..35] holds an eigenbasis of an earlier Jacobi call,
+  //         bit 2 = V[36..41] holds the smallest eigenvector of an earlier ik_solve_spd call
   if (!(*vwarm & 1)) { for (int k = 0; k < 7; k++) { sn[k] = sin(q[k]); cs[k] = cos(q[k]); } *vwarm |= 1; }      // exact once per launch
   const int niter = (int)C[D3C_NUM_ITER];
   for (int it = 0; it < niter; it++) {
-    ikr pos[3], cq[4], J[42];
+    ikr pos[3], cq[4];
     ik_fk(C, sn, cs, pos, cq, J);
     ikr dm = 0, dp = 0;
+#pragma unroll
     for (int k = 0; k < 4; k++) { dm += (cq[k] - des_quat[k]) * (cq[k] - des_quat[k]); dp += (cq[k] + des_quat[k]) * (cq[k] + des_quat[k]); }
-    if (dm > dp) for (int k = 0; k < 4; k++) des_quat[k] = -des_quat[k];
-    ikr qe[3], acc[6];
+    if (dm > dp) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) des_quat[k] = -des_quat[k];
+    }
+    ikr qe[3], rhs[6], qd_null[7], x[6];
     qe[0] = cq[0] * des_quat[1] - des_quat[0] * cq[1] - cq[3] * des_quat[2] + cq[2] * des_quat[3];
     qe[1] = cq[0] * des_quat[2] - des_quat[0] * cq[2] + cq[3] * des_quat[1] - cq[1] * des_quat[3];
     qe[2] = cq[0] * des_quat[3] - des_quat[0] * cq[3] - cq[2] * des_quat[1] + cq[1] * des_quat[2];
+#pragma unroll
     for (int k = 0; k < 3; k++) {
-      acc[k] = (ikr)C[D3C_PGAIN_POS + k] * ik_clamp((ikr)s.des_pos[k] - pos[k], -0.01, 0.01);
-      acc[3 + k] = (ikr)C[D3C_PGAIN_QUAT + k] * ik_clamp(qe[k], -0.1, 0.1);
+      rhs[k] = (ikr)C[D3C_PGAIN_POS + k] * ik_clamp((ikr)s.des_pos[k] - pos[k], -0.01, 0.01);
+      rhs[3 + k] = (ikr)C[D3C_PGAIN_QUAT + k] * ik_clamp(qe[k], -0.1, 0.1);
     }
-    ikr A[36];
-    for (int r = 0; r < 6; r++) for (int c = r; c < 6; c++) {
-      ikr sum = 0;
-      for (int k = 0; k < 7; k++) sum += J[r * 7 + k] * J[c * 7 + k];
-      if (r == c) sum += (ikr)C[D3C_JREG];
-      A[r * 6 + c] = sum; A[c * 6 + r] = sum;
-    }
-    ikr qd_null[7], rhs[6], x[6];
+#pragma unroll
     for (int k = 0; k < 7; k++) qd_null[k] = (ikr)C[D3C_PGAIN_NULL + k] * ik_clamp((ikr)C[D3C_REST + k] - q[k], -0.2, 0.2);
-    for (int r = 0; r < 6; r++) { ikr sum = acc[r]; for (int k = 0; k < 7; k++) sum -= J[r * 7 + k] * qd_null[k]; rhs[r] = sum; }
-    if (!ik_solve_unclipped(A, rhs, (ikr)C[D3C_SVD_MIN], (ikr)C[D3C_SVD_MAX], x)) {
-      // some eigenvalue is (or may be) outside the clip range: eigen-decomposition, clipped spectrum
-      ikr A2[36];
-      for (int k = 0; k < 36; k++) A2[k] = A[k];
-      ik_solve_clipped(A2, rhs, V, *vwarm & 2, (ikr)C[D3C_SVD_MIN], (ikr)C[D3C_SVD_MAX], x);
-      *vwarm |= 2;
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+#pragma unroll
+      for (int k = 0; k < 7; k++) rhs[r] -= IKJ(J, r * 7 + k) * qd_null[k];
+    }
+    int v1ok = (*vwarm >> 2) & 1;
+    const int need = !ik_solve_spd(J, (ikr)C[D3C_JREG], rhs, (ikr)C[D3C_SVD_MIN], (ikr)C[D3C_SVD_MAX], x, V + 36, &v1ok) && active;
+    if (v1ok) *vwarm |= 4;
+    // Some eigenvalue is (or may be) outside the clip range: eigen-decomposition with the clipped spectrum.  Rare (~2 % of
+    // the iterations of the random-walk workload, near the edge of the arm's reach) but 5x the cost of everything else, and in
+    // k_ik one needy env would stall the 31 others of its warp: so the WARP serves its needy envs one after the other, all
+    // lanes cooperating on one 6x6 matrix in shared memory (coop).  Host build: G = 1, the env serves itself.
+#ifdef __CUDA_ARCH__
+    unsigned todo = __ballot_sync(cx.mask, need);
+#else
+    unsigned todo = need ? 1u : 0u;
+#endif
+    while (todo) {
+#ifdef __CUDA_ARCH__
+      const int src = __ffs(todo) - 1;
+#else
+      const int src = cx.lane;
+#endif
+      todo &= todo - 1;
+      ikr *cA = coop, *cV = coop + 36, *cB1 = coop + 72, *cB2 = coop + 108, *cR = coop + 144, *cC = coop + 152;
+      const ikr* Js = J + (src - cx.lane);                      // the needy env's Jacobian (J[k][thread] in shared memory)
+      const bool mine = cx.lane == src;
+      int warm = (*vwarm >> 1) & 1;
+#ifdef __CUDA_ARCH__
+      warm = __shfl_sync(cx.mask, warm, src);
+#endif
+      LANES(e, 36) {
+        const int i = e / 6, j = e - 6 * i, a2 = i < j ? i : j, b2 = i < j ? j : i;
+        ikr sum = a2 == b2 ? (ikr)C[D3C_JREG] : (ikr)0;
+        for (int k = 0; k < 7; k++) sum += IKJ(Js, a2 * 7 + k) * IKJ(Js, b2 * 7 + k);
+        cA[e] = sum;
+      }
+      if (mine) { for (int k = 0; k < 6; k++) cR[k] = rhs[k]; if (warm) for (int k = 0; k < 36; k++) cV[k] = V[k]; }
+      gsync<G>(cx);
+      ikr x2[6];
+      ik_solve_clipped_lanes<G>(cx, cA, cR, cV, cB1, cB2, cC, warm, (ikr)C[D3C_SVD_MIN], (ikr)C[D3C_SVD_MAX], x2);
+      if (mine) { for (int k = 0; k < 6; k++) x[k] = x2[k]; for (int k = 0; k < 36; k++) V[k] = cV[k]; *vwarm |= 2; }
+      gsync<G>(cx);
     }
     ikr qd[7], nrm = 0;
-    for (int k = 0; k < 7; k++) { ikr sum = qd_null[k]; for (int r = 0; r < 6; r++) sum += J[r * 7 + k] * x[r]; qd[k] = sum; nrm += sum * sum; }
-    nrm = sqrt(nrm);
-    if (nrm > 3) for (int k = 0; k < 7; k++) qd[k] *= 3 / nrm;
+#pragma unroll
     for (int k = 0; k < 7; k++) {
-      ikr qn = ik_clamp(q[k] + (ikr)C[D3C_LRATE] * qd[k], (ikr)C[D3C_JMIN + k], (ikr)C[D3C_JMAX + k]);
+      ikr sum = qd_null[k];
+#pragma unroll
+      for (int r = 0; r < 6; r++) sum += IKJ(J, r * 7 + k) * x[r];
+      qd[k] = sum; nrm += sum * sum;
+    }
+    nrm = sqrt(nrm);
+    const ikr scl = nrm > 3 ? 3 / nrm : (ikr)1;
+#pragma unroll
+    for (int k = 0; k < 7; k++) {
+      ikr qn = ik_clamp(q[k] + (ikr)C[D3C_LRATE] * (qd[k] * scl), (ikr)C[D3C_JMIN + k], (ikr)C[D3C_JMAX + k]);
       // sin/cos by the angle-addition formulas with a short series in the increment (|dq| <= 3e-3: the dq^6 term is
       // 1e-18), then one Newton step back onto the unit circle: 1e-16 per update instead of a software sincos
       ikr dq = qn - q[k], d2 = dq * dq;
       ikr sd = dq * (1 - d2 * (1.0 / 6.0) * (1 - d2 * 0.05)), cd = 1 - d2 * 0.5 * (1 - d2 * (1.0 / 12.0));
       ikr s1 = sn[k] * cd + cs[k] * sd, c1 = cs[k] * cd - sn[k] * sd;
-      ikr nrm = 1.5 - 0.5 * (s1 * s1 + c1 * c1);
-      sn[k] = s1 * nrm; cs[k] = c1 * nrm;
+      ikr nn = 1.5 - 0.5 * (s1 * s1 + c1 * c1);
+      sn[k] = s1 * nn; cs[k] = c1 * nn;
       q[k] = qn;
     }
   }
-  for (int k = 0; k < 7; k++) {
+  if (active) for (int k = 0; k < 7; k++) {
     s.jt_q[k] = (real)q[k];
     s.jt_qlo[k] = (real)(q[k] - (double)s.jt_q[k]);
     s.jt_qd[k] = (real)((q[k] - s.q[k]) / (ikr)C[D3C_DT]);

@@ -61,7 +61,7 @@ k_env(DevCtx c, int n_single, int n_ticks, int gym, int flag_base, const float* 
     PHASE_T0();
     if (cx.lane == 0) {              // one lane per group waits for the k_ik block that owns its env
       const int want = flag_base + t + 1;
-      while (*(volatile int*)(c.ik_flags + e / IK_THREADS) < want) __nanosleep(100);
+      while (*(volatile int*)(c.ik_flags + e / IK_FLAG_ENVS) < want) __nanosleep(100);
       __threadfence();
     }
     PHASE(16);

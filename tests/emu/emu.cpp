@@ -9,7 +9,7 @@
 #include "../../d3il_b200/csrc/d3il_model.h"
 
 struct Emu {
-  Model m; Lay L; IkState ik; double V[36], sn[7], cs[7]; int vwarm;
+  Model m; Lay L; IkState ik; double V[42], sn[7], cs[7]; int vwarm;
   std::vector<real> w;
   real tol; int max_iter;
 };
@@ -37,7 +37,9 @@ static void tick(Emu* e) {
   real* w = e->w.data();
   if (w[e->L.misc + ST_CTRL_MODE] == 1) {
     if (!e->ik.valid) { for (int k = 0; k < 7; k++) e->ik.q[k] = (double)w[e->L.qpos + k] + (double)w[e->L.qlo + k]; e->ik.valid = 1; }
-    ik_tick(e->m.ctrl, e->ik, e->V, &e->vwarm, e->sn, e->cs);
+    double J[42], Cd[D3_CTRL_W], coop[160];
+    for (int k = 0; k < D3_CTRL_W; k++) Cd[k] = (double)e->m.ctrl[k];
+    ik_tick<1>(CX, Cd, e->ik, 1, e->V, &e->vwarm, e->sn, e->cs, J, coop);
   }
   if (e->m.maxdim == 4) physics_tick<1, false, 4>(CX, e->m, e->L, w, e->ik.jt_q, e->ik.jt_qlo, e->ik.jt_qd, e->tol, e->max_iter);
   else physics_tick<1, false, 3>(CX, e->m, e->L, w, e->ik.jt_q, e->ik.jt_qlo, e->ik.jt_qd, e->tol, e->max_iter);
@@ -98,4 +100,15 @@ extern "C" int emu_collide_boxes(const double* pA, const double* hA, const doubl
   int n = use_fast ? collide_slab_box(pa, ha, pb, RB, hb, sqrt(hb[0] * hb[0] + hb[1] * hb[1] + hb[2] * hb[2]), 0, rc) : collide_box_box(pa, RA, ha, pb, RB, hb, 0, rc);
   for (int i = 0; i < n; i++) { for (int k = 0; k < 3; k++) { out[7 * i + k] = rc[i].pos[k]; out[7 * i + 3 + k] = rc[i].n[k]; } out[7 * i + 6] = rc[i].dist; }
   return n;
+}
+
+// stand-alone probe of the IK's clipped-spectrum solve: method 0 = ik_solve_spd (Cholesky / one-eigenvalue deflation), 1 = Jacobi
+// lanes path.  Returns 1 if the method produced x.
+extern "C" int emu_ik_clipped_solve(const double* J42, const double* rhs, double reg, double lo, double hi, int method, double* x) {
+  if (method == 0) { double v1[6]; int ok = 0; return ik_solve_spd(J42, reg, rhs, lo, hi, x, v1, &ok); }
+  double A[36], V[36], B1[36], B2[36], cs[8], r[6];
+  for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) { double sum = i == j ? reg : 0; for (int k = 0; k < 7; k++) sum += J42[i * 7 + k] * J42[j * 7 + k]; A[i * 6 + j] = sum; }
+  for (int k = 0; k < 6; k++) r[k] = rhs[k];
+  ik_solve_clipped_lanes<1>(CX, A, r, V, B1, B2, cs, 0, lo, hi, x);
+  return 1;
 }

@@ -131,3 +131,40 @@ def test_ik_fast_path_and_clipped_spectrum_fallback():
             break
     lam_min = np.array(lam_min)
     assert lam_min[0] > 1e-2 and lam_min.min() < 5e-3, (lam_min[0], lam_min.min())     # both regimes were visited
+
+
+def test_ik_clipped_solve_known_answers():
+    """The three routes of the IK's clipped-spectrum solve (Cholesky when nothing is clipped, one-eigenvalue deflation by
+    inverse iteration, Jacobi eigen-decomposition) against numpy's restatement of IKControllers.py:239-262
+    (np.linalg.svd of J J^T + reg I, singular values clipped to [1e-2, 1e2])."""
+    L = lib("f64")
+    dp = C.POINTER(C.c_double)
+    L.emu_ik_clipped_solve.argtypes = [dp, dp, C.c_double, C.c_double, C.c_double, C.c_int, dp]
+    L.emu_ik_clipped_solve.restype = C.c_int
+    d = lambda a: np.ascontiguousarray(a, dtype=np.float64).ctypes.data_as(dp)   # noqa: E731
+    rng = np.random.default_rng(5)
+    lo, hi, reg = 1e-2, 1e2, 1e-12
+    seen = {0: 0, 1: 0, 2: 0}
+    for trial in range(600):
+        U, _ = np.linalg.qr(rng.normal(size=(6, 6)))
+        W, _ = np.linalg.qr(rng.normal(size=(7, 7)))
+        sv = np.sqrt(rng.uniform(0.02, 4.0, 6))
+        kind = trial % 3                       # 0: all inside the clip range, 1: one eigenvalue below, 2: two below
+        if kind >= 1:
+            sv[0] = np.sqrt(10 ** rng.uniform(-4, -2.05))
+        if kind == 2:
+            sv[1] = np.sqrt(10 ** rng.uniform(-4, -2.05))
+        J = (U * sv) @ W[:6]
+        rhs = rng.normal(size=6)
+        A = J @ J.T + reg * np.eye(6)
+        u, s, vt = np.linalg.svd(A)
+        want = (u * (1.0 / np.clip(s, lo, hi))) @ (vt @ rhs)
+        x0, x1 = np.zeros(6), np.zeros(6)
+        ok0 = L.emu_ik_clipped_solve(d(J), d(rhs), reg, lo, hi, 0, d(x0))
+        assert L.emu_ik_clipped_solve(d(J), d(rhs), reg, lo, hi, 1, d(x1)) == 1
+        assert np.allclose(x1, want, rtol=1e-9, atol=1e-9 * np.abs(want).max()), (trial, kind)
+        assert bool(ok0) == (kind < 2), (trial, kind)          # two small eigenvalues are left to the eigen-decomposition
+        if ok0:
+            assert np.allclose(x0, want, rtol=1e-10, atol=1e-10 * np.abs(want).max()), (trial, kind)
+        seen[kind] += 1
+    assert min(seen.values()) >= 190
