@@ -280,6 +280,8 @@ def run_gpu(args):
     K, W = args.steps, max(args.warmup, 3)
 
     env = BatchedEnv(task, n, local)
+    if args.max_iter:
+        env.set_solver(1e-6, args.max_iter)
     ctxs = load_contexts(wl["ctx"]) if wl["ctx"] else None
     ctx_ids = (np.arange(n) + rank * n) % (len(ctxs) if ctxs is not None else 1)
     ctx_t = torch.tensor(ctxs[ctx_ids], dtype=torch.float32, device=dev) if ctxs is not None else None
@@ -476,6 +478,7 @@ def main():
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the workload's BASELINE.json size)")
     ap.add_argument("--workload", default="pushing", choices=sorted(WORKLOADS) + ["mixed7"], help="default = the configuration the metric is quoted on")
     ap.add_argument("--no-preroll", action="store_true", help="skip the 400-step episode-phase pre-roll (debug)")
+    ap.add_argument("--max-iter", type=int, default=0, help="override the Newton iteration cap (diagnostics; default: the library's)")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.workload == "mixed7":

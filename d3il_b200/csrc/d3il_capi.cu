@@ -89,7 +89,8 @@ __global__ void __launch_bounds__(IK_THREADS) k_ik(DevCtx c, const float* __rest
   extern __shared__ __align__(16) double ik_smem[];      // IK_SMEM_BYTES: controller table (as doubles), Jacobians J[k][thread], per-warp cooperative scratch
   double* sctrl = ik_smem;
   double* sJ = sctrl + D3_CTRL_W;
-  double* coop_all = sJ + 42 * IK_THREADS;
+  double* sA = sJ + 42 * IK_THREADS;
+  double* coop_all = sA + 27 * IK_THREADS;
   double* coop = coop_all + 160 * (threadIdx.x / 32);
   Cx cx; cx.lane = threadIdx.x & 31; cx.mask = 0xffffffffu; cx.cta_threads = IK_THREADS;
   for (int i = threadIdx.x; i < D3_CTRL_W; i += blockDim.x) sctrl[i] = (double)c.model->ctrl[i];
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(IK_THREADS) k_ik(DevCtx c, const float* __rest
   }
   double V[42], sn[7], cs[7]; int vwarm = 0;   // eigenbasis and joint sines/cosines carried across the IK iterations of this launch
   for (int t = 0; t < n_ticks; t++) {
-    ik_tick<32>(cx, sctrl, s, cart, V, &vwarm, sn, cs, sJ + threadIdx.x, coop);
+    ik_tick<32>(cx, sctrl, s, cart && live, V, &vwarm, sn, cs, sJ + threadIdx.x, sA + threadIdx.x, coop);
     if (live) {
       float* tr = c.traj + (size_t)t * 21 * n + e;
       for (int k = 0; k < 7; k++) { tr[k * n] = s.jt_q[k]; tr[(7 + k) * n] = s.jt_qlo[k]; tr[(14 + k) * n] = s.jt_qd[k]; }
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(IK_THREADS) k_ik(DevCtx c, const float* __rest
   TL_END(1);
 }
 
-#define IK_SMEM_BYTES ((int)sizeof(double) * (D3_CTRL_W + 42 * IK_THREADS + 160 * (IK_THREADS / 32)))
+#define IK_SMEM_BYTES ((int)sizeof(double) * (D3_CTRL_W + (42 + 27) * IK_THREADS + 160 * (IK_THREADS / 32)))
 
 // ------------------------------------------------------------------------------------------------ C ABI
 static int create_impl(d3il_env* h, const void* blob, size_t nbytes, int n_envs, int device);
@@ -175,7 +176,7 @@ static int create_impl(d3il_env* h, const void* blob, size_t nbytes, int n_envs,
   CK(cudaSetDevice(device));
   DevCtx& d = h->d;
   d.lay = h->L; d.n = n_envs; d.row = (h->L.n_state + 31) & ~31; d.ws_stride = (h->L.total + 31) & ~31;
-  d.tol = 1e-6f; d.max_iter = 12;
+  d.tol = 1e-6f; d.max_iter = 24;      // cap never reached on the benchmark workloads (status bit 8 reports it if it is); 12 was hit by 0.4 % of the env steps
   Model* dm = nullptr;
   CK(cudaMalloc(&dm, sizeof(Model)));
   CK(cudaMemcpy(dm, &h->m, sizeof(Model), cudaMemcpyHostToDevice));

@@ -35,6 +35,7 @@ struct Cx { int lane; unsigned mask; int cta_threads; };   // cta_threads: threa
 template <int G> DEVFN void gsync(const Cx&) {}
 template <int G> DEVFN real gsum(const Cx&, real x) { return x; }
 template <int G> DEVFN real gmaxr(const Cx&, real x) { return x; }
+template <int G> DEVFN void gsum2(const Cx&, real&, real&) {}
 template <int G> DEVFN int gsumi(const Cx&, int x) { return x; }
 template <int G> DEVFN int gori(const Cx&, int x) { return x; }
 template <int G> DEVFN double gsumd(const Cx&, double x) { return x; }
@@ -49,6 +50,11 @@ template <int G> DEVFN real gsum(const Cx& cx, real x) {
 #pragma unroll
   for (int o = G / 2; o > 0; o >>= 1) x += __shfl_xor_sync(cx.mask, x, o, G);
   return x;
+}
+// two all-reduces in one butterfly: the shuffles of the two values interleave, half the latency of two gsum calls
+template <int G> DEVFN void gsum2(const Cx& cx, real& x, real& y) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) { const real a = __shfl_xor_sync(cx.mask, x, o, G), b = __shfl_xor_sync(cx.mask, y, o, G); x += a; y += b; }
 }
 template <int G> DEVFN real gmaxr(const Cx& cx, real x) {
 #pragma unroll
@@ -80,6 +86,9 @@ template <int G> DEVFN double gsumd(const Cx& cx, double x) {
 #define D3_MAXPAIR 88
 
 #define LANES(i, n) for (int i = cx.lane; i < (n); i += G)
+#ifndef D3IL_LS_TOL
+#define D3IL_LS_TOL 1e-3   // exact line search: |phi'(alpha)| <= tol |phi'(0)|  (MuJoCo's ls_tolerance default is 1e-2; the solution does not depend on it)
+#endif
 
 // The env-step kernel is instruction-fetch bound (tens of KB of straight-line code per phase, one env per group):
 // CTA-wide barriers at fixed phase boundaries keep every warp of the CTA inside the same code region, so one
@@ -105,6 +114,7 @@ template <bool CS> DEVFN void cta_sync(const Cx& cx) {
 #if defined(D3IL_PHASE_TIMING) && !defined(D3IL_EMU)
 // debug build only: per-phase cycle counts of the group that owns env 0 (profiles/phase_timing.py)
 static __device__ unsigned long long g_phase_cycles[24];
+static __device__ unsigned g_cta_stat[4 * 4096];            // per CTA: [0] CTA-uniform Newton passes, [1] of which warp 0's env was coupled, [2] Newton steps of warp 0's env, [3] line-search evaluations of warp 0
 static __device__ unsigned long long g_iter_hist[40];      // [0..15] Newton steps per tick, [16..31] same for ticks with a coupling contact, [32] sum ncon / [33] count of ticks with >= 8 steps
 #endif
 #if defined(D3IL_PHASE_TIMING) && defined(__CUDA_ARCH__)
@@ -175,6 +185,7 @@ struct Model {
   unsigned char p_cpl[D3_MAXPAIR];        // pair joins two different kinematic-tree blocks
   unsigned char g_slab[32];               // geom is a static, axis-aligned box (table top, support): eligible for the slab fast path
   int nblk, blk_s[8], blk_e[8];           // the kinematic-tree blocks as a list
+  unsigned char d_blk[D3_MAXV];           // block index of each dof
   unsigned diag_blk;                      // bit b: block b of M is diagonal (free body, CoM at its origin, principal axes = body axes)
   int nzp; unsigned char zp_a[8], zp_b[8]; // in-block dof pairs that CRBA never writes (the two fingers): must read as zero
   unsigned char tri_i[300], tri_j[300];   // row-major lower-triangle unranking table for n <= 24
@@ -202,6 +213,7 @@ struct Lay {
   int n_state;
   // scratch
   int xpos, xmat, S, I10, Ic, vel, cj, frc, F, M, mdinv, mpiv, H, hdinv, hpiv, bias, qfrc_smooth, qacc_smooth, qacc, qfrc_c, grad, pvec, Ma, tmpv;
+  int wood;           // Woodbury scratch: maxdim dof vectors (view 2)
   int act, jt, con, ncon_pair, limflag, cflag, J, aref, D, jar, frcE, Jp, hd, hb, etype, econ, total;
 };
 enum { ST_GRIP_SET = 0, ST_GRASP, ST_CTRL_MODE, ST_STEP, ST_TERM, ST_STATUS, ST_OBST, ST_TASK0, ST_TASK1, ST_TASK2, ST_TASK3, ST_COST_ITERS /* Newton iterations of the last env step */, ST_COST_COUPLED /* ticks with a tree-coupling contact */, ST_COST_NCON /* max contacts */, ST_NMISC = 16 };
@@ -231,6 +243,8 @@ static inline void d3il_layout(const Model& m, Lay& L) {
   o = x0;
   L.H = take(m.nv * m.nv); L.hdinv = take(m.nv); L.hpiv = take(m.nv); L.jar = take(m.maxrow); L.frcE = take(m.maxrow); L.Jp = take(m.maxrow);
   L.hb = take(m.maxdim * m.maxdim * m.maxcon); L.grad = take(m.nv); L.pvec = take(m.nv); L.Ma = take(m.nv); L.tmpv = take(m.nv);
+  // Woodbury scratch (maxdim dof vectors): dead before the line search writes Jp, so it shares Jp's storage when it fits
+  L.wood = m.maxrow >= m.maxdim * m.nv ? L.Jp : take(m.maxdim * m.nv);
   if (x1 > o) o = x1;
   L.etype = 0;
   L.total = o;
@@ -1122,6 +1136,122 @@ DEVNI void chol_solve_slots(const Cx& cx, const Model& m, const real* A, int n, 
   gsync<G>(cx);
 }
 
+// ---- register-resident block Cholesky ------------------------------------------------------------------------------
+// The matrices this path factors are block diagonal over the kinematic trees with blocks of at most D3_MAXB rows (the arm:
+// 7 joints + 2 fingers; a free body: 6).  Row i of its block lives in the registers of lane i % G (slot i / G): the whole
+// right-looking factorisation is shuffles + FMAs on registers, fully unrolled over the D3_MAXB column steps, all blocks
+// advancing together — no shared-memory traffic and no barriers inside (the shared-memory version spent two barriers and
+// several strided passes per column).  The factor goes back to the strict lower triangle of A (the triangular solves read
+// it from there) and 1 / L_kk to dinv.
+#define D3_MAXB 9
+// value `v[slot]` of the lane/slot that owns row `src_row` (every lane may ask for a different row)
+template <int G, int NS>
+DEVFN real row_bcast(const Cx& cx, const real* v, int src_row) {
+#ifdef D3IL_EMU
+  return v[src_row];
+#else
+  if (NS == 1) return __shfl_sync(cx.mask, v[0], src_row, G);
+  real out = 0;
+#pragma unroll
+  for (int sl = 0; sl < NS; sl++) { const real t = __shfl_sync(cx.mask, v[sl], src_row % G, G); if (sl == src_row / G) out = t; }
+  return out;
+#endif
+}
+// upper = true : the input block rows are read from the UPPER triangle (A[j][i], j < i) — the mass matrix as CRBA leaves it;
+// upper = false: from the lower triangle (the assembled Hessian).  diag[] holds the diagonal, diag_add (nullable) is added to it.
+template <int G, int NS> DEVFN int chol_reg_core(const Cx& cx, real (*a)[D3_MAXB], const int* bs, const int* be, const int* rr, real* myinv);
+template <int G, int NS>
+DEVNI int chol_blocks_reg_slots(const Cx& cx, const Model& m, real* A, int n, bool upper, const real* diag, const real* diag_add, real* dinv) {
+  real a[NS][D3_MAXB], myinv[NS];
+  int bs[NS], rr[NS], be[NS];
+#pragma unroll
+  for (int sl = 0; sl < NS; sl++) {
+    const int i = sl * G + cx.lane, ii = i < n ? i : n - 1;
+    bs[sl] = m.d_bs[ii]; be[sl] = m.d_be[ii]; rr[sl] = i < n ? i - bs[sl] : -1;      // rr < 0: no row in this slot
+#pragma unroll
+    for (int j = 0; j < D3_MAXB; j++) {
+      real v = 0;
+      if (j < rr[sl]) v = upper ? A[(bs[sl] + j) * n + i] : A[i * n + bs[sl] + j];
+      else if (j == rr[sl]) v = diag[i] + (diag_add ? diag_add[i] : (real)0);
+      a[sl][j] = v;
+    }
+    myinv[sl] = 1;
+  }
+  const int bad = chol_reg_core<G, NS>(cx, a, bs, be, rr, myinv);
+#pragma unroll
+  for (int sl = 0; sl < NS; sl++) {
+    const int i = sl * G + cx.lane;
+    if (rr[sl] < 0) continue;
+#pragma unroll
+    for (int j = 0; j < D3_MAXB; j++) if (j < rr[sl]) A[i * n + bs[sl] + j] = a[sl][j];
+    dinv[i] = myinv[sl];
+  }
+  gsync<G>(cx);
+  return gori<G>(cx, bad);
+}
+template <int G>
+DEVFN int chol_blocks_reg(const Cx& cx, const Model& m, real* A, int n, bool upper, const real* diag, const real* diag_add, real* dinv) {
+#ifdef D3IL_EMU
+  return chol_blocks_reg_slots<G, D3_SLOTS(G)>(cx, m, A, n, upper, diag, diag_add, dinv);
+#else
+  if (n <= G) return chol_blocks_reg_slots<G, 1>(cx, m, A, n, upper, diag, diag_add, dinv);
+  return chol_blocks_reg_slots<G, D3_SLOTS(G)>(cx, m, A, n, upper, diag, diag_add, dinv);
+#endif
+}
+
+// Block solve L L^T x = b for the same factor: the lane's row of L (forward sweep) and column of L (backward sweep) are
+// loaded into registers up front, x is register-distributed, every step is one shuffle + one FMA.
+template <int G, int NS>
+DEVNI void chol_blocks_solve_slots(const Cx& cx, const Model& m, const real* A, int n, const real* dinv, real* x) {
+  real lrow[NS][D3_MAXB], lcol[NS][D3_MAXB], xr[NS], di[NS], mine[NS];
+  int bs[NS], rr[NS], be[NS];
+#pragma unroll
+  for (int sl = 0; sl < NS; sl++) {
+    const int i = sl * G + cx.lane, ii = i < n ? i : n - 1;
+    bs[sl] = m.d_bs[ii]; be[sl] = m.d_be[ii]; rr[sl] = i < n ? i - bs[sl] : -1;
+    xr[sl] = i < n ? x[i] : (real)0; di[sl] = dinv[ii];
+#pragma unroll
+    for (int j = 0; j < D3_MAXB; j++) {
+      lrow[sl][j] = j < rr[sl] ? A[i * n + bs[sl] + j] : (real)0;
+      lcol[sl][j] = (rr[sl] >= 0 && j > rr[sl] && bs[sl] + j < be[sl]) ? A[(bs[sl] + j) * n + i] : (real)0;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < D3_MAXB; k++) {
+#pragma unroll
+    for (int sl = 0; sl < NS; sl++) mine[sl] = xr[sl] * di[sl];
+#pragma unroll
+    for (int sl = 0; sl < NS; sl++) {
+      const int src = bs[sl] + k < be[sl] ? bs[sl] + k : bs[sl];
+      const real xk = row_bcast<G, NS>(cx, mine, src);
+      if (rr[sl] == k) xr[sl] = mine[sl]; else if (rr[sl] > k) xr[sl] -= lrow[sl][k] * xk;
+    }
+  }
+#pragma unroll
+  for (int k = D3_MAXB - 1; k >= 0; k--) {
+#pragma unroll
+    for (int sl = 0; sl < NS; sl++) mine[sl] = xr[sl] * di[sl];
+#pragma unroll
+    for (int sl = 0; sl < NS; sl++) {
+      const int src = bs[sl] + k < be[sl] ? bs[sl] + k : bs[sl];
+      const real xk = row_bcast<G, NS>(cx, mine, src);
+      if (rr[sl] == k) xr[sl] = mine[sl]; else if (rr[sl] >= 0 && rr[sl] < k) xr[sl] -= lcol[sl][k] * xk;      // lcol is zero past the block's end
+    }
+  }
+#pragma unroll
+  for (int sl = 0; sl < NS; sl++) { const int i = sl * G + cx.lane; if (i < n) x[i] = xr[sl]; }
+  gsync<G>(cx);
+}
+template <int G>
+DEVFN void chol_blocks_solve(const Cx& cx, const Model& m, const real* A, int n, const real* dinv, real* x) {
+#ifdef D3IL_EMU
+  chol_blocks_solve_slots<G, D3_SLOTS(G)>(cx, m, A, n, dinv, x);
+#else
+  if (n <= G) chol_blocks_solve_slots<G, 1>(cx, m, A, n, dinv, x);
+  else chol_blocks_solve_slots<G, D3_SLOTS(G)>(cx, m, A, n, dinv, x);
+#endif
+}
+
 // NS = register slots per lane for the distributed vector: one when the system fits the group (n <= G)
 template <int G>
 DEVFN void chol_solve_part(const Cx& cx, const Model& m, const real* A, int n, bool whole, int maxsz, const real* dinv, real* x) {
@@ -1143,9 +1273,155 @@ DEVFN real mrow_dot(const Model& m, const real* M, int nv, int d, const real* v,
   return s;
 }
 
+// Number of active contacts that couple two kinematic trees (all lanes); *cplc = index of the last one (exact when the
+// count is 1, the only case that uses it).
+template <int G>
+DEVFN int count_coupling(const Cx& cx, const Model& m, const Lay& L, const real* w, int ncon, int* cplc) {
+  int nc = 0, last = -1;
+  LANES(c, ncon) { const real* cc = w + L.con + D3_CON_W * c; if ((int)cc[19] >= 0 && (int)cc[23] > (int)cc[22]) { nc++; last = c; } }
+  nc = gsumi<G>(cx, nc);
+  int lm = last + 1; lm = gori<G>(cx, lm);
+  *cplc = lm - 1;
+  return nc;
+}
+
+// core of the register factorisation (shared by chol_blocks_reg_slots and the Newton direction): rows in a[][], in place
+template <int G, int NS>
+DEVFN int chol_reg_core(const Cx& cx, real (*a)[D3_MAXB], const int* bs, const int* be, const int* rr, real* myinv) {
+  real colk[NS];
+  int bad = 0;
+#pragma unroll
+  for (int k = 0; k < D3_MAXB; k++) {
+#pragma unroll
+    for (int sl = 0; sl < NS; sl++) if (rr[sl] == k) {
+      real p = a[sl][k];
+      if (!(p > 0)) { bad = 1; p = 1; }
+      myinv[sl] = 1 / sqrt(p);
+    }
+#pragma unroll
+    for (int sl = 0; sl < NS; sl++) {
+      const int src = bs[sl] + k < be[sl] ? bs[sl] + k : bs[sl];
+      const real inv = row_bcast<G, NS>(cx, myinv, src);
+      if (rr[sl] > k) a[sl][k] *= inv;
+      colk[sl] = a[sl][k];
+    }
+#pragma unroll
+    for (int j = k + 1; j < D3_MAXB; j++) {
+#pragma unroll
+      for (int sl = 0; sl < NS; sl++) {
+        const int src = bs[sl] + j < be[sl] ? bs[sl] + j : bs[sl];
+        const real ljk = row_bcast<G, NS>(cx, colk, src);
+        if (rr[sl] >= j) a[sl][j] -= a[sl][k] * ljk;
+      }
+    }
+  }
+  return bad;
+}
+
+// One contact that couples two trees (the rod pushing a box — the slow envs of every batch) makes H = H_blocks + Jc^T B Jc
+// a rank-3 (rank-4 with torsional friction) update of the block-diagonal Hessian, so by the Woodbury identity
+//     p = y0 - W (I + B S)^-1 B (Jc y0),   y0 = -H_blocks^-1 grad,  W = H_blocks^-1 Jc^T,  S = Jc W :
+// dim more block solves and a dim x dim system every lane solves redundantly, instead of a dense nv x nv factorisation in
+// shared memory.  Two or more coupling contacts take the dense path (solve_constraints).
+// Woodbury correction of the block direction for the single coupling contact `cplc`.  In: pvec =
+// y0 = -H_blocks^-1 grad.  Out: pvec = -H^-1 grad.  wood: MD dof vectors of scratch.
+template <int G, int MD>
+DEVNI void newton_woodbury(const Cx& cx, const Model& m, const Lay& L, real* w, int cplc) {
+  const int nv = m.nv;
+  const real* J = w + L.J;
+  const real* cc = w + L.con + D3_CON_W * cplc;
+  const int cdim = MD == 3 ? 3 : (int)cc[15];
+  const int r0 = (int)cc[19], a0 = (int)cc[20], a1 = (int)cc[21], b0 = (int)cc[22], b1 = (int)cc[23];
+  real* W = w + L.wood;
+  // W_p = H_blocks^-1 Jc_p^T
+  for (int p = 0; p < cdim; p++) {
+    LANES(i, nv) {
+      real v = 0;
+      if (i >= a0 && i < a1) v = J[(r0 + p) * D3_JW + (i - a0)];
+      else if (i >= b0 && i < b1) v = J[(r0 + p) * D3_JW + (a1 - a0) + (i - b0)];
+      W[p * nv + i] = v;
+    }
+  }
+  gsync<G>(cx);
+  for (int p = 0; p < cdim; p++) chol_blocks_solve<G>(cx, m, w + L.H, nv, w + L.hdinv, W + p * nv);
+  // S = Jc W (symmetric), t = Jc y0
+  real S[MD][MD], t[MD], z[MD];
+#pragma unroll
+  for (int p = 0; p < MD; p++) {
+    t[p] = 0;
+#pragma unroll
+    for (int q = 0; q < MD; q++) S[p][q] = 0;
+  }
+#pragma unroll
+  for (int p = 0; p < MD; p++) {
+    if (p >= cdim) continue;
+    const real* Jr = J + (r0 + p) * D3_JW;
+    real pt = 0, ps[MD];
+#pragma unroll
+    for (int q = 0; q < MD; q++) ps[q] = 0;
+    LANES(i, nv) {
+      real jv = 0;
+      if (i >= a0 && i < a1) jv = Jr[i - a0]; else if (i >= b0 && i < b1) jv = Jr[(a1 - a0) + (i - b0)];
+      pt += jv * w[L.pvec + i];
+#pragma unroll
+      for (int q = 0; q < MD; q++) if (q >= p && q < cdim) ps[q] += jv * W[q * nv + i];
+    }
+    t[p] = gsum<G>(cx, pt);
+#pragma unroll
+    for (int q = 0; q < MD; q++) if (q >= p && q < cdim) { S[p][q] = gsum<G>(cx, ps[q]); S[q][p] = S[p][q]; }
+  }
+  // C z = B t with C = I + B S (B: the contact's cone Hessian block; rows / columns >= cdim are zero -> z = 0 there)
+  const real* Bm = w + L.hb + MD * MD * cplc;
+  real Cm[MD][MD + 1];
+#pragma unroll
+  for (int p = 0; p < MD; p++) {
+    real bt = 0;
+#pragma unroll
+    for (int q = 0; q < MD; q++) {
+      real v = p == q ? (real)1 : (real)0;
+#pragma unroll
+      for (int k = 0; k < MD; k++) v += Bm[MD * p + k] * S[k][q];
+      Cm[p][q] = v; bt += Bm[MD * p + q] * t[q];
+    }
+    Cm[p][MD] = bt;
+  }
+  // Gaussian elimination with partial pivoting (C is not symmetric), unrolled on registers
+#pragma unroll
+  for (int k = 0; k < MD; k++) {
+#pragma unroll
+    for (int i2 = k + 1; i2 < MD; i2++) {
+      const bool sw = absr(Cm[i2][k]) > absr(Cm[k][k]);
+#pragma unroll
+      for (int q = 0; q <= MD; q++) { const real u = Cm[k][q], v = Cm[i2][q]; Cm[k][q] = sw ? v : u; Cm[i2][q] = sw ? u : v; }
+    }
+    const real inv = 1 / Cm[k][k];
+#pragma unroll
+    for (int i2 = k + 1; i2 < MD; i2++) {
+      const real f = Cm[i2][k] * inv;
+#pragma unroll
+      for (int q = k; q <= MD; q++) Cm[i2][q] -= f * Cm[k][q];
+    }
+  }
+#pragma unroll
+  for (int k = MD - 1; k >= 0; k--) {
+    real v = Cm[k][MD];
+#pragma unroll
+    for (int q = k + 1; q < MD; q++) v -= Cm[k][q] * z[q];
+    z[k] = v / Cm[k][k];
+  }
+  LANES(i, nv) {
+    real v = w[L.pvec + i];
+#pragma unroll
+    for (int p = 0; p < MD; p++) if (p < cdim) v -= W[p * nv + i] * z[p];
+    w[L.pvec + i] = v;
+  }
+  gsync<G>(cx);
+}
+
 // Newton solver on the primal problem: result in qacc / frcE / qfrc_c.  Returns iterations.
 template <int G, bool CS, int MD>
-DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w, int ne, int nlimit, int ncon, int coupled, real tol, int max_iter) {
+DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w, int ne, int nlimit, int ncon, int ncpl, int cplc, real tol, int max_iter) {
+  const int coupled = ncpl > 1;      // dense path: two or more contacts couple kinematic trees (one is handled as a low-rank update of the block path)
   const int nv = m.nv;
   // Envs without active rows take qacc = qacc_smooth but keep walking the (CTA-uniform) iteration loop below.
   int done = ne == 0;
@@ -1220,9 +1496,13 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
     }
     // all groups of the CTA iterate together (converged ones idle) so the Newton body stays fetch-shared
     if (!cta_any<CS>(cx, !done)) break;
+#if defined(D3IL_PHASE_TIMING) && defined(__CUDA_ARCH__)
+    if (threadIdx.x == 0 && blockIdx.x < 4096) { g_cta_stat[4 * blockIdx.x] += 1; if (coupled) g_cta_stat[4 * blockIdx.x + 1] += 1; if (!done) g_cta_stat[4 * blockIdx.x + 2] += 1; }
+#endif
     if (!done) {
     nsteps++;
-    // ---- H = M + J^T Hc J (lower triangle).  Block diagonal unless a contact couples two trees.
+    int hfail;
+    // ---- H = M + J^T Hc J (lower triangle).  Block diagonal unless contacts couple two trees.
     // (A) every in-block entry is owned by one lane, which accumulates M, the limit rows and all contacts that live
     //     inside that block in a register and writes H once: no barriers between contacts.
     if (coupled) { LANES(e, nv * nv) w[L.H + e] = 0; gsync<G>(cx); }
@@ -1255,8 +1535,20 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
       }
     }
     gsync<G>(cx);
+    if (!coupled) {
+      // block path: factorisation in registers, block solve; a single coupling contact is a low-rank (Woodbury) update
+      PHASE(9);
+      LANES(d, nv) { w[L.hpiv + d] = w[L.H + d * nv + d]; w[L.pvec + d] = -w[L.grad + d]; }
+      gsync<G>(cx);
+      hfail = chol_blocks_reg<G>(cx, m, w + L.H, nv, false, w + L.hpiv, nullptr, w + L.hdinv);
+      PHASE(10);
+      if (!hfail) {
+        chol_blocks_solve<G>(cx, m, w + L.H, nv, w + L.hdinv, w + L.pvec);
+        if (ncpl == 1) newton_woodbury<G, MD>(cx, m, L, w, cplc);
+      }
+    } else {
     // (B) contacts that couple two blocks (rod-box, box-box): rare, added one after the other
-    if (coupled) for (int c = 0; c < ncon; c++) {
+    for (int c = 0; c < ncon; c++) {
       const real* cc = w + L.con + D3_CON_W * c;
       int r0 = (int)cc[19];
       if (r0 < 0 || (int)cc[23] == (int)cc[22]) continue;
@@ -1283,15 +1575,15 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
     PHASE(9);
     LANES(d, nv) { w[L.hpiv + d] = w[L.H + d * nv + d]; w[L.pvec + d] = -w[L.grad + d]; }
     gsync<G>(cx);
-    int maxsz = coupled ? nv : m.maxblk;
     // A Hessian that is not positive definite (NaN inputs included) ends this env's solve with status bit 4.  The env must
     // NOT leave the loop on its own: the iteration is CTA-uniform (cta_any above is a barrier every warp of the CTA has to
     // reach), so it turns `done` and idles through the remaining passes like a converged env.
-    const int hfail = chol_factor_part<G>(cx, m, w + L.H, nv, coupled != 0, maxsz, w + L.hpiv, w + L.hdinv);
-    if (hfail) { LANES(z, 1) w[L.misc + ST_STATUS] = (real)(((int)w[L.misc + ST_STATUS]) | D3_STATUS_H_NOT_PD); done = 1; gsync<G>(cx); }
+    hfail = chol_factor_part<G>(cx, m, w + L.H, nv, true, nv, w + L.hpiv, w + L.hdinv);
     PHASE(10);
+    if (!hfail) chol_solve_part<G>(cx, m, w + L.H, nv, true, nv, w + L.hdinv, w + L.pvec);
+    }
+    if (hfail) { LANES(z, 1) w[L.misc + ST_STATUS] = (real)(((int)w[L.misc + ST_STATUS]) | D3_STATUS_H_NOT_PD); done = 1; gsync<G>(cx); }
     if (!hfail) {
-    chol_solve_part<G>(cx, m, w + L.H, nv, coupled != 0, maxsz, w + L.hdinv, w + L.pvec);
     PHASE(11);
     // ---- exact line search (safeguarded 1-D Newton / false position), quantities reduced across lanes
     eval_jar<G>(cx, m, L, w, nlimit, ncon, L.pvec, L.Jp, false);
@@ -1301,7 +1593,8 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
       w[L.tmpv + d] = s;                                             // M p (tmpv is free until the Euler stage)
       a1s += w[L.pvec + d] * s; a2s += w[L.pvec + d] * w[L.Ma + d]; a3s += w[L.grad + d] * w[L.pvec + d];
     }
-    real pMp = gsum<G>(cx, a1s), pMa = gsum<G>(cx, a2s), d0 = gsum<G>(cx, a3s);
+    gsum2<G>(cx, a1s, a2s);
+    real pMp = a1s, pMa = a2s, d0 = gsum<G>(cx, a3s);
     real lo = 0, hi = -1, alpha = 1, dlo = d0, dhi = 0;
     for (int ls = 0; ls < 20; ls++) {
       // first and second directional derivatives at jar + alpha Jp (nothing is written: no barrier needed)
@@ -1337,8 +1630,12 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
           d2p += Dm * (dn * dn - NmT * mu * d2T);
         }
       }
-      real d1 = gsum<G>(cx, d1p) + pMa + alpha * pMp, d2 = gsum<G>(cx, d2p) + pMp;
-      if (absr(d1) <= (real)1e-3 * absr(d0)) break;
+      gsum2<G>(cx, d1p, d2p);
+      real d1 = d1p + pMa + alpha * pMp, d2 = d2p + pMp;
+#if defined(D3IL_PHASE_TIMING) && defined(__CUDA_ARCH__)
+      if (threadIdx.x == 0 && blockIdx.x < 4096) g_cta_stat[4 * blockIdx.x + 3] += 1;
+#endif
+      if (absr(d1) <= (real)D3IL_LS_TOL * absr(d0)) break;
       if (d1 < 0) { lo = alpha; dlo = d1; } else { hi = alpha; dhi = d1; }
       real next = alpha - d1 / d2;
       if (hi < 0) { if (!(next > lo)) next = 2 * alpha; }
@@ -1437,6 +1734,8 @@ DEVFN void physics_tick(const Cx& cx, const Model& m, const Lay& L, real* w, con
   cta_sync<CS>(cx);
   int nlimit = 0, coupled = 0;
   int ne = make_constraints<G, MD>(cx, m, L, w, ncon, &nlimit, &coupled);
+  int cplc = -1;
+  const int ncpl = count_coupling<G>(cx, m, L, w, ncon, &cplc);
   PHASE(3);
 #ifdef D3IL_PHASE_TIMING
   if (cx.lane == 0) { count_stat(21, coupled); count_stat(22, ncon); count_stat(23, 1); count_stat(19, ne); }
@@ -1452,13 +1751,13 @@ DEVFN void physics_tick(const Cx& cx, const Model& m, const Lay& L, real* w, con
     w[L.qfrc_smooth + d] = f; w[L.qacc_smooth + d] = f;
     w[L.mpiv + d] = w[L.M + d * nv + d];
   }
-  LANES(e, m.nmpair) { int a = m.mp_a[e], b = m.mp_b[e]; if (a != b) w[L.M + a * nv + b] = w[L.M + b * nv + a]; }   // lower <- upper
   gsync<G>(cx);
-  if (chol_factor_part<G>(cx, m, w + L.M, nv, false, m.maxblk, w + L.mpiv, w + L.mdinv, m.diag_blk)) { LANES(z, 1) w[L.misc + ST_STATUS] = (real)(((int)w[L.misc + ST_STATUS]) | 1); }
-  chol_solve_part<G>(cx, m, w + L.M, nv, false, m.maxblk, w + L.mdinv, w + L.qacc_smooth);
+  // chol(M): rows come from the upper triangle (where CRBA wrote M), the factor goes to the strict lower triangle
+  if (chol_blocks_reg<G>(cx, m, w + L.M, nv, true, w + L.mpiv, nullptr, w + L.mdinv)) { LANES(z, 1) w[L.misc + ST_STATUS] = (real)(((int)w[L.misc + ST_STATUS]) | D3_STATUS_M_NOT_PD); }
+  chol_blocks_solve<G>(cx, m, w + L.M, nv, w + L.mdinv, w + L.qacc_smooth);
   PHASE(4);
   cta_sync<CS>(cx);
-  int iters = solve_constraints<G, CS, MD>(cx, m, L, w, ne, nlimit, ncon, coupled, tol, max_iter);
+  int iters = solve_constraints<G, CS, MD>(cx, m, L, w, ne, nlimit, ncon, ncpl, cplc, tol, max_iter);
 #if defined(D3IL_ITER_HIST) && defined(__CUDA_ARCH__)
   if (cx.lane == 0) {
     int b = iters > 15 ? 15 : iters;
@@ -1474,31 +1773,13 @@ DEVFN void physics_tick(const Cx& cx, const Model& m, const Lay& L, real* w, con
   cta_sync<CS>(cx);
   LANES(d, nv) { w[L.warm + d] = w[L.qacc + d]; w[L.tmpv + d] = w[L.qfrc_smooth + d] + w[L.qfrc_c + d]; }
   LANES(k, D3_NROB) w[L.bias_prev + k] = w[L.bias + k];
-  // --- mj_Euler with implicit joint damping: (M + h B) qacc* = qfrc_smooth + qfrc_constraint.  Only the trailing
-  //     `ndamp` dofs of the arm block are damped (the fingers), so the factor of M + hB differs from the factor of M
-  //     in its last ndamp rows only: rebuild that corner (serial, ndamp = 2) instead of refactorising.
-  LANES(z, 1) {
-    const int f0 = m.damp_first, f1 = m.damp_end;
-    real T[16];
-    for (int a = f0; a < f1; a++) for (int b = f0; b <= a; b++) {
-      real s = 0;
-      for (int k = f0; k <= b; k++) {
-        real la = k == a ? 1 / w[L.mdinv + a] : w[L.M + a * nv + k], lb = k == b ? 1 / w[L.mdinv + b] : w[L.M + b * nv + k];
-        s += la * lb;
-      }
-      if (a == b) s += h * (real)m.link[D3_LINK_W * m.d_link[a] + 25];
-      T[(a - f0) * 4 + (b - f0)] = s;
-    }
-    for (int a = f0; a < f1; a++) {
-      for (int b = f0; b <= a; b++) {
-        real s = T[(a - f0) * 4 + (b - f0)];
-        for (int k = f0; k < b; k++) s -= w[L.M + a * nv + k] * w[L.M + b * nv + k];
-        if (a == b) w[L.mdinv + a] = 1 / sqrt(s); else w[L.M + a * nv + b] = s * w[L.mdinv + b];
-      }
-    }
-  }
+  // --- mj_Euler with implicit joint damping: (M + h B) qacc* = qfrc_smooth + qfrc_constraint.  M (upper triangle) and its
+  //     diagonal (mpiv) are still intact: the blocks of M + h B are simply factored again in registers (the only damped dofs
+  //     are the two fingers, but a register factorisation of every block costs less than a special case for the corner).
+  LANES(d, nv) { int li = m.d_link[d]; w[L.hpiv + d] = m.l_jtype[li] == 2 ? (real)0 : h * (real)m.link[D3_LINK_W * li + 25]; }
   gsync<G>(cx);
-  chol_solve_part<G>(cx, m, w + L.M, nv, false, m.maxblk, w + L.mdinv, w + L.tmpv);
+  chol_blocks_reg<G>(cx, m, w + L.M, nv, true, w + L.mpiv, w + L.hpiv, w + L.mdinv);
+  chol_blocks_solve<G>(cx, m, w + L.M, nv, w + L.mdinv, w + L.tmpv);
   LANES(d, nv) w[L.qvel + d] += h * w[L.tmpv + d];
   gsync<G>(cx);
   LANES(i, m.nlink) {

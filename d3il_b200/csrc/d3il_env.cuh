@@ -63,7 +63,9 @@ DEVFN ikr ik_clamp(ikr x, ikr lo, ikr hi) { return x < lo ? lo : (x > hi ? hi : 
 // Forward kinematics + geometric Jacobian of the URDF chain (core/Model.py:37-66).  Everything is unrolled and
 // statically indexed so that the 42 Jacobian doubles live in registers (k_ik is one thread per env).
 DEVFN void ik_fk(const ikr* C, const ikr* sn, const ikr* cs, ikr* pos, ikr* quat, ikr* J) {
-  ikr p[3] = {0, 0, 0}, R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, org[7][3], axs[7][3];
+  // joint origins and axes go straight into J's storage (origin in the linear rows, axis in the angular rows) and the
+  // linear rows are converted in place once the tool position is known: no 42-double org / axs arrays in registers
+  ikr p[3] = {0, 0, 0}, R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
 #pragma unroll
   for (int i = 0; i < 7; i++) {
     const ikr* o = C + D3C_IK_ORIGIN + 12 * i;
@@ -80,8 +82,8 @@ DEVFN void ik_fk(const ikr* C, const ikr* sn, const ikr* cs, ikr* pos, ikr* quat
     }
 #pragma unroll
     for (int k = 0; k < 9; k++) R[k] = Rn[k];
-    org[i][0] = p[0]; org[i][1] = p[1]; org[i][2] = p[2];
-    axs[i][0] = R[2]; axs[i][1] = R[5]; axs[i][2] = R[8];
+    IKJ(J, i) = p[0]; IKJ(J, 7 + i) = p[1]; IKJ(J, 14 + i) = p[2];
+    IKJ(J, 21 + i) = R[2]; IKJ(J, 28 + i) = R[5]; IKJ(J, 35 + i) = R[8];
   }
   const ikr* o = C + D3C_IK_EE;
   ikr Re[9];
@@ -94,9 +96,9 @@ DEVFN void ik_fk(const ikr* C, const ikr* sn, const ikr* cs, ikr* pos, ikr* quat
   ik_mat2quat(quat, Re);
 #pragma unroll
   for (int i = 0; i < 7; i++) {
-    const ikr r0 = pos[0] - org[i][0], r1 = pos[1] - org[i][1], r2 = pos[2] - org[i][2];
-    IKJ(J, i) = axs[i][1] * r2 - axs[i][2] * r1; IKJ(J, 7 + i) = axs[i][2] * r0 - axs[i][0] * r2; IKJ(J, 14 + i) = axs[i][0] * r1 - axs[i][1] * r0;
-    IKJ(J, 21 + i) = axs[i][0]; IKJ(J, 28 + i) = axs[i][1]; IKJ(J, 35 + i) = axs[i][2];
+    const ikr r0 = pos[0] - IKJ(J, i), r1 = pos[1] - IKJ(J, 7 + i), r2 = pos[2] - IKJ(J, 14 + i);
+    const ikr a0 = IKJ(J, 21 + i), a1 = IKJ(J, 28 + i), a2 = IKJ(J, 35 + i);
+    IKJ(J, i) = a1 * r2 - a2 * r1; IKJ(J, 7 + i) = a2 * r0 - a0 * r2; IKJ(J, 14 + i) = a0 * r1 - a1 * r0;
   }
 }
 
@@ -117,24 +119,24 @@ DEVFN void ik_gram(const ikr* J, ikr diag_add, ikr* A21) {      // A = J J^T + d
       ikr s = i == j ? diag_add : (ikr)0;
 #pragma unroll
       for (int k = 0; k < 7; k++) s += IKJ(J, i * 7 + k) * IKJ(J, j * 7 + k);
-      A21[IK_TRI(i, j)] = s;
+      IKJ(A21, IK_TRI(i, j)) = s;
     }
 }
 DEVFN int ik_chol21(ikr* A21, ikr* dinv) {      // in place: A21 <- L (strict lower part), dinv <- 1 / L_jj; 0 if a pivot is not positive
 #pragma unroll
   for (int j = 0; j < 6; j++) {
-    ikr sd = A21[IK_TRI(j, j)];
+    ikr sd = IKJ(A21, IK_TRI(j, j));
 #pragma unroll
-    for (int k = 0; k < j; k++) sd -= A21[IK_TRI(j, k)] * A21[IK_TRI(j, k)];
+    for (int k = 0; k < j; k++) sd -= IKJ(A21, IK_TRI(j, k)) * IKJ(A21, IK_TRI(j, k));
     if (!(sd > 1e-14)) return 0;
     const ikr d = ik_rsqrt(sd);
-    dinv[j] = d;
+    IKJ(dinv, j) = d;
 #pragma unroll
     for (int i = j + 1; i < 6; i++) {
-      ikr so = A21[IK_TRI(i, j)];
+      ikr so = IKJ(A21, IK_TRI(i, j));
 #pragma unroll
-      for (int k = 0; k < j; k++) so -= A21[IK_TRI(i, k)] * A21[IK_TRI(j, k)];
-      A21[IK_TRI(i, j)] = so * d;
+      for (int k = 0; k < j; k++) so -= IKJ(A21, IK_TRI(i, k)) * IKJ(A21, IK_TRI(j, k));
+      IKJ(A21, IK_TRI(i, j)) = so * d;
     }
   }
   return 1;
@@ -146,18 +148,18 @@ DEVFN int ik_ldl_inertia(ikr* A21, int* nneg) {
   int neg = 0;
 #pragma unroll
   for (int j = 0; j < 6; j++) {
-    ikr sd = A21[IK_TRI(j, j)];
+    ikr sd = IKJ(A21, IK_TRI(j, j));
 #pragma unroll
-    for (int k = 0; k < j; k++) sd -= A21[IK_TRI(j, k)] * A21[IK_TRI(j, k)] * dd[k];
+    for (int k = 0; k < j; k++) sd -= IKJ(A21, IK_TRI(j, k)) * IKJ(A21, IK_TRI(j, k)) * dd[k];
     if (!(fabs(sd) > 1e-12)) return 0;
     dd[j] = sd; neg += sd < 0;
     const ikr inv = 1 / sd;
 #pragma unroll
     for (int i = j + 1; i < 6; i++) {
-      ikr so = A21[IK_TRI(i, j)];
+      ikr so = IKJ(A21, IK_TRI(i, j));
 #pragma unroll
-      for (int k = 0; k < j; k++) so -= A21[IK_TRI(i, k)] * A21[IK_TRI(j, k)] * dd[k];
-      A21[IK_TRI(i, j)] = so * inv;
+      for (int k = 0; k < j; k++) so -= IKJ(A21, IK_TRI(i, k)) * IKJ(A21, IK_TRI(j, k)) * dd[k];
+      IKJ(A21, IK_TRI(i, j)) = so * inv;
     }
   }
   *nneg = neg;
@@ -168,13 +170,13 @@ DEVFN void ik_chol_solve21(const ikr* L21, const ikr* dinv, const ikr* b, ikr* x
 #pragma unroll
   for (int i = 0; i < 6; i++) { ikr so = b[i];
 #pragma unroll
-    for (int k = 0; k < i; k++) so -= L21[IK_TRI(i, k)] * y[k];
-    y[i] = so * dinv[i]; }
+    for (int k = 0; k < i; k++) so -= IKJ(L21, IK_TRI(i, k)) * y[k];
+    y[i] = so * IKJ(dinv, i); }
 #pragma unroll
   for (int i = 5; i >= 0; i--) { ikr so = y[i];
 #pragma unroll
-    for (int k = i + 1; k < 6; k++) so -= L21[IK_TRI(k, i)] * x[k];
-    x[i] = so * dinv[i]; }
+    for (int k = i + 1; k < 6; k++) so -= IKJ(L21, IK_TRI(k, i)) * x[k];
+    x[i] = so * IKJ(dinv, i); }
 }
 // x = V clip(Lambda, lo, hi)^-1 V^T rhs for A = J J^T + reg I WITHOUT an eigen-decomposition, in the two cases that cover the
 // tabletop workspace (measured on the random-walk workload: 98 % / 2 % / none):
@@ -186,10 +188,11 @@ DEVFN void ik_chol_solve21(const ikr* L21, const ikr* dinv, const ikr* b, ikr* x
 //       the previous call's v_1.  "Exactly one" is the inertia of A - lo I (LDL^T pivot signs).
 // Anything else (two small eigenvalues, an untrustworthy pivot, no convergence) returns 0 and the caller falls back to the
 // Jacobi eigen-decomposition.  The clipped inverse is continuous in A, so the case boundaries need no margins.
-DEVFN int ik_solve_spd(const ikr* J, ikr reg, const ikr* rhs, ikr lo, ikr hi, ikr* x, ikr* v1 /*6*/, int* v1_valid) {
-  ikr A[21], dinv[6];
+// Aw: 27 doubles of work space with the same stride as J (packed 6x6 lower triangle + 6 inverse pivots).
+DEVFN int ik_solve_spd(const ikr* J, ikr reg, const ikr* rhs, ikr lo, ikr hi, ikr* x, ikr* v1 /*6*/, int* v1_valid, ikr* Aw) {
+  ikr* A = Aw; ikr* dinv = Aw + 21 * IK_JSTRIDE;
   ik_gram(J, reg - lo, A);
-  if (!(A[IK_TRI(0, 0)] + A[IK_TRI(1, 1)] + A[IK_TRI(2, 2)] + A[IK_TRI(3, 3)] + A[IK_TRI(4, 4)] + A[IK_TRI(5, 5)] + 6 * lo < hi)) return 0;
+  if (!(IKJ(A, IK_TRI(0, 0)) + IKJ(A, IK_TRI(1, 1)) + IKJ(A, IK_TRI(2, 2)) + IKJ(A, IK_TRI(3, 3)) + IKJ(A, IK_TRI(4, 4)) + IKJ(A, IK_TRI(5, 5)) + 6 * lo < hi)) return 0;
   const int none_below = ik_chol21(A, dinv);
   if (!none_below) {
     int nneg = 0;
@@ -304,15 +307,18 @@ DEVNI void ik_solve_clipped_lanes(const Cx& cx, ikr* A, const ikr* rhs, ikr* V, 
 // `active` = 0: the thread only takes part in the warp-cooperative section (its own outputs are discarded).
 // coop: 160 doubles of scratch shared by the lane group (k_ik: shared memory per warp; host: a local array).
 template <int G>
-DEVFN void ik_tick(const Cx& cx, const ikr* C, IkState& s, int active, ikr* V, int* vwarm, ikr* sn, ikr* cs, ikr* J /*42 * IK_JSTRIDE*/, ikr* coop) {
+DEVFN void ik_tick(const Cx& cx, const ikr* C, IkState& s, int active, ikr* V, int* vwarm, ikr* sn, ikr* cs, ikr* J /*42 * IK_JSTRIDE*/, ikr* Aw /*27 * IK_JSTRIDE*/, ikr* coop) {
   ikr q[7], des_quat[4] = {(ikr)s.des_quat[0], (ikr)s.des_quat[1], (ikr)s.des_quat[2], (ikr)s.des_quat[3]};
   for (int k = 0; k < 7; k++) q[k] = s.q[k];
   // *vwarm: bit 0 = sn/cs hold the sines/cosines of q, bit 1 = V[0..35] holds an eigenbasis of an earlier Jacobi call,
   //         bit 2 = V[36..41] holds the smallest eigenvector of an earlier ik_solve_spd call
-  if (!(*vwarm & 1)) { for (int k = 0; k < 7; k++) { sn[k] = sin(q[k]); cs[k] = cos(q[k]); } *vwarm |= 1; }      // exact once per launch
+  if (active && !(*vwarm & 1)) { for (int k = 0; k < 7; k++) { sn[k] = sin(q[k]); cs[k] = cos(q[k]); } *vwarm |= 1; }      // exact once per launch
   const int niter = (int)C[D3C_NUM_ITER];
+#pragma unroll 1
   for (int it = 0; it < niter; it++) {
-    ikr pos[3], cq[4];
+    ikr pos[3], cq[4], rhs[6], qd_null[7], x[6];
+    int need = 0;
+    if (active) {      // lanes without an env (or in joint-PD mode) only take part in the cooperative section below
     ik_fk(C, sn, cs, pos, cq, J);
     ikr dm = 0, dp = 0;
 #pragma unroll
@@ -321,7 +327,7 @@ DEVFN void ik_tick(const Cx& cx, const ikr* C, IkState& s, int active, ikr* V, i
 #pragma unroll
       for (int k = 0; k < 4; k++) des_quat[k] = -des_quat[k];
     }
-    ikr qe[3], rhs[6], qd_null[7], x[6];
+    ikr qe[3];
     qe[0] = cq[0] * des_quat[1] - des_quat[0] * cq[1] - cq[3] * des_quat[2] + cq[2] * des_quat[3];
     qe[1] = cq[0] * des_quat[2] - des_quat[0] * cq[2] + cq[3] * des_quat[1] - cq[1] * des_quat[3];
     qe[2] = cq[0] * des_quat[3] - des_quat[0] * cq[3] - cq[2] * des_quat[1] + cq[1] * des_quat[2];
@@ -338,8 +344,9 @@ DEVFN void ik_tick(const Cx& cx, const ikr* C, IkState& s, int active, ikr* V, i
       for (int k = 0; k < 7; k++) rhs[r] -= IKJ(J, r * 7 + k) * qd_null[k];
     }
     int v1ok = (*vwarm >> 2) & 1;
-    const int need = !ik_solve_spd(J, (ikr)C[D3C_JREG], rhs, (ikr)C[D3C_SVD_MIN], (ikr)C[D3C_SVD_MAX], x, V + 36, &v1ok) && active;
+    need = !ik_solve_spd(J, (ikr)C[D3C_JREG], rhs, (ikr)C[D3C_SVD_MIN], (ikr)C[D3C_SVD_MAX], x, V + 36, &v1ok, Aw);
     if (v1ok) *vwarm |= 4;
+    }
     // Some eigenvalue is (or may be) outside the clip range: eigen-decomposition with the clipped spectrum.  Rare (~2 % of
     // the iterations of the random-walk workload, near the edge of the arm's reach) but 5x the cost of everything else, and in
     // k_ik one needy env would stall the 31 others of its warp: so the WARP serves its needy envs one after the other, all
@@ -376,6 +383,7 @@ DEVFN void ik_tick(const Cx& cx, const ikr* C, IkState& s, int active, ikr* V, i
       if (mine) { for (int k = 0; k < 6; k++) x[k] = x2[k]; for (int k = 0; k < 36; k++) V[k] = cV[k]; *vwarm |= 2; }
       gsync<G>(cx);
     }
+    if (active) {
     ikr qd[7], nrm = 0;
 #pragma unroll
     for (int k = 0; k < 7; k++) {
@@ -397,6 +405,7 @@ DEVFN void ik_tick(const Cx& cx, const ikr* C, IkState& s, int active, ikr* V, i
       ikr nn = 1.5 - 0.5 * (s1 * s1 + c1 * c1);
       sn[k] = s1 * nn; cs[k] = c1 * nn;
       q[k] = qn;
+    }
     }
   }
   if (active) for (int k = 0; k < 7; k++) {

@@ -79,6 +79,7 @@ static inline bool d3il_build_model(const void* blob, size_t nbytes, Model& m, L
     m.d_bs[d] = lo; m.d_be[d] = hi;
     if (hi - lo > m.maxblk) m.maxblk = hi - lo;
   }
+  if (m.maxblk > D3_MAXB) { err = "a kinematic tree has more dofs than the register-resident block factorisation handles (D3_MAXB)"; return false; }
   m.ndamp = 0; m.damp_first = m.damp_end = 0;
   for (int d = 0; d < m.nv; d++) if (m.l_jtype[m.d_link[d]] != 2 && m.link[D3_LINK_W * m.d_link[d] + 25] > 0) { if (!m.ndamp) m.damp_first = d; m.ndamp++; m.damp_end = d + 1; }
   if (m.ndamp) {
@@ -106,6 +107,7 @@ static inline bool d3il_build_model(const void* blob, size_t nbytes, Model& m, L
       if (m.l_jtype[li] == 2 && Lk[13] == 0 && Lk[14] == 0 && Lk[15] == 0 && Lk[19] == 0 && Lk[20] == 0 && Lk[21] == 0) m.diag_blk |= 1u << m.nblk;
     }
     m.nblk++; }
+  for (int d = 0; d < m.nv; d++) for (int b = 0; b < m.nblk; b++) if (d >= m.blk_s[b] && d < m.blk_e[b]) m.d_blk[d] = (unsigned char)b;
   // in-block (a > b) dof pairs that are not ancestor-related: CRBA never writes them
   for (int a = 0; a < m.nv; a++) for (int b = m.d_bs[a]; b < a; b++)
     if (!((m.l_anc[m.d_link[a]] >> m.d_link[b]) & 1u)) {

@@ -52,10 +52,12 @@ class BaseSim(abc.ABC):
 
     @staticmethod
     def shard_range(n_items: int, rank: int, world: int):
-        """Contiguous item range of this rank (the reference's ``contexts[i*workload:(i+1)*workload]`` split)."""
-        per = (n_items + world - 1) // world
-        lo = min(rank * per, n_items)
-        return lo, min(lo + per, n_items)
+        """Contiguous item range of this rank (the reference's ``contexts[i*workload:(i+1)*workload]`` split), balanced:
+        the first ``n_items % world`` ranks get one item more, so no rank is empty while ``n_items >= world``.  A rank whose
+        range IS empty (fewer items than ranks) skips the rollout but still takes part in ``gather_rows``."""
+        base, extra = divmod(n_items, world)
+        lo = rank * base + min(rank, extra)
+        return lo, lo + base + (1 if rank < extra else 0)
 
     @staticmethod
     def gather_rows(local_rows: torch.Tensor, n_items: int) -> torch.Tensor:
@@ -69,7 +71,8 @@ class BaseSim(abc.ABC):
         pad[: local_rows.shape[0]] = local_rows
         out = [torch.zeros_like(pad) for _ in range(world)]
         dist.all_gather(out, pad)
-        return torch.cat(out, 0)[:n_items]
+        counts = [BaseSim.shard_range(n_items, r, world) for r in range(world)]
+        return torch.cat([o[: hi - lo] for o, (lo, hi) in zip(out, counts)], 0)
 
     def _cuda_index(self) -> int:
         d = torch.device(self.device) if not isinstance(self.device, torch.device) else self.device

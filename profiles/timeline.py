@@ -26,19 +26,28 @@ for k in range(nwarm):
         des[:, :3] = torch.where(force.bool().unsqueeze(1), tcp0, des[:, :3])
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+torch.cuda.synchronize()
+if hasattr(lib.lib(), 'd3il_debug_cta_stat'): lib.lib().d3il_debug_cta_stat(None, 1)
 e0.record(); env.step(des); e1.record(); torch.cuda.synchronize()
+stat = None
+if hasattr(lib.lib(), 'd3il_debug_cta_stat'):
+    sb = (C.c_uint * (4 * 4096))(); lib.lib().d3il_debug_cta_stat(sb, 0); stat = np.array(sb, dtype=np.int64).reshape(4096, 4)
 print(f'last step by CUDA events: {e0.elapsed_time(e1):.3f} ms')
 e0.record()
 for k in range(10): env.step(des)
 e1.record(); torch.cuda.synchronize()
 print(f'10 more steps: {e0.elapsed_time(e1)/10:.3f} ms per step')
+if hasattr(lib.lib(), 'd3il_debug_cta_stat'):
+    lib.lib().d3il_debug_cta_stat(None, 1)
+    env.step(des); torch.cuda.synchronize()          # the step both the timeline and the per-CTA statistics below describe
+    sb = (C.c_uint * (4 * 4096))(); lib.lib().d3il_debug_cta_stat(sb, 0); stat = np.array(sb, dtype=np.int64).reshape(4096, 4)
 buf = (C.c_ulonglong * (4 * 4096))()
 lib.lib().d3il_debug_timeline(buf)
 a = np.array(buf, dtype=np.uint64).reshape(4096, 4).astype(np.int64)
 env_b = a[(a[:, 3] == 2)]; ik_b = a[(a[:, 3] == 1)]; sch = a[(a[:, 3] == 3)]
-t0 = min(env_b[:, 0].min(), ik_b[:, 0].min())
+t0 = min(env_b[:, 0].min(), ik_b[:, 0].min()) if len(ik_b) else env_b[:, 0].min()
 if len(sch): print(f"k_sched: start {(sch[0,0]-t0)/1e6:.3f} end {(sch[0,1]-t0)/1e6:.3f} ms (relative to the first k_ik block)")
-print(f"k_ik blocks {len(ik_b)}: start {(ik_b[:,0].min()-t0)/1e6:.3f}..{(ik_b[:,0].max()-t0)/1e6:.3f} ms, end {(ik_b[:,1].min()-t0)/1e6:.3f}..{(ik_b[:,1].max()-t0)/1e6:.3f} ms")
+if len(ik_b): print(f"k_ik blocks {len(ik_b)}: start {(ik_b[:,0].min()-t0)/1e6:.3f}..{(ik_b[:,0].max()-t0)/1e6:.3f} ms, end {(ik_b[:,1].min()-t0)/1e6:.3f}..{(ik_b[:,1].max()-t0)/1e6:.3f} ms")
 print(f"k_env CTAs {len(env_b)}: start {(env_b[:,0].min()-t0)/1e6:.3f}..{(env_b[:,0].max()-t0)/1e6:.3f} ms, end {(env_b[:,1].min()-t0)/1e6:.3f}..{(env_b[:,1].max()-t0)/1e6:.3f} ms")
 dur = (env_b[:, 1] - env_b[:, 0]) / 1e6
 st = (env_b[:, 0] - t0) / 1e6
@@ -61,3 +70,10 @@ for t in (0.3, 1.0, 2.0):
     on_ik = [per_sm[s] for s in range(148) if s in ik_sms]
     off_ik = [per_sm[s] for s in range(148) if s not in ik_sms]
     print(f"t={t} ms: running k_env CTAs {running.sum()}; per SM with k_ik: {np.bincount(on_ik, minlength=3)}; without: {np.bincount(off_ik, minlength=3) if off_ik else []}")
+
+if stat is not None:
+    order = np.argsort(-dur)[:12]
+    print("slowest CTAs of the timeline step (block, start ms, duration ms):", [(int(i), round(float(st[i]), 2), round(float(dur[i]), 2)) for i in order])
+    top = np.argsort(-stat[:len(env_b), 0])[:12]
+    print("most Newton passes in the stat step: block: passes/coupled/own-steps/ls-evals:", [(int(b), *map(int, stat[b])) for b in top])
+    print("Newton passes per CTA: p50 %d p90 %d p99 %d max %d" % tuple(np.percentile(stat[:len(env_b), 0], [50, 90, 99, 100])))

@@ -24,7 +24,7 @@ Emu* emu_create(const void* blob, size_t n) {
   memset(&e->ik, 0, sizeof(e->ik));
   e->vwarm = 0;
   e->tol = sizeof(real) == 4 ? (real)1e-6 : (real)1e-10;
-  e->max_iter = sizeof(real) == 4 ? 12 : 100;
+  e->max_iter = sizeof(real) == 4 ? 24 : 100;
   return e;
 }
 void emu_destroy(Emu* e) { delete e; }
@@ -37,9 +37,9 @@ static void tick(Emu* e) {
   real* w = e->w.data();
   if (w[e->L.misc + ST_CTRL_MODE] == 1) {
     if (!e->ik.valid) { for (int k = 0; k < 7; k++) e->ik.q[k] = (double)w[e->L.qpos + k] + (double)w[e->L.qlo + k]; e->ik.valid = 1; }
-    double J[42], Cd[D3_CTRL_W], coop[160];
+    double J[42], Aw[27], Cd[D3_CTRL_W], coop[160];
     for (int k = 0; k < D3_CTRL_W; k++) Cd[k] = (double)e->m.ctrl[k];
-    ik_tick<1>(CX, Cd, e->ik, 1, e->V, &e->vwarm, e->sn, e->cs, J, coop);
+    ik_tick<1>(CX, Cd, e->ik, 1, e->V, &e->vwarm, e->sn, e->cs, J, Aw, coop);
   }
   if (e->m.maxdim == 4) physics_tick<1, false, 4>(CX, e->m, e->L, w, e->ik.jt_q, e->ik.jt_qlo, e->ik.jt_qd, e->tol, e->max_iter);
   else physics_tick<1, false, 3>(CX, e->m, e->L, w, e->ik.jt_q, e->ik.jt_qlo, e->ik.jt_qd, e->tol, e->max_iter);
@@ -105,7 +105,7 @@ extern "C" int emu_collide_boxes(const double* pA, const double* hA, const doubl
 // stand-alone probe of the IK's clipped-spectrum solve: method 0 = ik_solve_spd (Cholesky / one-eigenvalue deflation), 1 = Jacobi
 // lanes path.  Returns 1 if the method produced x.
 extern "C" int emu_ik_clipped_solve(const double* J42, const double* rhs, double reg, double lo, double hi, int method, double* x) {
-  if (method == 0) { double v1[6]; int ok = 0; return ik_solve_spd(J42, reg, rhs, lo, hi, x, v1, &ok); }
+  if (method == 0) { double v1[6], Aw[27]; int ok = 0; return ik_solve_spd(J42, reg, rhs, lo, hi, x, v1, &ok, Aw); }
   double A[36], V[36], B1[36], B2[36], cs[8], r[6];
   for (int i = 0; i < 6; i++) for (int j = 0; j < 6; j++) { double sum = i == j ? reg : 0; for (int k = 0; k < 7; k++) sum += J42[i * 7 + k] * J42[j * 7 + k]; A[i * 6 + j] = sum; }
   for (int k = 0; k < 6; k++) r[k] = rhs[k];
