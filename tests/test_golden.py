@@ -53,6 +53,13 @@ def test_gpu_follows_golden_rollouts(task):
     # (tests/test_emu_tasks.py), so the tail is bounded as a quantile
     assert np.median(errs.max(axis=1)) <= 0.3, errs
     assert (errs.max(axis=1) <= 1.0).mean() >= 0.75, errs
+    # the tail, in physical units and explained: wherever fp32 leaves the box, the fp64 host build of the same kernel source
+    # (tests/emu) stays inside it from the same start state (conditioning of a tumbling box, not logic)
+    from tests.util import explain_tail
+    gots = [env.get_state(i) for i in range(n)]
+    tail = explain_tail(task, states[:n], acts, states[1:n + 1], gots, nq, nv)
+    for t in tail:
+        assert max(t["u64"]) <= 0.1 and t["dq"] <= 2e-3 and t["dv"] <= 1.0, (task, t)
     assert np.array_equal(d.astype(float), info[:, 1]) and np.allclose(inf[:, 0], info[:, 2])      # done flags and success
     assert (inf[:, -1] == 0).all()
     env.close()

@@ -71,7 +71,13 @@ def test_task_env_step_teacher_forced(task):
         assert np.array_equal(info[i, :2], ii[:2]) and info[i, 3] == 0
     errs = np.array(errs)
     assert (errs.max(axis=1) <= 1.0).mean() >= 0.85, errs
-    assert errs[:, 0].max() < 2e3
+    # the tail (a box tipping over an edge) is bounded in physical units and shown to be fp32 precision, not logic, in
+    # tests/test_gpu_protocol.py::test_env_step_tail_is_precision_not_logic (fp64 build of the same source inside the box)
+    gots = [env.get_state(i) for i in range(n)]
+    for i in range(n):
+        o2.set_state(states[i]); o2.step(acts[i])
+        ref = o2.get_state()
+        assert np.abs(gots[i][:nq] - ref[:nq]).max() <= 1e-3, (i, np.abs(gots[i][:nq] - ref[:nq]).max())      # 1 mm / 1 mrad after 35 ticks
     env.close()
 
 
@@ -140,5 +146,6 @@ def test_stacking_reset_and_grasp_teacher_forced():
         assert np.array_equal(info[i, [0, 1, 3]], ii[[0, 1, 3]]) and info[i, 4] == 0
     errs = np.array(errs)
     assert (errs.max(axis=1) <= 1.0).mean() >= 0.85, errs
+    assert errs[:, 0].max() * 5e-6 <= 1e-3 or errs[:, 0].max() <= 200      # worst qpos excursion <= 1 mm-equivalent (see test_gpu_protocol.py for the fp64 cross-check)
     assert outs[-1][0][2] > 0.14                      # the oracle lifted the red box
     env.close()
