@@ -385,3 +385,71 @@ def test_grasp_holds_the_box_kkt_and_torsional_cone():
     lin = slice(9, 12)
     assert np.allclose((J.T @ f)[lin], 0.05 * (qacc[lin] + np.array([0, 0, 9.81])), atol=1e-6)
     assert abs(qacc[11]) < 2.0                             # and it is (nearly) held: far from free fall
+
+
+# ---- analytic known answers of MuJoCo's soft-contact model [EXT], restated independently of oracle/d3il_oracle.c ---------
+def _mj_impedance(solimp, r):
+    """mj_makeImpedance / getimpedance (MuJoCo 2.3 engine_core_constraint.c): d(r) for |dist - margin| = r, power 2."""
+    d0, dmax, width, mid, power = solimp
+    x = min(abs(r) / width, 1.0)
+    y = x ** power / mid ** (power - 1) if x <= mid else 1 - (1 - x) ** power / (1 - mid) ** (power - 1)
+    return d0 + y * (dmax - d0)
+
+
+def test_rest_penetration_is_the_soft_contact_known_answer(pushing_scene, pushing_contexts):
+    """A box at rest on the table: every corner contact carries f = D * k * imp(r) * r with k = 1 / (dmax^2 tau^2 zeta^2)
+    (solref = (tau, zeta)), D = imp / ((1 - imp) * invweight sum) — and the four of them carry m g: the penetration depth is
+    r = (m g / 4) (1 - imp) w / (k imp^2).  Checked against the pair's solref / solimp from the compiled MJCF, not against
+    anything the oracle computed for itself."""
+    env, sc = make(pushing_scene)
+    env.reset(pushing_contexts[5])
+    env.substep(800)
+    f = env.probe("efc_force"); con = env.probe("contacts").reshape(-1, 12); D = env.probe("efc_D")
+    pair = sc.pair[0]                                   # table_plane - push box: same solref / solimp for both boxes
+    tau, zeta = pair[8], pair[9]
+    solimp = pair[10:15]
+    k = 1.0 / (solimp[1] ** 2 * tau ** 2 * zeta ** 2)
+    rows = [c for c in con if c[11] >= 0 and c[6] < 0]
+    assert len(rows) == 8                                # 2 boxes x 4 corners
+    for c in rows:
+        r, e0 = -c[6], int(c[11])
+        imp = _mj_impedance(solimp, r)
+        assert abs(f[e0] - D[e0] * k * imp * r) < 1e-6 * f[e0]          # normal force = D * (-aref) at rest (a = v = 0)
+        # D = 1 / R, R = (1 - imp) / imp * w with w = translational invweight0 of the two bodies = 1 / m + 0 (free box, world)
+        w = sc.geom[int(pair[0])][13] + sc.geom[int(pair[1])][13]
+        assert abs(w - 1 / 0.05) < 1e-9
+        assert abs(D[e0] - imp / ((1 - imp) * w)) < 1e-9 * D[e0]
+        r_closed = (0.05 * 9.81 / 4) * (1 - imp) * w / (k * imp * imp)    # closed form of the rest depth for a quarter of the weight
+        assert abs(r - r_closed) < 0.02 * r, (r, r_closed)              # corners share the weight evenly to 2 % (box CoM is central)
+    assert abs(sum(f[int(c[11])] for c in rows) - 2 * 0.05 * 9.81) < 1e-6
+
+
+def test_sliding_friction_stays_on_the_elliptic_cone_and_dissipates():
+    """A body given a horizontal velocity on the table (Aligning's 1.004 kg tray, priority-1 friction 0.3): while its
+    contacts are active the friction force sits ON the elliptic cone, |f_t| = mu f_n, the sliding speed never increases, and
+    the tray comes to rest.  (A textbook mu g deceleration is NOT a known answer of this model: in MuJoCo's convex contact
+    formulation a sliding contact also produces extra normal force — the tray hops — which this restatement reproduces.)"""
+    from d3il_b200.scene.blob import load_scene
+    from tests.util import task_contexts
+    blob, sc = load_scene("aligning")
+    env = OracleEnv(blob, sc.header)
+    env.reset(task_contexts("aligning")[0])
+    env.substep(600)
+    s = env.get_state()
+    nq = sc.header["nq"]
+    mu = 0.3
+    s[nq + 9] = 0.6                                     # tray x velocity (free joint: world-frame linear dofs first)
+    env.set_state(s)
+    v_prev, n_active = 0.6, 0
+    for k in range(400):
+        env.substep(1)
+        st = env.get_state()
+        f = env.probe("efc_force"); con = env.probe("contacts").reshape(-1, 12)
+        for c in con:
+            e0 = int(c[11])
+            if e0 >= 0 and f[e0] > 1e-9 and st[nq + 9] > 0.05:
+                assert abs(np.hypot(f[e0 + 1], f[e0 + 2]) - mu * f[e0]) <= 1e-6 * f[e0]      # sliding: on the cone
+                n_active += 1
+        assert st[nq + 9] <= v_prev + 1e-7 or abs(st[nq + 9]) < 1e-4                                             # friction only dissipates (free flight between hops: unchanged to rounding)
+        v_prev = st[nq + 9]
+    assert n_active > 100 and abs(v_prev) < 1e-3                                       # it slid in contact, and it stopped
