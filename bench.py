@@ -64,6 +64,8 @@ def _cpu_worker(args):
     from d3il_b200.scene.blob import load_scene
     from oracle.oracle import OracleEnv          # bench.py's cpu_baseline / reference leg: allowed user of oracle/
 
+    if workload == "mixed7":                    # BASELINE.json configs[4]: the workers cycle through the seven state-based configs
+        workload = MIXED7[wid % len(MIXED7)]
     wl = WORKLOADS[workload]
     blob, sc = load_scene(wl["task"])
     ctxs = load_contexts(wl["ctx"]) if wl["ctx"] else None
@@ -109,7 +111,7 @@ def run_reference(args):
     import oracle.oracle as oo
     oo.build()
     cores = os.cpu_count() or 1
-    task = WORKLOADS[args.workload]["task"]
+    task = "mixed7" if args.workload == "mixed7" else WORKLOADS[args.workload]["task"]
     steps_per_worker = 256 if task in ("pushing", "avoiding", "aligning", "sorting_2") else 64
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
@@ -129,14 +131,15 @@ def run_reference(args):
         "config": {"workload": f"{args.workload}-randomwalk (bounded CPU sample: one env per host core)", "task": task},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "native_so": os.path.join(ROOT, "oracle", "libd3il_oracle.so") + " (fp64 CPU oracle, loaded in the forked worker processes; no repo CUDA library on this arm)",
     }))
 
 
-# ------------------------------------------------------------------------------------------------ GPU arm
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_env launch at the workload's default size, from the committed
-# `ncu --set full` captures (profiles/): filled in per task as captures are taken; None = not captured
-TRAFFIC_NCU = {"pushing": 38.1e6}       # profiles/r1_summary.md: 29.50 MB read + 8.57 MB written per k_env launch (4096 envs)
+# Facts taken from committed ncu captures (profiles/): dram__bytes_read.sum + dram__bytes_write.sum and smsp__inst_executed.sum of
+# ONE k_env launch at the workload's default size.  None / absent = not captured for that workload.
+NCU_FACTS = {
+    "pushing": {"dram_bytes": 38.1e6, "warp_inst_per_env_step": 2665352472 / 4096, "source": "profiles/r1_summary.md (k_env<3>, 4096 envs, one launch)"},
+}
 
 
 class ClockSampler:
@@ -179,93 +182,127 @@ class ClockSampler:
         return out
 
 
-def run_mixed(args):
-    """--workload mixed7 (BASELINE.json configs[4]): 8192 envs per GPU split over the seven state-based task configs, one
-    BatchedEnv + CUDA stream per task, random-walk set-points, auto-reset; value = total env steps of all tasks / time."""
-    import torch
-    import torch.distributed as dist
+# ------------------------------------------------------------------------------------------------ GPU arm
+def _alg_bytes_per_env_step(env) -> int:
+    """Algorithmic HBM bytes of one env step of one env: persistent fp32 state words in + out, action in,
+    obs / reward / done / info out."""
+    h = env.scene.header
+    n_state = h["nq"] + h["nv"] * 2 + 9 + 9 + 7 + 16 + h.get("nextra", 0) + 7 * 2 + 7 + 21      # + IK reference (7 doubles), desired pose, joint set-point
+    return 2 * 4 * n_state + 4 * env.act_dim + 4 * env.obs_dim + 4 + 1 + 4 * env.info_dim
 
-    from d3il_b200.mixed import MixedBatch
 
-    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    torch.cuda.set_device(local)
-    dev = torch.device(f"cuda:{local}")
-    n = args.envs or 8192
-    K, W = args.steps, max(args.warmup, 3)
-    wls = [WORKLOADS[w] for w in MIXED7]
-    mb = MixedBatch(n, local, tasks=[w["task"] for w in wls])
-    gen = torch.Generator(device=dev).manual_seed(99 + rank)
-    ctxs, starts, des = [], [], []
-    for e, w in zip(mb.envs, wls):
-        c = load_contexts(w["ctx"]) if w["ctx"] else None
-        ctxs.append(torch.tensor(c[(np.arange(e.n_envs) + rank * e.n_envs) % len(c)], dtype=torch.float32, device=dev) if c is not None else None)
-    mb.reset(ctxs)
-    for e in mb.envs:
-        if e.act_dim == 8:
-            st = e.joint_state().clone(); st[:, 7] = 0.08
+class EnvStream:
+    """One task's env batch with its synthetic action stream, episode bookkeeping and auto-reset: everything
+    on the device, no host synchronisation, capturable in a CUDA graph (the env step's launch number lives on the device)."""
+
+    def __init__(self, workload: str, n: int, rank: int, local: int, max_iter: int = 0):
+        import torch
+        from d3il_b200.batched_env import BatchedEnv
+        self.torch = torch
+        wl = WORKLOADS[workload]
+        self.workload, self.task, self.n, self.n_act = workload, wl["task"], n, wl["n_act"]
+        self.dev = dev = torch.device(f"cuda:{local}")
+        self.env = env = BatchedEnv(self.task, n, local)
+        if max_iter:
+            env.set_solver(1e-6, max_iter)
+        self.ctxs = load_contexts(wl["ctx"]) if wl["ctx"] else None
+        self.ctx_ids = (np.arange(n) + rank * n) % (len(self.ctxs) if self.ctxs is not None else 1)
+        self.ctx_t = torch.tensor(self.ctxs[self.ctx_ids], dtype=torch.float32, device=dev) if self.ctxs is not None else None
+        env.reset(self.ctx_t)
+        self.joint_space = env.act_dim == 8
+        if self.joint_space:      # Stacking (SURVEY §8d config 4): q_des += U(-0.01, 0.01)^7, gripper command toggled every 50 steps
+            start = env.joint_state().clone(); start[:, 7] = 0.08
         else:
-            st = torch.cat([e.robot_state().clone(), torch.tensor([0.0, 1.0, 0.0, 0.0], device=dev).repeat(e.n_envs, 1)], 1)
-        starts.append(st.contiguous()); des.append(st.clone())
-    lo3, hi3 = torch.tensor([*WORKSPACE_LO, 0.02], device=dev), torch.tensor([*WORKSPACE_HI, 0.35], device=dev)
-    returns = [torch.zeros(e.n_envs, 3, device=dev) for e in mb.envs]
+            start = torch.cat([env.robot_state().clone(), torch.tensor([0.0, 1.0, 0.0, 0.0], device=dev).repeat(n, 1)], 1)
+        self.start, self.des = start.contiguous(), start.clone().contiguous()
+        self.lo = torch.tensor([WORKSPACE_LO[0], WORKSPACE_LO[1], 0.02], device=dev)[:self.n_act]
+        self.hi = torch.tensor([WORKSPACE_HI[0], WORKSPACE_HI[1], 0.35], device=dev)[:self.n_act]
+        self.policy = None
+        if wl["policy"] == "ddpm":
+            from d3il_b200.simulation.policies import SyntheticDDPMPolicy
+            self.policy = SyntheticDDPMPolicy(self.n_act + env.obs_dim, self.n_act, width=256, n_hidden_layers=8, n_timesteps=4, t_dim=8, device=dev, seed=rank)
+        self.last_info = torch.zeros(n, env.info_dim, device=dev)     # info row of every env at its latest episode end
+        self.episodes = torch.zeros((), dtype=torch.long, device=dev)
+        self.fault_steps = torch.zeros((), dtype=torch.long, device=dev)      # env steps with a non-zero status word
+        self.bit_counts = torch.zeros(5, dtype=torch.long, device=dev)        # ... per status bit 1, 2, 4, 8, 16
+        self.bits = torch.tensor([1, 2, 4, 8, 16], dtype=torch.int32, device=dev)
+        self.step_no = torch.zeros((), dtype=torch.long, device=dev)
+        self.last_obs = env.obs.clone()
+        self.ep_len = env.max_steps_per_episode
 
-    def advance(k):
-        for e, w, d in zip(mb.envs, wls, des):
-            na = w["n_act"]
-            delta = torch.rand(e.n_envs, na, generator=gen, device=dev) * 0.02 - 0.01
-            if e.act_dim == 8:
-                d[:, :7] += delta; d[:, 7] = 0.08 if (k // 50) % 2 == 0 else 0.0
-            else:
-                d[:, :na] = torch.minimum(torch.maximum(d[:, :na] + delta, lo3[:na]), hi3[:na])
-        outs = mb.step(des)
-        masks = []
-        for (obs, rew, done, info), r, d, st in zip(outs, returns, des, starts):
-            r.copy_(torch.where(done.bool().unsqueeze(1), info[:, :3], r))
-            d.copy_(torch.where(done.bool().unsqueeze(1), st, d))
-            masks.append(done)
-        mb.reset(ctxs, masks)
+    def advance(self, force=None, events=None):
+        torch, env, n_act = self.torch, self.env, self.n_act
+        # synthetic action stream: policy output (config 3) or U(-0.01, 0.01) deltas integrated on the last DESIRED set-point
+        if self.policy is not None:
+            delta = self.policy.predict_batch(torch.cat([self.des[:, :n_act], self.last_obs], 1))
+        else:
+            delta = torch.rand(self.n, n_act, device=self.dev) * 0.02 - 0.01
+        if self.joint_space:
+            self.des[:, :7] += delta
+            self.des[:, 7] = torch.where((self.step_no // 50) % 2 == 0, 0.08, 0.0)
+        else:
+            self.des[:, :n_act] = torch.minimum(torch.maximum(self.des[:, :n_act] + delta, self.lo), self.hi)
+        if events:
+            events[0].record()
+        obs, rew, done, info = env.step(self.des)
+        if events:
+            events[1].record()
+        self.last_obs.copy_(obs)
+        self.step_no.add_(1)
+        st = info[:, -1].to(torch.int32)
+        self.fault_steps.add_((st != 0).sum())
+        self.bit_counts.add_(((st.unsqueeze(1) & self.bits) != 0).sum(0))      # per-bit counts: an OR over envs, not a max
+        # episode bookkeeping + auto-reset of finished envs (masked reset kernel; the set-point snaps back to the start pose)
+        m = done if force is None else force
+        mb = m.bool().unsqueeze(1)
+        self.last_info.copy_(torch.where(mb, info, self.last_info))
+        self.episodes.add_(m.sum())
+        env.reset(self.ctx_t, m)
+        self.des.copy_(torch.where(mb, self.start, self.des))
 
-    # pre-roll: 300 steps with staggered forced resets would need per-task episode lengths; a plain 150-step run-in is used
-    for k in range(150 if not args.no_preroll else 0):
-        advance(k)
-    for k in range(W):
-        advance(k)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
-    l0 = mb.kernel_launches
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for k in range(K):
-        advance(W + k)
-    ev1.record()
-    torch.cuda.synchronize()
-    ms = ev0.elapsed_time(ev1)
-    if world > 1:
-        t = torch.tensor([ms], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX); ms = float(t.item())
-        allr = torch.cat(returns, 0)
-        gathered = [torch.zeros_like(allr) for _ in range(world)] if rank == 0 else None
-        dist.gather(allr, gathered, dst=0)
-    clocks = sampler.stop() if sampler else None
-    if rank == 0:
-        print(json.dumps({
-            "metric": METRIC, "value": world * mb.n_envs * K / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"mixed7-{mb.n_envs}env-per-gpu-randomwalk", "tasks": list(mb.tasks), "envs_per_task": mb.counts, "auto_reset": True, "run_in_steps": 150},
-            "clocks": clocks, "gpu_launches": int(mb.kernel_launches - l0),
-        }))
-    if world > 1:
-        dist.destroy_process_group()
+    def result_rows(self):
+        """Per-env result rows in the layout the task's ``*_Sim.test_agent`` gathers."""
+        torch, info = self.torch, self.last_info
+        if self.task == "stacking":
+            from d3il_b200.simulation.metrics import stacking_rows
+            return stacking_rows(info)                                           # mode_3, mode_1, mode_2, success, success_1, success_2
+        if self.task == "avoiding":
+            return torch.cat([info[:, 1:10], info[:, 0:1]], 1)                   # 9 mode bits + success
+        return torch.stack([info[:, 1], info[:, 0], info[:, 2]], 1)             # mode, success, mean_distance / mode_step
+
+
+def device_metrics(task: str, rows, n_ctx: int):
+    """Behaviour metrics of the gathered result rows, computed ON THE DEVICE (simulation/metrics.py): per-context mode
+    histograms over successful rollouts -> entropy (KL for Sorting / Stacking).  Rows are grouped as [context, rollout] by the
+    env index modulo the number of contexts."""
+    import torch
+    from d3il_b200.simulation import metrics as M
+    n = rows.shape[0]
+    if task == "avoiding":
+        probs, ent = M.avoiding_entropy(rows[:, :9], rows[:, 9])
+        return {"success": float(rows[:, 9].mean()), "entropy": float(ent)}
+    per = n // n_ctx
+    if per == 0:
+        return {}
+    idx = torch.arange(n, device=rows.device)
+    grid = rows[idx[: per * n_ctx].reshape(per, n_ctx).t().reshape(-1)].reshape(n_ctx, per, -1)      # env i -> context i % n_ctx
+    if task == "stacking":
+        from d3il_b200.simulation.stacking_sim import MODE_3, MODE_PROB
+        prior = {MODE_3[k]: v for k, v in MODE_PROB.items()}
+        _, ent, kl = M.mode_kl(grid[:, :, 0], grid[:, :, 3], prior)
+        return {"success": float(grid[:, :, 3].mean()), "success_1_box": float(grid[:, :, 4].mean()), "success_2_boxes": float(grid[:, :, 5].mean()), "entropy_3": ent, "KL_3": kl}
+    mode, succ = grid[:, :, 0], grid[:, :, 1]
+    if task.startswith("sorting"):
+        _, ent, kl = M.mode_kl(mode, succ, None)
+        return {"success": float(succ.mean()), "entropy": ent, "KL": kl}
+    n_modes = {"pushing": 4, "aligning": 2, "inserting": 6}[task]
+    _, ent = M.mode_entropy(mode, succ, n_modes)
+    return {"success": float(succ.mean()), "entropy": float(ent), "mean_distance": float(grid[:, :, 2].mean())}
 
 
 def run_gpu(args):
     import torch
     import torch.distributed as dist
-
-    from d3il_b200.batched_env import BatchedEnv
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -274,162 +311,175 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
-    wl = WORKLOADS[args.workload]
-    task = wl["task"]
-    n = args.envs or wl["envs"]
+    torch.manual_seed(1234 + rank)
     K, W = args.steps, max(args.warmup, 3)
-
-    env = BatchedEnv(task, n, local)
-    if args.max_iter:
-        env.set_solver(1e-6, args.max_iter)
-    ctxs = load_contexts(wl["ctx"]) if wl["ctx"] else None
-    ctx_ids = (np.arange(n) + rank * n) % (len(ctxs) if ctxs is not None else 1)
-    ctx_t = torch.tensor(ctxs[ctx_ids], dtype=torch.float32, device=dev) if ctxs is not None else None
-    env.reset(ctx_t)
-    joint_space = env.act_dim == 8
-    n_act = wl["n_act"]
-    if joint_space:
-        # Stacking: q_des += U(-0.01, 0.01)^7, gripper command toggled every 50 steps
-        start = env.joint_state().clone()
-        start[:, 7] = 0.08
+    mixed = args.workload == "mixed7"
+    if mixed:      # BASELINE.json configs[4]: 8192 envs per GPU split over the seven state-based configs, one env batch + stream per task
+        n_total = args.envs or 8192
+        counts = [n_total // len(MIXED7)] * len(MIXED7)
+        counts[0] += n_total - sum(counts)
+        streams = [EnvStream(w, c, rank, local, args.max_iter) for w, c in zip(MIXED7, counts)]
     else:
-        quat = torch.tensor([0.0, 1.0, 0.0, 0.0], device=dev).repeat(n, 1)
-        start = torch.cat([env.robot_state().clone(), quat], 1).contiguous()
-    des = start.clone()
-    lo3 = torch.tensor([WORKSPACE_LO[0], WORKSPACE_LO[1], 0.02], device=dev)[:n_act]
-    hi3 = torch.tensor([WORKSPACE_HI[0], WORKSPACE_HI[1], 0.35], device=dev)[:n_act]
-    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    policy = None
-    if wl["policy"] == "ddpm":
-        from d3il_b200.simulation.policies import SyntheticDDPMPolicy
-        policy = SyntheticDDPMPolicy(n_act + env.obs_dim, n_act, width=256, n_hidden_layers=8, n_timesteps=4, t_dim=8, device=dev, seed=rank)
-    pool_len = 64
-    deltas = (torch.rand(pool_len, n, n_act, generator=gen, device=dev) * 0.02 - 0.01)      # host-path (e2e) stream
-    returns = torch.zeros(n, 3, device=dev)          # per-env episode result rows (first three info words)
-    faults = torch.zeros((), dtype=torch.long, device=dev)      # env steps that raised a status bit (solver fault / contact or row overflow)
-    step_no = torch.zeros((), dtype=torch.long, device=dev)
-    fault_bits = torch.zeros((), dtype=torch.int32, device=dev)
-    last_obs = env.obs.clone()
+        streams = [EnvStream(args.workload, args.envs or WORKLOADS[args.workload]["envs"], rank, local, args.max_iter)]
+    n = sum(s.n for s in streams)
+    side = [torch.cuda.Stream(device=dev) for _ in streams] if mixed else None
 
-    def advance(force=None):
-        # synthetic action stream: policy output (config 3) or U(-0.01, 0.01) deltas integrated on the last DESIRED set-point
-        if policy is not None:
-            delta = policy.predict_batch(torch.cat([des[:, :n_act], last_obs], 1))
-        else:
-            delta = torch.rand(n, n_act, generator=gen, device=dev) * 0.02 - 0.01
-        if joint_space:
-            des[:, :7] += delta
-            des[:, 7] = torch.where((step_no // 50) % 2 == 0, 0.08, 0.0)
-        else:
-            des[:, :n_act] = torch.minimum(torch.maximum(des[:, :n_act] + delta, lo3), hi3)
-        obs, rew, done, info = env.step(des)
-        last_obs.copy_(obs)
-        step_no.add_(1)
-        faults.add_((info[:, -1] != 0).sum())
-        fault_bits.bitwise_or_(info[:, -1].to(torch.int32).max())        # status bits: 1 M not PD / NaN, 2 contact or row budget overflow, 4 Newton Hessian not PD
-        # episode bookkeeping + auto-reset of finished envs (masked reset kernel; set-point snaps back to the start pose)
-        m = done if force is None else force
-        returns.copy_(torch.where(m.bool().unsqueeze(1), info[:, :3], returns))
-        env.reset(ctx_t, m)
-        des.copy_(torch.where(m.bool().unsqueeze(1), start, des))
+    def step_all(force_k=None, events=None):
+        if not mixed:
+            s = streams[0]
+            s.advance(None if force_k is None else (torch.arange(s.n, device=dev) % s.ep_len == force_k).to(torch.uint8), events)
+            return
+        cur = torch.cuda.current_stream(dev)
+        if events:
+            events[0].record()
+        for s, st in zip(streams, side):                    # the per-task step kernels of one env step overlap on the device
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                s.advance(None if force_k is None else (torch.arange(s.n, device=dev) % s.ep_len == force_k).to(torch.uint8))
+        for st in side:
+            cur.wait_stream(st)
+        if events:
+            events[1].record()
 
-    # pre-roll (untimed, not part of W): spread the envs uniformly over the episode so the timed region sees the
-    # steady-state mix of episode phases (fresh resets, free motion, contact) instead of n synchronised envs;
-    # env i is force-reset once at pre-roll step i % ep_len.
-    ep_len = env.max_steps_per_episode
-    ids = torch.arange(n, device=dev)
-    for k in range(ep_len if not args.no_preroll else 0):
-        advance((ids % ep_len == k).to(torch.uint8))
+    # pre-roll (untimed, not part of W): spread the envs uniformly over the episode so the timed region sees the steady-state
+    # mix of episode phases (fresh resets, free motion, contact) instead of n synchronised envs; env i is force-reset once at
+    # pre-roll step i % ep_len.
+    preroll = 0 if args.no_preroll else min(max(s.ep_len for s in streams), 400 if mixed else 10 ** 9)
+    for k in range(preroll):
+        step_all(force_k=k)
     for k in range(W):
-        advance()
+        step_all()
     torch.cuda.synchronize()
+    launches_per_step = 0
+    l0 = sum(s.env.kernel_launches for s in streams)
+    step_all()
+    torch.cuda.synchronize()
+    launches_per_step = sum(s.env.kernel_launches for s in streams) - l0      # k_sched + k_ik + k_env (+ k_reset) per task
+    graph = None
+    if not args.no_graph:
+        # one env step of the whole job ([action stream / policy -> step -> bookkeeping -> masked reset] of every task) as ONE graph
+        # launch: no per-kernel launch gaps, no Python between the ~25 small kernels of the step
+        cap = torch.cuda.Stream(device=dev)
+        cap.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(cap):
+            for _ in range(2):
+                step_all()
+        torch.cuda.current_stream(dev).wait_stream(cap)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=cap):
+            step_all()
+        torch.cuda.synchronize()
+    run_step = graph.replay if graph is not None else step_all
+    for s in streams:
+        s.fault_steps.zero_(); s.bit_counts.zero_(); s.episodes.zero_()
     if world > 1:
         dist.barrier()
     sampler = ClockSampler(local) if rank == 0 else None
-    launches0 = env.kernel_launches
-    faults.zero_(); fault_bits.zero_()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     ev0.record()
     for k in range(K):
-        advance()
+        run_step()
     ev1.record()
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
-    n_faults = int(faults.item())
-    launches = env.kernel_launches - launches0
+    n_faults = int(sum(int(s.fault_steps.item()) for s in streams))
+    bit_counts = sum(s.bit_counts for s in streams).tolist()
+    episodes = int(sum(int(s.episodes.item()) for s in streams))
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
         dist.barrier()
-        # the path's only exchange: gather the per-env episode result rows at rollout end (replaces the shared-memory
-        # result tensors of simulation/pushing_sim.py:97-99)
-        gathered = [torch.zeros_like(returns) for _ in range(world)] if rank == 0 else None
-        dist.gather(returns, gathered, dst=0)
+    # the path's only exchange: ONE gather of the per-env episode result rows at rollout end (replaces the shared-memory result
+    # tensors of simulation/pushing_sim.py:97-99; Stacking: the six columns of stacking_sim.py:122-141), then the behaviour
+    # metrics on the gathered rows, on the device
+    metrics = {}
+    for s in streams:
+        rows = s.result_rows().contiguous()
+        if world > 1:
+            parts = [torch.zeros_like(rows) for _ in range(world)]
+            dist.all_gather(parts, rows)
+            rows = torch.cat(parts, 0)
+        metrics[s.task] = dict(device_metrics(s.task, rows, len(s.ctxs) if s.ctxs is not None else 1), rows=list(rows.shape))
     clocks = sampler.stop() if sampler else None
     value = world * n * K / (ms * 1e-3)
 
-    # ---- per-kernel device time (CUDA events on the launching stream, inside the library) for the roofline object
-    env.set_profiling(True)
-    for k in range(4):          # the library synchronises after every profiled step: let the stream settle first
-        advance()
-    env.set_profiling(True)     # (re-arming clears the accumulators)
-    for k in range(24):
-        advance()
-    ik_ms, env_ms, nprof = env.get_profile()
-    env.set_profiling(False)
-    k_env_ms = (ik_ms + env_ms) / max(nprof, 1)      # k_sched + k_ik + k_env of one env step (k_ik overlaps k_env: programmatic dependent launch)
-    n_state = env.scene.header["nq"] + env.scene.header["nv"] * 2 + 9 + 9 + 7 + 16 + env.scene.header.get("nextra", 0)      # persistent fp32 words per env
-    alg_bytes_env = 2 * 4 * n_state + 4 * env.act_dim + 4 * env.obs_dim + 4 + 1 + 4 * env.info_dim
-    alg_bytes_launch = alg_bytes_env * n
+    # ---- device time of the step's own kernels (k_sched + k_ik + k_env of every task): CUDA events recorded on the launching
+    # stream around env.step, NOT synchronised step by step (the overlap of k_ik and k_env stays intact), read back at the end
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(32)]
+    for e in evs:
+        step_all(events=e)
+    torch.cuda.synchronize()
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    alg_bytes_launch = sum(_alg_bytes_per_env_step(s.env) * s.n for s in streams)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    achieved = alg_bytes_launch / (k_env_ms * 1e-3) / 1e9
+    achieved = alg_bytes_launch / (kernel_ms * 1e-3) / 1e9
+    key = "mixed7" if mixed else streams[0].task
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": TRAFFIC_NCU.get(task), "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
-                "kernel": "k_env (+ overlapped k_ik, k_sched)", "kernel_ms": k_env_ms, "k_ik_done_ms": ik_ms / max(nprof, 1), "alg_bytes_per_env_step": alg_bytes_env,
-                "note": "fused n_substeps-tick kernel is ALU/latency-bound, not HBM-bound (SURVEY §8d); see DESIGN.md for the fp32 issue-rate view"}
+                "traffic": NCU_FACTS.get(key, {}).get("dram_bytes"), "traffic_source": NCU_FACTS.get(key, {}).get("source"),
+                "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)",
+                "kernel": "k_env (+ overlapped k_ik, k_sched)" + (" x 7 tasks on 7 streams" if mixed else ""), "kernel_ms": kernel_ms,
+                "alg_bytes_per_launch": alg_bytes_launch,
+                "note": "algorithmic bytes = state row in + out, action, obs, reward, done, info; the fused n_substeps-tick kernel keeps the state in shared memory and is issue / latency bound (second object)"}
+    inst = NCU_FACTS.get(key, {}).get("warp_inst_per_env_step")
+    sm_mhz = (clocks or {}).get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
+    roofline_issue = None
+    if inst:
+        ach = inst * n / (kernel_ms * 1e-3)
+        pk = 148 * 4 * sm_mhz * 1e6
+        roofline_issue = {"bound": "issue", "achieved": ach, "peak": pk, "unit": "warp-inst/s", "frac": ach / pk, "warp_inst_per_env_step": inst,
+                          "source": NCU_FACTS[key]["source"], "note": "148 SMs x 4 schedulers x 1 warp instruction per cycle at the SM clock sampled during the timed region"}
 
     # ---- e2e: same workload through the host-buffer C ABI (numpy in/out, H2D + D2H every step)
     e2e_steps = max(8, min(K, 64))
-    start_h = start.cpu().numpy().astype(np.float32)
-    des_h = des.cpu().numpy().astype(np.float32)          # continue from the steady-state mix of the timed region
-    deltas_h = deltas.cpu().numpy()
-    ctx_h = ctxs[ctx_ids].astype(np.float32) if ctxs is not None else None
-    lo_h, hi_h = lo3.cpu().numpy(), hi3.cpu().numpy()
+    host = []
+    for s in streams:
+        host.append(dict(des=s.des.cpu().numpy().astype(np.float32), start=s.start.cpu().numpy().astype(np.float32),
+                         ctx=s.ctxs[s.ctx_ids].astype(np.float32) if s.ctxs is not None else None, obs=s.last_obs.cpu().numpy(),
+                         lo=s.lo.cpu().numpy(), hi=s.hi.cpu().numpy(), rng=np.random.default_rng(7 + rank)))
     h2d = d2h = 0
-    obs_h = last_obs.cpu().numpy()
+
+    def host_step(k, count):
+        nonlocal h2d, d2h
+        for s, hb in zip(streams, host):
+            na = s.n_act
+            if s.policy is not None:      # policy on the GPU: observations go up, deltas come down, every step
+                pin = torch.from_numpy(np.concatenate([hb["des"][:, :na], hb["obs"]], 1)).to(dev)
+                delta = s.policy.predict_batch(pin).cpu().numpy()
+                if count:
+                    h2d += pin.numel() * 4; d2h += delta.nbytes
+            else:
+                delta = hb["rng"].uniform(-0.01, 0.01, (s.n, na)).astype(np.float32)
+            if s.joint_space:
+                hb["des"][:, :7] += delta
+                hb["des"][:, 7] = 0.08 if (k // 50) % 2 == 0 else 0.0
+            else:
+                hb["des"][:, :na] = np.clip(hb["des"][:, :na] + delta, hb["lo"], hb["hi"])
+            hb["obs"], rew_h, done_h, info_h = s.env.step_host(hb["des"])
+            if count:
+                h2d += hb["des"].nbytes
+                d2h += hb["obs"].nbytes + rew_h.nbytes + done_h.nbytes + info_h.nbytes
+            if done_h.any():
+                s.env.reset_host(hb["ctx"], done_h)
+                if count:
+                    h2d += (hb["ctx"].nbytes if hb["ctx"] is not None else 0) + done_h.nbytes
+                hb["des"][done_h.astype(bool)] = hb["start"][done_h.astype(bool)]
+
     for k in range(3):
-        env.step_host(des_h)
+        host_step(k, False)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
     for k in range(e2e_steps):
-        if policy is not None:      # policy on the GPU: observations go up, deltas come down, every step
-            pin = torch.from_numpy(np.concatenate([des_h[:, :n_act], obs_h], 1)).to(dev)
-            delta_h = policy.predict_batch(pin).cpu().numpy()
-            h2d += pin.numel() * 4
-            d2h += delta_h.nbytes
-        else:
-            delta_h = deltas_h[k % pool_len]
-        if joint_space:
-            des_h[:, :7] += delta_h
-            des_h[:, 7] = 0.08 if (k // 50) % 2 == 0 else 0.0
-        else:
-            des_h[:, :n_act] = np.clip(des_h[:, :n_act] + delta_h, lo_h, hi_h)
-        obs_h, rew_h, done_h, info_h = env.step_host(des_h)
-        h2d += des_h.nbytes
-        d2h += obs_h.nbytes + rew_h.nbytes + done_h.nbytes + info_h.nbytes
-        if done_h.any():
-            env.reset_host(ctx_h, done_h)
-            h2d += (ctx_h.nbytes if ctx_h is not None else 0) + done_h.nbytes
-            des_h[done_h.astype(bool)] = start_h[done_h.astype(bool)]
+        host_step(k, True)
     dt = time.perf_counter() - t0
     if world > 1:          # every rank drives its own GPU through the host API at the same time; slowest rank sets the rate
         t = torch.tensor([dt], device=dev)
@@ -446,23 +496,34 @@ def run_gpu(args):
     import oracle.oracle as oo
     oo.build()
     cores = os.cpu_count() or 1
+    cpu_wl = args.workload
     with mp.get_context("fork").Pool(cores) as pool:
-        probe_val, _ = cpu_sample(args.workload, cores, 32, pool)
+        probe_val, _ = cpu_sample(cpu_wl, cores, 32, pool)
         # bounded sample: ~20 s of CPU work in total (all cores for ~1.3 s each), sized from the probe's rate
         spw = int(min(4096, max(64, 1.3 * probe_val / cores)))
-        cpu_val, cpu_wall = cpu_sample(args.workload, cores, spw, pool)
-    one_val, one_wall = cpu_sample(args.workload, 1, 2 * spw)
+        cpu_val, cpu_wall = cpu_sample(cpu_wl, cores, spw, pool)
+    one_val, one_wall = cpu_sample(cpu_wl, 1, 2 * spw)
     cpu_baseline = {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
                     "sample": f"{cores} processes x {spw} env steps of the {args.workload} workload (one fp64 oracle env per core, {cpu_wall:.1f} s); single core: {one_val:.0f} env-steps/s over {2 * spw} steps",
                     "single_core_value": one_val}
 
+    s0 = streams[0]
+    config = {"workload": (f"mixed7-{n}env-per-gpu-randomwalk" if mixed else
+                           f"{args.workload}-{n}env-per-gpu-" + ("ddpm-mlp-in-loop" if s0.policy is not None else "randomwalk")),
+              "task": "mixed7" if mixed else s0.task, "envs_per_gpu": n, "auto_reset": True, "preroll_steps": preroll,
+              "cuda_graph": graph is not None,
+              "l2_note": "every env step rewrites the whole state working set (no cross-step reuse of inputs); timing is launch-to-launch on one stream"}
+    if mixed:
+        config.update(tasks=[s.task for s in streams], envs_per_task=[s.n for s in streams])
+    else:
+        config.update(n_substeps=s0.env.n_substeps, episode_len=s0.ep_len)
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}-{n}env-per-gpu-" + ("ddpm-mlp-in-loop" if policy is not None else "randomwalk"), "task": task, "envs_per_gpu": n,
-                   "n_substeps": env.n_substeps, "episode_len": ep_len, "auto_reset": True, "preroll_steps": 0 if args.no_preroll else ep_len,
-                   "l2_note": "state+trajectory working set per step is rewritten every step (no cross-step reuse of inputs); timing is launch-to-launch on one stream"},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "env_step_faults": n_faults, "env_step_fault_bits": int(fault_bits.item()), "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * K), "gpu_launches_per_step": int(launches_per_step),
+        "env_step_faults": n_faults, "env_step_fault_bit_counts": dict(zip(["1_M_not_PD", "2_overflow", "4_H_not_PD", "8_iter_cap", "16_bad_action"], bit_counts)),
+        "episodes_finished": episodes, "behaviour_metrics": metrics,
+        "roofline": roofline, "roofline_issue": roofline_issue, "cpu_baseline": cpu_baseline,
         "target": {"env_steps_per_sec": 1.0e6, "met": bool(value >= 1.0e6)},
     }))
     if world > 1:
@@ -479,13 +540,10 @@ def main():
     ap.add_argument("--workload", default="pushing", choices=sorted(WORKLOADS) + ["mixed7"], help="default = the configuration the metric is quoted on")
     ap.add_argument("--no-preroll", action="store_true", help="skip the 400-step episode-phase pre-roll (debug)")
     ap.add_argument("--max-iter", type=int, default=0, help="override the Newton iteration cap (diagnostics; default: the library's)")
+    ap.add_argument("--no-graph", action="store_true", help="launch the env step kernel by kernel instead of replaying one CUDA graph per env step")
     args = ap.parse_args()
     if args.impl == "reference":
-        if args.workload == "mixed7":
-            args.workload = "pushing"
         run_reference(args)
-    elif args.workload == "mixed7":
-        run_mixed(args)
     else:
         run_gpu(args)
 

@@ -34,7 +34,7 @@ extern "C" const char* d3il_last_error(void) { return g_err.c_str(); }
 struct d3il_env {
   Model m; Lay L;
   DevCtx d;
-  int device, n, max_ticks, n_ik_blocks, n_ik_flags, launch_id, n_single;
+  int device, n, max_ticks, n_ik_blocks, n_ik_flags, n_single;
   long long launches;
   size_t smem_bytes;
   // pinned + device staging for the *_host calls
@@ -61,6 +61,14 @@ __device__ __forceinline__ unsigned smid() { unsigned r; asm volatile("mov.u32 %
 __global__ void __launch_bounds__(1024) k_sched(DevCtx c) {
   TL_BEGIN(3, 4095);
   __shared__ int hist[256], start[256];
+  // advance the launch number (the base of this step's IK release flags); when it wraps, the monotonic flags restart from zero
+  // — nothing else runs on the stream while k_sched does
+  {
+    const int id = (*c.launch_no + 1) & 0xffffff;
+    __syncthreads();
+    if (threadIdx.x == 0) *c.launch_no = id;
+    if (id == 0) for (int i = threadIdx.x; i < c.n_ik_flags; i += blockDim.x) c.ik_flags[i] = 0;
+  }
   for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
   __syncthreads();
   const int off = c.lay.misc + ST_COST_ITERS;
@@ -80,7 +88,8 @@ __global__ void __launch_bounds__(1024) k_sched(DevCtx c) {
   TL_END(3);
 }
 
-__global__ void __launch_bounds__(IK_THREADS) k_ik(DevCtx c, const float* __restrict__ action, int n_ticks, int use_action, int flag_base, int ctrl_kind, int act_dim) {
+__global__ void __launch_bounds__(IK_THREADS) k_ik(DevCtx c, const float* __restrict__ action, int n_ticks, int use_action, int ctrl_kind, int act_dim) {
+  const int flag_base = *(volatile const int*)c.launch_no * 64;
   // Programmatic dependent launch: let the env-step kernel (next in the stream) start while this one is still running.
   // It consumes our set-points tick by tick through the release flags below; we never wait on anything, and we are
   // already resident when it is allowed to launch, so the hand-off cannot deadlock.
@@ -176,7 +185,7 @@ static int create_impl(d3il_env* h, const void* blob, size_t nbytes, int n_envs,
   CK(cudaSetDevice(device));
   DevCtx& d = h->d;
   d.lay = h->L; d.n = n_envs; d.row = (h->L.n_state + 31) & ~31; d.ws_stride = (h->L.total + 31) & ~31;
-  d.tol = 1e-6f; d.max_iter = 24;      // cap never reached on the benchmark workloads (status bit 8 reports it if it is); 12 was hit by 0.4 % of the env steps
+  d.tol = 1e-6f; d.max_iter = 32;      // the cap is not reached on the benchmark workloads (status bit 8 reports it if it is; 12 was hit by 0.4 % of the Pushing env steps, 24 by a few closing-gripper steps of Stacking); the loop is CTA-uniform with early exit, so a high cap costs nothing
   Model* dm = nullptr;
   CK(cudaMalloc(&dm, sizeof(Model)));
   CK(cudaMemcpy(dm, &h->m, sizeof(Model), cudaMemcpyHostToDevice));
@@ -192,11 +201,14 @@ static int create_impl(d3il_env* h, const void* blob, size_t nbytes, int n_envs,
   CK(cudaMemset(d.ik.jt, 0, (size_t)21 * n_envs * sizeof(float)));
   CK(cudaMemset(d.ik.valid, 0, (size_t)n_envs * sizeof(int)));
   CK(cudaMalloc(&d.traj, (size_t)h->max_ticks * 21 * n_envs * sizeof(float)));
-  h->n_ik_blocks = (n_envs + IK_THREADS - 1) / IK_THREADS; h->launch_id = 0;
+  h->n_ik_blocks = (n_envs + IK_THREADS - 1) / IK_THREADS;
   h->n_ik_flags = h->n_ik_blocks * (IK_THREADS / IK_FLAG_ENVS);
   CK(cudaMalloc(&d.ik_flags, (size_t)h->n_ik_flags * sizeof(int)));
   CK(cudaMalloc(&d.perm, (size_t)n_envs * sizeof(int)));
   CK(cudaMemset(d.ik_flags, 0, (size_t)h->n_ik_flags * sizeof(int)));
+  d.n_ik_flags = h->n_ik_flags;
+  CK(cudaMalloc(&d.launch_no, sizeof(int)));
+  CK(cudaMemset(d.launch_no, 0, sizeof(int)));
   // envs per CTA: ENVS_PER_CTA (two CTAs per SM for the small scenes), fewer when the per-env workspace is large (Sorting-4/6)
   const size_t model_bytes = d3il_model_bytes(h->m), env_bytes = (size_t)d.ws_stride * sizeof(float);
   d.model_bytes = (int)model_bytes;
@@ -240,7 +252,7 @@ extern "C" void d3il_destroy(d3il_env* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaFree((void*)h->d.model); cudaFree(h->d.state); cudaFree(h->d.ik.q); cudaFree(h->d.ik.des); cudaFree(h->d.ik.jt); cudaFree(h->d.ik.valid);
-  cudaFree(h->d.traj); cudaFree(h->d.ik_flags); cudaFree(h->d.perm); cudaFreeHost(h->h_in); cudaFreeHost(h->h_out); cudaFreeHost(h->h_mask); cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_mask);
+  cudaFree(h->d.traj); cudaFree(h->d.ik_flags); cudaFree(h->d.launch_no); cudaFree(h->d.perm); cudaFreeHost(h->h_in); cudaFreeHost(h->h_out); cudaFreeHost(h->h_mask); cudaFree(h->d_in); cudaFree(h->d_out); cudaFree(h->d_mask);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   for (int i = 0; i < 3; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   delete h;
@@ -274,21 +286,16 @@ extern "C" int d3il_get_profile(const d3il_env* h, double out_ms[2], long long* 
 // Scheduler + IK reference + env step: three launches on one stream, the last one with programmatic stream serialization
 // so that it overlaps k_ik (per-tick hand-off through ik_flags).  If the driver serialises them anyway the result is the same.
 static cudaError_t launch_step(d3il_env* h, cudaStream_t s, const float* action, int n_ticks, int gym, float* obs, float* reward, uint8_t* done, float* info, cudaEvent_t after_ik = nullptr) {
-  h->launch_id = (h->launch_id + 1) & 0xffffff;
-  // the release flags are monotonic (launch_id * 64 + tick + 1): when the id wraps they restart from zero, in stream order
-  // (every earlier k_env has finished by then), otherwise k_env would see stale larger values and stop waiting for k_ik
-  if (h->launch_id == 0) { cudaError_t e = cudaMemsetAsync(h->d.ik_flags, 0, (size_t)h->n_ik_flags * sizeof(int), s); if (e != cudaSuccess) return e; }
-  const int base = h->launch_id * 64;
 #ifdef D3IL_DIAG
   static const bool no_pdl = getenv("D3IL_NO_PDL") != nullptr;      // diagnosis build only: serialise the kernels
 #else
   const bool no_pdl = false;
 #endif
   k_sched<<<1, 1024, 0, s>>>(h->d);
-  k_ik<<<h->n_ik_blocks, IK_THREADS, IK_SMEM_BYTES, s>>>(h->d, action, n_ticks, gym, base, h->m.ctrl_kind, h->m.act_dim);
+  k_ik<<<h->n_ik_blocks, IK_THREADS, IK_SMEM_BYTES, s>>>(h->d, action, n_ticks, gym, h->m.ctrl_kind, h->m.act_dim);
   h->launches += 3;
   if (after_ik) cudaEventRecord(after_ik, s);        // completes when k_ik has finished (k_env may already be running: PDL)
-  return d3il_launch_env(h->d, h->m.maxdim, h->n_single, n_ticks, gym, base, action, obs, reward, done, info, h->smem_bytes, s, !no_pdl);
+  return d3il_launch_env(h->d, h->m.maxdim, h->n_single, n_ticks, gym, action, obs, reward, done, info, h->smem_bytes, s, !no_pdl);
 }
 
 extern "C" int d3il_reset(d3il_env* h, const float* ctx, const uint8_t* mask, float* obs, void* stream) {

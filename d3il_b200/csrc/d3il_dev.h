@@ -37,14 +37,17 @@ struct DevCtx {
   int epc;                // envs (warps) per CTA: ENVS_PER_CTA unless the scene's workspace needs more shared memory per env
   DevIk ik;
   float* traj;            // [ticks][21][n]
-  int* ik_flags;          // [ceil(n / IK_FLAG_ENVS)] ticks published by each k_ik warp (monotonic: launch_id * 64 + tick + 1)
+  int* ik_flags;          // [n_ik_flags] ticks published by each k_ik warp (monotonic: launch number * 64 + tick + 1)
+  int* launch_no;         // device-resident launch number, advanced by k_sched: no kernel argument changes from step to step, so a
+                          // whole env step (and the policy in front of it) can be captured in a CUDA graph and replayed
+  int n_ik_flags;
   int* perm;              // [n] env order of this step's k_env groups: most expensive envs (last step's Newton iterations) first
   float tol; int max_iter;
 };
 
 // host-side launchers of the kernels that live in d3il_kernels_env.cu
 cudaError_t d3il_env_kernels_configure(size_t smem_bytes);
-cudaError_t d3il_launch_env(const DevCtx& c, int maxdim, int n_single, int n_ticks, int gym, int flag_base, const float* action, float* obs, float* reward, uint8_t* done, float* info,
+cudaError_t d3il_launch_env(const DevCtx& c, int maxdim, int n_single, int n_ticks, int gym, const float* action, float* obs, float* reward, uint8_t* done, float* info,
                             size_t smem_bytes, cudaStream_t s, bool programmatic);
 void d3il_launch_reset(const DevCtx& c, const float* ctx, const uint8_t* mask, float* obs, size_t smem_bytes, cudaStream_t s);
 void d3il_launch_robot_state(const DevCtx& c, float* tcp, cudaStream_t s);

@@ -29,7 +29,7 @@ __device__ __forceinline__ void stage_model(Model* sm, const Model* gm, int byte
 // ptxas go to 146 and override -maxrregcount: at 125 registers the second CTA waited for k_ik to leave.)
 template <int MD>
 __global__ void __maxnreg__(120)
-k_env(DevCtx c, int n_single, int n_ticks, int gym, int flag_base, const float* __restrict__ action, float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ done, float* __restrict__ info) {
+k_env(DevCtx c, int n_single, int n_ticks, int gym, const float* __restrict__ action, float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ done, float* __restrict__ info) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TL_BEGIN(2, blockIdx.x);
   Model* sm = (Model*)smem_raw;
@@ -42,6 +42,7 @@ k_env(DevCtx c, int n_single, int n_ticks, int gym, int flag_base, const float* 
   // CTA composition: the first n_single CTAs carry ONE env each (the most expensive envs of the cost-sorted order run
   // alone, at their own pace, and start first); the others carry ENVS_PER_CTA envs.  Spare warps of a single-env CTA
   // exit here; the phase barriers count only the participating threads.
+  const int flag_base = *(volatile const int*)c.launch_no * 64;      // written by k_sched, which completed before k_ik (and hence this kernel) could start
   const int single = (int)blockIdx.x < n_single;
   const int cnt = single ? 1 : c.epc;
   const int pos0 = single ? (int)blockIdx.x : n_single + ((int)blockIdx.x - n_single) * c.epc;
@@ -136,7 +137,7 @@ cudaError_t d3il_env_kernels_configure(size_t smem_bytes) {
   return cudaFuncSetAttribute(k_reset, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
-cudaError_t d3il_launch_env(const DevCtx& c, int maxdim, int n_single, int n_ticks, int gym, int flag_base, const float* action, float* obs, float* reward, uint8_t* done, float* info,
+cudaError_t d3il_launch_env(const DevCtx& c, int maxdim, int n_single, int n_ticks, int gym, const float* action, float* obs, float* reward, uint8_t* done, float* info,
                             size_t smem_bytes, cudaStream_t s, bool programmatic) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(d3il_env_grid(c, n_single)); cfg.blockDim = dim3(c.epc * G_LANES); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = s;
@@ -144,8 +145,8 @@ cudaError_t d3il_launch_env(const DevCtx& c, int maxdim, int n_single, int n_tic
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = programmatic ? 1 : 0;
-  if (maxdim == 4) return cudaLaunchKernelEx(&cfg, k_env<4>, c, n_single, n_ticks, gym, flag_base, action, obs, reward, done, info);
-  return cudaLaunchKernelEx(&cfg, k_env<3>, c, n_single, n_ticks, gym, flag_base, action, obs, reward, done, info);
+  if (maxdim == 4) return cudaLaunchKernelEx(&cfg, k_env<4>, c, n_single, n_ticks, gym, action, obs, reward, done, info);
+  return cudaLaunchKernelEx(&cfg, k_env<3>, c, n_single, n_ticks, gym, action, obs, reward, done, info);
 }
 
 void d3il_launch_reset(const DevCtx& c, const float* ctx, const uint8_t* mask, float* obs, size_t smem_bytes, cudaStream_t s) {

@@ -39,7 +39,7 @@ class Aligning_Sim(BaseSim):
         items = np.stack(np.meshgrid(np.arange(self.n_contexts), np.arange(self.n_trajectories_per_context), indexing="ij"), -1).reshape(-1, 2)
         rank, world = self.dist_info()
         lo, hi = self.shard_range(n_items, rank, world)
-        rows = self.gather_rows(self.eval_agent(agent, items[lo:hi]), n_items).cpu()
+        rows = self.gather_rows(self.eval_agent(agent, items[lo:hi]), n_items)          # result rows and the metrics below stay on the device; only scalars and the returned tensors come back
         shape = (self.n_contexts, self.n_trajectories_per_context)
         mode_encoding, successes, mean_distance = (rows[:, k].reshape(shape).clone() for k in range(3))
         n_modes = 2
@@ -53,4 +53,4 @@ class Aligning_Sim(BaseSim):
         print(f"Mean Distance {mean_distance.mean().item()}")
         print(f"Successrate {success_rate}")
         print(f"entropy {entropy}")
-        return successes, mode_encoding, mean_distance
+        return successes.cpu(), mode_encoding.cpu(), mean_distance.cpu()

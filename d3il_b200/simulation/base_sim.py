@@ -81,6 +81,42 @@ class BaseSim(abc.ABC):
         return d.index if d.index is not None else torch.cuda.current_device()
 
 
+STATUS_BITS = {1: "mass matrix not positive definite / NaN state", 2: "contact or constraint-row budget exceeded (contacts dropped)",
+               4: "Newton Hessian not positive definite", 8: "Newton iteration cap reached", 16: "unusable action (set-point held)"}
+
+
+def report_faults(status: torch.Tensor, what: str) -> int:
+    """``status``: per-env OR of the env's fault word (last ``info`` column) over a rollout.  Logs which bits were raised by how
+    many envs; metrics computed from such rollouts are physically suspect and the caller should know.  Returns the count."""
+    n_bad = int((status != 0).sum())
+    if n_bad:
+        bits = {name: int(((status & b) != 0).sum()) for b, name in STATUS_BITS.items() if int(((status & b) != 0).sum())}
+        log.warning("%s: %d of %d env instances raised fault bits during the rollout: %s", what, n_bad, status.numel(), bits)
+    return n_bad
+
+
+@torch.no_grad()
+def episode_loop(env, policy_step, cap: int, sync_every: int = 8):
+    """The lock-step episode loop shared by every ``*_Sim``: ``policy_step(active) -> action`` computes the batch action from the
+    caller's own state (last desired pose, observation), the env steps, and each env's ``info`` row is latched at ITS final step.
+    The host looks at the device only every ``sync_every`` env steps (``active.any()``), not every step; the fault words are
+    OR-ed over the steps of each env.  Returns (info rows [n, info_dim], status [n] int32)."""
+    n, dev = env.n_envs, env.device
+    rows = torch.zeros(n, env.info_dim, device=dev)
+    status = torch.zeros(n, dtype=torch.int32, device=dev)
+    active = torch.ones(n, dtype=torch.bool, device=dev)
+    for k in range(cap + 1):
+        action = policy_step(active)
+        obs, _, done, info = env.step(action)
+        done = done.bool() | (k >= cap - 1)             # a shorter episode cap than the compiled one (config max_steps_per_episode)
+        rows = torch.where((active & done).unsqueeze(1), info, rows)
+        status |= torch.where(active, info[:, -1].to(torch.int32), torch.zeros_like(status))
+        active = active & ~done
+        if k % sync_every == sync_every - 1 and not bool(active.any()):
+            break
+    return rows, status
+
+
 @torch.no_grad()
 def cartesian_rollout(agent, task: str, contexts: torch.Tensor | None, n: int, dev_index: int, seed: int, n_act: int, max_steps: int | None = None):
     """The env loop shared by the Cartesian-action sims (``pushing_sim.py:55-85``, ``sorting_sim.py:99-136``,
@@ -91,26 +127,25 @@ def cartesian_rollout(agent, task: str, contexts: torch.Tensor | None, n: int, d
     from .agent_adapter import predict_batch
 
     dev = torch.device(f"cuda:{dev_index}")
+    if n == 0:                                          # an empty shard (fewer items than ranks) still takes part in the gather
+        from ..scene.blob import load_scene
+        return torch.zeros(0, load_scene(task)[1].header["info_dim"], device=dev)
     env = BatchedEnv(task, n, dev_index)
     torch.manual_seed(seed)
     agent.reset()
-    obs = env.reset(contexts).clone()
+    env.reset(contexts)
     tcp = env.robot_state().clone()
-    des = tcp[:, :n_act].clone()
+    state = {"des": tcp[:, :n_act].clone()}
     tail = torch.cat([tcp[:, n_act:], torch.tensor([0.0, 1.0, 0.0, 0.0], device=dev).repeat(n, 1)], 1)
-    rows = torch.zeros(n, env.info_dim, device=dev)
-    active = torch.ones(n, dtype=torch.bool, device=dev)
-    cap = env.max_steps_per_episode if max_steps is None else min(int(max_steps), env.max_steps_per_episode)
-    for k in range(cap + 1):
-        agent_in = torch.cat([des, obs], 1)
+
+    def policy_step(active):
+        agent_in = torch.cat([state["des"], env.obs], 1)
         delta = predict_batch(agent, agent_in)
-        des = torch.where(active.unsqueeze(1), delta + agent_in[:, :n_act], des)
-        obs_t, _, done, info = env.step(torch.cat([des, tail], 1))
-        obs = obs_t.clone()
-        done = done.bool() | (k >= cap - 1)             # a shorter episode cap than the compiled one (config max_steps_per_episode)
-        rows = torch.where((active & done).unsqueeze(1), info, rows)
-        active = active & ~done
-        if not bool(active.any()):
-            break
+        state["des"] = torch.where(active.unsqueeze(1), delta + agent_in[:, :n_act], state["des"])
+        return torch.cat([state["des"], tail], 1)
+
+    cap = env.max_steps_per_episode if max_steps is None else min(int(max_steps), env.max_steps_per_episode)
+    rows, status = episode_loop(env, policy_step, cap)
+    report_faults(status, task)
     env.close()
     return rows

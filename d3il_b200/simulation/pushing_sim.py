@@ -12,9 +12,7 @@ import os
 import numpy as np
 import torch
 
-from ..batched_env import BatchedEnv
-from .agent_adapter import predict_batch
-from .base_sim import BaseSim, _wandb_log
+from .base_sim import BaseSim, _wandb_log, cartesian_rollout
 from .metrics import mode_entropy
 
 log = logging.getLogger(__name__)
@@ -35,36 +33,12 @@ class Pushing_Sim(BaseSim):
     @torch.no_grad()
     def eval_agent(self, agent, items: np.ndarray):
         """Roll out the (context, rollout) pairs in ``items`` ([n, 2] ints) in lock-step; returns [n, 3] result rows
-        (mode, success, mean_distance) — the batched ``eval_agent`` of ``pushing_sim.py:43-85``."""
+        (mode, success, mean_distance) — the batched ``eval_agent`` of ``pushing_sim.py:43-85`` (agent input = [last desired
+        xy || env obs] :74, delta integrated on the last DESIRED xy :77, z frozen at the reset tcp height :69)."""
         dev_index = self._cuda_index()
-        dev = torch.device(f"cuda:{dev_index}")
-        n = len(items)
-        test_contexts = load_test_contexts()
-        env = BatchedEnv("pushing", n, dev_index)
-        torch.manual_seed(self.seed)
-        agent.reset()
-        ctx = torch.tensor(test_contexts[items[:, 0]], dtype=torch.float32, device=dev)
-        obs = env.reset(ctx).clone()                                   # :63
-        pred_action = env.robot_state().clone()                        # :68  tcp xyz
-        fixed_z = pred_action[:, 2:3].clone()                          # :69
-        quat = torch.tensor([0.0, 1.0, 0.0, 0.0], device=dev).repeat(n, 1)
-        rows = torch.zeros(n, 3, device=dev)
-        active = torch.ones(n, dtype=torch.bool, device=dev)
-        des_xy = pred_action[:, :2].clone()
-        for _ in range(env.max_steps_per_episode + 1):
-            agent_in = torch.cat([des_xy, obs], 1)                     # :74  [des_xy, env_obs]
-            delta = predict_batch(agent, agent_in)                     # :76
-            des_xy = torch.where(active.unsqueeze(1), delta + agent_in[:, :2], des_xy)   # :77 integrate on the last DESIRED xy
-            action = torch.cat([des_xy, fixed_z, quat], 1)             # :79
-            obs_t, _, done, info = env.step(action)                    # :81
-            obs = obs_t.clone()
-            just_done = active & done.bool()
-            rows = torch.where(just_done.unsqueeze(1), torch.stack([info[:, 1], info[:, 0], info[:, 2]], 1), rows)   # :83-85
-            active = active & ~done.bool()
-            if not bool(active.any()):
-                break
-        env.close()
-        return rows
+        ctx = torch.tensor(load_test_contexts()[items[:, 0]], dtype=torch.float32, device=f"cuda:{dev_index}").reshape(len(items), -1)
+        info = cartesian_rollout(agent, "pushing", ctx, len(items), dev_index, self.seed, 2)
+        return torch.stack([info[:, 1], info[:, 0], info[:, 2]], 1)                     # :83-85
 
     def test_agent(self, agent):
         log.info("Starting trained model evaluation")
@@ -73,7 +47,7 @@ class Pushing_Sim(BaseSim):
         rank, world = self.dist_info()
         lo, hi = self.shard_range(n_items, rank, world)
         rows = self.eval_agent(agent, items[lo:hi])
-        rows = self.gather_rows(rows, n_items).cpu()
+        rows = self.gather_rows(rows, n_items)          # result rows and the metrics below stay on the device; only scalars and the returned tensors come back
         shape = (self.n_contexts, self.n_trajectories_per_context)
         mode_encoding, successes, mean_distance = (rows[:, k].reshape(shape).clone() for k in range(3))
 
@@ -88,4 +62,4 @@ class Pushing_Sim(BaseSim):
         print(f"Mean Distance {mean_distance.mean().item()}")
         print(f"Successrate {success_rate}")
         print(f"entropy {entropy}")
-        return successes, mode_encoding, mean_distance
+        return successes.cpu(), mode_encoding.cpu(), mean_distance.cpu()

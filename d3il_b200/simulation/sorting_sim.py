@@ -46,7 +46,7 @@ class Sorting_Sim(BaseSim):
         items = np.stack(np.meshgrid(np.arange(self.n_contexts), np.arange(self.n_trajectories_per_context), indexing="ij"), -1).reshape(-1, 2)
         rank, world = self.dist_info()
         lo, hi = self.shard_range(n_items, rank, world)
-        rows = self.gather_rows(self.eval_agent(agent, items[lo:hi]), n_items).cpu()
+        rows = self.gather_rows(self.eval_agent(agent, items[lo:hi]), n_items)          # result rows and the metrics below stay on the device; only scalars and the returned tensors come back
         shape = (self.n_contexts, self.n_trajectories_per_context)
         mode_encoding, successes = rows[:, 0].reshape(shape).clone(), rows[:, 1].reshape(shape).clone()
         success_rate = torch.mean(successes).item()
@@ -59,4 +59,4 @@ class Sorting_Sim(BaseSim):
         print(f"Successrate {success_rate}")
         print(f"entropy {entropy}")
         print(f"KL {KL}")
-        return success_rate, mode_encoding
+        return success_rate, mode_encoding.cpu()

@@ -14,8 +14,8 @@ import torch
 
 from ..batched_env import BatchedEnv
 from .agent_adapter import predict_batch
-from .base_sim import BaseSim, _wandb_log
-from .metrics import mode_kl
+from .base_sim import BaseSim, _wandb_log, episode_loop, report_faults
+from .metrics import mode_kl, stacking_rows
 
 log = logging.getLogger(__name__)
 _DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "data")
@@ -54,36 +54,26 @@ class Stacking_Sim(BaseSim):
         dev_index = self._cuda_index()
         dev = torch.device(f"cuda:{dev_index}")
         n = len(items)
+        if n == 0:
+            return torch.zeros(0, 6, device=dev)
         env = BatchedEnv("stacking", n, dev_index)
         torch.manual_seed(self.seed)
         agent.reset()
-        obs = env.reset(torch.tensor(self.test_contexts[items[:, 0]], dtype=torch.float32, device=dev)).clone()
-        pred_action = env.joint_state().clone()                              # :89 joint positions + gripper width
-        info_rows = torch.zeros(n, env.info_dim, device=dev)
-        active = torch.ones(n, dtype=torch.bool, device=dev)
+        env.reset(torch.tensor(self.test_contexts[items[:, 0]], dtype=torch.float32, device=dev))
+        state = {"act": env.joint_state().clone()}                             # :89 joint positions + gripper width
+
+        def policy_step(active):
+            agent_in = torch.cat([state["act"], env.obs], 1)                    # :99
+            out = predict_batch(agent, agent_in)                                # :103
+            out[:, :7] = out[:, :7] + agent_in[:, :7]                           # :104
+            state["act"] = torch.where(active.unsqueeze(1), out, state["act"])
+            return state["act"]                                                 # :114
+
         cap = min(int(self.max_steps_per_episode), env.max_steps_per_episode)
-        for k in range(cap + 1):
-            agent_in = torch.cat([pred_action, obs], 1)                      # :99
-            out = predict_batch(agent, agent_in)                             # :103
-            out[:, :7] = out[:, :7] + agent_in[:, :7]                        # :104
-            pred_action = torch.where(active.unsqueeze(1), out, pred_action)
-            obs_t, _, done, info = env.step(pred_action)                     # :114
-            obs = obs_t.clone()
-            done = done.bool() | (k >= cap - 1)
-            info_rows = torch.where((active & done).unsqueeze(1), info, info_rows)
-            active = active & ~done
-            if not bool(active.any()):
-                break
+        info_rows, status = episode_loop(env, policy_step, cap)
+        report_faults(status, "stacking")
         env.close()
-        info_rows = info_rows.cpu()
-        rows = torch.zeros(n, 6)
-        for i in range(n):
-            mode = decode_mode(info_rows[i, 1].item(), info_rows[i, 3].item())
-            rows[i, 0] = MODE_3[mode[:3]] if len(mode) > 2 else 0
-            rows[i, 1] = MODE_1[mode[:1]] if len(mode) > 0 else 0
-            rows[i, 2] = MODE_2[mode[:2]] if len(mode) > 1 else 0
-            rows[i, 3], rows[i, 4], rows[i, 5] = info_rows[i, 0], float(len(mode) > 0), float(len(mode) > 1)
-        return rows.to(dev)
+        return stacking_rows(info_rows)
 
     def cal_KL(self, mode_encoding, successes, prior_encoding, n_mode=6):
         _, entropy, KL = mode_kl(mode_encoding, successes, {k: float(prior_encoding[k]) for k in range(n_mode)})
@@ -95,7 +85,7 @@ class Stacking_Sim(BaseSim):
         items = np.stack(np.meshgrid(np.arange(self.n_contexts), np.arange(self.n_trajectories_per_context), indexing="ij"), -1).reshape(-1, 2)
         rank, world = self.dist_info()
         lo, hi = self.shard_range(n_items, rank, world)
-        rows = self.gather_rows(self.eval_agent(agent, items[lo:hi]), n_items).cpu()
+        rows = self.gather_rows(self.eval_agent(agent, items[lo:hi]), n_items)          # result rows and the metrics below stay on the device; only scalars and the returned tensors come back
         shape = (self.n_contexts, self.n_trajectories_per_context)
         mode_encoding, mode_1, mode_2, successes, successes_1, successes_2 = (rows[:, k].reshape(shape).clone() for k in range(6))
         box1, box2, success_rate = successes_1.mean().item(), successes_2.mean().item(), successes.mean().item()
@@ -109,4 +99,4 @@ class Stacking_Sim(BaseSim):
         print(f"Successrate {success_rate}")
         print(f"Successrate_1 {box1}")
         print(f"Successrate_2 {box2}")
-        return successes, mode_encoding
+        return successes.cpu(), mode_encoding.cpu()

@@ -24,7 +24,7 @@ Emu* emu_create(const void* blob, size_t n) {
   memset(&e->ik, 0, sizeof(e->ik));
   e->vwarm = 0;
   e->tol = sizeof(real) == 4 ? (real)1e-6 : (real)1e-10;
-  e->max_iter = sizeof(real) == 4 ? 24 : 100;
+  e->max_iter = sizeof(real) == 4 ? 32 : 100;
   return e;
 }
 void emu_destroy(Emu* e) { delete e; }

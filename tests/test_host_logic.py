@@ -96,7 +96,7 @@ def test_agent_adapter_matches_single_sample_predict():
         def inverse_scale_output(self, y):
             return y * (self.y_std + 1e-12) + self.y_mean
 
-    class Agent:
+    class BC_Agent:                    # dispatch is by class name (agents/bc_agent.py)
         def __init__(self):
             torch.manual_seed(0)
             self.model = torch.nn.Sequential(torch.nn.Linear(10, 32), torch.nn.Mish(), torch.nn.Linear(32, 2))
@@ -112,7 +112,7 @@ def test_agent_adapter_matches_single_sample_predict():
         def reset(self):
             pass
 
-    agent = Agent()
+    agent = BC_Agent()
     obs = torch.randn(17, 10)
     batched = predict_batch(agent, obs)
     looped = np.stack([agent.predict(o.numpy())[0] for o in obs])
@@ -149,6 +149,31 @@ def test_sharding_and_gather_world_size_2():
     assert ranges[0][0] == 0 and ranges[-1][1] == n_items and ranges[0][1] == ranges[1][0]
     for _, _, _, out in res:
         assert np.array_equal(out, expect)
+
+
+def test_shard_ranges_are_balanced_and_an_empty_shard_still_gathers():
+    """ceil-sized shards left trailing ranks empty (9 items on 8 ranks) and an empty rank raised in d3il_create
+    while the others blocked in all_gather.  Ranges are balanced now; with fewer items than ranks the empty rank contributes a
+    [0, k] tensor to the same collective (gloo, world_size 2, ONE item)."""
+    import torch.multiprocessing as mp
+    from d3il_b200.simulation.base_sim import BaseSim
+    for n_items, world in ((9, 8), (37, 2), (64, 8), (5, 8), (0, 4)):
+        rs = [BaseSim.shard_range(n_items, r, world) for r in range(world)]
+        assert rs[0][0] == 0 and rs[-1][1] == n_items and all(a[1] == b[0] for a, b in zip(rs, rs[1:]))
+        sizes = [hi - lo for lo, hi in rs]
+        assert max(sizes) - min(sizes) <= 1 and (min(sizes) >= 1 or n_items < world)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    world, port = 2, 30100 + os.getpid() % 500
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, 1, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted((lo, hi) for _, lo, hi, _ in res) == [(0, 1), (1, 1)]
+    for _, _, _, out in res:
+        assert out.shape == (1, 3) and np.array_equal(out, np.zeros((1, 3), np.float32))
 
 
 def test_mode_kl_matches_reference_loops():
@@ -213,3 +238,91 @@ def test_bench_reference_arm_contract():
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                          capture_output=True, text=True, timeout=120, cwd=root, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_agent_adapter_ddpm_window_and_ema_and_refusals():
+    """DiffusionAgent path (ddpm_agent.py:214-274 restated on a stub): a window of past observations per env (deque, cleared by
+    reset), EMA parameters swapped in for the forward pass and restored afterwards — batched == N independent single-env agents.
+    Agents with per-episode state and no batched path are refused instead of silently sharing one state across envs."""
+    from collections import deque
+    from d3il_b200.simulation.agent_adapter import predict_batch
+
+    class Ema:
+        def __init__(self, params):
+            self.shadow = [p.detach().clone() * 0.5 for p in params]
+            self.saved = None
+            self.swaps = 0
+
+        def store(self, params):
+            self.saved = [p.detach().clone() for p in params]
+
+        def copy_to(self, params):
+            self.swaps += 1
+            for p, s in zip(params, self.shadow):
+                p.data.copy_(s)
+
+        def restore(self, params):
+            for p, s in zip(params, self.saved):
+                p.data.copy_(s)
+
+    class Net(torch.nn.Module):          # deterministic stand-in for the reverse-diffusion sampler: consumes [B, T, obs], returns [B, T, act]
+        def __init__(self):
+            super().__init__()
+            torch.manual_seed(1)
+            self.lin = torch.nn.Linear(6, 2)
+
+        def forward(self, state, goal):
+            return torch.cumsum(self.lin(state), dim=1)          # depends on the WHOLE window
+
+    class Scaler:
+        def scale_input(self, x):
+            return (x * 2.0 - 0.1).float()
+
+        def inverse_scale_output(self, y):
+            return y * 0.01
+
+    class DiffusionAgent:
+        def __init__(self):
+            self.model, self.scaler, self.device = Net(), Scaler(), "cpu"
+            self.window_size, self.use_ema, self.diffusion_kde = 3, True, False
+            self.obs_context = deque(maxlen=self.window_size)
+            self.ema_helper = Ema(list(self.model.parameters()))
+
+        def reset(self):
+            self.obs_context.clear()
+
+        @torch.no_grad()
+        def predict(self, state):                                   # the reference's single-env law
+            st = self.scaler.scale_input(torch.from_numpy(state).float().unsqueeze(0))
+            self.obs_context.append(st)
+            inp = torch.stack(tuple(self.obs_context), dim=1)
+            self.ema_helper.store(self.model.parameters()); self.ema_helper.copy_to(self.model.parameters())
+            pred = self.model(inp, None)[:, -1, :]
+            self.ema_helper.restore(self.model.parameters())
+            return self.scaler.inverse_scale_output(pred).numpy()
+
+    n, steps = 5, 6
+    rng = np.random.default_rng(0)
+    obs_seq = rng.normal(size=(steps, n, 6)).astype(np.float32)
+    batched_agent = DiffusionAgent(); batched_agent.reset()
+    w_before = [p.detach().clone() for p in batched_agent.model.parameters()]
+    singles = [DiffusionAgent() for _ in range(n)]
+    for a in singles:
+        a.reset()
+    for k in range(steps):
+        out = predict_batch(batched_agent, torch.from_numpy(obs_seq[k]))
+        ref = np.stack([singles[i].predict(obs_seq[k, i])[0] for i in range(n)])
+        assert np.allclose(out.numpy(), ref, atol=1e-6), k
+    assert batched_agent.ema_helper.swaps == steps
+    assert all(torch.equal(a, b) for a, b in zip(w_before, batched_agent.model.parameters()))      # training weights restored
+    assert len(batched_agent.obs_context) == 3
+
+    class ACT_Agent:                     # action chunking: per-episode state, no batched law here
+        def __init__(self):
+            self.model, self.scaler, self.action_counter = Net(), Scaler(), 0
+
+        def predict(self, state):
+            return np.zeros((1, 2))
+
+    with pytest.raises(NotImplementedError):
+        predict_batch(ACT_Agent(), torch.zeros(3, 6))
