@@ -84,3 +84,118 @@ def test_trajectory_recorder_matches_dataset_format():
     vel = st["robot"]["des_c_pos"][1:, :2] - st["robot"]["des_c_pos"][:-1, :2]           # the dataset's action definition
     assert np.allclose(vel, [[0.0, 0.005]] * 5, atol=1e-6)
     env.close()
+
+
+def test_reference_eval_loop_runs_unmodified_on_the_gym_shim():
+    """the body of the reference's ``Pushing_Sim.eval_agent`` (simulation/pushing_sim.py:48-85), restated line
+    for line, runs against ``Block_Push_Env`` imported at the reference's own path — and against the same loop on the fp64
+    oracle it yields the same info (mode, success) and the same mean_distance to 2 cm after a contact-rich 90-step push."""
+    import os
+    import sys
+    compat = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "d3il_b200", "compat")
+    sys.path.insert(0, compat)
+    try:
+        from envs.gym_pushing_env.gym_pushing.envs.pushing import Block_Push_Env
+    finally:
+        sys.path.remove(compat)
+    from d3il_b200.scene.blob import load_scene
+    from oracle.oracle import OracleEnv
+
+    raw = np.load(os.path.join(compat, "..", "data", "pushing_test_contexts_raw.npy"))
+    test_contexts = [[r[0:3], r[3:7], r[7:10], r[10:14]] for r in raw]          # test_contexts.pkl: [red_pos, quat, green_pos, quat2]
+
+    class Agent:                       # deterministic stand-in: drives towards the first box, then pushes it in +y for a while
+        def reset(self):
+            self.k = 0
+
+        def predict(self, obs):
+            self.k += 1
+            des, box = obs[:2], obs[4:6]
+            goal = box + np.array([0.0, -0.08]) if self.k < 45 else box + np.array([0.0, 0.05])
+            d = goal - des
+            n = np.linalg.norm(d)
+            return (d / max(n, 1e-9) * min(n, 0.008) * (self.k < 90))[None]
+
+    class OracleShim:                  # the same Gym-shaped surface on the fp64 oracle
+        def __init__(self):
+            self.blob, self.sc = load_scene("pushing")
+
+        def start(self):
+            self.o = OracleEnv(self.blob, self.sc.header)
+
+        def reset(self, random=True, context=None):
+            rows = np.array([[context[0][0], context[0][1], 0.0, *context[1]], [context[2][0], context[2][1], 0.0, *context[3]]])
+            return self.o.reset(rows)
+
+        def robot_state(self):
+            return self.o.robot_state()
+
+        def step(self, a):
+            obs, r, d, info = self.o.step(np.asarray(a, float))
+            return obs, r, d, {"mode": int(info[1]), "success": bool(info[0]), "mean_distance": float(info[2])}
+
+    results = {}
+    for name, env in (("gpu", Block_Push_Env(render=False)), ("oracle", OracleShim())):
+        agent = Agent()
+        env.start()                                                         # pushing_sim.py:50-51
+        out = []
+        for context in (0, 7, 13):                                          # :58
+            for i in range(1):                                              # :59
+                agent.reset()                                               # :61
+                obs = env.reset(random=False, context=test_contexts[context])       # :66
+                pred_action = env.robot_state()                             # :71
+                fixed_z = pred_action[2:]                                   # :72
+                done, steps = False, 0
+                while not done and steps < 100:                             # :75 (bounded here: the stand-in stops acting at step 90)
+                    obs = np.concatenate((pred_action[:2], obs))            # :77
+                    pred_action = agent.predict(obs)                        # :79
+                    pred_action = pred_action[0] + obs[:2]                  # :80
+                    pred_action = np.concatenate((pred_action, fixed_z, [0, 1, 0, 0]), axis=0)      # :82
+                    obs, reward, done, info = env.step(pred_action)         # :84
+                    steps += 1
+                out.append((info["mode"], info["success"], info["mean_distance"], obs.copy()))
+        results[name] = out
+    for g, o in zip(results["gpu"], results["oracle"]):
+        assert g[0] == o[0] and g[1] == o[1]
+        # a point contact pushing a free box is an unstable (yaw-diverging) configuration: closed-loop trajectories of two
+        # precisions separate by millimetres to a centimetre over a 45-step push (cf. test_gpu_protocol.py, protocol iv)
+        assert abs(g[2] - o[2]) < 2e-2
+        assert np.abs(g[3] - o[3])[[0, 1, 2, 3, 5, 6]].max() < 3e-2          # tcp and box positions at the end of the push
+    # the push moved the first box (the loop is contact-rich, not a free-space check)
+    assert abs(results["oracle"][0][3][3] - test_contexts[0][0][1]) > 0.03
+
+
+def test_gym_shim_surface_of_every_env():
+    """start / reset(random=True) / reset(context) / step / robot_state of the six single-env classes at the reference paths."""
+    import os
+    import sys
+    compat = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "d3il_b200", "compat")
+    sys.path.insert(0, compat)
+    try:
+        from envs.gym_aligning_env.gym_aligning.envs.aligning import Robot_Push_Env
+        from envs.gym_avoiding_env.gym_avoiding.envs.avoiding import ObstacleAvoidanceEnv
+        from envs.gym_inserting_env.gym_inserting.envs.gate_insertion import Gate_Insertion_Env
+        from envs.gym_pushing_env.gym_pushing.envs.pushing import Block_Push_Env
+        from envs.gym_sorting_env.gym_sorting.envs.sorting import Sorting_Env
+        from envs.gym_stacking_env.gym_stacking.envs.stacking import CubeStacking_Env
+    finally:
+        sys.path.remove(compat)
+    for cls, kw, act_dim, obs_dim in ((Block_Push_Env, {}, 7, 8), (ObstacleAvoidanceEnv, {}, 7, 2), (Robot_Push_Env, {}, 7, 17),
+                                      (Sorting_Env, {"num_boxes": 4}, 7, 14), (CubeStacking_Env, {}, 8, 12), (Gate_Insertion_Env, {}, 7, 11)):
+        env = cls(render=False, **kw)
+        env.start()
+        obs = env.reset(random=True)                                        # BlockContextManager.sample()
+        assert obs.shape == (obs_dim,) and np.isfinite(obs).all()
+        ctx = env.manager.sample()
+        obs2 = env.reset(random=False, context=ctx) if cls is not ObstacleAvoidanceEnv else env.reset()
+        rs = env.robot_state()
+        if act_dim == 8:
+            a = np.concatenate([rs[0][:7], [0.08]])
+            assert rs[0].shape == (8,)
+        else:
+            a = np.concatenate([rs, [0, 1, 0, 0]])
+            assert np.allclose(env.robot.current_c_pos, rs)
+        obs3, rew, done, info = env.step(a)
+        assert obs3.shape == (obs_dim,) and np.isfinite(obs3).all() and isinstance(done, bool)
+        assert env._status == 0
+        env.close()
