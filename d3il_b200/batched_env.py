@@ -28,7 +28,10 @@ class BatchedEnv:
         self.scene = scene
         self._L = _lib.lib()
         h = C.c_void_p()
-        _lib.check(self._L.d3il_create(C.byref(h), blob, len(blob), self.n_envs, dev.index or 0), "d3il_create")
+        if dev.index is None:                   # plain "cuda": the CURRENT device, not device 0 (the output tensors below live there too)
+            dev = torch.device("cuda", torch.cuda.current_device())
+            self.device = dev
+        _lib.check(self._L.d3il_create(C.byref(h), blob, len(blob), self.n_envs, dev.index), "d3il_create")
         self._h = h
         dims = (C.c_int32 * 8)()
         _lib.check(self._L.d3il_dims(self._h, dims), "d3il_dims")
@@ -89,6 +92,14 @@ class BatchedEnv:
         """[n_envs, 8]: joint positions + gripper width (``CubeStacking_Env.robot_state``, stacking.py:218-226)."""
         _lib.check(self._L.d3il_joint_state(self._h, C.c_void_p(self.joints.data_ptr()), self._stream()), "d3il_joint_state")
         return self.joints
+
+    def robot_kinematics(self) -> torch.Tensor:
+        """[n_envs, 22]: tcp pos (3) + quat (4), joint positions (7), joint velocities (7), gripper width — the robot fields of the
+        reference's dataset pickles (``MjRobot.receiveState``, MjRobot.py:133-184)."""
+        if not hasattr(self, "_kin"):
+            self._kin = torch.zeros(self.n_envs, 22, device=self.device)
+        _lib.check(self._L.d3il_robot_kinematics(self._h, C.c_void_p(self._kin.data_ptr()), self._stream()), "d3il_robot_kinematics")
+        return self._kin
 
     def object_poses(self) -> torch.Tensor:
         """[n_envs, n_obj, 7] xyz + quat wxyz of the free objects (``Scene.get_obj_pos`` / ``get_obj_quat``)."""

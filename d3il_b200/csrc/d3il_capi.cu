@@ -359,6 +359,15 @@ extern "C" int d3il_joint_state(d3il_env* h, float* j8, void* stream) {
   return 0;
 }
 
+extern "C" int d3il_robot_kinematics(d3il_env* h, float* out22, void* stream) {
+  if (!h || !out22) { g_err = "d3il_robot_kinematics: null argument"; return -1; }
+  CK(cudaSetDevice(h->device));
+  d3il_launch_robot_kinematics(h->d, out22, (cudaStream_t)stream);
+  h->launches += 1;
+  CK(cudaGetLastError());
+  return 0;
+}
+
 extern "C" int d3il_object_poses(d3il_env* h, float* out, void* stream) {
   if (!h || !out) { g_err = "d3il_object_poses: null argument"; return -1; }
   CK(cudaSetDevice(h->device));

@@ -52,6 +52,7 @@ cudaError_t d3il_launch_env(const DevCtx& c, int maxdim, int n_single, int n_tic
 void d3il_launch_reset(const DevCtx& c, const float* ctx, const uint8_t* mask, float* obs, size_t smem_bytes, cudaStream_t s);
 void d3il_launch_robot_state(const DevCtx& c, float* tcp, cudaStream_t s);
 void d3il_launch_joint_state(const DevCtx& c, float* j8, cudaStream_t s);
+void d3il_launch_robot_kinematics(const DevCtx& c, float* out22, cudaStream_t s);
 void d3il_launch_object_poses(const DevCtx& c, int nobj, float* out, cudaStream_t s);
 int d3il_env_grid(const DevCtx& c, int n_single);
 

@@ -173,6 +173,16 @@ __global__ void k_object_poses(DevCtx c, int nobj, float* __restrict__ out) {
 void d3il_launch_object_poses(const DevCtx& c, int nobj, float* out, cudaStream_t s) {
   if (nobj > 0) k_object_poses<<<(c.n * nobj * 7 + 255) / 256, 256, 0, s>>>(c, nobj, out);
 }
+__global__ void k_robot_kinematics(DevCtx c, float* __restrict__ out) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= c.n) return;
+  const float* row = c.state + (size_t)e * c.row;
+  float* o = out + (size_t)e * 22;
+  for (int k = 0; k < 7; k++) o[k] = row[c.lay.tcp + k];
+  for (int k = 0; k < 7; k++) { o[7 + k] = (float)((double)row[c.lay.qpos + k] + (double)row[c.lay.qlo + k]); o[14 + k] = row[c.lay.qvel + k]; }
+  o[21] = row[c.lay.qpos + 7] + row[c.lay.qpos + 8];
+}
+void d3il_launch_robot_kinematics(const DevCtx& c, float* out, cudaStream_t s) { k_robot_kinematics<<<(c.n + 127) / 128, 128, 0, s>>>(c, out); }
 void d3il_launch_joint_state(const DevCtx& c, float* j8, cudaStream_t s) { k_joint_state<<<(c.n + 127) / 128, 128, 0, s>>>(c, j8); }
 
 #ifdef D3IL_PHASE_TIMING

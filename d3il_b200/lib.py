@@ -19,7 +19,7 @@ DIM_NAMES = ("obs", "act", "ctx", "info", "state", "n_envs", "n_substeps", "max_
 EXPORTS = (
     "d3il_create", "d3il_destroy", "d3il_last_error", "d3il_dims", "d3il_reset", "d3il_step", "d3il_robot_state",
     "d3il_reset_host", "d3il_step_host", "d3il_robot_state_host", "d3il_substep", "d3il_get_state", "d3il_set_state",
-    "d3il_set_solver", "d3il_kernel_launches", "d3il_set_profiling", "d3il_get_profile", "d3il_joint_state", "d3il_joint_state_host", "d3il_object_poses",
+    "d3il_set_solver", "d3il_kernel_launches", "d3il_set_profiling", "d3il_get_profile", "d3il_joint_state", "d3il_joint_state_host", "d3il_object_poses", "d3il_robot_kinematics",
 )
 
 
@@ -53,6 +53,7 @@ def lib():
         L.d3il_joint_state.argtypes = [vp, fp, vp]
         L.d3il_joint_state_host.argtypes = [vp, fp]
         L.d3il_object_poses.argtypes = [vp, fp, vp]
+        L.d3il_robot_kinematics.argtypes = [vp, fp, vp]
         L.d3il_substep.argtypes = [vp, C.c_int, vp]
         L.d3il_get_state.argtypes = [vp, dp, C.c_int]
         L.d3il_set_state.argtypes = [vp, dp, C.c_int]

@@ -57,6 +57,12 @@ int d3il_robot_state(d3il_env* env, float* tcp, void* cu_stream);
  * positions + gripper width, dev [n_envs, 8]. */
 int d3il_joint_state(d3il_env* env, float* j8, void* cu_stream);
 
+/* Replaces the fields of MjRobot.receiveState (sims/mj_beta/MjRobot.py:133-184) the reference's RobotLogger writes into the
+ * dataset pickles (core/logger.py; read back by environments/dataset/stacking_dataset.py:92-104): dev [n_envs, 22] =
+ * current_c_pos (3), current_c_quat (4, wxyz; both one tick stale like the reference's), current_j_pos (7),
+ * current_j_vel (7), gripper_width (1). */
+int d3il_robot_kinematics(d3il_env* env, float* out22, void* cu_stream);
+
 /* Replaces Scene.get_obj_pos / get_obj_quat (MjScene._get_obj_pos_and_quat, sims/mj_beta/MjScene.py:233-247) for every free
  * object of the scene: dev [n_envs, n_obj, 7] = (x, y, z, qw, qx, qy, qz) read from qpos (what the reference's ObjectLogger
  * records for the datasets, core/logger.py). */

@@ -199,3 +199,67 @@ def test_gym_shim_surface_of_every_env():
         assert obs3.shape == (obs_dim,) and np.isfinite(obs3).all() and isinstance(done, bool)
         assert env._status == 0
         env.close()
+
+
+def test_recorder_feeds_stacking_and_aligning_dataset_arithmetic():
+    """Verdict r1 item 9: the Stacking dataset reads des_j_pos / des_j_vel / des_c_pos / des_c_quat / c_pos / c_quat / j_pos /
+    j_vel / gripper_width and the three boxes (stacking_dataset.py:92-130), Aligning reads push-box and target-box
+    (aligning_dataset.py:62-80).  The recorded dicts go through that arithmetic (restated) and the numbers are the env's."""
+    _need_gpu()
+    from d3il_b200.batched_env import BatchedEnv
+    from d3il_b200.simulation.recorder import TrajectoryRecorder, chain_fk
+    from tests.util import task_contexts
+
+    def tan_yaw(quat):                                   # np.tan(quat2euler(q)[:, -1:]) for yaw-only quaternions
+        w, z = quat[:, 0], quat[:, 3]
+        return np.tan(2 * np.arctan2(z, w))[:, None]
+
+    # ---- Stacking (joint-space action)
+    n, T = 3, 8
+    env = BatchedEnv("stacking", n, 0)
+    ctx = task_contexts("stacking")[:n]
+    env.reset(torch.tensor(ctx, dtype=torch.float32, device="cuda"))
+    rec = TrajectoryRecorder(env)
+    act = env.joint_state().clone(); act[:, 7] = 0.08
+    for k in range(T):
+        act[:, 1] += 0.002
+        rec.record(act)
+        obs, _, _, _ = env.step(act)
+    st = rec.env_states()[2]
+    r = st["robot"]
+    for key, shape in (("des_j_pos", (T, 7)), ("des_j_vel", (T, 7)), ("des_c_pos", (T, 3)), ("des_c_quat", (T, 4)), ("c_pos", (T, 3)), ("c_quat", (T, 4)),
+                       ("j_pos", (T, 7)), ("j_vel", (T, 7)), ("gripper_width", (T,))):
+        assert r[key].shape == shape, key
+    robot_gripper = np.expand_dims(r["gripper_width"], -1)                             # stacking_dataset.py:104
+    boxes = [np.concatenate((st[b]["pos"], tan_yaw(st[b]["quat"])), -1) for b in ("red-box", "green-box", "blue-box")]
+    input_state = np.concatenate((r["des_j_pos"], robot_gripper, *boxes), axis=-1)     # :126-127
+    vel_state = r["des_j_pos"][1:] - r["des_j_pos"][:-1]                               # :132
+    action = np.concatenate((vel_state, robot_gripper[1:]), axis=-1)                   # :137
+    assert input_state.shape == (T, 20) and action.shape == (T - 1, 8)
+    assert np.allclose(vel_state[:, 1], 0.002, atol=1e-6) and np.allclose(np.delete(vel_state, 1, 1), 0, atol=1e-7)
+    assert np.allclose(input_state[-1, 8:20], obs[2].cpu().numpy(), atol=2e-3)         # the env's own observation one step later: boxes at rest
+    # the commanded Cartesian pose is the FK of the commanded joints; the measured one follows it (tool pointing down)
+    assert np.abs(r["des_c_pos"][-1] - r["c_pos"][-1]).max() < 1.5e-2 and abs(abs(r["c_quat"][-1] @ r["des_c_quat"][-1]) - 1) < 1e-3
+    assert np.allclose(r["j_pos"][-1], r["des_j_pos"][-2], atol=1.5e-2) and abs(r["gripper_width"][-1] - 0.08) < 2e-3      # joint PD lags the ramp by a few steps
+    p0, q0 = chain_fk(np.asarray(env.scene.ctrl, np.float64), np.array([0, -0.043619, 0, -2.188421, 0, 2.149904, 0.785398]))
+    assert np.allclose(p0, [0.525, 0.0, 0.3015], atol=2e-3) and abs(abs(q0 @ [0, 1, 0, 0]) - 1) < 1e-4      # SURVEY §8c: Stacking start pose
+    env.close()
+
+    # ---- Aligning (target pose per context)
+    env = BatchedEnv("aligning", n, 0)
+    ctx = task_contexts("aligning")[:n]
+    env.reset(torch.tensor(ctx, dtype=torch.float32, device="cuda"))
+    rec = TrajectoryRecorder(env)
+    des = torch.cat([env.robot_state().clone(), torch.tensor([0.0, 1.0, 0.0, 0.0], device="cuda").repeat(n, 1)], 1)
+    for k in range(5):
+        des[:, 2] -= 0.004
+        rec.record(des)
+        env.step(des)
+    st = rec.env_states()[1]
+    input_state = np.concatenate((st["robot"]["des_c_pos"], st["robot"]["c_pos"], st["push-box"]["pos"], st["push-box"]["quat"],
+                                  st["target-box"]["pos"], st["target-box"]["quat"]), axis=-1)            # aligning_dataset.py:77
+    vel_state = st["robot"]["des_c_pos"][1:] - st["robot"]["des_c_pos"][:-1]                               # :79
+    assert input_state.shape == (5, 20) and np.allclose(vel_state, [[0, 0, -0.004]] * 4, atol=1e-6)
+    assert np.allclose(st["target-box"]["pos"][0], ctx[1, 1, :3], atol=1e-6) and np.allclose(st["target-box"]["quat"][0], ctx[1, 1, 3:], atol=1e-6)
+    assert np.allclose(st["push-box"]["pos"][0, :2], ctx[1, 0, :2], atol=1e-3)
+    env.close()
