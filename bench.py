@@ -138,7 +138,8 @@ def run_reference(args):
 # Facts taken from committed ncu captures (profiles/): dram__bytes_read.sum + dram__bytes_write.sum and smsp__inst_executed.sum of
 # ONE k_env launch at the workload's default size.  None / absent = not captured for that workload.
 NCU_FACTS = {
-    "pushing": {"dram_bytes": 38.1e6, "warp_inst_per_env_step": 2665352472 / 4096, "source": "profiles/r1_summary.md (k_env<3>, 4096 envs, one launch)"},
+    "pushing": {"dram_bytes": 29.790720e6 + 17.644032e6, "warp_inst_per_env_step": 2204490177 / 4096,
+                "source": "profiles/r2_summary.md (k_env<3>, 4096 envs, one launch, ncu --set full: cold caches, so the 12 MB set-point hand-off that stays in L2 in steady state is counted as DRAM traffic)"},
 }
 
 

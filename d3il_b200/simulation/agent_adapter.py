@@ -35,6 +35,19 @@ def _kind(agent) -> str | None:
     return None
 
 
+def graph_safe(agent) -> bool:
+    """True when ``predict_batch(agent, .)`` is pure tensor code with no Python-side state between calls, i.e. the rollout body can
+    be captured in a CUDA graph: agents that say so (``graph_safe = True``: the synthetic policies), the BC path, and the
+    diffusion path without an observation window (the deque of past observations is Python state a graph replay would skip)."""
+    if getattr(agent, "graph_safe", None) is not None:
+        return bool(agent.graph_safe)
+    if hasattr(agent, "predict_batch"):
+        return False
+    kind = _kind(agent)
+    dev = str(getattr(agent, "device", "cuda"))
+    return dev.startswith("cuda") and (kind == "bc" or (kind == "ddpm" and getattr(agent, "window_size", 1) <= 1))
+
+
 @torch.no_grad()
 def predict_batch(agent, obs: torch.Tensor) -> torch.Tensor:
     """obs: [N, obs_dim] float tensor (any device). Returns [N, act_dim] float32 on obs.device."""

@@ -96,35 +96,59 @@ def report_faults(status: torch.Tensor, what: str) -> int:
 
 
 @torch.no_grad()
-def episode_loop(env, policy_step, cap: int, sync_every: int = 8):
+def episode_loop(env, policy_step, cap: int, sync_every: int = 8, graph: bool = False):
     """The lock-step episode loop shared by every ``*_Sim``: ``policy_step(active) -> action`` computes the batch action from the
-    caller's own state (last desired pose, observation), the env steps, and each env's ``info`` row is latched at ITS final step.
-    The host looks at the device only every ``sync_every`` env steps (``active.any()``), not every step; the fault words are
-    OR-ed over the steps of each env.  Returns (info rows [n, info_dim], status [n] int32)."""
+    caller's own state (last desired pose, observation; updated IN PLACE), the env steps, and each env's ``info`` row is latched
+    at ITS final step.  The host looks at the device only every ``sync_every`` env steps (``active.any()``), not every step; the
+    fault words are OR-ed over the steps of each env.
+
+    ``graph=True`` (policies whose batched forward is pure tensor code, ``agent_adapter.graph_safe``): after two eager steps
+    the body [policy -> env step -> bookkeeping] is captured once in a CUDA graph and replayed — one launch per env step
+    instead of ~25 kernel launches plus the Python between them (the env step's launch number lives on the device, so nothing in
+    the graph changes from step to step).  Returns (info rows [n, info_dim], status [n] int32)."""
     n, dev = env.n_envs, env.device
     rows = torch.zeros(n, env.info_dim, device=dev)
     status = torch.zeros(n, dtype=torch.int32, device=dev)
     active = torch.ones(n, dtype=torch.bool, device=dev)
-    for k in range(cap + 1):
+    step_no = torch.zeros((), dtype=torch.long, device=dev)
+
+    def body():
         action = policy_step(active)
         obs, _, done, info = env.step(action)
-        done = done.bool() | (k >= cap - 1)             # a shorter episode cap than the compiled one (config max_steps_per_episode)
-        rows = torch.where((active & done).unsqueeze(1), info, rows)
-        status |= torch.where(active, info[:, -1].to(torch.int32), torch.zeros_like(status))
-        active = active & ~done
+        step_no.add_(1)
+        fin = active & (done.bool() | (step_no >= cap))         # a shorter episode cap than the compiled one (config max_steps_per_episode)
+        rows.copy_(torch.where(fin.unsqueeze(1), info, rows))
+        status.bitwise_or_(torch.where(active, info[:, -1].to(torch.int32), torch.zeros_like(status)))
+        active.logical_and_(~fin)
+
+    run, k0 = body, 0
+    if graph and cap > 4:
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            body(); body()                                       # real env steps 1 and 2, on the capture stream
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            body()                                               # captured, not executed
+        run, k0 = g.replay, 2
+    for k in range(k0, cap + 1):
+        run()
         if k % sync_every == sync_every - 1 and not bool(active.any()):
             break
     return rows, status
 
 
 @torch.no_grad()
-def cartesian_rollout(agent, task: str, contexts: torch.Tensor | None, n: int, dev_index: int, seed: int, n_act: int, max_steps: int | None = None):
+def cartesian_rollout(agent, task: str, contexts: torch.Tensor | None, n: int, dev_index: int, seed: int, n_act: int, max_steps: int | None = None,
+                      use_graph: bool | None = None):
     """The env loop shared by the Cartesian-action sims (``pushing_sim.py:55-85``, ``sorting_sim.py:99-136``,
     ``aligning_sim.py:105-120``, ``avoiding_sim.py:45-76``), all (context, rollout) pairs in lock-step:
     agent input = [last DESIRED tcp xy(z) || env obs], policy output = delta integrated on the last desired pose,
     z frozen at the reset tcp height when the action is 2-D.  Returns the ``info`` row of every env at ITS final step."""
     from ..batched_env import BatchedEnv
-    from .agent_adapter import predict_batch
+    from .agent_adapter import graph_safe, predict_batch
 
     dev = torch.device(f"cuda:{dev_index}")
     if n == 0:                                          # an empty shard (fewer items than ranks) still takes part in the gather
@@ -135,17 +159,17 @@ def cartesian_rollout(agent, task: str, contexts: torch.Tensor | None, n: int, d
     agent.reset()
     env.reset(contexts)
     tcp = env.robot_state().clone()
-    state = {"des": tcp[:, :n_act].clone()}
-    tail = torch.cat([tcp[:, n_act:], torch.tensor([0.0, 1.0, 0.0, 0.0], device=dev).repeat(n, 1)], 1)
+    action = torch.cat([tcp, torch.tensor([0.0, 1.0, 0.0, 0.0], device=dev).repeat(n, 1)], 1).contiguous()      # [des xy(z) | frozen z | quat]
+    des = action[:, :n_act]
 
     def policy_step(active):
-        agent_in = torch.cat([state["des"], env.obs], 1)
+        agent_in = torch.cat([des, env.obs], 1)
         delta = predict_batch(agent, agent_in)
-        state["des"] = torch.where(active.unsqueeze(1), delta + agent_in[:, :n_act], state["des"])
-        return torch.cat([state["des"], tail], 1)
+        des.copy_(torch.where(active.unsqueeze(1), delta + agent_in[:, :n_act], des))
+        return action
 
     cap = env.max_steps_per_episode if max_steps is None else min(int(max_steps), env.max_steps_per_episode)
-    rows, status = episode_loop(env, policy_step, cap)
+    rows, status = episode_loop(env, policy_step, cap, graph=graph_safe(agent) if use_graph is None else use_graph)
     report_faults(status, task)
     env.close()
     return rows

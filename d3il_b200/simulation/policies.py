@@ -43,6 +43,8 @@ class ResidualMLP(nn.Module):
 
 
 class SyntheticBCPolicy:
+    graph_safe = True          # pure tensor code: the rollout body can be captured in a CUDA graph
+
     def __init__(self, obs_dim: int, act_dim: int, width: int = 128, n_hidden_layers: int = 6, bound: float = 0.01, device="cuda", seed: int = 0):
         g = torch.random.fork_rng(devices=[])
         with g:
@@ -63,6 +65,8 @@ class SyntheticBCPolicy:
 
 
 class SyntheticDDPMPolicy:
+    graph_safe = True          # pure tensor code (torch.randn on the default CUDA generator is graph-capturable)
+
     def __init__(self, obs_dim: int, act_dim: int, width: int = 256, n_hidden_layers: int = 8, n_timesteps: int = 4, t_dim: int = 8,
                  bound: float = 0.01, device="cuda", seed: int = 0):
         with torch.random.fork_rng(devices=[]):
@@ -84,7 +88,8 @@ class SyntheticDDPMPolicy:
         self.sigma = f(torch.sqrt((beta * (1 - abar_prev) / (1 - abar)).clamp(min=1e-20)))
         half = t_dim // 2
         self.freq = torch.exp(torch.arange(half, device=device) * -(math.log(10000.0) / max(half - 1, 1)))
-        self.gen = torch.Generator(device=device).manual_seed(seed)
+        # noise comes from the DEFAULT CUDA generator (seed it with torch.manual_seed): that one is registered with CUDA graphs, a private
+        # torch.Generator is not ("Attempt to increase offset for a CUDA generator not in capture mode")
 
     def reset(self):
         pass
@@ -93,7 +98,7 @@ class SyntheticDDPMPolicy:
     def predict_batch(self, obs: torch.Tensor) -> torch.Tensor:
         s = obs.to(self.device, torch.float32)
         n = s.shape[0]
-        x = torch.randn(n, self.act_dim, device=self.device, generator=self.gen)
+        x = torch.randn(n, self.act_dim, device=self.device)
         for t in range(self.T - 1, -1, -1):
             ang = t * self.freq
             temb = self.t_mlp(torch.cat([ang.sin(), ang.cos()])[None]).expand(n, -1)
@@ -101,7 +106,7 @@ class SyntheticDDPMPolicy:
             x0 = (self.c_x0_from_xt[t] * x - self.c_x0_from_eps[t] * eps).clamp_(-1.0, 1.0)
             x = self.c_mean_x0[t] * x0 + self.c_mean_xt[t] * x
             if t > 0:
-                x = x + self.sigma[t] * torch.randn(n, self.act_dim, device=self.device, generator=self.gen)
+                x = x + self.sigma[t] * torch.randn(n, self.act_dim, device=self.device)
         return x.clamp_(-1.0, 1.0) * self.bound
 
     def predict(self, obs):

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from ..batched_env import BatchedEnv
-from .agent_adapter import predict_batch
+from .agent_adapter import graph_safe, predict_batch
 from .base_sim import BaseSim, _wandb_log, episode_loop, report_faults
 from .metrics import mode_kl, stacking_rows
 
@@ -60,17 +60,17 @@ class Stacking_Sim(BaseSim):
         torch.manual_seed(self.seed)
         agent.reset()
         env.reset(torch.tensor(self.test_contexts[items[:, 0]], dtype=torch.float32, device=dev))
-        state = {"act": env.joint_state().clone()}                             # :89 joint positions + gripper width
+        act = env.joint_state().clone()                                        # :89 joint positions + gripper width
 
         def policy_step(active):
-            agent_in = torch.cat([state["act"], env.obs], 1)                    # :99
+            agent_in = torch.cat([act, env.obs], 1)                             # :99
             out = predict_batch(agent, agent_in)                                # :103
             out[:, :7] = out[:, :7] + agent_in[:, :7]                           # :104
-            state["act"] = torch.where(active.unsqueeze(1), out, state["act"])
-            return state["act"]                                                 # :114
+            act.copy_(torch.where(active.unsqueeze(1), out, act))
+            return act                                                          # :114
 
         cap = min(int(self.max_steps_per_episode), env.max_steps_per_episode)
-        info_rows, status = episode_loop(env, policy_step, cap)
+        info_rows, status = episode_loop(env, policy_step, cap, graph=graph_safe(agent))
         report_faults(status, "stacking")
         env.close()
         return stacking_rows(info_rows)

@@ -1,4 +1,5 @@
-"""Turn gpurun_out/{launches_r1.csv, prof_kenv_r1.ncu-rep, prof_kik_r1.ncu-rep} into profiles/r1_*.{csv,md} (run here, no GPU)."""
+"""Turn gpurun_out/<sub>/{launches_<tag>.csv, prof_kenv_<tag>.ncu-rep, prof_kik_<tag>.ncu-rep} into profiles/<tag>_*.{csv,md}
+(run in the dev container, no GPU):  python profiles/summarize.py r2 r2prof"""
 import csv
 import os
 import subprocess
@@ -16,7 +17,9 @@ def raw(rep):
 
 
 # ---- launch list
-lp = os.path.join(ROOT, "gpurun_out", "launches_r1.csv")
+TAG = sys.argv[1] if len(sys.argv) > 1 else "r1"
+SUB = sys.argv[2] if len(sys.argv) > 2 else ""
+lp = os.path.join(ROOT, "gpurun_out", SUB, f"launches_{TAG}.csv")
 if os.path.exists(lp):
     rows = [r for r in csv.reader(open(lp)) if len(r) > 5]
     hdr = rows[0]
@@ -29,11 +32,11 @@ if os.path.exists(lp):
         except (ValueError, IndexError):
             pass
     tot = sum(v[1] for v in agg.values())
-    with open(os.path.join(ROOT, "profiles", "r1_launches.csv"), "w") as f:
+    with open(os.path.join(ROOT, "profiles", f"{TAG}_launches.csv"), "w") as f:
         f.write("kernel,launches,total_ms,share\n")
         for k, (n, ms) in sorted(agg.items(), key=lambda x: -x[1][1]):
             f.write(f"{k},{n},{ms:.3f},{ms / tot:.4f}\n")
-    out_md.append("## Launch list (ncu --metrics gpu__time_duration.sum --clock-control none, `python bench.py --steps 12 --warmup 3`)\n")
+    out_md.append("## Launch list (ncu --metrics gpu__time_duration.sum --clock-control none, `python bench.py --steps 12 --warmup 3 --no-graph`, timed-region launches after the pre-roll)\n")
     out_md.append("| kernel | launches | total ms | share |\n|---|---|---|---|")
     for k, (n, ms) in sorted(agg.items(), key=lambda x: -x[1][1])[:12]:
         out_md.append(f"| `{k}` | {n} | {ms:.2f} | {100 * ms / tot:.1f} % |")
@@ -44,8 +47,8 @@ keys = ["gpu__time_duration.sum", "smsp__inst_executed.sum", "smsp__issue_active
         "launch__occupancy_limit_registers", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"]
-for name in ("prof_kenv_r1", "prof_kik_r1"):
-    rep = os.path.join(ROOT, "gpurun_out", name + ".ncu-rep")
+for name in (f"prof_kenv_{TAG}", f"prof_kik_{TAG}"):
+    rep = os.path.join(ROOT, "gpurun_out", SUB, name + ".ncu-rep")
     if not os.path.exists(rep):
         continue
     d = raw(rep)
@@ -61,5 +64,5 @@ for name in ("prof_kenv_r1", "prof_kik_r1"):
     out_md.append("")
     lines = subprocess.run([sys.executable, os.path.join(ROOT, "profiles", "ncu_lines.py"), rep, "25"], capture_output=True, text=True).stdout
     out_md.append("Hottest source lines (warp instructions executed):\n\n```\n" + lines + "```\n")
-open(os.path.join(ROOT, "profiles", "r1_summary.md"), "w").write("# Round-1 ncu summary (B200)\n\n" + "\n".join(out_md))
+open(os.path.join(ROOT, "profiles", f"{TAG}_summary.md"), "w").write(f"# Round {TAG[1:]} ncu summary (B200)\n\n" + "\n".join(out_md))
 print("\n".join(out_md)[:3000])

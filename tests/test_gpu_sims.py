@@ -263,3 +263,21 @@ def test_recorder_feeds_stacking_and_aligning_dataset_arithmetic():
     assert np.allclose(st["target-box"]["pos"][0], ctx[1, 1, :3], atol=1e-6) and np.allclose(st["target-box"]["quat"][0], ctx[1, 1, 3:], atol=1e-6)
     assert np.allclose(st["push-box"]["pos"][0, :2], ctx[1, 0, :2], atol=1e-3)
     env.close()
+
+
+def test_graph_replayed_rollout_equals_eager_rollout():
+    """the rollout body [policy -> env step -> bookkeeping] captured once in a CUDA graph and replayed gives
+    bit-identical result rows to launching it kernel by kernel (the env step carries no host-side per-step argument: its launch
+    number lives on the device), and the loop looks at the device every 8th step only."""
+    _need_gpu()
+    from d3il_b200.simulation.base_sim import cartesian_rollout
+    from d3il_b200.simulation.policies import SyntheticBCPolicy
+    from tests.util import task_contexts
+    n = 24
+    ctx = torch.tensor(task_contexts("pushing")[:n], dtype=torch.float32, device="cuda").reshape(n, -1)
+    out = []
+    for use_graph in (False, True):
+        agent = SyntheticBCPolicy(10, 2, seed=3)
+        out.append(cartesian_rollout(agent, "pushing", ctx, n, 0, seed=0, n_act=2, max_steps=70, use_graph=use_graph).cpu().numpy())
+    assert np.array_equal(out[0], out[1])
+    assert (out[0][:, -1] == 0).all() and (out[0][:, 2] > 0).all()
