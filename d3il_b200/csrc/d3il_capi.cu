@@ -34,7 +34,7 @@ extern "C" const char* d3il_last_error(void) { return g_err.c_str(); }
 struct d3il_env {
   Model m; Lay L;
   DevCtx d;
-  int device, n, max_ticks, n_ik_blocks, n_ik_flags, n_single;
+  int device, n, max_ticks, n_ik_blocks, n_ik_flags, n_free;
   long long launches;
   size_t smem_bytes;
   // pinned + device staging for the *_host calls
@@ -212,8 +212,16 @@ static int create_impl(d3il_env* h, const void* blob, size_t nbytes, int n_envs,
   // envs per CTA: ENVS_PER_CTA (two CTAs per SM for the small scenes), fewer when the per-env workspace is large (Sorting-4/6)
   const size_t model_bytes = d3il_model_bytes(h->m), env_bytes = (size_t)d.ws_stride * sizeof(float);
   d.model_bytes = (int)model_bytes;
-  d.epc = ENVS_PER_CTA;
-  while (d.epc > 1 && model_bytes + d.epc * env_bytes > 227 * 1024) d.epc--;
+  // pick the CTA size that keeps the most env warps resident per SM: at most two CTAs per SM (registers), each CTA's shared
+  // memory + 1 KB of system reserve out of the SM's 228 KB
+  d.epc = 1;
+  { int best = 0;
+    for (int e = ENVS_PER_CTA; e >= 1; e--) {
+      const size_t bytes = model_bytes + (size_t)e * env_bytes;
+      if (bytes > 227 * 1024) continue;
+      const int ctas = (int)((228 * 1024) / (bytes + 1024)) >= 2 ? 2 : 1, warps = ctas * e;
+      if (warps > best) { best = warps; d.epc = e; }
+    } }
   h->smem_bytes = model_bytes + (size_t)d.epc * env_bytes;
 #ifdef D3IL_DIAG
   if (const char* ev = getenv("D3IL_SMEM_PAD_KB")) {      // diagnosis build only: pad the request so fewer CTAs share an SM
@@ -226,11 +234,19 @@ static int create_impl(d3il_env* h, const void* blob, size_t nbytes, int n_envs,
   CK(cudaFuncSetAttribute(k_ik, cudaFuncAttributeMaxDynamicSharedMemorySize, IK_SMEM_BYTES));
   CK(cudaFuncSetAttribute(k_ik, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   CK(cudaFuncSetAttribute(k_sched, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  // the most expensive envs of each step run one per CTA (cost-sorted order, see k_sched / k_env)
-  // (more single-env CTAs shorten the tail CTA but add CTAs; at 4096 envs = 585 x 7 + 1 exactly one is free)
-  h->n_single = (G_LANES == 32 && n_envs >= 512) ? 1 + (n_envs - 1) % d.epc : 0;
+  // the head of each step's cost-sorted order runs in free-running CTAs (see k_sched / k_env): fpc envs each (one warp per SM
+  // sub-partition), enough of them for the ~1.5 % of envs that are in a contact-rich phase at any time, rounded so that
+  // the lock-step CTAs behind them are all full
+  d.fpc = 4; h->n_free = 0;
+  if (G_LANES == 32 && n_envs >= 512) {
+    int want = (n_envs / 64 + d.fpc - 1) / d.fpc;                        // ~1.5 % of the envs
+    if (want > 64) want = 64;
+    h->n_free = want;
+    for (int k = 0; k < d.epc; k++) if ((n_envs - (want + k) * d.fpc) % d.epc == 0) { h->n_free = want + k; break; }
+  }
 #ifdef D3IL_DIAG
-  if (const char* ev = getenv("D3IL_N_SINGLE")) { h->n_single = atoi(ev); if (h->n_single < 0 || h->n_single > n_envs / 2 || G_LANES != 32) h->n_single = 0; }
+  if (const char* ev = getenv("D3IL_FPC")) { d.fpc = atoi(ev); if (d.fpc < 1 || d.fpc > d.epc) d.fpc = 1; }
+  if (const char* ev = getenv("D3IL_N_FREE")) { h->n_free = atoi(ev); if (h->n_free < 0 || h->n_free * d.fpc > n_envs / 2 || G_LANES != 32) h->n_free = 0; }
 #endif
   // staging for the host-buffer entry points
   const Model& m = h->m;
@@ -295,7 +311,7 @@ static cudaError_t launch_step(d3il_env* h, cudaStream_t s, const float* action,
   k_ik<<<h->n_ik_blocks, IK_THREADS, IK_SMEM_BYTES, s>>>(h->d, action, n_ticks, gym, h->m.ctrl_kind, h->m.act_dim);
   h->launches += 3;
   if (after_ik) cudaEventRecord(after_ik, s);        // completes when k_ik has finished (k_env may already be running: PDL)
-  return d3il_launch_env(h->d, h->m.maxdim, h->n_single, n_ticks, gym, action, obs, reward, done, info, h->smem_bytes, s, !no_pdl);
+  return d3il_launch_env(h->d, h->m.maxdim, h->n_free, n_ticks, gym, action, obs, reward, done, info, h->smem_bytes, s, !no_pdl);
 }
 
 extern "C" int d3il_reset(d3il_env* h, const float* ctx, const uint8_t* mask, float* obs, void* stream) {

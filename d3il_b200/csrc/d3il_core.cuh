@@ -38,6 +38,7 @@ template <int G> DEVFN real gmaxr(const Cx&, real x) { return x; }
 template <int G> DEVFN void gsum2(const Cx&, real&, real&) {}
 template <int G> DEVFN int gsumi(const Cx&, int x) { return x; }
 template <int G> DEVFN int gori(const Cx&, int x) { return x; }
+template <int G, int N> DEVFN void gsumn(const Cx&, real*) {}
 template <int G> DEVFN double gsumd(const Cx&, double x) { return x; }
 #else
 #define DEVFN __device__ __forceinline__
@@ -55,6 +56,17 @@ template <int G> DEVFN real gsum(const Cx& cx, real x) {
 template <int G> DEVFN void gsum2(const Cx& cx, real& x, real& y) {
 #pragma unroll
   for (int o = G / 2; o > 0; o >>= 1) { const real a = __shfl_xor_sync(cx.mask, x, o, G), b = __shfl_xor_sync(cx.mask, y, o, G); x += a; y += b; }
+}
+// N all-reduces in one butterfly (the shuffles of the N values pipeline)
+template <int G, int N> DEVFN void gsumn(const Cx& cx, real* v) {
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) {
+    real t[N];
+#pragma unroll
+    for (int k = 0; k < N; k++) t[k] = __shfl_xor_sync(cx.mask, v[k], o, G);
+#pragma unroll
+    for (int k = 0; k < N; k++) v[k] += t[k];
+  }
 }
 template <int G> DEVFN real gmaxr(const Cx& cx, real x) {
 #pragma unroll
@@ -84,6 +96,7 @@ template <int G> DEVFN double gsumd(const Cx& cx, double x) {
 #define D3_MAXQ 56
 #define D3_MAXGEOM 24
 #define D3_MAXPAIR 88
+#define D3_MAXHE 192       // in-block lower-triangle entries (Sorting-6: 45 + 6 x 21 = 171)
 
 #define LANES(i, n) for (int i = cx.lane; i < (n); i += G)
 #ifndef D3IL_LS_TOL
@@ -96,7 +109,7 @@ template <int G> DEVFN double gsumd(const Cx& cx, double x) {
 // CTA-wide "does anybody still need another iteration" vote (plain flag without CTA barriers)
 template <bool CS> DEVFN int cta_any(const Cx& cx, int pred) {
 #if defined(__CUDA_ARCH__)
-  if (CS) {
+  if (CS && cx.cta_threads > 32) {        // a free-running CTA (cta_threads = one warp) votes alone: pred is group-uniform
     int out;
     asm volatile("{ .reg .pred p, q; setp.ne.s32 p, %1, 0; bar.red.or.pred q, 1, %2, p; selp.s32 %0, 1, 0, q; }" : "=r"(out) : "r"(pred), "r"(cx.cta_threads) : "memory");
     return out;
@@ -107,7 +120,7 @@ template <bool CS> DEVFN int cta_any(const Cx& cx, int pred) {
 // Named barrier 1 over the participating threads only (CTAs that carry fewer envs than warps let the spare warps exit)
 template <bool CS> DEVFN void cta_sync(const Cx& cx) {
 #if defined(__CUDA_ARCH__)
-  if (CS) asm volatile("bar.sync 1, %0;" :: "r"(cx.cta_threads) : "memory");
+  if (CS) { if (cx.cta_threads > 32) asm volatile("bar.sync 1, %0;" :: "r"(cx.cta_threads) : "memory"); else __syncwarp(); }
 #endif
 }
 
@@ -122,10 +135,15 @@ static __device__ unsigned long long g_iter_hist[40];      // [0..15] Newton ste
 #ifndef D3IL_PHASE_BLOCK
 #define D3IL_PHASE_BLOCK 0      // which CTA of the cost-sorted grid is sampled (e.g. -DD3IL_PHASE_BLOCK="(gridDim.x/2)" = median cost)
 #endif
-__device__ __forceinline__ bool blockIdx_is0() { return blockIdx.x == D3IL_PHASE_BLOCK && threadIdx.x == 0; }
-__device__ __forceinline__ void count_iter() { g_phase_cycles[20] += 1; }
+#ifdef D3IL_PHASE_LO                                          // a range of CTAs (first warp of each): -DD3IL_PHASE_LO=3 -DD3IL_PHASE_HI=8
+#define D3IL_PHASE_COND (blockIdx.x >= D3IL_PHASE_LO && blockIdx.x < D3IL_PHASE_HI)
+#else
+#define D3IL_PHASE_COND (blockIdx.x == D3IL_PHASE_BLOCK)
+#endif
+__device__ __forceinline__ bool blockIdx_is0() { return D3IL_PHASE_COND && threadIdx.x == 0; }
+__device__ __forceinline__ void count_iter() { atomicAdd(&g_phase_cycles[20], 1ull); }
 __device__ __forceinline__ void count_stat(int k, int v) { atomicAdd(&g_phase_cycles[k], (unsigned long long)v); }
-#define PHASE(k) do { long long t_now = clock64(); if (blockIdx.x == D3IL_PHASE_BLOCK && threadIdx.x == 0) g_phase_cycles[k] += (unsigned long long)(t_now - t_ph); t_ph = t_now; } while (0)
+#define PHASE(k) do { long long t_now = clock64(); if (D3IL_PHASE_COND && threadIdx.x == 0) atomicAdd(&g_phase_cycles[k], (unsigned long long)(t_now - t_ph)); t_ph = t_now; } while (0)
 #else
 #define PHASE_T0() ((void)0)
 #define PHASE(k) ((void)0)
@@ -186,6 +204,10 @@ struct Model {
   unsigned char g_slab[32];               // geom is a static, axis-aligned box (table top, support): eligible for the slab fast path
   int nblk, blk_s[8], blk_e[8];           // the kinematic-tree blocks as a list
   unsigned char d_blk[D3_MAXV];           // block index of each dof
+  short m_row[D3_MAXV];                   // packed mass matrix: M(r, c) = Mbuf[m_row[r] + c] for c inside r's block (blocks stored back to back, row-major squares)
+  short m_base[D3_MAXV];                  // offset of the dof's block in the packed buffer
+  int m_size;                             // floats of the packed buffer = sum of block sizes squared
+  int nhe; unsigned char he_i[D3_MAXHE], he_j[D3_MAXHE];   // all in-block lower-triangle entries (gi >= gj) of the block-diagonal Hessian, as one list
   unsigned diag_blk;                      // bit b: block b of M is diagonal (free body, CoM at its origin, principal axes = body axes)
   int nzp; unsigned char zp_a[8], zp_b[8]; // in-block dof pairs that CRBA never writes (the two fingers): must read as zero
   unsigned char tri_i[300], tri_j[300];   // row-major lower-triangle unranking table for n <= 24
@@ -214,6 +236,7 @@ struct Lay {
   // scratch
   int xpos, xmat, S, I10, Ic, vel, cj, frc, F, M, mdinv, mpiv, H, hdinv, hpiv, bias, qfrc_smooth, qacc_smooth, qacc, qfrc_c, grad, pvec, Ma, tmpv;
   int wood;           // Woodbury scratch: maxdim dof vectors (view 2)
+  int blist;          // per kinematic-tree block: [count, contact ids ...] bytes, stride maxcon + 1 (bit 7: the contact couples two blocks)
   int act, jt, con, ncon_pair, limflag, cflag, J, aref, D, jar, frcE, Jp, hd, hb, etype, econ, total;
 };
 enum { ST_GRIP_SET = 0, ST_GRASP, ST_CTRL_MODE, ST_STEP, ST_TERM, ST_STATUS, ST_OBST, ST_TASK0, ST_TASK1, ST_TASK2, ST_TASK3, ST_COST_ITERS /* Newton iterations of the last env step */, ST_COST_COUPLED /* ticks with a tree-coupling contact */, ST_COST_NCON /* max contacts */, ST_NMISC = 16 };
@@ -230,10 +253,10 @@ static inline void d3il_layout(const Model& m, Lay& L) {
   L.qpos = take(m.nq); L.qlo = take(D3_NROB); L.qvel = take(m.nv); L.warm = take(m.nv); L.bias_prev = take(D3_NROB); L.tcp = take(7); L.misc = take(ST_NMISC); L.extra = take(m.nextra);
   L.n_state = o;
   // live for the whole tick
-  L.M = take(m.nv * m.nv); L.mdinv = take(m.nv); L.mpiv = take(m.nv);
+  L.M = take(m.m_size); L.mdinv = take(m.nv); L.mpiv = take(m.nv);
   L.bias = take(m.nv); L.qfrc_smooth = take(m.nv); L.qacc_smooth = take(m.nv); L.qacc = take(m.nv); L.qfrc_c = take(m.nv);
   L.act = take(D3_NROB); L.jt = take(3 * D3_NARM); L.con = take(D3_CON_W * m.maxcon);
-  L.J = take(m.maxrow * D3_JW); L.aref = take(m.maxrow); L.D = take(m.maxrow); L.hd = take(2 * D3_NROB); L.econ = take(2 * D3_NROB);
+  L.J = take(m.maxrow * D3_JW); L.aref = take(m.maxrow); L.D = take(m.maxrow); L.hd = take(2 * D3_NROB); L.econ = take(2 * D3_NROB); L.blist = take((m.nblk * (m.maxcon + 1) + 3) / 4);
   // region X, two views that are never live together:
   //   view 1 (kinematics, dynamics, collision, constraint assembly)   view 2 (Newton solver, Euler)
   const int x0 = o;
@@ -457,7 +480,7 @@ DEVNI void dynamics(const Cx& cx, const Model& m, const Lay& L, real* w) {
     int a = m.mp_a[e], b = m.mp_b[e];
     real s = 0;
     for (int k = 0; k < 6; k++) s += w[L.S + 6 * b + k] * w[L.F + 6 * a + k];
-    w[L.M + b * nv + a] = s;                                          // upper triangle + diagonal hold M (b <= a)
+    w[L.M + m.m_row[b] + a] = s;                                      // upper triangle + diagonal hold M (b <= a), blocks packed
   }
   LANES(d, nv) {
     int li = m.d_link[d];
@@ -962,6 +985,20 @@ DEVFN int make_constraints(const Cx& cx, const Model& m, const Lay& L, real* w, 
       w[L.aref + row0 + r] = -bb * vel - (r == 0 ? kk * imp * (cc[12] - cc[13]) : 0);
     }
   }
+  // per-block lists of the active contacts that touch the block (bit 7: the contact also touches another block): the Newton
+  // loop's gradient and Hessian assembly walk these instead of scanning every contact for every dof / matrix entry
+  LANES(b, m.nblk) {
+    unsigned char* bl = (unsigned char*)(w + L.blist) + b * (m.maxcon + 1);
+    const int bs = m.blk_s[b], be = m.blk_e[b];
+    int n = 0;
+    for (int c = 0; c < ncon; c++) {
+      const real* cc = w + L.con + D3_CON_W * c;
+      if ((int)cc[19] < 0) continue;
+      const int a0 = (int)cc[20], b0 = (int)cc[22], b1 = (int)cc[23], cpl = b1 > b0;
+      if ((a0 >= bs && a0 < be) || (cpl && b0 >= bs && b0 < be)) bl[1 + n++] = (unsigned char)(c | (cpl ? 0x80 : 0));
+    }
+    bl[0] = (unsigned char)n;
+  }
   gsync<G>(cx);
   return row;
 }
@@ -1157,21 +1194,24 @@ DEVFN real row_bcast(const Cx& cx, const real* v, int src_row) {
   return out;
 #endif
 }
-// upper = true : the input block rows are read from the UPPER triangle (A[j][i], j < i) — the mass matrix as CRBA leaves it;
-// upper = false: from the lower triangle (the assembled Hessian).  diag[] holds the diagonal, diag_add (nullable) is added to it.
+// upper = true : A is the PACKED mass matrix (Model::m_row) and the input block rows are read from its UPPER triangle
+//                (A[j][i], j < i), as CRBA leaves it;
+// upper = false: A is a dense n x n buffer, rows from the lower triangle (the assembled Hessian).  diag[] holds the diagonal, diag_add (nullable) is added to it.
 template <int G, int NS> DEVFN int chol_reg_core(const Cx& cx, real (*a)[D3_MAXB], const int* bs, const int* be, const int* rr, real* myinv);
 template <int G, int NS>
 DEVNI int chol_blocks_reg_slots(const Cx& cx, const Model& m, real* A, int n, bool upper, const real* diag, const real* diag_add, real* dinv) {
   real a[NS][D3_MAXB], myinv[NS];
-  int bs[NS], rr[NS], be[NS];
+  int bs[NS], rr[NS], be[NS], base[NS], st[NS];
 #pragma unroll
   for (int sl = 0; sl < NS; sl++) {
     const int i = sl * G + cx.lane, ii = i < n ? i : n - 1;
     bs[sl] = m.d_bs[ii]; be[sl] = m.d_be[ii]; rr[sl] = i < n ? i - bs[sl] : -1;      // rr < 0: no row in this slot
+    // element (bs + r, bs + c) of the lane's block sits at base + r * st + c: the packed mass matrix, or a dense n x n buffer
+    st[sl] = upper ? be[sl] - bs[sl] : n; base[sl] = upper ? (int)m.m_base[ii] : bs[sl] * (n + 1);
 #pragma unroll
     for (int j = 0; j < D3_MAXB; j++) {
       real v = 0;
-      if (j < rr[sl]) v = upper ? A[(bs[sl] + j) * n + i] : A[i * n + bs[sl] + j];
+      if (j < rr[sl]) v = upper ? A[base[sl] + j * st[sl] + rr[sl]] : A[base[sl] + rr[sl] * st[sl] + j];
       else if (j == rr[sl]) v = diag[i] + (diag_add ? diag_add[i] : (real)0);
       a[sl][j] = v;
     }
@@ -1183,7 +1223,7 @@ DEVNI int chol_blocks_reg_slots(const Cx& cx, const Model& m, real* A, int n, bo
     const int i = sl * G + cx.lane;
     if (rr[sl] < 0) continue;
 #pragma unroll
-    for (int j = 0; j < D3_MAXB; j++) if (j < rr[sl]) A[i * n + bs[sl] + j] = a[sl][j];
+    for (int j = 0; j < D3_MAXB; j++) if (j < rr[sl]) A[base[sl] + rr[sl] * st[sl] + j] = a[sl][j];
     dinv[i] = myinv[sl];
   }
   gsync<G>(cx);
@@ -1202,7 +1242,7 @@ DEVFN int chol_blocks_reg(const Cx& cx, const Model& m, real* A, int n, bool upp
 // Block solve L L^T x = b for the same factor: the lane's row of L (forward sweep) and column of L (backward sweep) are
 // loaded into registers up front, x is register-distributed, every step is one shuffle + one FMA.
 template <int G, int NS>
-DEVNI void chol_blocks_solve_slots(const Cx& cx, const Model& m, const real* A, int n, const real* dinv, real* x) {
+DEVNI void chol_blocks_solve_slots(const Cx& cx, const Model& m, const real* A, int n, bool packed, const real* dinv, real* x) {
   real lrow[NS][D3_MAXB], lcol[NS][D3_MAXB], xr[NS], di[NS], mine[NS];
   int bs[NS], rr[NS], be[NS];
 #pragma unroll
@@ -1210,10 +1250,11 @@ DEVNI void chol_blocks_solve_slots(const Cx& cx, const Model& m, const real* A, 
     const int i = sl * G + cx.lane, ii = i < n ? i : n - 1;
     bs[sl] = m.d_bs[ii]; be[sl] = m.d_be[ii]; rr[sl] = i < n ? i - bs[sl] : -1;
     xr[sl] = i < n ? x[i] : (real)0; di[sl] = dinv[ii];
+    const int st = packed ? be[sl] - bs[sl] : n, base = packed ? (int)m.m_base[ii] : bs[sl] * (n + 1);
 #pragma unroll
     for (int j = 0; j < D3_MAXB; j++) {
-      lrow[sl][j] = j < rr[sl] ? A[i * n + bs[sl] + j] : (real)0;
-      lcol[sl][j] = (rr[sl] >= 0 && j > rr[sl] && bs[sl] + j < be[sl]) ? A[(bs[sl] + j) * n + i] : (real)0;
+      lrow[sl][j] = j < rr[sl] ? A[base + rr[sl] * st + j] : (real)0;
+      lcol[sl][j] = (rr[sl] >= 0 && j > rr[sl] && bs[sl] + j < be[sl]) ? A[base + j * st + rr[sl]] : (real)0;
     }
   }
 #pragma unroll
@@ -1243,14 +1284,59 @@ DEVNI void chol_blocks_solve_slots(const Cx& cx, const Model& m, const real* A, 
   gsync<G>(cx);
 }
 template <int G>
-DEVFN void chol_blocks_solve(const Cx& cx, const Model& m, const real* A, int n, const real* dinv, real* x) {
+DEVFN void chol_blocks_solve(const Cx& cx, const Model& m, const real* A, int n, bool packed, const real* dinv, real* x) {
 #ifdef D3IL_EMU
-  chol_blocks_solve_slots<G, D3_SLOTS(G)>(cx, m, A, n, dinv, x);
+  chol_blocks_solve_slots<G, D3_SLOTS(G)>(cx, m, A, n, packed, dinv, x);
 #else
-  if (n <= G) chol_blocks_solve_slots<G, 1>(cx, m, A, n, dinv, x);
-  else chol_blocks_solve_slots<G, D3_SLOTS(G)>(cx, m, A, n, dinv, x);
+  if (n <= G) chol_blocks_solve_slots<G, 1>(cx, m, A, n, packed, dinv, x);
+  else chol_blocks_solve_slots<G, D3_SLOTS(G)>(cx, m, A, n, packed, dinv, x);
 #endif
 }
+
+#ifndef D3IL_EMU
+// The same block solve for NR right-hand sides at once (X: NR dof vectors, stride n), systems that fit one group (n <= G):
+// the factor's row / column is loaded once and every elimination step is NR independent shuffle + FMA pairs.
+template <int G, int NR>
+DEVNI void chol_blocks_solve_multi(const Cx& cx, const Model& m, const real* A, int n, bool packed, const real* dinv, real* X, int nr) {
+  const int i = cx.lane, ii = i < n ? i : n - 1;
+  const int bs = m.d_bs[ii], be = m.d_be[ii], rr = i < n ? i - bs : -1;
+  const int st = packed ? be - bs : n, base = packed ? (int)m.m_base[ii] : bs * (n + 1);
+  const real di = dinv[ii];
+  real lrow[D3_MAXB], lcol[D3_MAXB], xr[NR], mine[NR];
+#pragma unroll
+  for (int j = 0; j < D3_MAXB; j++) {
+    lrow[j] = j < rr ? A[base + rr * st + j] : (real)0;
+    lcol[j] = (rr >= 0 && j > rr && bs + j < be) ? A[base + j * st + rr] : (real)0;
+  }
+#pragma unroll
+  for (int r = 0; r < NR; r++) xr[r] = (i < n && r < nr) ? X[r * n + i] : (real)0;
+#pragma unroll
+  for (int k = 0; k < D3_MAXB; k++) {
+    const int src = bs + k < be ? bs + k : bs;
+#pragma unroll
+    for (int r = 0; r < NR; r++) mine[r] = xr[r] * di;
+#pragma unroll
+    for (int r = 0; r < NR; r++) {
+      const real xk = __shfl_sync(cx.mask, mine[r], src, G);
+      if (rr == k) xr[r] = mine[r]; else if (rr > k) xr[r] -= lrow[k] * xk;
+    }
+  }
+#pragma unroll
+  for (int k = D3_MAXB - 1; k >= 0; k--) {
+    const int src = bs + k < be ? bs + k : bs;
+#pragma unroll
+    for (int r = 0; r < NR; r++) mine[r] = xr[r] * di;
+#pragma unroll
+    for (int r = 0; r < NR; r++) {
+      const real xk = __shfl_sync(cx.mask, mine[r], src, G);
+      if (rr == k) xr[r] = mine[r]; else if (rr >= 0 && rr < k) xr[r] -= lcol[k] * xk;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < NR; r++) if (i < n && r < nr) X[r * n + i] = xr[r];
+  gsync<G>(cx);
+}
+#endif
 
 // NS = register slots per lane for the distributed vector: one when the system fits the group (n <= G)
 template <int G>
@@ -1266,8 +1352,9 @@ DEVFN void chol_solve_part(const Cx& cx, const Model& m, const real* A, int n, b
 // y_d = sum_k M[d][k] v[k] within the dof's block (M stored in the upper triangle + diagonal of the M buffer)
 DEVFN real mrow_dot(const Model& m, const real* M, int nv, int d, const real* v, const real* vsub) {
   real s = 0;
+  const int rd = m.m_row[d];
   for (int k = m.d_bs[d]; k < m.d_be[d]; k++) {
-    real mk = k >= d ? M[d * nv + k] : M[k * nv + d];
+    real mk = k >= d ? M[rd + k] : M[m.m_row[k] + d];
     s += mk * (vsub ? v[k] - vsub[k] : v[k]);
   }
   return s;
@@ -1318,6 +1405,98 @@ DEVFN int chol_reg_core(const Cx& cx, real (*a)[D3_MAXB], const int* bs, const i
   return bad;
 }
 
+// Exact line search of the Newton step: safeguarded 1-D Newton / false position on phi'(alpha), phi = cost along
+// qacc + alpha p.  Everything a row contributes is linear in alpha before the cone projection, so each lane loads the data
+// of its limit row / contact ONCE into registers (NSL contact slots, NLL limit slots per lane) and an evaluation is
+// arithmetic plus one fused all-reduce — no shared-memory traffic inside the loop.  d0 = phi'(0) (= grad . p),
+// pMa = p . M (a - a_s), pMp = p . M p.  Rows: jar (at alpha = 0) and Jp = J p in the workspace.
+template <int G, int MD, int NSL, int NLL>
+DEVNI real line_search(const Cx& cx, const Model& m, const Lay& L, const real* w, int nlimit, int ncon, real d0, real pMa, real pMp) {
+  real lj0[NLL], ljp[NLL], lDjp[NLL];
+#pragma unroll
+  for (int sl = 0; sl < NLL; sl++) {
+    const int i = sl * G + cx.lane;
+    lj0[sl] = 0; ljp[sl] = 0; lDjp[sl] = 0;
+    if (i < nlimit) { lj0[sl] = w[L.jar + i]; ljp[sl] = w[L.Jp + i]; lDjp[sl] = w[L.D + i] * ljp[sl]; }
+  }
+  real U0[NSL][MD], V[NSL][MD], VV[NSL], A1[NSL], A2[NSL], Dm[NSL], mu[NSL];
+  bool act[NSL];
+#pragma unroll
+  for (int sl = 0; sl < NSL; sl++) {
+    const int c = sl * G + cx.lane;
+    act[sl] = false; VV[sl] = 0; A1[sl] = 0; A2[sl] = 0; Dm[sl] = 0; mu[sl] = 0;
+#pragma unroll
+    for (int j = 0; j < MD; j++) { U0[sl][j] = 0; V[sl][j] = 0; }
+    if (c < ncon) {
+      const real* cc = w + L.con + D3_CON_W * c;
+      const int i = (int)cc[19];
+      if (i >= 0) {
+        act[sl] = true;
+        const tab_t* pr = m.pair + D3_PAIR_W * (int)cc[18];
+        const int dim = MD == 3 ? 3 : (int)cc[15];
+        mu[sl] = cc[14];
+#pragma unroll
+        for (int j = 0; j < MD; j++) {
+          if (j >= dim) continue;
+          const real fj = j == 0 ? mu[sl] : (real)pr[2 + j], ja = w[L.jar + i + j], jp = w[L.Jp + i + j], Dv = w[L.D + i + j];
+          U0[sl][j] = ja * fj; V[sl][j] = jp * fj;
+          if (j > 0) VV[sl] += V[sl][j] * V[sl][j];
+          A1[sl] += Dv * ja * jp; A2[sl] += Dv * jp * jp;
+        }
+        Dm[sl] = w[L.D + i] / maxr((real)1e-15, mu[sl] * mu[sl] * (1 + mu[sl] * mu[sl]));
+      }
+    }
+  }
+  real lo = 0, hi = -1, alpha = 1, dlo = d0, dhi = 0;
+  for (int ls = 0; ls < 20; ls++) {
+    // first and second directional derivatives at jar + alpha Jp
+    real d1p = 0, d2p = 0;
+#pragma unroll
+    for (int sl = 0; sl < NLL; sl++) {
+      const real j = lj0[sl] + alpha * ljp[sl];
+      if (j < 0) { d1p += lDjp[sl] * j; d2p += lDjp[sl] * ljp[sl]; }
+    }
+#pragma unroll
+    for (int sl = 0; sl < NSL; sl++) {
+      if (!act[sl]) continue;
+      real U[MD], UV = 0, T2 = 0;
+#pragma unroll
+      for (int j = 0; j < MD; j++) { U[j] = U0[sl][j] + alpha * V[sl][j]; if (j > 0) { T2 += U[j] * U[j]; UV += U[j] * V[sl][j]; } }
+      const real T = sqrt(T2), N = U[0], mus = mu[sl];
+      if (N >= mus * T || (T <= 0 && N >= 0)) {
+      } else if (mus * N + T <= 0 || (T <= 0 && N < 0)) {
+        d1p += A1[sl] + alpha * A2[sl]; d2p += A2[sl];
+      } else {
+        // s = 0.5 Dm (N - mu T)^2 along the line: dN = V0, dT = (U_t . V_t)/T, d2T = (|V_t|^2 - dT^2)/T
+        const real NmT = N - mus * T, dT = UV / T, d2T = (VV[sl] - dT * dT) / T, dn = V[sl][0] - mus * dT;
+        d1p += Dm[sl] * NmT * dn;
+        d2p += Dm[sl] * (dn * dn - NmT * mus * d2T);
+      }
+    }
+    gsum2<G>(cx, d1p, d2p);
+    const real d1 = d1p + pMa + alpha * pMp, d2 = d2p + pMp;
+#if defined(D3IL_PHASE_TIMING) && defined(__CUDA_ARCH__)
+    if (threadIdx.x == 0 && blockIdx.x < 4096) g_cta_stat[4 * blockIdx.x + 3] += 1;
+    if (blockIdx_is0()) atomicAdd(&g_phase_cycles[18], 1ull);
+#endif
+    if (absr(d1) <= (real)D3IL_LS_TOL * absr(d0)) break;
+    if (d1 < 0) { lo = alpha; dlo = d1; } else { hi = alpha; dhi = d1; }
+    real next = alpha - d1 / d2;
+    if (hi < 0) { if (!(next > lo)) next = 2 * alpha; }
+    else {
+      // bracketed: Newton step unless it hugs an end point (it can cycle across a kink of phi'), then false position
+      const real wd = hi - lo;
+      if (!(next > lo + (real)0.05 * wd && next < hi - (real)0.05 * wd)) {
+        const real sec = lo + wd * (-dlo) / (dhi - dlo);
+        next = clampr(sec, lo + (real)0.05 * wd, hi - (real)0.05 * wd);
+      }
+      if (wd < (real)1e-6 * (1 + hi)) { alpha = next; break; }
+    }
+    alpha = next;
+  }
+  return alpha;
+}
+
 // One contact that couples two trees (the rod pushing a box — the slow envs of every batch) makes H = H_blocks + Jc^T B Jc
 // a rank-3 (rank-4 with torsional friction) update of the block-diagonal Hessian, so by the Woodbury identity
 //     p = y0 - W (I + B S)^-1 B (Jc y0),   y0 = -H_blocks^-1 grad,  W = H_blocks^-1 Jc^T,  S = Jc W :
@@ -1343,32 +1522,40 @@ DEVNI void newton_woodbury(const Cx& cx, const Model& m, const Lay& L, real* w, 
     }
   }
   gsync<G>(cx);
-  for (int p = 0; p < cdim; p++) chol_blocks_solve<G>(cx, m, w + L.H, nv, w + L.hdinv, W + p * nv);
-  // S = Jc W (symmetric), t = Jc y0
+#ifndef D3IL_EMU
+  if (nv <= G) chol_blocks_solve_multi<G, MD>(cx, m, w + L.H, nv, false, w + L.hdinv, W, cdim);
+  else
+#endif
+  for (int p = 0; p < cdim; p++) chol_blocks_solve<G>(cx, m, w + L.H, nv, false, w + L.hdinv, W + p * nv);
+  // S = Jc W (symmetric), t = Jc y0: all partial sums in one pass over the dofs, then ONE interleaved all-reduce
   real S[MD][MD], t[MD], z[MD];
+  {
+    real acc[MD + MD * (MD + 1) / 2];
 #pragma unroll
-  for (int p = 0; p < MD; p++) {
-    t[p] = 0;
-#pragma unroll
-    for (int q = 0; q < MD; q++) S[p][q] = 0;
-  }
-#pragma unroll
-  for (int p = 0; p < MD; p++) {
-    if (p >= cdim) continue;
-    const real* Jr = J + (r0 + p) * D3_JW;
-    real pt = 0, ps[MD];
-#pragma unroll
-    for (int q = 0; q < MD; q++) ps[q] = 0;
+    for (int k = 0; k < MD + MD * (MD + 1) / 2; k++) acc[k] = 0;
     LANES(i, nv) {
-      real jv = 0;
-      if (i >= a0 && i < a1) jv = Jr[i - a0]; else if (i >= b0 && i < b1) jv = Jr[(a1 - a0) + (i - b0)];
-      pt += jv * w[L.pvec + i];
+      const int loc = (i >= a0 && i < a1) ? i - a0 : ((i >= b0 && i < b1) ? (a1 - a0) + (i - b0) : -1);
+      if (loc < 0) continue;
+      const real y0 = w[L.pvec + i];
+      real jv[MD], wq[MD];
 #pragma unroll
-      for (int q = 0; q < MD; q++) if (q >= p && q < cdim) ps[q] += jv * W[q * nv + i];
+      for (int p = 0; p < MD; p++) { jv[p] = p < cdim ? J[(r0 + p) * D3_JW + loc] : (real)0; wq[p] = p < cdim ? W[p * nv + i] : (real)0; }
+      int k = MD;
+#pragma unroll
+      for (int p = 0; p < MD; p++) {
+        acc[p] += jv[p] * y0;
+#pragma unroll
+        for (int q = p; q < MD; q++) acc[k++] += jv[p] * wq[q];
+      }
     }
-    t[p] = gsum<G>(cx, pt);
+    gsumn<G, MD + MD * (MD + 1) / 2>(cx, acc);
+    int k = MD;
 #pragma unroll
-    for (int q = 0; q < MD; q++) if (q >= p && q < cdim) { S[p][q] = gsum<G>(cx, ps[q]); S[q][p] = S[p][q]; }
+    for (int p = 0; p < MD; p++) {
+      t[p] = acc[p];
+#pragma unroll
+      for (int q = p; q < MD; q++) { S[p][q] = acc[k]; S[q][p] = acc[k]; k++; }
+    }
   }
   // C z = B t with C = I + B S (B: the contact's cone Hessian block; rows / columns >= cdim are zero -> z = 0 there)
   const real* Bm = w + L.hb + MD * MD * cplc;
@@ -1464,10 +1651,11 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
     LANES(d, nv) {
       real s = w[L.Ma + d];
       for (int i = 0; i < nlimit; i++) { int sd = (int)w[L.econ + i]; if (sd == d + 1) s -= w[L.frcE + i]; else if (sd == -(d + 1)) s += w[L.frcE + i]; }
-      for (int c = 0; c < ncon; c++) {
-        const real* cc = w + L.con + D3_CON_W * c;
+      const unsigned char* bl = (const unsigned char*)(w + L.blist) + m.d_blk[d] * (m.maxcon + 1);
+      const int nbl = bl[0];
+      for (int k = 0; k < nbl; k++) {
+        const real* cc = w + L.con + D3_CON_W * (bl[1 + k] & 0x7f);
         int i = (int)cc[19];
-        if (i < 0) continue;
         int a0 = (int)cc[20], a1 = (int)cc[21], b0 = (int)cc[22], b1 = (int)cc[23];
         if ((d >= a0 && d < a1) || (d >= b0 && d < b1)) {
           const real* Jr = w + L.J + i * D3_JW + (d < a1 && d >= a0 ? d - a0 : (a1 - a0) + d - b0);
@@ -1506,33 +1694,34 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
     // (A) every in-block entry is owned by one lane, which accumulates M, the limit rows and all contacts that live
     //     inside that block in a register and writes H once: no barriers between contacts.
     if (coupled) { LANES(e, nv * nv) w[L.H + e] = 0; gsync<G>(cx); }
-    for (int b = 0; b < m.nblk; b++) {
-      const int bs = m.blk_s[b], sz = m.blk_e[b] - bs;
-      LANES(t, sz * (sz + 1) / 2) {
-        const int gi = bs + m.tri_i[t], gj = bs + m.tri_j[t];
-        real acc = M[gj * nv + gi];
-        if (gi == gj) for (int i = 0; i < nlimit; i++) { int sd = (int)w[L.econ + i]; if ((sd > 0 ? sd : -sd) - 1 == gi) acc += w[L.hd + i]; }
-        for (int c = 0; c < ncon; c++) {
-          const real* cc = w + L.con + D3_CON_W * c;
-          const int r0 = (int)cc[19], a0 = (int)cc[20], a1 = (int)cc[21];
-          if (r0 < 0 || (int)cc[23] != (int)cc[22] || a0 != bs || gi >= a1) continue;      // gj <= gi < a1
-          const real* Hb = w + L.hb + MD * MD * c;
-          const real *J0 = w + L.J + r0 * D3_JW, *J1 = J0 + D3_JW, *J2 = J1 + D3_JW;
-          const int li = gi - a0, lj = gj - a0;
-          real i0 = J0[li], i1 = J1[li], i2 = J2[li];
-          if (MD == 3) {
-            real t0 = i0 * Hb[0] + i1 * Hb[3] + i2 * Hb[6], t1 = i0 * Hb[1] + i1 * Hb[4] + i2 * Hb[7], t2 = i0 * Hb[2] + i1 * Hb[5] + i2 * Hb[8];
-            acc += t0 * J0[lj] + t1 * J1[lj] + t2 * J2[lj];
-          } else {           // 4 x 4 cone block; the block's row/column 3 is zero for condim-3 contacts
-            const bool d4 = (int)cc[15] == 4;
-            real i3 = d4 ? J2[D3_JW + li] : (real)0, j3 = d4 ? J2[D3_JW + lj] : (real)0;
-            real t0 = i0 * Hb[0] + i1 * Hb[4] + i2 * Hb[8] + i3 * Hb[12], t1 = i0 * Hb[1] + i1 * Hb[5] + i2 * Hb[9] + i3 * Hb[13];
-            real t2 = i0 * Hb[2] + i1 * Hb[6] + i2 * Hb[10] + i3 * Hb[14], t3 = i0 * Hb[3] + i1 * Hb[7] + i2 * Hb[11] + i3 * Hb[15];
-            acc += t0 * J0[lj] + t1 * J1[lj] + t2 * J2[lj] + t3 * j3;
-          }
+    LANES(e, m.nhe) {
+      const int gi = m.he_i[e], gj = m.he_j[e], bs = m.d_bs[gi];
+      real acc = M[m.m_row[gj] + gi];
+      if (gi == gj) for (int i = 0; i < nlimit; i++) { int sd = (int)w[L.econ + i]; if ((sd > 0 ? sd : -sd) - 1 == gi) acc += w[L.hd + i]; }
+      const unsigned char* bl = (const unsigned char*)(w + L.blist) + m.d_blk[gi] * (m.maxcon + 1);
+      const int nbl = bl[0];
+      for (int k = 0; k < nbl; k++) {
+        const int c = bl[1 + k];
+        if (c & 0x80) continue;                                                            // couples two blocks: Woodbury / dense path
+        const real* cc = w + L.con + D3_CON_W * c;
+        const int r0 = (int)cc[19], a1 = (int)cc[21];
+        if (gi >= a1) continue;                                                            // gj <= gi < a1
+        const real* Hb = w + L.hb + MD * MD * c;
+        const real *J0 = w + L.J + r0 * D3_JW, *J1 = J0 + D3_JW, *J2 = J1 + D3_JW;
+        const int li = gi - bs, lj = gj - bs;
+        real i0 = J0[li], i1 = J1[li], i2 = J2[li];
+        if (MD == 3) {
+          real t0 = i0 * Hb[0] + i1 * Hb[3] + i2 * Hb[6], t1 = i0 * Hb[1] + i1 * Hb[4] + i2 * Hb[7], t2 = i0 * Hb[2] + i1 * Hb[5] + i2 * Hb[8];
+          acc += t0 * J0[lj] + t1 * J1[lj] + t2 * J2[lj];
+        } else {           // 4 x 4 cone block; the block's row/column 3 is zero for condim-3 contacts
+          const bool d4 = (int)cc[15] == 4;
+          real i3 = d4 ? J2[D3_JW + li] : (real)0, j3 = d4 ? J2[D3_JW + lj] : (real)0;
+          real t0 = i0 * Hb[0] + i1 * Hb[4] + i2 * Hb[8] + i3 * Hb[12], t1 = i0 * Hb[1] + i1 * Hb[5] + i2 * Hb[9] + i3 * Hb[13];
+          real t2 = i0 * Hb[2] + i1 * Hb[6] + i2 * Hb[10] + i3 * Hb[14], t3 = i0 * Hb[3] + i1 * Hb[7] + i2 * Hb[11] + i3 * Hb[15];
+          acc += t0 * J0[lj] + t1 * J1[lj] + t2 * J2[lj] + t3 * j3;
         }
-        w[L.H + gi * nv + gj] = acc;
       }
+      w[L.H + gi * nv + gj] = acc;
     }
     gsync<G>(cx);
     if (!coupled) {
@@ -1543,7 +1732,7 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
       hfail = chol_blocks_reg<G>(cx, m, w + L.H, nv, false, w + L.hpiv, nullptr, w + L.hdinv);
       PHASE(10);
       if (!hfail) {
-        chol_blocks_solve<G>(cx, m, w + L.H, nv, w + L.hdinv, w + L.pvec);
+        chol_blocks_solve<G>(cx, m, w + L.H, nv, false, w + L.hdinv, w + L.pvec);
         if (ncpl == 1) newton_woodbury<G, MD>(cx, m, L, w, cplc);
       }
     } else {
@@ -1595,61 +1784,11 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
     }
     gsum2<G>(cx, a1s, a2s);
     real pMp = a1s, pMa = a2s, d0 = gsum<G>(cx, a3s);
-    real lo = 0, hi = -1, alpha = 1, dlo = d0, dhi = 0;
-    for (int ls = 0; ls < 20; ls++) {
-      // first and second directional derivatives at jar + alpha Jp (nothing is written: no barrier needed)
-      real d1p = 0, d2p = 0;
-      LANES(i, nlimit) {
-        real j = w[L.jar + i] + alpha * w[L.Jp + i];
-        if (j < 0) { d1p += w[L.D + i] * j * w[L.Jp + i]; d2p += w[L.D + i] * w[L.Jp + i] * w[L.Jp + i]; }
-      }
-      LANES(c, ncon) {
-        const real* cc = w + L.con + D3_CON_W * c;
-        int i = (int)cc[19];
-        if (i < 0) continue;
-        const tab_t* pr = m.pair + D3_PAIR_W * (int)cc[18];
-        const int dim = MD == 3 ? 3 : (int)cc[15];
-        real mu = cc[14], U[MD], V[MD], jl[MD], UV = 0, VV = 0, T2 = 0;
-#pragma unroll
-        for (int j = 0; j < MD; j++) {
-          real fj = j == 0 ? mu : (real)pr[2 + j];
-          jl[j] = j < dim ? w[L.jar + i + j] + alpha * w[L.Jp + i + j] : (real)0;
-          U[j] = jl[j] * fj; V[j] = j < dim ? w[L.Jp + i + j] * fj : (real)0;
-          if (j > 0) { T2 += U[j] * U[j]; UV += U[j] * V[j]; VV += V[j] * V[j]; }
-        }
-        real T = sqrt(T2), N = U[0];
-        if (N >= mu * T || (T <= 0 && N >= 0)) {
-        } else if (mu * N + T <= 0 || (T <= 0 && N < 0)) {
-#pragma unroll
-          for (int j = 0; j < MD; j++) if (j < dim) { real Dv = w[L.D + i + j], jp = w[L.Jp + i + j]; d1p += Dv * jl[j] * jp; d2p += Dv * jp * jp; }
-        } else {
-          // s = 0.5 Dm (N - mu T)^2 along the line: dN = V0, dT = (U_t . V_t)/T, d2T = (|V_t|^2 - dT^2)/T
-          real Dm = w[L.D + i] / maxr((real)1e-15, mu * mu * (1 + mu * mu)), NmT = N - mu * T;
-          real dT = UV / T, d2T = (VV - dT * dT) / T, dn = V[0] - mu * dT;
-          d1p += Dm * NmT * dn;
-          d2p += Dm * (dn * dn - NmT * mu * d2T);
-        }
-      }
-      gsum2<G>(cx, d1p, d2p);
-      real d1 = d1p + pMa + alpha * pMp, d2 = d2p + pMp;
-#if defined(D3IL_PHASE_TIMING) && defined(__CUDA_ARCH__)
-      if (threadIdx.x == 0 && blockIdx.x < 4096) g_cta_stat[4 * blockIdx.x + 3] += 1;
+#ifdef D3IL_EMU
+    const real alpha = line_search<G, MD, 64, 2 * D3_NROB>(cx, m, L, w, nlimit, ncon, d0, pMa, pMp);
+#else
+    const real alpha = m.maxcon <= G ? line_search<G, MD, 1, 1>(cx, m, L, w, nlimit, ncon, d0, pMa, pMp) : line_search<G, MD, 2, 1>(cx, m, L, w, nlimit, ncon, d0, pMa, pMp);
 #endif
-      if (absr(d1) <= (real)D3IL_LS_TOL * absr(d0)) break;
-      if (d1 < 0) { lo = alpha; dlo = d1; } else { hi = alpha; dhi = d1; }
-      real next = alpha - d1 / d2;
-      if (hi < 0) { if (!(next > lo)) next = 2 * alpha; }
-      else {
-        // bracketed: Newton step unless it hugs an end point (it can cycle across a kink of phi'), then false position
-        real wd = hi - lo;
-        if (!(next > lo + (real)0.05 * wd && next < hi - (real)0.05 * wd)) {
-          real sec = lo + wd * (-dlo) / (dhi - dlo);
-          next = clampr(sec, lo + (real)0.05 * wd, hi - (real)0.05 * wd);
-        }
-        if (wd < (real)1e-6 * (1 + hi)) { alpha = next; break; }
-      }
-      alpha = next;
-    }
     // step: everything linear in the iterate moves incrementally (jar = J a - aref, Ma = M (a - a_s)); then the
     // evaluation of the NEXT iteration (cost, forces, cone Hessian blocks) at the new iterate
     LANES(d, nv) { w[L.qacc + d] += alpha * w[L.pvec + d]; w[L.Ma + d] += alpha * w[L.tmpv + d]; }
@@ -1725,7 +1864,7 @@ DEVFN void physics_tick(const Cx& cx, const Model& m, const Lay& L, real* w, con
   }
   PHASE(0);
   cta_sync<CS>(cx);
-  LANES(e, m.nzp) { int a = m.zp_a[e], b = m.zp_b[e]; w[L.M + a * nv + b] = 0; w[L.M + b * nv + a] = 0; }     // in-block pairs CRBA never writes (the two fingers)
+  LANES(e, m.nzp) { int a = m.zp_a[e], b = m.zp_b[e]; w[L.M + m.m_row[a] + b] = 0; w[L.M + m.m_row[b] + a] = 0; }     // in-block pairs CRBA never writes (the two fingers)
   dynamics<G>(cx, m, L, w);
   PHASE(1);
   cta_sync<CS>(cx);
@@ -1739,6 +1878,7 @@ DEVFN void physics_tick(const Cx& cx, const Model& m, const Lay& L, real* w, con
   PHASE(3);
 #ifdef D3IL_PHASE_TIMING
   if (cx.lane == 0) { count_stat(21, coupled); count_stat(22, ncon); count_stat(23, 1); count_stat(19, ne); }
+  if (blockIdx_is0()) { count_stat(17, ncon); count_stat(14, ncpl == 1); count_stat(13, ncpl > 1); count_stat(7, ne); }
 #define D3IL_ITER_HIST 1
 #endif
   cta_sync<CS>(cx);
@@ -1749,12 +1889,12 @@ DEVFN void physics_tick(const Cx& cx, const Model& m, const Lay& L, real* w, con
     real act = d < D3_NROB ? w[L.act + d] : (real)0;
     real f = passive - w[L.bias + d] + act;
     w[L.qfrc_smooth + d] = f; w[L.qacc_smooth + d] = f;
-    w[L.mpiv + d] = w[L.M + d * nv + d];
+    w[L.mpiv + d] = w[L.M + m.m_row[d] + d];
   }
   gsync<G>(cx);
   // chol(M): rows come from the upper triangle (where CRBA wrote M), the factor goes to the strict lower triangle
   if (chol_blocks_reg<G>(cx, m, w + L.M, nv, true, w + L.mpiv, nullptr, w + L.mdinv)) { LANES(z, 1) w[L.misc + ST_STATUS] = (real)(((int)w[L.misc + ST_STATUS]) | D3_STATUS_M_NOT_PD); }
-  chol_blocks_solve<G>(cx, m, w + L.M, nv, w + L.mdinv, w + L.qacc_smooth);
+  chol_blocks_solve<G>(cx, m, w + L.M, nv, true, w + L.mdinv, w + L.qacc_smooth);
   PHASE(4);
   cta_sync<CS>(cx);
   int iters = solve_constraints<G, CS, MD>(cx, m, L, w, ne, nlimit, ncon, ncpl, cplc, tol, max_iter);
@@ -1779,7 +1919,7 @@ DEVFN void physics_tick(const Cx& cx, const Model& m, const Lay& L, real* w, con
   LANES(d, nv) { int li = m.d_link[d]; w[L.hpiv + d] = m.l_jtype[li] == 2 ? (real)0 : h * (real)m.link[D3_LINK_W * li + 25]; }
   gsync<G>(cx);
   chol_blocks_reg<G>(cx, m, w + L.M, nv, true, w + L.mpiv, w + L.hpiv, w + L.mdinv);
-  chol_blocks_solve<G>(cx, m, w + L.M, nv, w + L.mdinv, w + L.tmpv);
+  chol_blocks_solve<G>(cx, m, w + L.M, nv, true, w + L.mdinv, w + L.tmpv);
   LANES(d, nv) w[L.qvel + d] += h * w[L.tmpv + d];
   gsync<G>(cx);
   LANES(i, m.nlink) {

@@ -1,7 +1,7 @@
 // d3il_dev.h — declarations shared by the two CUDA translation units of libd3il.so:
 //   d3il_capi.cu        : C ABI, k_sched, k_ik (fp64 IK reference; compiled with the full register budget)
 //   d3il_kernels_env.cu : k_env<3|4>, k_reset, k_robot_state, k_joint_state, k_object_poses.  k_env is capped at 120
-//                         registers (__maxnreg__; -maxrregcount covers the rest of the unit): two 7-warp CTAs per SM, or one
+//                         registers (__maxnreg__; -maxrregcount covers the rest of the unit): two 8-warp CTAs per SM, or one
 //                         beside a 4-warp k_ik block (see IK_THREADS below and DESIGN.md "IK placement")
 #pragma once
 #include <cuda_runtime.h>
@@ -13,7 +13,8 @@
 #define G_LANES 32          // lanes cooperating on one env (32 = one warp per env; 16 = two envs per warp)
 #endif
 #ifndef ENVS_PER_CTA
-#define ENVS_PER_CTA 7     // 2 CTAs/SM x 7 envs: 4096 envs = 1.98 waves on 148 SMs (13.3 KB of shared memory per env)
+#define ENVS_PER_CTA 8     // 2 CTAs/SM x 8 envs (Pushing: 12.25 KB of shared memory per env with the packed mass matrix): 4096 envs = 512 CTAs
+                           // on 296 slots - 264 start at once beside the 32 k_ik blocks, the other 248 form one second wave
 #endif
 #define CTA_THREADS (G_LANES * ENVS_PER_CTA)
 #ifndef IK_THREADS
@@ -34,6 +35,7 @@ struct DevCtx {
   float* state;           // [n][row]
   int row, n, ws_stride;
   int model_bytes;        // staged prefix of the Model (d3il_model_bytes), multiple of 128
+  int fpc;                // envs per FREE-RUNNING CTA (the head of the cost-sorted order, see k_env)
   int epc;                // envs (warps) per CTA: ENVS_PER_CTA unless the scene's workspace needs more shared memory per env
   DevIk ik;
   float* traj;            // [ticks][21][n]
@@ -47,14 +49,14 @@ struct DevCtx {
 
 // host-side launchers of the kernels that live in d3il_kernels_env.cu
 cudaError_t d3il_env_kernels_configure(size_t smem_bytes);
-cudaError_t d3il_launch_env(const DevCtx& c, int maxdim, int n_single, int n_ticks, int gym, const float* action, float* obs, float* reward, uint8_t* done, float* info,
+cudaError_t d3il_launch_env(const DevCtx& c, int maxdim, int n_free, int n_ticks, int gym, const float* action, float* obs, float* reward, uint8_t* done, float* info,
                             size_t smem_bytes, cudaStream_t s, bool programmatic);
 void d3il_launch_reset(const DevCtx& c, const float* ctx, const uint8_t* mask, float* obs, size_t smem_bytes, cudaStream_t s);
 void d3il_launch_robot_state(const DevCtx& c, float* tcp, cudaStream_t s);
 void d3il_launch_joint_state(const DevCtx& c, float* j8, cudaStream_t s);
 void d3il_launch_robot_kinematics(const DevCtx& c, float* out22, cudaStream_t s);
 void d3il_launch_object_poses(const DevCtx& c, int nobj, float* out, cudaStream_t s);
-int d3il_env_grid(const DevCtx& c, int n_single);
+int d3il_env_grid(const DevCtx& c, int n_free);
 
 #ifdef D3IL_PHASE_TIMING
 int d3il_debug_timeline_env(unsigned long long* out4096x4);     // k_env CTA records (the k_ik ones live in d3il_capi.cu)

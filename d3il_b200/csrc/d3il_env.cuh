@@ -665,7 +665,7 @@ DEVFN void env_reset(const Cx& cx, const Model& m, const Lay& L, real* w, const 
     for (int k = 0; k < 3; k++) w[L.tcp + k] = w[L.xpos + 18 + k] + o[k];
     quat2mat(Rt, tq); mat_mul3(R, w + L.xmat + 54, Rt); mat2quat(w + L.tcp + 3, R);
   }
-  LANES(e, m.nv * m.nv) w[L.M + e] = 0;       // whole buffer once per reset: out-of-block entries stay zero afterwards
+  LANES(e, m.m_size) w[L.M + e] = 0;       // whole buffer once per reset: out-of-block entries stay zero afterwards
   gsync<G>(cx);
   dynamics<G>(cx, m, L, w);
   LANES(k, D3_NROB) w[L.bias_prev + k] = w[L.bias + k];

@@ -29,7 +29,7 @@ __device__ __forceinline__ void stage_model(Model* sm, const Model* gm, int byte
 // ptxas go to 146 and override -maxrregcount: at 125 registers the second CTA waited for k_ik to leave.)
 template <int MD>
 __global__ void __maxnreg__(120)
-k_env(DevCtx c, int n_single, int n_ticks, int gym, const float* __restrict__ action, float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ done, float* __restrict__ info) {
+k_env(DevCtx c, int n_free, int n_ticks, int gym, const float* __restrict__ action, float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ done, float* __restrict__ info) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TL_BEGIN(2, blockIdx.x);
   Model* sm = (Model*)smem_raw;
@@ -39,15 +39,16 @@ k_env(DevCtx c, int n_single, int n_ticks, int gym, const float* __restrict__ ac
   const int warp = threadIdx.x / G_LANES;
   Cx cx; cx.lane = threadIdx.x % G_LANES;
   cx.mask = G_LANES == 32 ? 0xffffffffu : (((1u << G_LANES) - 1u) << (((threadIdx.x & 31) / G_LANES) * G_LANES));
-  // CTA composition: the first n_single CTAs carry ONE env each (the most expensive envs of the cost-sorted order run
-  // alone, at their own pace, and start first); the others carry ENVS_PER_CTA envs.  Spare warps of a single-env CTA
-  // exit here; the phase barriers count only the participating threads.
+  // CTA composition: the first n_free CTAs are FREE-RUNNING: they carry the c.fpc most expensive envs of the cost-sorted order
+  // each, their warps never meet at a CTA barrier (every env advances at its own pace: its time is the sum of its OWN Newton
+  // passes, not of the per-tick maxima over the CTA), and they start first.  The others carry c.epc envs in lock step (phase
+  // barriers, CTA-uniform Newton loop: shared instruction fetch).  Spare warps of a free CTA exit here.
   const int flag_base = *(volatile const int*)c.launch_no * 64;      // written by k_sched, which completed before k_ik (and hence this kernel) could start
-  const int single = (int)blockIdx.x < n_single;
-  const int cnt = single ? 1 : c.epc;
-  const int pos0 = single ? (int)blockIdx.x : n_single + ((int)blockIdx.x - n_single) * c.epc;
+  const int freecta = (int)blockIdx.x < n_free;
+  const int cnt = freecta ? c.fpc : c.epc;
+  const int pos0 = freecta ? (int)blockIdx.x * c.fpc : n_free * c.fpc + ((int)blockIdx.x - n_free) * c.epc;
   if (warp >= cnt) return;
-  cx.cta_threads = cnt * G_LANES;
+  cx.cta_threads = freecta ? G_LANES : cnt * G_LANES;          // cta_sync / cta_any are warp-local when this is one group
   // Groups past the end of the batch shadow the last env (same inputs, same control flow, identical outputs) so that
   // every thread of the CTA reaches the phase barriers inside physics_tick.
   const int e_raw = pos0 + warp;                               // position in this step's cost-sorted order
@@ -117,7 +118,7 @@ __global__ void k_robot_state(DevCtx c, float* __restrict__ tcp) {
 
 
 // ------------------------------------------------------------------------------------------------ host launchers
-int d3il_env_grid(const DevCtx& c, int n_single) { return n_single + (c.n - n_single + c.epc - 1) / c.epc; }
+int d3il_env_grid(const DevCtx& c, int n_free) { return n_free + (c.n - n_free * c.fpc + c.epc - 1) / c.epc; }
 
 cudaError_t d3il_env_kernels_configure(size_t smem_bytes) {
   cudaError_t e;
@@ -137,16 +138,16 @@ cudaError_t d3il_env_kernels_configure(size_t smem_bytes) {
   return cudaFuncSetAttribute(k_reset, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
-cudaError_t d3il_launch_env(const DevCtx& c, int maxdim, int n_single, int n_ticks, int gym, const float* action, float* obs, float* reward, uint8_t* done, float* info,
+cudaError_t d3il_launch_env(const DevCtx& c, int maxdim, int n_free, int n_ticks, int gym, const float* action, float* obs, float* reward, uint8_t* done, float* info,
                             size_t smem_bytes, cudaStream_t s, bool programmatic) {
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(d3il_env_grid(c, n_single)); cfg.blockDim = dim3(c.epc * G_LANES); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = s;
+  cfg.gridDim = dim3(d3il_env_grid(c, n_free)); cfg.blockDim = dim3(c.epc * G_LANES); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = programmatic ? 1 : 0;
-  if (maxdim == 4) return cudaLaunchKernelEx(&cfg, k_env<4>, c, n_single, n_ticks, gym, action, obs, reward, done, info);
-  return cudaLaunchKernelEx(&cfg, k_env<3>, c, n_single, n_ticks, gym, action, obs, reward, done, info);
+  if (maxdim == 4) return cudaLaunchKernelEx(&cfg, k_env<4>, c, n_free, n_ticks, gym, action, obs, reward, done, info);
+  return cudaLaunchKernelEx(&cfg, k_env<3>, c, n_free, n_ticks, gym, action, obs, reward, done, info);
 }
 
 void d3il_launch_reset(const DevCtx& c, const float* ctx, const uint8_t* mask, float* obs, size_t smem_bytes, cudaStream_t s) {
@@ -188,5 +189,11 @@ void d3il_launch_joint_state(const DevCtx& c, float* j8, cudaStream_t s) { k_joi
 #ifdef D3IL_PHASE_TIMING
 int d3il_debug_timeline_env(unsigned long long* out) { return cudaMemcpyFromSymbol(out, g_tl, sizeof(unsigned long long) * 4 * 4096) == cudaSuccess ? 0 : -2; }
 extern "C" int d3il_debug_iter_hist(unsigned long long* out40) { return cudaMemcpyFromSymbol(out40, g_iter_hist, sizeof(unsigned long long) * 40) == cudaSuccess ? 0 : -2; }
+// per-CTA Newton statistics of the launches since the last clear (out == nullptr or clear != 0 zeroes them)
+extern "C" int d3il_debug_cta_stat(unsigned* out4096x4, int clear) {
+  if (out4096x4 && cudaMemcpyFromSymbol(out4096x4, g_cta_stat, sizeof(unsigned) * 4 * 4096) != cudaSuccess) return -2;
+  if (clear || !out4096x4) { static unsigned z[4 * 4096]; if (cudaMemcpyToSymbol(g_cta_stat, z, sizeof(z)) != cudaSuccess) return -2; }
+  return 0;
+}
 int d3il_debug_phase_cycles_env(unsigned long long* out24) { return cudaMemcpyFromSymbol(out24, g_phase_cycles, sizeof(unsigned long long) * 24) == cudaSuccess ? 0 : -2; }
 #endif

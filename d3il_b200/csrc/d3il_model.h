@@ -108,6 +108,18 @@ static inline bool d3il_build_model(const void* blob, size_t nbytes, Model& m, L
     }
     m.nblk++; }
   for (int d = 0; d < m.nv; d++) for (int b = 0; b < m.nblk; b++) if (d >= m.blk_s[b] && d < m.blk_e[b]) m.d_blk[d] = (unsigned char)b;
+  m.nhe = 0;
+  for (int b = 0; b < m.nblk; b++) for (int i = m.blk_s[b]; i < m.blk_e[b]; i++) for (int j = m.blk_s[b]; j <= i; j++) {
+    if (m.nhe >= D3_MAXHE) { err = "too many in-block Hessian entries (D3_MAXHE)"; return false; }
+    m.he_i[m.nhe] = (unsigned char)i; m.he_j[m.nhe] = (unsigned char)j; m.nhe++;
+  }
+  // packed mass matrix: the blocks back to back as row-major squares
+  m.m_size = 0;
+  for (int b = 0; b < m.nblk; b++) {
+    const int bs = m.blk_s[b], sz = m.blk_e[b] - bs;
+    for (int d = bs; d < bs + sz; d++) { m.m_base[d] = (short)m.m_size; m.m_row[d] = (short)(m.m_size + (d - bs) * sz - bs); }
+    m.m_size += sz * sz;
+  }
   // in-block (a > b) dof pairs that are not ancestor-related: CRBA never writes them
   for (int a = 0; a < m.nv; a++) for (int b = m.d_bs[a]; b < a; b++)
     if (!((m.l_anc[m.d_link[a]] >> m.d_link[b]) & 1u)) {

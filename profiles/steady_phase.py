@@ -46,6 +46,9 @@ if has_phase:
         print(f"{names[k]:28s} {out[k]/ticks:10.0f} cycles/tick  {100*out[k]/tot:5.1f}%")
     print(f"all envs: coupled ticks {out[21]/max(out[23],1):.4f}, mean contacts {out[22]/max(out[23],1):.2f}, mean rows {out[19]/max(out[23],1):.2f}")
     print("total cycles/tick", tot / ticks, "newton iterations/tick (sampled CTA)", out[20] / ticks)
+    nit = max(out[20], 1)
+    print(f"sampled warps per tick: contacts {out[17]/ticks:.2f}, rows {out[7]/ticks:.2f}, ticks with one coupling contact {out[14]/ticks:.3f}, with several {out[13]/ticks:.3f} (per sampled warp: divide by their number)")
+    print("per Newton loop pass of the sampled warps (cycles): " + ", ".join(f"{names[k].split(': ')[1]} {out[k]/nit:.0f}" for k in (15, 8, 9, 10, 11, 12)) + f"; line-search evaluations per pass {out[18]/nit:.2f}; passes {nit}")
 rows = np.array([env.get_state(e)[-8:] for e in range(0, n, 4)])
 it, cp, nc = rows[:, 4], rows[:, 5], rows[:, 6]
 print("newton steps per env step: mean %.1f p10 %.0f p50 %.0f p90 %.0f p99 %.0f max %.0f" % (it.mean(), *np.percentile(it, [10, 50, 90, 99, 100])))

@@ -31,16 +31,8 @@ if hasattr(lib.lib(), 'd3il_debug_cta_stat'): lib.lib().d3il_debug_cta_stat(None
 e0.record(); env.step(des); e1.record(); torch.cuda.synchronize()
 stat = None
 if hasattr(lib.lib(), 'd3il_debug_cta_stat'):
-    sb = (C.c_uint * (4 * 4096))(); lib.lib().d3il_debug_cta_stat(sb, 0); stat = np.array(sb, dtype=np.int64).reshape(4096, 4)
+    sb = (C.c_uint * (4 * 4096))(); lib.lib().d3il_debug_cta_stat(C.cast(sb, C.POINTER(C.c_uint)), 0); stat = np.array(sb, dtype=np.int64).reshape(4096, 4)
 print(f'last step by CUDA events: {e0.elapsed_time(e1):.3f} ms')
-e0.record()
-for k in range(10): env.step(des)
-e1.record(); torch.cuda.synchronize()
-print(f'10 more steps: {e0.elapsed_time(e1)/10:.3f} ms per step')
-if hasattr(lib.lib(), 'd3il_debug_cta_stat'):
-    lib.lib().d3il_debug_cta_stat(None, 1)
-    env.step(des); torch.cuda.synchronize()          # the step both the timeline and the per-CTA statistics below describe
-    sb = (C.c_uint * (4 * 4096))(); lib.lib().d3il_debug_cta_stat(sb, 0); stat = np.array(sb, dtype=np.int64).reshape(4096, 4)
 buf = (C.c_ulonglong * (4 * 4096))()
 lib.lib().d3il_debug_timeline(buf)
 a = np.array(buf, dtype=np.uint64).reshape(4096, 4).astype(np.int64)
@@ -73,7 +65,10 @@ for t in (0.3, 1.0, 2.0):
 
 if stat is not None:
     order = np.argsort(-dur)[:12]
-    print("slowest CTAs of the timeline step (block, start ms, duration ms):", [(int(i), round(float(st[i]), 2), round(float(dur[i]), 2)) for i in order])
+    rows = np.nonzero(a[:, 3] == 2)[0]
+    print("slowest CTAs of the timeline step (block, start ms, duration ms, passes/coupled/own-steps/ls-evals):", [(int(rows[i]), round(float(st[i]), 2), round(float(dur[i]), 2), *map(int, stat[rows[i]])) for i in order])
+    last = np.argsort(-en)[:12]
+    print("last CTAs to end (block, start ms, end ms, passes):", [(int(rows[i]), round(float(st[i]), 2), round(float(en[i]), 2), int(stat[rows[i], 0])) for i in last])
     top = np.argsort(-stat[:len(env_b), 0])[:12]
     print("most Newton passes in the stat step: block: passes/coupled/own-steps/ls-evals:", [(int(b), *map(int, stat[b])) for b in top])
     print("Newton passes per CTA: p50 %d p90 %d p99 %d max %d" % tuple(np.percentile(stat[:len(env_b), 0], [50, 90, 99, 100])))

@@ -76,12 +76,15 @@ void emu_get_obs(Emu* e, float* obs) { task_obs(e->m, e->L, e->w.data(), obs); }
 int emu_probe(Emu* e, const char* what, double* out, int cap) {
   const Lay& L = e->L; const Model& m = e->m; int off = -1, n = 0;
   std::string s(what);
-  if (s == "M") { off = L.M; n = m.nv * m.nv; } else if (s == "bias") { off = L.bias; n = m.nv; } else if (s == "qacc") { off = L.qacc; n = m.nv; }
+  if (s == "M") {          // dense nv x nv view of the packed buffer (upper triangle + diagonal are the mass matrix, the strict lower triangle its factor)
+    n = m.nv * m.nv; if (n > cap) return -1;
+    for (int r = 0; r < m.nv; r++) for (int c = 0; c < m.nv; c++) out[r * m.nv + c] = (c >= m.d_bs[r] && c < m.d_be[r]) ? (double)e->w[L.M + m.m_row[r] + c] : 0.0;
+    return n;
+  } else if (s == "bias") { off = L.bias; n = m.nv; } else if (s == "qacc") { off = L.qacc; n = m.nv; }
   else if (s == "qacc_smooth") { off = L.qacc_smooth; n = m.nv; } else if (s == "efc_J") { off = L.J; n = m.maxrow * m.nv; }
   else if (s == "efc_aref") { off = L.aref; n = m.maxrow; } else if (s == "efc_D") { off = L.D; n = m.maxrow; } else if (s == "efc_force") { off = L.frcE; n = m.maxrow; }
   else if (s == "contacts") { off = L.con; n = D3_CON_W * m.maxcon; } else if (s == "qfrc_c") { off = L.qfrc_c; n = m.nv; } else if (s == "act") { off = L.act; n = 9; }
   else if (s == "qfrc_smooth") { off = L.qfrc_smooth; n = m.nv; }
-  else if (s == "M") { off = L.M; n = m.nv * m.nv; }
   if (off < 0 || n > cap) return -1;
   for (int k = 0; k < n; k++) out[k] = e->w[off + k];
   return n;
