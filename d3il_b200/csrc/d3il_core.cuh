@@ -126,12 +126,13 @@ template <bool CS> DEVFN void cta_sync(const Cx& cx) {
 
 #if defined(D3IL_PHASE_TIMING) && !defined(D3IL_EMU)
 // debug build only: per-phase cycle counts of the group that owns env 0 (profiles/phase_timing.py)
-static __device__ unsigned long long g_phase_cycles[24];
+static __device__ unsigned long long g_phase_cycles[40];
 static __device__ unsigned g_cta_stat[4 * 4096];            // per CTA: [0] CTA-uniform Newton passes, [1] of which warp 0's env was coupled, [2] Newton steps of warp 0's env, [3] line-search evaluations of warp 0
 static __device__ unsigned long long g_iter_hist[40];      // [0..15] Newton steps per tick, [16..31] same for ticks with a coupling contact, [32] sum ncon / [33] count of ticks with >= 8 steps
 #endif
 #if defined(D3IL_PHASE_TIMING) && defined(__CUDA_ARCH__)
 #define PHASE_T0() long long t_ph = clock64()
+#define PHASE2_T0() long long t_ph2 = clock64()
 #ifndef D3IL_PHASE_BLOCK
 #define D3IL_PHASE_BLOCK 0      // which CTA of the cost-sorted grid is sampled (e.g. -DD3IL_PHASE_BLOCK="(gridDim.x/2)" = median cost)
 #endif
@@ -143,10 +144,13 @@ static __device__ unsigned long long g_iter_hist[40];      // [0..15] Newton ste
 __device__ __forceinline__ bool blockIdx_is0() { return D3IL_PHASE_COND && threadIdx.x == 0; }
 __device__ __forceinline__ void count_iter() { atomicAdd(&g_phase_cycles[20], 1ull); }
 __device__ __forceinline__ void count_stat(int k, int v) { atomicAdd(&g_phase_cycles[k], (unsigned long long)v); }
+#define PHASE2(k) do { long long t_now2 = clock64(); if (D3IL_PHASE_COND && threadIdx.x == 0) atomicAdd(&g_phase_cycles[k], (unsigned long long)(t_now2 - t_ph2)); t_ph2 = t_now2; } while (0)
 #define PHASE(k) do { long long t_now = clock64(); if (D3IL_PHASE_COND && threadIdx.x == 0) atomicAdd(&g_phase_cycles[k], (unsigned long long)(t_now - t_ph)); t_ph = t_now; } while (0)
 #else
 #define PHASE_T0() ((void)0)
+#define PHASE2_T0() ((void)0)
 #define PHASE(k) ((void)0)
+#define PHASE2(k) ((void)0)
 DEVFN bool blockIdx_is0() { return false; }
 DEVFN void count_iter() {}
 DEVFN void count_stat(int, int) {}
@@ -1338,6 +1342,64 @@ DEVNI void chol_blocks_solve_multi(const Cx& cx, const Model& m, const real* A, 
 }
 #endif
 
+#ifndef D3IL_EMU
+// Dense n x n system (n <= MB <= G: one group, row i in lane i) factored AND solved on registers: the tree-coupled Newton
+// Hessian of a scene with nv <= 32.  A: strict lower triangle in shared memory (leading dimension n), diag[] its diagonal,
+// x: right-hand side in, solution out.  The factor's rows are written back to A so that each lane can read its column
+// for the backward sweep.  Returns 1 (all lanes) if a pivot was not positive.
+template <int G, int MB>
+DEVNI int chol_dense_reg_solve(const Cx& cx, real* A, int n, const real* diag, real* x) {
+  const int i = cx.lane;
+  const bool mine_row = i < n;
+  real a[MB], myinv = 1;
+#pragma unroll
+  for (int j = 0; j < MB; j++) a[j] = (mine_row && j < i) ? A[i * n + j] : ((mine_row && j == i) ? diag[i] : (real)0);
+  int bad = 0;
+#pragma unroll
+  for (int k = 0; k < MB; k++) {
+    if (k < n) {
+      if (i == k) { real p = a[k]; if (!(p > 0)) { bad = 1; p = 1; } myinv = 1 / sqrt(p); }
+      const real inv = __shfl_sync(cx.mask, myinv, k, G);
+      if (i > k) a[k] *= inv;
+      const real colk = a[k];
+#pragma unroll
+      for (int j = k + 1; j < MB; j++) {
+        if (j < n) {
+          const real ljk = __shfl_sync(cx.mask, colk, j, G);
+          if (i >= j) a[j] -= colk * ljk;
+        }
+      }
+    }
+  }
+  if (mine_row) {
+#pragma unroll
+    for (int j = 0; j < MB; j++) if (j < i) A[i * n + j] = a[j];
+  }
+  gsync<G>(cx);
+  real lcol[MB];
+#pragma unroll
+  for (int j = 0; j < MB; j++) lcol[j] = (mine_row && j > i && j < n) ? A[j * n + i] : (real)0;
+  real xr = mine_row ? x[i] : (real)0;
+#pragma unroll
+  for (int k = 0; k < MB; k++) {
+    if (k < n) {
+      const real xk = __shfl_sync(cx.mask, xr * myinv, k, G);
+      if (i == k) xr = xk; else if (i > k) xr -= a[k] * xk;
+    }
+  }
+#pragma unroll
+  for (int k = MB - 1; k >= 0; k--) {
+    if (k < n) {
+      const real xk = __shfl_sync(cx.mask, xr * myinv, k, G);
+      if (i == k) xr = xk; else if (i < k) xr -= lcol[k] * xk;
+    }
+  }
+  if (mine_row) x[i] = xr;
+  gsync<G>(cx);
+  return gori<G>(cx, bad);
+}
+#endif
+
 // NS = register slots per lane for the distributed vector: one when the system fits the group (n <= G)
 template <int G>
 DEVFN void chol_solve_part(const Cx& cx, const Model& m, const real* A, int n, bool whole, int maxsz, const real* dinv, real* x) {
@@ -1608,7 +1670,12 @@ DEVNI void newton_woodbury(const Cx& cx, const Model& m, const Lay& L, real* w, 
 // Newton solver on the primal problem: result in qacc / frcE / qfrc_c.  Returns iterations.
 template <int G, bool CS, int MD>
 DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w, int ne, int nlimit, int ncon, int ncpl, int cplc, real tol, int max_iter) {
+  PHASE2_T0();
+#ifdef D3IL_NO_WOODBURY
+  const int coupled = ncpl > 0;
+#else
   const int coupled = ncpl > 1;      // dense path: two or more contacts couple kinematic trees (one is handled as a low-rank update of the block path)
+#endif
   const int nv = m.nv;
   // Envs without active rows take qacc = qacc_smooth but keep walking the (CTA-uniform) iteration loop below.
   int done = ne == 0;
@@ -1640,6 +1707,7 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
     }
     gsync<G>(cx);
   }
+  PHASE2(34);
   int iter = 0, nsteps = 0;      // nsteps: Newton steps this env actually took (iter also counts idle CTA-uniform passes)
   int grad_fresh = 0;            // grad / Ma / frcE all belong to the current iterate (then J^T f = Ma - grad)
   PHASE_T0();
@@ -1667,6 +1735,7 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
     }
     real gn = sqrt(gsum<G>(cx, g2));
     gsync<G>(cx);
+    PHASE2(31);
     grad_fresh = 1;
 #ifdef D3IL_DEBUG_SOLVER
     printf("  newton it %d cost %.12g gn %.6g\n", iter, (double)cost, (double)gn);
@@ -1694,6 +1763,7 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
     // (A) every in-block entry is owned by one lane, which accumulates M, the limit rows and all contacts that live
     //     inside that block in a register and writes H once: no barriers between contacts.
     if (coupled) { LANES(e, nv * nv) w[L.H + e] = 0; gsync<G>(cx); }
+    PHASE2(32);
     LANES(e, m.nhe) {
       const int gi = m.he_i[e], gj = m.he_j[e], bs = m.d_bs[gi];
       real acc = M[m.m_row[gj] + gi];
@@ -1724,6 +1794,7 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
       w[L.H + gi * nv + gj] = acc;
     }
     gsync<G>(cx);
+    PHASE2(33);
     if (!coupled) {
       // block path: factorisation in registers, block solve; a single coupling contact is a low-rank (Woodbury) update
       PHASE(9);
@@ -1733,7 +1804,9 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
       PHASE(10);
       if (!hfail) {
         chol_blocks_solve<G>(cx, m, w + L.H, nv, false, w + L.hdinv, w + L.pvec);
+        PHASE2(29);
         if (ncpl == 1) newton_woodbury<G, MD>(cx, m, L, w, cplc);
+        PHASE2(30);
       }
     } else {
     // (B) contacts that couple two blocks (rod-box, box-box): rare, added one after the other
@@ -1767,15 +1840,23 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
     // A Hessian that is not positive definite (NaN inputs included) ends this env's solve with status bit 4.  The env must
     // NOT leave the loop on its own: the iteration is CTA-uniform (cta_any above is a barrier every warp of the CTA has to
     // reach), so it turns `done` and idles through the remaining passes like a converged env.
+#ifndef D3IL_EMU
+    if (nv <= 24) { hfail = chol_dense_reg_solve<G, 24>(cx, w + L.H, nv, w + L.hpiv, w + L.pvec); PHASE(10); }
+    else if (nv <= G) { hfail = chol_dense_reg_solve<G, (G < 32 ? G : 32)>(cx, w + L.H, nv, w + L.hpiv, w + L.pvec); PHASE(10); }
+    else
+#endif
+    {
     hfail = chol_factor_part<G>(cx, m, w + L.H, nv, true, nv, w + L.hpiv, w + L.hdinv);
     PHASE(10);
     if (!hfail) chol_solve_part<G>(cx, m, w + L.H, nv, true, nv, w + L.hdinv, w + L.pvec);
+    }
     }
     if (hfail) { LANES(z, 1) w[L.misc + ST_STATUS] = (real)(((int)w[L.misc + ST_STATUS]) | D3_STATUS_H_NOT_PD); done = 1; gsync<G>(cx); }
     if (!hfail) {
     PHASE(11);
     // ---- exact line search (safeguarded 1-D Newton / false position), quantities reduced across lanes
     eval_jar<G>(cx, m, L, w, nlimit, ncon, L.pvec, L.Jp, false);
+    PHASE2(24);
     real a1s = 0, a2s = 0, a3s = 0;
     LANES(d, nv) {
       real s = mrow_dot(m, M, nv, d, w + L.pvec, nullptr);
@@ -1784,16 +1865,19 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
     }
     gsum2<G>(cx, a1s, a2s);
     real pMp = a1s, pMa = a2s, d0 = gsum<G>(cx, a3s);
+    PHASE2(25);
 #ifdef D3IL_EMU
     const real alpha = line_search<G, MD, 64, 2 * D3_NROB>(cx, m, L, w, nlimit, ncon, d0, pMa, pMp);
 #else
     const real alpha = m.maxcon <= G ? line_search<G, MD, 1, 1>(cx, m, L, w, nlimit, ncon, d0, pMa, pMp) : line_search<G, MD, 2, 1>(cx, m, L, w, nlimit, ncon, d0, pMa, pMp);
 #endif
+    PHASE2(26);
     // step: everything linear in the iterate moves incrementally (jar = J a - aref, Ma = M (a - a_s)); then the
     // evaluation of the NEXT iteration (cost, forces, cone Hessian blocks) at the new iterate
     LANES(d, nv) { w[L.qacc + d] += alpha * w[L.pvec + d]; w[L.Ma + d] += alpha * w[L.tmpv + d]; }
     LANES(i, ne) w[L.jar + i] += alpha * w[L.Jp + i];
     gsync<G>(cx);
+    PHASE2(27);
     oldcost = cost;
     cost = constraint_eval<G, true, MD>(cx, m, L, w, nlimit, ncon, L.jar, L.frcE);
     real partc = 0;
@@ -1801,6 +1885,7 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
     cost += gsum<G>(cx, partc);
     gsync<G>(cx);
     grad_fresh = 0;
+    PHASE2(28);
     PHASE(12);
     }
     }
@@ -1826,6 +1911,7 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
     w[L.qfrc_c + d] = s;
   }
   gsync<G>(cx);
+  PHASE2(35);
   return nsteps;
 }
 

@@ -195,5 +195,5 @@ extern "C" int d3il_debug_cta_stat(unsigned* out4096x4, int clear) {
   if (clear || !out4096x4) { static unsigned z[4 * 4096]; if (cudaMemcpyToSymbol(g_cta_stat, z, sizeof(z)) != cudaSuccess) return -2; }
   return 0;
 }
-int d3il_debug_phase_cycles_env(unsigned long long* out24) { return cudaMemcpyFromSymbol(out24, g_phase_cycles, sizeof(unsigned long long) * 24) == cudaSuccess ? 0 : -2; }
+int d3il_debug_phase_cycles_env(unsigned long long* out24) { return cudaMemcpyFromSymbol(out24, g_phase_cycles, sizeof(unsigned long long) * 40) == cudaSuccess ? 0 : -2; }
 #endif

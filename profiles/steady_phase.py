@@ -27,7 +27,7 @@ for k in range(400):
     step((ids % 400 == k).to(torch.uint8))
 torch.cuda.synchronize()
 has_phase = hasattr(lib.lib(), "d3il_debug_phase_cycles")
-base = (C.c_ulonglong * 24)()
+base = (C.c_ulonglong * 40)()
 if has_phase: lib.lib().d3il_debug_phase_cycles(base)
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -36,8 +36,8 @@ for k in range(steps): step()
 ev1.record(); torch.cuda.synchronize()
 print("ms/step", ev0.elapsed_time(ev1) / steps)
 if has_phase:
-    out = (C.c_ulonglong * 24)(); lib.lib().d3il_debug_phase_cycles(out)
-    out = [out[i] - base[i] for i in range(24)]
+    out = (C.c_ulonglong * 40)(); lib.lib().d3il_debug_phase_cycles(out)
+    out = [out[i] - base[i] for i in range(40)]
     names = {0: "ctrl+kinematics+tcp", 1: "dynamics", 2: "collision", 3: "make_constraints", 4: "chol(M)+solve", 5: "newton total", 6: "euler+integrate",
              15: "newton: loop top", 16: "wait for IK tick (thread 0)", 8: "newton: jar+eval+grad", 9: "newton: H assembly", 10: "newton: chol(H)", 11: "newton: solve", 12: "newton: line search"}
     ticks = steps * 35
@@ -47,6 +47,9 @@ if has_phase:
     print(f"all envs: coupled ticks {out[21]/max(out[23],1):.4f}, mean contacts {out[22]/max(out[23],1):.2f}, mean rows {out[19]/max(out[23],1):.2f}")
     print("total cycles/tick", tot / ticks, "newton iterations/tick (sampled CTA)", out[20] / ticks)
     nit = max(out[20], 1)
+    sub = {24: "ls: J p", 25: "ls: M p + reductions", 26: "ls: search", 27: "ls: update", 28: "ls: eval at new iterate", 29: "solve: block solve", 30: "solve: woodbury",
+           31: "grad: gradient loop", 32: "H: clear (dense)", 33: "H: in-block assembly", 34: "warm start", 35: "after loop"}
+    print("finer (cycles per pass): " + ", ".join(f"{v} {out[k]/nit:.0f}" for k, v in sub.items()))
     print(f"sampled warps per tick: contacts {out[17]/ticks:.2f}, rows {out[7]/ticks:.2f}, ticks with one coupling contact {out[14]/ticks:.3f}, with several {out[13]/ticks:.3f} (per sampled warp: divide by their number)")
     print("per Newton loop pass of the sampled warps (cycles): " + ", ".join(f"{names[k].split(': ')[1]} {out[k]/nit:.0f}" for k in (15, 8, 9, 10, 11, 12)) + f"; line-search evaluations per pass {out[18]/nit:.2f}; passes {nit}")
 rows = np.array([env.get_state(e)[-8:] for e in range(0, n, 4)])
