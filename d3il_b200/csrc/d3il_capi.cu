@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(1024) k_sched(DevCtx c) {
   const int off = c.lay.misc + ST_COST_ITERS;
   for (int e = threadIdx.x; e < c.n; e += blockDim.x) {
     const float* row = c.state + (size_t)e * c.row;
-    int b = (int)(row[off] + 4.f * row[off + 1]) >> 1;
+    int b = (int)(row[off] + 4.f * row[off + 1] + (row[off + 3] > 0.f ? 16.f : 0.f)) >> 1;      // Newton iterations, ticks with a coupling contact, contact imminent
     atomicAdd(&hist[b > 255 ? 255 : b], 1);
   }
   __syncthreads();
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(1024) k_sched(DevCtx c) {
   __syncthreads();
   for (int e = threadIdx.x; e < c.n; e += blockDim.x) {
     const float* row = c.state + (size_t)e * c.row;
-    int b = (int)(row[off] + 4.f * row[off + 1]) >> 1;
+    int b = (int)(row[off] + 4.f * row[off + 1] + (row[off + 3] > 0.f ? 16.f : 0.f)) >> 1;      // Newton iterations, ticks with a coupling contact, contact imminent
     c.perm[atomicAdd(&start[b > 255 ? 255 : b], 1)] = e;
   }
   TL_END(3);

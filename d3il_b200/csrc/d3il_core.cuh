@@ -240,10 +240,11 @@ struct Lay {
   // scratch
   int xpos, xmat, S, I10, Ic, vel, cj, frc, F, M, mdinv, mpiv, H, hdinv, hpiv, bias, qfrc_smooth, qacc_smooth, qacc, qfrc_c, grad, pvec, Ma, tmpv;
   int wood;           // Woodbury scratch: maxdim dof vectors (view 2)
+  int rowc;           // per constraint row >= nlimit: contact id | (row within the contact << 6), bytes
   int blist;          // per kinematic-tree block: [count, contact ids ...] bytes, stride maxcon + 1 (bit 7: the contact couples two blocks)
   int act, jt, con, ncon_pair, limflag, cflag, J, aref, D, jar, frcE, Jp, hd, hb, etype, econ, total;
 };
-enum { ST_GRIP_SET = 0, ST_GRASP, ST_CTRL_MODE, ST_STEP, ST_TERM, ST_STATUS, ST_OBST, ST_TASK0, ST_TASK1, ST_TASK2, ST_TASK3, ST_COST_ITERS /* Newton iterations of the last env step */, ST_COST_COUPLED /* ticks with a tree-coupling contact */, ST_COST_NCON /* max contacts */, ST_NMISC = 16 };
+enum { ST_GRIP_SET = 0, ST_GRASP, ST_CTRL_MODE, ST_STEP, ST_TERM, ST_STATUS, ST_OBST, ST_TASK0, ST_TASK1, ST_TASK2, ST_TASK3, ST_COST_ITERS /* Newton iterations of the last env step */, ST_COST_COUPLED /* ticks with a tree-coupling contact */, ST_COST_NCON /* max contacts */, ST_COST_NEAR /* ticks in which a tree-coupling pair passed the broad phase: contact is imminent */, ST_NMISC = 16 };
 // per-env fault word (misc[ST_STATUS], last column of `info`; sticky until the env is reset)
 enum { D3_STATUS_M_NOT_PD = 1, D3_STATUS_OVERFLOW = 2 /* contact / row budget exceeded: contacts dropped */, D3_STATUS_H_NOT_PD = 4,
        D3_STATUS_ITER_CAP = 8 /* Newton loop left at max_iter without passing the convergence test */, D3_STATUS_BAD_ACTION = 16 /* non-finite action or zero quaternion: last set-point held */ };
@@ -260,7 +261,7 @@ static inline void d3il_layout(const Model& m, Lay& L) {
   L.M = take(m.m_size); L.mdinv = take(m.nv); L.mpiv = take(m.nv);
   L.bias = take(m.nv); L.qfrc_smooth = take(m.nv); L.qacc_smooth = take(m.nv); L.qacc = take(m.nv); L.qfrc_c = take(m.nv);
   L.act = take(D3_NROB); L.jt = take(3 * D3_NARM); L.con = take(D3_CON_W * m.maxcon);
-  L.J = take(m.maxrow * D3_JW); L.aref = take(m.maxrow); L.D = take(m.maxrow); L.hd = take(2 * D3_NROB); L.econ = take(2 * D3_NROB); L.blist = take((m.nblk * (m.maxcon + 1) + 3) / 4);
+  L.J = take(m.maxrow * D3_JW); L.aref = take(m.maxrow); L.D = take(m.maxrow); L.hd = take(2 * D3_NROB); L.econ = take(2 * D3_NROB); L.blist = take((m.nblk * (m.maxcon + 1) + 3) / 4); L.rowc = take((m.maxrow + 3) / 4);
   // region X, two views that are never live together:
   //   view 1 (kinematics, dynamics, collision, constraint assembly)   view 2 (Newton solver, Euler)
   const int x0 = o;
@@ -791,7 +792,7 @@ DEVFN int collision(const Cx& cx, const Model& m, const Lay& L, real* w) {
   RawCon rc[8];
   int myn = 0, mypair = -1;
   // NOTE: npair <= G is required for the single-pass scheme below (checked on the host); pairs beyond G use more passes.
-  int ntot = 0, obst = 0;
+  int ntot = 0, obst = 0, near = 0;
   for (int base = 0; base < m.npair; base += G) {
     int ip = base + cx.lane;
     myn = 0; mypair = -1;
@@ -803,6 +804,7 @@ DEVFN int collision(const Cx& cx, const Model& m, const Lay& L, real* w) {
       geom_pose(m, L, w, g1, p1, R1); geom_pose(m, L, w, g2, p2, R2);
       real dc[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]}, margin = pr[15];
       if (norm3(dc) <= (real)ga[12] + (real)gb[12] + margin) {
+        if (m.p_cpl[ip]) near = 1;
         real s1[3] = {(real)ga[9], (real)ga[10], (real)ga[11]}, s2[3] = {(real)gb[9], (real)gb[10], (real)gb[11]};
         int t1 = (int)ga[0], t2 = (int)gb[0];
         if (t1 == D3G_BOX && t2 == D3G_BOX) {
@@ -835,9 +837,10 @@ DEVFN int collision(const Cx& cx, const Model& m, const Lay& L, real* w) {
     for (int j = 0; j < cnt_here; j++) ntot += (int)w[L.ncon_pair + j];
     gsync<G>(cx);
   }
-  obst = gori<G>(cx, obst);
+  obst = gori<G>(cx, obst); near = gori<G>(cx, near);
   LANES(z, 1) {
     w[L.misc + ST_OBST] = (real)obst;
+    w[L.misc + ST_COST_NEAR] += (real)near;
     if (ntot > m.maxcon) w[L.misc + ST_STATUS] = (real)(((int)w[L.misc + ST_STATUS]) | 2);
   }
   if (ntot > m.maxcon) ntot = m.maxcon;
@@ -984,10 +987,18 @@ DEVFN int make_constraints(const Cx& cx, const Model& m, const Lay& L, real* w, 
     cc[14] = fr[0] * sqrt(R1 / R0);
     for (int r = 0; r < dim; r++) {
       real Rv = r == 0 ? R0 : (r == 1 ? R1 : R1 * fr[0] * fr[0] / (fr[r - 1] * fr[r - 1]));
-      real vel = jrow_dot(w + L.J + (row0 + r) * D3_JW, w + L.qvel, (int)cc[20], (int)cc[21], (int)cc[22], (int)cc[23]);
       w[L.D + row0 + r] = 1 / Rv;
-      w[L.aref + row0 + r] = -bb * vel - (r == 0 ? kk * imp * (cc[12] - cc[13]) : 0);
+      w[L.aref + row0 + r] = -(r == 0 ? kk * imp * (cc[12] - cc[13]) : 0);       // the damping term -b (J qvel) is added per row below
+      ((unsigned char*)(w + L.rowc))[row0 + r] = (unsigned char)(c | (r << 6));
     }
+  }
+  gsync<G>(cx);
+  LANES(r, row) {      // one lane per contact row: aref -= b * (J qvel)_r
+    if (r < nl) continue;
+    const real* cc = w + L.con + D3_CON_W * (((const unsigned char*)(w + L.rowc))[r] & 63);
+    const tab_t* pr = m.pair + D3_PAIR_W * (int)cc[18];
+    const real bb = 2 / ((real)pr[11] * (real)pr[8]);
+    w[L.aref + r] -= bb * jrow_dot(w + L.J + r * D3_JW, w + L.qvel, (int)cc[20], (int)cc[21], (int)cc[22], (int)cc[23]);
   }
   // per-block lists of the active contacts that touch the block (bit 7: the contact also touches another block): the Newton
   // loop's gradient and Hessian assembly walk these instead of scanning every contact for every dof / matrix entry
@@ -1007,24 +1018,20 @@ DEVFN int make_constraints(const Cx& cx, const Model& m, const Lay& L, real* w, 
   return row;
 }
 
-// jar = J v - aref for every row (v: workspace offset of a dof vector).  One lane per limit row / per contact.
+// jar = J v - aref for every row (v: workspace offset of a dof vector).  One lane per constraint row.
 template <int G>
-DEVNI void eval_jar(const Cx& cx, const Model& m, const Lay& L, real* w, int nlimit, int ncon, int v_off, int out_off, bool sub_aref) {
-  const int nv = m.nv;
-  LANES(i, nlimit) {
-    int sd = (int)w[L.econ + i];
-    real s = sd > 0 ? w[v_off + sd - 1] : -w[v_off - sd - 1];
-    w[out_off + i] = sub_aref ? s - w[L.aref + i] : s;
-  }
-  LANES(c, ncon) {
-    const real* cc = w + L.con + D3_CON_W * c;
-    int i = (int)cc[19];
-    if (i < 0) continue;
-    int dim = (int)cc[15];
-    for (int r = 0; r < dim; r++) {
-      real s = jrow_dot(w + L.J + (i + r) * D3_JW, w + v_off, (int)cc[20], (int)cc[21], (int)cc[22], (int)cc[23]);
-      w[out_off + i + r] = sub_aref ? s - w[L.aref + i + r] : s;
+DEVNI void eval_jar(const Cx& cx, const Model& m, const Lay& L, real* w, int nlimit, int ne, int v_off, int out_off, bool sub_aref) {
+  const unsigned char* rowc = (const unsigned char*)(w + L.rowc);
+  LANES(r, ne) {
+    real s;
+    if (r < nlimit) {
+      int sd = (int)w[L.econ + r];
+      s = sd > 0 ? w[v_off + sd - 1] : -w[v_off - sd - 1];
+    } else {
+      const real* cc = w + L.con + D3_CON_W * (rowc[r] & 63);
+      s = jrow_dot(w + L.J + r * D3_JW, w + v_off, (int)cc[20], (int)cc[21], (int)cc[22], (int)cc[23]);
     }
+    w[out_off + r] = sub_aref ? s - w[L.aref + r] : s;
   }
   gsync<G>(cx);
 }
@@ -1686,10 +1693,10 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
   //      Hessian blocks, M (a - a_s)) is iteration 0's evaluation when the warm start wins - the usual case.
   real cost = 0, oldcost = 0, gn_prev = 0;
   if (!done) {
-    eval_jar<G>(cx, m, L, w, nlimit, ncon, L.qacc_smooth, L.jar, true);
+    eval_jar<G>(cx, m, L, w, nlimit, ne, L.qacc_smooth, L.jar, true);
     real cs = constraint_eval<G, false, MD>(cx, m, L, w, nlimit, ncon, L.jar, L.frcE);
     gsync<G>(cx);
-    eval_jar<G>(cx, m, L, w, nlimit, ncon, L.warm, L.jar, true);
+    eval_jar<G>(cx, m, L, w, nlimit, ne, L.warm, L.jar, true);
     real cw = constraint_eval<G, true, MD>(cx, m, L, w, nlimit, ncon, L.jar, L.frcE);
     real part = 0;
     LANES(d, nv) {
@@ -1702,7 +1709,7 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
     else {
       LANES(d, nv) { w[L.qacc + d] = w[L.qacc_smooth + d]; w[L.Ma + d] = 0; }
       gsync<G>(cx);
-      eval_jar<G>(cx, m, L, w, nlimit, ncon, L.qacc_smooth, L.jar, true);
+      eval_jar<G>(cx, m, L, w, nlimit, ne, L.qacc_smooth, L.jar, true);
       cost = constraint_eval<G, true, MD>(cx, m, L, w, nlimit, ncon, L.jar, L.frcE);
     }
     gsync<G>(cx);
@@ -1855,7 +1862,7 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
     if (!hfail) {
     PHASE(11);
     // ---- exact line search (safeguarded 1-D Newton / false position), quantities reduced across lanes
-    eval_jar<G>(cx, m, L, w, nlimit, ncon, L.pvec, L.Jp, false);
+    eval_jar<G>(cx, m, L, w, nlimit, ne, L.pvec, L.Jp, false);
     PHASE2(24);
     real a1s = 0, a2s = 0, a3s = 0;
     LANES(d, nv) {

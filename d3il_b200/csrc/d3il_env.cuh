@@ -709,7 +709,7 @@ DEVFN void env_prestep(const Cx& cx, const Model& m, const Lay& L, real* w, cons
       }
       w[L.misc + ST_CTRL_MODE] = 2;
     } else { w[L.misc + ST_GRIP_SET] = (real)0.04; w[L.misc + ST_GRASP] = 0; w[L.misc + ST_CTRL_MODE] = 1; }
-    w[L.misc + ST_COST_ITERS] = 0; w[L.misc + ST_COST_COUPLED] = 0; w[L.misc + ST_COST_NCON] = 0;
+    w[L.misc + ST_COST_ITERS] = 0; w[L.misc + ST_COST_COUPLED] = 0; w[L.misc + ST_COST_NCON] = 0; w[L.misc + ST_COST_NEAR] = 0;
     task_obs(m, L, w, obs);
     *reward = (float)task_reward(m, L, w);
     int early = task_early_term(m, L, w);

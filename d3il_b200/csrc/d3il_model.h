@@ -129,6 +129,7 @@ static inline bool d3il_build_model(const void* blob, size_t nbytes, Model& m, L
   // contact budget: 4 per free body resting on a support + 12 for transients (deep spawn penetration touches two supports,
   // box-box / rod contacts); overflow raises status bit 2, never drops silently
   { int cap = hdr_maxcon > 0 ? hdr_maxcon : 4 * m.nobj + 12; m.maxcon = ((conmax < cap ? conmax : cap) + 3) & ~3; }
+  if (m.maxcon > 64) { err = "contact budget above 64 (row / block contact lists keep 6-bit contact ids)"; return false; }
   if (m.maxdim < 3) m.maxdim = 3;
   m.maxrow = m.maxdim * m.maxcon + 4;
   d3il_layout(m, L);
