@@ -95,7 +95,7 @@ template <int G> DEVFN double gsumd(const Cx& cx, double x) {
 #define D3_MAXV 48
 #define D3_MAXQ 56
 #define D3_MAXGEOM 24
-#define D3_MAXPAIR 88
+#define D3_MAXPAIR 96
 #define D3_MAXHE 192       // in-block lower-triangle entries (Sorting-6: 45 + 6 x 21 = 171)
 
 #define LANES(i, n) for (int i = cx.lane; i < (n); i += G)

@@ -163,7 +163,10 @@ def load_robot(ref, with_rod=True):
 
 
 def load_surroundings(ref):
-    """Only the two geoms tabletop objects can touch: ``table_plane`` and ``support_body``."""
+    """The static geoms free objects can touch: ``table_plane`` and ``support_body`` of the frame, and the
+    ground plane of ``base.xml`` (body ``ground`` at z = -0.94), which catches what is pushed off the table.  The plane is
+    compiled as the top face of a big static axis-aligned slab: for the convex objects that land on it that is the same
+    contact set, and it takes the slab fast path of the box narrow phase (one comparison per tick while nothing is near)."""
     xml = os.path.join(ref, D3IL, "models/mujoco/surroundings/lab_surrounding.xml")
     root = ET.parse(xml).getroot()
     bodies = M.parse_bodies(root.find("worldbody"), {})
@@ -174,6 +177,14 @@ def load_surroundings(ref):
             p, R = info["static"][b.name]
             g = b.geoms[0]
             out.append(dict(name=b.name, type=g.type, size=g.size, pos=p + R @ g.pos, R=R @ M.quat2mat(g.quat), params=g.params))
+    base = ET.parse(os.path.join(ref, D3IL, "models/mj/surroundings/base.xml")).getroot()
+    for b in M.parse_bodies(base.find("worldbody"), {}):
+        if b.name == "ground":
+            g = b.geoms[0]
+            assert g.type == "plane" and np.allclose(M.quat2mat(M.quat_normalize(b.quat)), np.eye(3)) and np.allclose(M.quat2mat(g.quat), np.eye(3))
+            half = np.array([4.0, 4.0, 0.5])
+            out.append(dict(name="ground", type="box", size=half, pos=np.asarray(b.pos, float) + g.pos - np.array([0.0, 0.0, half[2]]), R=np.eye(3), params=g.params))
+    assert out[-1]["name"] == "ground"
     return out
 
 
@@ -423,6 +434,8 @@ def compile_task(task, ref):
                     continue
             if min(a["link"], b["link"]) == -1 and max(a["link"], b["link"]) < 9 and 4 in (a["tag"], b["tag"]):
                 continue                                        # hand vs table: unreachable before the fingers are 4 cm deep
+            if "ground" in (a["name"], b["name"]) and max(a["link"], b["link"]) < 9:
+                continue                                        # the ground, 0.92 m below the table top, is out of the arm's reach: free objects only
             pa, pb = a["params"], b["params"]
             if not ((pa["contype"] & pb["conaffinity"]) or (pb["contype"] & pa["conaffinity"])):
                 continue

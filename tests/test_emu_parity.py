@@ -22,6 +22,8 @@ def test_core_logic_equals_oracle_fp64(pushing_contexts, ctx_id):
     o.reset(ctx); e.reset(ctx)
     assert np.abs(o.get_state()[:-4] - e.get_state()[:-4]).max() < 1e-6     # contexts pass through float32 on the kernel side; last 4 words = kernel-side cost counters
     saw_coupled = False
+    import json, os
+    rod = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "d3il_b200", "scenes", "pushing.json")))["geoms"].index("rod:geom_rb0")
     for a in scripted_push_actions(ctx, o.robot_state(), n_steps=100):
         e.set_state(o.get_state())
         ro, re = o.step(a), e.step(a)
@@ -30,7 +32,7 @@ def test_core_logic_equals_oracle_fp64(pushing_contexts, ctx_id):
         assert np.abs(so[nq:nq + nv] - se[nq:nq + nv]).max() < 1e-7 * (1 + np.abs(so[nq:nq + nv]).max())
         assert np.allclose(ro[0], re[0], atol=1e-6) and ro[2] == re[2] and np.allclose(ro[3], re[3], atol=1e-6)
         con = o.probe("contacts").reshape(-1, 12)
-        saw_coupled |= bool(((con[:, 8] == 2) & (con[:, 11] >= 0)).any())     # rod geom (index 2) in an active contact
+        saw_coupled |= bool(((con[:, 8] == rod) & (con[:, 11] >= 0)).any())     # rod geom in an active contact
     assert saw_coupled
 
 

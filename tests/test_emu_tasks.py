@@ -169,3 +169,45 @@ def test_stacking_mode_and_success_bookkeeping():
     assert info[3] == 2 and info[1] in (2 + 4 * 1, 2 + 4 * 3) and info[0] == 1     # second arrival appended; all three within 6 cm, z gaps > 3 cm
     obs, r, done, info = o.step(hold)
     assert done and info[3] == 3
+
+
+def test_box_off_the_table_lands_on_the_ground():
+    """A box released beyond the table's front edge (x = 0.89) falls 0.92 m and comes to rest on the ground plane of base.xml
+    (body `ground`, z = -0.94), carrying its weight there - it used to fall for ever.  Oracle, fp64 and fp32 host builds of the
+    kernel core agree along the fall, through the impact and at rest."""
+    blob, sc = load_scene("pushing")
+    nq, nv = sc.header["nq"], sc.header["nv"]
+    ctx = task_contexts("pushing")[0]
+    o = OracleEnv(blob, sc.header)
+    o.reset(ctx)
+    s = o.get_state()
+    s[9:12] = [1.0, 0.05, 0.0]                    # box 1, 11 cm past the edge
+    s[nq:nq + nv] = 0
+    o.set_state(s)
+    emus = {p: EmuEnv(blob, sc.header, p) for p in ("f64", "f32")}
+    for e in emus.values():
+        e.reset(ctx); e.set_state(s)
+    zs = []
+    for k in range(18):                              # 18 x 50 ticks = 0.9 s: free fall takes 0.43 s
+        o.substep(50)
+        so = o.get_state()
+        zs.append(so[11])
+        for p, e in emus.items():
+            e.substep(50)
+            se = e.get_state()
+            if p == "f64":
+                assert np.abs(so[:nq] - se[:nq]).max() < 1e-7 and np.abs(so[nq:nq + nv] - se[nq:nq + nv]).max() < 1e-5, (k, p)
+            e.set_state(so)                          # teacher-forced every 50 ticks
+            if p == "f32":
+                assert np.abs(so[9:12] - se[9:12]).max() < 2e-4 + 1e-3 * (k in (8, 9)), (k, np.abs(so[9:12] - se[9:12]).max())      # the impact (0.43 s) is the ill-conditioned window
+    assert zs[3] < -0.15 and min(zs) > -0.98          # it fell; the impact at 4.2 m/s sinks ~3 cm into the default-solref (20 ms) contact and comes back
+    so = o.get_state()
+    assert abs(so[11] - (-0.94 + 0.03)) < 5e-4 and np.abs(so[nq + 9:nq + 15]).max() < 2e-3       # at rest on the ground
+    con = o.probe("contacts").reshape(-1, 12)
+    import json, os
+    names = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "d3il_b200", "scenes", "pushing.json")))["geoms"]
+    on_ground = con[(con[:, 8] == names.index("ground")) & (con[:, 11] >= 0)]
+    assert len(on_ground) == 4
+    f = o.probe("efc_force")
+    fn = sum(f[int(r)] for r in on_ground[:, 11])
+    assert abs(fn - 0.05 * 9.81) < 0.02 * 0.05 * 9.81                               # the four corner contacts carry m g

@@ -149,3 +149,37 @@ def test_stacking_reset_and_grasp_teacher_forced():
     assert errs[:, 0].max() * 5e-6 <= 1e-3 or errs[:, 0].max() <= 200      # worst qpos excursion <= 1 mm-equivalent (see test_gpu_protocol.py for the fp64 cross-check)
     assert outs[-1][0][2] > 0.14                      # the oracle lifted the red box
     env.close()
+
+
+def test_boxes_off_the_table_land_on_the_ground():
+    """Boxes released past the table's edges (front x = 0.89, sides y = +-0.98) fall onto the ground plane (z = -0.94) and
+    rest there like the oracle's; the env next to them in the CTA, whose boxes stay on the table, is bit-identical to a run
+    without falling neighbours; no fault bits."""
+    blob, sc = load_scene("pushing")
+    nq, nv = sc.header["nq"], sc.header["nv"]
+    ctx = task_contexts("pushing")[0]
+    spots = [(1.0, 0.05, 0.0), (1.05, -0.4, 0.02), (0.5, 1.1, 0.0), (0.3, -1.12, 0.05)]
+    n = 2 * len(spots)
+    env = _benv("pushing", n)
+    env.reset(torch.tensor(np.repeat(ctx[None], n, 0), dtype=torch.float32, device="cuda"))
+    o = OracleEnv(blob, sc.header)
+    o.reset(ctx)
+    s0 = o.get_state()
+    refs = []
+    for i, sp in enumerate(spots):
+        s = s0.copy(); s[9:12] = sp; s[nq:nq + nv] = 0
+        env.set_state(2 * i, s)                       # odd envs keep the untouched reset state
+        o.set_state(s); o.substep(900); refs.append(o.get_state())
+    env.substep(900)
+    for i, sp in enumerate(spots):
+        got, ref = env.get_state(2 * i), refs[i]
+        assert abs(ref[11] - (-0.94 + 0.03)) < 5e-4, ref[9:12]                           # the oracle's box rests on the ground
+        assert np.abs(got[9:12] - ref[9:12]).max() < 2e-3 and abs(got[11] - ref[11]) < 2e-4, (sp, got[9:12], ref[9:12])
+        assert np.abs(got[nq + 9:nq + 15]).max() < 5e-3                                   # at rest
+    o.set_state(s0); o.substep(900)
+    quiet = o.get_state()
+    for i in range(len(spots)):
+        got = env.get_state(2 * i + 1)
+        assert np.array_equal(got, env.get_state(1))                                      # neighbours of falling boxes: bit-identical to each other
+        assert np.allclose(got[:nq], quiet[:nq], rtol=1e-4, atol=5e-6)
+    env.close()

@@ -48,7 +48,7 @@ def test_scene_tables_known_answers():
     init_qpos = sc.ctrl[B.C_INIT_QPOS:B.C_INIT_QPOS + 7]
     assert np.allclose(init_qpos, [-0.356409, 0.429445, -0.135011, -2.054652, 0.093578, 2.480718, 0.232507], atol=2e-6)
     # free boxes: invweight0 = (1/m, 1/I) for a 0.05 kg, 6 cm cube
-    box = sc.geom[3]
+    box = sc.geom[4]      # table_plane, support_body, ground, rod, then the boxes
     assert abs(box[13] - 20.0) < 1e-9 and abs(box[14] - 1.0 / (0.05 / 3 * 2 * 0.03 ** 2)) < 1e-3
     # mixed box-table contact parameters (App. B.5): solref[0] = (0.002 + 0.02)/2, friction 1
     pair = sc.pair[0]
