@@ -82,7 +82,7 @@ def _cpu_worker(args):
     for k in range(n_steps):
         if joint_space:
             des[:7] += rng.uniform(-0.01, 0.01, 7)
-            des[7] = 0.08 if (k // 50) % 2 == 0 else 0.0
+            des[7] = 0.08 if ((k + 37 * wid) // 50) % 2 == 0 else 0.0       # same per-env toggling phase as the GPU arm
         else:
             des[:n_act] = np.clip(des[:n_act] + rng.uniform(-0.01, 0.01, n_act), lo, hi)
         _, _, done, _ = env.step(des)
@@ -138,7 +138,7 @@ def run_reference(args):
 # Facts taken from committed ncu captures (profiles/): dram__bytes_read.sum + dram__bytes_write.sum and smsp__inst_executed.sum of
 # ONE k_env launch at the workload's default size.  None / absent = not captured for that workload.
 NCU_FACTS = {
-    "pushing": {"dram_bytes": 29.790720e6 + 17.644032e6, "warp_inst_per_env_step": 2204490177 / 4096,
+    "pushing": {"dram_bytes": 29.613568e6 + 28.661248e6, "warp_inst_per_env_step": 1973641028 / 4096,
                 "source": "profiles/r2_summary.md (k_env<3>, 4096 envs, one launch, ncu --set full: cold caches, so the 12 MB set-point hand-off that stays in L2 in steady state is counted as DRAM traffic)"},
 }
 
@@ -228,6 +228,7 @@ class EnvStream:
         self.bit_counts = torch.zeros(5, dtype=torch.long, device=dev)        # ... per status bit 1, 2, 4, 8, 16
         self.bits = torch.tensor([1, 2, 4, 8, 16], dtype=torch.int32, device=dev)
         self.step_no = torch.zeros((), dtype=torch.long, device=dev)
+        self.grip_phase = (torch.arange(n, device=dev) * 37) % 100      # every env toggles its gripper every 50 steps, on its own phase: the cost of a step does not depend on when it is timed
         self.last_obs = env.obs.clone()
         self.ep_len = env.max_steps_per_episode
 
@@ -240,7 +241,7 @@ class EnvStream:
             delta = torch.rand(self.n, n_act, device=self.dev) * 0.02 - 0.01
         if self.joint_space:
             self.des[:, :7] += delta
-            self.des[:, 7] = torch.where((self.step_no // 50) % 2 == 0, 0.08, 0.0)
+            self.des[:, 7] = torch.where(((self.step_no + self.grip_phase) // 50) % 2 == 0, 0.08, 0.0)
         else:
             self.des[:, :n_act] = torch.minimum(torch.maximum(self.des[:, :n_act] + delta, self.lo), self.hi)
         if events:
@@ -460,7 +461,7 @@ def run_gpu(args):
                 delta = hb["rng"].uniform(-0.01, 0.01, (s.n, na)).astype(np.float32)
             if s.joint_space:
                 hb["des"][:, :7] += delta
-                hb["des"][:, 7] = 0.08 if (k // 50) % 2 == 0 else 0.0
+                hb["des"][:, 7] = np.where(((k + (np.arange(s.n) * 37) % 100) // 50) % 2 == 0, 0.08, 0.0)
             else:
                 hb["des"][:, :na] = np.clip(hb["des"][:, :na] + delta, hb["lo"], hb["hi"])
             hb["obs"], rew_h, done_h, info_h = s.env.step_host(hb["des"])
