@@ -377,15 +377,23 @@ def run_gpu(args):
         s.fault_steps.zero_(); s.bit_counts.zero_(); s.episodes.zero_()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local) if rank == 0 and not os.environ.get("D3IL_NO_CLOCKS") else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    seg = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)] if os.environ.get("D3IL_SEG") and graph is None else None
     ev0.record()
     for k in range(K):
-        run_step()
+        if seg:
+            step_all(events=seg[k])
+        else:
+            run_step()
     ev1.record()
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
+    if seg:      # debug: per-step device time of env.step and of the gaps between consecutive env.step calls
+        st = np.array([a.elapsed_time(b) for a, b in seg]); gap = np.array([seg[k][1].elapsed_time(seg[k + 1][0]) for k in range(K - 1)])
+        print("[seg] env.step ms by step: " + " ".join(f"{x:.1f}" for x in st), file=sys.stderr)
+        print(f"[seg] env.step mean {st.mean():.3f} p50 {np.median(st):.3f} p90 {np.percentile(st, 90):.3f} max {st.max():.3f}; between steps mean {gap.mean():.3f} p50 {np.median(gap):.3f} p90 {np.percentile(gap, 90):.3f} max {gap.max():.3f}", file=sys.stderr)
     n_faults = int(sum(int(s.fault_steps.item()) for s in streams))
     bit_counts = sum(s.bit_counts for s in streams).tolist()
     episodes = int(sum(int(s.episodes.item()) for s in streams))
@@ -407,6 +415,21 @@ def run_gpu(args):
         metrics[s.task] = dict(device_metrics(s.task, rows, len(s.ctxs) if s.ctxs is not None else 1), rows=list(rows.shape))
     clocks = sampler.stop() if sampler else None
     value = world * n * K / (ms * 1e-3)
+    if os.environ.get("D3IL_TL"):      # timing build only (profiles/build_variant.sh ... -DD3IL_PHASE_TIMING): where the LAST timed step spent its time
+        import ctypes as C
+        from d3il_b200 import lib as _lib
+        buf = (C.c_ulonglong * (4 * 4096))(); _lib.lib().d3il_debug_timeline(buf)
+        a = np.array(buf, dtype=np.uint64).reshape(4096, 4).astype(np.int64)
+        t0 = a[a[:, 3] == 3][0, 0]
+        for kind, name in ((3, "k_sched"), (1, "k_ik"), (2, "k_env"), (5, "k_reset (CTAs without work)"), (4, "k_reset (CTAs that reset an env)")):
+            r = a[a[:, 3] == kind]
+            if len(r):
+                print(f"[timeline] {name:34s} blocks {len(r):4d} start {(r[:, 0].min() - t0) / 1e6:7.3f} .. {(r[:, 0].max() - t0) / 1e6:7.3f} ms, end {(r[:, 1].min() - t0) / 1e6:7.3f} .. {(r[:, 1].max() - t0) / 1e6:7.3f} ms", file=sys.stderr)
+        rows = np.nonzero(a[:, 3] == 2)[0]
+        late = rows[np.argsort(-a[rows, 1])[:8]]
+        print("[timeline] last k_env CTAs to end (block, start ms, end ms): " + ", ".join(f"({b}, {(a[b, 0] - t0) / 1e6:.2f}, {(a[b, 1] - t0) / 1e6:.2f})" for b in late), file=sys.stderr)
+        prev = a[a[:, 3] == 6]
+        print(f"[timeline] mean period {ms / K:.3f} ms per step; the previous step's k_sched started {(t0 - prev[0, 0]) / 1e6 if len(prev) else float('nan'):.3f} ms before this one's", file=sys.stderr)
 
     # ---- device time of the step's own kernels (k_sched + k_ik + k_env of every task): CUDA events recorded on the launching
     # stream around env.step, NOT synchronised step by step (the overlap of k_ik and k_env stays intact), read back at the end
@@ -415,6 +438,8 @@ def run_gpu(args):
         step_all(events=e)
     torch.cuda.synchronize()
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    if os.environ.get("D3IL_SEG"):
+        print("[seg] kernel_ms pass by step: " + " ".join(f"{a.elapsed_time(b):.1f}" for a, b in evs), file=sys.stderr)
     alg_bytes_launch = sum(_alg_bytes_per_env_step(s.env) * s.n for s in streams)
     peaks = {}
     try:

@@ -18,7 +18,7 @@
 
 #include "../../include/d3il.h"
 #ifndef IK_THREADS
-#define IK_THREADS 128
+#define IK_THREADS 256             // see d3il_dev.h
 #endif
 #define IK_JSTRIDE IK_THREADS      // k_ik keeps the Jacobians of its block in shared memory as J[k][thread]
 #include "d3il_dev.h"
@@ -49,7 +49,7 @@ static __device__ unsigned long long g_tl[4 * 4096];     // debug timeline of th
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 __device__ __forceinline__ unsigned smid() { unsigned r; asm volatile("mov.u32 %0, %smid;" : "=r"(r)); return r; }
 #define TL_BEGIN(kind, idx) unsigned long long tl_t0 = gtime(); const int tl_i = (idx)
-#define TL_END(kind) do { if (threadIdx.x == 0 && tl_i < 4096) { g_tl[4 * tl_i] = tl_t0; g_tl[4 * tl_i + 1] = gtime(); g_tl[4 * tl_i + 2] = smid(); g_tl[4 * tl_i + 3] = kind; } } while (0)
+#define TL_END(kind) do { if (threadIdx.x == 0 && tl_i < 4096) { if (kind == 3) { g_tl[4 * 4094] = g_tl[4 * tl_i]; g_tl[4 * 4094 + 1] = g_tl[4 * tl_i + 1]; g_tl[4 * 4094 + 3] = 6; } g_tl[4 * tl_i] = tl_t0; g_tl[4 * tl_i + 1] = gtime(); g_tl[4 * tl_i + 2] = smid(); g_tl[4 * tl_i + 3] = kind; } } while (0)
 #else
 #define TL_BEGIN(kind, idx) ((void)0)
 #define TL_END(kind) ((void)0)

@@ -130,6 +130,7 @@ template <bool CS> DEVFN void cta_sync(const Cx& cx) {
 #if defined(D3IL_PHASE_TIMING) && !defined(D3IL_EMU)
 // debug build only: per-phase cycle counts of the group that owns env 0 (profiles/phase_timing.py)
 static __device__ unsigned long long g_phase_cycles[40];
+static __device__ int g_ph_on[64];            // D3IL_PHASE_DENSE: per free-running CTA, the current tick has >= 2 tree-coupling contacts
 static __device__ unsigned g_cta_stat[4 * 4096];            // per CTA: [0] CTA-uniform Newton passes, [1] of which warp 0's env was coupled, [2] Newton steps of warp 0's env, [3] line-search evaluations of warp 0
 static __device__ unsigned long long g_iter_hist[40];      // [0..15] Newton steps per tick, [16..31] same for ticks with a coupling contact, [32] sum ncon / [33] count of ticks with >= 8 steps
 #endif
@@ -139,10 +140,16 @@ static __device__ unsigned long long g_iter_hist[40];      // [0..15] Newton ste
 #ifndef D3IL_PHASE_BLOCK
 #define D3IL_PHASE_BLOCK 0      // which CTA of the cost-sorted grid is sampled (e.g. -DD3IL_PHASE_BLOCK="(gridDim.x/2)" = median cost)
 #endif
-#ifdef D3IL_PHASE_LO                                          // a range of CTAs (first warp of each): -DD3IL_PHASE_LO=3 -DD3IL_PHASE_HI=8
+#ifdef D3IL_PHASE_DENSE                                       // first warp of the free-running CTAs, only in ticks with >= 2 tree-coupling contacts
+#define D3IL_PHASE_COND (blockIdx.x < 16 && g_ph_on[blockIdx.x])
+#define PHASE_MARK_DENSE(on) do { if (threadIdx.x == 0 && blockIdx.x < 16) g_ph_on[blockIdx.x] = (on); } while (0)
+#elif defined(D3IL_PHASE_LO)                                          // a range of CTAs (first warp of each): -DD3IL_PHASE_LO=3 -DD3IL_PHASE_HI=8
 #define D3IL_PHASE_COND (blockIdx.x >= D3IL_PHASE_LO && blockIdx.x < D3IL_PHASE_HI)
 #else
 #define D3IL_PHASE_COND (blockIdx.x == D3IL_PHASE_BLOCK)
+#endif
+#ifndef PHASE_MARK_DENSE
+#define PHASE_MARK_DENSE(on) ((void)0)
 #endif
 __device__ __forceinline__ bool blockIdx_is0() { return D3IL_PHASE_COND && threadIdx.x == 0; }
 __device__ __forceinline__ void count_iter() { atomicAdd(&g_phase_cycles[20], 1ull); }
@@ -152,6 +159,7 @@ __device__ __forceinline__ void count_stat(int k, int v) { atomicAdd(&g_phase_cy
 #else
 #define PHASE_T0() ((void)0)
 #define PHASE2_T0() ((void)0)
+#define PHASE_MARK_DENSE(on) ((void)0)
 #define PHASE(k) ((void)0)
 #define PHASE2(k) ((void)0)
 DEVFN bool blockIdx_is0() { return false; }
@@ -1353,58 +1361,62 @@ DEVNI void chol_blocks_solve_multi(const Cx& cx, const Model& m, const real* A, 
 #endif
 
 #ifndef D3IL_EMU
-// Dense n x n system (n <= MB <= G: one group, row i in lane i) factored AND solved on registers: the tree-coupled Newton
-// Hessian of a scene with nv <= 32.  A: strict lower triangle in shared memory (leading dimension n), diag[] its diagonal,
-// x: right-hand side in, solution out.  The factor's rows are written back to A so that each lane can read its column
-// for the backward sweep.  Returns 1 (all lanes) if a pivot was not positive.
-template <int G, int MB>
-DEVNI int chol_dense_reg_solve(const Cx& cx, real* A, int n, const real* diag, real* x) {
+// Dense n x n system (n <= G: one group, row i in lane i) factored AND solved with ROLLED loops on the shared-memory
+// matrix: the tree-coupled Newton Hessian of a scene with nv <= 32 (two or more contacts join kinematic trees: a box pushed
+// into another box).  Only a handful of envs are in that state at a time and each runs alone in a free-running CTA, where
+// instruction fetch is not shared with other warps: 20 KB of unrolled register code cost 34 k cycles per call (one L2 fetch per
+// 128-byte line), this loop nest is a few hundred bytes.  A: strict lower triangle (leading dimension n, odd strides are
+// bank-conflict free), diag[] its diagonal, x: right-hand side in, solution out.  Returns 1 (all lanes) on a non-positive pivot.
+template <int G>
+DEVNI int chol_dense_rolled_solve(const Cx& cx, const Model& m, real* A, int n, const real* diag, real* x) {
   const int i = cx.lane;
-  const bool mine_row = i < n;
-  real a[MB], myinv = 1;
-#pragma unroll
-  for (int j = 0; j < MB; j++) a[j] = (mine_row && j < i) ? A[i * n + j] : ((mine_row && j == i) ? diag[i] : (real)0);
+  const bool mine = i < n;
+  real* row = A + (mine ? i : 0) * n;
+  real dii = mine ? diag[i] : (real)1, myinv = 1;
   int bad = 0;
-#pragma unroll
-  for (int k = 0; k < MB; k++) {
-    if (k < n) {
-      if (i == k) { real p = a[k]; if (!(p > 0)) { bad = 1; p = 1; } myinv = 1 / sqrt(p); }
-      const real inv = __shfl_sync(cx.mask, myinv, k, G);
-      if (i > k) a[k] *= inv;
-      const real colk = a[k];
-#pragma unroll
-      for (int j = k + 1; j < MB; j++) {
-        if (j < n) {
-          const real ljk = __shfl_sync(cx.mask, colk, j, G);
-          if (i >= j) a[j] -= colk * ljk;
-        }
+  if (n <= 24) {
+    // entry-parallel trailing update (the unranking table covers triangles up to 24 rows): per column one round to scale it and
+    // ceil(m (m + 1) / 64) rounds over the m x m trailing triangle, instead of m dependent steps per lane
+    real* d = const_cast<real*>(diag);
+    for (int k = 0; k < n; k++) {
+      real p = d[k];
+      if (!(p > 0)) { bad = 1; p = 1; }
+      const real inv = 1 / sqrt(p);
+      if (i == k) myinv = inv;
+      if (mine && i > k) row[k] *= inv;
+      gsync<G>(cx);
+      const int mm = n - k - 1;
+      for (int e = i; e < mm * (mm + 1) / 2; e += G) {
+        const int r = k + 1 + m.tri_i[e], c = k + 1 + m.tri_j[e];
+        const real v = A[r * n + k] * A[c * n + k];
+        if (r == c) d[r] -= v; else A[r * n + c] -= v;
       }
+      gsync<G>(cx);
     }
-  }
-  if (mine_row) {
-#pragma unroll
-    for (int j = 0; j < MB; j++) if (j < i) A[i * n + j] = a[j];
+  } else
+  for (int k = 0; k < n; k++) {
+    if (i == k) { real p = dii; if (!(p > 0)) { bad = 1; p = 1; } myinv = 1 / sqrt(p); }
+    const real inv = __shfl_sync(cx.mask, myinv, k, G);
+    real colk = 0;
+    if (mine && i > k) { colk = row[k] * inv; row[k] = colk; }
+    // trailing update, column by column: lane i owns row i (entries j <= i), L_jk comes from lane j
+    for (int j = k + 1; j < n; j++) {
+      const real ljk = __shfl_sync(cx.mask, colk, j, G);
+      if (mine && i > j) row[j] -= colk * ljk;
+      else if (i == j) dii -= colk * ljk;
+    }
   }
   gsync<G>(cx);
-  real lcol[MB];
-#pragma unroll
-  for (int j = 0; j < MB; j++) lcol[j] = (mine_row && j > i && j < n) ? A[j * n + i] : (real)0;
-  real xr = mine_row ? x[i] : (real)0;
-#pragma unroll
-  for (int k = 0; k < MB; k++) {
-    if (k < n) {
-      const real xk = __shfl_sync(cx.mask, xr * myinv, k, G);
-      if (i == k) xr = xk; else if (i > k) xr -= a[k] * xk;
-    }
+  real xr = mine ? x[i] : (real)0;
+  for (int k = 0; k < n; k++) {
+    const real xk = __shfl_sync(cx.mask, xr * myinv, k, G);
+    if (i == k) xr = xk; else if (mine && i > k) xr -= row[k] * xk;
   }
-#pragma unroll
-  for (int k = MB - 1; k >= 0; k--) {
-    if (k < n) {
-      const real xk = __shfl_sync(cx.mask, xr * myinv, k, G);
-      if (i == k) xr = xk; else if (i < k) xr -= lcol[k] * xk;
-    }
+  for (int k = n - 1; k >= 0; k--) {
+    const real xk = __shfl_sync(cx.mask, xr * myinv, k, G);
+    if (i == k) xr = xk; else if (i < k) xr -= A[k * n + i] * xk;
   }
-  if (mine_row) x[i] = xr;
+  if (mine) x[i] = xr;
   gsync<G>(cx);
   return gori<G>(cx, bad);
 }
@@ -1857,8 +1869,7 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
     // NOT leave the loop on its own: the iteration is CTA-uniform (cta_any above is a barrier every warp of the CTA has to
     // reach), so it turns `done` and idles through the remaining passes like a converged env.
 #ifndef D3IL_EMU
-    if (nv <= 24) { hfail = chol_dense_reg_solve<G, 24>(cx, w + L.H, nv, w + L.hpiv, w + L.pvec); PHASE(10); }
-    else if (nv <= G) { hfail = chol_dense_reg_solve<G, (G < 32 ? G : 32)>(cx, w + L.H, nv, w + L.hpiv, w + L.pvec); PHASE(10); }
+    if (nv <= G) { hfail = chol_dense_rolled_solve<G>(cx, m, w + L.H, nv, w + L.hpiv, w + L.pvec); PHASE(10); }
     else
 #endif
     {
@@ -1978,6 +1989,7 @@ DEVFN void physics_tick(const Cx& cx, const Model& m, const Lay& L, real* w, con
   int cplc = -1;
   const int ncpl = count_coupling<G>(cx, m, L, w, ncon, &cplc);
   PHASE(3);
+  PHASE_MARK_DENSE(ncpl > 1);
 #ifdef D3IL_PHASE_TIMING
   if (cx.lane == 0) { count_stat(21, coupled); count_stat(22, ncon); count_stat(23, 1); count_stat(19, ne); }
   if (blockIdx_is0()) { count_stat(17, ncon); count_stat(14, ncpl == 1); count_stat(13, ncpl > 1); count_stat(7, ne); }

@@ -18,9 +18,11 @@
 #endif
 #define CTA_THREADS (G_LANES * ENVS_PER_CTA)
 #ifndef IK_THREADS
-#define IK_THREADS 128   // 32 k_ik blocks at 4096 envs.  Registers are allocated to a CTA in units of 4 warps, so a k_ik block always costs
-                         // >= 4 x 32 x 255 registers: an SM that hosts one takes only ONE k_env CTA (2 x 8-warp units) until it leaves.
-                         // Four warps per block keep the number of such SMs at 32 (one-warp blocks: 128 SMs, measured -14 %).
+#define IK_THREADS 256   // 16 k_ik blocks at 4096 envs.  Registers are allocated to a CTA in units of 4 warps, so ANY k_ik block costs
+                         // >= 4 x 32 x 255 registers and evicts a k_env CTA from its SM until it leaves; an 8-warp block takes the
+                         // whole register file of its SM (no k_env CTA beside it), a 4-warp block leaves room for one.  Either way 264 of
+                         // the 296 k_env slots are free at t = 0; measured: 64 threads -10 %, 128 baseline, 256 +4 % (fewer SMs whose
+                         // k_env CTA shares issue slots and L1 with the fp64 IK warps).
 #endif
 #define IK_FLAG_ENVS 32  // release flags are per k_ik WARP: a warp whose envs need the slow clipped-spectrum path does not hold back the others
 struct DevIk {            // SoA views, [field][n]

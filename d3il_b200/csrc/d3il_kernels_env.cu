@@ -28,7 +28,10 @@ __device__ __forceinline__ void stage_model(Model* sm, const Model* gm, int byte
 // env step can start on the SMs that still run the IK reference.  (__launch_bounds__ with a min-blocks hint would let
 // ptxas go to 146 and override -maxrregcount: at 125 registers the second CTA waited for k_ik to leave.)
 template <int MD>
-__global__ void __maxnreg__(120)
+#ifndef D3IL_ENV_REGS
+#define D3IL_ENV_REGS 120
+#endif
+__global__ void __maxnreg__(D3IL_ENV_REGS)
 k_env(DevCtx c, int n_free, int n_ticks, int gym, const float* __restrict__ action, float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ done, float* __restrict__ info) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   TL_BEGIN(2, blockIdx.x);
@@ -83,8 +86,9 @@ k_reset(DevCtx c, const float* __restrict__ ctx, const uint8_t* __restrict__ mas
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x / G_LANES;
   const int e = blockIdx.x * c.epc + warp;
+  TL_BEGIN(4, 1024 + blockIdx.x);
   // masked reset (auto-reset of the ~1 % of envs that finished): CTAs without a masked env leave before staging the tables
-  if (!__syncthreads_or(e < c.n && (!mask || mask[e]))) return;
+  if (!__syncthreads_or(e < c.n && (!mask || mask[e]))) { TL_END(5); return; }
   Model* sm = (Model*)smem_raw;
   stage_model(sm, c.model, c.model_bytes);
   const Model& m = *sm;
@@ -107,6 +111,7 @@ k_reset(DevCtx c, const float* __restrict__ ctx, const uint8_t* __restrict__ mas
     c.ik.valid[e] = 0;
     if (obs) task_obs(m, L, w, obs + (size_t)e * m.obs_dim);
   }
+  TL_END(4);
 }
 
 __global__ void k_robot_state(DevCtx c, float* __restrict__ tcp) {

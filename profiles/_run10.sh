@@ -1,0 +1,6 @@
+mkdir -p gpurun_out/r2e
+run() { python profiles/run_variant.py bench.py --steps 80 --warmup 10 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$1', 'ms_per_step', round(d['ms_per_step'],3), 'kernel_ms', round(d['roofline']['kernel_ms'],3), 'value', round(d['value']))"; }
+( D3IL_VARIANT=r120 run r120
+D3IL_VARIANT=r128 run r128
+D3IL_VARIANT=r120 run r120b
+D3IL_VARIANT=r128 run r128b ) | tee gpurun_out/r2e/sweep_regs.log
