@@ -138,7 +138,7 @@ def run_reference(args):
 # Facts taken from committed ncu captures (profiles/): dram__bytes_read.sum + dram__bytes_write.sum and smsp__inst_executed.sum of
 # ONE k_env launch at the workload's default size.  None / absent = not captured for that workload.
 NCU_FACTS = {
-    "pushing": {"dram_bytes": 29.613568e6 + 28.661248e6, "warp_inst_per_env_step": 1973641028 / 4096,
+    "pushing": {"dram_bytes": 27.778816e6 + 19.564032e6, "warp_inst_per_env_step": 1970974251 / 4096,
                 "source": "profiles/r2_summary.md (k_env<3>, 4096 envs, one launch, ncu --set full: cold caches, so the 12 MB set-point hand-off that stays in L2 in steady state is counted as DRAM traffic)"},
 }
 
