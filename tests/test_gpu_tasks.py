@@ -183,3 +183,44 @@ def test_boxes_off_the_table_land_on_the_ground():
         assert np.array_equal(got, env.get_state(1))                                      # neighbours of falling boxes: bit-identical to each other
         assert np.allclose(got[:nq], quiet[:nq], rtol=1e-4, atol=5e-6)
     env.close()
+
+
+def test_box_pushed_into_box_teacher_forced():
+    """Several contacts that couple kinematic trees at once (rod -> box 1 -> box 2: one rod contact + the box-box face contacts):
+    the Newton Hessian is dense over arm + both boxes and takes the dense rolled Cholesky of the kernel, not the block /
+    Woodbury route.  Teacher-forced env steps against the oracle along the push."""
+    import json, os
+    blob, sc = load_scene("pushing")
+    nq, nv = sc.header["nq"], sc.header["nv"]
+    ctx = np.array([[0.5, -0.12, 0.0, 1.0, 0.0, 0.0, 0.0], [0.5, -0.055, 0.0, 1.0, 0.0, 0.0, 0.0]])
+    o = OracleEnv(blob, sc.header)
+    o.reset(ctx)
+    from tests.util import scripted_push_actions
+    acts = scripted_push_actions(ctx, o.robot_state(), n_steps=90, approach_steps=45)
+    names = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "d3il_b200", "scenes", "pushing.json")))["geoms"]
+    rod, b1, b2 = names.index("rod:geom_rb0"), names.index("push_box:geom"), names.index("push_box2:geom")
+    states, multi = [o.get_state()], []
+    for a in acts:
+        o.step(a)
+        states.append(o.get_state())
+        con = o.probe("contacts").reshape(-1, 12)
+        act = con[con[:, 11] >= 0]
+        pairs = {(int(r[8]), int(r[9])) for r in act}
+        multi.append(int(any(rod in p for p in pairs)) + sum(1 for r in act if {int(r[8]), int(r[9])} == {b1, b2}))
+    multi = np.array(multi)
+    assert (multi >= 2).sum() >= 10, multi                       # the script really produces multi-coupling ticks
+    n = len(acts)
+    env = _benv("pushing", n)
+    env.reset(torch.tensor(np.repeat(ctx[None], n, 0), dtype=torch.float32, device="cuda"))
+    for i in range(n):
+        env.set_state(i, states[i])
+    obs, rew, done, info = (t.cpu().numpy() for t in env.step(torch.tensor(acts, dtype=torch.float32, device="cuda")))
+    assert (info[:, -1] == 0).all()
+    errs = np.array([step_errors(states[i + 1], env.get_state(i), nq, nv) for i in range(n)])
+    sel = multi >= 2
+    print(f"[box into box] multi-coupling steps {sel.sum()}: inside the tolerance box {(errs[sel].max(axis=1) <= 1.0).mean():.3f}, median {np.median(errs[sel].max(axis=1)):.3f}; all steps inside {(errs.max(axis=1) <= 1.0).mean():.3f}")
+    assert (errs.max(axis=1) <= 1.0).mean() >= 0.85 and (errs[sel].max(axis=1) <= 1.0).mean() >= 0.8, errs
+    for i in range(n):
+        got = env.get_state(i)
+        assert np.abs(got[:nq] - states[i + 1][:nq]).max() <= 1e-3, (i, np.abs(got[:nq] - states[i + 1][:nq]).max())
+    env.close()
