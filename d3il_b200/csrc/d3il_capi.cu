@@ -212,15 +212,17 @@ static int create_impl(d3il_env* h, const void* blob, size_t nbytes, int n_envs,
   // envs per CTA: ENVS_PER_CTA (two CTAs per SM for the small scenes), fewer when the per-env workspace is large (Sorting-4/6)
   const size_t model_bytes = d3il_model_bytes(h->m), env_bytes = (size_t)d.ws_stride * sizeof(float);
   d.model_bytes = (int)model_bytes;
-  // pick the CTA size that keeps the most env warps resident per SM: at most two CTAs per SM (registers), each CTA's shared
-  // memory + 1 KB of system reserve out of the SM's 228 KB
+  // pick the CTA size that keeps the most env warps resident per SM.  Shared memory: each CTA's bytes + 1 KB of system reserve
+  // out of the SM's 228 KB.  Registers: 120 per thread, allocated in units of 4 warps -> two CTAs per SM only up to 8 warps
+  // each, one CTA up to 16.  (Pushing: 2 x 8; Sorting-4: 1 x 9; Inserting: 1 x 10; Stacking: 1 x 8; Sorting-6: 1 x 6.)
   d.epc = 1;
   { int best = 0;
-    for (int e = ENVS_PER_CTA; e >= 1; e--) {
+    for (int e = ENVS_PER_CTA_MAX; e >= 1; e--) {
       const size_t bytes = model_bytes + (size_t)e * env_bytes;
       if (bytes > 227 * 1024) continue;
-      const int ctas = (int)((228 * 1024) / (bytes + 1024)) >= 2 ? 2 : 1, warps = ctas * e;
-      if (warps > best) { best = warps; d.epc = e; }
+      const int by_smem = (int)((228 * 1024) / (bytes + 1024)), by_regs = ((e + 3) / 4) * 4 <= 8 ? 2 : 1;
+      const int ctas = by_smem >= 2 && by_regs >= 2 ? 2 : 1, score = ctas * e * (ctas == 2 ? 23 : 20);      // two smaller lock-step groups beat one big one unless it holds >= 15 % more envs
+      if (score > best) { best = score; d.epc = e; }
     } }
   h->smem_bytes = model_bytes + (size_t)d.epc * env_bytes;
 #ifdef D3IL_DIAG

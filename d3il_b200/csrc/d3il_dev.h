@@ -16,7 +16,10 @@
 #define ENVS_PER_CTA 8     // 2 CTAs/SM x 8 envs (Pushing: 12.25 KB of shared memory per env with the packed mass matrix): 4096 envs = 512 CTAs
                            // on 296 slots - 264 start at once beside the 32 k_ik blocks, the other 248 form one second wave
 #endif
-#define CTA_THREADS (G_LANES * ENVS_PER_CTA)
+#ifndef ENVS_PER_CTA_MAX
+#define ENVS_PER_CTA_MAX 12  // scenes whose workspace allows only one CTA per SM may put up to 12 envs into it (d3il_create picks)
+#endif
+#define CTA_THREADS (G_LANES * ENVS_PER_CTA_MAX)
 #ifndef IK_THREADS
 #define IK_THREADS 256   // 16 k_ik blocks at 4096 envs.  Registers are allocated to a CTA in units of 4 warps, so ANY k_ik block costs
                          // >= 4 x 32 x 255 registers and evicts a k_env CTA from its SM until it leaves; an 8-warp block takes the
