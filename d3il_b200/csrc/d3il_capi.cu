@@ -184,7 +184,7 @@ static int create_impl(d3il_env* h, const void* blob, size_t nbytes, int n_envs,
   h->device = device; h->n = n_envs; h->launches = 0; h->max_ticks = h->m.n_substeps > 64 ? h->m.n_substeps : 64;
   CK(cudaSetDevice(device));
   DevCtx& d = h->d;
-  d.lay = h->L; d.n = n_envs; d.row = (h->L.n_state + 31) & ~31; d.ws_stride = (h->L.total + 31) & ~31;
+  d.lay = h->L; d.n = n_envs; d.row = (h->L.n_state + 31) & ~31; d.ws_stride = (h->L.total + 3) & ~3;       // 16-byte alignment is all the workspace needs (warps never share an instruction across workspaces)
   d.tol = 1e-6f; d.max_iter = 32;      // the cap is not reached on the benchmark workloads (status bit 8 reports it if it is; 12 was hit by 0.4 % of the Pushing env steps, 24 by a few closing-gripper steps of Stacking); the loop is CTA-uniform with early exit, so a high cap costs nothing
   Model* dm = nullptr;
   CK(cudaMalloc(&dm, sizeof(Model)));
@@ -214,7 +214,7 @@ static int create_impl(d3il_env* h, const void* blob, size_t nbytes, int n_envs,
   d.model_bytes = (int)model_bytes;
   // pick the CTA size that keeps the most env warps resident per SM.  Shared memory: each CTA's bytes + 1 KB of system reserve
   // out of the SM's 228 KB.  Registers: 120 per thread, allocated in units of 4 warps -> two CTAs per SM only up to 8 warps
-  // each, one CTA up to 16.  (Pushing: 2 x 8; Sorting-4: 1 x 9; Inserting: 1 x 10; Stacking: 1 x 8; Sorting-6: 1 x 6.)
+  // each, one CTA up to 16.  (Pushing: 2 x 8; Sorting-2: 2 x 6; Sorting-4, Stacking, Inserting: 1 x 8; Sorting-6: 1 x 6.)
   d.epc = 1;
   { int best = 0;
     for (int e = ENVS_PER_CTA_MAX; e >= 1; e--) {

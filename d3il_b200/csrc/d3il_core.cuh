@@ -249,7 +249,7 @@ struct Lay {
                                                     // tcp: pos3+quat4 ; misc: 16 scalars (see ST_*)
   int n_state;
   // scratch
-  int xpos, xmat, S, I10, Ic, vel, cj, frc, F, M, mdinv, mpiv, H, hdinv, hpiv, bias, qfrc_smooth, qacc_smooth, qacc, qfrc_c, grad, pvec, Ma, tmpv;
+  int xpos, xmat, S, I10, Ic, vel, cj, frc, F, M, mdinv, H, hdinv, hpiv, bias, qfrc_smooth, qacc_smooth, qacc, qfrc_c, grad, pvec, Ma, tmpv;
   int wood;           // Woodbury scratch: maxdim dof vectors (view 2)
   int rowc;           // per constraint row >= nlimit: contact id | (row within the contact << 6), bytes
   int blist;          // per kinematic-tree block: [count, contact ids ...] bytes, stride maxcon + 1 (bit 7: the contact couples two blocks)
@@ -269,7 +269,7 @@ static inline void d3il_layout(const Model& m, Lay& L) {
   L.qpos = take(m.nq); L.qlo = take(D3_NROB); L.qvel = take(m.nv); L.warm = take(m.nv); L.bias_prev = take(D3_NROB); L.tcp = take(7); L.misc = take(ST_NMISC); L.extra = take(m.nextra);
   L.n_state = o;
   // live for the whole tick
-  L.M = take(m.m_size); L.mdinv = take(m.nv); L.mpiv = take(m.nv);
+  L.M = take(m.m_size); L.mdinv = take(m.nv);
   L.bias = take(m.nv); L.qfrc_smooth = take(m.nv); L.qacc_smooth = take(m.nv); L.qacc = take(m.nv); L.qfrc_c = take(m.nv);
   L.act = take(D3_NROB); L.jt = take(3 * D3_NARM); L.con = take(D3_CON_W * m.maxcon);
   L.J = take(m.maxrow * D3_JW); L.aref = take(m.maxrow); L.D = take(m.maxrow); L.hd = take(2 * D3_NROB); L.econ = take(2 * D3_NROB); L.blist = take((m.nblk * (m.maxcon + 1) + 3) / 4); L.rowc = take((m.maxrow + 3) / 4);
@@ -1218,7 +1218,7 @@ DEVFN real row_bcast(const Cx& cx, const real* v, int src_row) {
 }
 // upper = true : A is the PACKED mass matrix (Model::m_row) and the input block rows are read from its UPPER triangle
 //                (A[j][i], j < i), as CRBA leaves it;
-// upper = false: A is a dense n x n buffer, rows from the lower triangle (the assembled Hessian).  diag[] holds the diagonal, diag_add (nullable) is added to it.
+// upper = false: A is a dense n x n buffer, rows from the lower triangle (the assembled Hessian).  diag[] holds the diagonal (nullptr: A's own), diag_add (nullable) is added to it.
 template <int G, int NS> DEVFN int chol_reg_core(const Cx& cx, real (*a)[D3_MAXB], const int* bs, const int* be, const int* rr, real* myinv);
 template <int G, int NS>
 DEVNI int chol_blocks_reg_slots(const Cx& cx, const Model& m, real* A, int n, bool upper, const real* diag, const real* diag_add, real* dinv) {
@@ -1234,7 +1234,7 @@ DEVNI int chol_blocks_reg_slots(const Cx& cx, const Model& m, real* A, int n, bo
     for (int j = 0; j < D3_MAXB; j++) {
       real v = 0;
       if (j < rr[sl]) v = upper ? A[base[sl] + j * st[sl] + rr[sl]] : A[base[sl] + rr[sl] * st[sl] + j];
-      else if (j == rr[sl]) v = diag[i] + (diag_add ? diag_add[i] : (real)0);
+      else if (j == rr[sl]) v = (diag ? diag[i] : A[base[sl] + rr[sl] * st[sl] + rr[sl]]) + (diag_add ? diag_add[i] : (real)0);      // diag == nullptr: the buffer's own diagonal (the factor only writes the strict lower triangle)
       a[sl][j] = v;
     }
     myinv[sl] = 1;
@@ -2003,11 +2003,10 @@ DEVFN void physics_tick(const Cx& cx, const Model& m, const Lay& L, real* w, con
     real act = d < D3_NROB ? w[L.act + d] : (real)0;
     real f = passive - w[L.bias + d] + act;
     w[L.qfrc_smooth + d] = f; w[L.qacc_smooth + d] = f;
-    w[L.mpiv + d] = w[L.M + m.m_row[d] + d];
   }
   gsync<G>(cx);
   // chol(M): rows come from the upper triangle (where CRBA wrote M), the factor goes to the strict lower triangle
-  if (chol_blocks_reg<G>(cx, m, w + L.M, nv, true, w + L.mpiv, nullptr, w + L.mdinv)) { LANES(z, 1) w[L.misc + ST_STATUS] = (real)(((int)w[L.misc + ST_STATUS]) | D3_STATUS_M_NOT_PD); }
+  if (chol_blocks_reg<G>(cx, m, w + L.M, nv, true, nullptr, nullptr, w + L.mdinv)) { LANES(z, 1) w[L.misc + ST_STATUS] = (real)(((int)w[L.misc + ST_STATUS]) | D3_STATUS_M_NOT_PD); }
   chol_blocks_solve<G>(cx, m, w + L.M, nv, true, w + L.mdinv, w + L.qacc_smooth);
   PHASE(4);
   cta_sync<CS>(cx);
@@ -2028,11 +2027,11 @@ DEVFN void physics_tick(const Cx& cx, const Model& m, const Lay& L, real* w, con
   LANES(d, nv) { w[L.warm + d] = w[L.qacc + d]; w[L.tmpv + d] = w[L.qfrc_smooth + d] + w[L.qfrc_c + d]; }
   LANES(k, D3_NROB) w[L.bias_prev + k] = w[L.bias + k];
   // --- mj_Euler with implicit joint damping: (M + h B) qacc* = qfrc_smooth + qfrc_constraint.  M (upper triangle) and its
-  //     diagonal (mpiv) are still intact: the blocks of M + h B are simply factored again in registers (the only damped dofs
+  //     diagonal are still intact: the blocks of M + h B are simply factored again in registers (the only damped dofs
   //     are the two fingers, but a register factorisation of every block costs less than a special case for the corner).
   LANES(d, nv) { int li = m.d_link[d]; w[L.hpiv + d] = m.l_jtype[li] == 2 ? (real)0 : h * (real)m.link[D3_LINK_W * li + 25]; }
   gsync<G>(cx);
-  chol_blocks_reg<G>(cx, m, w + L.M, nv, true, w + L.mpiv, w + L.hpiv, w + L.mdinv);
+  chol_blocks_reg<G>(cx, m, w + L.M, nv, true, nullptr, w + L.hpiv, w + L.mdinv);
   chol_blocks_solve<G>(cx, m, w + L.M, nv, true, w + L.mdinv, w + L.tmpv);
   LANES(d, nv) w[L.qvel + d] += h * w[L.tmpv + d];
   gsync<G>(cx);

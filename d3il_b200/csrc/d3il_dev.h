@@ -17,7 +17,8 @@
                            // on 296 slots - 264 start at once beside the 32 k_ik blocks, the other 248 form one second wave
 #endif
 #ifndef ENVS_PER_CTA_MAX
-#define ENVS_PER_CTA_MAX 12  // scenes whose workspace allows only one CTA per SM may put up to 12 envs into it (d3il_create picks)
+#define ENVS_PER_CTA_MAX 8   // larger lock-step groups lose more to their slowest env than the extra warp brings: Sorting-4 at 9 envs per CTA
+                            // (one CTA per SM either way) measured -10 % against 8
 #endif
 #define CTA_THREADS (G_LANES * ENVS_PER_CTA_MAX)
 #ifndef IK_THREADS
