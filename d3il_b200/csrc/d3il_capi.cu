@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(IK_THREADS) k_ik(DevCtx c, const float* __rest
   double* sA = sJ + 42 * IK_THREADS;
   double* coop_all = sA + 27 * IK_THREADS;
   double* coop = coop_all + 160 * (threadIdx.x / 32);
-  Cx cx; cx.lane = threadIdx.x & 31; cx.mask = 0xffffffffu; cx.cta_threads = IK_THREADS;
+  Cx cx; cx.lane = threadIdx.x & 31; cx.mask = 0xffffffffu; cx.cta_threads = IK_THREADS; cx.bar_id = 1;
   for (int i = threadIdx.x; i < D3_CTRL_W; i += blockDim.x) sctrl[i] = (double)c.model->ctrl[i];
   __syncthreads();
   const int e_raw = blockIdx.x * blockDim.x + threadIdx.x;
@@ -212,18 +212,25 @@ static int create_impl(d3il_env* h, const void* blob, size_t nbytes, int n_envs,
   // envs per CTA: ENVS_PER_CTA (two CTAs per SM for the small scenes), fewer when the per-env workspace is large (Sorting-4/6)
   const size_t model_bytes = d3il_model_bytes(h->m), env_bytes = (size_t)d.ws_stride * sizeof(float);
   d.model_bytes = (int)model_bytes;
-  // pick the CTA size that keeps the most env warps resident per SM.  Shared memory: each CTA's bytes + 1 KB of system reserve
-  // out of the SM's 228 KB.  Registers: 120 per thread, allocated in units of 4 warps -> two CTAs per SM only up to 8 warps
-  // each, one CTA up to 16.  (Pushing: 2 x 8; Sorting-2: 2 x 6; Sorting-4, Stacking, Inserting: 1 x 8; Sorting-6: 1 x 6.)
+  // CTA size.  Measured on Pushing (4096 envs): one lock-step CTA of 16 envs per SM 676 k env-steps/s, two CTAs of 8 620 k, lock-step
+  // sub-groups of 4 inside them 532 k, one CTA of 12 564 k; Sorting-4: 8 envs 253 k, 9 envs 227 k.  So: (1) as many resident env
+  // warps per SM as shared memory (CTA bytes + 1 KB reserve out of 228 KB) and registers (120 per thread, allocated in units of 4
+  // warps: two CTAs only up to 8 warps each) allow, counted in whole multiples of 4 - a 9th warp only unbalances the four
+  // schedulers; (2) among equals ONE big lock-step group, because every instruction fetch then serves all its warps (the kernel
+  // is 490 KB of mostly straight-line code); (3) then the smaller group (less waiting for the slowest env).
   d.epc = 1;
-  { int best = 0;
+  { int best = -1;
     for (int e = ENVS_PER_CTA_MAX; e >= 1; e--) {
       const size_t bytes = model_bytes + (size_t)e * env_bytes;
       if (bytes > 227 * 1024) continue;
       const int by_smem = (int)((228 * 1024) / (bytes + 1024)), by_regs = ((e + 3) / 4) * 4 <= 8 ? 2 : 1;
-      const int ctas = by_smem >= 2 && by_regs >= 2 ? 2 : 1, score = ctas * e * (ctas == 2 ? 23 : 20);      // two smaller lock-step groups beat one big one unless it holds >= 15 % more envs
+      const int ctas = by_smem >= 2 && by_regs >= 2 ? 2 : 1, warps = ctas * e;
+      const int score = (warps >= 8 ? (warps & ~3) : warps) * 64 + (ctas == 1 ? 32 : 0) + (ENVS_PER_CTA_MAX - e);
       if (score > best) { best = score; d.epc = e; }
     } }
+#ifdef D3IL_DIAG
+  if (const char* ev = getenv("D3IL_EPC")) { const int e = atoi(ev); if (e >= 1 && e <= ENVS_PER_CTA_MAX && model_bytes + (size_t)e * env_bytes <= 227 * 1024) d.epc = e; }
+#endif
   h->smem_bytes = model_bytes + (size_t)d.epc * env_bytes;
 #ifdef D3IL_DIAG
   if (const char* ev = getenv("D3IL_SMEM_PAD_KB")) {      // diagnosis build only: pad the request so fewer CTAs share an SM
@@ -239,7 +246,7 @@ static int create_impl(d3il_env* h, const void* blob, size_t nbytes, int n_envs,
   // the head of each step's cost-sorted order runs in free-running CTAs (see k_sched / k_env): fpc envs each (one warp per SM
   // sub-partition), enough of them for the ~1.5 % of envs that are in a contact-rich phase at any time, rounded so that
   // the lock-step CTAs behind them are all full
-  d.fpc = 4; h->n_free = 0;
+  d.fpc = 4; h->n_free = 0; d.lsg = 0;
   if (G_LANES == 32 && n_envs >= 512) {
     int want = (n_envs / 64 + d.fpc - 1) / d.fpc;                        // ~1.5 % of the envs
     if (want > 64) want = 64;
@@ -247,6 +254,7 @@ static int create_impl(d3il_env* h, const void* blob, size_t nbytes, int n_envs,
     for (int k = 0; k < d.epc; k++) if ((n_envs - (want + k) * d.fpc) % d.epc == 0) { h->n_free = want + k; break; }
   }
 #ifdef D3IL_DIAG
+  if (const char* ev = getenv("D3IL_LSG")) d.lsg = atoi(ev);
   if (const char* ev = getenv("D3IL_FPC")) { d.fpc = atoi(ev); if (d.fpc < 1 || d.fpc > d.epc) d.fpc = 1; }
   if (const char* ev = getenv("D3IL_N_FREE")) { h->n_free = atoi(ev); if (h->n_free < 0 || h->n_free * d.fpc > n_envs / 2 || G_LANES != 32) h->n_free = 0; }
 #endif

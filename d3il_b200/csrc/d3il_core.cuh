@@ -31,7 +31,7 @@ typedef float tab_t;    // model tables are fp32 in shared memory
 #define DEVNI static inline
 #define HDFN static inline
 #define D3_RESTRICT
-struct Cx { int lane; unsigned mask; int cta_threads; };   // cta_threads: threads of this CTA that take part in the phase barriers
+struct Cx { int lane; unsigned mask; int cta_threads; int bar_id; };   // cta_threads: threads of this CTA that take part in the phase barriers
 template <int G> DEVFN void gsync(const Cx&) {}
 template <int G> DEVFN real gsum(const Cx&, real x) { return x; }
 template <int G> DEVFN real gmaxr(const Cx&, real x) { return x; }
@@ -45,7 +45,7 @@ template <int G> DEVFN double gsumd(const Cx&, double x) { return x; }
 #define HDFN __host__ __device__ __forceinline__
 #define DEVNI static __device__ __noinline__       // big, multiply-instantiated routines: the kernel is instruction-fetch bound
 #define D3_RESTRICT __restrict__
-struct Cx { int lane; unsigned mask; int cta_threads; };   // cta_threads: threads of this CTA that take part in the phase barriers
+struct Cx { int lane; unsigned mask; int cta_threads; int bar_id; };   // cta_threads: threads of this CTA that take part in the phase barriers
 template <int G> DEVFN void gsync(const Cx& cx) { __syncwarp(cx.mask); }
 template <int G> DEVFN real gsum(const Cx& cx, real x) {
 #pragma unroll
@@ -114,7 +114,7 @@ template <bool CS> DEVFN int cta_any(const Cx& cx, int pred) {
 #if defined(__CUDA_ARCH__)
   if (CS && cx.cta_threads > 32) {        // a free-running CTA (cta_threads = one warp) votes alone: pred is group-uniform
     int out;
-    asm volatile("{ .reg .pred p, q; setp.ne.s32 p, %1, 0; bar.red.or.pred q, 1, %2, p; selp.s32 %0, 1, 0, q; }" : "=r"(out) : "r"(pred), "r"(cx.cta_threads) : "memory");
+    asm volatile("{ .reg .pred p, q; setp.ne.s32 p, %1, 0; bar.red.or.pred q, %3, %2, p; selp.s32 %0, 1, 0, q; }" : "=r"(out) : "r"(pred), "r"(cx.cta_threads), "r"(cx.bar_id) : "memory");
     return out;
   }
 #endif
@@ -123,7 +123,7 @@ template <bool CS> DEVFN int cta_any(const Cx& cx, int pred) {
 // Named barrier 1 over the participating threads only (CTAs that carry fewer envs than warps let the spare warps exit)
 template <bool CS> DEVFN void cta_sync(const Cx& cx) {
 #if defined(__CUDA_ARCH__)
-  if (CS) { if (cx.cta_threads > 32) asm volatile("bar.sync 1, %0;" :: "r"(cx.cta_threads) : "memory"); else __syncwarp(); }
+  if (CS) { if (cx.cta_threads > 32) asm volatile("bar.sync %1, %0;" :: "r"(cx.cta_threads), "r"(cx.bar_id) : "memory"); else __syncwarp(); }
 #endif
 }
 

@@ -13,12 +13,10 @@
 #define G_LANES 32          // lanes cooperating on one env (32 = one warp per env; 16 = two envs per warp)
 #endif
 #ifndef ENVS_PER_CTA
-#define ENVS_PER_CTA 8     // 2 CTAs/SM x 8 envs (Pushing: 12.25 KB of shared memory per env with the packed mass matrix): 4096 envs = 512 CTAs
-                           // on 296 slots - 264 start at once beside the 32 k_ik blocks, the other 248 form one second wave
+#define ENVS_PER_CTA 8     // historical default of the diagnostic builds; the product picks the size at d3il_create (ENVS_PER_CTA_MAX)
 #endif
 #ifndef ENVS_PER_CTA_MAX
-#define ENVS_PER_CTA_MAX 8   // larger lock-step groups lose more to their slowest env than the extra warp brings: Sorting-4 at 9 envs per CTA
-                            // (one CTA per SM either way) measured -10 % against 8
+#define ENVS_PER_CTA_MAX 16  // one lock-step CTA of 16 envs per SM where the workspace allows (d3il_create picks the size, see there)
 #endif
 #define CTA_THREADS (G_LANES * ENVS_PER_CTA_MAX)
 #ifndef IK_THREADS
@@ -41,6 +39,7 @@ struct DevCtx {
   float* state;           // [n][row]
   int row, n, ws_stride;
   int model_bytes;        // staged prefix of the Model (d3il_model_bytes), multiple of 128
+  int lsg;                // lock-step sub-group size inside a CTA (0 = the whole CTA)
   int fpc;                // envs per FREE-RUNNING CTA (the head of the cost-sorted order, see k_env)
   int epc;                // envs (warps) per CTA: ENVS_PER_CTA unless the scene's workspace needs more shared memory per env
   DevIk ik;

@@ -52,6 +52,11 @@ k_env(DevCtx c, int n_free, int n_ticks, int gym, const float* __restrict__ acti
   const int pos0 = freecta ? (int)blockIdx.x * c.fpc : n_free * c.fpc + ((int)blockIdx.x - n_free) * c.epc;
   if (warp >= cnt) return;
   cx.cta_threads = freecta ? G_LANES : cnt * G_LANES;          // cta_sync / cta_any are warp-local when this is one group
+  cx.bar_id = 1;
+  if (!freecta && c.lsg > 0 && c.lsg < cnt) {                  // lock-step SUB-groups of c.lsg envs, each on its own named barrier
+    const int sg = warp / c.lsg, first = sg * c.lsg, members = cnt - first < c.lsg ? cnt - first : c.lsg;
+    cx.bar_id = 1 + sg; cx.cta_threads = members * G_LANES;
+  }
   // Groups past the end of the batch shadow the last env (same inputs, same control flow, identical outputs) so that
   // every thread of the CTA reaches the phase barriers inside physics_tick.
   const int e_raw = pos0 + warp;                               // position in this step's cost-sorted order
@@ -96,7 +101,7 @@ k_reset(DevCtx c, const float* __restrict__ ctx, const uint8_t* __restrict__ mas
   Cx cx; cx.lane = threadIdx.x % G_LANES;
   cx.mask = G_LANES == 32 ? 0xffffffffu : (((1u << G_LANES) - 1u) << (((threadIdx.x & 31) / G_LANES) * G_LANES));
   if (e >= c.n) return;
-  cx.cta_threads = c.epc * G_LANES;
+  cx.cta_threads = c.epc * G_LANES; cx.bar_id = 1;
   if (mask && !mask[e]) return;
   float* w = (float*)(smem_raw + c.model_bytes) + (size_t)warp * c.ws_stride;
   env_reset<G_LANES>(cx, m, L, w, (ctx && m.ctx_dim > 0) ? ctx + (size_t)e * m.ctx_dim : nullptr, c.tol, c.max_iter);
