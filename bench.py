@@ -138,7 +138,7 @@ def run_reference(args):
 # Facts taken from committed ncu captures (profiles/): dram__bytes_read.sum + dram__bytes_write.sum and smsp__inst_executed.sum of
 # ONE k_env launch at the workload's default size.  None / absent = not captured for that workload.
 NCU_FACTS = {
-    "pushing": {"dram_bytes": 27.778816e6 + 19.564032e6, "warp_inst_per_env_step": 1970974251 / 4096,
+    "pushing": {"dram_bytes": 28.183040e6 + 21.610240e6, "warp_inst_per_env_step": 1992753372 / 4096,
                 "source": "profiles/r2_summary.md (k_env<3>, 4096 envs, one launch, ncu --set full: cold caches, so the 12 MB set-point hand-off that stays in L2 in steady state is counted as DRAM traffic)"},
 }
 
