@@ -244,7 +244,7 @@ def task_spec(task, ref):
         return dict(
             rod=True, n_substeps=35, max_steps={2: 500, 4: 700, 6: 1200}[k], init_tcp=[0.525, -0.3, 0.25], ctrl_kind=0,
             objects=objs, obs_dim=2 + 3 * k, act_dim=7, info_dim=4, spawn_z=0.05,
-            maxcon={2: 28, 4: 40, 6: 52}[k],     # 4 per resting box + piles pushed together / boxes against the bin walls (a scripted push of one box into its bin reaches 21; overflow raises status 2)
+            maxcon={2: 28, 4: 40, 6: 64}[k],     # 4 per resting box + piles pushed together / boxes against the bin walls (a scripted push of one box into its bin reaches 21 with two boxes; six boxes pushed into a pile reached 52 on the GPU; overflow raises status 2)
             # red target xy, blue target xy, red bin x range, blue bin x range, bin y range, num_boxes, bogus xy  (sorting.py:300-306,477-536)
             taskp=[0.4, 0.32, 0.625, 0.32, 0.3, 0.5, 0.525, 0.725, 0.22, 0.41, k, bogus[0], bogus[1]],
         )

@@ -221,9 +221,10 @@ def _iv_plan(task, ci):
     if task == "pushing":          # pushing.py:341-377: modes = visiting order of (box, target) pairs
         G1, G2 = np.array([0.42, 0.3]), np.array([0.63, 0.3])
         return [[(0, G1), (1, G2)], [(1, G2), (0, G1)], [(0, G2), (1, G1)], [(1, G1), (0, G2)]][ci % 4]
-    if task == "sorting_2":        # sorting.py: red box -> red bin (x 0.3..0.5), blue box -> blue bin (x 0.525..0.725), bins at y 0.22..0.41
+    if task.startswith("sorting"):   # sorting.py: red box -> red bin (x 0.3..0.5), blue box -> blue bin (x 0.525..0.725), bins at y 0.22..0.41
+        k = int(task.split("_")[1])   # observation order: k/2 red boxes, then k/2 blue ones
         R, B = np.array([0.4, 0.33]), np.array([0.625, 0.33])
-        return [[(0, R)], [(1, B)]][ci % 2]      # one box into its bin, then hold (getting behind the second box between the bin walls needs a planner)
+        return [[(0, R)], [(k // 2, B)]][ci % 2]      # one box into its bin, then hold (getting behind the next box between the bin walls needs a planner)
     if task == "aligning":
         return None
     raise ValueError(task)
@@ -239,7 +240,8 @@ def iv_policy_step(task, ci, obs, des, phase):
         return np.array([d2[0], d2[1], z]), phase
     plan = _iv_plan(task, ci)
     stride = 3
-    boxes = [obs[2 + stride * b:4 + stride * b].astype(np.float64) for b in range(2)]
+    nbox = int(task.split("_")[1]) if task.startswith("sorting") else 2
+    boxes = [obs[2 + stride * b:4 + stride * b].astype(np.float64) for b in range(nbox)]
     while phase < len(plan) and np.linalg.norm(boxes[plan[phase][0]] - plan[phase][1]) < 0.03:
         phase += 1
     if phase >= len(plan):
@@ -265,3 +267,18 @@ def iv_oracle_episode(args):
         if done:
             break
     return np.array(info), k + 1
+
+
+def iv_stacking_episode(ci):
+    """Scripted grasp-and-lift of the red box in Stacking context `ci` on the fp64 oracle (process-pool worker): the
+    open-loop joint-space script is a function of the context and the reset observation only.  Returns (actions, info row
+    after the last step, final red-box height)."""
+    blob, sc = load_scene("stacking")
+    ctx = task_contexts("stacking")[ci]
+    o = OracleEnv(blob, sc.header)
+    obs0 = o.reset(ctx)
+    acts = scripted_grasp_actions(sc, ctx, o.robot_state(), o.joint_state()[:7], obs0)
+    info = None
+    for a in acts:
+        _, _, _, info = o.step(a)
+    return acts, np.array(info), float(o.get_state()[9 + 2])
