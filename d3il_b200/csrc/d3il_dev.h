@@ -1,8 +1,8 @@
 // d3il_dev.h — declarations shared by the two CUDA translation units of libd3il.so:
 //   d3il_capi.cu        : C ABI, k_sched, k_ik (fp64 IK reference; compiled with the full register budget)
 //   d3il_kernels_env.cu : k_env<3|4>, k_reset, k_robot_state, k_joint_state, k_object_poses.  k_env is capped at 120
-//                         registers (__maxnreg__; -maxrregcount covers the rest of the unit): two 8-warp CTAs per SM, or one
-//                         beside a 4-warp k_ik block (see IK_THREADS below and DESIGN.md "IK placement")
+//                         registers (__maxnreg__; -maxrregcount covers the rest of the unit): 16 env warps per SM, as one lock-step CTA
+//                         of 16 or two of 8 (d3il_create picks per scene; see IK_THREADS below and DESIGN.md §2)
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>

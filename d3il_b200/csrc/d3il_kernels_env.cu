@@ -24,9 +24,8 @@ __device__ __forceinline__ void stage_model(Model* sm, const Model* gm, int byte
 // IK reference generator: one thread per env (a5/a6).  mode: 1 = take the set-point from `action` (env step),
 // 0 = keep the stored set-point (d3il_substep).  In joint-PD mode (after reset) the held set-point is replicated.
 // Env step: one warp per env.  gym = 1: GymEnvWrapper.step semantics around the ticks; gym = 0: bare ticks (substep).
-// 120 registers: two 7-warp k_env CTAs (2 x 224 x 120) and one k_ik warp (32 x 255) share the SM's 64 K registers, so the
-// env step can start on the SMs that still run the IK reference.  (__launch_bounds__ with a min-blocks hint would let
-// ptxas go to 146 and override -maxrregcount: at 125 registers the second CTA waited for k_ik to leave.)
+// 120 registers: 16 env warps (16 x 32 x 120 = 61 440 of the SM's 65 536 registers) as one lock-step CTA or two CTAs of 8.
+// (__launch_bounds__ with a min-blocks hint would let ptxas go to 146 and override -maxrregcount; 128 measured the same as 120.)
 template <int MD>
 #ifndef D3IL_ENV_REGS
 #define D3IL_ENV_REGS 120
