@@ -310,7 +310,11 @@ def run_gpu(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries the one JSON line only (NCCL_DEBUG=VERSION would print there)
+        # stdout carries the one JSON line only: NCCL prints its version banner to fd 1 when the communicator is created
+        # (NCCL_DEBUG=VERSION in the box environment), so fd 1 points at stderr until the line is printed
+        sys.stdout.flush()
+        run_gpu.saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
@@ -545,6 +549,9 @@ def run_gpu(args):
         config.update(tasks=[s.task for s in streams], envs_per_task=[s.n for s in streams])
     else:
         config.update(n_substeps=s0.env.n_substeps, episode_len=s0.ep_len)
+    if getattr(run_gpu, "saved_stdout", None) is not None:
+        sys.stdout.flush()
+        os.dup2(run_gpu.saved_stdout, 1)
     print(json.dumps({
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
