@@ -1942,6 +1942,10 @@ DEVFN int solve_constraints(const Cx& cx, const Model& m, const Lay& L, real* w,
   return nsteps;
 }
 
+#ifndef D3IL_SKIP_BARS
+#define D3IL_SKIP_BARS 0   // diagnostic: bit i drops the i-th phase barrier of the tick (placement sweeps)
+#endif
+#define PH_SYNC(i) do { if (!((D3IL_SKIP_BARS >> (i)) & 1)) cta_sync<CS>(cx); } while (0)
 // ------------------------------------------------------------------------------------------------ one physics tick
 // jt_q / jt_qlo / jt_qd: joint set-point for this tick (from the IK reference in Cartesian mode, or the held pose).
 template <int G, bool CS, int MD>
@@ -1976,14 +1980,14 @@ DEVFN void physics_tick(const Cx& cx, const Model& m, const Lay& L, real* w, con
     quat2mat(Rt, tq); mat_mul3(R, w + L.xmat + 54, Rt); mat2quat(w + L.tcp + 3, R);
   }
   PHASE(0);
-  cta_sync<CS>(cx);
+  PH_SYNC(0);
   LANES(e, m.nzp) { int a = m.zp_a[e], b = m.zp_b[e]; w[L.M + m.m_row[a] + b] = 0; w[L.M + m.m_row[b] + a] = 0; }     // in-block pairs CRBA never writes (the two fingers)
   dynamics<G>(cx, m, L, w);
   PHASE(1);
-  cta_sync<CS>(cx);
+  PH_SYNC(1);
   int ncon = collision<G>(cx, m, L, w);
   PHASE(2);
-  cta_sync<CS>(cx);
+  PH_SYNC(2);
   int nlimit = 0, coupled = 0;
   int ne = make_constraints<G, MD>(cx, m, L, w, ncon, &nlimit, &coupled);
   int cplc = -1;
@@ -1995,7 +1999,7 @@ DEVFN void physics_tick(const Cx& cx, const Model& m, const Lay& L, real* w, con
   if (blockIdx_is0()) { count_stat(17, ncon); count_stat(14, ncpl == 1); count_stat(13, ncpl > 1); count_stat(7, ne); }
 #define D3IL_ITER_HIST 1
 #endif
-  cta_sync<CS>(cx);
+  PH_SYNC(3);
   // --- smooth dynamics: qacc_smooth = M^-1 (passive - bias + actuation); M is block diagonal over the trees
   LANES(d, nv) {
     int li = m.d_link[d];
@@ -2009,7 +2013,7 @@ DEVFN void physics_tick(const Cx& cx, const Model& m, const Lay& L, real* w, con
   if (chol_blocks_reg<G>(cx, m, w + L.M, nv, true, nullptr, nullptr, w + L.mdinv)) { LANES(z, 1) w[L.misc + ST_STATUS] = (real)(((int)w[L.misc + ST_STATUS]) | D3_STATUS_M_NOT_PD); }
   chol_blocks_solve<G>(cx, m, w + L.M, nv, true, w + L.mdinv, w + L.qacc_smooth);
   PHASE(4);
-  cta_sync<CS>(cx);
+  PH_SYNC(4);
   int iters = solve_constraints<G, CS, MD>(cx, m, L, w, ne, nlimit, ncon, ncpl, cplc, tol, max_iter);
 #if defined(D3IL_ITER_HIST) && defined(__CUDA_ARCH__)
   if (cx.lane == 0) {
@@ -2023,7 +2027,7 @@ DEVFN void physics_tick(const Cx& cx, const Model& m, const Lay& L, real* w, con
     if ((real)ncon > w[L.misc + ST_COST_NCON]) w[L.misc + ST_COST_NCON] = (real)ncon;
   }
   PHASE(5);
-  cta_sync<CS>(cx);
+  PH_SYNC(5);
   LANES(d, nv) { w[L.warm + d] = w[L.qacc + d]; w[L.tmpv + d] = w[L.qfrc_smooth + d] + w[L.qfrc_c + d]; }
   LANES(k, D3_NROB) w[L.bias_prev + k] = w[L.bias + k];
   // --- mj_Euler with implicit joint damping: (M + h B) qacc* = qfrc_smooth + qfrc_constraint.  M (upper triangle) and its
@@ -2057,5 +2061,5 @@ DEVFN void physics_tick(const Cx& cx, const Model& m, const Lay& L, real* w, con
   }
   gsync<G>(cx);
   PHASE(6);
-  cta_sync<CS>(cx);
+  PH_SYNC(6);
 }
